@@ -1,0 +1,300 @@
+"""ctypes binding of libdmlmc_sm100.so (C ABI: include/dmlmc.h).
+
+PyTorch is used for device memory, streams and (in stoch_trace) torch.distributed only;
+all arithmetic of the hot path happens in the hand-written sm_100a kernels behind the C ABI.
+There is NO fallback: if the shared library is missing or no CUDA device is present the
+calls raise.
+"""
+import ctypes
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libdmlmc_sm100.so")
+
+C128, C64 = 0, 1
+
+_lib = None
+
+_SIGS = {
+    "dmlmc_abi_version": (ctypes.c_int, []),
+    "dmlmc_last_error": (ctypes.c_char_p, []),
+    "dmlmc_hier_create": (ctypes.c_int, [ctypes.c_int, ctypes.c_void_p, ctypes.c_int, ctypes.POINTER(ctypes.c_void_p)]),
+    "dmlmc_hier_destroy": (ctypes.c_int, [ctypes.c_void_p]),
+    "dmlmc_set_stencil": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_void_p,
+                                         ctypes.c_double, ctypes.c_double]),
+    "dmlmc_set_bsr": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int,
+                                     ctypes.c_void_p, ctypes.c_void_p]),
+    "dmlmc_set_transfer": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int,
+                                          ctypes.c_int, ctypes.c_void_p]),
+    "dmlmc_set_coarsest_inverse": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p]),
+    "dmlmc_set_smoother": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_void_p]),
+    "dmlmc_set_perm": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_void_p,
+                                      ctypes.c_void_p]),
+    "dmlmc_set_deflation": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_void_p]),
+    "dmlmc_spmm": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int]),
+    "dmlmc_restrict": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int]),
+    "dmlmc_prolong_add": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int]),
+    "dmlmc_coarsest_apply": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int]),
+    "dmlmc_smooth": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int]),
+    "dmlmc_vcycle": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int]),
+    "dmlmc_dotc": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_void_p]),
+    "dmlmc_deflate": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p, ctypes.c_int]),
+    "dmlmc_probe_expand": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_void_p]),
+    "dmlmc_apply_perm": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int]),
+    "dmlmc_workspace_bytes": (ctypes.c_size_t, [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_int]),
+    "dmlmc_set_workspace": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t]),
+    "dmlmc_set_inner_precision": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int]),
+    "dmlmc_fgmres": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int,
+                                    ctypes.c_double, ctypes.c_int, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p]),
+    "dmlmc_level_sample": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_void_p,
+                                          ctypes.c_int, ctypes.c_double, ctypes.c_int, ctypes.c_int, ctypes.c_void_p,
+                                          ctypes.c_void_p]),
+    "dmlmc_level_sample_host": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_void_p,
+                                               ctypes.c_int, ctypes.c_double, ctypes.c_int, ctypes.c_int, ctypes.c_void_p,
+                                               ctypes.c_void_p]),
+    "dmlmc_launch_count": (ctypes.c_longlong, [ctypes.c_void_p]),
+}
+
+EXPORTED_SYMBOLS = tuple(_SIGS.keys())
+
+
+def load():
+    """Load libdmlmc_sm100.so (built in-tree by __graft_entry__.build()).  Raises if absent."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.isfile(LIB_PATH):
+        raise RuntimeError(
+            "libdmlmc_sm100.so not found at %s -- build it with `python -c 'import __graft_entry__ as g; g.build()'`; "
+            "this package has no CPU fallback" % LIB_PATH)
+    lib = ctypes.CDLL(LIB_PATH)
+    for name, (res, args) in _SIGS.items():
+        fn = getattr(lib, name)          # AttributeError if the ABI is incomplete
+        fn.restype = res
+        fn.argtypes = args
+    if lib.dmlmc_abi_version() != 1:
+        raise RuntimeError("libdmlmc_sm100.so ABI version mismatch")
+    _lib = lib
+    return lib
+
+
+class DmlmcError(Exception):
+    pass
+
+
+def _check(rc):
+    if rc != 0:
+        msg = load().dmlmc_last_error()
+        raise DmlmcError("libdmlmc_sm100 error %d: %s" % (rc, msg.decode() if msg else "?"))
+
+
+def _host_c128(a):
+    a = np.ascontiguousarray(a, dtype=np.complex128)
+    return a, a.ctypes.data_as(ctypes.c_void_p)
+
+
+def _host_i32(a):
+    a = np.ascontiguousarray(a, dtype=np.int32)
+    return a, a.ctypes.data_as(ctypes.c_void_p)
+
+
+class Hierarchy:
+    """Device-resident multigrid hierarchy + batched solver (one per GPU / stream)."""
+
+    def __init__(self, n_levels, device=None):
+        import torch
+        if not torch.cuda.is_available():
+            raise RuntimeError("deflatedmlmc_schwinger_b200 needs a CUDA device (B200, sm_100a); there is no CPU fallback")
+        self.torch = torch
+        self.lib = load()
+        self.device = torch.device("cuda", torch.cuda.current_device() if device is None else device)
+        torch.cuda.set_device(self.device)
+        self.stream = torch.cuda.current_stream(self.device)
+        self.n_levels = n_levels
+        h = ctypes.c_void_p()
+        _check(self.lib.dmlmc_hier_create(self.device.index, ctypes.c_void_p(self.stream.cuda_stream), n_levels,
+                                          ctypes.byref(h)))
+        self.h = h
+        self.sizes = [0] * n_levels
+        self._ws = None
+        self._ws_key = None
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.dmlmc_hier_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ---- setup ---------------------------------------------------------------------
+    def set_stencil(self, level, links, diag):
+        links, p = _host_c128(links)
+        _, LX, LT = links.shape
+        _check(self.lib.dmlmc_set_stencil(self.h, level, LX, LT, p, float(np.real(diag)), float(np.imag(diag))))
+        self.sizes[level] = 2 * LX * LT
+
+    def set_bsr(self, level, n, bs, colidx, vals):
+        colidx, pc = _host_i32(colidx)
+        vals, pv = _host_c128(vals)
+        _check(self.lib.dmlmc_set_bsr(self.h, level, n, bs, colidx.shape[1], pc, pv))
+        self.sizes[level] = n
+
+    def set_transfer(self, level, n_f, aggr_size, dofi, nvec, pvals):
+        pvals, p = _host_c128(pvals)
+        assert pvals.shape == (n_f, nvec)
+        _check(self.lib.dmlmc_set_transfer(self.h, level, n_f, aggr_size, dofi, nvec, p))
+
+    def set_coarsest_inverse(self, minv):
+        minv, p = _host_c128(minv)
+        _check(self.lib.dmlmc_set_coarsest_inverse(self.h, minv.shape[0], p))
+        self.sizes[self.n_levels - 1] = minv.shape[0]
+
+    def set_smoother(self, level, inv_roots):
+        inv_roots, p = _host_c128(inv_roots)
+        _check(self.lib.dmlmc_set_smoother(self.h, level, inv_roots.shape[0], p))
+
+    def set_perm(self, level, shift, cols=None, vals=None):
+        if cols is None:
+            _check(self.lib.dmlmc_set_perm(self.h, level, int(shift), 0, None, None))
+        else:
+            cols, pc = _host_i32(cols)
+            vals, pv = _host_c128(vals)
+            _check(self.lib.dmlmc_set_perm(self.h, level, int(shift), cols.shape[1], pc, pv))
+
+    def set_deflation(self, level, V):
+        if V is None:
+            _check(self.lib.dmlmc_set_deflation(self.h, level, 0, None))
+        else:
+            V, p = _host_c128(V)
+            _check(self.lib.dmlmc_set_deflation(self.h, level, V.shape[1], p))
+
+    def set_inner_precision(self, prec):
+        _check(self.lib.dmlmc_set_inner_precision(self.h, prec))
+
+    # ---- helpers -------------------------------------------------------------------
+    def _dtype(self, prec):
+        return self.torch.complex128 if prec == C128 else self.torch.complex64
+
+    def _prec(self, t):
+        if t.dtype == self.torch.complex128:
+            return C128
+        if t.dtype == self.torch.complex64:
+            return C64
+        raise TypeError("expected a complex64/complex128 CUDA tensor")
+
+    def _chk(self, t, n=None):
+        assert t.is_cuda and t.is_contiguous() and t.dim() == 2, "expected a contiguous CUDA tensor [n, k]"
+        if n is not None:
+            assert t.shape[0] == n, (t.shape, n)
+        return ctypes.c_void_p(t.data_ptr())
+
+    def empty(self, n, k, prec=C128):
+        return self.torch.empty((n, k), dtype=self._dtype(prec), device=self.device)
+
+    def ensure_workspace(self, level, k, restart):
+        key = (level, k, restart)
+        need = self.lib.dmlmc_workspace_bytes(self.h, level, k, restart)
+        if self._ws is None or self._ws.numel() < need:
+            self._ws = None
+            self._ws = self.torch.empty(need, dtype=self.torch.uint8, device=self.device)
+        if self._ws_key != key:
+            _check(self.lib.dmlmc_set_workspace(self.h, ctypes.c_void_p(self._ws.data_ptr()), self._ws.numel()))
+            self._ws_key = key
+
+    # ---- operators -------------------------------------------------------------------
+    def spmm(self, level, X, Y=None):
+        Y = self.torch.empty_like(X) if Y is None else Y
+        _check(self.lib.dmlmc_spmm(self.h, level, self._prec(X), self._chk(X, self.sizes[level]), self._chk(Y), X.shape[1]))
+        return Y
+
+    def restrict(self, level, Xf):
+        Xc = self.empty(self.sizes[level + 1], Xf.shape[1], self._prec(Xf))
+        _check(self.lib.dmlmc_restrict(self.h, level, self._prec(Xf), self._chk(Xf, self.sizes[level]), self._chk(Xc), Xf.shape[1]))
+        return Xc
+
+    def prolong_add(self, level, Xc, Xf):
+        _check(self.lib.dmlmc_prolong_add(self.h, level, self._prec(Xc), self._chk(Xc, self.sizes[level + 1]),
+                                          self._chk(Xf, self.sizes[level]), Xc.shape[1]))
+        return Xf
+
+    def coarsest_apply(self, B):
+        X = self.torch.empty_like(B)
+        _check(self.lib.dmlmc_coarsest_apply(self.h, self._prec(B), self._chk(B, self.sizes[-1]), self._chk(X), B.shape[1]))
+        return X
+
+    def smooth(self, level, R):
+        self.ensure_workspace(level, R.shape[1], 1)
+        E = self.torch.empty_like(R)
+        _check(self.lib.dmlmc_smooth(self.h, level, self._prec(R), self._chk(R, self.sizes[level]), self._chk(E), R.shape[1]))
+        return E
+
+    def vcycle(self, level, B):
+        self.ensure_workspace(level, B.shape[1], 1)
+        X = self.torch.empty_like(B)
+        _check(self.lib.dmlmc_vcycle(self.h, level, self._prec(B), self._chk(B, self.sizes[level]), self._chk(X), B.shape[1]))
+        return X
+
+    def dotc(self, X, Y):
+        self.ensure_workspace(0, X.shape[1], 1)
+        out = self.torch.empty(X.shape[1], dtype=self.torch.complex128, device=self.device)
+        _check(self.lib.dmlmc_dotc(self.h, self._chk(X), self._chk(Y, X.shape[0]), X.shape[0], X.shape[1],
+                                   ctypes.c_void_p(out.data_ptr())))
+        return out
+
+    def deflate(self, level, X):
+        self.ensure_workspace(level, X.shape[1], 1)
+        _check(self.lib.dmlmc_deflate(self.h, level, self._chk(X, self.sizes[level]), X.shape[1]))
+        return X
+
+    def probe_expand(self, bits_dev, n, k):
+        X0 = self.empty(n, k, C128)
+        _check(self.lib.dmlmc_probe_expand(self.h, ctypes.c_void_p(bits_dev.data_ptr()), n, k, self._chk(X0)))
+        return X0
+
+    def apply_perm(self, level, X):
+        Y = self.torch.empty_like(X)
+        _check(self.lib.dmlmc_apply_perm(self.h, level, self._chk(X, self.sizes[level]), self._chk(Y), X.shape[1]))
+        return Y
+
+    # ---- solver ----------------------------------------------------------------------
+    def fgmres(self, level, B, tol, restart=40, maxiter=1000):
+        k = B.shape[1]
+        self.ensure_workspace(level, k, restart)
+        X = self.torch.empty_like(B)
+        iters = np.zeros(k, dtype=np.int32)
+        relres = np.zeros(k, dtype=np.float64)
+        _check(self.lib.dmlmc_fgmres(self.h, level, self._chk(B, self.sizes[level]), self._chk(X), k, float(tol),
+                                     int(restart), int(maxiter), iters.ctypes.data_as(ctypes.c_void_p),
+                                     relres.ctypes.data_as(ctypes.c_void_p)))
+        return X, iters, relres
+
+    def level_sample(self, method, level_f, level_c, X0, tol, restart=40, maxiter=1000):
+        k = X0.shape[1]
+        self.ensure_workspace(level_f, k, restart)
+        e = self.torch.empty(k, dtype=self.torch.complex128, device=self.device)
+        iters = np.zeros(2 * k, dtype=np.int32)
+        _check(self.lib.dmlmc_level_sample(self.h, method, level_f, level_c, self._chk(X0, self.sizes[level_f]), k,
+                                           float(tol), int(restart), int(maxiter), ctypes.c_void_p(e.data_ptr()),
+                                           iters.ctypes.data_as(ctypes.c_void_p)))
+        return e, iters.reshape(2, k)
+
+    def level_sample_host(self, method, level_f, level_c, bits_host, k, tol, restart=40, maxiter=1000):
+        """bits_host: packed uint8 (numpy, bitorder='little') of k probes of length n_f; returns (e[k] numpy, iters[2,k])."""
+        self.ensure_workspace(level_f, k, restart)
+        bits_host = np.ascontiguousarray(bits_host, dtype=np.uint8)
+        assert bits_host.size * 8 >= self.sizes[level_f] * k
+        e = np.zeros(k, dtype=np.complex128)
+        iters = np.zeros(2 * k, dtype=np.int32)
+        _check(self.lib.dmlmc_level_sample_host(self.h, method, level_f, level_c, bits_host.ctypes.data_as(ctypes.c_void_p),
+                                                k, float(tol), int(restart), int(maxiter),
+                                                e.ctypes.data_as(ctypes.c_void_p), iters.ctypes.data_as(ctypes.c_void_p)))
+        return e, iters.reshape(2, k)
+
+    def launch_count(self):
+        return int(self.lib.dmlmc_launch_count(self.h))

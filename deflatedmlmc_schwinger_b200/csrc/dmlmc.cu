@@ -1,0 +1,780 @@
+// dmlmc.cu -- libdmlmc_sm100.so: device-resident multigrid hierarchy, V-cycle, batched FGMRES,
+// the fused per-batch sample of utils.one_defl_Hutch_step and the C ABI of include/dmlmc.h.
+// Host code here only orders kernel launches on one CUDA stream; all arithmetic is in the
+// kernels of op_kernels.cuh / krylov_kernels.cuh.  There is no CPU fallback.
+#include "../../include/dmlmc.h"
+#include "common.cuh"
+#include "op_kernels.cuh"
+#include "krylov_kernels.cuh"
+
+#include <algorithm>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+using namespace dmlmc;
+
+static thread_local std::string g_err;
+static int fail(int code, const std::string& msg) { g_err = msg; return code; }
+
+#define CU(call)                                                                              \
+  do {                                                                                        \
+    cudaError_t e_ = (call);                                                                  \
+    if (e_ != cudaSuccess)                                                                    \
+      return fail((int)e_, std::string(#call) + ": " + cudaGetErrorString(e_));               \
+  } while (0)
+#define CHECK(cond, msg) do { if (!(cond)) return fail(-1, std::string("dmlmc: ") + msg); } while (0)
+#define RET(call) do { int rc_ = (call); if (rc_ != 0) return rc_; } while (0)
+
+namespace {
+
+constexpr int ROWS_PER_CHUNK = 256;
+constexpr int MAX_LEVELS = 12;
+
+template <typename T> struct LevelT {
+  // stencil (level 0) or BSR
+  Cx<T>* Ut = nullptr; Cx<T>* Ux = nullptr; Cx<T> diag;
+  Cx<T>* bsr_vals = nullptr;
+  Cx<T>* pv = nullptr;
+  Cx<T>* perm_vals = nullptr;
+};
+
+struct Level {
+  int n = 0;
+  int kind = -1;            // 0 stencil, 1 bsr
+  int LX = 0, LT = 0;
+  int bs = 0, bpr = 0, nb = 0; int* bsr_col = nullptr;
+  bool has_transfer = false; int aggr = 0, dofi = 0, nvec = 0, n_c = 0;
+  std::vector<Cx<double>> inv_roots;      // smoother
+  bool has_perm = false; int shift = 0, perm_nnz = 0; int* perm_cols = nullptr;
+  int defl_d = 0; Cx<double>* defl_V = nullptr;
+  LevelT<double> d;
+  LevelT<float> f;
+};
+
+template <typename T> struct Sel;
+template <> struct Sel<double> { static LevelT<double>& get(Level& L) { return L.d; } };
+template <> struct Sel<float>  { static LevelT<float>&  get(Level& L) { return L.f; } };
+
+}  // namespace
+
+struct dmlmc_hier {
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  int n_levels = 0;
+  Level lv[MAX_LEVELS];
+  int coarse_n = 0; Cx<double>* minv_d = nullptr; Cx<float>* minv_f = nullptr;
+  int inner_prec = DMLMC_C64;
+  char* ws = nullptr; size_t ws_bytes = 0, ws_off = 0;
+  int* h_nactive = nullptr;        // pinned
+  long long launches = 0;
+  std::vector<void*> owned;
+};
+
+namespace {
+
+template <typename T> int upload(dmlmc_hier* h, const T* host, size_t count, T** out) {
+  T* p = nullptr;
+  CU(cudaMalloc(&p, std::max<size_t>(count, 1) * sizeof(T)));
+  h->owned.push_back(p);
+  if (count) CU(cudaMemcpyAsync(p, host, count * sizeof(T), cudaMemcpyHostToDevice, h->stream));
+  CU(cudaStreamSynchronize(h->stream));
+  *out = p;
+  return 0;
+}
+// complex128 host array -> device copies in both precisions
+int upload_cx(dmlmc_hier* h, const double* host, size_t count, Cx<double>** d, Cx<float>** f) {
+  RET(upload<Cx<double>>(h, reinterpret_cast<const Cx<double>*>(host), count, d));
+  std::vector<Cx<float>> tmp(count);
+  for (size_t i = 0; i < count; ++i) tmp[i] = cx<float>((float)host[2 * i], (float)host[2 * i + 1]);
+  RET(upload<Cx<float>>(h, tmp.data(), count, f));
+  return 0;
+}
+
+inline unsigned nblocks(size_t total, int bs) { return (unsigned)((total + bs - 1) / bs); }
+
+#define LAUNCH_CHECK(h)                                                                       \
+  do { (h)->launches++; cudaError_t e_ = cudaGetLastError();                                  \
+       if (e_ != cudaSuccess) return fail((int)e_, std::string("kernel launch: ") + cudaGetErrorString(e_)); } while (0)
+
+// ---- work-space bump allocator ------------------------------------------------------------
+struct WsMark { size_t off; };
+inline size_t align_up(size_t x) { return (x + 255) & ~(size_t)255; }
+int ws_alloc(dmlmc_hier* h, size_t bytes, void** out) {
+  size_t off = align_up(h->ws_off);
+  if (h->ws == nullptr || off + bytes > h->ws_bytes)
+    return fail(-2, "dmlmc: work space too small (call dmlmc_workspace_bytes / dmlmc_set_workspace)");
+  *out = h->ws + off;
+  h->ws_off = off + bytes;
+  return 0;
+}
+template <typename T> int ws_get(dmlmc_hier* h, size_t count, T** out) {
+  void* p; RET(ws_alloc(h, count * sizeof(T), &p)); *out = reinterpret_cast<T*>(p); return 0;
+}
+
+// ---- operator dispatch ----------------------------------------------------------------------
+template <typename T, int NC, int MODE>
+int launch_op_nc(dmlmc_hier* h, int level, const void* X, const void* B, void* Y, void* E, Cx<double> w, int k) {
+  Level& L = h->lv[level];
+  LevelT<T>& D = Sel<T>::get(L);
+  const int kp = k / NC;
+  typedef Pack<T, NC> P;
+  const Cx<T> wt = cx<T>((T)w.re, (T)w.im);
+  if (L.kind == 0) {
+    StencilDev<T> op; op.LX = L.LX; op.LT = L.LT; op.Ut = D.Ut; op.Ux = D.Ux; op.diag = D.diag;
+    const size_t total = (size_t)L.LX * L.LT * kp;
+    stencil_kernel<T, NC, MODE><<<nblocks(total, 256), 256, 0, h->stream>>>(op, (const P*)X, (const P*)B, (P*)Y, (P*)E, wt, kp);
+  } else if (L.kind == 1) {
+    BsrDev<T> op; op.nb = L.nb; op.bpr = L.bpr; op.col = L.bsr_col; op.vals = D.bsr_vals;
+    const size_t total = (size_t)L.nb * kp;
+    const unsigned g = nblocks(total, 128);
+    switch (L.bs) {
+      case 1: bsr_kernel<T, NC, 1, MODE><<<g, 128, 0, h->stream>>>(op, (const P*)X, (const P*)B, (P*)Y, (P*)E, wt, kp); break;
+      case 2: bsr_kernel<T, NC, 2, MODE><<<g, 128, 0, h->stream>>>(op, (const P*)X, (const P*)B, (P*)Y, (P*)E, wt, kp); break;
+      case 4: bsr_kernel<T, NC, 4, MODE><<<g, 128, 0, h->stream>>>(op, (const P*)X, (const P*)B, (P*)Y, (P*)E, wt, kp); break;
+      case 8: bsr_kernel<T, NC, 8, MODE><<<g, 128, 0, h->stream>>>(op, (const P*)X, (const P*)B, (P*)Y, (P*)E, wt, kp); break;
+      default: return fail(-1, "dmlmc: unsupported BSR block size");
+    }
+  } else {
+    return fail(-1, "dmlmc: operator of this level not set");
+  }
+  LAUNCH_CHECK(h);
+  return 0;
+}
+template <typename T> constexpr int max_nc() { return sizeof(T) == 4 ? 2 : 1; }
+
+template <typename T, int MODE>
+int launch_op(dmlmc_hier* h, int level, const void* X, const void* B, void* Y, void* E, Cx<double> w, int k) {
+  if (max_nc<T>() == 2 && (k % 2) == 0) return launch_op_nc<T, max_nc<T>(), MODE>(h, level, X, B, Y, E, w, k);
+  return launch_op_nc<T, 1, MODE>(h, level, X, B, Y, E, w, k);
+}
+
+template <typename T, int NC>
+int launch_restrict_nc(dmlmc_hier* h, int level, const void* Xf, void* Xc, int k) {
+  Level& L = h->lv[level];
+  TransferDev<T> tr; tr.n_f = L.n; tr.n_c = L.n_c; tr.aggr = L.aggr; tr.dofi = L.dofi; tr.h = L.dofi / 2; tr.nvec = L.nvec;
+  tr.pv = Sel<T>::get(L).pv;
+  const int kp = k / NC; typedef Pack<T, NC> P;
+  const size_t total = (size_t)(L.n_c / L.nvec) * kp;
+  const unsigned g = nblocks(total, 128);
+  switch (L.nvec) {
+    case 1: restrict_kernel<T, NC, 1><<<g, 128, 0, h->stream>>>(tr, (const P*)Xf, (P*)Xc, kp); break;
+    case 2: restrict_kernel<T, NC, 2><<<g, 128, 0, h->stream>>>(tr, (const P*)Xf, (P*)Xc, kp); break;
+    case 4: restrict_kernel<T, NC, 4><<<g, 128, 0, h->stream>>>(tr, (const P*)Xf, (P*)Xc, kp); break;
+    case 8: restrict_kernel<T, NC, 8><<<g, 128, 0, h->stream>>>(tr, (const P*)Xf, (P*)Xc, kp); break;
+    default: return fail(-1, "dmlmc: unsupported number of test vectors");
+  }
+  LAUNCH_CHECK(h);
+  return 0;
+}
+template <typename T> int launch_restrict(dmlmc_hier* h, int level, const void* Xf, void* Xc, int k) {
+  if (!h->lv[level].has_transfer) return fail(-1, "dmlmc: transfer operator of this level not set");
+  if (max_nc<T>() == 2 && (k % 2) == 0) return launch_restrict_nc<T, max_nc<T>()>(h, level, Xf, Xc, k);
+  return launch_restrict_nc<T, 1>(h, level, Xf, Xc, k);
+}
+template <typename T, int NC>
+int launch_prolong_nc(dmlmc_hier* h, int level, const void* Xc, void* Xf, int k) {
+  Level& L = h->lv[level];
+  TransferDev<T> tr; tr.n_f = L.n; tr.n_c = L.n_c; tr.aggr = L.aggr; tr.dofi = L.dofi; tr.h = L.dofi / 2; tr.nvec = L.nvec;
+  tr.pv = Sel<T>::get(L).pv;
+  const int kp = k / NC; typedef Pack<T, NC> P;
+  const size_t total = (size_t)L.n * kp;
+  const unsigned g = nblocks(total, 256);
+  switch (L.nvec) {
+    case 1: prolong_add_kernel<T, NC, 1><<<g, 256, 0, h->stream>>>(tr, (const P*)Xc, (P*)Xf, kp); break;
+    case 2: prolong_add_kernel<T, NC, 2><<<g, 256, 0, h->stream>>>(tr, (const P*)Xc, (P*)Xf, kp); break;
+    case 4: prolong_add_kernel<T, NC, 4><<<g, 256, 0, h->stream>>>(tr, (const P*)Xc, (P*)Xf, kp); break;
+    case 8: prolong_add_kernel<T, NC, 8><<<g, 256, 0, h->stream>>>(tr, (const P*)Xc, (P*)Xf, kp); break;
+    default: return fail(-1, "dmlmc: unsupported number of test vectors");
+  }
+  LAUNCH_CHECK(h);
+  return 0;
+}
+template <typename T> int launch_prolong(dmlmc_hier* h, int level, const void* Xc, void* Xf, int k) {
+  if (!h->lv[level].has_transfer) return fail(-1, "dmlmc: transfer operator of this level not set");
+  if (max_nc<T>() == 2 && (k % 2) == 0) return launch_prolong_nc<T, max_nc<T>()>(h, level, Xc, Xf, k);
+  return launch_prolong_nc<T, 1>(h, level, Xc, Xf, k);
+}
+
+template <typename T> Cx<T>* minv_of(dmlmc_hier* h);
+template <> Cx<double>* minv_of<double>(dmlmc_hier* h) { return h->minv_d; }
+template <> Cx<float>*  minv_of<float>(dmlmc_hier* h)  { return h->minv_f; }
+
+template <typename T> int launch_dense(dmlmc_hier* h, const void* B, void* X, int k) {
+  if (h->coarse_n == 0) return fail(-1, "dmlmc: coarsest inverse not set");
+  const int n = h->coarse_n;
+  dim3 blk(32, 8);
+  if (max_nc<T>() == 2 && (k % 2) == 0) {
+    constexpr int NC = max_nc<T>(); const int kp = k / NC;
+    dim3 grd((kp + 31) / 32, (n + 31) / 32);
+    dense_kernel<T, NC><<<grd, blk, 0, h->stream>>>(minv_of<T>(h), n, (const Pack<T, NC>*)B, (Pack<T, NC>*)X, kp);
+  } else {
+    dim3 grd((k + 31) / 32, (n + 31) / 32);
+    dense_kernel<T, 1><<<grd, blk, 0, h->stream>>>(minv_of<T>(h), n, (const Pack<T, 1>*)B, (Pack<T, 1>*)X, k);
+  }
+  LAUNCH_CHECK(h);
+  return 0;
+}
+
+// E += w * R (elementwise), used for the last Richardson step of the post-smoother
+template <typename T>
+__global__ void __launch_bounds__(256) axpy_w_kernel(Cx<T> w, const Cx<T>* __restrict__ R, Cx<T>* __restrict__ E, size_t count) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= count) return;
+  Pack<T, 1> e = *reinterpret_cast<const Pack<T, 1>*>(E + i);
+  pfma<T, 1>(e, w, *reinterpret_cast<const Pack<T, 1>*>(R + i));
+  *reinterpret_cast<Pack<T, 1>*>(E + i) = e;
+}
+template <typename T> int launch_axpy_w(dmlmc_hier* h, Cx<double> w, const void* R, void* E, size_t count) {
+  axpy_w_kernel<T><<<nblocks(count, 256), 256, 0, h->stream>>>(cx<T>((T)w.re, (T)w.im), (const Cx<T>*)R, (Cx<T>*)E, count);
+  LAUNCH_CHECK(h);
+  return 0;
+}
+
+// ---- smoother: e = p(A) r by Richardson steps, r_{i+1} = r_i - w_i A r_i, e += w_i r_i --------
+// On return *r_final points to the buffer (t0 or t1) holding the final residual if need_residual;
+// otherwise the last step skips the operator application.
+template <typename T>
+int smooth(dmlmc_hier* h, int level, const void* R, void* E, bool e_is_zero, void* t0, void* t1,
+           bool need_residual, const void** r_final, int k) {
+  Level& L = h->lv[level];
+  const int d = (int)L.inv_roots.size();
+  if (d < 1) return fail(-1, "dmlmc: smoother of this level not set");
+  const void* rin = R;
+  void* bufs[2] = {t0, t1};
+  int nb = 0;
+  for (int i = 0; i < d; ++i) {
+    const bool last = (i == d - 1);
+    const bool first = e_is_zero && i == 0;
+    if (last && !need_residual) {
+      if (first) {   // degree-1 smoother on a zero start: E = w R
+        CU(cudaMemsetAsync(E, 0, (size_t)L.n * k * sizeof(Cx<T>), h->stream));
+      }
+      RET(launch_axpy_w<T>(h, L.inv_roots[i], rin, E, (size_t)L.n * k));
+      break;
+    }
+    void* rout = bufs[nb]; nb ^= 1;
+    if (first) RET((launch_op<T, M_SMOOTH_FIRST>(h, level, rin, nullptr, rout, E, L.inv_roots[i], k)));
+    else       RET((launch_op<T, M_SMOOTH>(h, level, rin, nullptr, rout, E, L.inv_roots[i], k)));
+    rin = rout;
+  }
+  if (r_final) *r_final = rin;
+  return 0;
+}
+
+// ---- V-cycle (multigrid.py:369-447) -----------------------------------------------------------
+template <typename T>
+int vcycle(dmlmc_hier* h, int level0, const void* Bin, void* Xout, int k) {
+  const int nl = h->n_levels;
+  CHECK(level0 >= 0 && level0 < nl, "vcycle: bad level");
+  if (level0 == nl - 1) return launch_dense<T>(h, Bin, Xout, k);
+  const size_t mark = h->ws_off;
+  std::vector<void*> b(nl, nullptr), x(nl, nullptr), t0(nl, nullptr), t1(nl, nullptr);
+  for (int l = level0; l < nl; ++l) {
+    const size_t cnt = (size_t)h->lv[l].n * k;
+    if (l > level0) { Cx<T>* p; RET(ws_get<Cx<T>>(h, cnt, &p)); b[l] = p; RET(ws_get<Cx<T>>(h, cnt, &p)); x[l] = p; }
+    if (l < nl - 1) { Cx<T>* p; RET(ws_get<Cx<T>>(h, cnt, &p)); t0[l] = p; RET(ws_get<Cx<T>>(h, cnt, &p)); t1[l] = p; }
+  }
+  x[level0] = Xout;
+  const void* bl0 = Bin;
+  for (int l = level0; l < nl - 1; ++l) {
+    const void* bl = (l == level0) ? bl0 : b[l];
+    const void* rfin = nullptr;
+    RET(smooth<T>(h, l, bl, x[l], true, t0[l], t1[l], true, &rfin, k));
+    RET(launch_restrict<T>(h, l, rfin, b[l + 1], k));
+  }
+  RET(launch_dense<T>(h, b[nl - 1], x[nl - 1], k));
+  for (int l = nl - 2; l >= level0; --l) {
+    const void* bl = (l == level0) ? bl0 : b[l];
+    RET(launch_prolong<T>(h, l, x[l + 1], x[l], k));
+    RET((launch_op<T, M_RES>(h, l, x[l], bl, t0[l], nullptr, cx<double>(0, 0), k)));
+    // post-smoothing on r = t0: ping-pong must not overwrite its own input
+    const int d = (int)h->lv[l].inv_roots.size();
+    const void* rin = t0[l];
+    void* pp[2] = {t1[l], t0[l]};
+    for (int i = 0; i < d; ++i) {
+      if (i == d - 1) { RET(launch_axpy_w<T>(h, h->lv[l].inv_roots[i], rin, x[l], (size_t)h->lv[l].n * k)); break; }
+      void* rout = pp[i & 1];
+      RET((launch_op<T, M_SMOOTH>(h, l, rin, nullptr, rout, x[l], h->lv[l].inv_roots[i], k)));
+      rin = rout;
+    }
+  }
+  h->ws_off = mark;
+  return 0;
+}
+
+// ---- complex128 reductions ---------------------------------------------------------------------
+int multi_dot(dmlmc_hier* h, const Z* Vbase, size_t vstride, int nv, const Z* W, int n, int k, Z* partial, Z* out, int accumulate) {
+  const int nchunks = (n + ROWS_PER_CHUNK - 1) / ROWS_PER_CHUNK;
+  dim3 blk(DOT_TX, DOT_TY), grd((k + DOT_TX - 1) / DOT_TX, nchunks);
+  multi_dot_kernel<<<grd, blk, 0, h->stream>>>(Vbase, vstride, nv, W, n, k, ROWS_PER_CHUNK, partial);
+  LAUNCH_CHECK(h);
+  sum_partials_kernel<<<nblocks((size_t)nv * k, 256), 256, 0, h->stream>>>(partial, nchunks, nv * k, out, accumulate);
+  LAUNCH_CHECK(h);
+  return 0;
+}
+size_t partial_count(int n, int nv, int k) { return (size_t)((n + ROWS_PER_CHUNK - 1) / ROWS_PER_CHUNK) * nv * k; }
+
+int multi_axpy(dmlmc_hier* h, const Z* Vbase, size_t vstride, int nv, const Z* hc, Z* W, int n, int k, double sgn) {
+  const size_t nk = (size_t)n * k;
+  multi_axpy_kernel<<<nblocks(nk, 256), 256, 0, h->stream>>>(Vbase, vstride, nv, hc, W, nk, k, sgn);
+  LAUNCH_CHECK(h);
+  return 0;
+}
+
+int precond(dmlmc_hier* h, int level, const Z* V, Z* Zout, int k) {
+  const size_t cnt = (size_t)h->lv[level].n * k;
+  if (h->inner_prec == DMLMC_C128) return vcycle<double>(h, level, V, Zout, k);
+  const size_t mark = h->ws_off;
+  Cx<float>* bf; Cx<float>* xf;
+  RET(ws_get<Cx<float>>(h, cnt, &bf)); RET(ws_get<Cx<float>>(h, cnt, &xf));
+  const unsigned g = std::min<unsigned>(nblocks(cnt, 256), 148u * 16u);
+  cvt_d2f_kernel<<<g, 256, 0, h->stream>>>((const double*)V, (float*)bf, cnt); LAUNCH_CHECK(h);
+  RET(vcycle<float>(h, level, bf, xf, k));
+  cvt_f2d_kernel<<<g, 256, 0, h->stream>>>((const float*)xf, (double*)Zout, cnt); LAUNCH_CHECK(h);
+  h->ws_off = mark;
+  return 0;
+}
+
+int read_nactive(dmlmc_hier* h, int* dev_counter, int* out) {
+  CU(cudaMemcpyAsync(h->h_nactive, dev_counter, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+  CU(cudaStreamSynchronize(h->stream));
+  *out = *h->h_nactive;
+  return 0;
+}
+
+// ---- batched FGMRES (multigrid.py:347-366 / pyamg.krylov.fgmres) ------------------------------
+int fgmres(dmlmc_hier* h, int level, const Z* B, Z* X, int k, double tol, int restart, int maxiter,
+           int32_t* iters_host, double* relres_host) {
+  CHECK(level >= 0 && level < h->n_levels, "fgmres: bad level");
+  CHECK(k >= 1 && restart >= 1 && maxiter >= 1, "fgmres: bad k / restart / maxiter");
+  Level& L = h->lv[level];
+  const int n = L.n, m = restart;
+  const size_t nk = (size_t)n * k;
+  const size_t mark = h->ws_off;
+  GmresState s; s.k = k; s.m = m;
+  Z *Vb, *Zb, *W, *Rb, *partial;
+  RET(ws_get<Z>(h, nk * (m + 1), &Vb));
+  RET(ws_get<Z>(h, nk * m, &Zb));
+  RET(ws_get<Z>(h, nk, &W));
+  RET(ws_get<Z>(h, nk, &Rb));
+  RET(ws_get<Z>(h, partial_count(n, m + 1, k), &partial));
+  RET(ws_get<Z>(h, (size_t)(m + 1) * k, &s.hsum));
+  RET(ws_get<Z>(h, (size_t)k, &s.nrm2));
+  RET(ws_get<Z>(h, (size_t)m * m * k, &s.Rm));
+  RET(ws_get<double>(h, (size_t)m * k, &s.cs));
+  RET(ws_get<Z>(h, (size_t)m * k, &s.sn));
+  RET(ws_get<Z>(h, (size_t)(m + 1) * k, &s.g));
+  RET(ws_get<Z>(h, (size_t)m * k, &s.y));
+  RET(ws_get<double>(h, (size_t)k, &s.normb));
+  RET(ws_get<double>(h, (size_t)k, &s.scale));
+  RET(ws_get<double>(h, (size_t)k, &s.relres));
+  RET(ws_get<int>(h, (size_t)k, &s.active));
+  RET(ws_get<int>(h, (size_t)k, &s.done));
+  RET(ws_get<int>(h, (size_t)k, &s.it_cycle));
+  RET(ws_get<int>(h, (size_t)k, &s.it_total));
+  RET(ws_get<int>(h, 1, &s.n_active));
+
+  CU(cudaMemsetAsync(X, 0, nk * sizeof(Z), h->stream));
+  const Z* Rsrc = B;
+  int total_it = 0, nact = 0;
+  bool first = true;
+  const unsigned gk = nblocks(k, 128);
+  while (true) {
+    RET(multi_dot(h, Rsrc, 0, 1, Rsrc, n, k, partial, s.nrm2, 0));
+    CU(cudaMemsetAsync(s.n_active, 0, sizeof(int), h->stream));
+    gmres_init_kernel<<<nblocks(k, 256), 256, 0, h->stream>>>(s, tol, first ? 1 : 0); LAUNCH_CHECK(h);
+    first = false;
+    col_scale_kernel<<<nblocks(nk, 256), 256, 0, h->stream>>>(Rsrc, s.scale, Vb, nk, k); LAUNCH_CHECK(h);
+    RET(read_nactive(h, s.n_active, &nact));
+    if (nact == 0) break;
+    int j = 0;
+    for (; j < m; ++j) {
+      Z* Vj = Vb + (size_t)j * nk;
+      Z* Zj = Zb + (size_t)j * nk;
+      RET(precond(h, level, Vj, Zj, k));
+      RET((launch_op<double, M_AX>(h, level, Zj, nullptr, W, nullptr, cx<double>(0, 0), k)));
+      // classical Gram-Schmidt with one re-orthogonalisation pass
+      RET(multi_dot(h, Vb, nk, j + 1, W, n, k, partial, s.hsum, 0));
+      RET(multi_axpy(h, Vb, nk, j + 1, s.hsum, W, n, k, -1.0));
+      RET(multi_dot(h, Vb, nk, j + 1, W, n, k, partial, s.y, 0));       // s.y used as scratch [(j+1)][k]
+      RET(multi_axpy(h, Vb, nk, j + 1, s.y, W, n, k, -1.0));
+      {  // hsum += second-pass coefficients
+        const int cnt = (j + 1) * k;
+        sum_partials_kernel<<<nblocks(cnt, 256), 256, 0, h->stream>>>(s.y, 1, cnt, s.hsum, 1); LAUNCH_CHECK(h);
+      }
+      RET(multi_dot(h, W, 0, 1, W, n, k, partial, s.nrm2, 0));
+      CU(cudaMemsetAsync(s.n_active, 0, sizeof(int), h->stream));
+      gmres_step_kernel<<<gk, 128, 0, h->stream>>>(s, j, tol); LAUNCH_CHECK(h);
+      ++total_it;
+      if (j + 1 < m) { col_scale_kernel<<<nblocks(nk, 256), 256, 0, h->stream>>>(W, s.scale, Vb + (size_t)(j + 1) * nk, nk, k); LAUNCH_CHECK(h); }
+      RET(read_nactive(h, s.n_active, &nact));
+      if (nact == 0 || total_it >= maxiter) { ++j; break; }
+    }
+    const int steps = std::min(j, m);
+    gmres_solve_kernel<<<gk, 128, 0, h->stream>>>(s, steps); LAUNCH_CHECK(h);
+    RET(multi_axpy(h, Zb, nk, steps, s.y, X, n, k, +1.0));
+    if (nact == 0 || total_it >= maxiter) break;
+    // restart: true residual of all columns
+    RET((launch_op<double, M_RES>(h, level, X, B, Rb, nullptr, cx<double>(0, 0), k)));
+    Rsrc = Rb;
+  }
+  if (iters_host) CU(cudaMemcpyAsync(iters_host, s.it_total, sizeof(int) * k, cudaMemcpyDeviceToHost, h->stream));
+  if (relres_host) CU(cudaMemcpyAsync(relres_host, s.relres, sizeof(double) * k, cudaMemcpyDeviceToHost, h->stream));
+  if (iters_host || relres_host) CU(cudaStreamSynchronize(h->stream));
+  h->ws_off = mark;
+  return 0;
+}
+
+int apply_perm(dmlmc_hier* h, int level, const Z* X, Z* Y, int k) {
+  Level& L = h->lv[level];
+  const size_t nk = (size_t)L.n * k;
+  if (!L.has_perm) { CU(cudaMemcpyAsync(Y, X, nk * sizeof(Z), cudaMemcpyDeviceToDevice, h->stream)); return 0; }
+  perm_kernel<double, 1><<<nblocks(nk, 256), 256, 0, h->stream>>>(L.n, L.shift, L.perm_nnz, L.perm_cols, L.d.perm_vals,
+                                                                 (const Pack<double, 1>*)X, (Pack<double, 1>*)Y, k);
+  LAUNCH_CHECK(h);
+  return 0;
+}
+
+int deflate(dmlmc_hier* h, int level, Z* X, int k) {
+  Level& L = h->lv[level];
+  if (L.defl_d == 0) return 0;
+  const int n = L.n, d = L.defl_d;
+  const size_t mark = h->ws_off;
+  Z *partial, *C;
+  RET(ws_get<Z>(h, partial_count(n, d, k), &partial));
+  RET(ws_get<Z>(h, (size_t)d * k, &C));
+  const int nchunks = (n + ROWS_PER_CHUNK - 1) / ROWS_PER_CHUNK;
+  dim3 blk(DOT_TX, DOT_TY), grd((k + DOT_TX - 1) / DOT_TX, nchunks);
+  defl_dot_kernel<<<grd, blk, 0, h->stream>>>(L.defl_V, d, X, n, k, ROWS_PER_CHUNK, partial); LAUNCH_CHECK(h);
+  sum_partials_kernel<<<nblocks((size_t)d * k, 256), 256, 0, h->stream>>>(partial, nchunks, d * k, C, 0); LAUNCH_CHECK(h);
+  const size_t nk = (size_t)n * k;
+  defl_axpy_kernel<<<nblocks(nk, 256), 256, 0, h->stream>>>(L.defl_V, d, C, X, nk, k); LAUNCH_CHECK(h);
+  h->ws_off = mark;
+  return 0;
+}
+
+// ---- one batch of utils.one_defl_Hutch_step (utils.py:207-361) ----------------------------------
+int level_sample(dmlmc_hier* h, int method, int lf, int lc, const Z* X0, int k, double tol, int restart,
+                 int maxiter, Z* e_dev, int32_t* iters_host) {
+  const int nl = h->n_levels;
+  CHECK(lf >= 0 && lf < nl - 1, "level_sample: bad fine level");
+  CHECK(method == 0 || method == 1, "level_sample: bad method");
+  if (method == 0) CHECK(lf == 0, "level_sample: hutchinson runs on level 0");
+  if (method == 1) CHECK(lc == lf + 1 || lc == lf + 2, "level_sample: coarse level must be fine+1 or fine+2");
+  if (method == 1) CHECK(lc < nl, "level_sample: coarse level out of range");
+  Level& Lf = h->lv[lf];
+  const int nf = Lf.n;
+  const size_t nkf = (size_t)nf * k;
+  const size_t mark = h->ws_off;
+  Z *Xdef, *RHS, *Zs, *partial, *e1;
+  RET(ws_get<Z>(h, nkf, &Xdef));
+  RET(ws_get<Z>(h, nkf, &RHS));
+  RET(ws_get<Z>(h, nkf, &Zs));
+  RET(ws_get<Z>(h, partial_count(nf, 1, k), &partial));
+  RET(ws_get<Z>(h, (size_t)k, &e1));
+  // x_def = x0 - V (V^H x0)            utils.py:224,266
+  const Z* xd = X0;
+  if (Lf.defl_d > 0) {
+    CU(cudaMemcpyAsync(Xdef, X0, nkf * sizeof(Z), cudaMemcpyDeviceToDevice, h->stream));
+    RET(deflate(h, lf, Xdef, k));
+    xd = Xdef;
+  }
+  // rhs = Bblock_perm * roll(x_def, +shift)   utils.py:232,288-290
+  const Z* rhs = xd;
+  if (Lf.has_perm) { RET(apply_perm(h, lf, xd, RHS, k)); rhs = RHS; }
+  RET(fgmres(h, lf, rhs, Zs, k, tol, restart, maxiter, iters_host, nullptr));
+  RET(multi_dot(h, X0, 0, 1, Zs, nf, k, partial, e1, 0));            // e1 = x0^H z   utils.py:249,336
+  if (method == 0) {
+    CU(cudaMemcpyAsync(e_dev, e1, sizeof(Z) * k, cudaMemcpyDeviceToDevice, h->stream));
+    h->ws_off = mark;
+    return 0;
+  }
+  // xc = R (R) rhs                      utils.py:299-303
+  const bool skip = (lc == lf + 2);
+  const int nc = h->lv[lc].n;
+  Z *Xm = nullptr, *Xc, *Y, *e2;
+  if (skip) RET(ws_get<Z>(h, (size_t)h->lv[lf + 1].n * k, &Xm));
+  RET(ws_get<Z>(h, (size_t)nc * k, &Xc));
+  RET(ws_get<Z>(h, (size_t)nc * k, &Y));
+  RET(ws_get<Z>(h, (size_t)k, &e2));
+  if (skip) { RET(launch_restrict<double>(h, lf, rhs, Xm, k)); RET(launch_restrict<double>(h, lf + 1, Xm, Xc, k)); }
+  else      { RET(launch_restrict<double>(h, lf, rhs, Xc, k)); }
+  // y = A_c^{-1} xc                     utils.py:306-329
+  if (lc == nl - 1) RET(launch_dense<double>(h, Xc, Y, k));
+  else RET(fgmres(h, lc, Xc, Y, k, tol, restart, maxiter, iters_host ? iters_host + k : nullptr, nullptr));
+  // w = P (P) y ; e2 = x0^H w           utils.py:337-353  (w overwrites the solution buffer's sibling RHS)
+  Z* Wf = RHS;     // RHS is no longer needed (rhs may alias X0/Xdef when no perm: then RHS is free as well)
+  CU(cudaMemsetAsync(Wf, 0, nkf * sizeof(Z), h->stream));
+  if (skip) {
+    CU(cudaMemsetAsync(Xm, 0, (size_t)h->lv[lf + 1].n * k * sizeof(Z), h->stream));
+    RET(launch_prolong<double>(h, lf + 1, Y, Xm, k));
+    RET(launch_prolong<double>(h, lf, Xm, Wf, k));
+  } else {
+    RET(launch_prolong<double>(h, lf, Y, Wf, k));
+  }
+  RET(multi_dot(h, X0, 0, 1, Wf, nf, k, partial, e2, 0));
+  zsub_kernel<<<nblocks(k, 128), 128, 0, h->stream>>>(e1, e2, e_dev, k); LAUNCH_CHECK(h);
+  h->ws_off = mark;
+  return 0;
+}
+
+size_t vcycle_bytes(dmlmc_hier* h, int level, int k, size_t elem) {
+  size_t b = 0;
+  for (int l = level; l < h->n_levels; ++l) b += 4 * align_up((size_t)h->lv[l].n * k * elem);
+  return b + 4096;
+}
+size_t fgmres_bytes(dmlmc_hier* h, int level, int k, int m) {
+  const size_t n = h->lv[level].n, nk = n * (size_t)k, z = sizeof(Z);
+  size_t b = 0;
+  b += align_up(nk * (m + 1) * z) + align_up(nk * m * z) + 2 * align_up(nk * z);
+  b += align_up(partial_count((int)n, m + 1, k) * z);
+  b += align_up((size_t)m * m * k * z) + 6 * align_up((size_t)(m + 1) * k * z) + 16 * align_up((size_t)k * 16);
+  b += 2 * align_up(nk * sizeof(Cx<float>));
+  b += vcycle_bytes(h, level, k, sizeof(Z));
+  return b + (1 << 16);
+}
+
+}  // namespace
+
+// =================================================================================================
+extern "C" {
+
+int dmlmc_abi_version(void) { return DMLMC_ABI_VERSION; }
+const char* dmlmc_last_error(void) { return g_err.c_str(); }
+
+int dmlmc_hier_create(int device, void* cuda_stream, int n_levels, dmlmc_hier** out) {
+  CHECK(out != nullptr, "hier_create: out is NULL");
+  CHECK(n_levels >= 1 && n_levels <= MAX_LEVELS, "hier_create: bad number of levels");
+  int ndev = 0;
+  cudaError_t e = cudaGetDeviceCount(&ndev);
+  if (e != cudaSuccess || ndev == 0)
+    return fail(e != cudaSuccess ? (int)e : -3, "dmlmc: no CUDA device available (this library has no CPU fallback)");
+  CU(cudaSetDevice(device));
+  dmlmc_hier* h = new dmlmc_hier();
+  h->device = device; h->stream = (cudaStream_t)cuda_stream; h->n_levels = n_levels;
+  cudaError_t e2 = cudaMallocHost(&h->h_nactive, sizeof(int));
+  if (e2 != cudaSuccess) { delete h; return fail((int)e2, "cudaMallocHost failed"); }
+  *out = h;
+  return 0;
+}
+
+int dmlmc_hier_destroy(dmlmc_hier* h) {
+  if (!h) return 0;
+  cudaSetDevice(h->device);
+  cudaStreamSynchronize(h->stream);
+  for (void* p : h->owned) cudaFree(p);
+  if (h->h_nactive) cudaFreeHost(h->h_nactive);
+  delete h;
+  return 0;
+}
+
+int dmlmc_set_stencil(dmlmc_hier* h, int level, int LX, int LT, const double* links_host, double diag_re, double diag_im) {
+  CHECK(h && level >= 0 && level < h->n_levels, "set_stencil: bad handle/level");
+  CHECK(LX >= 2 && LT >= 2 && links_host, "set_stencil: bad lattice");
+  CU(cudaSetDevice(h->device));
+  Level& L = h->lv[level];
+  L.kind = 0; L.LX = LX; L.LT = LT; L.n = 2 * LX * LT;
+  const size_t V = (size_t)LX * LT;
+  RET(upload_cx(h, links_host, V, &L.d.Ut, &L.f.Ut));
+  RET(upload_cx(h, links_host + 2 * V, V, &L.d.Ux, &L.f.Ux));
+  L.d.diag = cx<double>(diag_re, diag_im); L.f.diag = cx<float>((float)diag_re, (float)diag_im);
+  return 0;
+}
+
+int dmlmc_set_bsr(dmlmc_hier* h, int level, int n, int bs, int bpr, const int32_t* colidx_host, const double* vals_host) {
+  CHECK(h && level >= 0 && level < h->n_levels, "set_bsr: bad handle/level");
+  CHECK(bs == 1 || bs == 2 || bs == 4 || bs == 8, "set_bsr: block size must be 1, 2, 4 or 8");
+  CHECK(n > 0 && n % bs == 0 && bpr >= 1 && colidx_host && vals_host, "set_bsr: bad arguments");
+  CU(cudaSetDevice(h->device));
+  Level& L = h->lv[level];
+  L.kind = 1; L.n = n; L.bs = bs; L.bpr = bpr; L.nb = n / bs;
+  for (size_t i = 0; i < (size_t)L.nb * bpr; ++i) CHECK(colidx_host[i] >= -1 && colidx_host[i] < L.nb, "set_bsr: block column out of range");
+  RET(upload<int>(h, colidx_host, (size_t)L.nb * bpr, &L.bsr_col));
+  RET(upload_cx(h, vals_host, (size_t)L.nb * bpr * bs * bs, &L.d.bsr_vals, &L.f.bsr_vals));
+  return 0;
+}
+
+int dmlmc_set_transfer(dmlmc_hier* h, int level, int n_f, int aggr_size, int dofi, int nvec, const double* pvals_host) {
+  CHECK(h && level >= 0 && level < h->n_levels - 1, "set_transfer: bad handle/level");
+  CHECK(nvec == 1 || nvec == 2 || nvec == 4 || nvec == 8, "set_transfer: nvec must be 1, 2, 4 or 8");
+  CHECK(n_f > 0 && aggr_size > 0 && dofi >= 2 && dofi % 2 == 0 && aggr_size % dofi == 0 && n_f % aggr_size == 0 && pvals_host,
+        "set_transfer: inconsistent aggregation");
+  CU(cudaSetDevice(h->device));
+  Level& L = h->lv[level];
+  CHECK(L.n == 0 || L.n == n_f, "set_transfer: n_f does not match the level's operator");
+  L.n = n_f; L.has_transfer = true; L.aggr = aggr_size; L.dofi = dofi; L.nvec = nvec; L.n_c = (n_f / aggr_size) * 2 * nvec;
+  RET(upload_cx(h, pvals_host, (size_t)n_f * nvec, &L.d.pv, &L.f.pv));
+  return 0;
+}
+
+int dmlmc_set_coarsest_inverse(dmlmc_hier* h, int n, const double* minv_host) {
+  CHECK(h && n > 0 && minv_host, "set_coarsest_inverse: bad arguments");
+  CU(cudaSetDevice(h->device));
+  h->coarse_n = n;
+  Level& L = h->lv[h->n_levels - 1];
+  CHECK(L.n == 0 || L.n == n, "set_coarsest_inverse: size does not match the coarsest level");
+  L.n = n;
+  RET(upload_cx(h, minv_host, (size_t)n * n, &h->minv_d, &h->minv_f));
+  return 0;
+}
+
+int dmlmc_set_smoother(dmlmc_hier* h, int level, int degree, const double* inv_roots_host) {
+  CHECK(h && level >= 0 && level < h->n_levels, "set_smoother: bad handle/level");
+  CHECK(degree >= 1 && inv_roots_host, "set_smoother: degree must be >= 1");
+  Level& L = h->lv[level];
+  L.inv_roots.resize(degree);
+  for (int i = 0; i < degree; ++i) L.inv_roots[i] = cx<double>(inv_roots_host[2 * i], inv_roots_host[2 * i + 1]);
+  return 0;
+}
+
+int dmlmc_set_perm(dmlmc_hier* h, int level, int shift, int nnz_per_row, const int32_t* cols_host, const double* vals_host) {
+  CHECK(h && level >= 0 && level < h->n_levels, "set_perm: bad handle/level");
+  Level& L = h->lv[level];
+  CHECK(L.n > 0, "set_perm: set the level's operator first");
+  CHECK(shift >= 0 && shift < L.n && nnz_per_row >= 0, "set_perm: bad shift");
+  CU(cudaSetDevice(h->device));
+  L.has_perm = true; L.shift = shift; L.perm_nnz = nnz_per_row;
+  if (nnz_per_row > 0) {
+    CHECK(cols_host && vals_host, "set_perm: missing Bblock_perm arrays");
+    RET(upload<int>(h, cols_host, (size_t)L.n * nnz_per_row, &L.perm_cols));
+    RET(upload_cx(h, vals_host, (size_t)L.n * nnz_per_row, &L.d.perm_vals, &L.f.perm_vals));
+  }
+  return 0;
+}
+
+int dmlmc_set_deflation(dmlmc_hier* h, int level, int d, const double* v_host) {
+  CHECK(h && level >= 0 && level < h->n_levels, "set_deflation: bad handle/level");
+  Level& L = h->lv[level];
+  CHECK(L.n > 0, "set_deflation: set the level's operator first");
+  CU(cudaSetDevice(h->device));
+  L.defl_d = 0;
+  if (d > 0) {
+    CHECK(v_host, "set_deflation: missing vectors");
+    RET(upload<Cx<double>>(h, reinterpret_cast<const Cx<double>*>(v_host), (size_t)L.n * d, &L.defl_V));
+    L.defl_d = d;
+  }
+  return 0;
+}
+
+#define ENTER(h) do { CHECK((h) != nullptr, "NULL handle"); CU(cudaSetDevice((h)->device)); } while (0)
+#define CHECK_LEVEL(h, level) CHECK((level) >= 0 && (level) < (h)->n_levels && (h)->lv[level].n > 0, "bad level")
+#define CHECK_PREC(prec) CHECK((prec) == DMLMC_C128 || (prec) == DMLMC_C64, "bad precision")
+
+int dmlmc_spmm(dmlmc_hier* h, int level, int prec, const void* X, void* Y, int k) {
+  ENTER(h); CHECK_LEVEL(h, level); CHECK_PREC(prec); CHECK(X && Y && k >= 1, "spmm: bad arguments");
+  if (level == h->n_levels - 1 && h->lv[level].kind < 0) return fail(-1, "spmm: the coarsest level has no sparse operator");
+  if (prec == DMLMC_C128) return launch_op<double, M_AX>(h, level, X, nullptr, Y, nullptr, cx<double>(0, 0), k);
+  return launch_op<float, M_AX>(h, level, X, nullptr, Y, nullptr, cx<double>(0, 0), k);
+}
+int dmlmc_restrict(dmlmc_hier* h, int level, int prec, const void* Xf, void* Xc, int k) {
+  ENTER(h); CHECK_LEVEL(h, level); CHECK_PREC(prec); CHECK(Xf && Xc && k >= 1, "restrict: bad arguments");
+  return prec == DMLMC_C128 ? launch_restrict<double>(h, level, Xf, Xc, k) : launch_restrict<float>(h, level, Xf, Xc, k);
+}
+int dmlmc_prolong_add(dmlmc_hier* h, int level, int prec, const void* Xc, void* Xf, int k) {
+  ENTER(h); CHECK_LEVEL(h, level); CHECK_PREC(prec); CHECK(Xf && Xc && k >= 1, "prolong_add: bad arguments");
+  return prec == DMLMC_C128 ? launch_prolong<double>(h, level, Xc, Xf, k) : launch_prolong<float>(h, level, Xc, Xf, k);
+}
+int dmlmc_coarsest_apply(dmlmc_hier* h, int prec, const void* B, void* X, int k) {
+  ENTER(h); CHECK_PREC(prec); CHECK(B && X && k >= 1, "coarsest_apply: bad arguments");
+  return prec == DMLMC_C128 ? launch_dense<double>(h, B, X, k) : launch_dense<float>(h, B, X, k);
+}
+int dmlmc_smooth(dmlmc_hier* h, int level, int prec, const void* R, void* E, int k) {
+  ENTER(h); CHECK_LEVEL(h, level); CHECK_PREC(prec); CHECK(R && E && k >= 1, "smooth: bad arguments");
+  const size_t mark = h->ws_off;
+  const size_t cnt = (size_t)h->lv[level].n * k;
+  int rc;
+  if (prec == DMLMC_C128) {
+    Cx<double>*t0, *t1; RET(ws_get<Cx<double>>(h, cnt, &t0)); RET(ws_get<Cx<double>>(h, cnt, &t1));
+    rc = smooth<double>(h, level, R, E, true, t0, t1, false, nullptr, k);
+  } else {
+    Cx<float>*t0, *t1; RET(ws_get<Cx<float>>(h, cnt, &t0)); RET(ws_get<Cx<float>>(h, cnt, &t1));
+    rc = smooth<float>(h, level, R, E, true, t0, t1, false, nullptr, k);
+  }
+  h->ws_off = mark;
+  return rc;
+}
+int dmlmc_vcycle(dmlmc_hier* h, int level, int prec, const void* B, void* X, int k) {
+  ENTER(h); CHECK_LEVEL(h, level); CHECK_PREC(prec); CHECK(B && X && k >= 1, "vcycle: bad arguments");
+  return prec == DMLMC_C128 ? vcycle<double>(h, level, B, X, k) : vcycle<float>(h, level, B, X, k);
+}
+int dmlmc_dotc(dmlmc_hier* h, const void* X, const void* Y, int n, int k, void* out_dev) {
+  ENTER(h); CHECK(X && Y && out_dev && n >= 1 && k >= 1, "dotc: bad arguments");
+  const size_t mark = h->ws_off;
+  Z* partial; RET(ws_get<Z>(h, partial_count(n, 1, k), &partial));
+  int rc = multi_dot(h, (const Z*)X, 0, 1, (const Z*)Y, n, k, partial, (Z*)out_dev, 0);
+  h->ws_off = mark;
+  return rc;
+}
+int dmlmc_deflate(dmlmc_hier* h, int level, void* X, int k) {
+  ENTER(h); CHECK_LEVEL(h, level); CHECK(X && k >= 1, "deflate: bad arguments");
+  return deflate(h, level, (Z*)X, k);
+}
+int dmlmc_probe_expand(dmlmc_hier* h, const uint8_t* bits_dev, int n, int k, void* X0) {
+  ENTER(h); CHECK(bits_dev && X0 && n >= 1 && k >= 1, "probe_expand: bad arguments");
+  const size_t nk = (size_t)n * k;
+  probe_expand_kernel<<<nblocks(nk, 256), 256, 0, h->stream>>>(bits_dev, n, k, (Cx<double>*)X0);
+  LAUNCH_CHECK(h);
+  return 0;
+}
+int dmlmc_apply_perm(dmlmc_hier* h, int level, const void* X, void* RHS, int k) {
+  ENTER(h); CHECK_LEVEL(h, level); CHECK(X && RHS && X != RHS && k >= 1, "apply_perm: bad arguments");
+  return apply_perm(h, level, (const Z*)X, (Z*)RHS, k);
+}
+
+size_t dmlmc_workspace_bytes(dmlmc_hier* h, int level, int k, int restart) {
+  if (!h || level < 0 || level >= h->n_levels || k < 1 || restart < 1) return 0;
+  // level_sample: fine solve + (sequentially) coarse solve share the FGMRES arena
+  size_t b = fgmres_bytes(h, level, k, restart);
+  const size_t nk = (size_t)h->lv[level].n * k * sizeof(Z);
+  b += 8 * align_up(nk) + align_up(partial_count(h->lv[level].n, 64, k) * sizeof(Z));
+  b += align_up((size_t)h->lv[level].n * k / 8 + 64);
+  return b + (1 << 20);
+}
+int dmlmc_set_workspace(dmlmc_hier* h, void* ws_dev, size_t bytes) {
+  CHECK(h != nullptr, "NULL handle");
+  h->ws = (char*)ws_dev; h->ws_bytes = bytes; h->ws_off = 0;
+  return 0;
+}
+int dmlmc_set_inner_precision(dmlmc_hier* h, int prec) {
+  CHECK(h != nullptr, "NULL handle"); CHECK_PREC(prec);
+  h->inner_prec = prec;
+  return 0;
+}
+int dmlmc_fgmres(dmlmc_hier* h, int level, const void* B, void* X, int k, double tol, int restart, int maxiter,
+                 int32_t* iters_host, double* relres_host) {
+  ENTER(h); CHECK_LEVEL(h, level); CHECK(B && X && B != X, "fgmres: bad arguments");
+  if (level == h->n_levels - 1) return fail(-1, "fgmres: the coarsest level is solved by dmlmc_coarsest_apply");
+  return fgmres(h, level, (const Z*)B, (Z*)X, k, tol, restart, maxiter, iters_host, relres_host);
+}
+int dmlmc_level_sample(dmlmc_hier* h, int method, int level_f, int level_c, const void* X0, int k, double tol,
+                       int restart, int maxiter, void* e_dev, int32_t* iters_host) {
+  ENTER(h); CHECK(X0 && e_dev && k >= 1, "level_sample: bad arguments");
+  return level_sample(h, method, level_f, level_c, (const Z*)X0, k, tol, restart, maxiter, (Z*)e_dev, iters_host);
+}
+int dmlmc_level_sample_host(dmlmc_hier* h, int method, int level_f, int level_c, const uint8_t* bits_host, int k,
+                            double tol, int restart, int maxiter, double* e_host, int32_t* iters_host) {
+  ENTER(h); CHECK(bits_host && e_host && k >= 1, "level_sample_host: bad arguments");
+  CHECK(level_f >= 0 && level_f < h->n_levels && h->lv[level_f].n > 0, "level_sample_host: bad level");
+  const int n = h->lv[level_f].n;
+  const size_t nbits = (size_t)n * k, nbytes = (nbits + 7) / 8;
+  const size_t mark = h->ws_off;
+  uint8_t* bits_dev; Z* X0; Z* e_dev;
+  RET(ws_get<uint8_t>(h, nbytes, &bits_dev));
+  RET(ws_get<Z>(h, (size_t)n * k, &X0));
+  RET(ws_get<Z>(h, (size_t)k, &e_dev));
+  CU(cudaMemcpyAsync(bits_dev, bits_host, nbytes, cudaMemcpyHostToDevice, h->stream));
+  probe_expand_kernel<<<nblocks(nbits, 256), 256, 0, h->stream>>>(bits_dev, n, k, X0); LAUNCH_CHECK(h);
+  int rc = level_sample(h, method, level_f, level_c, X0, k, tol, restart, maxiter, e_dev, iters_host);
+  if (rc == 0) {
+    cudaError_t e = cudaMemcpyAsync(e_host, e_dev, sizeof(Z) * k, cudaMemcpyDeviceToHost, h->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
+    if (e != cudaSuccess) rc = fail((int)e, std::string("level_sample_host: ") + cudaGetErrorString(e));
+  }
+  h->ws_off = mark;
+  return rc;
+}
+long long dmlmc_launch_count(dmlmc_hier* h) { return h ? h->launches : 0; }
+
+}  // extern "C"

@@ -1,0 +1,271 @@
+// krylov_kernels.cuh -- device side of the batched (one Krylov space per column) FGMRES:
+// column-wise inner products, Gram-Schmidt updates, Givens/Hessenberg bookkeeping and the
+// triangular solves, all complex128 and all on the device (no per-iteration host math).
+// Replaces pyamg.krylov.fgmres as called at multigrid.py:362 and the np.vdot / np.dot
+// call sites of utils.py:224,249,266,336,353.
+#pragma once
+#include "common.cuh"
+
+namespace dmlmc {
+
+typedef Cx<double> Z;   // complex128
+
+__device__ __forceinline__ Z zadd(Z a, Z b) { return cx<double>(a.re + b.re, a.im + b.im); }
+__device__ __forceinline__ Z zsub(Z a, Z b) { return cx<double>(a.re - b.re, a.im - b.im); }
+__device__ __forceinline__ Z zscale(double s, Z a) { return cx<double>(s * a.re, s * a.im); }
+__device__ __forceinline__ double zabs2(Z a) { return a.re * a.re + a.im * a.im; }
+// acc += conj(a) * b
+__device__ __forceinline__ void zfma_conj(Z& acc, Z a, Z b) {
+  acc.re = fma(a.re, b.re, fma(a.im, b.im, acc.re));
+  acc.im = fma(a.re, b.im, fma(-a.im, b.re, acc.im));
+}
+__device__ __forceinline__ void zfma(Z& acc, Z a, Z b) {
+  acc.re = fma(a.re, b.re, fma(-a.im, b.im, acc.re));
+  acc.im = fma(a.re, b.im, fma(a.im, b.re, acc.im));
+}
+
+constexpr int DOT_NI = 8;            // vectors per register tile
+constexpr int DOT_TX = 32, DOT_TY = 8;
+
+// partial[chunk][i][col] = sum_{r in chunk} conj(V_i[r][col]) * W[r][col],  V_i = Vbase + i*vstride
+// grid (ceil(k/32), nchunks), block (32, 8).  Deterministic: fixed row chunking, no atomics, so a
+// column's result does not depend on which batch it is part of.
+__global__ void __launch_bounds__(256)
+multi_dot_kernel(const Z* __restrict__ Vbase, size_t vstride, int nv, const Z* __restrict__ W,
+                 int n, int k, int rows_per_chunk, Z* __restrict__ partial) {
+  __shared__ Z red[DOT_TY][DOT_NI][DOT_TX + 1];
+  const int tx = threadIdx.x, ty = threadIdx.y;
+  const int col = blockIdx.x * DOT_TX + tx;
+  const int r0 = blockIdx.y * rows_per_chunk;
+  const int r1 = min(n, r0 + rows_per_chunk);
+  const bool ok = col < k;
+  for (int i0 = 0; i0 < nv; i0 += DOT_NI) {
+    Z acc[DOT_NI];
+#pragma unroll
+    for (int i = 0; i < DOT_NI; ++i) acc[i] = cx<double>(0.0, 0.0);
+    if (ok) {
+      for (int r = r0 + ty; r < r1; r += DOT_TY) {
+        const size_t off = (size_t)r * k + col;
+        const Z w = ldc_ro<double>(W, off);
+#pragma unroll
+        for (int i = 0; i < DOT_NI; ++i)
+          if (i0 + i < nv) zfma_conj(acc[i], ldc_ro<double>(Vbase, (size_t)(i0 + i) * vstride + off), w);
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < DOT_NI; ++i) red[ty][i][tx] = acc[i];
+    __syncthreads();
+    // thread (tx, ty) reduces vector i = ty over the 8 row lanes
+    Z s = cx<double>(0.0, 0.0);
+#pragma unroll
+    for (int y = 0; y < DOT_TY; ++y) s = zadd(s, red[y][ty][tx]);
+    if (ok && i0 + ty < nv) partial[((size_t)blockIdx.y * nv + (i0 + ty)) * k + col] = s;
+    __syncthreads();
+  }
+}
+
+// out[idx] (+)= sum_chunk partial[chunk*count + idx]
+__global__ void __launch_bounds__(256)
+sum_partials_kernel(const Z* __restrict__ partial, int nchunks, int count, Z* __restrict__ out, int accumulate) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= count) return;
+  Z s = cx<double>(0.0, 0.0);
+  for (int c = 0; c < nchunks; ++c) s = zadd(s, partial[(size_t)c * count + idx]);
+  if (accumulate) s = zadd(s, out[idx]);
+  out[idx] = s;
+}
+
+// W[r][col] += sgn * sum_i h[i][col] * V_i[r][col]
+__global__ void __launch_bounds__(256)
+multi_axpy_kernel(const Z* __restrict__ Vbase, size_t vstride, int nv, const Z* __restrict__ h,
+                  Z* __restrict__ W, size_t nk, int k, double sgn) {
+  const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= nk) return;
+  const int col = (int)(idx % k);
+  Z acc = cx<double>(0.0, 0.0);
+  for (int i = 0; i < nv; ++i) zfma(acc, ldc_ro<double>(h, (size_t)i * k + col), ldc_ro<double>(Vbase, (size_t)i * vstride + idx));
+  Z w = W[idx];
+  w.re = fma(sgn, acc.re, w.re);
+  w.im = fma(sgn, acc.im, w.im);
+  W[idx] = w;
+}
+
+// Out[r][col] = In[r][col] * scale[col]
+__global__ void __launch_bounds__(256)
+col_scale_kernel(const Z* __restrict__ In, const double* __restrict__ scale, Z* __restrict__ Out, size_t nk, int k) {
+  const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= nk) return;
+  const double s = __ldg(scale + (idx % k));
+  Out[idx] = zscale(s, ldc_ro<double>(In, idx));
+}
+
+// deflation with a dense V[n][d] shared by all columns:  C[i][col] = sum_r conj(V[r][i]) X[r][col]
+__global__ void __launch_bounds__(256)
+defl_dot_kernel(const Z* __restrict__ Vd, int d, const Z* __restrict__ X, int n, int k, int rows_per_chunk,
+                Z* __restrict__ partial) {
+  __shared__ Z red[DOT_TY][DOT_NI][DOT_TX + 1];
+  const int tx = threadIdx.x, ty = threadIdx.y;
+  const int col = blockIdx.x * DOT_TX + tx;
+  const int r0 = blockIdx.y * rows_per_chunk;
+  const int r1 = min(n, r0 + rows_per_chunk);
+  const bool ok = col < k;
+  for (int i0 = 0; i0 < d; i0 += DOT_NI) {
+    Z acc[DOT_NI];
+#pragma unroll
+    for (int i = 0; i < DOT_NI; ++i) acc[i] = cx<double>(0.0, 0.0);
+    if (ok) {
+      for (int r = r0 + ty; r < r1; r += DOT_TY) {
+        const Z x = ldc_ro<double>(X, (size_t)r * k + col);
+#pragma unroll
+        for (int i = 0; i < DOT_NI; ++i)
+          if (i0 + i < d) zfma_conj(acc[i], ldc_ro<double>(Vd, (size_t)r * d + i0 + i), x);
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < DOT_NI; ++i) red[ty][i][tx] = acc[i];
+    __syncthreads();
+    Z s = cx<double>(0.0, 0.0);
+#pragma unroll
+    for (int y = 0; y < DOT_TY; ++y) s = zadd(s, red[y][ty][tx]);
+    if (ok && i0 + ty < d) partial[((size_t)blockIdx.y * d + (i0 + ty)) * k + col] = s;
+    __syncthreads();
+  }
+}
+// X[r][col] -= sum_i V[r][i] * C[i][col]
+__global__ void __launch_bounds__(256)
+defl_axpy_kernel(const Z* __restrict__ Vd, int d, const Z* __restrict__ C, Z* __restrict__ X, size_t nk, int k) {
+  const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= nk) return;
+  const int col = (int)(idx % k);
+  const size_t r = idx / k;
+  Z acc = cx<double>(0.0, 0.0);
+  for (int i = 0; i < d; ++i) zfma(acc, ldc_ro<double>(Vd, r * d + i), ldc_ro<double>(C, (size_t)i * k + col));
+  X[idx] = zsub(X[idx], acc);
+}
+
+// ------------------------------------------------------------------------------------------
+// per-column FGMRES state (all arrays column-contiguous)
+struct GmresState {
+  int k, m;            // columns, restart length
+  Z* hsum;             // [(m+1)][k]  Gram-Schmidt coefficients of the current step
+  Z* nrm2;             // [k]         <w,w> after orthogonalisation
+  Z* Rm;               // [m][m][k]   rotated Hessenberg (upper triangular), (i,j) at (j*m+i)*k+col
+  double* cs;          // [m][k]
+  Z* sn;               // [m][k]
+  Z* g;                // [(m+1)][k]
+  Z* y;                // [m][k]
+  double* normb;       // [k]
+  double* scale;       // [k]
+  double* relres;      // [k]
+  int* active;         // [k]
+  int* done;           // [k]
+  int* it_cycle;       // [k]
+  int* it_total;       // [k]
+  int* n_active;       // [1]
+};
+
+// start of a cycle: nrm2 = <r,r>.  first != 0: normb = ||r|| (x0 = 0 so r = b).
+__global__ void __launch_bounds__(256)
+gmres_init_kernel(GmresState s, double tol, int first) {
+  const int col = blockIdx.x * blockDim.x + threadIdx.x;
+  if (col >= s.k) return;
+  const double nr = sqrt(fmax(s.nrm2[col].re, 0.0));
+  if (first) {
+    s.normb[col] = (nr == 0.0) ? 1.0 : nr;
+    s.done[col] = 0;
+    s.it_total[col] = 0;
+  }
+  const double rel = nr / s.normb[col];
+  s.it_cycle[col] = 0;
+  int act = 0;
+  if (!s.done[col]) {
+    s.relres[col] = rel;
+    if (rel < tol || nr == 0.0) s.done[col] = 1; else act = 1;
+  }
+  s.active[col] = act;
+  s.scale[col] = act ? 1.0 / nr : 0.0;
+  s.g[col] = cx<double>(act ? nr : 0.0, 0.0);
+  if (act) atomicAdd(s.n_active, 1);
+}
+
+// after step j: apply the stored rotations to the new Hessenberg column, make the new one,
+// update g and the residual estimate, decide convergence.            (Saad, Alg. 6.9 / pyamg fgmres)
+__global__ void __launch_bounds__(128)
+gmres_step_kernel(GmresState s, int j, double tol) {
+  const int col = blockIdx.x * blockDim.x + threadIdx.x;
+  if (col >= s.k) return;
+  if (!s.active[col]) { s.scale[col] = 0.0; return; }
+  const int k = s.k, m = s.m;
+  const double hn = sqrt(fmax(s.nrm2[col].re, 0.0));
+  Z hi = s.hsum[col];
+  for (int i = 0; i < j; ++i) {
+    const Z hn1 = s.hsum[(size_t)(i + 1) * k + col];
+    const double c = s.cs[(size_t)i * k + col];
+    const Z sn = s.sn[(size_t)i * k + col];
+    // t = c*h_i + s*h_{i+1} ; h_{i+1} = -conj(s)*h_i + c*h_{i+1}
+    Z t = zscale(c, hi); zfma(t, sn, hn1);
+    Z u = zscale(c, hn1);
+    Z ms = cx<double>(-sn.re, sn.im);     // -conj(s)
+    zfma(u, ms, hi);
+    s.Rm[((size_t)j * m + i) * k + col] = t;
+    hi = u;
+  }
+  // hi = h_j (rotated), b = hn (real >= 0)
+  const double aa = sqrt(zabs2(hi));
+  const double den = sqrt(aa * aa + hn * hn);
+  double c; Z sn;
+  if (den == 0.0) { c = 1.0; sn = cx<double>(0.0, 0.0); }
+  else if (aa == 0.0) { c = 0.0; sn = cx<double>(1.0, 0.0); }
+  else { c = aa / den; sn = zscale(hn / (den * aa), hi); }
+  Z rjj = zscale(c, hi);
+  rjj.re += sn.re * hn; rjj.im += sn.im * hn;
+  s.Rm[((size_t)j * m + j) * k + col] = rjj;
+  s.cs[(size_t)j * k + col] = c;
+  s.sn[(size_t)j * k + col] = sn;
+  const Z gj = s.g[(size_t)j * k + col];
+  Z gn = cx<double>(0.0, 0.0);
+  zfma(gn, cx<double>(-sn.re, sn.im), gj);
+  s.g[(size_t)(j + 1) * k + col] = gn;
+  s.g[(size_t)j * k + col] = zscale(c, gj);
+  const double rel = sqrt(zabs2(gn)) / s.normb[col];
+  s.relres[col] = rel;
+  s.it_cycle[col] = j + 1;
+  s.it_total[col] += 1;
+  if (rel < tol) {
+    s.active[col] = 0; s.done[col] = 1; s.scale[col] = 0.0;
+  } else {
+    s.scale[col] = (hn > 0.0) ? 1.0 / hn : 0.0;
+    atomicAdd(s.n_active, 1);
+  }
+}
+
+// y = R^{-1} g for the steps each column actually took; zero beyond
+__global__ void __launch_bounds__(128)
+gmres_solve_kernel(GmresState s, int jmax) {
+  const int col = blockIdx.x * blockDim.x + threadIdx.x;
+  if (col >= s.k) return;
+  const int k = s.k, m = s.m;
+  const int mc = s.it_cycle[col];
+  for (int i = mc; i < jmax; ++i) s.y[(size_t)i * k + col] = cx<double>(0.0, 0.0);
+  for (int i = mc - 1; i >= 0; --i) {
+    Z acc = s.g[(size_t)i * k + col];
+    for (int l = i + 1; l < mc; ++l) {
+      const Z r = s.Rm[((size_t)l * m + i) * k + col];
+      const Z yl = s.y[(size_t)l * k + col];
+      zfma(acc, cx<double>(-r.re, -r.im), yl);
+    }
+    const Z d = s.Rm[((size_t)i * m + i) * k + col];
+    const double d2 = zabs2(d);
+    Z yi = cx<double>(0.0, 0.0);
+    if (d2 > 0.0) { zfma_conj(yi, d, acc); yi = zscale(1.0 / d2, yi); }   // acc / d
+    s.y[(size_t)i * k + col] = yi;
+  }
+}
+
+// e[col] = a[col] - b[col]
+__global__ void zsub_kernel(const Z* a, const Z* b, Z* e, int k) {
+  const int col = blockIdx.x * blockDim.x + threadIdx.x;
+  if (col < k) e[col] = zsub(a[col], b[col]);
+}
+
+}  // namespace dmlmc

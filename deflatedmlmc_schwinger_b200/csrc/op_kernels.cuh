@@ -1,0 +1,283 @@
+// op_kernels.cuh -- operator kernels on column batches X[n][k] (k contiguous).
+//   stencil_kernel : level-0 Wilson-Dirac operator in link form      (multigrid.py:552-557 on A_0)
+//   bsr_kernel     : coarse operators A_l = R A P as padded block rows (multigrid.py:276, :552-557)
+//   restrict/prolong kernels : R_l = P_l^H and P_l                   (multigrid.py:406,429)
+//   dense_kernel   : coarsest_inv * B                                (multigrid.py:413-416)
+//   perm_kernel    : Bblock_perm * roll(x, +shift)                   (utils.py:232,288-290)
+//   probe_expand_kernel : packed MT19937 bits -> +-1 complex128      (utils.py:213-216)
+// All of them are HBM-streaming kernels: one thread owns one 16-byte pack of columns of one
+// lattice site / block row, so a warp reads and writes 512 contiguous bytes per row.
+#pragma once
+#include "common.cuh"
+
+namespace dmlmc {
+
+// what the operator kernels write
+enum { M_AX = 0,            // Y = A X
+       M_RES = 1,           // Y = B - A X
+       M_SMOOTH_FIRST = 2,  // Y = X - w A X ; E  = w X      (first Richardson step, e starts at 0)
+       M_SMOOTH = 3 };      // Y = X - w A X ; E += w X
+
+template <typename T> struct StencilDev {
+  int LX, LT;
+  const Cx<T>* Ut;   // [LX*LT]  U_t(x,t)
+  const Cx<T>* Ux;   // [LX*LT]  U_x(x,t)
+  Cx<T> diag;        // 4 + m
+};
+
+template <typename T, int NC, int MODE>
+__device__ __forceinline__ void op_epilogue(const Pack<T, NC>& ax, const Pack<T, NC>& xin, size_t idx,
+                                            const Pack<T, NC>* __restrict__ B, Pack<T, NC>* __restrict__ Y,
+                                            Pack<T, NC>* __restrict__ E, Cx<T> w) {
+  if constexpr (MODE == M_AX) {
+    Y[idx] = ax;
+  } else if constexpr (MODE == M_RES) {
+    Y[idx] = psub<T, NC>(ldp_ro<T, NC>(B, idx), ax);
+  } else {
+    Pack<T, NC> rn = xin;
+    pfms<T, NC>(rn, w, ax);
+    Y[idx] = rn;
+    if constexpr (MODE == M_SMOOTH_FIRST) {
+      E[idx] = pscale<T, NC>(w, xin);
+    } else {
+      Pack<T, NC> e = E[idx];
+      pfma<T, NC>(e, w, xin);
+      E[idx] = e;
+    }
+  }
+}
+
+// A psi(x) = diag psi(x) - [ (1-s1) Ut(x) psi(x+t) + (1+s1) Ut(x-t)^* psi(x-t)
+//                          + (1-s2) Ux(x) psi(x+x) + (1+s2) Ux(x-x)^* psi(x-x) ]
+// with the spin projections (1-s1)phi = (a,-a), a = phi0-phi1; (1+s1)phi = (b,b), b = phi0+phi1;
+// (1-s2)phi = (c,-ic), c = phi0+i phi1; (1+s2)phi = (d, id), d = phi0-i phi1.
+template <typename T, int NC, int MODE>
+__global__ void __launch_bounds__(256)
+stencil_kernel(StencilDev<T> op, const Pack<T, NC>* __restrict__ X, const Pack<T, NC>* __restrict__ B,
+               Pack<T, NC>* __restrict__ Y, Pack<T, NC>* __restrict__ E, Cx<T> w, int kp) {
+  const int LX = op.LX, LT = op.LT, V = LX * LT;
+  const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const int site = (int)(gid / kp);
+  const int cp = (int)(gid - (long long)site * kp);
+  if (site >= V) return;
+  const int x = site / LT, t = site - x * LT;
+  const int tp = (t + 1 == LT) ? 0 : t + 1, tm = (t == 0) ? LT - 1 : t - 1;
+  const int xp = (x + 1 == LX) ? 0 : x + 1, xm = (x == 0) ? LX - 1 : x - 1;
+  const int s_tp = x * LT + tp, s_tm = x * LT + tm, s_xp = xp * LT + t, s_xm = xm * LT + t;
+  const size_t kpz = (size_t)kp, Vz = (size_t)V;
+
+  typedef Pack<T, NC> P;
+  const P c0 = ldp_ro<T, NC>(X, (size_t)site * kpz + cp),  c1 = ldp_ro<T, NC>(X, (Vz + site) * kpz + cp);
+  const P f0 = ldp_ro<T, NC>(X, (size_t)s_tp * kpz + cp),  f1 = ldp_ro<T, NC>(X, (Vz + s_tp) * kpz + cp);
+  const P b0 = ldp_ro<T, NC>(X, (size_t)s_tm * kpz + cp),  b1 = ldp_ro<T, NC>(X, (Vz + s_tm) * kpz + cp);
+  const P r0 = ldp_ro<T, NC>(X, (size_t)s_xp * kpz + cp),  r1 = ldp_ro<T, NC>(X, (Vz + s_xp) * kpz + cp);
+  const P l0 = ldp_ro<T, NC>(X, (size_t)s_xm * kpz + cp),  l1 = ldp_ro<T, NC>(X, (Vz + s_xm) * kpz + cp);
+  const Cx<T> ut = ldc_ro<T>(op.Ut, site), utb = cconj(ldc_ro<T>(op.Ut, s_tm));
+  const Cx<T> ux = ldc_ro<T>(op.Ux, site), uxb = cconj(ldc_ro<T>(op.Ux, s_xm));
+
+  const P a = psub<T, NC>(f0, f1);                       // (1-s1) psi(x+t) = (a,-a)
+  const P b = padd<T, NC>(b0, b1);                       // (1+s1) psi(x-t) = (b, b)
+  const P c = padd<T, NC>(r0, pmul_i<T, NC>(r1));        // (1-s2) psi(x+x) = (c,-ic)
+  const P d = psub<T, NC>(l0, pmul_i<T, NC>(l1));        // (1+s2) psi(x-x) = (d, id)
+  const P ua = pscale<T, NC>(ut, a), ub = pscale<T, NC>(utb, b);
+  const P uc = pscale<T, NC>(ux, c), ud = pscale<T, NC>(uxb, d);
+
+  P y0 = pscale<T, NC>(op.diag, c0), y1 = pscale<T, NC>(op.diag, c1);
+  y0 = psub<T, NC>(y0, padd<T, NC>(padd<T, NC>(ua, ub), padd<T, NC>(uc, ud)));
+  // spin 1: -ua + ub - i uc + i ud
+  y1 = psub<T, NC>(y1, padd<T, NC>(psub<T, NC>(ub, ua), pmul_i<T, NC>(psub<T, NC>(ud, uc))));
+
+  op_epilogue<T, NC, MODE>(y0, c0, (size_t)site * kpz + cp, B, Y, E, w);
+  op_epilogue<T, NC, MODE>(y1, c1, (Vz + site) * kpz + cp, B, Y, E, w);
+}
+
+// ------------------------------------------------------------------------------------------
+template <typename T> struct BsrDev {
+  int nb, bpr;
+  const int* col;      // [nb][bpr] block column or -1
+  const Cx<T>* vals;   // [nb][bpr][BS][BS]
+};
+
+template <typename T, int NC, int BS, int MODE>
+__global__ void __launch_bounds__(128)
+bsr_kernel(BsrDev<T> op, const Pack<T, NC>* __restrict__ X, const Pack<T, NC>* __restrict__ B,
+           Pack<T, NC>* __restrict__ Y, Pack<T, NC>* __restrict__ E, Cx<T> w, int kp) {
+  const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const int I = (int)(gid / kp);
+  const int cp = (int)(gid - (long long)I * kp);
+  if (I >= op.nb) return;
+  const size_t kpz = (size_t)kp;
+  typedef Pack<T, NC> P;
+  P acc[BS];
+#pragma unroll
+  for (int r = 0; r < BS; ++r) acc[r] = pzero<T, NC>();
+  for (int blk = 0; blk < op.bpr; ++blk) {
+    const int J = __ldg(op.col + (size_t)I * op.bpr + blk);
+    if (J < 0) continue;
+    P xv[BS];
+#pragma unroll
+    for (int c = 0; c < BS; ++c) xv[c] = ldp_ro<T, NC>(X, ((size_t)J * BS + c) * kpz + cp);
+    const Cx<T>* vb = op.vals + ((size_t)I * op.bpr + blk) * (BS * BS);
+#pragma unroll
+    for (int r = 0; r < BS; ++r) {
+#pragma unroll
+      for (int c = 0; c < BS; ++c) pfma<T, NC>(acc[r], ldc_ro<T>(vb, r * BS + c), xv[c]);
+    }
+  }
+#pragma unroll
+  for (int r = 0; r < BS; ++r) {
+    const size_t idx = ((size_t)I * BS + r) * kpz + cp;
+    P xin = pzero<T, NC>();
+    if constexpr (MODE == M_SMOOTH || MODE == M_SMOOTH_FIRST) xin = ldp_ro<T, NC>(X, idx);
+    op_epilogue<T, NC, MODE>(acc[r], xin, idx, B, Y, E, w);
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// aggregation transfer operators.  Row r of P_l: aggregate j = r / aggr, half = ((r % aggr) % dofi) >= h,
+// columns (2j + half)*NV + [0,NV).                                   (multigrid.py:203-227)
+template <typename T> struct TransferDev {
+  int n_f, n_c, aggr, dofi, h, nvec;
+  const Cx<T>* pv;     // [n_f][nvec]
+};
+
+template <typename T, int NC, int NV>
+__global__ void __launch_bounds__(128)
+restrict_kernel(TransferDev<T> tr, const Pack<T, NC>* __restrict__ Xf, Pack<T, NC>* __restrict__ Xc, int kp) {
+  const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const int g = (int)(gid / kp);                   // (aggregate, half)
+  const int cp = (int)(gid - (long long)g * kp);
+  if (g >= tr.n_c / NV) return;
+  const int j = g >> 1, half = g & 1;
+  const size_t kpz = (size_t)kp;
+  typedef Pack<T, NC> P;
+  P acc[NV];
+#pragma unroll
+  for (int v = 0; v < NV; ++v) acc[v] = pzero<T, NC>();
+  const int nw = tr.aggr / tr.dofi;
+  for (int wq = 0; wq < nw; ++wq) {
+    for (int z = 0; z < tr.h; ++z) {
+      const int r = j * tr.aggr + wq * tr.dofi + half * tr.h + z;
+      const P x = ldp_ro<T, NC>(Xf, (size_t)r * kpz + cp);
+#pragma unroll
+      for (int v = 0; v < NV; ++v) pfma_conj<T, NC>(acc[v], ldc_ro<T>(tr.pv, (size_t)r * NV + v), x);
+    }
+  }
+#pragma unroll
+  for (int v = 0; v < NV; ++v) Xc[((size_t)g * NV + v) * kpz + cp] = acc[v];
+}
+
+template <typename T, int NC, int NV>
+__global__ void __launch_bounds__(256)
+prolong_add_kernel(TransferDev<T> tr, const Pack<T, NC>* __restrict__ Xc, Pack<T, NC>* __restrict__ Xf, int kp) {
+  const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const int r = (int)(gid / kp);
+  const int cp = (int)(gid - (long long)r * kp);
+  if (r >= tr.n_f) return;
+  const int j = r / tr.aggr;
+  const int q = (r - j * tr.aggr) % tr.dofi;
+  const int g = 2 * j + (q >= tr.h ? 1 : 0);
+  const size_t kpz = (size_t)kp;
+  typedef Pack<T, NC> P;
+  P acc = Xf[(size_t)r * kpz + cp];
+#pragma unroll
+  for (int v = 0; v < NV; ++v)
+    pfma<T, NC>(acc, ldc_ro<T>(tr.pv, (size_t)r * NV + v), ldp_ro<T, NC>(Xc, ((size_t)g * NV + v) * kpz + cp));
+  Xf[(size_t)r * kpz + cp] = acc;
+}
+
+// ------------------------------------------------------------------------------------------
+// X[n][k] = M[n][n] B[n][k], M row-major.  32x(32 packs) output tile per CTA, 32-deep k-chunks
+// staged in shared memory; thread (tx,ty) owns rows ty, ty+8, ty+16, ty+24 of pack column tx.
+template <typename T, int NC>
+__global__ void __launch_bounds__(256)
+dense_kernel(const Cx<T>* __restrict__ M, int n, const Pack<T, NC>* __restrict__ B, Pack<T, NC>* __restrict__ X, int kp) {
+  __shared__ Cx<T> Ms[32][33];
+  __shared__ Pack<T, NC> Bs[32][32];
+  const int tx = threadIdx.x, ty = threadIdx.y;
+  const int cp = blockIdx.x * 32 + tx;
+  const int i0 = blockIdx.y * 32;
+  typedef Pack<T, NC> P;
+  P acc[4];
+#pragma unroll
+  for (int r = 0; r < 4; ++r) acc[r] = pzero<T, NC>();
+  for (int j0 = 0; j0 < n; j0 += 32) {
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+      const int i = i0 + ty + 8 * r, j = j0 + tx;
+      Ms[ty + 8 * r][tx] = (i < n && j < n) ? M[(size_t)i * n + j] : cx<T>(T(0), T(0));
+      const int jr = j0 + ty + 8 * r;
+      Bs[ty + 8 * r][tx] = (jr < n && cp < kp) ? B[(size_t)jr * kp + cp] : pzero<T, NC>();
+    }
+    __syncthreads();
+#pragma unroll 8
+    for (int jj = 0; jj < 32; ++jj) {
+      const P b = Bs[jj][tx];
+#pragma unroll
+      for (int r = 0; r < 4; ++r) pfma<T, NC>(acc[r], Ms[ty + 8 * r][jj], b);
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int r = 0; r < 4; ++r) {
+    const int i = i0 + ty + 8 * r;
+    if (i < n && cp < kp) X[(size_t)i * kp + cp] = acc[r];
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// RHS[i] = sum_j vals[i][j] X[(cols[i][j] - shift) mod n]   (nnz == 0: RHS[i] = X[(i - shift) mod n])
+template <typename T, int NC>
+__global__ void __launch_bounds__(256)
+perm_kernel(int n, int shift, int nnz, const int* __restrict__ cols, const Cx<T>* __restrict__ vals,
+            const Pack<T, NC>* __restrict__ X, Pack<T, NC>* __restrict__ Y, int kp) {
+  const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const int i = (int)(gid / kp);
+  const int cp = (int)(gid - (long long)i * kp);
+  if (i >= n) return;
+  const size_t kpz = (size_t)kp;
+  if (nnz == 0) {
+    int src = i - shift; if (src < 0) src += n;
+    Y[(size_t)i * kpz + cp] = ldp_ro<T, NC>(X, (size_t)src * kpz + cp);
+    return;
+  }
+  Pack<T, NC> acc = pzero<T, NC>();
+  for (int j = 0; j < nnz; ++j) {
+    const int c = __ldg(cols + (size_t)i * nnz + j);
+    if (c < 0) continue;
+    int src = c - shift; if (src < 0) src += n;
+    pfma<T, NC>(acc, ldc_ro<T>(vals, (size_t)i * nnz + j), ldp_ro<T, NC>(X, (size_t)src * kpz + cp));
+  }
+  Y[(size_t)i * kpz + cp] = acc;
+}
+
+// element i of probe p = 2*bit(p*n+i) - 1                       (utils.py:213-216)
+__global__ void __launch_bounds__(256)
+probe_expand_kernel(const uint8_t* __restrict__ bits, int n, int k, Cx<double>* __restrict__ X0) {
+  const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const int i = (int)(gid / k);
+  const int p = (int)(gid - (long long)i * k);
+  if (i >= n) return;
+  const long long j = (long long)p * n + i;
+  const int bit = (bits[j >> 3] >> (j & 7)) & 1;
+  X0[(size_t)i * k + p] = cx<double>(bit ? 1.0 : -1.0, 0.0);
+}
+
+__global__ void __launch_bounds__(256) cvt_d2f_kernel(const double* __restrict__ in, float* __restrict__ out, size_t n) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  for (; i < n; i += stride) {   // n counts double2 elements
+    double2 v = reinterpret_cast<const double2*>(in)[i];
+    reinterpret_cast<float2*>(out)[i] = make_float2((float)v.x, (float)v.y);
+  }
+}
+__global__ void __launch_bounds__(256) cvt_f2d_kernel(const float* __restrict__ in, double* __restrict__ out, size_t n) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  for (; i < n; i += stride) {
+    float2 v = reinterpret_cast<const float2*>(in)[i];
+    reinterpret_cast<double2*>(out)[i] = make_double2((double)v.x, (double)v.y);
+  }
+}
+
+}  // namespace dmlmc

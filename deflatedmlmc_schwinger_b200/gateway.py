@@ -1,0 +1,97 @@
+"""Drop-in for the reference's gateway.py: the experiment registry G101/G102/G201/G202
+(gateway.py:10-59) and the parameter sets (set_params, gateway.py:63-169).
+
+The shipped 16^2 set of the reference is stale (missing keys; dof=[2,2,2] gives an empty
+prolongator and a singular coarsest matrix).  Here it carries the missing
+keys and the working dof=[2,4,4] / aggrs=[4,4]; the 128^2 set is verbatim."""
+import numpy as np
+
+from .examples import EXAMPLE_001, EXAMPLE_002
+
+
+def G101():
+    params = set_params('schwinger16')
+    params['function_tol'] = 1e-12
+    return EXAMPLE_001(params)
+
+
+def G201():
+    params = set_params('schwinger16')
+    params['function_tol'] = 1e-12
+    return EXAMPLE_002(params)
+
+
+def G102():
+    params = set_params('schwinger128')
+    params['function_tol'] = 1e-12
+    return EXAMPLE_001(params)
+
+
+def G202():
+    params = set_params('schwinger128')
+    params['function_tol'] = 1e-12
+    return EXAMPLE_002(params)
+
+
+def set_params(example_name):
+    if example_name == 'schwinger16':
+        np.random.seed(51234)
+        params = dict()
+        matrix_params = dict()
+        params['trace_tol'] = 1.0e-2
+        params['max_nr_levels'] = 3
+        params['coarsest_level_directly'] = True
+        params['accuracy_mg_eigvs'] = 'low'
+        params['nr_deflat_vctrs'] = 64
+        params['mlmc_deflat_vctrs'] = [16, 16]
+        params['mlmc_levels_to_skip'] = []
+        matrix_params['mass'] = -1.00690114 * 0.99
+        params['aggrs'] = [2 * 2, 2 * 2]
+        params['dof'] = [2, 4, 4]
+        # keys missing from the reference's 16^2 set (KeyError at utils.py:86,112)
+        params['check_quality_MG'] = False
+        params['test_vectors_type'] = 'EVs'
+        params['defl_type'] = "exact"
+        params['defl_eigvs_tol_Hutch'] = 1.0e-9
+        params['defl_eigvs_tol_MLMC'] = 1.0e-1
+        params['diff_lev_op_tol'] = 1.0e-3
+        params['use_permuted'] = False
+        params['latt_dims'] = [16, 16]
+        params['x_displacement'] = 2
+        matrix_params['problem_name'] = 'schwinger'
+        params['matrix'] = 'schwinger16.mat'
+        params['matrix_params'] = matrix_params
+        return params
+
+    elif example_name == 'schwinger128':
+        # for m0 = -0.1320, permuted = True, x_displacement = 2 the <exact> trace is
+        # -8.748242701374695+50.215154098005584j                       (gateway.py:100-104)
+        np.random.seed(51234)
+        params = dict()
+        matrix_params = dict()
+        params['trace_tol'] = 1.0e-2
+        params['aggrs'] = [4 * 4, 2 * 2, 2 * 2]
+        params['dof'] = [2, 8, 8, 8]
+        params['max_nr_levels'] = 4
+        params['coarsest_level_directly'] = True
+        params['accuracy_mg_eigvs'] = 'high'
+        params['check_quality_MG'] = False
+        params['test_vectors_type'] = 'EVs'
+        params['mlmc_levels_to_skip'] = [1]
+        params['nr_deflat_vctrs'] = 8
+        params['mlmc_deflat_vctrs'] = [0, 0, 0]
+        params['defl_type'] = "exact"
+        params['defl_eigvs_tol_Hutch'] = 1.0e-9
+        params['defl_eigvs_tol_MLMC'] = 1.0e-1
+        params['diff_lev_op_tol'] = 1.0e-3
+        matrix_params['mass'] = -0.1320
+        params['use_permuted'] = True
+        params['latt_dims'] = [128, 128]
+        params['x_displacement'] = 2
+        matrix_params['problem_name'] = 'schwinger'
+        params['matrix'] = 'schwinger128.mat'
+        params['matrix_params'] = matrix_params
+        return params
+
+    else:
+        raise Exception("Non-existent option for example type.")

@@ -1,0 +1,398 @@
+"""Drop-in for the reference's multigrid.py: class MG with the same attributes and methods
+(setup / solve / one_mg_step / diff_op / diff_op_Q / matvec), whose solve path runs on the
+GPU through libdmlmc_sm100.so (batched FGMRES + V-cycle, see csrc/dmlmc.cu).
+
+What stays on the host, once per hierarchy: the test-vector eigensolve (scipy eigs exactly as
+multigrid.py:174; SURVEY.md 8f "next"), the aggregation prolongator (closed-form index maps of
+multigrid.py:192-227, bit-exact; per-aggregate classical Gram-Schmidt of :232-259 done sparse,
+never through the dense n_l x n_{l+1} array of :200), R = P^H, the Galerkin products and the
+dense coarsest inverse (:342-344).  The results are uploaded once and every solve is on device.
+
+The smoother is NOT the reference's lgmres(maxiter=2) (multigrid.py:393-394): FGMRES is
+flexible and parity is on the converged solution, so the V-cycle uses a
+reduction-free fixed polynomial of A (Leja-ordered harmonic-Ritz roots of a degree-`smoother_degree`
+GMRES polynomial computed at setup), applied as fused operator+update Richardson steps.
+"""
+import numpy as np
+from scipy.sparse import csr_matrix, identity, diags
+from scipy.sparse.linalg import eigs
+
+from .utils import CustomTimer
+from . import lattice
+from . import _lib
+
+
+class LevelML:
+    """multigrid.py:26-37"""
+    R = 0
+    P = 0
+    A = 0
+    Q = 0
+    Pperm = 0
+    perm_shift = 0
+    Bblock_perm = 0
+    g3 = 0
+
+
+class SimpleML:
+    """multigrid.py:39-48"""
+    def __init__(self):
+        self.levels = []
+
+    def __str__(self):
+        out = ""
+        for idx, level in enumerate(self.levels[:-1]):
+            out += "Level: " + str(idx) + "\n"
+            out += "\tsize(R) = " + str(level.R.shape) + "\n"
+            out += "\tsize(P) = " + str(level.P.shape) + "\n"
+            out += "\tsize(A) = " + str(level.A.shape) + "\n"
+        return out
+
+
+# ------------------------------------------------------------------------------------------
+# host helpers of the setup
+
+def aggregation_maps(n, aggr_size, dofi, nvec):
+    """Closed-form structure of P_l (multigrid.py:203-227): for fine row r returns
+    (half[r], first_col[r]) with its nvec entries in columns first_col[r] + [0, nvec)."""
+    r = np.arange(n)
+    j = r // aggr_size
+    q = (r % aggr_size) % dofi
+    half = (q >= dofi // 2).astype(np.int64)
+    return half, (2 * j + half) * nvec
+
+
+def build_prolongator_values(eig_vecs, aggr_size, dofi, nvec):
+    """Per-(aggregate, half) classical Gram-Schmidt (multigrid.py:232-259): the projections of column k
+    on the already orthonormalised columns w<k are all taken from the unmodified column, subtracted in
+    order, then the column is normalised.  The inner products run over the full aggregate column
+    (the other half's rows are zero) with np.vdot, as in the reference, so that the values are
+    bit-identical to the reference's for the same test vectors.  Returns pvals[n][nvec]."""
+    n = eig_vecs.shape[0]
+    na = n // aggr_size
+    h = dofi // 2
+    nw = aggr_size // dofi
+    rel = [(np.arange(nw)[:, None] * dofi + np.arange(h)[None, :]).ravel() + half * h for half in (0, 1)]
+    pv = np.zeros((n, nvec), dtype=np.complex128)
+    ev = np.asarray(eig_vecs)
+    sqrt = np.sqrt
+    for j in range(na):
+        base = j * aggr_size
+        blk = np.zeros((aggr_size, 2 * nvec), dtype=np.complex128)
+        blk[rel[0], :nvec] = ev[base + rel[0], :nvec]
+        blk[rel[1], nvec:] = ev[base + rel[1], :nvec]
+        for off in (0, nvec):
+            for k in range(nvec):
+                col = blk[:, off + k]
+                rs = [np.vdot(blk[:, off + w], col) for w in range(k)]
+                for w in range(k):
+                    col -= rs[w] * blk[:, off + w]
+                col /= sqrt(np.vdot(col, col).real)
+        pv[base + rel[0], :] = blk[rel[0], :nvec]
+        pv[base + rel[1], :] = blk[rel[1], nvec:]
+    return pv
+
+
+def prolongator_csr(pvals, aggr_size, dofi, nvec):
+    n = pvals.shape[0]
+    _, first = aggregation_maps(n, aggr_size, dofi, nvec)
+    indices = (first[:, None] + np.arange(nvec)[None, :]).ravel()
+    indptr = np.arange(n + 1) * nvec
+    n_c = (n // aggr_size) * 2 * nvec
+    return csr_matrix((pvals.ravel(), indices, indptr), shape=(n, n_c))
+
+
+def harmonic_ritz_inv_roots(A, degree, seed=7):
+    """Inverse roots 1/theta_i of the degree-`degree` GMRES residual polynomial of A for a fixed
+    random vector (harmonic Ritz values of an Arnoldi run), in Leja order for stability."""
+    n = A.shape[0]
+    degree = int(min(degree, n - 1))
+    rs = np.random.RandomState(seed)
+    b = rs.standard_normal(n) + 1j * rs.standard_normal(n)
+    b /= np.linalg.norm(b)
+    V = np.zeros((degree + 1, n), dtype=np.complex128)
+    H = np.zeros((degree + 1, degree), dtype=np.complex128)
+    V[0] = b
+    for j in range(degree):
+        w = A @ V[j]
+        for _ in range(2):
+            hh = np.conj(V[:j + 1]) @ w
+            H[:j + 1, j] += hh
+            w = w - hh @ V[:j + 1]
+        H[j + 1, j] = np.linalg.norm(w)
+        V[j + 1] = w / H[j + 1, j]
+    Hm = H[:degree, :degree]
+    em = np.zeros(degree)
+    em[-1] = 1.0
+    f = np.linalg.solve(Hm.conj().T, em)
+    theta = list(np.linalg.eigvals(Hm + (abs(H[degree, degree - 1]) ** 2) * np.outer(f, em)))
+    out = [max(theta, key=abs)]
+    theta.remove(out[0])
+    while theta:
+        arr = np.array(out)
+        nxt = max(theta, key=lambda t: np.sum(np.log(np.abs(t - arr) + 1e-300)))
+        out.append(nxt)
+        theta.remove(nxt)
+    return 1.0 / np.array(out, dtype=np.complex128)
+
+
+def bsr_padded(A, bs):
+    """scipy matrix -> (colidx[nb][bpr] with -1 padding, vals[nb][bpr][bs][bs])."""
+    B = csr_matrix(A).tobsr(blocksize=(bs, bs))
+    B.sort_indices()
+    nb = B.shape[0] // bs
+    counts = np.diff(B.indptr)
+    bpr = int(counts.max())
+    col = -np.ones((nb, bpr), dtype=np.int32)
+    vals = np.zeros((nb, bpr, bs, bs), dtype=np.complex128)
+    rowid = np.repeat(np.arange(nb), counts)
+    pos = np.arange(B.indices.shape[0]) - np.repeat(B.indptr[:-1], counts)
+    col[rowid, pos] = B.indices
+    vals[rowid, pos] = B.data
+    return col, vals
+
+
+def ell_padded(M):
+    """scipy matrix -> (cols[n][w] with -1 padding, vals[n][w])."""
+    M = csr_matrix(M)
+    M.sort_indices()
+    n = M.shape[0]
+    counts = np.diff(M.indptr)
+    w = int(max(counts.max(), 1))
+    cols = -np.ones((n, w), dtype=np.int32)
+    vals = np.zeros((n, w), dtype=np.complex128)
+    rowid = np.repeat(np.arange(n), counts)
+    pos = np.arange(M.indices.shape[0]) - np.repeat(M.indptr[:-1], counts)
+    cols[rowid, pos] = M.indices
+    vals[rowid, pos] = M.data
+    return cols, vals
+
+
+# ------------------------------------------------------------------------------------------
+
+class MG:
+    """Same public surface as the reference's MG (multigrid.py:56-557)."""
+
+    def __init__(self, A, smooth_iters=2, smoother_degree=32, restart=40, inner_precision="c64",
+                 device=None):
+        self.level_nr = 0
+        self.ml = []
+        self.A = A
+        self.x = []
+        self.num_iters = 0
+        self.total_levels = 0
+        self.coarsest_iters = 0
+        self.coarsest_iters_tot = 0
+        self.coarsest_iters_avg = 0
+        self.nr_calls = 0
+        self.smooth_iters = smooth_iters
+        self.coarsest_lev_iters = [0, 0, 0, 0, 0, 0, 0, 0, 0, 0]
+        self.level_for_diff_op = 0
+        self.solve_tol = 1.0e-1
+        self.coarsest_inv = []
+        self.timer = CustomTimer()
+        self.skip_level = False
+        # B200 specifics
+        self.smoother_degree = smoother_degree
+        self.restart = restart
+        self.inner_precision = inner_precision
+        self.device = device
+        self.dev = None                      # _lib.Hierarchy
+        self.test_vectors = []
+        self.level_shapes = []
+
+    # ---- multigrid.py:100-344 ---------------------------------------------------------------
+    def setup(self, dof=[2, 8, 8], aggrs=[2 * 2, 2 * 2], max_levels=3, dim=2, acc_eigvs='low',
+              sys_type='schwinger', params=None, test_vectors=None):
+        if params is None:
+            params = {}
+        use_permuted = bool(params.get('use_permuted', False))
+        tv_type = params.get('test_vectors_type', 'EVs')
+        if tv_type != "EVs":
+            raise Exception("only test_vectors_type='EVs' is supported (LSVs/RSVs are disabled in the reference set)")
+        if test_vectors is None:
+            test_vectors = params.get('test_vectors', None)
+
+        Al = self.A.copy()
+        ml = SimpleML()
+        ml.levels.append(LevelML())
+        ml.levels[0].A = Al.copy()
+        self.test_vectors = []
+        self._transfer_meta = []
+
+        for i in range(max_levels - 1):
+            dofi = dof[i] if i == 0 else int(dof[i] / 2)
+            dofip1 = int(dof[i + 1] / 2)
+            n = Al.shape[0]
+            diag_g3 = np.ones(n, dtype=Al.dtype)
+            diag_g3[int(n / 2):] = -1.0
+            ml.levels[i].g3 = diags([diag_g3], [0])
+
+            if use_permuted and i == 0:
+                nt = params['latt_dims'][0]
+                mat_disp = nt * 2 * params['x_displacement']
+                ml.levels[0].perm_shift = mat_disp
+                ml.levels[0].Pperm = diags([np.ones(n - mat_disp), np.ones(mat_disp)],
+                                           [-mat_disp, n - mat_disp]).transpose()
+                ml.levels[0].Bblock_perm = identity(n, dtype=Al.dtype)
+
+            if acc_eigvs == 'low':
+                tolx, ncvx = 1.0e-3, dofip1 + 2
+            elif acc_eigvs == 'high':
+                tolx, ncvx = 1.0e-9, None
+            else:
+                raise Exception("<accuracy_mg_eigvs> does not have a possible value.")
+
+            if test_vectors is not None:
+                eig_vecs = np.asarray(test_vectors[i])
+            else:
+                _, eig_vecs = eigs(Al, k=dofip1, which='LM', tol=tolx, maxiter=1000000, sigma=0.0, ncv=ncvx)
+            self.test_vectors.append(eig_vecs)
+
+            aggr_size = aggrs[i] * dofi if i == 0 else aggrs[i] * dofi * 2
+            if dofi < 2 or dofi % 2 or aggr_size % dofi or n % aggr_size or dofip1 < 1:
+                raise Exception("inconsistent dof/aggrs for level " + str(i))
+            pvals = build_prolongator_values(eig_vecs, aggr_size, dofi, dofip1)
+            Pl = prolongator_csr(pvals, aggr_size, dofi, dofip1)
+            self._transfer_meta.append((aggr_size, dofi, dofip1, pvals))
+            ml.levels[i].P = Pl
+            Rl = Pl.conjugate().transpose().tocsr()
+            ml.levels[i].R = Rl
+            Al = (Rl * Al * Pl).tocsr()
+            ml.levels.append(LevelML())
+            ml.levels[i + 1].A = Al.copy()
+
+            if use_permuted:
+                mat_disp = int((ml.levels[i].perm_shift / (dof[i] * aggrs[i])) * dof[i + 1])
+                ml.levels[i + 1].perm_shift = mat_disp
+                nc = Pl.shape[1]
+                ml.levels[i + 1].Pperm = diags([np.ones(nc - mat_disp), np.ones(mat_disp)],
+                                               [-mat_disp, nc - mat_disp]).transpose()
+                Bl = ml.levels[i].Pperm.transpose().conjugate() * (Pl * ml.levels[i + 1].Pperm)
+                Bl = (Rl * ml.levels[i].Bblock_perm) * Bl
+                ml.levels[i + 1].Bblock_perm = Bl
+
+        self.ml = ml
+        self.coarsest_inv = np.linalg.inv(np.asarray(ml.levels[-1].A.todense()))
+        self.level_shapes = [l.A.shape[0] for l in ml.levels]
+        self._upload(params, use_permuted)
+
+    def _upload(self, params, use_permuted):
+        """Re-lay out the hierarchy for the device kernels and copy it to the GPU once."""
+        lv = self.ml.levels
+        nl = len(lv)
+        dev = _lib.Hierarchy(nl, self.device)
+        # level 0: link form if A is a Wilson-Dirac stencil, else generic padded rows (bs = 1)
+        A0 = lv[0].A
+        n0 = A0.shape[0]
+        dims = params.get('latt_dims', None)
+        if dims is None:
+            L = int(round(np.sqrt(n0 / 2)))
+            dims = [L, L]
+        try:
+            links, diag = lattice.links_from_matrix(A0, dims[1] if len(dims) > 1 else dims[0], dims[0])
+            dev.set_stencil(0, links, diag)
+            self.level0_format = "stencil"
+        except Exception:
+            col, vals = bsr_padded(A0, 1)
+            dev.set_bsr(0, n0, 1, col, vals)
+            self.level0_format = "bsr1"
+        for i in range(nl - 1):
+            aggr_size, dofi, nvec, pvals = self._transfer_meta[i]
+            dev.set_transfer(i, lv[i].A.shape[0], aggr_size, dofi, nvec, pvals)
+            if i + 1 < nl - 1:
+                col, vals = bsr_padded(lv[i + 1].A, nvec)
+                dev.set_bsr(i + 1, lv[i + 1].A.shape[0], nvec, col, vals)
+        dev.set_coarsest_inverse(self.coarsest_inv)
+        for i in range(nl - 1):
+            dev.set_smoother(i, harmonic_ritz_inv_roots(csr_matrix(lv[i].A), self.smoother_degree))
+        if use_permuted:
+            for i in range(nl):
+                if i == 0:
+                    dev.set_perm(0, lv[0].perm_shift)
+                else:
+                    cols, vals = ell_padded(lv[i].Bblock_perm)
+                    dev.set_perm(i, lv[i].perm_shift, cols, vals)
+        dev.set_inner_precision(_lib.C64 if self.inner_precision == "c64" else _lib.C128)
+        self.dev = dev
+
+    # ---- device-side batched API ---------------------------------------------------------------
+    def _to_dev(self, v):
+        import torch
+        a = np.asarray(v, dtype=np.complex128)
+        if a.ndim == 1:
+            a = a.reshape(-1, 1)
+        return torch.from_numpy(np.ascontiguousarray(a)).to(self.dev.device)
+
+    def solve_batch(self, level, B, tol, maxiter=None):
+        """B: torch complex128 CUDA tensor [n_level, k] -> (X, iters[k], relres[k])."""
+        n = self.level_shapes[level]
+        if maxiter is None:
+            maxiter = n if n < 1000 else 1000                       # multigrid.py:354-357
+        return self.dev.fgmres(level, B, tol, restart=min(self.restart, maxiter), maxiter=maxiter)
+
+    # ---- multigrid.py:347-366 --------------------------------------------------------------------
+    def solve(self, A, b, tol):
+        B = self._to_dev(b)
+        X, iters, _ = self.solve_batch(self.level_nr, B, tol)
+        x = X.cpu().numpy()
+        self.x = x.reshape(-1) if np.asarray(b).ndim == 1 else x
+        self.num_iters = int(iters.max())
+
+    # ---- multigrid.py:369-447 --------------------------------------------------------------------
+    def one_mg_step(self, b):
+        B = self._to_dev(b)
+        X = self.dev.vcycle(self.level_nr, B)
+        self.coarsest_lev_iters[self.level_nr] += 1
+        self.nr_calls += 1
+        x = X.cpu().numpy()
+        return x.reshape(-1) if np.asarray(b).ndim == 1 else x
+
+    def __str__(self):
+        str_out = ""
+        str_out += "\nMultilevel information:\n"
+        for idx, level in enumerate(self.ml.levels):
+            str_out += "Level: " + str(idx) + "\n"
+            if idx < (len(self.ml.levels) - 1): str_out += "\tsize(R) = " + str(level.R.shape) + "\n"
+            if idx < (len(self.ml.levels) - 1): str_out += "\tsize(P) = " + str(level.P.shape) + "\n"
+            str_out += "\tsize(A) = " + str(level.A.shape) + "\n"
+        return str_out
+
+    # ---- multigrid.py:461-549 (the input vector is NOT modified, unlike :465-466) -----------------
+    def diff_op_Q(self, v):
+        vx = np.array(v, dtype=np.complex128, copy=True).reshape(-1)
+        h = int(vx.shape[0] / 2)
+        vx[h:] = -vx[h:]
+        return self.diff_op(vx)
+
+    def diff_op(self, v):
+        """( Af^{-1} - P Ac^{-1} R ) v at tolerance self.solve_tol, on the device."""
+        l = self.level_for_diff_op
+        nl = len(self.ml.levels)
+        skip = self.skip_level and l == 0
+        lc = l + 2 if skip else l + 1
+        V = self._to_dev(np.asarray(v).reshape(-1))
+        self.level_nr = l
+        T1, _, _ = self.solve_batch(l, V, self.solve_tol)
+        Vc = self.dev.restrict(l, V)
+        if skip:
+            Vc = self.dev.restrict(l + 1, Vc)
+        if lc == nl - 1:
+            T2 = self.dev.coarsest_apply(Vc)
+        else:
+            self.level_nr = lc
+            T2, _, _ = self.solve_batch(lc, Vc, self.solve_tol)
+        if skip:
+            Tm = self.dev.torch.zeros((self.level_shapes[l + 1], 1), dtype=T2.dtype, device=T2.device)
+            self.dev.prolong_add(l + 1, T2, Tm)
+            T2 = Tm
+        W = self.dev.torch.zeros_like(T1)
+        self.dev.prolong_add(l, T2, W)
+        return (T1 - W).cpu().numpy().reshape(-1)
+
+    # ---- multigrid.py:552-557 -----------------------------------------------------------------------
+    def matvec(self, x):
+        X = self._to_dev(x)
+        Y = self.dev.spmm(self.level_nr, X)
+        y = Y.cpu().numpy()
+        return y.reshape(-1) if np.asarray(x).ndim == 1 else y

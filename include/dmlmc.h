@@ -1,0 +1,131 @@
+/*
+ * dmlmc.h -- C ABI of libdmlmc_sm100.so: the sm_100a (B200) hot path of the deflated
+ * multilevel-Monte-Carlo Hutchinson estimator for tr(D^-1) of the 2-D Schwinger
+ * Wilson-Dirac operator.
+ *
+ * The reference (Gustavroot/DeflatedMLMC_Schwinger) is pure Python and has no FFI; the
+ * boundary below is what its hot-path call sites bind to when they are moved to the GPU.
+ * Each entry point cites the reference call site (file:line) it replaces.
+ *
+ * Conventions
+ *   - every function returns 0 on success, <0 for an argument / layout error, >0 for a
+ *     CUDA runtime error code; dmlmc_last_error() gives the message (thread local).
+ *   - "vectors" are column batches X[n][k] of k probes: row-major, k contiguous,
+ *     complex interleaved (re,im).  prec selects the scalar: DMLMC_C128 (double) or
+ *     DMLMC_C64 (float).
+ *   - `*_dev` / "device pointer" arguments are caller-owned device memory (torch tensors);
+ *     `*_host` arguments are host memory.  Everything runs asynchronously on the stream
+ *     given at creation; the only host synchronisations are the documented convergence
+ *     polls inside dmlmc_fgmres / dmlmc_level_sample* and the *_host entry points.
+ *   - the library allocates device memory only for the operators it is handed at setup
+ *     (dmlmc_set_*); solver work space is supplied by the caller (dmlmc_set_workspace).
+ *   - one hierarchy handle is single-threaded; different handles are independent.
+ *   - there is NO CPU fallback: without a CUDA device every call that touches data fails.
+ */
+#ifndef DMLMC_H
+#define DMLMC_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define DMLMC_ABI_VERSION 1
+
+enum { DMLMC_C128 = 0, DMLMC_C64 = 1 };
+
+typedef struct dmlmc_hier dmlmc_hier;
+
+int         dmlmc_abi_version(void);
+const char* dmlmc_last_error(void);
+
+/* ---- hierarchy: replaces the containers LevelML / SimpleML (multigrid.py:26-48) and the
+ *      attributes MG.setup leaves behind (multigrid.py:339-344) ------------------------ */
+int dmlmc_hier_create(int device, void* cuda_stream, int n_levels, dmlmc_hier** out);
+int dmlmc_hier_destroy(dmlmc_hier* h);
+
+/* level-0 operator A = S + m I in link form (matrix.py:14-31; stencil of SURVEY.md sec. 0):
+ * links_host = [2][LX][LT] complex128 (U_t then U_x), diag = 4 + m. Row i = s*V + x*LT + t. */
+int dmlmc_set_stencil(dmlmc_hier* h, int level, int LX, int LT, const double* links_host,
+                      double diag_re, double diag_im);
+/* coarse operator A_l = R A P (multigrid.py:276) as padded block-sparse rows:
+ * colidx_host[n/bs][bpr] (block column, -1 = padding), vals_host[n/bs][bpr][bs][bs] complex128 */
+int dmlmc_set_bsr(dmlmc_hier* h, int level, int n, int bs, int bpr, const int32_t* colidx_host,
+                  const double* vals_host);
+/* aggregation prolongator P_l (multigrid.py:192-262): row r of P has its nvec entries in
+ * columns j*2*nvec + half*nvec + [0,nvec), j = r / aggr_size, half = ((r % aggr_size) % dofi) >= dofi/2;
+ * pvals_host[n_f][nvec] complex128.  R_l = P_l^H (multigrid.py:267-274). */
+int dmlmc_set_transfer(dmlmc_hier* h, int level, int n_f, int aggr_size, int dofi, int nvec,
+                       const double* pvals_host);
+/* dense inverse of the coarsest operator (multigrid.py:342-344), row-major n x n complex128 */
+int dmlmc_set_coarsest_inverse(dmlmc_hier* h, int n, const double* minv_host);
+/* smoother on `level`: e = p(A) r with p given by its `degree` inverse roots (complex128),
+ * applied as Richardson steps in the given order.  Replaces the lgmres call of
+ * multigrid.py:393-394 / 438-439 (FGMRES is flexible: parity is on the converged solve). */
+int dmlmc_set_smoother(dmlmc_hier* h, int level, int degree, const double* inv_roots_host);
+/* permutation data of a level (multigrid.py:142-155, 320-331): x_perm = roll(x, +shift),
+ * then Bblock_perm (nnz_per_row == 0: identity) in padded row form cols/vals[n][nnz_per_row] */
+int dmlmc_set_perm(dmlmc_hier* h, int level, int shift, int nnz_per_row,
+                   const int32_t* cols_host, const double* vals_host);
+/* deflation vectors of a level, V[n][d] row-major complex128 (utils.py:145-157); d = 0 clears */
+int dmlmc_set_deflation(dmlmc_hier* h, int level, int d, const double* v_host);
+
+/* ---- single operators (device pointers) -------------------------------------------- */
+/* Y = A_level X          MG.matvec (multigrid.py:552-557), residual sites :388,402,433 */
+int dmlmc_spmm(dmlmc_hier* h, int level, int prec, const void* X, void* Y, int k);
+/* Xc = R_level Xf        multigrid.py:406; utils.py:301-303 */
+int dmlmc_restrict(dmlmc_hier* h, int level, int prec, const void* Xf, void* Xc, int k);
+/* Xf += P_level Xc       multigrid.py:429; utils.py:339-341 */
+int dmlmc_prolong_add(dmlmc_hier* h, int level, int prec, const void* Xc, void* Xf, int k);
+/* X = coarsest_inv B     multigrid.py:413-416; utils.py:309,321 */
+int dmlmc_coarsest_apply(dmlmc_hier* h, int prec, const void* B, void* X, int k);
+/* E = p(A_level) R       the smoother, multigrid.py:393-394 */
+int dmlmc_smooth(dmlmc_hier* h, int level, int prec, const void* R, void* E, int k);
+/* X = V-cycle(B) from `level` down to the coarsest   MG.one_mg_step (multigrid.py:369-447) */
+int dmlmc_vcycle(dmlmc_hier* h, int level, int prec, const void* B, void* X, int k);
+/* out[c] = sum_r conj(X[r][c]) Y[r][c]   np.vdot (utils.py:249,336,353); out = k complex128 (device) */
+int dmlmc_dotc(dmlmc_hier* h, const void* X, const void* Y, int n, int k, void* out_dev);
+/* X -= V (V^H X) with the level's deflation vectors   utils.py:224,266 */
+int dmlmc_deflate(dmlmc_hier* h, int level, void* X, int k);
+/* Rademacher probes from packed bits (utils.py:213-216,255-258): element i of probe p is
+ * 2*bit(p*n+i)-1 where bit(j) = (bits[j>>3] >> (j&7)) & 1 (numpy packbits, bitorder='little');
+ * X0[n][k] complex128 */
+int dmlmc_probe_expand(dmlmc_hier* h, const uint8_t* bits_dev, int n, int k, void* X0);
+/* RHS = Bblock_perm_level * roll(X, +shift_level)   utils.py:232,288-290 (identity if no perm set) */
+int dmlmc_apply_perm(dmlmc_hier* h, int level, const void* X, void* RHS, int k);
+
+/* ---- solver ---------------------------------------------------------------------- */
+/* bytes of caller-supplied device work space needed by dmlmc_fgmres / dmlmc_level_sample
+ * for batches of k probes on `level` with restart length `restart` */
+size_t dmlmc_workspace_bytes(dmlmc_hier* h, int level, int k, int restart);
+int    dmlmc_set_workspace(dmlmc_hier* h, void* ws_dev, size_t bytes);
+/* inner (V-cycle) precision: DMLMC_C64 (default) or DMLMC_C128; the outer FGMRES is always
+ * complex128, so per-probe solves meet the complex128 tolerance either way */
+int    dmlmc_set_inner_precision(dmlmc_hier* h, int prec);
+/* batched right-preconditioned flexible GMRES, x0 = 0, one Krylov space per column, stops a
+ * column when ||r|| < tol ||b||  (MG.solve, multigrid.py:347-366; pyamg.krylov.fgmres).
+ * B, X: [n_level][k] complex128 device.  iters_host[k], relres_host[k] may be NULL. */
+int dmlmc_fgmres(dmlmc_hier* h, int level, const void* B, void* X, int k, double tol,
+                 int restart, int maxiter, int32_t* iters_host, double* relres_host);
+
+/* one batch of k samples of utils.one_defl_Hutch_step (utils.py:207-361):
+ *   method 0 ("hutchinson"): e = x0^H A_0^{-1} C x_def
+ *   method 1 ("mlmc")      : e = x0^H (A_f^{-1} - P A_c^{-1} R) C_f x_def, level_c = level_f+1 or +2 (skip)
+ * X0[n_f][k] complex128 device (probes); e_dev[k] complex128 device; iters_host[2*k] (fine, coarse) or NULL */
+int dmlmc_level_sample(dmlmc_hier* h, int method, int level_f, int level_c, const void* X0, int k,
+                       double tol, int restart, int maxiter, void* e_dev, int32_t* iters_host);
+/* same with HOST buffers (the end-to-end call): packed probe bits in, estimates out;
+ * host<->device copies happen inside */
+int dmlmc_level_sample_host(dmlmc_hier* h, int method, int level_f, int level_c,
+                            const uint8_t* bits_host, int k, double tol, int restart, int maxiter,
+                            double* e_host, int32_t* iters_host);
+
+/* number of kernels launched by this handle since creation (bench.py's gpu_launches) */
+long long dmlmc_launch_count(dmlmc_hier* h);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DMLMC_H */

@@ -1,0 +1,179 @@
+"""GPU tier: every kernel behind the C ABI against scipy/numpy (the oracle's arithmetic) on the
+same inputs.  complex128 kernels must agree to rounding (1e-13 relative), complex64 ones to 2e-5."""
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+TOL = {torch.complex128: 1e-13, torch.complex64: 2e-5}
+
+
+def rnd(n, k, dtype, seed=0):
+    rs = np.random.RandomState(seed)
+    a = rs.standard_normal((n, k)) + 1j * rs.standard_normal((n, k))
+    return torch.from_numpy(a).to("cuda").to(dtype).contiguous()
+
+
+def relerr(a, b):
+    a = np.asarray(a, dtype=np.complex128); b = np.asarray(b, dtype=np.complex128)
+    return np.abs(a - b).max() / max(np.abs(b).max(), 1e-300)
+
+
+def host(t):
+    return t.cpu().numpy().astype(np.complex128)
+
+
+@pytest.mark.parametrize("dtype", [torch.complex128, torch.complex64])
+@pytest.mark.parametrize("k", [1, 3, 8, 64])
+def test_spmm_all_levels_128(mg128, dtype, k):
+    mg, tp, A = mg128
+    for lvl in range(3):
+        Al = mg.ml.levels[lvl].A
+        X = rnd(Al.shape[0], k, dtype, seed=lvl)
+        Y = mg.dev.spmm(lvl, X)
+        assert relerr(host(Y), Al @ host(X)) < TOL[dtype], (lvl, k)
+
+
+@pytest.mark.parametrize("dtype", [torch.complex128, torch.complex64])
+def test_spmm_16_bs2(mg16, dtype):
+    mg, tp, A = mg16
+    for lvl in range(2):
+        Al = mg.ml.levels[lvl].A
+        X = rnd(Al.shape[0], 5, dtype)
+        assert relerr(host(mg.dev.spmm(lvl, X)), Al @ host(X)) < TOL[dtype]
+
+
+def test_spmm_probe_input_is_exact_linear(mg128):
+    # +-1 inputs (the actual probes), k = 256 (BASELINE config 3), linearity A(x+y) = Ax + Ay
+    mg, tp, A = mg128
+    rs = np.random.RandomState(1)
+    X = torch.from_numpy((rs.randint(2, size=(32768, 256)) * 2 - 1).astype(np.complex128)).cuda()
+    Y = mg.dev.spmm(0, X)
+    ref = A @ host(X[:, :4])
+    assert relerr(host(Y[:, :4]), ref) < 1e-14
+    Z = rnd(32768, 256, torch.complex128, 5)
+    lhs = mg.dev.spmm(0, X + Z)
+    rhs = Y + mg.dev.spmm(0, Z)
+    assert relerr(host(lhs), host(rhs)) < 1e-13
+
+
+@pytest.mark.parametrize("dtype", [torch.complex128, torch.complex64])
+@pytest.mark.parametrize("k", [1, 6, 32])
+def test_restrict_prolong(mg128, dtype, k):
+    mg, tp, A = mg128
+    for lvl in range(3):
+        P, R = mg.ml.levels[lvl].P, mg.ml.levels[lvl].R
+        Xf = rnd(P.shape[0], k, dtype, 10 + lvl)
+        Xc = mg.dev.restrict(lvl, Xf)
+        assert relerr(host(Xc), R @ host(Xf)) < TOL[dtype]
+        Yc = rnd(P.shape[1], k, dtype, 20 + lvl)
+        Yf = rnd(P.shape[0], k, dtype, 30 + lvl)
+        ref = host(Yf) + P @ host(Yc)
+        mg.dev.prolong_add(lvl, Yc, Yf)
+        assert relerr(host(Yf), ref) < TOL[dtype]
+
+
+@pytest.mark.parametrize("dtype", [torch.complex128, torch.complex64])
+@pytest.mark.parametrize("k", [1, 7, 64])
+def test_coarsest_apply(mg128, dtype, k):
+    mg, tp, A = mg128
+    B = rnd(512, k, dtype, 3)
+    X = mg.dev.coarsest_apply(B)
+    ref = mg.coarsest_inv @ host(B)
+    tol = 1e-12 if dtype == torch.complex128 else 5e-5
+    assert relerr(host(X), ref) < tol
+
+
+def test_perm_and_probe_expand(mg128):
+    mg, tp, A = mg128
+    for lvl in range(4):
+        lv = mg.ml.levels[lvl]
+        n = lv.A.shape[0]
+        X = rnd(n, 5, torch.complex128, 40 + lvl)
+        Y = mg.dev.apply_perm(lvl, X)
+        ref = lv.Bblock_perm @ (lv.Pperm.transpose() @ host(X))
+        assert relerr(host(Y), ref) < 1e-13, lvl
+    np.random.seed(123456)
+    from deflatedmlmc_schwinger_b200 import utils, sampling
+    bits = sampling.draw_probe_bits(2048 * 6)
+    dev_bits = torch.from_numpy(utils.pack_bits(bits)).cuda()
+    X0 = mg.dev.probe_expand(dev_bits, 2048, 6)
+    ref = (bits.reshape(6, 2048).T.astype(np.float64) * 2 - 1)
+    assert np.array_equal(host(X0).real, ref) and np.all(host(X0).imag == 0)
+
+
+def test_dotc_and_deflate(mg16, g16):
+    mg, tp, A = mg16
+    X = rnd(512, 9, torch.complex128, 1); Y = rnd(512, 9, torch.complex128, 2)
+    d = mg.dev.dotc(X, Y)
+    ref = np.einsum("ij,ij->j", np.conj(host(X)), host(Y))
+    assert relerr(host(d), ref) < 1e-13
+    V = g16["defl_Ux"]
+    mg.dev.set_deflation(0, V)
+    Xd = X.clone()
+    mg.dev.deflate(0, Xd)
+    ref = host(X) - V @ (V.conj().T @ host(X))
+    assert relerr(host(Xd), ref) < 1e-13
+    mg.dev.set_deflation(0, None)
+    mg.__dict__.pop("_defl_cache", None)
+
+
+@pytest.mark.parametrize("dtype", [torch.complex128, torch.complex64])
+def test_smoother_is_the_polynomial(mg128, dtype):
+    from deflatedmlmc_schwinger_b200.multigrid import harmonic_ritz_inv_roots
+    from scipy.sparse import csr_matrix
+    mg, tp, A = mg128
+    for lvl in range(3):
+        Al = csr_matrix(mg.ml.levels[lvl].A)
+        w = harmonic_ritz_inv_roots(Al, mg.smoother_degree)
+        R = rnd(Al.shape[0], 4, dtype, 50 + lvl)
+        E = mg.dev.smooth(lvl, R)
+        r = host(R); e = np.zeros_like(r)
+        for wi in w:
+            e = e + wi * r
+            r = r - wi * (Al @ r)
+        tol = 1e-11 if dtype == torch.complex128 else 2e-3
+        assert relerr(host(E), e) < tol, lvl
+
+
+def _vcycle_numpy(mg, b, l0):
+    from deflatedmlmc_schwinger_b200.multigrid import harmonic_ritz_inv_roots
+    from scipy.sparse import csr_matrix
+    lv = mg.ml.levels
+    nl = len(lv)
+    if l0 == nl - 1:
+        return mg.coarsest_inv @ b
+    Al = csr_matrix(lv[l0].A)
+    w = harmonic_ritz_inv_roots(Al, mg.smoother_degree)
+    r = b.copy(); x = np.zeros_like(b)
+    for wi in w:
+        x = x + wi * r; r = r - wi * (Al @ r)
+    x = x + lv[l0].P @ _vcycle_numpy(mg, lv[l0].R @ r, l0 + 1)
+    r = b - Al @ x
+    for wi in w:
+        x = x + wi * r; r = r - wi * (Al @ r)
+    return x
+
+
+@pytest.mark.parametrize("l0", [0, 1, 2, 3])
+def test_vcycle_matches_numpy_restatement(mg128, l0):
+    mg, tp, A = mg128
+    n = mg.level_shapes[l0]
+    B = rnd(n, 3, torch.complex128, 60 + l0)
+    X = mg.dev.vcycle(l0, B)
+    ref = _vcycle_numpy(mg, host(B), l0)
+    assert relerr(host(X), ref) < 1e-9
+    Xf = mg.dev.vcycle(l0, B.to(torch.complex64))
+    assert relerr(host(Xf), ref) < 5e-3
+
+
+def test_argument_errors_are_reported(mg16):
+    from deflatedmlmc_schwinger_b200 import _lib
+    mg, tp, A = mg16
+    X = rnd(512, 2, torch.complex128)
+    with pytest.raises(_lib.DmlmcError):
+        mg.dev.lib.dmlmc_spmm.restype  # noqa: B018
+        _lib._check(mg.dev.lib.dmlmc_spmm(mg.dev.h, 7, 0, X.data_ptr(), X.data_ptr(), 2))
+    with pytest.raises(_lib.DmlmcError):
+        _lib._check(mg.dev.lib.dmlmc_fgmres(mg.dev.h, 2, X.data_ptr(), X.data_ptr(), 2, 1e-8, 10, 10, None, None))

@@ -1,0 +1,190 @@
+"""CPU tier: host-side logic of the product (no GPU): probe stream handling, sampling loops and the
+stop rule, aggregation maps, prolongator values, operator re-layout, parameter plumbing."""
+import numpy as np
+import pytest
+import scipy.sparse as sp
+
+from deflatedmlmc_schwinger_b200 import gateway, lattice, matrix, sampling, utils
+from deflatedmlmc_schwinger_b200 import multigrid as mgm
+from oracle import refport
+
+
+def test_draw_probe_bits_consumes_the_reference_stream():
+    np.random.seed(123456)
+    a = np.random.randint(2, size=5000)
+    b = np.random.randint(2, size=777)
+    st = np.random.get_state()
+    np.random.seed(123456)
+    a2 = sampling.draw_probe_bits(5000)
+    b2 = sampling.draw_probe_bits(777)
+    assert np.array_equal(a, a2) and np.array_equal(b, b2)
+    assert np.array_equal(np.random.get_state()[1], st[1]) and np.random.get_state()[2] == st[2]
+    np.random.seed(1)
+    sampling.skip_probe_words(1000)
+    x = sampling.draw_probe_bits(10)
+    np.random.seed(1)
+    y = np.random.randint(2, size=1010)[1000:]
+    assert np.array_equal(x, y)
+
+
+def test_pack_bits_layout():
+    bits = np.array([1, 0, 0, 1, 1, 1, 0, 0, 1, 0], dtype=np.uint8)
+    p = utils.pack_bits(bits)
+    for j in range(10):
+        assert ((p[j >> 3] >> (j & 7)) & 1) == bits[j]
+
+
+def _sequential_reference_loop(n, tol, max_nr, value_fn):
+    """the reference's loop shape (stoch_trace.py:386-406) on a deterministic per-probe function"""
+    ests = np.zeros(max_nr, dtype=complex)
+    for j in range(max_nr):
+        x = np.random.randint(2, size=n) * 2 - 1
+        ests[j] = value_fn(x)
+        avg, dev, err = sampling.reference_stats(ests, j)
+        if j >= 5 and err < tol:
+            break
+    return j, avg, dev
+
+
+def _value(x):
+    n = x.shape[0]
+    w = np.cos(np.arange(n)) + 1j * np.sin(0.3 * np.arange(n))
+    return np.dot(w, x) * (1 + 0.01 * x[0]) + 3.0
+
+
+def _sample_fn(n, k):
+    def fn(bits01):
+        xs = bits01.reshape(k, n).astype(np.int64) * 2 - 1
+        return np.array([_value(x) for x in xs]), np.ones(k, dtype=np.int64)
+    return fn
+
+
+@pytest.mark.parametrize("k", [1, 4, 16, 64])
+def test_run_sampling_equals_sequential_loop(k):
+    n, tol = 64, 0.9
+    np.random.seed(42)
+    j_ref, avg_ref, dev_ref = _sequential_reference_loop(n, tol, 5000, _value)
+    after_ref = np.random.randint(2, size=8)
+    np.random.seed(42)
+    res = sampling.run_sampling(_sample_fn(n, k), n, k, tol, 5000)
+    after = np.random.randint(2, size=8)
+    assert res["j_stop"] == j_ref
+    assert abs(res["avg"] - avg_ref) < 1e-12 * abs(avg_ref) and abs(res["dev"] - dev_ref) < 1e-12 * dev_ref
+    assert np.array_equal(after, after_ref)           # stream rewound to exactly after the last used probe
+    assert res["iters_sum"] == j_ref + 1
+
+
+def test_run_sampling_fixed_count_and_max():
+    n, k = 32, 8
+    np.random.seed(7)
+    res = sampling.run_sampling(_sample_fn(n, k), n, k, 0.0, 5, fixed_count=5)
+    assert res["j_stop"] == 4 and res["ests"].shape[0] == 5
+    np.random.seed(7)
+    ref = [_value(np.random.randint(2, size=n) * 2 - 1) for _ in range(5)]
+    assert np.allclose(res["ests"], ref)
+    np.random.seed(7)
+    res = sampling.run_sampling(_sample_fn(n, k), n, k, 1e-30, 20)      # never converges -> max_nr_ests
+    assert res["j_stop"] == 19
+
+
+def test_reduce_level_sums_single_process():
+    e = np.array([1 + 2j, 3 - 1j, -2 + 0.5j])
+    m, s, N = sampling.reduce_level_sums(e)
+    assert N == 3 and abs(m - e.mean()) < 1e-15 and abs(s - np.sqrt(np.mean(np.abs(e - e.mean()) ** 2))) < 1e-14
+
+
+def test_aggregation_maps_closed_form_vs_oracle(port128):
+    mp, tp = port128
+    meta = [(32, 2, 4), (32, 4, 4), (32, 4, 4)]
+    for i, (a, dofi, c) in enumerate(meta):
+        P = mp.levels[i].P.tocsr(); P.sort_indices()
+        n = P.shape[0]
+        half, first = mgm.aggregation_maps(n, a, dofi, c)
+        idx = (first[:, None] + np.arange(c)[None, :]).ravel()
+        assert np.array_equal(idx, P.indices)                         # bit-exact index maps
+
+
+def test_prolongator_values_vs_oracle(port128, g128):
+    mp, tp = port128
+    for i, (a, dofi, c, tv) in enumerate([(32, 2, 4, g128["tv0"]), (32, 4, 4, g128["tv1"]), (32, 4, 4, g128["tv2"])]):
+        pv = mgm.build_prolongator_values(tv, a, dofi, c)
+        P = mgm.prolongator_csr(pv, a, dofi, c)
+        D = P - mp.levels[i].P
+        assert (abs(D).max() if D.nnz else 0.0) == 0.0            # bit-identical to the oracle (and the reference)
+
+
+def test_bsr_and_ell_padding_roundtrip(port128):
+    mp, tp = port128
+    for lvl, bs in ((1, 4), (2, 4)):
+        A = mp.levels[lvl].A
+        col, vals = mgm.bsr_padded(A, bs)
+        nb = A.shape[0] // bs
+        assert col.shape[0] == nb
+        x = np.random.RandomState(0).standard_normal(A.shape[0]) + 0j
+        y = np.zeros(A.shape[0], dtype=complex)
+        for I in range(nb):
+            for b in range(col.shape[1]):
+                J = col[I, b]
+                if J >= 0:
+                    y[I * bs:(I + 1) * bs] += vals[I, b] @ x[J * bs:(J + 1) * bs]
+        assert np.abs(y - A @ x).max() < 1e-12
+    # structural claim of SURVEY.md 2.1: A1 has 9 4x4 blocks per block row
+    col, _ = mgm.bsr_padded(mp.levels[1].A, 4)
+    assert col.shape[1] == 9
+    cols, vals = mgm.ell_padded(mp.levels[2].Bblock_perm)
+    x = np.arange(2048) + 1j
+    y = np.array([sum(vals[i, j] * x[cols[i, j]] for j in range(cols.shape[1]) if cols[i, j] >= 0) for i in range(2048)])
+    assert np.abs(y - mp.levels[2].Bblock_perm @ x).max() < 1e-12
+
+
+def test_perm_is_roll(port128):
+    mp, tp = port128
+    for l in range(4):
+        n = mp.levels[l].A.shape[0]
+        x = np.arange(n) + 0j
+        assert np.array_equal(mp.levels[l].Pperm.transpose() @ x, np.roll(x, mp.levels[l].perm_shift))
+
+
+def test_harmonic_ritz_polynomial_reduces_residual(port128):
+    mp, tp = port128
+    A = sp.csr_matrix(mp.levels[2].A)
+    w = mgm.harmonic_ritz_inv_roots(A, 16)
+    assert w.shape == (16,)
+    r = np.random.RandomState(3).standard_normal(A.shape[0]) + 0j
+    r0 = np.linalg.norm(r)
+    for wi in w:
+        r = r - wi * (A @ r)
+    assert np.linalg.norm(r) < 0.7 * r0
+
+
+def test_lattice_roundtrip_and_synthetic():
+    links = lattice.random_u1_links(8, seed=5)
+    A = lattice.wilson_matrix(links, -0.1)
+    l2, d = lattice.links_from_matrix(A, 8, 8)
+    assert np.array_equal(l2, links) and d == 4.0 - 0.1
+    B = refport.wilson_from_links(links)
+    D = A - (B + (-0.1) * sp.identity(128, format="csc"))
+    assert (abs(D).max() if D.nnz else 0.0) < 1e-15
+    with pytest.raises(Exception):
+        lattice.links_from_matrix(sp.random(128, 128, 0.1, format="csr") + sp.identity(128), 8, 8)
+    A2 = matrix.loadMatrix("synthetic:8:5", {"mass": -0.1})
+    assert abs(A2 - A).max() == 0
+
+
+def test_gateway_and_param_plumbing():
+    p = gateway.set_params("schwinger128")
+    assert p["aggrs"] == [16, 4, 4] and p["dof"] == [2, 8, 8, 8] and p["matrix_params"]["mass"] == -0.1320
+    assert p["mlmc_levels_to_skip"] == [1] and p["nr_deflat_vctrs"] == 8 and p["use_permuted"] is True
+    p["function_tol"] = 1e-12
+    tp = utils.trace_params_from_params(p, "mlmc")
+    assert tp["max_nr_ests"] == 100000 and tp["function_params"]["tol"] == 1e-12 and tp["tol"] == 1e-2
+    th = utils.trace_params_from_params(p, "hutchinson")
+    assert "mlmc_deflat_vctrs" not in th and th["defl-type"] == "exact"
+    with pytest.raises(Exception):
+        utils.trace_params_from_params(p, "nope")
+    with pytest.raises(Exception):
+        gateway.set_params("nope")
+    t = utils.CustomTimer()
+    t.start("mvm"); t.end("mvm")
+    with pytest.raises(Exception):
+        t.end("mvm")
