@@ -1,0 +1,342 @@
+#!/usr/bin/env python
+"""bench.py -- throughput of the hot path on B200(s):  tr(D^-1) probes/sec, Schwinger 128^2.
+
+A "step" is one batch of K_PROBES deflated-MLMC level-0 samples of the shipped 128^2
+configuration (BASELINE.json configs[1]; gateway.set_params('schwinger128'): permuted, level 1
+skipped): per probe one FGMRES solve on level 0 (n = 32768) to 1e-12, one on level 2 (n = 2048),
+the transfers R1 R0 / P0 P1, the permutation and the two inner products -- i.e. one call of the
+fused dmlmc_level_sample on k probes (reference: utils.one_defl_Hutch_step, utils.py:252-357).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--probes k] [--impl reference]
+
+One JSON line on stdout (rank 0).  `value` times the device-resident path (probe bits already in
+HBM); `e2e` times the host-buffer C-ABI call dmlmc_level_sample_host (packed probe bits H2D and the
+estimates D2H inside the timed region).  N > 1: one process per GPU (torchrun), probes sharded by
+rank, no data-path collective except the single all_reduce of the level's partial sums.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+os.environ.setdefault("OMP_NUM_THREADS", "1")
+
+import numpy as np  # noqa: E402
+
+METRIC = "tr(D^-1) probes/sec, Schwinger 128^2 (deflated-MLMC level-0 difference samples)"
+WORKLOAD = "schwinger128.mat deflated MLMC level-0 samples (configs[1]; permuted, skip level 1, tol 1e-12)"
+
+
+def golden_tvs():
+    g = np.load(os.path.join(ROOT, "tests", "golden", "schwinger128.npz"))
+    return [g["tv0"], g["tv1"], g["tv2"]]
+
+
+def params128():
+    from deflatedmlmc_schwinger_b200 import gateway, utils
+    p = gateway.set_params("schwinger128")
+    p["function_tol"] = 1e-12
+    p["verbose"] = False
+    return p, utils.trace_params_from_params(p, "mlmc")
+
+
+# ------------------------------------------------------------------------------------------------
+# CPU side: the oracle port of the reference algorithm (the reference is Python and cannot travel)
+
+_CPU = {}
+
+
+def _cpu_setup():
+    if "mp" not in _CPU:
+        from oracle import refport
+        p, tp = params128()
+        mp = refport.MGPort(refport.load_matrix(p["matrix"], p["matrix_params"]["mass"]))
+        mp.setup(tp["dof"], tp["aggrs"], tp["max_nr_levels"], tp["accuracy_mg_eigvs"], tp, test_vectors=golden_tvs())
+        mp.skip_level = True
+        _CPU["mp"], _CPU["tp"] = mp, tp
+    return _CPU["mp"], _CPU["tp"]
+
+
+def _cpu_probe(seed):
+    """one level-0 MLMC sample with the reference algorithm (FGMRES + V-cycle with lgmres smoother)"""
+    from oracle import refport
+    mp, tp = _cpu_setup()
+    rs = np.random.RandomState(seed)
+    t = time.time()
+    e, _ = refport.one_defl_hutch_step(mp.levels[0].A, mp.levels[2].A, mp, tp, "mlmc", 0, None, None, rs, 0)
+    return time.time() - t, complex(e)
+
+
+def cpu_baseline_single(n_probes=2):
+    _cpu_setup()
+    t = time.time()
+    for q in range(n_probes):
+        _cpu_probe(1000 + q)
+    dt = time.time() - t
+    return {"value": n_probes / dt, "unit": "probes/s", "cores": 1, "kind": "port",
+            "sample": "%d level-0 MLMC samples of the same workload (oracle port of the reference algorithm: "
+                      "pyamg-style FGMRES + V-cycle with scipy lgmres(30,3)x2 smoother, tol 1e-12), 1 thread" % n_probes}
+
+
+def run_reference_arm(args):
+    """--impl reference: the reference algorithm (oracle port; the Python reference itself is not
+    present on the GPU box) on all host cores, one probe per core per step."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    import multiprocessing as mpx
+    cores = max(1, (os.cpu_count() or 1))
+    cores = min(cores, int(os.environ.get("DMLMC_REF_CORES", cores)))
+    ctx = mpx.get_context("fork")
+    _cpu_setup()
+    with ctx.Pool(cores) as pool:
+        step = 0
+        for _ in range(args.warmup):
+            pool.map(_cpu_probe, [step * cores + c for c in range(cores)]); step += 1
+        t = time.time()
+        for _ in range(args.steps):
+            pool.map(_cpu_probe, [step * cores + c for c in range(cores)]); step += 1
+        dt = time.time() - t
+    value = args.steps * cores / dt
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": "probes/s", "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "c128",
+            "data": "schwinger128 gauge field (reference input) + MT19937 Rademacher probes",
+            "config": {"workload": WORKLOAD, "probes_per_step": cores},
+            "cpu_baseline": {"value": value, "unit": "probes/s", "cores": cores, "kind": "port",
+                             "sample": "%d level-0 MLMC samples per step, one per core (oracle port of the reference "
+                                       "algorithm; the Python reference cannot travel to the GPU box)" % cores},
+            "e2e": {"value": value, "unit": "probes/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------
+
+class ClockSampler(threading.Thread):
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index = index
+        self.samples = []
+        self.reasons = set()
+        self._halt = threading.Event()
+        self.max_mhz = None
+
+    def run(self):
+        q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        while not self._halt.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + q, "--format=csv,noheader,nounits"],
+                                     capture_output=True, text=True, timeout=5).stdout.strip().split(",")
+                self.samples.append(float(out[0])); self.max_mhz = float(out[1])
+                for nm, v in zip(names, out[2:]):
+                    if v.strip().lower().startswith("active"):
+                        self.reasons.add(nm)
+            except Exception:
+                pass
+            self._halt.wait(0.2)
+
+    def stop(self):
+        self._halt.set()
+        self.join(timeout=6)
+        med = float(np.median(self.samples)) if self.samples else None
+        return {"sm_mhz": med, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons), "samples": len(self.samples)}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=8)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--probes", type=int, default=256, help="probes per step per GPU")
+    ap.add_argument("--impl", default="b200")
+    ap.add_argument("--degree", type=int, default=32)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference_arm(args)
+        return
+
+    import torch
+    import torch.distributed as dist
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    assert torch.cuda.is_available(), "bench.py needs a CUDA device; there is no CPU fallback"
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    import __graft_entry__ as ge
+    if rank == 0:
+        ge.build()
+    if world > 1:
+        dist.barrier()
+    from deflatedmlmc_schwinger_b200 import matrix, multigrid, sampling, utils, _lib
+
+    p, tp = params128()
+    A = matrix.loadMatrix(p["matrix"], p["matrix_params"])
+    t0 = time.time()
+    mg = multigrid.MG(A, smoother_degree=args.degree)
+    mg.setup(dof=tp["dof"], aggrs=tp["aggrs"], max_levels=tp["max_nr_levels"], acc_eigvs=tp["accuracy_mg_eigvs"],
+             params=tp, test_vectors=golden_tvs())
+    mg.skip_level = True
+    setup_s = time.time() - t0
+    dev = mg.dev
+    n0, k = mg.level_shapes[0], args.probes
+    tol, restart, maxiter = 1e-12, 40, 1000
+    total_steps = args.warmup + args.steps
+
+    # probes: rank g owns the g-th block of k probes of every round of the MT19937(123456) stream
+    np.random.seed(123456)
+    nbytes = (n0 * k + 7) // 8
+    host_bits = torch.empty((total_steps, nbytes), dtype=torch.uint8).pin_memory()
+    for s in range(total_steps):
+        sampling.skip_probe_words(rank * k * n0)
+        host_bits[s].copy_(torch.from_numpy(utils.pack_bits(sampling.draw_probe_bits(k * n0))))
+        sampling.skip_probe_words((world - 1 - rank) * k * n0)
+    dev_bits = host_bits.cuda()
+    dev.ensure_workspace(0, k, restart)
+    stream = torch.cuda.current_stream()
+
+    def step_device(s):
+        X0 = dev.probe_expand(dev_bits[s], n0, k)
+        return dev.level_sample(1, 0, 2, X0, tol, restart, maxiter)
+
+    def step_host(s):
+        return dev.level_sample_host(1, 0, 2, host_bits[s].numpy(), k, tol, restart, maxiter)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- device-resident timing ------------------------------------------------------------------
+    for s in range(args.warmup):
+        step_device(s)
+    sampler = ClockSampler(local)
+    barrier()
+    sampler.start()
+    l0 = dev.launch_count()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record(stream)
+    es, its = [], []
+    for s in range(args.warmup, total_steps):
+        e, it = step_device(s)
+        es.append(e); its.append(it)
+    e_all = torch.cat(es)
+    if world > 1:   # the single collective of the level: [sum Re e, sum Im e, sum |e|^2, N]
+        sums = torch.stack([e_all.real.sum(), e_all.imag.sum(), (e_all.abs() ** 2).sum(),
+                            torch.tensor(float(e_all.numel()), device=e_all.device, dtype=torch.float64)])
+        dist.all_reduce(sums)
+    ev1.record(stream)
+    barrier()
+    launches = dev.launch_count() - l0
+    clocks = sampler.stop()
+    ms = ev0.elapsed_time(ev1)
+    if world > 1:
+        t = torch.tensor([ms], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    value = world * k * args.steps / (ms * 1e-3)
+    iters = np.concatenate(its, axis=1)
+
+    # ---- end-to-end timing through the host-buffer C-ABI call ----------------------------------------
+    for s in range(min(args.warmup, 2)):
+        step_host(s)
+    barrier()
+    ev0.record(stream)
+    for s in range(args.warmup, total_steps):
+        e_h, _ = step_host(s)
+    ev1.record(stream)
+    barrier()
+    ms_e2e = ev0.elapsed_time(ev1)
+    if world > 1:
+        t = torch.tensor([ms_e2e], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms_e2e = float(t.item())
+    e2e = {"value": world * k * args.steps / (ms_e2e * 1e-3), "unit": "probes/s",
+           "h2d_bytes_per_step": int(nbytes), "d2h_bytes_per_step": int(16 * k + 8 * k),
+           "api": "dmlmc_level_sample_host (utils.defl_Hutch_batch)"}
+    same = float(np.abs(e_h - es[-1].cpu().numpy()).max())
+
+    # ---- roofline of the dominant kernel: the level-0 fused stencil + Richardson-update step (c64) ------
+    roof = None
+    if rank == 0:
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except Exception:
+            pass
+        peak = float(peaks.get("hbm_gbs", 6650.0))
+        R = torch.randn(n0, k, device="cuda", dtype=torch.float32).to(torch.complex64).contiguous()
+        d = mg.smoother_degree
+        reps = 5
+        for _ in range(2):
+            dev.smooth(0, R)
+        torch.cuda.synchronize()
+        ev0.record(stream)
+        for _ in range(reps):
+            dev.smooth(0, R)
+        ev1.record(stream)
+        torch.cuda.synchronize()
+        t_call = ev0.elapsed_time(ev1) * 1e-3 / reps
+        s = 8                                   # bytes per complex64
+        vec = n0 * k * s
+        # dmlmc_smooth(degree d, e0 = 0, no final residual): 1 first step (read r; write r', e) + (d-2) steps
+        # (read r, e; write r', e) + 1 axpy (read r, e; write e); links 2 complex per site per operator step
+        alg_bytes = 3 * vec + (d - 2) * 4 * vec + 3 * vec + (d - 1) * n0 * s
+        n_launch = d
+        achieved = alg_bytes / t_call / 1e9
+        roof = {"bound": "hbm", "kernel": "stencil_kernel<float,2,M_SMOOTH> (level-0 operator + Richardson update, c64, k=%d)" % k,
+                "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                "peak_source": "MEASURED_PEAKS.json hbm_gbs" if "hbm_gbs" in peaks else "fallback 6650",
+                "frac_of_nominal_8TBs": achieved / 8000.0,
+                "avg_launch_us": 1e6 * t_call / n_launch, "alg_bytes_per_launch": alg_bytes / n_launch, "traffic": None}
+        # plain SpMM Y = A X (config 3), c128 and c64, bytes n0*s*(2k) + links
+        spmm = {}
+        for name, dt, sb in (("c128", torch.complex128, 16), ("c64", torch.complex64, 8)):
+            X = R.to(dt).contiguous(); Y = torch.empty_like(X)
+            for _ in range(3):
+                dev.spmm(0, X, Y)
+            torch.cuda.synchronize()
+            ev0.record(stream)
+            for _ in range(20):
+                dev.spmm(0, X, Y)
+            ev1.record(stream)
+            torch.cuda.synchronize()
+            tt = ev0.elapsed_time(ev1) * 1e-3 / 20
+            by = n0 * sb * (1 + 2 * k)
+            spmm[name] = {"us": 1e6 * tt, "GBps": by / tt / 1e9, "frac": by / tt / 1e9 / peak}
+        roof["spmm_level0"] = spmm
+
+    line = {"metric": METRIC, "value": value, "unit": "probes/s", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "c128 (FGMRES, transfers, dots) + c64 (V-cycle)",
+            "data": "schwinger128 gauge field (reference input) + MT19937(123456) Rademacher probes",
+            "config": {"workload": WORKLOAD, "probes_per_step_per_gpu": k, "solver_tol": tol,
+                       "smoother": "fixed GMRES polynomial, degree %d per level" % args.degree,
+                       "fgmres_restart": restart, "l2_flush": "inputs larger than L2 (Krylov basis %.1f GB per step)"
+                       % (2 * 26 * n0 * k * 16 / 1e9), "parallelism": "probes sharded x%d" % world},
+            "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
+            "fgmres_iters": {"level0": [int(iters[0].min()), int(iters[0].max())],
+                             "level2": [int(iters[1].min()), int(iters[1].max())]},
+            "setup_s": setup_s, "e2e_vs_device_max_abs_diff": same}
+    if roof is not None:
+        line["roofline"] = roof
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        line["cpu_baseline"] = cpu_baseline_single(2)
+    if rank == 0:
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

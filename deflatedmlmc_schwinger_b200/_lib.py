@@ -54,6 +54,7 @@ _SIGS = {
     "dmlmc_level_sample_host": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_void_p,
                                                ctypes.c_int, ctypes.c_double, ctypes.c_int, ctypes.c_int, ctypes.c_void_p,
                                                ctypes.c_void_p]),
+    "dmlmc_set_option": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_char_p, ctypes.c_double]),
     "dmlmc_launch_count": (ctypes.c_longlong, [ctypes.c_void_p]),
 }
 
@@ -173,6 +174,9 @@ class Hierarchy:
         else:
             V, p = _host_c128(V)
             _check(self.lib.dmlmc_set_deflation(self.h, level, V.shape[1], p))
+
+    def set_option(self, name, value):
+        _check(self.lib.dmlmc_set_option(self.h, name.encode(), float(value)))
 
     def set_inner_precision(self, prec):
         _check(self.lib.dmlmc_set_inner_precision(self.h, prec))

@@ -11,6 +11,7 @@
 #include <cstdio>
 #include <cstring>
 #include <string>
+#include <type_traits>
 #include <vector>
 
 using namespace dmlmc;
@@ -44,7 +45,7 @@ struct Level {
   int n = 0;
   int kind = -1;            // 0 stencil, 1 bsr
   int LX = 0, LT = 0;
-  int bs = 0, bpr = 0, nb = 0; int* bsr_col = nullptr;
+  int bs = 0, bpr = 0, nb = 0; int* bsr_col = nullptr; float4* bsr_vals4 = nullptr;   // (mr,mr,mi,mi) per entry
   bool has_transfer = false; int aggr = 0, dofi = 0, nvec = 0, n_c = 0;
   std::vector<Cx<double>> inv_roots;      // smoother
   bool has_perm = false; int shift = 0, perm_nnz = 0; int* perm_cols = nullptr;
@@ -66,6 +67,7 @@ struct dmlmc_hier {
   Level lv[MAX_LEVELS];
   int coarse_n = 0; Cx<double>* minv_d = nullptr; Cx<float>* minv_f = nullptr;
   int inner_prec = DMLMC_C64;
+  int reorth = 1;
   char* ws = nullptr; size_t ws_bytes = 0, ws_off = 0;
   int* h_nactive = nullptr;        // pinned
   long long launches = 0;
@@ -126,6 +128,26 @@ int launch_op_nc(dmlmc_hier* h, int level, const void* X, const void* B, void* Y
     const size_t total = (size_t)L.LX * L.LT * kp;
     stencil_kernel<T, NC, MODE><<<nblocks(total, 256), 256, 0, h->stream>>>(op, (const P*)X, (const P*)B, (P*)Y, (P*)E, wt, kp);
   } else if (L.kind == 1) {
+    if constexpr (std::is_same<T, float>::value && NC == 2) {
+      // Blackwell FFMA2 + shared-memory path for the complex64 V-cycle
+      const int PPT = (L.bs <= 4) ? 2 : 1;
+      const int need = (kp + PPT - 1) / PPT;
+      int tpr = 1;
+      if (need >= 32) tpr = std::min(128, ((need + 31) / 32) * 32); else while (tpr < need) tpr *= 2;
+      const size_t per_row = (size_t)L.bpr * L.bs * L.bs * sizeof(float4) + (size_t)L.bpr * sizeof(int);
+      int RB = std::max(1, 128 / tpr);
+      RB = (int)std::max<size_t>(1, std::min<size_t>(RB, 40960 / per_row));
+      const size_t smem = RB * per_row + 16;
+      if (smem <= 48 * 1024 && L.bs >= 2) {
+        dim3 blk(tpr, RB), grd((L.nb + RB - 1) / RB, (kp + tpr * PPT - 1) / (tpr * PPT));
+#define BSR2(BS_, PPT_) bsr_f32x2_kernel<BS_, PPT_, MODE><<<grd, blk, smem, h->stream>>>(L.nb, L.bpr, L.bsr_col, L.bsr_vals4, \
+            (const P*)X, (const P*)B, (P*)Y, (P*)E, wt, kp)
+        if (L.bs == 2) BSR2(2, 2); else if (L.bs == 4) BSR2(4, 2); else BSR2(8, 1);
+#undef BSR2
+        LAUNCH_CHECK(h);
+        return 0;
+      }
+    }
     BsrDev<T> op; op.nb = L.nb; op.bpr = L.bpr; op.col = L.bsr_col; op.vals = D.bsr_vals;
     const size_t total = (size_t)L.nb * kp;
     const unsigned g = nblocks(total, 128);
@@ -398,9 +420,10 @@ int fgmres(dmlmc_hier* h, int level, const Z* B, Z* X, int k, double tol, int re
       // classical Gram-Schmidt with one re-orthogonalisation pass
       RET(multi_dot(h, Vb, nk, j + 1, W, n, k, partial, s.hsum, 0));
       RET(multi_axpy(h, Vb, nk, j + 1, s.hsum, W, n, k, -1.0));
-      RET(multi_dot(h, Vb, nk, j + 1, W, n, k, partial, s.y, 0));       // s.y used as scratch [(j+1)][k]
-      RET(multi_axpy(h, Vb, nk, j + 1, s.y, W, n, k, -1.0));
-      {  // hsum += second-pass coefficients
+      if (h->reorth) {
+        RET(multi_dot(h, Vb, nk, j + 1, W, n, k, partial, s.y, 0));       // s.y used as scratch [(j+1)][k]
+        RET(multi_axpy(h, Vb, nk, j + 1, s.y, W, n, k, -1.0));
+        // hsum += second-pass coefficients
         const int cnt = (j + 1) * k;
         sum_partials_kernel<<<nblocks(cnt, 256), 256, 0, h->stream>>>(s.y, 1, cnt, s.hsum, 1); LAUNCH_CHECK(h);
       }
@@ -593,6 +616,15 @@ int dmlmc_set_bsr(dmlmc_hier* h, int level, int n, int bs, int bpr, const int32_
   for (size_t i = 0; i < (size_t)L.nb * bpr; ++i) CHECK(colidx_host[i] >= -1 && colidx_host[i] < L.nb, "set_bsr: block column out of range");
   RET(upload<int>(h, colidx_host, (size_t)L.nb * bpr, &L.bsr_col));
   RET(upload_cx(h, vals_host, (size_t)L.nb * bpr * bs * bs, &L.d.bsr_vals, &L.f.bsr_vals));
+  {
+    const size_t cnt = (size_t)L.nb * bpr * bs * bs;
+    std::vector<float4> v4(cnt);
+    for (size_t i = 0; i < cnt; ++i) {
+      const float mr = (float)vals_host[2 * i], mi = (float)vals_host[2 * i + 1];
+      v4[i] = make_float4(mr, mr, mi, mi);
+    }
+    RET(upload<float4>(h, v4.data(), cnt, &L.bsr_vals4));
+  }
   return 0;
 }
 
@@ -774,6 +806,11 @@ int dmlmc_level_sample_host(dmlmc_hier* h, int method, int level_f, int level_c,
   }
   h->ws_off = mark;
   return rc;
+}
+int dmlmc_set_option(dmlmc_hier* h, const char* name, double value) {
+  CHECK(h != nullptr && name != nullptr, "set_option: bad arguments");
+  if (std::strcmp(name, "reorth") == 0) { h->reorth = value != 0.0 ? 1 : 0; return 0; }
+  return fail(-1, std::string("dmlmc: unknown option ") + name);
 }
 long long dmlmc_launch_count(dmlmc_hier* h) { return h ? h->launches : 0; }
 

@@ -134,6 +134,94 @@ bsr_kernel(BsrDev<T> op, const Pack<T, NC>* __restrict__ X, const Pack<T, NC>* _
 }
 
 // ------------------------------------------------------------------------------------------
+// complex64 coarse operator, Blackwell path: packed FP32 FMA (fma.rn.f32x2 -> SASS FFMA2, sm_100+)
+// with the block row's matrix staged in shared memory as (mr, mr, mi, mi) per entry, so the inner
+// loop is one broadcast LDS.128 per matrix entry feeding 4*PPT FFMA2 and no shuffles/swaps:
+//   a += (mr,mr)*(xr,xi)   b += (mi,mi)*(xr,xi)   =>   (A x).re = a.re - b.im, (A x).im = a.im + b.re
+// blockDim = (tpr, RB): RB block rows per CTA, thread tx owns PPT packs (2 columns each) tx + p*tpr.
+__device__ __forceinline__ void fma2x(float4& acc, float2 m, const float4& x) {
+  const float2 lo = __ffma2_rn(m, make_float2(x.x, x.y), make_float2(acc.x, acc.y));
+  const float2 hi = __ffma2_rn(m, make_float2(x.z, x.w), make_float2(acc.z, acc.w));
+  acc = make_float4(lo.x, lo.y, hi.x, hi.y);
+}
+
+template <int BS, int PPT, int MODE>
+__global__ void __launch_bounds__(128)
+bsr_f32x2_kernel(int nb, int bpr, const int* __restrict__ col, const float4* __restrict__ vals4,
+                 const Pack<float, 2>* __restrict__ X, const Pack<float, 2>* __restrict__ B,
+                 Pack<float, 2>* __restrict__ Y, Pack<float, 2>* __restrict__ E, Cx<float> w, int kp) {
+  extern __shared__ float4 bsr_smem[];
+  const int tpr = blockDim.x, RB = blockDim.y;
+  const int tx = threadIdx.x, rb = threadIdx.y;
+  const int nent = bpr * BS * BS;
+  float4* vs = bsr_smem;
+  int* cs = reinterpret_cast<int*>(bsr_smem + (size_t)RB * nent);
+  const int I0 = blockIdx.x * RB;
+  const int tid = rb * tpr + tx, nthr = tpr * RB;
+  for (int i = tid; i < RB * nent; i += nthr) {
+    const int rbi = i / nent, Ii = I0 + rbi;
+    vs[i] = (Ii < nb) ? __ldg(vals4 + (size_t)Ii * nent + (i - rbi * nent)) : make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+  for (int i = tid; i < RB * bpr; i += nthr) {
+    const int rbi = i / bpr, Ii = I0 + rbi;
+    cs[i] = (Ii < nb) ? __ldg(col + (size_t)Ii * bpr + (i - rbi * bpr)) : -1;
+  }
+  __syncthreads();
+  const int I = I0 + rb;
+  if (I >= nb) return;
+  const size_t kpz = (size_t)kp;
+  int cp[PPT]; bool ok[PPT];
+#pragma unroll
+  for (int p = 0; p < PPT; ++p) {
+    const int c = blockIdx.y * (tpr * PPT) + tx + p * tpr;
+    ok[p] = c < kp;
+    cp[p] = ok[p] ? c : kp - 1;
+  }
+  float4 a[BS][PPT], b[BS][PPT];
+#pragma unroll
+  for (int r = 0; r < BS; ++r)
+#pragma unroll
+    for (int p = 0; p < PPT; ++p) { a[r][p] = make_float4(0.f, 0.f, 0.f, 0.f); b[r][p] = make_float4(0.f, 0.f, 0.f, 0.f); }
+  const float4* vrow = vs + (size_t)rb * nent;
+  const int* crow = cs + rb * bpr;
+  const float4* X4 = reinterpret_cast<const float4*>(X);
+  for (int blk = 0; blk < bpr; ++blk) {
+    const int J = crow[blk];
+    if (J < 0) continue;
+    float4 xv[BS][PPT];
+#pragma unroll
+    for (int c = 0; c < BS; ++c)
+#pragma unroll
+      for (int p = 0; p < PPT; ++p) xv[c][p] = __ldg(X4 + ((size_t)J * BS + c) * kpz + cp[p]);
+    const float4* vb = vrow + blk * (BS * BS);
+#pragma unroll
+    for (int r = 0; r < BS; ++r) {
+#pragma unroll
+      for (int c = 0; c < BS; ++c) {
+        const float4 m = vb[r * BS + c];
+        const float2 mr = make_float2(m.x, m.y), mi = make_float2(m.z, m.w);
+#pragma unroll
+        for (int p = 0; p < PPT; ++p) { fma2x(a[r][p], mr, xv[c][p]); fma2x(b[r][p], mi, xv[c][p]); }
+      }
+    }
+  }
+#pragma unroll
+  for (int r = 0; r < BS; ++r) {
+#pragma unroll
+    for (int p = 0; p < PPT; ++p) {
+      if (!ok[p]) continue;
+      Pack<float, 2> ax;
+      ax.d[0] = a[r][p].x - b[r][p].y; ax.d[1] = a[r][p].y + b[r][p].x;
+      ax.d[2] = a[r][p].z - b[r][p].w; ax.d[3] = a[r][p].w + b[r][p].z;
+      const size_t idx = ((size_t)I * BS + r) * kpz + cp[p];
+      Pack<float, 2> xin = pzero<float, 2>();
+      if constexpr (MODE == M_SMOOTH || MODE == M_SMOOTH_FIRST) xin = ldp_ro<float, 2>(X, idx);
+      op_epilogue<float, 2, MODE>(ax, xin, idx, B, Y, E, w);
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------
 // aggregation transfer operators.  Row r of P_l: aggregate j = r / aggr, half = ((r % aggr) % dofi) >= h,
 // columns (2j + half)*NV + [0,NV).                                   (multigrid.py:203-227)
 template <typename T> struct TransferDev {

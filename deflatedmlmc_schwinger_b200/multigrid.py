@@ -305,7 +305,7 @@ class MG:
                 dev.set_bsr(i + 1, lv[i + 1].A.shape[0], nvec, col, vals)
         dev.set_coarsest_inverse(self.coarsest_inv)
         for i in range(nl - 1):
-            dev.set_smoother(i, harmonic_ritz_inv_roots(csr_matrix(lv[i].A), self.smoother_degree))
+            dev.set_smoother(i, harmonic_ritz_inv_roots(csr_matrix(lv[i].A), self.level_degree(i)))
         if use_permuted:
             for i in range(nl):
                 if i == 0:
@@ -315,6 +315,13 @@ class MG:
                     dev.set_perm(i, lv[i].perm_shift, cols, vals)
         dev.set_inner_precision(_lib.C64 if self.inner_precision == "c64" else _lib.C128)
         self.dev = dev
+
+    def level_degree(self, i):
+        """smoother polynomial degree on level i (smoother_degree may be an int or a per-level list)"""
+        d = self.smoother_degree
+        if isinstance(d, (list, tuple)):
+            return int(d[min(i, len(d) - 1)])
+        return int(d)
 
     # ---- device-side batched API ---------------------------------------------------------------
     def _to_dev(self, v):

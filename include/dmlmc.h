@@ -122,6 +122,10 @@ int dmlmc_level_sample_host(dmlmc_hier* h, int method, int level_f, int level_c,
                             const uint8_t* bits_host, int k, double tol, int restart, int maxiter,
                             double* e_host, int32_t* iters_host);
 
+/* solver options by name: "reorth" (1 = classical Gram-Schmidt with one re-orthogonalisation pass,
+ * default; 0 = single pass).  Unknown names are an error. */
+int dmlmc_set_option(dmlmc_hier* h, const char* name, double value);
+
 /* number of kernels launched by this handle since creation (bench.py's gpu_launches) */
 long long dmlmc_launch_count(dmlmc_hier* h);
 

@@ -126,7 +126,7 @@ def test_smoother_is_the_polynomial(mg128, dtype):
     mg, tp, A = mg128
     for lvl in range(3):
         Al = csr_matrix(mg.ml.levels[lvl].A)
-        w = harmonic_ritz_inv_roots(Al, mg.smoother_degree)
+        w = harmonic_ritz_inv_roots(Al, mg.level_degree(lvl))
         R = rnd(Al.shape[0], 4, dtype, 50 + lvl)
         E = mg.dev.smooth(lvl, R)
         r = host(R); e = np.zeros_like(r)
@@ -145,7 +145,7 @@ def _vcycle_numpy(mg, b, l0):
     if l0 == nl - 1:
         return mg.coarsest_inv @ b
     Al = csr_matrix(lv[l0].A)
-    w = harmonic_ritz_inv_roots(Al, mg.smoother_degree)
+    w = harmonic_ritz_inv_roots(Al, mg.level_degree(lvl))
     r = b.copy(); x = np.zeros_like(b)
     for wi in w:
         x = x + wi * r; r = r - wi * (Al @ r)
