@@ -145,7 +145,7 @@ def _vcycle_numpy(mg, b, l0):
     if l0 == nl - 1:
         return mg.coarsest_inv @ b
     Al = csr_matrix(lv[l0].A)
-    w = harmonic_ritz_inv_roots(Al, mg.level_degree(lvl))
+    w = harmonic_ritz_inv_roots(Al, mg.level_degree(l0))
     r = b.copy(); x = np.zeros_like(b)
     for wi in w:
         x = x + wi * r; r = r - wi * (Al @ r)
