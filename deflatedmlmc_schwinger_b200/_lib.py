@@ -29,6 +29,7 @@ _SIGS = {
     "dmlmc_set_transfer": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int,
                                           ctypes.c_int, ctypes.c_void_p]),
     "dmlmc_set_coarsest_inverse": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p]),
+    "dmlmc_set_dense_inverse": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_void_p]),
     "dmlmc_set_smoother": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_void_p]),
     "dmlmc_set_perm": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_void_p,
                                       ctypes.c_void_p]),
@@ -155,6 +156,10 @@ class Hierarchy:
         minv, p = _host_c128(minv)
         _check(self.lib.dmlmc_set_coarsest_inverse(self.h, minv.shape[0], p))
         self.sizes[self.n_levels - 1] = minv.shape[0]
+
+    def set_dense_inverse(self, level, minv):
+        minv, p = _host_c128(minv)
+        _check(self.lib.dmlmc_set_dense_inverse(self.h, level, minv.shape[0], p))
 
     def set_smoother(self, level, inv_roots):
         inv_roots, p = _host_c128(inv_roots)

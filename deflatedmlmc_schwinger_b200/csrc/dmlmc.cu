@@ -50,6 +50,7 @@ struct Level {
   std::vector<Cx<double>> inv_roots;      // smoother
   bool has_perm = false; int shift = 0, perm_nnz = 0; int* perm_cols = nullptr;
   int defl_d = 0; Cx<double>* defl_V = nullptr;
+  bool has_dense = false; Cx<double>* minv_d = nullptr; Cx<float>* minv_f = nullptr; float4* minv4 = nullptr;
   LevelT<double> d;
   LevelT<float> f;
 };
@@ -65,7 +66,6 @@ struct dmlmc_hier {
   cudaStream_t stream = nullptr;
   int n_levels = 0;
   Level lv[MAX_LEVELS];
-  int coarse_n = 0; Cx<double>* minv_d = nullptr; Cx<float>* minv_f = nullptr;
   int inner_prec = DMLMC_C64;
   int reorth = 1;
   char* ws = nullptr; size_t ws_bytes = 0, ws_off = 0;
@@ -219,21 +219,26 @@ template <typename T> int launch_prolong(dmlmc_hier* h, int level, const void* X
   return launch_prolong_nc<T, 1>(h, level, Xc, Xf, k);
 }
 
-template <typename T> Cx<T>* minv_of(dmlmc_hier* h);
-template <> Cx<double>* minv_of<double>(dmlmc_hier* h) { return h->minv_d; }
-template <> Cx<float>*  minv_of<float>(dmlmc_hier* h)  { return h->minv_f; }
+template <typename T> Cx<T>* minv_of(Level& L);
+template <> Cx<double>* minv_of<double>(Level& L) { return L.minv_d; }
+template <> Cx<float>*  minv_of<float>(Level& L)  { return L.minv_f; }
 
-template <typename T> int launch_dense(dmlmc_hier* h, const void* B, void* X, int k) {
-  if (h->coarse_n == 0) return fail(-1, "dmlmc: coarsest inverse not set");
-  const int n = h->coarse_n;
+// X = A_level^{-1} B with the level's dense inverse
+template <typename T> int launch_dense(dmlmc_hier* h, int level, const void* B, void* X, int k) {
+  Level& L = h->lv[level];
+  if (!L.has_dense) return fail(-1, "dmlmc: dense inverse of this level not set");
+  const int n = L.n;
   dim3 blk(32, 8);
   if (max_nc<T>() == 2 && (k % 2) == 0) {
     constexpr int NC = max_nc<T>(); const int kp = k / NC;
     dim3 grd((kp + 31) / 32, (n + 31) / 32);
-    dense_kernel<T, NC><<<grd, blk, 0, h->stream>>>(minv_of<T>(h), n, (const Pack<T, NC>*)B, (Pack<T, NC>*)X, kp);
+    if constexpr (std::is_same<T, float>::value)
+      dense_f32x2_kernel<<<grd, blk, 0, h->stream>>>(L.minv4, n, (const Pack<float, 2>*)B, (Pack<float, 2>*)X, kp);
+    else
+      dense_kernel<T, NC><<<grd, blk, 0, h->stream>>>(minv_of<T>(L), n, (const Pack<T, NC>*)B, (Pack<T, NC>*)X, kp);
   } else {
     dim3 grd((k + 31) / 32, (n + 31) / 32);
-    dense_kernel<T, 1><<<grd, blk, 0, h->stream>>>(minv_of<T>(h), n, (const Pack<T, 1>*)B, (Pack<T, 1>*)X, k);
+    dense_kernel<T, 1><<<grd, blk, 0, h->stream>>>(minv_of<T>(L), n, (const Pack<T, 1>*)B, (Pack<T, 1>*)X, k);
   }
   LAUNCH_CHECK(h);
   return 0;
@@ -290,24 +295,27 @@ template <typename T>
 int vcycle(dmlmc_hier* h, int level0, const void* Bin, void* Xout, int k) {
   const int nl = h->n_levels;
   CHECK(level0 >= 0 && level0 < nl, "vcycle: bad level");
-  if (level0 == nl - 1) return launch_dense<T>(h, Bin, Xout, k);
+  // the cycle bottoms out at the first level (from level0 down) that owns a dense inverse
+  int lb = level0;
+  while (lb < nl - 1 && !h->lv[lb].has_dense) ++lb;
+  if (lb == level0) return launch_dense<T>(h, level0, Bin, Xout, k);
   const size_t mark = h->ws_off;
   std::vector<void*> b(nl, nullptr), x(nl, nullptr), t0(nl, nullptr), t1(nl, nullptr);
-  for (int l = level0; l < nl; ++l) {
+  for (int l = level0; l <= lb; ++l) {
     const size_t cnt = (size_t)h->lv[l].n * k;
     if (l > level0) { Cx<T>* p; RET(ws_get<Cx<T>>(h, cnt, &p)); b[l] = p; RET(ws_get<Cx<T>>(h, cnt, &p)); x[l] = p; }
-    if (l < nl - 1) { Cx<T>* p; RET(ws_get<Cx<T>>(h, cnt, &p)); t0[l] = p; RET(ws_get<Cx<T>>(h, cnt, &p)); t1[l] = p; }
+    if (l < lb) { Cx<T>* p; RET(ws_get<Cx<T>>(h, cnt, &p)); t0[l] = p; RET(ws_get<Cx<T>>(h, cnt, &p)); t1[l] = p; }
   }
   x[level0] = Xout;
   const void* bl0 = Bin;
-  for (int l = level0; l < nl - 1; ++l) {
+  for (int l = level0; l < lb; ++l) {
     const void* bl = (l == level0) ? bl0 : b[l];
     const void* rfin = nullptr;
     RET(smooth<T>(h, l, bl, x[l], true, t0[l], t1[l], true, &rfin, k));
     RET(launch_restrict<T>(h, l, rfin, b[l + 1], k));
   }
-  RET(launch_dense<T>(h, b[nl - 1], x[nl - 1], k));
-  for (int l = nl - 2; l >= level0; --l) {
+  RET(launch_dense<T>(h, lb, b[lb], x[lb], k));
+  for (int l = lb - 1; l >= level0; --l) {
     const void* bl = (l == level0) ? bl0 : b[l];
     RET(launch_prolong<T>(h, l, x[l + 1], x[l], k));
     RET((launch_op<T, M_RES>(h, l, x[l], bl, t0[l], nullptr, cx<double>(0, 0), k)));
@@ -525,7 +533,7 @@ int level_sample(dmlmc_hier* h, int method, int lf, int lc, const Z* X0, int k, 
   if (skip) { RET(launch_restrict<double>(h, lf, rhs, Xm, k)); RET(launch_restrict<double>(h, lf + 1, Xm, Xc, k)); }
   else      { RET(launch_restrict<double>(h, lf, rhs, Xc, k)); }
   // y = A_c^{-1} xc                     utils.py:306-329
-  if (lc == nl - 1) RET(launch_dense<double>(h, Xc, Y, k));
+  if (lc == nl - 1) RET(launch_dense<double>(h, lc, Xc, Y, k));
   else RET(fgmres(h, lc, Xc, Y, k, tol, restart, maxiter, iters_host ? iters_host + k : nullptr, nullptr));
   // w = P (P) y ; e2 = x0^H w           utils.py:337-353  (w overwrites the solution buffer's sibling RHS)
   Z* Wf = RHS;     // RHS is no longer needed (rhs may alias X0/Xdef when no perm: then RHS is free as well)
@@ -641,15 +649,29 @@ int dmlmc_set_transfer(dmlmc_hier* h, int level, int n_f, int aggr_size, int dof
   return 0;
 }
 
-int dmlmc_set_coarsest_inverse(dmlmc_hier* h, int n, const double* minv_host) {
-  CHECK(h && n > 0 && minv_host, "set_coarsest_inverse: bad arguments");
+int dmlmc_set_dense_inverse(dmlmc_hier* h, int level, int n, const double* minv_host) {
+  CHECK(h && level >= 0 && level < h->n_levels && n > 0 && minv_host, "set_dense_inverse: bad arguments");
   CU(cudaSetDevice(h->device));
-  h->coarse_n = n;
-  Level& L = h->lv[h->n_levels - 1];
-  CHECK(L.n == 0 || L.n == n, "set_coarsest_inverse: size does not match the coarsest level");
+  Level& L = h->lv[level];
+  CHECK(L.n == 0 || L.n == n, "set_dense_inverse: size does not match the level");
   L.n = n;
-  RET(upload_cx(h, minv_host, (size_t)n * n, &h->minv_d, &h->minv_f));
+  RET(upload_cx(h, minv_host, (size_t)n * n, &L.minv_d, &L.minv_f));
+  {
+    const size_t cnt = (size_t)n * n;
+    std::vector<float4> v4(cnt);
+    for (size_t i = 0; i < cnt; ++i) {
+      const float mr = (float)minv_host[2 * i], mi = (float)minv_host[2 * i + 1];
+      v4[i] = make_float4(mr, mr, mi, mi);
+    }
+    RET(upload<float4>(h, v4.data(), cnt, &L.minv4));
+  }
+  L.has_dense = true;
   return 0;
+}
+
+int dmlmc_set_coarsest_inverse(dmlmc_hier* h, int n, const double* minv_host) {
+  CHECK(h != nullptr, "NULL handle");
+  return dmlmc_set_dense_inverse(h, h->n_levels - 1, n, minv_host);
 }
 
 int dmlmc_set_smoother(dmlmc_hier* h, int level, int degree, const double* inv_roots_host) {
@@ -710,7 +732,8 @@ int dmlmc_prolong_add(dmlmc_hier* h, int level, int prec, const void* Xc, void* 
 }
 int dmlmc_coarsest_apply(dmlmc_hier* h, int prec, const void* B, void* X, int k) {
   ENTER(h); CHECK_PREC(prec); CHECK(B && X && k >= 1, "coarsest_apply: bad arguments");
-  return prec == DMLMC_C128 ? launch_dense<double>(h, B, X, k) : launch_dense<float>(h, B, X, k);
+  const int lc = h->n_levels - 1;
+  return prec == DMLMC_C128 ? launch_dense<double>(h, lc, B, X, k) : launch_dense<float>(h, lc, B, X, k);
 }
 int dmlmc_smooth(dmlmc_hier* h, int level, int prec, const void* R, void* E, int k) {
   ENTER(h); CHECK_LEVEL(h, level); CHECK_PREC(prec); CHECK(R && E && k >= 1, "smooth: bad arguments");
@@ -778,6 +801,7 @@ int dmlmc_fgmres(dmlmc_hier* h, int level, const void* B, void* X, int k, double
                  int32_t* iters_host, double* relres_host) {
   ENTER(h); CHECK_LEVEL(h, level); CHECK(B && X && B != X, "fgmres: bad arguments");
   if (level == h->n_levels - 1) return fail(-1, "fgmres: the coarsest level is solved by dmlmc_coarsest_apply");
+  if (h->lv[level].kind < 0) return fail(-1, "fgmres: operator of this level not set");
   return fgmres(h, level, (const Z*)B, (Z*)X, k, tol, restart, maxiter, iters_host, relres_host);
 }
 int dmlmc_level_sample(dmlmc_hier* h, int method, int level_f, int level_c, const void* X0, int k, double tol,

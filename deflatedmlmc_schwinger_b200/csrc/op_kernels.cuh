@@ -313,6 +313,54 @@ dense_kernel(const Cx<T>* __restrict__ M, int n, const Pack<T, NC>* __restrict__
   }
 }
 
+// complex64 dense apply with packed FP32 FMA: M4[n][n] holds (mr,mr,mi,mi) per entry.  32 x (32 packs)
+// output tile per CTA, thread (tx,ty) owns rows ty+8r (r<4) of pack tx; per k-step 1 LDS.128 of B and
+// 4 broadcast LDS.128 of M feed 16 FFMA2.
+__global__ void __launch_bounds__(256)
+dense_f32x2_kernel(const float4* __restrict__ M4, int n, const Pack<float, 2>* __restrict__ B,
+                   Pack<float, 2>* __restrict__ X, int kp) {
+  __shared__ float4 Ms[32][33];
+  __shared__ float4 Bs[32][32];
+  const int tx = threadIdx.x, ty = threadIdx.y;
+  const int cp = blockIdx.x * 32 + tx;
+  const int i0 = blockIdx.y * 32;
+  const float4* B4 = reinterpret_cast<const float4*>(B);
+  float4 a[4], b[4];
+#pragma unroll
+  for (int r = 0; r < 4; ++r) { a[r] = make_float4(0.f, 0.f, 0.f, 0.f); b[r] = make_float4(0.f, 0.f, 0.f, 0.f); }
+  const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int j0 = 0; j0 < n; j0 += 32) {
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+      const int i = i0 + ty + 8 * r, j = j0 + tx;
+      Ms[ty + 8 * r][tx] = (i < n && j < n) ? __ldg(M4 + (size_t)i * n + j) : z4;
+      const int jr = j0 + ty + 8 * r;
+      Bs[ty + 8 * r][tx] = (jr < n && cp < kp) ? __ldg(B4 + (size_t)jr * kp + cp) : z4;
+    }
+    __syncthreads();
+#pragma unroll 8
+    for (int jj = 0; jj < 32; ++jj) {
+      const float4 x = Bs[jj][tx];
+#pragma unroll
+      for (int r = 0; r < 4; ++r) {
+        const float4 m = Ms[ty + 8 * r][jj];
+        fma2x(a[r], make_float2(m.x, m.y), x);
+        fma2x(b[r], make_float2(m.z, m.w), x);
+      }
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int r = 0; r < 4; ++r) {
+    const int i = i0 + ty + 8 * r;
+    if (i < n && cp < kp) {
+      Pack<float, 2> o;
+      o.d[0] = a[r].x - b[r].y; o.d[1] = a[r].y + b[r].x; o.d[2] = a[r].z - b[r].w; o.d[3] = a[r].w + b[r].z;
+      X[(size_t)i * kp + cp] = o;
+    }
+  }
+}
+
 // ------------------------------------------------------------------------------------------
 // RHS[i] = sum_j vals[i][j] X[(cols[i][j] - shift) mod n]   (nnz == 0: RHS[i] = X[(i - shift) mod n])
 template <typename T, int NC>

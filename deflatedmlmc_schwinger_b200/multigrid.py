@@ -174,7 +174,7 @@ class MG:
     """Same public surface as the reference's MG (multigrid.py:56-557)."""
 
     def __init__(self, A, smooth_iters=2, smoother_degree=32, restart=40, inner_precision="c64",
-                 device=None):
+                 device=None, dense_coarse_threshold=2048):
         self.level_nr = 0
         self.ml = []
         self.A = A
@@ -197,6 +197,8 @@ class MG:
         self.restart = restart
         self.inner_precision = inner_precision
         self.device = device
+        self.dense_coarse_threshold = dense_coarse_threshold
+        self.dense_level = None              # level at which the V-cycle bottoms out with a dense inverse
         self.dev = None                      # _lib.Hierarchy
         self.test_vectors = []
         self.level_shapes = []
@@ -315,6 +317,21 @@ class MG:
                     dev.set_perm(i, lv[i].perm_shift, cols, vals)
         dev.set_inner_precision(_lib.C64 if self.inner_precision == "c64" else _lib.C128)
         self.dev = dev
+        # V-cycle bottom: the finest intermediate level small enough for a dense inverse, computed with
+        # the batched device solver itself (A_l X = I, all n_l columns in one batch)
+        self.dense_level = nl - 1
+        for i in range(1, nl - 1):
+            n_i = lv[i].A.shape[0]
+            if n_i <= self.dense_coarse_threshold:
+                import torch
+                eye = torch.eye(n_i, dtype=torch.complex128, device=dev.device)
+                Minv, _, relres = dev.fgmres(i, eye, 1e-13, restart=min(self.restart, n_i), maxiter=n_i)
+                if not np.all(relres < 1e-12):
+                    raise Exception("dense coarse inverse: the device solve did not converge")
+                dev.set_dense_inverse(i, Minv.cpu().numpy())
+                self.dense_level = i
+                del eye, Minv
+                break
 
     def level_degree(self, i):
         """smoother polynomial degree on level i (smoother_degree may be an int or a per-level list)"""

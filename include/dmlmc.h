@@ -61,6 +61,9 @@ int dmlmc_set_transfer(dmlmc_hier* h, int level, int n_f, int aggr_size, int dof
                        const double* pvals_host);
 /* dense inverse of the coarsest operator (multigrid.py:342-344), row-major n x n complex128 */
 int dmlmc_set_coarsest_inverse(dmlmc_hier* h, int n, const double* minv_host);
+/* optional dense inverse of an intermediate level: the V-cycle then bottoms out there (exact coarse
+ * solve) instead of recursing to the coarsest level.  Same layout as dmlmc_set_coarsest_inverse. */
+int dmlmc_set_dense_inverse(dmlmc_hier* h, int level, int n, const double* minv_host);
 /* smoother on `level`: e = p(A) r with p given by its `degree` inverse roots (complex128),
  * applied as Richardson steps in the given order.  Replaces the lgmres call of
  * multigrid.py:393-394 / 438-439 (FGMRES is flexible: parity is on the converged solve). */

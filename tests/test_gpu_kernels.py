@@ -144,6 +144,8 @@ def _vcycle_numpy(mg, b, l0):
     nl = len(lv)
     if l0 == nl - 1:
         return mg.coarsest_inv @ b
+    if l0 >= mg.dense_level:
+        return np.linalg.solve(lv[l0].A.toarray(), b)
     Al = csr_matrix(lv[l0].A)
     w = harmonic_ritz_inv_roots(Al, mg.level_degree(l0))
     r = b.copy(); x = np.zeros_like(b)
@@ -163,7 +165,7 @@ def test_vcycle_matches_numpy_restatement(mg128, l0):
     B = rnd(n, 3, torch.complex128, 60 + l0)
     X = mg.dev.vcycle(l0, B)
     ref = _vcycle_numpy(mg, host(B), l0)
-    assert relerr(host(X), ref) < 1e-9
+    assert relerr(host(X), ref) < 1e-8
     Xf = mg.dev.vcycle(l0, B.to(torch.complex64))
     assert relerr(host(Xf), ref) < 5e-3
 
