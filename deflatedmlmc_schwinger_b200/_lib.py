@@ -30,7 +30,8 @@ _SIGS = {
                                           ctypes.c_int, ctypes.c_void_p]),
     "dmlmc_set_coarsest_inverse": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p]),
     "dmlmc_set_dense_inverse": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_void_p]),
-    "dmlmc_set_smoother": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_void_p]),
+    "dmlmc_set_smoother": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_void_p,
+                                          ctypes.c_double, ctypes.c_double]),
     "dmlmc_set_perm": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_void_p,
                                       ctypes.c_void_p]),
     "dmlmc_set_deflation": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_void_p]),
@@ -57,6 +58,7 @@ _SIGS = {
                                                ctypes.c_void_p]),
     "dmlmc_set_option": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_char_p, ctypes.c_double]),
     "dmlmc_launch_count": (ctypes.c_longlong, [ctypes.c_void_p]),
+    "dmlmc_vcycle_chunk_cols": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_int]),
 }
 
 EXPORTED_SYMBOLS = tuple(_SIGS.keys())
@@ -76,7 +78,7 @@ def load():
         fn = getattr(lib, name)          # AttributeError if the ABI is incomplete
         fn.restype = res
         fn.argtypes = args
-    if lib.dmlmc_abi_version() != 1:
+    if lib.dmlmc_abi_version() != 2:
         raise RuntimeError("libdmlmc_sm100.so ABI version mismatch")
     _lib = lib
     return lib
@@ -161,9 +163,11 @@ class Hierarchy:
         minv, p = _host_c128(minv)
         _check(self.lib.dmlmc_set_dense_inverse(self.h, level, minv.shape[0], p))
 
-    def set_smoother(self, level, inv_roots):
-        inv_roots, p = _host_c128(inv_roots)
-        _check(self.lib.dmlmc_set_smoother(self.h, level, inv_roots.shape[0], p))
+    def set_smoother(self, level, nu, p0):
+        """p(A) = p0 * prod_i (I - nu[i] A)"""
+        nu, p = _host_c128(np.asarray(nu).reshape(-1))
+        _check(self.lib.dmlmc_set_smoother(self.h, level, nu.shape[0], p if nu.shape[0] else None,
+                                           float(np.real(p0)), float(np.imag(p0))))
 
     def set_perm(self, level, shift, cols=None, vals=None):
         if cols is None:
@@ -307,3 +311,6 @@ class Hierarchy:
 
     def launch_count(self):
         return int(self.lib.dmlmc_launch_count(self.h))
+
+    def vcycle_chunk_cols(self, level, prec, k):
+        return int(self.lib.dmlmc_vcycle_chunk_cols(self.h, level, prec, k))

@@ -47,7 +47,8 @@ struct Level {
   int LX = 0, LT = 0;
   int bs = 0, bpr = 0, nb = 0; int* bsr_col = nullptr; float4* bsr_vals4 = nullptr;   // (mr,mr,mi,mi) per entry
   bool has_transfer = false; int aggr = 0, dofi = 0, nvec = 0, n_c = 0;
-  std::vector<Cx<double>> inv_roots;      // smoother
+  // smoother polynomial in product form: p(A) = p0 * prod_i (I - nu_i A)
+  bool has_smoother = false; std::vector<Cx<double>> nu; Cx<double> p0;
   bool has_perm = false; int shift = 0, perm_nnz = 0; int* perm_cols = nullptr;
   int defl_d = 0; Cx<double>* defl_V = nullptr;
   bool has_dense = false; Cx<double>* minv_d = nullptr; Cx<float>* minv_f = nullptr; float4* minv4 = nullptr;
@@ -67,7 +68,11 @@ struct dmlmc_hier {
   int n_levels = 0;
   Level lv[MAX_LEVELS];
   int inner_prec = DMLMC_C64;
-  int reorth = 1;
+  int reorth = 0;
+  int stencil_by = 4, stencil_bz = 4;     // site tile (t, x) of the stencil kernel's thread block
+  int stencil_minb = 3;                   // resident 512-thread blocks per SM the stencil kernel is compiled for
+  int chunk_cols = 0;                     // V-cycle column chunk (0 = sized from l2_budget_mb)
+  double l2_budget_mb = 0.0;              // MB the per-chunk working vectors may occupy (0 = no chunking)
   char* ws = nullptr; size_t ws_bytes = 0, ws_off = 0;
   int* h_nactive = nullptr;        // pinned
   long long launches = 0;
@@ -117,16 +122,21 @@ template <typename T> int ws_get(dmlmc_hier* h, size_t count, T** out) {
 
 // ---- operator dispatch ----------------------------------------------------------------------
 template <typename T, int NC, int MODE>
-int launch_op_nc(dmlmc_hier* h, int level, const void* X, const void* B, void* Y, void* E, Cx<double> w, int k) {
+int launch_op_nc(dmlmc_hier* h, int level, const void* X, const void* B, void* Y, Cx<double> w, Cx<double> c, int k) {
   Level& L = h->lv[level];
   LevelT<T>& D = Sel<T>::get(L);
   const int kp = k / NC;
   typedef Pack<T, NC> P;
-  const Cx<T> wt = cx<T>((T)w.re, (T)w.im);
+  const Cx<T> wt = cx<T>((T)w.re, (T)w.im), ct = cx<T>((T)c.re, (T)c.im);
   if (L.kind == 0) {
     StencilDev<T> op; op.LX = L.LX; op.LT = L.LT; op.Ut = D.Ut; op.Ux = D.Ux; op.diag = D.diag;
-    const size_t total = (size_t)L.LX * L.LT * kp;
-    stencil_kernel<T, NC, MODE><<<nblocks(total, 256), 256, 0, h->stream>>>(op, (const P*)X, (const P*)B, (P*)Y, (P*)E, wt, kp);
+    int bx = 1; while (bx < 32 && bx < kp) bx *= 2;
+    int by = std::max(1, std::min(h->stencil_by, L.LT)), bz = std::max(1, std::min(h->stencil_bz, L.LX));
+    while (bx * by * bz > 512) { if (bz > 1) bz /= 2; else by /= 2; }
+    while (bx * by * bz < 256 && by < L.LT) by *= 2;
+    dim3 blk(bx, by, bz), grd((kp + bx - 1) / bx, (L.LT + by - 1) / by, (L.LX + bz - 1) / bz);
+    if (h->stencil_minb == 3) stencil_kernel<T, NC, MODE, 3><<<grd, blk, 0, h->stream>>>(op, (const P*)X, (const P*)B, (P*)Y, wt, ct, kp);
+    else                      stencil_kernel<T, NC, MODE, 2><<<grd, blk, 0, h->stream>>>(op, (const P*)X, (const P*)B, (P*)Y, wt, ct, kp);
   } else if (L.kind == 1) {
     if constexpr (std::is_same<T, float>::value && NC == 2) {
       // Blackwell FFMA2 + shared-memory path for the complex64 V-cycle
@@ -141,7 +151,7 @@ int launch_op_nc(dmlmc_hier* h, int level, const void* X, const void* B, void* Y
       if (smem <= 48 * 1024 && L.bs >= 2) {
         dim3 blk(tpr, RB), grd((L.nb + RB - 1) / RB, (kp + tpr * PPT - 1) / (tpr * PPT));
 #define BSR2(BS_, PPT_) bsr_f32x2_kernel<BS_, PPT_, MODE><<<grd, blk, smem, h->stream>>>(L.nb, L.bpr, L.bsr_col, L.bsr_vals4, \
-            (const P*)X, (const P*)B, (P*)Y, (P*)E, wt, kp)
+            (const P*)X, (const P*)B, (P*)Y, wt, ct, kp)
         if (L.bs == 2) BSR2(2, 2); else if (L.bs == 4) BSR2(4, 2); else BSR2(8, 1);
 #undef BSR2
         LAUNCH_CHECK(h);
@@ -152,10 +162,10 @@ int launch_op_nc(dmlmc_hier* h, int level, const void* X, const void* B, void* Y
     const size_t total = (size_t)L.nb * kp;
     const unsigned g = nblocks(total, 128);
     switch (L.bs) {
-      case 1: bsr_kernel<T, NC, 1, MODE><<<g, 128, 0, h->stream>>>(op, (const P*)X, (const P*)B, (P*)Y, (P*)E, wt, kp); break;
-      case 2: bsr_kernel<T, NC, 2, MODE><<<g, 128, 0, h->stream>>>(op, (const P*)X, (const P*)B, (P*)Y, (P*)E, wt, kp); break;
-      case 4: bsr_kernel<T, NC, 4, MODE><<<g, 128, 0, h->stream>>>(op, (const P*)X, (const P*)B, (P*)Y, (P*)E, wt, kp); break;
-      case 8: bsr_kernel<T, NC, 8, MODE><<<g, 128, 0, h->stream>>>(op, (const P*)X, (const P*)B, (P*)Y, (P*)E, wt, kp); break;
+      case 1: bsr_kernel<T, NC, 1, MODE><<<g, 128, 0, h->stream>>>(op, (const P*)X, (const P*)B, (P*)Y, wt, ct, kp); break;
+      case 2: bsr_kernel<T, NC, 2, MODE><<<g, 128, 0, h->stream>>>(op, (const P*)X, (const P*)B, (P*)Y, wt, ct, kp); break;
+      case 4: bsr_kernel<T, NC, 4, MODE><<<g, 128, 0, h->stream>>>(op, (const P*)X, (const P*)B, (P*)Y, wt, ct, kp); break;
+      case 8: bsr_kernel<T, NC, 8, MODE><<<g, 128, 0, h->stream>>>(op, (const P*)X, (const P*)B, (P*)Y, wt, ct, kp); break;
       default: return fail(-1, "dmlmc: unsupported BSR block size");
     }
   } else {
@@ -166,14 +176,17 @@ int launch_op_nc(dmlmc_hier* h, int level, const void* X, const void* B, void* Y
 }
 template <typename T> constexpr int max_nc() { return sizeof(T) == 4 ? 2 : 1; }
 
+// X, B, Y: compact [n_level][k]
 template <typename T, int MODE>
-int launch_op(dmlmc_hier* h, int level, const void* X, const void* B, void* Y, void* E, Cx<double> w, int k) {
-  if (max_nc<T>() == 2 && (k % 2) == 0) return launch_op_nc<T, max_nc<T>(), MODE>(h, level, X, B, Y, E, w, k);
-  return launch_op_nc<T, 1, MODE>(h, level, X, B, Y, E, w, k);
+int launch_op(dmlmc_hier* h, int level, const void* X, const void* B, void* Y, Cx<double> w, Cx<double> c, int k) {
+  if (max_nc<T>() == 2 && (k % 2) == 0) return launch_op_nc<T, max_nc<T>(), MODE>(h, level, X, B, Y, w, c, k);
+  return launch_op_nc<T, 1, MODE>(h, level, X, B, Y, w, c, k);
 }
+const Cx<double> ZERO = {0.0, 0.0};
 
+// transfers on k columns; rows of the fine / coarse arrays are ldf / ldc complex elements apart
 template <typename T, int NC>
-int launch_restrict_nc(dmlmc_hier* h, int level, const void* Xf, void* Xc, int k) {
+int launch_restrict_nc(dmlmc_hier* h, int level, const void* Xf, void* Xc, int k, int ldf, int ldc) {
   Level& L = h->lv[level];
   TransferDev<T> tr; tr.n_f = L.n; tr.n_c = L.n_c; tr.aggr = L.aggr; tr.dofi = L.dofi; tr.h = L.dofi / 2; tr.nvec = L.nvec;
   tr.pv = Sel<T>::get(L).pv;
@@ -181,22 +194,28 @@ int launch_restrict_nc(dmlmc_hier* h, int level, const void* Xf, void* Xc, int k
   const size_t total = (size_t)(L.n_c / L.nvec) * kp;
   const unsigned g = nblocks(total, 128);
   switch (L.nvec) {
-    case 1: restrict_kernel<T, NC, 1><<<g, 128, 0, h->stream>>>(tr, (const P*)Xf, (P*)Xc, kp); break;
-    case 2: restrict_kernel<T, NC, 2><<<g, 128, 0, h->stream>>>(tr, (const P*)Xf, (P*)Xc, kp); break;
-    case 4: restrict_kernel<T, NC, 4><<<g, 128, 0, h->stream>>>(tr, (const P*)Xf, (P*)Xc, kp); break;
-    case 8: restrict_kernel<T, NC, 8><<<g, 128, 0, h->stream>>>(tr, (const P*)Xf, (P*)Xc, kp); break;
+    case 1: restrict_kernel<T, NC, 1><<<g, 128, 0, h->stream>>>(tr, (const P*)Xf, (P*)Xc, kp, ldf / NC, ldc / NC); break;
+    case 2: restrict_kernel<T, NC, 2><<<g, 128, 0, h->stream>>>(tr, (const P*)Xf, (P*)Xc, kp, ldf / NC, ldc / NC); break;
+    case 4: restrict_kernel<T, NC, 4><<<g, 128, 0, h->stream>>>(tr, (const P*)Xf, (P*)Xc, kp, ldf / NC, ldc / NC); break;
+    case 8: restrict_kernel<T, NC, 8><<<g, 128, 0, h->stream>>>(tr, (const P*)Xf, (P*)Xc, kp, ldf / NC, ldc / NC); break;
     default: return fail(-1, "dmlmc: unsupported number of test vectors");
   }
   LAUNCH_CHECK(h);
   return 0;
 }
-template <typename T> int launch_restrict(dmlmc_hier* h, int level, const void* Xf, void* Xc, int k) {
+inline bool pack2_ok(const void* a, const void* b, int k, int ldf, int ldc) {
+  return (k % 2) == 0 && (ldf % 2) == 0 && (ldc % 2) == 0 && ((uintptr_t)a % 16) == 0 && ((uintptr_t)b % 16) == 0;
+}
+template <typename T> int launch_restrict(dmlmc_hier* h, int level, const void* Xf, void* Xc, int k, int ldf, int ldc) {
   if (!h->lv[level].has_transfer) return fail(-1, "dmlmc: transfer operator of this level not set");
-  if (max_nc<T>() == 2 && (k % 2) == 0) return launch_restrict_nc<T, max_nc<T>()>(h, level, Xf, Xc, k);
-  return launch_restrict_nc<T, 1>(h, level, Xf, Xc, k);
+  if (max_nc<T>() == 2 && pack2_ok(Xf, Xc, k, ldf, ldc)) return launch_restrict_nc<T, max_nc<T>()>(h, level, Xf, Xc, k, ldf, ldc);
+  return launch_restrict_nc<T, 1>(h, level, Xf, Xc, k, ldf, ldc);
+}
+template <typename T> int launch_restrict(dmlmc_hier* h, int level, const void* Xf, void* Xc, int k) {
+  return launch_restrict<T>(h, level, Xf, Xc, k, k, k);
 }
 template <typename T, int NC>
-int launch_prolong_nc(dmlmc_hier* h, int level, const void* Xc, void* Xf, int k) {
+int launch_prolong_nc(dmlmc_hier* h, int level, const void* Xc, void* Xf, int k, int ldf, int ldc) {
   Level& L = h->lv[level];
   TransferDev<T> tr; tr.n_f = L.n; tr.n_c = L.n_c; tr.aggr = L.aggr; tr.dofi = L.dofi; tr.h = L.dofi / 2; tr.nvec = L.nvec;
   tr.pv = Sel<T>::get(L).pv;
@@ -204,19 +223,22 @@ int launch_prolong_nc(dmlmc_hier* h, int level, const void* Xc, void* Xf, int k)
   const size_t total = (size_t)L.n * kp;
   const unsigned g = nblocks(total, 256);
   switch (L.nvec) {
-    case 1: prolong_add_kernel<T, NC, 1><<<g, 256, 0, h->stream>>>(tr, (const P*)Xc, (P*)Xf, kp); break;
-    case 2: prolong_add_kernel<T, NC, 2><<<g, 256, 0, h->stream>>>(tr, (const P*)Xc, (P*)Xf, kp); break;
-    case 4: prolong_add_kernel<T, NC, 4><<<g, 256, 0, h->stream>>>(tr, (const P*)Xc, (P*)Xf, kp); break;
-    case 8: prolong_add_kernel<T, NC, 8><<<g, 256, 0, h->stream>>>(tr, (const P*)Xc, (P*)Xf, kp); break;
+    case 1: prolong_add_kernel<T, NC, 1><<<g, 256, 0, h->stream>>>(tr, (const P*)Xc, (P*)Xf, kp, ldf / NC, ldc / NC); break;
+    case 2: prolong_add_kernel<T, NC, 2><<<g, 256, 0, h->stream>>>(tr, (const P*)Xc, (P*)Xf, kp, ldf / NC, ldc / NC); break;
+    case 4: prolong_add_kernel<T, NC, 4><<<g, 256, 0, h->stream>>>(tr, (const P*)Xc, (P*)Xf, kp, ldf / NC, ldc / NC); break;
+    case 8: prolong_add_kernel<T, NC, 8><<<g, 256, 0, h->stream>>>(tr, (const P*)Xc, (P*)Xf, kp, ldf / NC, ldc / NC); break;
     default: return fail(-1, "dmlmc: unsupported number of test vectors");
   }
   LAUNCH_CHECK(h);
   return 0;
 }
-template <typename T> int launch_prolong(dmlmc_hier* h, int level, const void* Xc, void* Xf, int k) {
+template <typename T> int launch_prolong(dmlmc_hier* h, int level, const void* Xc, void* Xf, int k, int ldf, int ldc) {
   if (!h->lv[level].has_transfer) return fail(-1, "dmlmc: transfer operator of this level not set");
-  if (max_nc<T>() == 2 && (k % 2) == 0) return launch_prolong_nc<T, max_nc<T>()>(h, level, Xc, Xf, k);
-  return launch_prolong_nc<T, 1>(h, level, Xc, Xf, k);
+  if (max_nc<T>() == 2 && pack2_ok(Xf, Xc, k, ldf, ldc)) return launch_prolong_nc<T, max_nc<T>()>(h, level, Xc, Xf, k, ldf, ldc);
+  return launch_prolong_nc<T, 1>(h, level, Xc, Xf, k, ldf, ldc);
+}
+template <typename T> int launch_prolong(dmlmc_hier* h, int level, const void* Xc, void* Xf, int k) {
+  return launch_prolong<T>(h, level, Xc, Xf, k, k, k);
 }
 
 template <typename T> Cx<T>* minv_of(Level& L);
@@ -244,94 +266,141 @@ template <typename T> int launch_dense(dmlmc_hier* h, int level, const void* B, 
   return 0;
 }
 
-// E += w * R (elementwise), used for the last Richardson step of the post-smoother
-template <typename T>
-__global__ void __launch_bounds__(256) axpy_w_kernel(Cx<T> w, const Cx<T>* __restrict__ R, Cx<T>* __restrict__ E, size_t count) {
-  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= count) return;
-  Pack<T, 1> e = *reinterpret_cast<const Pack<T, 1>*>(E + i);
-  pfma<T, 1>(e, w, *reinterpret_cast<const Pack<T, 1>*>(R + i));
-  *reinterpret_cast<Pack<T, 1>*>(E + i) = e;
-}
-template <typename T> int launch_axpy_w(dmlmc_hier* h, Cx<double> w, const void* R, void* E, size_t count) {
-  axpy_w_kernel<T><<<nblocks(count, 256), 256, 0, h->stream>>>(cx<T>((T)w.re, (T)w.im), (const Cx<T>*)R, (Cx<T>*)E, count);
+// Out[:, 0:w] = (Tout) In[:, 0:w] between batches with leading dimensions ld_in / ld_out
+template <typename Tin, typename Tout>
+int cvt_cols(dmlmc_hier* h, const Cx<Tin>* in, size_t ld_in, Cx<Tout>* out, size_t ld_out, int n, int w) {
+  if (std::is_same<Tin, Tout>::value && (const void*)in == (const void*)out) return 0;
+  cvt_cols_kernel<Tin, Tout><<<nblocks((size_t)n * w, 256), 256, 0, h->stream>>>(in, ld_in, out, ld_out, n, w);
   LAUNCH_CHECK(h);
   return 0;
 }
 
-// ---- smoother: e = p(A) r by Richardson steps, r_{i+1} = r_i - w_i A r_i, e += w_i r_i --------
-// On return *r_final points to the buffer (t0 or t1) holding the final residual if need_residual;
-// otherwise the last step skips the operator application.
+// ---- smoother: E (+)= p(A) R with p in product form, p(A) = p0 prod_i (I - nu_i A) ---------------
+// One fused kernel per factor (operator + update: read x, write x'), no reductions, no host
+// synchronisation.  R, E, t0, t1: compact [n_level][k]; R may alias t0; E must not alias R, t0, t1.
 template <typename T>
-int smooth(dmlmc_hier* h, int level, const void* R, void* E, bool e_is_zero, void* t0, void* t1,
-           bool need_residual, const void** r_final, int k) {
+int smooth_apply(dmlmc_hier* h, int level, const void* R, void* E, bool acc, void* t0, void* t1, int k) {
   Level& L = h->lv[level];
-  const int d = (int)L.inv_roots.size();
-  if (d < 1) return fail(-1, "dmlmc: smoother of this level not set");
-  const void* rin = R;
-  void* bufs[2] = {t0, t1};
-  int nb = 0;
-  for (int i = 0; i < d; ++i) {
-    const bool last = (i == d - 1);
-    const bool first = e_is_zero && i == 0;
-    if (last && !need_residual) {
-      if (first) {   // degree-1 smoother on a zero start: E = w R
-        CU(cudaMemsetAsync(E, 0, (size_t)L.n * k * sizeof(Cx<T>), h->stream));
-      }
-      RET(launch_axpy_w<T>(h, L.inv_roots[i], rin, E, (size_t)L.n * k));
-      break;
-    }
-    void* rout = bufs[nb]; nb ^= 1;
-    if (first) RET((launch_op<T, M_SMOOTH_FIRST>(h, level, rin, nullptr, rout, E, L.inv_roots[i], k)));
-    else       RET((launch_op<T, M_SMOOTH>(h, level, rin, nullptr, rout, E, L.inv_roots[i], k)));
-    rin = rout;
+  if (!L.has_smoother) return fail(-1, "dmlmc: smoother of this level not set");
+  const int m = (int)L.nu.size();
+  if (m == 0) {
+    const size_t cnt = (size_t)L.n * k;
+    const Cx<T> c = cx<T>((T)L.p0.re, (T)L.p0.im);
+    if (acc) scale_kernel<T, 1><<<nblocks(cnt, 256), 256, 0, h->stream>>>(c, (const Cx<T>*)R, (Cx<T>*)E, cnt);
+    else     scale_kernel<T, 0><<<nblocks(cnt, 256), 256, 0, h->stream>>>(c, (const Cx<T>*)R, (Cx<T>*)E, cnt);
+    LAUNCH_CHECK(h);
+    return 0;
   }
-  if (r_final) *r_final = rin;
+  void* pp[2] = {t0, t1};
+  if (R == t0) { pp[0] = t1; pp[1] = t0; }
+  const void* in = R;
+  for (int i = 0; i < m; ++i) {
+    if (i == m - 1) {
+      if (acc) RET((launch_op<T, M_STEP_ACC>(h, level, in, nullptr, E, L.nu[i], L.p0, k)));
+      else     RET((launch_op<T, M_STEP_SET>(h, level, in, nullptr, E, L.nu[i], L.p0, k)));
+    } else {
+      void* out = pp[i & 1];
+      RET((launch_op<T, M_STEP>(h, level, in, nullptr, out, L.nu[i], ZERO, k)));
+      in = out;
+    }
+  }
   return 0;
 }
 
+// columns per chunk on `level`.  With option "l2_budget_mb" > 0 the chunk's working vectors (b, x and
+// the smoother's ping-pong pair) are sized to stay resident in the 126 MB L2 while the level's
+// ~2(d+1) kernels run over them.  Measured on B200 (profiles/r1_run4_*): the level-0 kernel is not
+// DRAM-bound enough for this to pay (8.9 us per 64-column launch vs 29 us per 256-column launch), so
+// the default is one chunk.
+int chunk_cols(dmlmc_hier* h, int level, int k, size_t elem) {
+  if (h->chunk_cols > 0) return std::min(k, std::max(2, h->chunk_cols & ~1));
+  if (h->l2_budget_mb <= 0.0) return k;
+  const double per_col = 4.0 * (double)h->lv[level].n * (double)elem;
+  long kc = (long)(h->l2_budget_mb * 1048576.0 / per_col);
+  long c = 64; while (c * 2 <= kc) c *= 2;      // 64 * 2^a: chunks of a level nest in those of the next
+  return c >= k ? k : (int)c;
+}
+
 // ---- V-cycle (multigrid.py:369-447) -----------------------------------------------------------
-template <typename T>
+// B, X: [n_level0][k] of scalar TIO; the cycle computes in T on compact per-level arrays stored as
+// consecutive column chunks [chunk][n_l][w].  Per level: for every chunk (pre-smooth, residual,
+// restrict), then the coarser level on all k columns, then for every chunk (prolong, residual,
+// post-smooth).
+template <typename T> struct VcBuf { Cx<T>* b = nullptr; Cx<T>* x = nullptr; Cx<T>* t0 = nullptr; Cx<T>* t1 = nullptr; int kc = 0; };
+
+template <typename T, typename TIO>
+int vcycle_level(dmlmc_hier* h, int l, int level0, int lb, std::vector<VcBuf<T>>& vb, const Cx<TIO>* Bio, Cx<TIO>* Xio, int k) {
+  Level& L = h->lv[l];
+  const int n = L.n;
+  VcBuf<T>& me = vb[l];
+  if (l == lb) {
+    for (int col0 = 0; col0 < k; col0 += me.kc) {
+      const int w = std::min(me.kc, k - col0);
+      RET(launch_dense<T>(h, l, me.b + (size_t)col0 * n, me.x + (size_t)col0 * n, w));
+    }
+    return 0;
+  }
+  VcBuf<T>& co = vb[l + 1];
+  const int nc = h->lv[l + 1].n;
+  for (int phase = 0; phase < 2; ++phase) {
+    for (int col0 = 0; col0 < k; col0 += me.kc) {
+      const int w = std::min(me.kc, k - col0);
+      Cx<T>* bc = me.b + (size_t)col0 * n;
+      Cx<T>* xc = me.x + (size_t)col0 * n;
+      const int C0 = (col0 / co.kc) * co.kc, wC = std::min(co.kc, k - C0);
+      const size_t coff = (size_t)C0 * nc + (col0 - C0);
+      if (phase == 0) {
+        if (l == level0) RET((cvt_cols<TIO, T>(h, Bio + col0, (size_t)k, bc, (size_t)w, n, w)));
+        RET(smooth_apply<T>(h, l, bc, xc, false, me.t0, me.t1, w));
+        RET((launch_op<T, M_RES>(h, l, xc, bc, me.t0, ZERO, ZERO, w)));
+        RET(launch_restrict<T>(h, l, me.t0, co.b + coff, w, w, wC));
+      } else {
+        RET(launch_prolong<T>(h, l, co.x + coff, xc, w, w, wC));
+        RET((launch_op<T, M_RES>(h, l, xc, bc, me.t0, ZERO, ZERO, w)));
+        RET(smooth_apply<T>(h, l, me.t0, xc, true, me.t0, me.t1, w));
+        if (l == level0) RET((cvt_cols<T, TIO>(h, xc, (size_t)w, Xio + col0, (size_t)k, n, w)));
+      }
+    }
+    if (phase == 0) RET((vcycle_level<T, TIO>(h, l + 1, level0, lb, vb, Bio, Xio, k)));
+  }
+  return 0;
+}
+
+template <typename T, typename TIO>
 int vcycle(dmlmc_hier* h, int level0, const void* Bin, void* Xout, int k) {
   const int nl = h->n_levels;
   CHECK(level0 >= 0 && level0 < nl, "vcycle: bad level");
   // the cycle bottoms out at the first level (from level0 down) that owns a dense inverse
   int lb = level0;
   while (lb < nl - 1 && !h->lv[lb].has_dense) ++lb;
-  if (lb == level0) return launch_dense<T>(h, level0, Bin, Xout, k);
+  CHECK(h->lv[lb].has_dense, "vcycle: no dense inverse at the bottom of the cycle");
   const size_t mark = h->ws_off;
-  std::vector<void*> b(nl, nullptr), x(nl, nullptr), t0(nl, nullptr), t1(nl, nullptr);
-  for (int l = level0; l <= lb; ++l) {
-    const size_t cnt = (size_t)h->lv[l].n * k;
-    if (l > level0) { Cx<T>* p; RET(ws_get<Cx<T>>(h, cnt, &p)); b[l] = p; RET(ws_get<Cx<T>>(h, cnt, &p)); x[l] = p; }
-    if (l < lb) { Cx<T>* p; RET(ws_get<Cx<T>>(h, cnt, &p)); t0[l] = p; RET(ws_get<Cx<T>>(h, cnt, &p)); t1[l] = p; }
-  }
-  x[level0] = Xout;
-  const void* bl0 = Bin;
-  for (int l = level0; l < lb; ++l) {
-    const void* bl = (l == level0) ? bl0 : b[l];
-    const void* rfin = nullptr;
-    RET(smooth<T>(h, l, bl, x[l], true, t0[l], t1[l], true, &rfin, k));
-    RET(launch_restrict<T>(h, l, rfin, b[l + 1], k));
-  }
-  RET(launch_dense<T>(h, lb, b[lb], x[lb], k));
-  for (int l = lb - 1; l >= level0; --l) {
-    const void* bl = (l == level0) ? bl0 : b[l];
-    RET(launch_prolong<T>(h, l, x[l + 1], x[l], k));
-    RET((launch_op<T, M_RES>(h, l, x[l], bl, t0[l], nullptr, cx<double>(0, 0), k)));
-    // post-smoothing on r = t0: ping-pong must not overwrite its own input
-    const int d = (int)h->lv[l].inv_roots.size();
-    const void* rin = t0[l];
-    void* pp[2] = {t1[l], t0[l]};
-    for (int i = 0; i < d; ++i) {
-      if (i == d - 1) { RET(launch_axpy_w<T>(h, h->lv[l].inv_roots[i], rin, x[l], (size_t)h->lv[l].n * k)); break; }
-      void* rout = pp[i & 1];
-      RET((launch_op<T, M_SMOOTH>(h, l, rin, nullptr, rout, x[l], h->lv[l].inv_roots[i], k)));
-      rin = rout;
+  if (lb == level0) {
+    int rc;
+    if constexpr (std::is_same<T, TIO>::value) {
+      rc = launch_dense<T>(h, level0, Bin, Xout, k);
+    } else {
+      const size_t cnt = (size_t)h->lv[level0].n * k;
+      Cx<T>*bt, *xt; RET(ws_get<Cx<T>>(h, cnt, &bt)); RET(ws_get<Cx<T>>(h, cnt, &xt));
+      RET((cvt_cols<TIO, T>(h, (const Cx<TIO>*)Bin, (size_t)k, bt, (size_t)k, h->lv[level0].n, k)));
+      rc = launch_dense<T>(h, level0, bt, xt, k);
+      if (rc == 0) rc = cvt_cols<T, TIO>(h, xt, (size_t)k, (Cx<TIO>*)Xout, (size_t)k, h->lv[level0].n, k);
     }
+    h->ws_off = mark;
+    return rc;
   }
+  std::vector<VcBuf<T>> vb(nl);
+  int kc_prev = 0;
+  for (int l = level0; l <= lb; ++l) {
+    const size_t n = h->lv[l].n;
+    vb[l].kc = std::max(kc_prev, chunk_cols(h, l, k, sizeof(Cx<T>)));
+    kc_prev = vb[l].kc;
+    RET(ws_get<Cx<T>>(h, n * k, &vb[l].b)); RET(ws_get<Cx<T>>(h, n * k, &vb[l].x));
+    if (l < lb) { RET(ws_get<Cx<T>>(h, n * vb[l].kc, &vb[l].t0)); RET(ws_get<Cx<T>>(h, n * vb[l].kc, &vb[l].t1)); }
+  }
+  int rc = vcycle_level<T, TIO>(h, level0, level0, lb, vb, (const Cx<TIO>*)Bin, (Cx<TIO>*)Xout, k);
   h->ws_off = mark;
-  return 0;
+  return rc;
 }
 
 // ---- complex128 reductions ---------------------------------------------------------------------
@@ -354,17 +423,8 @@ int multi_axpy(dmlmc_hier* h, const Z* Vbase, size_t vstride, int nv, const Z* h
 }
 
 int precond(dmlmc_hier* h, int level, const Z* V, Z* Zout, int k) {
-  const size_t cnt = (size_t)h->lv[level].n * k;
-  if (h->inner_prec == DMLMC_C128) return vcycle<double>(h, level, V, Zout, k);
-  const size_t mark = h->ws_off;
-  Cx<float>* bf; Cx<float>* xf;
-  RET(ws_get<Cx<float>>(h, cnt, &bf)); RET(ws_get<Cx<float>>(h, cnt, &xf));
-  const unsigned g = std::min<unsigned>(nblocks(cnt, 256), 148u * 16u);
-  cvt_d2f_kernel<<<g, 256, 0, h->stream>>>((const double*)V, (float*)bf, cnt); LAUNCH_CHECK(h);
-  RET(vcycle<float>(h, level, bf, xf, k));
-  cvt_f2d_kernel<<<g, 256, 0, h->stream>>>((const float*)xf, (double*)Zout, cnt); LAUNCH_CHECK(h);
-  h->ws_off = mark;
-  return 0;
+  if (h->inner_prec == DMLMC_C128) return vcycle<double, double>(h, level, V, Zout, k);
+  return vcycle<float, double>(h, level, V, Zout, k);
 }
 
 int read_nactive(dmlmc_hier* h, int* dev_counter, int* out) {
@@ -409,23 +469,26 @@ int fgmres(dmlmc_hier* h, int level, const Z* B, Z* X, int k, double tol, int re
   CU(cudaMemsetAsync(X, 0, nk * sizeof(Z), h->stream));
   const Z* Rsrc = B;
   int total_it = 0, nact = 0;
-  bool first = true;
+  int mode = 1;                      // 1: first cycle (r = b), 2: later cycles (true residual of every column)
   const unsigned gk = nblocks(k, 128);
   while (true) {
+    // Every cycle after the first starts from the TRUE residual b - A x of every column: a column
+    // leaves the solve only when that residual meets the tolerance, whatever the Arnoldi recurrence
+    // estimated (this is what makes single-pass Gram-Schmidt safe).
     RET(multi_dot(h, Rsrc, 0, 1, Rsrc, n, k, partial, s.nrm2, 0));
     CU(cudaMemsetAsync(s.n_active, 0, sizeof(int), h->stream));
-    gmres_init_kernel<<<nblocks(k, 256), 256, 0, h->stream>>>(s, tol, first ? 1 : 0); LAUNCH_CHECK(h);
-    first = false;
-    col_scale_kernel<<<nblocks(nk, 256), 256, 0, h->stream>>>(Rsrc, s.scale, Vb, nk, k); LAUNCH_CHECK(h);
+    gmres_init_kernel<<<nblocks(k, 256), 256, 0, h->stream>>>(s, tol, mode); LAUNCH_CHECK(h);
+    mode = 2;
     RET(read_nactive(h, s.n_active, &nact));
-    if (nact == 0) break;
+    if (nact == 0 || total_it >= maxiter) break;
+    col_scale_kernel<<<nblocks(nk, 256), 256, 0, h->stream>>>(Rsrc, s.scale, Vb, nk, k); LAUNCH_CHECK(h);
     int j = 0;
     for (; j < m; ++j) {
       Z* Vj = Vb + (size_t)j * nk;
       Z* Zj = Zb + (size_t)j * nk;
       RET(precond(h, level, Vj, Zj, k));
-      RET((launch_op<double, M_AX>(h, level, Zj, nullptr, W, nullptr, cx<double>(0, 0), k)));
-      // classical Gram-Schmidt with one re-orthogonalisation pass
+      RET((launch_op<double, M_AX>(h, level, Zj, nullptr, W, ZERO, ZERO, k)));
+      // classical Gram-Schmidt, optionally with one re-orthogonalisation pass
       RET(multi_dot(h, Vb, nk, j + 1, W, n, k, partial, s.hsum, 0));
       RET(multi_axpy(h, Vb, nk, j + 1, s.hsum, W, n, k, -1.0));
       if (h->reorth) {
@@ -446,9 +509,7 @@ int fgmres(dmlmc_hier* h, int level, const Z* B, Z* X, int k, double tol, int re
     const int steps = std::min(j, m);
     gmres_solve_kernel<<<gk, 128, 0, h->stream>>>(s, steps); LAUNCH_CHECK(h);
     RET(multi_axpy(h, Zb, nk, steps, s.y, X, n, k, +1.0));
-    if (nact == 0 || total_it >= maxiter) break;
-    // restart: true residual of all columns
-    RET((launch_op<double, M_RES>(h, level, X, B, Rb, nullptr, cx<double>(0, 0), k)));
+    RET((launch_op<double, M_RES>(h, level, X, B, Rb, ZERO, ZERO, k)));
     Rsrc = Rb;
   }
   if (iters_host) CU(cudaMemcpyAsync(iters_host, s.it_total, sizeof(int) * k, cudaMemcpyDeviceToHost, h->stream));
@@ -551,6 +612,23 @@ int level_sample(dmlmc_hier* h, int method, int lf, int lc, const Z* X0, int k, 
   return 0;
 }
 
+template <typename T>
+int smooth_chunked(dmlmc_hier* h, int level, const Cx<T>* R, Cx<T>* E, int k) {
+  const size_t mark = h->ws_off;
+  const int n = h->lv[level].n;
+  const int kc = chunk_cols(h, level, k, sizeof(Cx<T>));
+  Cx<T>*rc, *ec, *t0, *t1;
+  RET(ws_get<Cx<T>>(h, (size_t)n * kc, &rc)); RET(ws_get<Cx<T>>(h, (size_t)n * kc, &ec));
+  RET(ws_get<Cx<T>>(h, (size_t)n * kc, &t0)); RET(ws_get<Cx<T>>(h, (size_t)n * kc, &t1));
+  for (int col0 = 0; col0 < k; col0 += kc) {
+    const int w = std::min(kc, k - col0);
+    RET((cvt_cols<T, T>(h, R + col0, (size_t)k, rc, (size_t)w, n, w)));
+    RET(smooth_apply<T>(h, level, rc, ec, false, t0, t1, w));
+    RET((cvt_cols<T, T>(h, ec, (size_t)w, E + col0, (size_t)k, n, w)));
+  }
+  h->ws_off = mark;
+  return 0;
+}
 size_t vcycle_bytes(dmlmc_hier* h, int level, int k, size_t elem) {
   size_t b = 0;
   for (int l = level; l < h->n_levels; ++l) b += 4 * align_up((size_t)h->lv[l].n * k * elem);
@@ -562,7 +640,6 @@ size_t fgmres_bytes(dmlmc_hier* h, int level, int k, int m) {
   b += align_up(nk * (m + 1) * z) + align_up(nk * m * z) + 2 * align_up(nk * z);
   b += align_up(partial_count((int)n, m + 1, k) * z);
   b += align_up((size_t)m * m * k * z) + 6 * align_up((size_t)(m + 1) * k * z) + 16 * align_up((size_t)k * 16);
-  b += 2 * align_up(nk * sizeof(Cx<float>));
   b += vcycle_bytes(h, level, k, sizeof(Z));
   return b + (1 << 16);
 }
@@ -674,12 +751,14 @@ int dmlmc_set_coarsest_inverse(dmlmc_hier* h, int n, const double* minv_host) {
   return dmlmc_set_dense_inverse(h, h->n_levels - 1, n, minv_host);
 }
 
-int dmlmc_set_smoother(dmlmc_hier* h, int level, int degree, const double* inv_roots_host) {
+int dmlmc_set_smoother(dmlmc_hier* h, int level, int nfactors, const double* nu_host, double p0_re, double p0_im) {
   CHECK(h && level >= 0 && level < h->n_levels, "set_smoother: bad handle/level");
-  CHECK(degree >= 1 && inv_roots_host, "set_smoother: degree must be >= 1");
+  CHECK(nfactors >= 0 && (nfactors == 0 || nu_host), "set_smoother: bad factors");
   Level& L = h->lv[level];
-  L.inv_roots.resize(degree);
-  for (int i = 0; i < degree; ++i) L.inv_roots[i] = cx<double>(inv_roots_host[2 * i], inv_roots_host[2 * i + 1]);
+  L.nu.resize(nfactors);
+  for (int i = 0; i < nfactors; ++i) L.nu[i] = cx<double>(nu_host[2 * i], nu_host[2 * i + 1]);
+  L.p0 = cx<double>(p0_re, p0_im);
+  L.has_smoother = true;
   return 0;
 }
 
@@ -719,8 +798,8 @@ int dmlmc_set_deflation(dmlmc_hier* h, int level, int d, const double* v_host) {
 int dmlmc_spmm(dmlmc_hier* h, int level, int prec, const void* X, void* Y, int k) {
   ENTER(h); CHECK_LEVEL(h, level); CHECK_PREC(prec); CHECK(X && Y && k >= 1, "spmm: bad arguments");
   if (level == h->n_levels - 1 && h->lv[level].kind < 0) return fail(-1, "spmm: the coarsest level has no sparse operator");
-  if (prec == DMLMC_C128) return launch_op<double, M_AX>(h, level, X, nullptr, Y, nullptr, cx<double>(0, 0), k);
-  return launch_op<float, M_AX>(h, level, X, nullptr, Y, nullptr, cx<double>(0, 0), k);
+  if (prec == DMLMC_C128) return launch_op<double, M_AX>(h, level, X, nullptr, Y, ZERO, ZERO, k);
+  return launch_op<float, M_AX>(h, level, X, nullptr, Y, ZERO, ZERO, k);
 }
 int dmlmc_restrict(dmlmc_hier* h, int level, int prec, const void* Xf, void* Xc, int k) {
   ENTER(h); CHECK_LEVEL(h, level); CHECK_PREC(prec); CHECK(Xf && Xc && k >= 1, "restrict: bad arguments");
@@ -736,23 +815,13 @@ int dmlmc_coarsest_apply(dmlmc_hier* h, int prec, const void* B, void* X, int k)
   return prec == DMLMC_C128 ? launch_dense<double>(h, lc, B, X, k) : launch_dense<float>(h, lc, B, X, k);
 }
 int dmlmc_smooth(dmlmc_hier* h, int level, int prec, const void* R, void* E, int k) {
-  ENTER(h); CHECK_LEVEL(h, level); CHECK_PREC(prec); CHECK(R && E && k >= 1, "smooth: bad arguments");
-  const size_t mark = h->ws_off;
-  const size_t cnt = (size_t)h->lv[level].n * k;
-  int rc;
-  if (prec == DMLMC_C128) {
-    Cx<double>*t0, *t1; RET(ws_get<Cx<double>>(h, cnt, &t0)); RET(ws_get<Cx<double>>(h, cnt, &t1));
-    rc = smooth<double>(h, level, R, E, true, t0, t1, false, nullptr, k);
-  } else {
-    Cx<float>*t0, *t1; RET(ws_get<Cx<float>>(h, cnt, &t0)); RET(ws_get<Cx<float>>(h, cnt, &t1));
-    rc = smooth<float>(h, level, R, E, true, t0, t1, false, nullptr, k);
-  }
-  h->ws_off = mark;
-  return rc;
+  ENTER(h); CHECK_LEVEL(h, level); CHECK_PREC(prec); CHECK(R && E && R != E && k >= 1, "smooth: bad arguments");
+  return prec == DMLMC_C128 ? smooth_chunked<double>(h, level, (const Cx<double>*)R, (Cx<double>*)E, k)
+                            : smooth_chunked<float>(h, level, (const Cx<float>*)R, (Cx<float>*)E, k);
 }
 int dmlmc_vcycle(dmlmc_hier* h, int level, int prec, const void* B, void* X, int k) {
-  ENTER(h); CHECK_LEVEL(h, level); CHECK_PREC(prec); CHECK(B && X && k >= 1, "vcycle: bad arguments");
-  return prec == DMLMC_C128 ? vcycle<double>(h, level, B, X, k) : vcycle<float>(h, level, B, X, k);
+  ENTER(h); CHECK_LEVEL(h, level); CHECK_PREC(prec); CHECK(B && X && B != X && k >= 1, "vcycle: bad arguments");
+  return prec == DMLMC_C128 ? vcycle<double, double>(h, level, B, X, k) : vcycle<float, float>(h, level, B, X, k);
 }
 int dmlmc_dotc(dmlmc_hier* h, const void* X, const void* Y, int n, int k, void* out_dev) {
   ENTER(h); CHECK(X && Y && out_dev && n >= 1 && k >= 1, "dotc: bad arguments");
@@ -834,8 +903,17 @@ int dmlmc_level_sample_host(dmlmc_hier* h, int method, int level_f, int level_c,
 int dmlmc_set_option(dmlmc_hier* h, const char* name, double value) {
   CHECK(h != nullptr && name != nullptr, "set_option: bad arguments");
   if (std::strcmp(name, "reorth") == 0) { h->reorth = value != 0.0 ? 1 : 0; return 0; }
+  if (std::strcmp(name, "chunk_cols") == 0) { h->chunk_cols = (int)value; return 0; }
+  if (std::strcmp(name, "l2_budget_mb") == 0) { CHECK(value >= 0, "l2_budget_mb must be >= 0"); h->l2_budget_mb = value; return 0; }
+  if (std::strcmp(name, "stencil_by") == 0) { CHECK(value >= 1, "stencil_by must be >= 1"); h->stencil_by = (int)value; return 0; }
+  if (std::strcmp(name, "stencil_minb") == 0) { CHECK(value == 2 || value == 3, "stencil_minb must be 2 or 3"); h->stencil_minb = (int)value; return 0; }
+  if (std::strcmp(name, "stencil_bz") == 0) { CHECK(value >= 1, "stencil_bz must be >= 1"); h->stencil_bz = (int)value; return 0; }
   return fail(-1, std::string("dmlmc: unknown option ") + name);
 }
 long long dmlmc_launch_count(dmlmc_hier* h) { return h ? h->launches : 0; }
+int dmlmc_vcycle_chunk_cols(dmlmc_hier* h, int level, int prec, int k) {
+  if (!h || level < 0 || level >= h->n_levels || k < 1) return 0;
+  return chunk_cols(h, level, k, prec == DMLMC_C128 ? sizeof(Cx<double>) : sizeof(Cx<float>));
+}
 
 }  // extern "C"

@@ -164,24 +164,28 @@ struct GmresState {
   int* n_active;       // [1]
 };
 
-// start of a cycle: nrm2 = <r,r>.  first != 0: normb = ||r|| (x0 = 0 so r = b).
+// start of a cycle: nrm2 = <r,r> of the residual the cycle starts from.
+//   mode 1 (first cycle): r = b (x0 = 0); normb = ||b||.
+//   mode 2 (later cycles): r is the TRUE residual b - A x of every column, so this is also the
+//   verification of the columns that stopped on the Arnoldi estimate: a column is finished iff its
+//   true relative residual is below tol (with a rounding allowance), otherwise it iterates on.
 __global__ void __launch_bounds__(256)
-gmres_init_kernel(GmresState s, double tol, int first) {
+gmres_init_kernel(GmresState s, double tol, int mode) {
   const int col = blockIdx.x * blockDim.x + threadIdx.x;
   if (col >= s.k) return;
   const double nr = sqrt(fmax(s.nrm2[col].re, 0.0));
-  if (first) {
+  double accept = tol;
+  if (mode == 1) {
     s.normb[col] = (nr == 0.0) ? 1.0 : nr;
-    s.done[col] = 0;
     s.it_total[col] = 0;
+  } else {
+    accept = 1.25 * tol + 1e-14;
   }
   const double rel = nr / s.normb[col];
   s.it_cycle[col] = 0;
-  int act = 0;
-  if (!s.done[col]) {
-    s.relres[col] = rel;
-    if (rel < tol || nr == 0.0) s.done[col] = 1; else act = 1;
-  }
+  s.relres[col] = rel;
+  const int act = (rel < accept || nr == 0.0) ? 0 : 1;
+  s.done[col] = !act;
   s.active[col] = act;
   s.scale[col] = act ? 1.0 / nr : 0.0;
   s.g[col] = cx<double>(act ? nr : 0.0, 0.0);

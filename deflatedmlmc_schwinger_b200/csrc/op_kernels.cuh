@@ -13,10 +13,11 @@
 namespace dmlmc {
 
 // what the operator kernels write
-enum { M_AX = 0,            // Y = A X
-       M_RES = 1,           // Y = B - A X
-       M_SMOOTH_FIRST = 2,  // Y = X - w A X ; E  = w X      (first Richardson step, e starts at 0)
-       M_SMOOTH = 3 };      // Y = X - w A X ; E += w X
+enum { M_AX = 0,         // Y = A X
+       M_RES = 1,        // Y = B - A X
+       M_STEP = 2,       // Y = X - w A X                 (one factor of the smoother polynomial)
+       M_STEP_SET = 3,   // Y = c (X - w A X)             (last factor, pre-smoother:  x  = p(A) b)
+       M_STEP_ACC = 4 }; // Y += c (X - w A X)            (last factor, post-smoother: x += p(A) r)
 
 template <typename T> struct StencilDev {
   int LX, LT;
@@ -28,7 +29,7 @@ template <typename T> struct StencilDev {
 template <typename T, int NC, int MODE>
 __device__ __forceinline__ void op_epilogue(const Pack<T, NC>& ax, const Pack<T, NC>& xin, size_t idx,
                                             const Pack<T, NC>* __restrict__ B, Pack<T, NC>* __restrict__ Y,
-                                            Pack<T, NC>* __restrict__ E, Cx<T> w) {
+                                            Cx<T> w, Cx<T> c) {
   if constexpr (MODE == M_AX) {
     Y[idx] = ax;
   } else if constexpr (MODE == M_RES) {
@@ -36,13 +37,14 @@ __device__ __forceinline__ void op_epilogue(const Pack<T, NC>& ax, const Pack<T,
   } else {
     Pack<T, NC> rn = xin;
     pfms<T, NC>(rn, w, ax);
-    Y[idx] = rn;
-    if constexpr (MODE == M_SMOOTH_FIRST) {
-      E[idx] = pscale<T, NC>(w, xin);
+    if constexpr (MODE == M_STEP) {
+      Y[idx] = rn;
+    } else if constexpr (MODE == M_STEP_SET) {
+      Y[idx] = pscale<T, NC>(c, rn);
     } else {
-      Pack<T, NC> e = E[idx];
-      pfma<T, NC>(e, w, xin);
-      E[idx] = e;
+      Pack<T, NC> e = Y[idx];
+      pfma<T, NC>(e, c, rn);
+      Y[idx] = e;
     }
   }
 }
@@ -51,16 +53,21 @@ __device__ __forceinline__ void op_epilogue(const Pack<T, NC>& ax, const Pack<T,
 //                          + (1-s2) Ux(x) psi(x+x) + (1+s2) Ux(x-x)^* psi(x-x) ]
 // with the spin projections (1-s1)phi = (a,-a), a = phi0-phi1; (1+s1)phi = (b,b), b = phi0+phi1;
 // (1-s2)phi = (c,-ic), c = phi0+i phi1; (1+s2)phi = (d, id), d = phi0-i phi1.
-template <typename T, int NC, int MODE>
-__global__ void __launch_bounds__(256)
+// Thread block = (packs, TT sites in t, TX sites in x): the 2-D site tile makes the x- and t-neighbour
+// rows of a site hit in L1 (fetched by the CTA's own threads), so each vector row is pulled from L2
+// (TT*TX + 2TT + 2TX)/(TT*TX) times instead of 5.
+// MINB = 2: 64 registers, all 14 loads of a thread in flight at once; MINB = 3: 40 registers, loads in
+// batches of 6 but 50 % more resident threads.
+template <typename T, int NC, int MODE, int MINB>
+__global__ void __launch_bounds__(512, MINB)
 stencil_kernel(StencilDev<T> op, const Pack<T, NC>* __restrict__ X, const Pack<T, NC>* __restrict__ B,
-               Pack<T, NC>* __restrict__ Y, Pack<T, NC>* __restrict__ E, Cx<T> w, int kp) {
+               Pack<T, NC>* __restrict__ Y, Cx<T> w, Cx<T> cfin, int kp) {
   const int LX = op.LX, LT = op.LT, V = LX * LT;
-  const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  const int site = (int)(gid / kp);
-  const int cp = (int)(gid - (long long)site * kp);
-  if (site >= V) return;
-  const int x = site / LT, t = site - x * LT;
+  const int cp = blockIdx.x * blockDim.x + threadIdx.x;
+  const int t = blockIdx.y * blockDim.y + threadIdx.y;
+  const int x = blockIdx.z * blockDim.z + threadIdx.z;
+  if (cp >= kp || t >= LT || x >= LX) return;
+  const int site = x * LT + t;
   const int tp = (t + 1 == LT) ? 0 : t + 1, tm = (t == 0) ? LT - 1 : t - 1;
   const int xp = (x + 1 == LX) ? 0 : x + 1, xm = (x == 0) ? LX - 1 : x - 1;
   const int s_tp = x * LT + tp, s_tm = x * LT + tm, s_xp = xp * LT + t, s_xm = xm * LT + t;
@@ -87,8 +94,8 @@ stencil_kernel(StencilDev<T> op, const Pack<T, NC>* __restrict__ X, const Pack<T
   // spin 1: -ua + ub - i uc + i ud
   y1 = psub<T, NC>(y1, padd<T, NC>(psub<T, NC>(ub, ua), pmul_i<T, NC>(psub<T, NC>(ud, uc))));
 
-  op_epilogue<T, NC, MODE>(y0, c0, (size_t)site * kpz + cp, B, Y, E, w);
-  op_epilogue<T, NC, MODE>(y1, c1, (Vz + site) * kpz + cp, B, Y, E, w);
+  op_epilogue<T, NC, MODE>(y0, c0, (size_t)site * kpz + cp, B, Y, w, cfin);
+  op_epilogue<T, NC, MODE>(y1, c1, (Vz + site) * kpz + cp, B, Y, w, cfin);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -101,7 +108,7 @@ template <typename T> struct BsrDev {
 template <typename T, int NC, int BS, int MODE>
 __global__ void __launch_bounds__(128)
 bsr_kernel(BsrDev<T> op, const Pack<T, NC>* __restrict__ X, const Pack<T, NC>* __restrict__ B,
-           Pack<T, NC>* __restrict__ Y, Pack<T, NC>* __restrict__ E, Cx<T> w, int kp) {
+           Pack<T, NC>* __restrict__ Y, Cx<T> w, Cx<T> cfin, int kp) {
   const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   const int I = (int)(gid / kp);
   const int cp = (int)(gid - (long long)I * kp);
@@ -128,8 +135,8 @@ bsr_kernel(BsrDev<T> op, const Pack<T, NC>* __restrict__ X, const Pack<T, NC>* _
   for (int r = 0; r < BS; ++r) {
     const size_t idx = ((size_t)I * BS + r) * kpz + cp;
     P xin = pzero<T, NC>();
-    if constexpr (MODE == M_SMOOTH || MODE == M_SMOOTH_FIRST) xin = ldp_ro<T, NC>(X, idx);
-    op_epilogue<T, NC, MODE>(acc[r], xin, idx, B, Y, E, w);
+    if constexpr (MODE >= M_STEP) xin = ldp_ro<T, NC>(X, idx);
+    op_epilogue<T, NC, MODE>(acc[r], xin, idx, B, Y, w, cfin);
   }
 }
 
@@ -149,7 +156,7 @@ template <int BS, int PPT, int MODE>
 __global__ void __launch_bounds__(128)
 bsr_f32x2_kernel(int nb, int bpr, const int* __restrict__ col, const float4* __restrict__ vals4,
                  const Pack<float, 2>* __restrict__ X, const Pack<float, 2>* __restrict__ B,
-                 Pack<float, 2>* __restrict__ Y, Pack<float, 2>* __restrict__ E, Cx<float> w, int kp) {
+                 Pack<float, 2>* __restrict__ Y, Cx<float> w, Cx<float> cfin, int kp) {
   extern __shared__ float4 bsr_smem[];
   const int tpr = blockDim.x, RB = blockDim.y;
   const int tx = threadIdx.x, rb = threadIdx.y;
@@ -215,8 +222,8 @@ bsr_f32x2_kernel(int nb, int bpr, const int* __restrict__ col, const float4* __r
       ax.d[2] = a[r][p].z - b[r][p].w; ax.d[3] = a[r][p].w + b[r][p].z;
       const size_t idx = ((size_t)I * BS + r) * kpz + cp[p];
       Pack<float, 2> xin = pzero<float, 2>();
-      if constexpr (MODE == M_SMOOTH || MODE == M_SMOOTH_FIRST) xin = ldp_ro<float, 2>(X, idx);
-      op_epilogue<float, 2, MODE>(ax, xin, idx, B, Y, E, w);
+      if constexpr (MODE >= M_STEP) xin = ldp_ro<float, 2>(X, idx);
+      op_epilogue<float, 2, MODE>(ax, xin, idx, B, Y, w, cfin);
     }
   }
 }
@@ -231,13 +238,14 @@ template <typename T> struct TransferDev {
 
 template <typename T, int NC, int NV>
 __global__ void __launch_bounds__(128)
-restrict_kernel(TransferDev<T> tr, const Pack<T, NC>* __restrict__ Xf, Pack<T, NC>* __restrict__ Xc, int kp) {
+restrict_kernel(TransferDev<T> tr, const Pack<T, NC>* __restrict__ Xf, Pack<T, NC>* __restrict__ Xc, int kp,
+                int ldf, int ldc) {   // kp packs per row are processed; rows are ldf / ldc packs apart
   const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   const int g = (int)(gid / kp);                   // (aggregate, half)
   const int cp = (int)(gid - (long long)g * kp);
   if (g >= tr.n_c / NV) return;
   const int j = g >> 1, half = g & 1;
-  const size_t kpz = (size_t)kp;
+  const size_t ldfz = (size_t)ldf, ldcz = (size_t)ldc;
   typedef Pack<T, NC> P;
   P acc[NV];
 #pragma unroll
@@ -246,18 +254,19 @@ restrict_kernel(TransferDev<T> tr, const Pack<T, NC>* __restrict__ Xf, Pack<T, N
   for (int wq = 0; wq < nw; ++wq) {
     for (int z = 0; z < tr.h; ++z) {
       const int r = j * tr.aggr + wq * tr.dofi + half * tr.h + z;
-      const P x = ldp_ro<T, NC>(Xf, (size_t)r * kpz + cp);
+      const P x = ldp_ro<T, NC>(Xf, (size_t)r * ldfz + cp);
 #pragma unroll
       for (int v = 0; v < NV; ++v) pfma_conj<T, NC>(acc[v], ldc_ro<T>(tr.pv, (size_t)r * NV + v), x);
     }
   }
 #pragma unroll
-  for (int v = 0; v < NV; ++v) Xc[((size_t)g * NV + v) * kpz + cp] = acc[v];
+  for (int v = 0; v < NV; ++v) Xc[((size_t)g * NV + v) * ldcz + cp] = acc[v];
 }
 
 template <typename T, int NC, int NV>
 __global__ void __launch_bounds__(256)
-prolong_add_kernel(TransferDev<T> tr, const Pack<T, NC>* __restrict__ Xc, Pack<T, NC>* __restrict__ Xf, int kp) {
+prolong_add_kernel(TransferDev<T> tr, const Pack<T, NC>* __restrict__ Xc, Pack<T, NC>* __restrict__ Xf, int kp,
+                   int ldf, int ldc) {
   const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   const int r = (int)(gid / kp);
   const int cp = (int)(gid - (long long)r * kp);
@@ -265,13 +274,13 @@ prolong_add_kernel(TransferDev<T> tr, const Pack<T, NC>* __restrict__ Xc, Pack<T
   const int j = r / tr.aggr;
   const int q = (r - j * tr.aggr) % tr.dofi;
   const int g = 2 * j + (q >= tr.h ? 1 : 0);
-  const size_t kpz = (size_t)kp;
+  const size_t ldfz = (size_t)ldf, ldcz = (size_t)ldc;
   typedef Pack<T, NC> P;
-  P acc = Xf[(size_t)r * kpz + cp];
+  P acc = Xf[(size_t)r * ldfz + cp];
 #pragma unroll
   for (int v = 0; v < NV; ++v)
-    pfma<T, NC>(acc, ldc_ro<T>(tr.pv, (size_t)r * NV + v), ldp_ro<T, NC>(Xc, ((size_t)g * NV + v) * kpz + cp));
-  Xf[(size_t)r * kpz + cp] = acc;
+    pfma<T, NC>(acc, ldc_ro<T>(tr.pv, (size_t)r * NV + v), ldp_ro<T, NC>(Xc, ((size_t)g * NV + v) * ldcz + cp));
+  Xf[(size_t)r * ldfz + cp] = acc;
 }
 
 // ------------------------------------------------------------------------------------------
@@ -399,21 +408,29 @@ probe_expand_kernel(const uint8_t* __restrict__ bits, int n, int k, Cx<double>* 
   X0[(size_t)i * k + p] = cx<double>(bit ? 1.0 : -1.0, 0.0);
 }
 
-__global__ void __launch_bounds__(256) cvt_d2f_kernel(const double* __restrict__ in, float* __restrict__ out, size_t n) {
-  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-  const size_t stride = (size_t)gridDim.x * blockDim.x;
-  for (; i < n; i += stride) {   // n counts double2 elements
-    double2 v = reinterpret_cast<const double2*>(in)[i];
-    reinterpret_cast<float2*>(out)[i] = make_float2((float)v.x, (float)v.y);
-  }
+// Out[r][c] = (Tout) In[r][c], r < n, c < w: copies / converts a block of w columns between two
+// row-major batches with leading dimensions ld_in / ld_out (complex elements).  This is how a column
+// chunk of the FGMRES basis (complex128, [n][k]) becomes the compact, L2-resident [n][w] working
+// array of the V-cycle and back.
+template <typename Tin, typename Tout>
+__global__ void __launch_bounds__(256)
+cvt_cols_kernel(const Cx<Tin>* __restrict__ in, size_t ld_in, Cx<Tout>* __restrict__ out, size_t ld_out, int n, int w) {
+  const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const size_t r = idx / w;
+  const int c = (int)(idx - r * w);
+  if (r >= (size_t)n) return;
+  const Cx<Tin> v = ldc_ro<Tin>(in, r * ld_in + c);
+  out[r * ld_out + c] = cx<Tout>((Tout)v.re, (Tout)v.im);
 }
-__global__ void __launch_bounds__(256) cvt_f2d_kernel(const float* __restrict__ in, double* __restrict__ out, size_t n) {
-  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-  const size_t stride = (size_t)gridDim.x * blockDim.x;
-  for (; i < n; i += stride) {
-    float2 v = reinterpret_cast<const float2*>(in)[i];
-    reinterpret_cast<double2*>(out)[i] = make_double2((double)v.x, (double)v.y);
-  }
+
+// Y = c X (elementwise) / Y += c X
+template <typename T, int ACC>
+__global__ void __launch_bounds__(256) scale_kernel(Cx<T> c, const Cx<T>* __restrict__ X, Cx<T>* __restrict__ Y, size_t count) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= count) return;
+  Pack<T, 1> y = ACC ? *reinterpret_cast<const Pack<T, 1>*>(Y + i) : pzero<T, 1>();
+  pfma<T, 1>(y, c, *reinterpret_cast<const Pack<T, 1>*>(X + i));
+  *reinterpret_cast<Pack<T, 1>*>(Y + i) = y;
 }
 
 }  // namespace dmlmc

@@ -136,6 +136,52 @@ def harmonic_ritz_inv_roots(A, degree, seed=7):
     return 1.0 / np.array(out, dtype=np.complex128)
 
 
+def leja_order(points):
+    """Leja ordering of complex points: start from the largest modulus, then repeatedly take the point
+    that maximises the product of distances to the points already chosen."""
+    pts = list(points)
+    out = [max(pts, key=abs)]
+    pts.remove(out[0])
+    while pts:
+        arr = np.array(out)
+        nxt = max(pts, key=lambda t: np.sum(np.log(np.abs(t - arr) + 1e-300)))
+        out.append(nxt)
+        pts.remove(nxt)
+    return np.array(out, dtype=np.complex128)
+
+
+def smoother_product_form(omega):
+    """The smoother polynomial p(z) = sum_i omega_i prod_{j<i} (1 - omega_j z) (what d Richardson steps
+    r <- r - omega_i A r, e <- e + omega_i r accumulate; 1 - z p(z) is the GMRES residual polynomial)
+    rewritten as  p(z) = p0 * prod_{i<d-1} (1 - nu_i z):  each factor is then ONE kernel that reads a
+    vector and writes a vector -- no accumulator to read and write, half the memory traffic.
+    The roots 1/nu_i of p are the eigenvalues of the comrade matrix of p in the basis
+    N_i(z) = prod_{j<i} (1 - omega_j z)  (z N_i = (N_i - N_{i+1}) / omega_i), Leja-ordered.
+    Returns (nu[d-1], p0)."""
+    w = np.asarray(omega, dtype=np.complex128).reshape(-1)
+    d = w.shape[0]
+    p0 = complex(np.sum(w))
+    m = d - 1
+    if m == 0:
+        return np.zeros(0, dtype=np.complex128), p0
+    C = np.zeros((m, m), dtype=np.complex128)
+    for i in range(m):
+        C[i, i] = 1.0 / w[i]
+        if i + 1 < m:
+            C[i, i + 1] = -1.0 / w[i]
+    C[m - 1, :] += w[:m] / (w[m - 1] * w[m])
+    mu = leja_order(np.linalg.eigvals(C))
+    nu = 1.0 / mu
+    # self-check on the spectrum-side sample points 1/omega_j (the harmonic Ritz values), where p = 1/z
+    z = 1.0 / w
+    ref = 1.0 / z
+    val = p0 * np.prod(1.0 - np.outer(z, nu), axis=1)
+    err = np.max(np.abs(val - ref) / np.abs(ref))
+    if not err < 1e-6:
+        raise Exception("smoother polynomial: product form is inaccurate (%.2e); lower the degree" % err)
+    return nu, p0
+
+
 def bsr_padded(A, bs):
     """scipy matrix -> (colidx[nb][bpr] with -1 padding, vals[nb][bpr][bs][bs])."""
     B = csr_matrix(A).tobsr(blocksize=(bs, bs))
@@ -306,8 +352,11 @@ class MG:
                 col, vals = bsr_padded(lv[i + 1].A, nvec)
                 dev.set_bsr(i + 1, lv[i + 1].A.shape[0], nvec, col, vals)
         dev.set_coarsest_inverse(self.coarsest_inv)
+        self.smoother_polys = []
         for i in range(nl - 1):
-            dev.set_smoother(i, harmonic_ritz_inv_roots(csr_matrix(lv[i].A), self.level_degree(i)))
+            nu, p0 = smoother_product_form(harmonic_ritz_inv_roots(csr_matrix(lv[i].A), self.level_degree(i)))
+            self.smoother_polys.append((nu, p0))
+            dev.set_smoother(i, nu, p0)
         if use_permuted:
             for i in range(nl):
                 if i == 0:

@@ -32,7 +32,7 @@
 extern "C" {
 #endif
 
-#define DMLMC_ABI_VERSION 1
+#define DMLMC_ABI_VERSION 2
 
 enum { DMLMC_C128 = 0, DMLMC_C64 = 1 };
 
@@ -64,10 +64,12 @@ int dmlmc_set_coarsest_inverse(dmlmc_hier* h, int n, const double* minv_host);
 /* optional dense inverse of an intermediate level: the V-cycle then bottoms out there (exact coarse
  * solve) instead of recursing to the coarsest level.  Same layout as dmlmc_set_coarsest_inverse. */
 int dmlmc_set_dense_inverse(dmlmc_hier* h, int level, int n, const double* minv_host);
-/* smoother on `level`: e = p(A) r with p given by its `degree` inverse roots (complex128),
- * applied as Richardson steps in the given order.  Replaces the lgmres call of
+/* smoother on `level`: e = p(A_level) r with the fixed polynomial p in product form,
+ *   p(A) = p0 * prod_{i<nfactors} (I - nu_i A)       (nu_host: nfactors complex128, applied in order),
+ * one fused operator+update kernel per factor, no inner products.  Replaces the lgmres call of
  * multigrid.py:393-394 / 438-439 (FGMRES is flexible: parity is on the converged solve). */
-int dmlmc_set_smoother(dmlmc_hier* h, int level, int degree, const double* inv_roots_host);
+int dmlmc_set_smoother(dmlmc_hier* h, int level, int nfactors, const double* nu_host,
+                       double p0_re, double p0_im);
 /* permutation data of a level (multigrid.py:142-155, 320-331): x_perm = roll(x, +shift),
  * then Bblock_perm (nnz_per_row == 0: identity) in padded row form cols/vals[n][nnz_per_row] */
 int dmlmc_set_perm(dmlmc_hier* h, int level, int shift, int nnz_per_row,
@@ -125,12 +127,20 @@ int dmlmc_level_sample_host(dmlmc_hier* h, int method, int level_f, int level_c,
                             const uint8_t* bits_host, int k, double tol, int restart, int maxiter,
                             double* e_host, int32_t* iters_host);
 
-/* solver options by name: "reorth" (1 = classical Gram-Schmidt with one re-orthogonalisation pass,
- * default; 0 = single pass).  Unknown names are an error. */
+/* solver options by name.  Unknown names are an error.
+ *   "reorth"       1 = classical Gram-Schmidt with a re-orthogonalisation pass, 0 = single pass (default;
+ *                  every column is verified against its true residual before it leaves the solve)
+ *   "chunk_cols"   columns per V-cycle chunk; 0 (default) = derive from "l2_budget_mb"
+ *   "l2_budget_mb" MB that the four working vectors of a chunk may occupy (so that they stay L2-resident
+ *                  over the smoother's kernels); 0 (default) = one chunk
+ *   "stencil_by", "stencil_bz"   site tile (t, x) of the level-0 kernel's thread block (default 4 x 4)
+ *   "stencil_minb" 2 | 3 (default): resident 512-thread blocks per SM the level-0 kernel is compiled for */
 int dmlmc_set_option(dmlmc_hier* h, const char* name, double value);
 
 /* number of kernels launched by this handle since creation (bench.py's gpu_launches) */
 long long dmlmc_launch_count(dmlmc_hier* h);
+/* columns per chunk the V-cycle uses on `level` for a batch of k columns of precision prec */
+int dmlmc_vcycle_chunk_cols(dmlmc_hier* h, int level, int prec, int k);
 
 #ifdef __cplusplus
 }

@@ -1,5 +1,6 @@
 """Dev tool (GPU): time one batch of k level-0 MLMC samples of the 128^2 set for a grid of smoother
-degrees / solver options.  python profiles/tune.py "32,32,32;1" "64,32,32;0" ...  (degrees;reorth)"""
+degrees / solver options.  python profiles/tune.py "32,32,32;1" "64,32,32;0;40;chunk_cols=128,stencil_by=8" ...
+(degrees;reorth;restart;option=value,...)"""
 import os, sys, time, json
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
@@ -25,6 +26,12 @@ for cfg in sys.argv[1:]:
     mg.skip_level = True
     dev = mg.dev
     dev.set_option("reorth", reorth)
+    opts = {}
+    if len(parts) > 3 and parts[3]:
+        for kv in parts[3].split(","):
+            name, val = kv.split("=")
+            opts[name] = float(val)
+            dev.set_option(name, float(val))
     X0 = dev.probe_expand(bits, 32768, k)
     for _ in range(2):
         e, it = dev.level_sample(1, 0, 2, X0, 1e-12, restart, 1000)
@@ -38,7 +45,7 @@ for cfg in sys.argv[1:]:
     e = e.cpu().numpy()
     if e_ref is None:
         e_ref = e
-    print(json.dumps({"deg": deg, "reorth": reorth, "restart": restart, "ms": 1e3 * dt, "probes_per_s": k / dt,
+    print(json.dumps({"deg": deg, "reorth": reorth, "restart": restart, "opts": opts, "ms": 1e3 * dt, "probes_per_s": k / dt,
                       "it0": [int(it[0].min()), int(it[0].max())], "it2": [int(it[1].min()), int(it[1].max())],
                       "launches": (dev.launch_count() - l0) // reps,
                       "max_rel_diff_vs_first": float(np.abs(e - e_ref).max() / np.abs(e_ref).max())}), flush=True)

@@ -188,3 +188,24 @@ def test_gateway_and_param_plumbing():
     t.start("mvm"); t.end("mvm")
     with pytest.raises(Exception):
         t.end("mvm")
+
+
+def test_smoother_product_form_matches_richardson(port128):
+    """multigrid.smoother_product_form: p0 prod_i (1 - nu_i A) b == sum_i omega_i prod_{j<i} (1 - omega_j A) b"""
+    mp, tp = port128
+    A = sp.csr_matrix(mp.levels[0].A)
+    for d in (1, 2, 9, 32):
+        w = mgm.harmonic_ritz_inv_roots(A, d)
+        nu, p0 = mgm.smoother_product_form(w)
+        assert nu.shape == (d - 1,)
+        rs = np.random.RandomState(d)
+        b = rs.standard_normal(A.shape[0]) + 1j * rs.standard_normal(A.shape[0])
+        r = b.copy(); e = np.zeros_like(b)
+        for i, wi in enumerate(w):
+            e = e + wi * r
+            if i < d - 1:
+                r = r - wi * (A @ r)
+        y = b.copy()
+        for v in nu:
+            y = y - v * (A @ y)
+        assert np.linalg.norm(p0 * y - e) / np.linalg.norm(e) < 1e-12
