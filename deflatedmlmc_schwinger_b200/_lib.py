@@ -30,6 +30,7 @@ _SIGS = {
                                           ctypes.c_int, ctypes.c_void_p]),
     "dmlmc_set_coarsest_inverse": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p]),
     "dmlmc_set_dense_inverse": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_void_p]),
+    "dmlmc_set_dense_inverse_device": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_void_p]),
     "dmlmc_set_smoother": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_void_p,
                                           ctypes.c_double, ctypes.c_double]),
     "dmlmc_set_perm": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_void_p,
@@ -162,6 +163,12 @@ class Hierarchy:
     def set_dense_inverse(self, level, minv):
         minv, p = _host_c128(minv)
         _check(self.lib.dmlmc_set_dense_inverse(self.h, level, minv.shape[0], p))
+
+    def set_dense_inverse_device(self, level, minv_dev):
+        """minv_dev: torch complex128 CUDA tensor [n, n] (row-major inverse)"""
+        assert minv_dev.is_cuda and minv_dev.is_contiguous() and minv_dev.dtype == self.torch.complex128
+        _check(self.lib.dmlmc_set_dense_inverse_device(self.h, level, minv_dev.shape[0], ctypes.c_void_p(minv_dev.data_ptr())))
+        self.torch.cuda.current_stream(self.device).synchronize()
 
     def set_smoother(self, level, nu, p0):
         """p(A) = p0 * prod_i (I - nu[i] A)"""

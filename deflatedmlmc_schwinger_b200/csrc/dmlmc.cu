@@ -6,6 +6,7 @@
 #include "common.cuh"
 #include "op_kernels.cuh"
 #include "krylov_kernels.cuh"
+#include "dense_umma.cuh"
 
 #include <algorithm>
 #include <cstdio>
@@ -52,6 +53,9 @@ struct Level {
   bool has_perm = false; int shift = 0, perm_nnz = 0; int* perm_cols = nullptr;
   int defl_d = 0; Cx<double>* defl_V = nullptr;
   bool has_dense = false; Cx<double>* minv_d = nullptr; Cx<float>* minv_f = nullptr; float4* minv4 = nullptr;
+  // tensor-core operand of the dense inverse: Mt[2n][2n] BF16 (2x2 real block per complex entry) + its TMA map
+  bool has_umma = false; __nv_bfloat16* minv_bf16 = nullptr; CUtensorMap tmA;
+  const void* tmB_ptr = nullptr; int tmB_k = 0; CUtensorMap tmB;
   LevelT<double> d;
   LevelT<float> f;
 };
@@ -70,6 +74,9 @@ struct dmlmc_hier {
   int inner_prec = DMLMC_C64;
   int reorth = 0;
   int stencil_by = 4, stencil_bz = 4;     // site tile (t, x) of the stencil kernel's thread block
+  int dense_direct_exact = 1;             // a dense level solved directly (not from a finer level) uses its FP32 copy
+  int dense_tensor_min_n = 1024;          // dense inverses at least this large are applied on the tensor cores
+  bool umma_attr_set = false;
   int stencil_minb = 3;                   // resident 512-thread blocks per SM the stencil kernel is compiled for
   int chunk_cols = 0;                     // V-cycle column chunk (0 = sized from l2_budget_mb)
   double l2_budget_mb = 0.0;              // MB the per-chunk working vectors may occupy (0 = no chunking)
@@ -245,11 +252,40 @@ template <typename T> Cx<T>* minv_of(Level& L);
 template <> Cx<double>* minv_of<double>(Level& L) { return L.minv_d; }
 template <> Cx<float>*  minv_of<float>(Level& L)  { return L.minv_f; }
 
-// X = A_level^{-1} B with the level's dense inverse
-template <typename T> int launch_dense(dmlmc_hier* h, int level, const void* B, void* X, int k) {
+// X = A_level^{-1} B on the tensor cores (complex64 in/out, BF16 operands, FP32 accumulation)
+int launch_dense_umma(dmlmc_hier* h, int level, const Cx<float>* B, Cx<float>* X, int k) {
+  Level& L = h->lv[level];
+  const int n = L.n;
+  const size_t mark = h->ws_off;
+  __nv_bfloat16* Bt;
+  RET(ws_get<__nv_bfloat16>(h, (size_t)k * 2 * n, &Bt));
+  dim3 pblk(32, 8), pgrd((n + 31) / 32, (k + 31) / 32);
+  umma_pack_rhs_kernel<float><<<pgrd, pblk, 0, h->stream>>>(B, k, n, k, Bt); LAUNCH_CHECK(h);
+  if (L.tmB_ptr != Bt || L.tmB_k != k) {
+    if (make_tmap_bf16(&L.tmB, Bt, (uint64_t)k, (uint64_t)2 * n, UM_BN) != 0) return fail(-4, "dmlmc: cuTensorMapEncodeTiled failed (rhs)");
+    L.tmB_ptr = Bt; L.tmB_k = k;
+  }
+  if (!h->umma_attr_set) {
+    CU(cudaFuncSetAttribute(dense_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)UM_SMEM));
+    h->umma_attr_set = true;
+  }
+  dim3 grd((2 * n + UM_BM - 1) / UM_BM, (k + UM_BN - 1) / UM_BN);
+  dense_umma_kernel<<<grd, UM_THREADS, UM_SMEM, h->stream>>>(L.tmA, L.tmB, reinterpret_cast<float*>(X), k, 2 * n, k);
+  LAUNCH_CHECK(h);
+  h->ws_off = mark;
+  return 0;
+}
+
+// X = A_level^{-1} B with the level's dense inverse; B, X compact [n][k]
+template <typename T> int launch_dense(dmlmc_hier* h, int level, const void* B, void* X, int k, bool prefer_exact = false) {
   Level& L = h->lv[level];
   if (!L.has_dense) return fail(-1, "dmlmc: dense inverse of this level not set");
   const int n = L.n;
+  if constexpr (std::is_same<T, float>::value) {
+    if (L.has_umma && (L.minv4 == nullptr || (!prefer_exact && n >= h->dense_tensor_min_n)))
+      return launch_dense_umma(h, level, (const Cx<float>*)B, (Cx<float>*)X, k);
+  }
+  if (minv_of<T>(L) == nullptr) return fail(-1, "dmlmc: this level's dense inverse exists only as the tensor-core (complex64) operand");
   dim3 blk(32, 8);
   if (max_nc<T>() == 2 && (k % 2) == 0) {
     constexpr int NC = max_nc<T>(); const int kp = k / NC;
@@ -263,6 +299,21 @@ template <typename T> int launch_dense(dmlmc_hier* h, int level, const void* B, 
     dense_kernel<T, 1><<<grd, blk, 0, h->stream>>>(minv_of<T>(L), n, (const Pack<T, 1>*)B, (Pack<T, 1>*)X, k);
   }
   LAUNCH_CHECK(h);
+  return 0;
+}
+
+// build the tensor-core operand of a level's dense inverse from the complex128 matrix on the device
+int build_umma_operand(dmlmc_hier* h, int level, const Cx<double>* minv_dev) {
+  Level& L = h->lv[level];
+  const size_t n = L.n;
+  if (n % 8 != 0) return 0;                       // TMA needs 16-byte row strides; such tiny levels use the SIMT kernel
+  __nv_bfloat16* mt = nullptr;
+  CU(cudaMalloc(&mt, 4 * n * n * sizeof(__nv_bfloat16)));
+  h->owned.push_back(mt);
+  umma_expand_matrix_kernel<<<nblocks(n * n, 256), 256, 0, h->stream>>>(minv_dev, (int)n, mt); LAUNCH_CHECK(h);
+  CU(cudaStreamSynchronize(h->stream));
+  if (make_tmap_bf16(&L.tmA, mt, 2 * n, 2 * n, UM_BM) != 0) return fail(-4, "dmlmc: cuTensorMapEncodeTiled failed (matrix)");
+  L.minv_bf16 = mt; L.has_umma = true; L.tmB_ptr = nullptr;
   return 0;
 }
 
@@ -370,20 +421,27 @@ template <typename T, typename TIO>
 int vcycle(dmlmc_hier* h, int level0, const void* Bin, void* Xout, int k) {
   const int nl = h->n_levels;
   CHECK(level0 >= 0 && level0 < nl, "vcycle: bad level");
-  // the cycle bottoms out at the first level (from level0 down) that owns a dense inverse
+  // the cycle bottoms out at the first level (from level0 down) that owns a dense inverse usable in
+  // precision T (tensor-core-only inverses serve the complex64 cycle)
+  auto usable = [&](const Level& L) {
+    return L.has_dense && (std::is_same<T, float>::value ? (L.has_umma || L.minv4 != nullptr) : L.minv_d != nullptr);
+  };
   int lb = level0;
-  while (lb < nl - 1 && !h->lv[lb].has_dense) ++lb;
-  CHECK(h->lv[lb].has_dense, "vcycle: no dense inverse at the bottom of the cycle");
+  while (lb < nl - 1 && !usable(h->lv[lb])) ++lb;
+  CHECK(usable(h->lv[lb]), "vcycle: no dense inverse at the bottom of the cycle");
   const size_t mark = h->ws_off;
   if (lb == level0) {
+    // the dense inverse IS the preconditioner of this level's own solve: use the most accurate copy
+    // (a BF16 inverse costs ~20 FGMRES iterations at 1e-12 instead of 3)
     int rc;
+    const bool exact = h->dense_direct_exact != 0;
     if constexpr (std::is_same<T, TIO>::value) {
-      rc = launch_dense<T>(h, level0, Bin, Xout, k);
+      rc = launch_dense<T>(h, level0, Bin, Xout, k, exact);
     } else {
       const size_t cnt = (size_t)h->lv[level0].n * k;
       Cx<T>*bt, *xt; RET(ws_get<Cx<T>>(h, cnt, &bt)); RET(ws_get<Cx<T>>(h, cnt, &xt));
       RET((cvt_cols<TIO, T>(h, (const Cx<TIO>*)Bin, (size_t)k, bt, (size_t)k, h->lv[level0].n, k)));
-      rc = launch_dense<T>(h, level0, bt, xt, k);
+      rc = launch_dense<T>(h, level0, bt, xt, k, exact);
       if (rc == 0) rc = cvt_cols<T, TIO>(h, xt, (size_t)k, (Cx<TIO>*)Xout, (size_t)k, h->lv[level0].n, k);
     }
     h->ws_off = mark;
@@ -743,6 +801,19 @@ int dmlmc_set_dense_inverse(dmlmc_hier* h, int level, int n, const double* minv_
     RET(upload<float4>(h, v4.data(), cnt, &L.minv4));
   }
   L.has_dense = true;
+  if (n >= 256) RET(build_umma_operand(h, level, L.minv_d));
+  return 0;
+}
+
+int dmlmc_set_dense_inverse_device(dmlmc_hier* h, int level, int n, const void* minv_dev) {
+  CHECK(h && level >= 0 && level < h->n_levels && n > 0 && minv_dev, "set_dense_inverse_device: bad arguments");
+  CHECK(n % 8 == 0, "set_dense_inverse_device: n must be a multiple of 8");
+  CU(cudaSetDevice(h->device));
+  Level& L = h->lv[level];
+  CHECK(L.n == 0 || L.n == n, "set_dense_inverse_device: size does not match the level");
+  L.n = n;
+  RET(build_umma_operand(h, level, (const Cx<double>*)minv_dev));
+  L.has_dense = true;
   return 0;
 }
 
@@ -906,6 +977,8 @@ int dmlmc_set_option(dmlmc_hier* h, const char* name, double value) {
   if (std::strcmp(name, "chunk_cols") == 0) { h->chunk_cols = (int)value; return 0; }
   if (std::strcmp(name, "l2_budget_mb") == 0) { CHECK(value >= 0, "l2_budget_mb must be >= 0"); h->l2_budget_mb = value; return 0; }
   if (std::strcmp(name, "stencil_by") == 0) { CHECK(value >= 1, "stencil_by must be >= 1"); h->stencil_by = (int)value; return 0; }
+  if (std::strcmp(name, "dense_direct_exact") == 0) { h->dense_direct_exact = value != 0.0; return 0; }
+  if (std::strcmp(name, "dense_tensor_min_n") == 0) { h->dense_tensor_min_n = (int)value; return 0; }
   if (std::strcmp(name, "stencil_minb") == 0) { CHECK(value == 2 || value == 3, "stencil_minb must be 2 or 3"); h->stencil_minb = (int)value; return 0; }
   if (std::strcmp(name, "stencil_bz") == 0) { CHECK(value >= 1, "stencil_bz must be >= 1"); h->stencil_bz = (int)value; return 0; }
   return fail(-1, std::string("dmlmc: unknown option ") + name);

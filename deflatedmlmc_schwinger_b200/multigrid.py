@@ -220,7 +220,7 @@ class MG:
     """Same public surface as the reference's MG (multigrid.py:56-557)."""
 
     def __init__(self, A, smooth_iters=2, smoother_degree=32, restart=40, inner_precision="c64",
-                 device=None, dense_coarse_threshold=2048):
+                 device=None, dense_coarse_threshold=8192):
         self.level_nr = 0
         self.ml = []
         self.A = A
@@ -366,21 +366,47 @@ class MG:
                     dev.set_perm(i, lv[i].perm_shift, cols, vals)
         dev.set_inner_precision(_lib.C64 if self.inner_precision == "c64" else _lib.C128)
         self.dev = dev
-        # V-cycle bottom: the finest intermediate level small enough for a dense inverse, computed with
-        # the batched device solver itself (A_l X = I, all n_l columns in one batch)
+        # V-cycle bottom: every intermediate level small enough gets a dense inverse, computed with the
+        # batched device solver itself (A_l X = I), coarser levels first so that finer ones already use them.
+        # Up to n = 4096 the inverse is kept in all precisions; larger ones only as the BF16 tensor-core
+        # operand of the complex64 V-cycle (dmlmc_set_dense_inverse_device).
         self.dense_level = nl - 1
-        for i in range(1, nl - 1):
+        self.dense_levels = {nl - 1: "host"}
+        for i in range(nl - 2, 0, -1):
             n_i = lv[i].A.shape[0]
-            if n_i <= self.dense_coarse_threshold:
-                import torch
-                eye = torch.eye(n_i, dtype=torch.complex128, device=dev.device)
-                Minv, _, relres = dev.fgmres(i, eye, 1e-13, restart=min(self.restart, n_i), maxiter=n_i)
-                if not np.all(relres < 1e-12):
-                    raise Exception("dense coarse inverse: the device solve did not converge")
-                dev.set_dense_inverse(i, Minv.cpu().numpy())
-                self.dense_level = i
-                del eye, Minv
+            if n_i > self.dense_coarse_threshold or n_i % 8:
                 break
+            small = n_i <= 4096
+            Minv = self._device_inverse(i, 1e-13 if small else 1e-9)
+            if small:
+                dev.set_dense_inverse(i, Minv.cpu().numpy())
+            else:
+                dev.set_dense_inverse_device(i, Minv)
+            self.dense_levels[i] = "host" if small else "tensor"
+            self.dense_level = i
+            del Minv
+        dev._ws = None
+        dev._ws_key = None
+        import torch
+        torch.cuda.empty_cache()
+
+    def _device_inverse(self, level, tol, batch=1024):
+        """A_level^{-1} as a torch complex128 CUDA tensor [n, n], solved in column batches on the device"""
+        import torch
+        dev = self.dev
+        n = self.ml.levels[level].A.shape[0]
+        Minv = torch.empty((n, n), dtype=torch.complex128, device=dev.device)
+        kb = min(n, batch)
+        for c0 in range(0, n, kb):
+            w = min(kb, n - c0)
+            B = torch.zeros((n, w), dtype=torch.complex128, device=dev.device)
+            B[c0:c0 + w, :] = torch.eye(w, dtype=torch.complex128, device=dev.device)
+            X, _, relres = dev.fgmres(level, B, tol, restart=min(self.restart, n), maxiter=n)
+            if not np.all(relres < 10 * tol):
+                raise Exception("dense coarse inverse: the device solve did not converge")
+            Minv[:, c0:c0 + w] = X
+            del B, X
+        return Minv
 
     def level_degree(self, i):
         """smoother polynomial degree on level i (smoother_degree may be an int or a per-level list)"""

@@ -64,6 +64,10 @@ int dmlmc_set_coarsest_inverse(dmlmc_hier* h, int n, const double* minv_host);
 /* optional dense inverse of an intermediate level: the V-cycle then bottoms out there (exact coarse
  * solve) instead of recursing to the coarsest level.  Same layout as dmlmc_set_coarsest_inverse. */
 int dmlmc_set_dense_inverse(dmlmc_hier* h, int level, int n, const double* minv_host);
+/* same from a DEVICE matrix (complex128 [n][n], e.g. the batched solver's answer to A X = I); only the
+ * tensor-core operand is kept: BF16 [2n][2n], every complex entry as the real block [[re,-im],[im,re]],
+ * applied by the tcgen05 kernel with FP32 accumulation.  Such a level serves the complex64 V-cycle only. */
+int dmlmc_set_dense_inverse_device(dmlmc_hier* h, int level, int n, const void* minv_dev);
 /* smoother on `level`: e = p(A_level) r with the fixed polynomial p in product form,
  *   p(A) = p0 * prod_{i<nfactors} (I - nu_i A)       (nu_host: nfactors complex128, applied in order),
  * one fused operator+update kernel per factor, no inner products.  Replaces the lgmres call of
@@ -133,6 +137,10 @@ int dmlmc_level_sample_host(dmlmc_hier* h, int method, int level_f, int level_c,
  *   "chunk_cols"   columns per V-cycle chunk; 0 (default) = derive from "l2_budget_mb"
  *   "l2_budget_mb" MB that the four working vectors of a chunk may occupy (so that they stay L2-resident
  *                  over the smoother's kernels); 0 (default) = one chunk
+ *   "dense_tensor_min_n"  dense inverses with n >= this (default 1024) are applied on the tensor cores
+ *                  inside the complex64 V-cycle (BF16 operands, FP32 accumulation); smaller ones by the FP32 kernel
+ *   "dense_direct_exact"  1 (default): a V-cycle that STARTS on a dense level (that level's own solve) uses
+ *                  the FP32 copy of the inverse when there is one; 0: tensor cores there as well
  *   "stencil_by", "stencil_bz"   site tile (t, x) of the level-0 kernel's thread block (default 4 x 4)
  *   "stencil_minb" 2 | 3 (default): resident 512-thread blocks per SM the level-0 kernel is compiled for */
 int dmlmc_set_option(dmlmc_hier* h, const char* name, double value);

@@ -137,21 +137,30 @@ def test_smoother_is_the_polynomial(mg128, dtype):
         assert relerr(host(E), e) < tol, lvl
 
 
-def _vcycle_numpy(mg, b, l0):
+_DENSE_LU = {}
+
+
+def _vcycle_numpy(mg, b, l0, dense_from=None):
+    """numpy restatement of the device V-cycle; levels >= dense_from are solved exactly"""
     from deflatedmlmc_schwinger_b200.multigrid import harmonic_ritz_inv_roots
-    from scipy.sparse import csr_matrix
+    from scipy.sparse import csr_matrix, csc_matrix
+    from scipy.sparse.linalg import splu
     lv = mg.ml.levels
     nl = len(lv)
+    if dense_from is None:
+        dense_from = min(l for l, kind in mg.dense_levels.items() if kind == "host")
     if l0 == nl - 1:
         return mg.coarsest_inv @ b
-    if l0 >= mg.dense_level:
-        return np.linalg.solve(lv[l0].A.toarray(), b)
+    if l0 >= dense_from:
+        if (id(mg), l0) not in _DENSE_LU:
+            _DENSE_LU[(id(mg), l0)] = splu(csc_matrix(lv[l0].A))
+        return _DENSE_LU[(id(mg), l0)].solve(b)
     Al = csr_matrix(lv[l0].A)
     w = harmonic_ritz_inv_roots(Al, mg.level_degree(l0))
     r = b.copy(); x = np.zeros_like(b)
     for wi in w:
         x = x + wi * r; r = r - wi * (Al @ r)
-    x = x + lv[l0].P @ _vcycle_numpy(mg, lv[l0].R @ r, l0 + 1)
+    x = x + lv[l0].P @ _vcycle_numpy(mg, lv[l0].R @ r, l0 + 1, dense_from)
     r = b - Al @ x
     for wi in w:
         x = x + wi * r; r = r - wi * (Al @ r)
@@ -166,8 +175,38 @@ def test_vcycle_matches_numpy_restatement(mg128, l0):
     X = mg.dev.vcycle(l0, B)
     ref = _vcycle_numpy(mg, host(B), l0)
     assert relerr(host(X), ref) < 1e-8
+    # the complex64 cycle bottoms out at the first dense level of any kind; a tensor-core (BF16) inverse
+    # is a preconditioner-grade solve
+    first = min(mg.dense_levels)
+    bf16 = (l0 < first and (mg.dense_levels[first] == "tensor" or mg.level_shapes[first] >= 1024)) or \
+           (l0 == first and mg.dense_levels[first] == "tensor")
     Xf = mg.dev.vcycle(l0, B.to(torch.complex64))
-    assert relerr(host(Xf), ref) < 5e-3
+    assert relerr(host(Xf), _vcycle_numpy(mg, host(B), l0, first)) < (3e-2 if bf16 else 5e-3)
+
+
+def _bf16_round(a):
+    t = torch.from_numpy(np.ascontiguousarray(a))
+    return (t.real.float().bfloat16().double() + 1j * t.imag.float().bfloat16().double()).numpy()
+
+
+@pytest.mark.parametrize("k", [256, 64, 19, 2])
+def test_tensor_core_dense_apply(mg128, k):
+    """tcgen05 kernel: X = Minv B with BF16 operands and FP32 accumulation == the same product formed in
+    float64 from BF16-rounded operands (level 2, n = 2048: 32 CTAs x 64 k-blocks, ragged N for k = 19, 2)."""
+    mg, tp, A = mg128
+    lvl = 2
+    n = mg.level_shapes[lvl]
+    Minv = np.linalg.inv(mg.ml.levels[lvl].A.toarray())
+    B = rnd(n, k, torch.complex64, 80 + k)
+    mg.dev.set_option("dense_tensor_min_n", 1024)
+    mg.dev.set_option("dense_direct_exact", 0)
+    X = mg.dev.vcycle(lvl, B)
+    mg.dev.set_option("dense_direct_exact", 1)
+    ref = _bf16_round(Minv) @ _bf16_round(host(B))
+    assert relerr(host(X), ref) < 2e-5
+    assert relerr(host(X), Minv @ host(B)) < 2e-2
+    Xs = mg.dev.vcycle(lvl, B)                             # direct solve of the level: FP32 kernel
+    assert relerr(host(Xs), Minv @ host(B)) < 2e-5
 
 
 @pytest.mark.parametrize("dtype", [torch.complex128, torch.complex64])
@@ -180,8 +219,9 @@ def test_vcycle_column_chunks(mg128, dtype, k):
     mg.dev.set_option("chunk_cols", 64)
     X = mg.dev.vcycle(0, B)
     cols = [0, 1, 63, 64, k - 1]
-    ref = _vcycle_numpy(mg, host(B)[:, cols], 0)
-    assert relerr(host(X)[:, cols], ref) < (1e-8 if dtype == torch.complex128 else 5e-3)
+    first = min(mg.dense_levels)
+    ref = _vcycle_numpy(mg, host(B)[:, cols], 0, None if dtype == torch.complex128 else first)
+    assert relerr(host(X)[:, cols], ref) < (1e-8 if dtype == torch.complex128 else 3e-2)
     if k % 2 == 0:      # same kernel variants whatever the chunking: bitwise identical
         mg.dev.set_option("chunk_cols", 100000)
         X1 = mg.dev.vcycle(0, B)
