@@ -157,7 +157,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--probes", type=int, default=256, help="probes per step per GPU")
     ap.add_argument("--impl", default="b200")
-    ap.add_argument("--degree", type=int, default=32)
+    ap.add_argument("--degree", type=int, default=64)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":
@@ -220,6 +220,8 @@ def main():
     # ---- device-resident timing ------------------------------------------------------------------
     for s in range(args.warmup):
         step_device(s)
+    if world > 1:   # the level's collective once outside the timed region (NCCL sets up its channels on first use)
+        dist.all_reduce(torch.zeros(4, device="cuda", dtype=torch.float64))
     sampler = ClockSampler(local)
     barrier()
     sampler.start()

@@ -47,6 +47,7 @@ struct Level {
   int kind = -1;            // 0 stencil, 1 bsr
   int LX = 0, LT = 0;
   int bs = 0, bpr = 0, nb = 0; int* bsr_col = nullptr; float4* bsr_vals4 = nullptr;   // (mr,mr,mi,mi) per entry
+  float4* links4 = nullptr;          // [4][V] (ur,ur,ui,ui): U_t(x), U_t(x-t)^*, U_x(x), U_x(x-x)^*
   bool has_transfer = false; int aggr = 0, dofi = 0, nvec = 0, n_c = 0;
   // smoother polynomial in product form: p(A) = p0 * prod_i (I - nu_i A)
   bool has_smoother = false; std::vector<Cx<double>> nu; Cx<double> p0;
@@ -74,6 +75,8 @@ struct dmlmc_hier {
   int inner_prec = DMLMC_C64;
   int reorth = 0;
   int stencil_by = 4, stencil_bz = 4;     // site tile (t, x) of the stencil kernel's thread block
+  int stencil_fast = 1;                   // packed-FP32 (FFMA2) kernel for the FP16-stored smoother factors
+  int smoother_half = 1;                  // FP16 storage of the level-0 smoother's intermediate vectors (c64 cycle)
   int dense_direct_exact = 1;             // a dense level solved directly (not from a finer level) uses its FP32 copy
   int dense_tensor_min_n = 1024;          // dense inverses at least this large are applied on the tensor cores
   bool umma_attr_set = false;
@@ -128,7 +131,7 @@ template <typename T> int ws_get(dmlmc_hier* h, size_t count, T** out) {
 }
 
 // ---- operator dispatch ----------------------------------------------------------------------
-template <typename T, int NC, int MODE>
+template <typename T, int NC, int MODE, bool HIN = false, bool HOUT = false>
 int launch_op_nc(dmlmc_hier* h, int level, const void* X, const void* B, void* Y, Cx<double> w, Cx<double> c, int k) {
   Level& L = h->lv[level];
   LevelT<T>& D = Sel<T>::get(L);
@@ -142,9 +145,15 @@ int launch_op_nc(dmlmc_hier* h, int level, const void* X, const void* B, void* Y
     while (bx * by * bz > 512) { if (bz > 1) bz /= 2; else by /= 2; }
     while (bx * by * bz < 256 && by < L.LT) by *= 2;
     dim3 blk(bx, by, bz), grd((kp + bx - 1) / bx, (L.LT + by - 1) / by, (L.LX + bz - 1) / bz);
-    if (h->stencil_minb == 3) stencil_kernel<T, NC, MODE, 3><<<grd, blk, 0, h->stream>>>(op, (const P*)X, (const P*)B, (P*)Y, wt, ct, kp);
-    else                      stencil_kernel<T, NC, MODE, 2><<<grd, blk, 0, h->stream>>>(op, (const P*)X, (const P*)B, (P*)Y, wt, ct, kp);
-  } else if (L.kind == 1) {
+    if (h->stencil_minb == 3) stencil_kernel<T, NC, MODE, 3, HIN, HOUT><<<grd, blk, 0, h->stream>>>(op, X, (const P*)B, Y, wt, ct, kp);
+    else                      stencil_kernel<T, NC, MODE, 2, HIN, HOUT><<<grd, blk, 0, h->stream>>>(op, X, (const P*)B, Y, wt, ct, kp);
+    LAUNCH_CHECK(h);
+    return 0;
+  }
+  if constexpr (HIN || HOUT) {
+    return fail(-1, "dmlmc: FP16 vector storage is implemented for the level-0 stencil only");
+  } else {
+  if (L.kind == 1) {
     if constexpr (std::is_same<T, float>::value && NC == 2) {
       // Blackwell FFMA2 + shared-memory path for the complex64 V-cycle
       const int PPT = (L.bs <= 4) ? 2 : 1;
@@ -180,6 +189,7 @@ int launch_op_nc(dmlmc_hier* h, int level, const void* X, const void* B, void* Y
   }
   LAUNCH_CHECK(h);
   return 0;
+  }
 }
 template <typename T> constexpr int max_nc() { return sizeof(T) == 4 ? 2 : 1; }
 
@@ -345,13 +355,53 @@ int smooth_apply(dmlmc_hier* h, int level, const void* R, void* E, bool acc, voi
   void* pp[2] = {t0, t1};
   if (R == t0) { pp[0] = t1; pp[1] = t0; }
   const void* in = R;
+  const Cx<double> ONE = {1.0, 0.0};
+  if constexpr (std::is_same<T, float>::value) {
+    // complex64 cycle on the level-0 stencil: the intermediate vectors of the product are stored as FP16
+    // (FP32 arithmetic), which halves the bytes every factor kernel moves.  The vectors are pre-scaled by
+    // HS so that their entries (~ HS / sqrt(n) for a unit-norm input) sit in the middle of FP16's range.
+    if (h->smoother_half && L.kind == 0 && (k % 2) == 0 && m >= 2) {
+      const double HS = 64.0;
+      const Cx<double> cfirst = {HS, 0.0}, clast = {L.p0.re / HS, L.p0.im / HS};
+      for (int i = 0; i < m; ++i) {
+        if (i == 0) {
+          RET((launch_op_nc<float, 2, M_STEP, false, true>(h, level, in, nullptr, pp[0], L.nu[i], cfirst, k)));
+          in = pp[0];
+        } else if (i == m - 1) {
+          if (acc) RET((launch_op_nc<float, 2, M_STEP_ACC, true, false>(h, level, in, nullptr, E, L.nu[i], clast, k)));
+          else     RET((launch_op_nc<float, 2, M_STEP, true, false>(h, level, in, nullptr, E, L.nu[i], clast, k)));
+        } else {
+          void* out = pp[i & 1];
+          if (h->stencil_fast && L.d.diag.im == 0.0 && (size_t)L.n * (k / 2) < (1ull << 32)) {
+            const int kp = k / 2;
+            int bx = 1; while (bx < 32 && bx < kp) bx *= 2;
+            int by = std::max(1, std::min(h->stencil_by, L.LT)), bz = std::max(1, std::min(h->stencil_bz, L.LX));
+            while (bx * by * bz > 512) { if (bz > 1) bz /= 2; else by /= 2; }
+            while (bx * by * bz < 256 && by < L.LT) by *= 2;
+            dim3 blk(bx, by, bz), grd((kp + bx - 1) / bx, (L.LT + by - 1) / by, (L.LX + bz - 1) / bz);
+            if (h->stencil_minb == 3)
+              stencil_step_h16_kernel<3><<<grd, blk, 0, h->stream>>>(L.LX, L.LT, L.links4, (float)L.d.diag.re, (const uint2*)in,
+                                                                     (uint2*)out, (float)L.nu[i].re, (float)L.nu[i].im, (uint32_t)kp);
+            else
+              stencil_step_h16_kernel<2><<<grd, blk, 0, h->stream>>>(L.LX, L.LT, L.links4, (float)L.d.diag.re, (const uint2*)in,
+                                                                     (uint2*)out, (float)L.nu[i].re, (float)L.nu[i].im, (uint32_t)kp);
+            LAUNCH_CHECK(h);
+          } else {
+            RET((launch_op_nc<float, 2, M_STEP, true, true>(h, level, in, nullptr, out, L.nu[i], ONE, k)));
+          }
+          in = out;
+        }
+      }
+      return 0;
+    }
+  }
   for (int i = 0; i < m; ++i) {
     if (i == m - 1) {
       if (acc) RET((launch_op<T, M_STEP_ACC>(h, level, in, nullptr, E, L.nu[i], L.p0, k)));
-      else     RET((launch_op<T, M_STEP_SET>(h, level, in, nullptr, E, L.nu[i], L.p0, k)));
+      else     RET((launch_op<T, M_STEP>(h, level, in, nullptr, E, L.nu[i], L.p0, k)));
     } else {
       void* out = pp[i & 1];
-      RET((launch_op<T, M_STEP>(h, level, in, nullptr, out, L.nu[i], ZERO, k)));
+      RET((launch_op<T, M_STEP>(h, level, in, nullptr, out, L.nu[i], ONE, k)));
       in = out;
     }
   }
@@ -746,6 +796,22 @@ int dmlmc_set_stencil(dmlmc_hier* h, int level, int LX, int LT, const double* li
   RET(upload_cx(h, links_host, V, &L.d.Ut, &L.f.Ut));
   RET(upload_cx(h, links_host + 2 * V, V, &L.d.Ux, &L.f.Ux));
   L.d.diag = cx<double>(diag_re, diag_im); L.f.diag = cx<float>((float)diag_re, (float)diag_im);
+  {
+    // pre-splatted, pre-conjugated links of the packed-FP32 kernel (stencil_step_h16_kernel)
+    std::vector<float4> l4(4 * V);
+    const double* ut = links_host; const double* ux = links_host + 2 * V;
+    for (int x = 0; x < LX; ++x)
+      for (int t = 0; t < LT; ++t) {
+        const size_t s = (size_t)x * LT + t;
+        const size_t stm = (size_t)x * LT + (t == 0 ? LT - 1 : t - 1), sxm = (size_t)(x == 0 ? LX - 1 : x - 1) * LT + t;
+        auto splat = [](double re, double im) { return make_float4((float)re, (float)re, (float)im, (float)im); };
+        l4[s] = splat(ut[2 * s], ut[2 * s + 1]);
+        l4[V + s] = splat(ut[2 * stm], -ut[2 * stm + 1]);
+        l4[2 * V + s] = splat(ux[2 * s], ux[2 * s + 1]);
+        l4[3 * V + s] = splat(ux[2 * sxm], -ux[2 * sxm + 1]);
+      }
+    RET(upload<float4>(h, l4.data(), 4 * V, &L.links4));
+  }
   return 0;
 }
 
@@ -977,6 +1043,8 @@ int dmlmc_set_option(dmlmc_hier* h, const char* name, double value) {
   if (std::strcmp(name, "chunk_cols") == 0) { h->chunk_cols = (int)value; return 0; }
   if (std::strcmp(name, "l2_budget_mb") == 0) { CHECK(value >= 0, "l2_budget_mb must be >= 0"); h->l2_budget_mb = value; return 0; }
   if (std::strcmp(name, "stencil_by") == 0) { CHECK(value >= 1, "stencil_by must be >= 1"); h->stencil_by = (int)value; return 0; }
+  if (std::strcmp(name, "stencil_fast") == 0) { h->stencil_fast = value != 0.0; return 0; }
+  if (std::strcmp(name, "smoother_half") == 0) { h->smoother_half = value != 0.0; return 0; }
   if (std::strcmp(name, "dense_direct_exact") == 0) { h->dense_direct_exact = value != 0.0; return 0; }
   if (std::strcmp(name, "dense_tensor_min_n") == 0) { h->dense_tensor_min_n = (int)value; return 0; }
   if (std::strcmp(name, "stencil_minb") == 0) { CHECK(value == 2 || value == 3, "stencil_minb must be 2 or 3"); h->stencil_minb = (int)value; return 0; }

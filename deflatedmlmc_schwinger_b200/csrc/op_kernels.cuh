@@ -9,15 +9,15 @@
 // lattice site / block row, so a warp reads and writes 512 contiguous bytes per row.
 #pragma once
 #include "common.cuh"
+#include <cuda_fp16.h>
 
 namespace dmlmc {
 
 // what the operator kernels write
 enum { M_AX = 0,         // Y = A X
        M_RES = 1,        // Y = B - A X
-       M_STEP = 2,       // Y = X - w A X                 (one factor of the smoother polynomial)
-       M_STEP_SET = 3,   // Y = c (X - w A X)             (last factor, pre-smoother:  x  = p(A) b)
-       M_STEP_ACC = 4 }; // Y += c (X - w A X)            (last factor, post-smoother: x += p(A) r)
+       M_STEP = 2,       // Y = c (X - w A X)     one factor of the smoother polynomial (c = 1 except at the ends)
+       M_STEP_ACC = 3 }; // Y += c (X - w A X)    last factor of the post-smoother: x += p(A) r
 
 template <typename T> struct StencilDev {
   int LX, LT;
@@ -26,27 +26,49 @@ template <typename T> struct StencilDev {
   Cx<T> diag;        // 4 + m
 };
 
+// value an operator kernel writes at idx, given (A X)[idx] and X[idx]
 template <typename T, int NC, int MODE>
-__device__ __forceinline__ void op_epilogue(const Pack<T, NC>& ax, const Pack<T, NC>& xin, size_t idx,
-                                            const Pack<T, NC>* __restrict__ B, Pack<T, NC>* __restrict__ Y,
-                                            Cx<T> w, Cx<T> c) {
+__device__ __forceinline__ Pack<T, NC> op_value(const Pack<T, NC>& ax, const Pack<T, NC>& xin, size_t idx,
+                                                const Pack<T, NC>* __restrict__ B, const Pack<T, NC>* Yold,
+                                                Cx<T> w, Cx<T> c) {
   if constexpr (MODE == M_AX) {
-    Y[idx] = ax;
+    return ax;
   } else if constexpr (MODE == M_RES) {
-    Y[idx] = psub<T, NC>(ldp_ro<T, NC>(B, idx), ax);
+    return psub<T, NC>(ldp_ro<T, NC>(B, idx), ax);
   } else {
     Pack<T, NC> rn = xin;
     pfms<T, NC>(rn, w, ax);
     if constexpr (MODE == M_STEP) {
-      Y[idx] = rn;
-    } else if constexpr (MODE == M_STEP_SET) {
-      Y[idx] = pscale<T, NC>(c, rn);
+      return pscale<T, NC>(c, rn);
     } else {
-      Pack<T, NC> e = Y[idx];
+      Pack<T, NC> e = Yold[idx];
       pfma<T, NC>(e, c, rn);
-      Y[idx] = e;
+      return e;
     }
   }
+}
+template <typename T, int NC, int MODE>
+__device__ __forceinline__ void op_epilogue(const Pack<T, NC>& ax, const Pack<T, NC>& xin, size_t idx,
+                                            const Pack<T, NC>* __restrict__ B, Pack<T, NC>* __restrict__ Y,
+                                            Cx<T> w, Cx<T> c) {
+  Y[idx] = op_value<T, NC, MODE>(ax, xin, idx, B, Y, w, c);
+}
+
+// two complex64 columns stored as FP16 (8 bytes): the storage format of the level-0 smoother's
+// intermediate vectors (arithmetic stays FP32; QUDA-style half-precision preconditioner storage)
+__device__ __forceinline__ Pack<float, 2> ldh2_ro(const void* base, size_t idx) {
+  const float2 raw = __ldg(reinterpret_cast<const float2*>(base) + idx);
+  const float2 a = __half22float2(*reinterpret_cast<const __half2*>(&raw.x));
+  const float2 b = __half22float2(*reinterpret_cast<const __half2*>(&raw.y));
+  Pack<float, 2> r; r.d[0] = a.x; r.d[1] = a.y; r.d[2] = b.x; r.d[3] = b.y;
+  return r;
+}
+__device__ __forceinline__ void sth2(void* base, size_t idx, const Pack<float, 2>& v) {
+  const __half2 a = __floats2half2_rn(v.d[0], v.d[1]), b = __floats2half2_rn(v.d[2], v.d[3]);
+  float2 raw;
+  *reinterpret_cast<__half2*>(&raw.x) = a;
+  *reinterpret_cast<__half2*>(&raw.y) = b;
+  reinterpret_cast<float2*>(base)[idx] = raw;
 }
 
 // A psi(x) = diag psi(x) - [ (1-s1) Ut(x) psi(x+t) + (1+s1) Ut(x-t)^* psi(x-t)
@@ -58,10 +80,17 @@ __device__ __forceinline__ void op_epilogue(const Pack<T, NC>& ax, const Pack<T,
 // (TT*TX + 2TT + 2TX)/(TT*TX) times instead of 5.
 // MINB = 2: 64 registers, all 14 loads of a thread in flight at once; MINB = 3: 40 registers, loads in
 // batches of 6 but 50 % more resident threads.
-template <typename T, int NC, int MODE, int MINB>
+// HIN / HOUT: X / Y are FP16-stored (complex64 arithmetic, NC = 2 only).
+template <typename T, int NC, int MODE, int MINB, bool HIN = false, bool HOUT = false>
 __global__ void __launch_bounds__(512, MINB)
-stencil_kernel(StencilDev<T> op, const Pack<T, NC>* __restrict__ X, const Pack<T, NC>* __restrict__ B,
-               Pack<T, NC>* __restrict__ Y, Cx<T> w, Cx<T> cfin, int kp) {
+stencil_kernel(StencilDev<T> op, const void* __restrict__ Xv, const Pack<T, NC>* __restrict__ B,
+               void* __restrict__ Yv, Cx<T> w, Cx<T> cfin, int kp) {
+  static_assert(!(HIN || HOUT) || (sizeof(T) == 4 && NC == 2), "FP16 storage is a complex64, 2-column format");
+  const Pack<T, NC>* __restrict__ X = reinterpret_cast<const Pack<T, NC>*>(Xv);
+  Pack<T, NC>* __restrict__ Y = reinterpret_cast<Pack<T, NC>*>(Yv);
+  auto ldx = [&](size_t idx) -> Pack<T, NC> {
+    if constexpr (HIN) return ldh2_ro(Xv, idx); else return ldp_ro<T, NC>(X, idx);
+  };
   const int LX = op.LX, LT = op.LT, V = LX * LT;
   const int cp = blockIdx.x * blockDim.x + threadIdx.x;
   const int t = blockIdx.y * blockDim.y + threadIdx.y;
@@ -74,11 +103,11 @@ stencil_kernel(StencilDev<T> op, const Pack<T, NC>* __restrict__ X, const Pack<T
   const size_t kpz = (size_t)kp, Vz = (size_t)V;
 
   typedef Pack<T, NC> P;
-  const P c0 = ldp_ro<T, NC>(X, (size_t)site * kpz + cp),  c1 = ldp_ro<T, NC>(X, (Vz + site) * kpz + cp);
-  const P f0 = ldp_ro<T, NC>(X, (size_t)s_tp * kpz + cp),  f1 = ldp_ro<T, NC>(X, (Vz + s_tp) * kpz + cp);
-  const P b0 = ldp_ro<T, NC>(X, (size_t)s_tm * kpz + cp),  b1 = ldp_ro<T, NC>(X, (Vz + s_tm) * kpz + cp);
-  const P r0 = ldp_ro<T, NC>(X, (size_t)s_xp * kpz + cp),  r1 = ldp_ro<T, NC>(X, (Vz + s_xp) * kpz + cp);
-  const P l0 = ldp_ro<T, NC>(X, (size_t)s_xm * kpz + cp),  l1 = ldp_ro<T, NC>(X, (Vz + s_xm) * kpz + cp);
+  const P c0 = ldx((size_t)site * kpz + cp),  c1 = ldx((Vz + site) * kpz + cp);
+  const P f0 = ldx((size_t)s_tp * kpz + cp),  f1 = ldx((Vz + s_tp) * kpz + cp);
+  const P b0 = ldx((size_t)s_tm * kpz + cp),  b1 = ldx((Vz + s_tm) * kpz + cp);
+  const P r0 = ldx((size_t)s_xp * kpz + cp),  r1 = ldx((Vz + s_xp) * kpz + cp);
+  const P l0 = ldx((size_t)s_xm * kpz + cp),  l1 = ldx((Vz + s_xm) * kpz + cp);
   const Cx<T> ut = ldc_ro<T>(op.Ut, site), utb = cconj(ldc_ro<T>(op.Ut, s_tm));
   const Cx<T> ux = ldc_ro<T>(op.Ux, site), uxb = cconj(ldc_ro<T>(op.Ux, s_xm));
 
@@ -94,8 +123,101 @@ stencil_kernel(StencilDev<T> op, const Pack<T, NC>* __restrict__ X, const Pack<T
   // spin 1: -ua + ub - i uc + i ud
   y1 = psub<T, NC>(y1, padd<T, NC>(psub<T, NC>(ub, ua), pmul_i<T, NC>(psub<T, NC>(ud, uc))));
 
-  op_epilogue<T, NC, MODE>(y0, c0, (size_t)site * kpz + cp, B, Y, w, cfin);
-  op_epilogue<T, NC, MODE>(y1, c1, (Vz + site) * kpz + cp, B, Y, w, cfin);
+  const size_t i0 = (size_t)site * kpz + cp, i1 = (Vz + site) * kpz + cp;
+  const P o0 = op_value<T, NC, MODE>(y0, c0, i0, B, Y, w, cfin);
+  const P o1 = op_value<T, NC, MODE>(y1, c1, i1, B, Y, w, cfin);
+  if constexpr (HOUT) { sth2(Yv, i0, o0); sth2(Yv, i1, o1); } else { Y[i0] = o0; Y[i1] = o1; }
+}
+
+// ------------------------------------------------------------------------------------------
+// The hot kernel of the complex64 V-cycle: one factor Y = X - w A X of the level-0 smoother with
+// FP16-stored vectors.  The generic stencil_kernel is instruction-issue bound (ncu: 80 % issue-active,
+// 313 instructions per thread, DRAM and L2 below 20 % because the FP16 ping-pong vectors live in L2),
+// so this version minimises instructions:
+//   * the two columns of a thread are held as (re0,re1) / (im0,im1) register pairs, so every
+//     complex operation is packed FP32 (FADD2 / FMUL2 / FFMA2, Blackwell) for both columns at once;
+//   * links come pre-splatted and pre-conjugated, L4[dir][site] = (ur,ur,ui,ui) for
+//     dir = U_t(x), U_t(x-t)^*, U_x(x), U_x(x-x)^*: one LDG.128 per direction, no splat/negate code;
+//   * 32-bit element indices (one IMAD.WIDE per address).
+struct C2 { float2 re, im; };     // two complex64 columns
+
+__device__ __forceinline__ C2 ldh_c2(const uint2* __restrict__ base, uint32_t idx) {
+  const uint2 raw = __ldg(base + idx);
+  const __half2 a = *reinterpret_cast<const __half2*>(&raw.x), b = *reinterpret_cast<const __half2*>(&raw.y);
+  C2 r;
+  r.re = make_float2(__low2float(a), __low2float(b));
+  r.im = make_float2(__high2float(a), __high2float(b));
+  return r;
+}
+__device__ __forceinline__ void sth_c2(uint2* __restrict__ base, uint32_t idx, const C2& v) {
+  const __half2 a = __floats2half2_rn(v.re.x, v.im.x), b = __floats2half2_rn(v.re.y, v.im.y);
+  uint2 raw;
+  raw.x = *reinterpret_cast<const uint32_t*>(&a);
+  raw.y = *reinterpret_cast<const uint32_t*>(&b);
+  base[idx] = raw;
+}
+__device__ __forceinline__ float2 neg2(float2 a) { return make_float2(-a.x, -a.y); }
+// u * v with u = (ur,ur,ui,ui)
+__device__ __forceinline__ C2 cmul_splat(const float4& u, const C2& v) {
+  const float2 ur = make_float2(u.x, u.y), ui = make_float2(u.z, u.w);
+  C2 p;
+  p.re = __ffma2_rn(neg2(ui), v.im, __fmul2_rn(ur, v.re));
+  p.im = __ffma2_rn(ui, v.re, __fmul2_rn(ur, v.im));
+  return p;
+}
+
+template <int MINB>
+__global__ void __launch_bounds__(512, MINB)
+stencil_step_h16_kernel(int LX, int LT, const float4* __restrict__ L4, float diag,
+                        const uint2* __restrict__ X, uint2* __restrict__ Y, float wr, float wi, uint32_t kp) {
+  const uint32_t cp = blockIdx.x * blockDim.x + threadIdx.x;
+  const uint32_t t = blockIdx.y * blockDim.y + threadIdx.y;
+  const uint32_t x = blockIdx.z * blockDim.z + threadIdx.z;
+  if (cp >= kp || t >= (uint32_t)LT || x >= (uint32_t)LX) return;
+  const uint32_t V = (uint32_t)LX * LT;
+  const uint32_t site = x * LT + t;
+  const uint32_t s_tp = (t + 1 == (uint32_t)LT) ? site + 1 - LT : site + 1;
+  const uint32_t s_tm = (t == 0) ? site + LT - 1 : site - 1;
+  const uint32_t s_xp = (x + 1 == (uint32_t)LX) ? t : site + LT;
+  const uint32_t s_xm = (x == 0) ? site + V - LT : site - LT;
+  const uint32_t sp = V * kp;                        // offset of the second spin component
+
+  const uint32_t ic = site * kp + cp, itp = s_tp * kp + cp, itm = s_tm * kp + cp, ixp = s_xp * kp + cp, ixm = s_xm * kp + cp;
+  const C2 c0 = ldh_c2(X, ic),  c1 = ldh_c2(X, ic + sp);
+  const C2 f0 = ldh_c2(X, itp), f1 = ldh_c2(X, itp + sp);
+  const C2 b0 = ldh_c2(X, itm), b1 = ldh_c2(X, itm + sp);
+  const C2 r0 = ldh_c2(X, ixp), r1 = ldh_c2(X, ixp + sp);
+  const C2 l0 = ldh_c2(X, ixm), l1 = ldh_c2(X, ixm + sp);
+  const float4 ut = __ldg(L4 + site), utb = __ldg(L4 + V + site), ux = __ldg(L4 + 2 * V + site), uxb = __ldg(L4 + 3 * V + site);
+
+  C2 a, b, c, d;                                     // spin projections (see stencil_kernel)
+  a.re = __fadd2_rn(f0.re, neg2(f1.re)); a.im = __fadd2_rn(f0.im, neg2(f1.im));      // f0 - f1
+  b.re = __fadd2_rn(b0.re, b1.re);       b.im = __fadd2_rn(b0.im, b1.im);            // b0 + b1
+  c.re = __fadd2_rn(r0.re, neg2(r1.im)); c.im = __fadd2_rn(r0.im, r1.re);            // r0 + i r1
+  d.re = __fadd2_rn(l0.re, l1.im);       d.im = __fadd2_rn(l0.im, neg2(l1.re));      // l0 - i l1
+  const C2 ua = cmul_splat(ut, a), ub = cmul_splat(utb, b), uc = cmul_splat(ux, c), ud = cmul_splat(uxb, d);
+
+  // (A x)_0 = diag c0 - (ua + ub + uc + ud);   (A x)_1 = diag c1 + (ua - ub) + i (uc - ud)
+  const float2 dg = make_float2(diag, diag);
+  C2 s, q, tt, y0, y1;
+  s.re = __fadd2_rn(__fadd2_rn(ua.re, ub.re), __fadd2_rn(uc.re, ud.re));
+  s.im = __fadd2_rn(__fadd2_rn(ua.im, ub.im), __fadd2_rn(uc.im, ud.im));
+  q.re = __fadd2_rn(ua.re, neg2(ub.re));  q.im = __fadd2_rn(ua.im, neg2(ub.im));
+  tt.re = __fadd2_rn(uc.re, neg2(ud.re)); tt.im = __fadd2_rn(uc.im, neg2(ud.im));
+  y0.re = __ffma2_rn(dg, c0.re, neg2(s.re));
+  y0.im = __ffma2_rn(dg, c0.im, neg2(s.im));
+  y1.re = __ffma2_rn(dg, c1.re, __fadd2_rn(q.re, neg2(tt.im)));
+  y1.im = __ffma2_rn(dg, c1.im, __fadd2_rn(q.im, tt.re));
+
+  // x - w (A x)
+  const float2 w_r = make_float2(wr, wr), w_i = make_float2(wi, wi);
+  C2 o0, o1;
+  o0.re = __ffma2_rn(w_i, y0.im, __ffma2_rn(neg2(w_r), y0.re, c0.re));
+  o0.im = __ffma2_rn(neg2(w_i), y0.re, __ffma2_rn(neg2(w_r), y0.im, c0.im));
+  o1.re = __ffma2_rn(w_i, y1.im, __ffma2_rn(neg2(w_r), y1.re, c1.re));
+  o1.im = __ffma2_rn(neg2(w_i), y1.re, __ffma2_rn(neg2(w_r), y1.im, c1.im));
+  sth_c2(Y, ic, o0);
+  sth_c2(Y, ic + sp, o1);
 }
 
 // ------------------------------------------------------------------------------------------

@@ -22,7 +22,7 @@ def _say(params, *a, **kw):
 
 
 def _make_solver(A, params):
-    mg_solver = MG(A, smoother_degree=params.get('smoother_degree', 32), restart=params.get('fgmres_restart', 40),
+    mg_solver = MG(A, smoother_degree=params.get('smoother_degree', 64), restart=params.get('fgmres_restart', 40),
                    inner_precision=params.get('inner_precision', 'c64'))
     mg_solver.coarsest_iters = 0
     mg_solver.coarsest_iters_tot = 0

@@ -1,0 +1,77 @@
+"""End-to-end run of the reference's shipped experiment G202 (gateway.py:52-59: Schwinger 128^2, deflated MLMC,
+permuted, level 1 skipped, variance target trace_tol = 1e-2) and of G102 (deflated Hutchinson) on the GPU path,
+through the drop-in modules.  One JSON line per experiment on rank 0.
+
+    python profiles/run_e2e.py [--golden-tvs] [--skip-hutchinson] [--batch 256]
+    python -m torch.distributed.run --nproc-per-node N --master-addr 127.0.0.1 profiles/run_e2e.py ...
+
+--golden-tvs injects the test vectors of tests/golden/schwinger128.npz (skips the host eigensolve of
+multigrid.py:174, so that the hierarchy equals the oracle's)."""
+import argparse, json, os, sys, time
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+os.environ.setdefault("OMP_NUM_THREADS", "1")
+import numpy as np
+
+EXACT_DISPLACED = -8.748242701374695 + 50.215154098005584j      # gateway.py:104
+
+ap = argparse.ArgumentParser()
+ap.add_argument("--golden-tvs", action="store_true")
+ap.add_argument("--skip-hutchinson", action="store_true")
+ap.add_argument("--batch", type=int, default=256)
+ap.add_argument("--fixed", action="store_true", help="sequential_stop=False: sample count from a pilot round, one all_reduce per level")
+args = ap.parse_args()
+
+import torch
+import torch.distributed as dist
+rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1")); local = int(os.environ.get("LOCAL_RANK", "0"))
+torch.cuda.set_device(local)
+if world > 1:
+    dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+import __graft_entry__ as ge
+if rank == 0:
+    ge.build()
+if world > 1:
+    dist.barrier()
+from deflatedmlmc_schwinger_b200 import gateway, matrix, stoch_trace, utils
+
+
+def run(method):
+    p = gateway.set_params("schwinger128")
+    p["function_tol"] = 1e-12
+    p["verbose"] = False
+    p["probe_batch"] = args.batch
+    p["sequential_stop"] = not args.fixed
+    tp = utils.trace_params_from_params(p, method)
+    if args.golden_tvs:
+        g = np.load(os.path.join(ROOT, "tests", "golden", "schwinger128.npz"))
+        tp["test_vectors"] = [g["tv0"], g["tv1"], g["tv2"]]
+    A = matrix.loadMatrix(p["matrix"], p["matrix_params"])
+    t0 = time.time()
+    res = (stoch_trace.mlmc if method == "mlmc" else stoch_trace.hutchinson)(A, tp)
+    torch.cuda.synchronize()
+    wall = time.time() - t0
+    out = {"experiment": "G202 (mlmc)" if method == "mlmc" else "G102 (hutchinson)", "n_gpus": world,
+           "trace": [float(np.real(res["trace"])), float(np.imag(res["trace"]))],
+           "exact": [EXACT_DISPLACED.real, EXACT_DISPLACED.imag],
+           "abs_err": float(abs(res["trace"] - EXACT_DISPLACED)),
+           "target_err": float(abs(1e-2 * res["rough_trace"])),
+           "rough_trace": [float(np.real(res["rough_trace"])), float(np.imag(res["rough_trace"]))],
+           "wall_s": wall, "sampling_s": float(res["sampling_seconds"]), "probes_evaluated": res["probes_evaluated"],
+           "sequential_stop": not args.fixed, "probe_batch_per_gpu": args.batch}
+    if method == "mlmc":
+        out["levels"] = [{"nr_ests": int(r["nr_ests"]), "avg": [float(np.real(r["ests_avg"])), float(np.imag(r["ests_avg"]))],
+                          "dev": float(r["ests_dev"]), "function_iters": int(r["function_iters"])} for r in res["results"]]
+        out["probes_per_s"] = float(sum(res["probes_evaluated"]) / res["sampling_seconds"])
+    else:
+        out["nr_ests"] = int(res["nr_ests"]); out["std_dev"] = float(res["std_dev"])
+        out["probes_per_s"] = float(res["probes_evaluated"] / res["sampling_seconds"])
+    if rank == 0:
+        print(json.dumps(out), flush=True)
+
+
+run("mlmc")
+if not args.skip_hutchinson:
+    run("hutchinson")
+if world > 1:
+    dist.destroy_process_group()
