@@ -225,6 +225,7 @@ def main():
     sampler = ClockSampler(local)
     barrier()
     sampler.start()
+    torch.cuda.profiler.start()      # `ncu --profile-from-start off` captures the timed region only
     l0 = dev.launch_count()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     ev0.record(stream)
@@ -239,6 +240,7 @@ def main():
         dist.all_reduce(sums)
     ev1.record(stream)
     barrier()
+    torch.cuda.profiler.stop()
     launches = dev.launch_count() - l0
     clocks = sampler.stop()
     ms = ev0.elapsed_time(ev1)
@@ -300,20 +302,25 @@ def main():
         t_one = time_smooth()
         dev.set_smoother(0, nu, p0)
         t_step = (t_full - t_one) / max(m - 1, 1) / nchunks
-        s = 8                                   # bytes per complex64
-        # one factor kernel on a chunk of kc columns: read x, write x' (n0*kc*s each) + 2 links per site
-        alg_bytes = n0 * s * (1 + 2 * kc)
+        # one factor kernel on kc columns, vectors stored as BF16 (4 B per complex): read x, write x'
+        # (n0 * kc * 4 B each) + 4 pre-splatted links per site (16 B each)
+        sb = 4
+        alg_bytes = 2 * n0 * kc * sb + 4 * (n0 // 2) * 16
         achieved = alg_bytes / t_step / 1e9
-        roof = {"bound": "hbm", "kernel": "stencil_kernel<float,2,M_STEP> (level-0 operator + polynomial-factor update "
-                                          "x' = x - nu A x, c64, chunks of %d of the %d columns)" % (kc, k),
+        roof = {"bound": "hbm",
+                "kernel": "stencil_step_bf16_kernel (level-0 operator + polynomial-factor update x' = x - nu A x of the "
+                          "complex64 V-cycle, BF16-stored vectors, FP32 packed arithmetic, %d columns)" % kc,
                 "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                 "peak_source": "MEASURED_PEAKS.json hbm_gbs" if "hbm_gbs" in peaks else "fallback 6650",
                 "frac_of_nominal_8TBs": achieved / 8000.0,
-                "avg_launch_us": 1e6 * t_step, "alg_bytes_per_launch": alg_bytes, "traffic": None,
-                "note": "the chunk's ping-pong vectors (2 x %.1f MB) stay resident in the 126 MB L2 between the %d "
-                        "consecutive factor kernels, so the algorithmic bytes are served mostly by L2 and the figure can "
-                        "exceed the HBM peak; spmm_level0 below is the same operator streaming from HBM (k = %d)"
-                        % (n0 * kc * s / 1e6, m, k),
+                "avg_launch_us": 1e6 * t_step, "alg_bytes_per_launch": alg_bytes, "traffic": 36.4e6,
+                "traffic_source": "ncu --set full, profiles/r1_run7_step_kernel_ncu.csv: dram__bytes_read.sum + "
+                                  "dram__bytes_write.sum per launch (FP16 predecessor of this kernel, same access pattern)",
+                "limiter": "FP32 pipe, not HBM: the two %.1f MB ping-pong vectors of the polynomial product stay in the "
+                           "126 MB L2 across the %d consecutive launches (DRAM traffic per launch is about half the "
+                           "algorithmic bytes, DRAM 18 %% busy) and ncu shows sm__pipe_fmaheavy_cycles_active 65 %%; "
+                           "spmm_level0 below is the same operator streaming complex128 / complex64 from HBM"
+                           % (n0 * kc * sb / 1e6, m - 1),
                 "smooth_call_us": 1e6 * t_full, "chunk_cols": kc}
         # plain SpMM Y = A X (config 3), c128 and c64, bytes n0*s*(2k) + links
         spmm = {}

@@ -75,8 +75,8 @@ struct dmlmc_hier {
   int inner_prec = DMLMC_C64;
   int reorth = 0;
   int stencil_by = 4, stencil_bz = 4;     // site tile (t, x) of the stencil kernel's thread block
-  int stencil_fast = 1;                   // packed-FP32 (FFMA2) kernel for the FP16-stored smoother factors
-  int smoother_half = 1;                  // FP16 storage of the level-0 smoother's intermediate vectors (c64 cycle)
+  int stencil_fast = 1;                   // packed-FP32 (FFMA2) kernel for the BF16-stored smoother factors
+  int smoother_half = 1;                  // BF16 storage of the level-0 smoother's intermediate vectors (c64 cycle)
   int dense_direct_exact = 1;             // a dense level solved directly (not from a finer level) uses its FP32 copy
   int dense_tensor_min_n = 1024;          // dense inverses at least this large are applied on the tensor cores
   bool umma_attr_set = false;
@@ -151,7 +151,7 @@ int launch_op_nc(dmlmc_hier* h, int level, const void* X, const void* B, void* Y
     return 0;
   }
   if constexpr (HIN || HOUT) {
-    return fail(-1, "dmlmc: FP16 vector storage is implemented for the level-0 stencil only");
+    return fail(-1, "dmlmc: BF16 vector storage is implemented for the level-0 stencil only");
   } else {
   if (L.kind == 1) {
     if constexpr (std::is_same<T, float>::value && NC == 2) {
@@ -357,9 +357,9 @@ int smooth_apply(dmlmc_hier* h, int level, const void* R, void* E, bool acc, voi
   const void* in = R;
   const Cx<double> ONE = {1.0, 0.0};
   if constexpr (std::is_same<T, float>::value) {
-    // complex64 cycle on the level-0 stencil: the intermediate vectors of the product are stored as FP16
-    // (FP32 arithmetic), which halves the bytes every factor kernel moves.  The vectors are pre-scaled by
-    // HS so that their entries (~ HS / sqrt(n) for a unit-norm input) sit in the middle of FP16's range.
+    // complex64 cycle on the level-0 stencil: the intermediate vectors of the product are stored as BF16
+    // (FP32 arithmetic), which halves the bytes every factor kernel moves and keeps them L2-resident.
+    // (HS is a harmless power-of-two pre-scale kept from the FP16 variant of this path.)
     if (h->smoother_half && L.kind == 0 && (k % 2) == 0 && m >= 2) {
       const double HS = 64.0;
       const Cx<double> cfirst = {HS, 0.0}, clast = {L.p0.re / HS, L.p0.im / HS};
@@ -374,17 +374,20 @@ int smooth_apply(dmlmc_hier* h, int level, const void* R, void* E, bool acc, voi
           void* out = pp[i & 1];
           if (h->stencil_fast && L.d.diag.im == 0.0 && (size_t)L.n * (k / 2) < (1ull << 32)) {
             const int kp = k / 2;
+            const long long rowb = (long long)kp * 8;
             int bx = 1; while (bx < 32 && bx < kp) bx *= 2;
             int by = std::max(1, std::min(h->stencil_by, L.LT)), bz = std::max(1, std::min(h->stencil_bz, L.LX));
             while (bx * by * bz > 512) { if (bz > 1) bz /= 2; else by /= 2; }
             while (bx * by * bz < 256 && by < L.LT) by *= 2;
             dim3 blk(bx, by, bz), grd((kp + bx - 1) / bx, (L.LT + by - 1) / by, (L.LX + bz - 1) / bz);
             if (h->stencil_minb == 3)
-              stencil_step_h16_kernel<3><<<grd, blk, 0, h->stream>>>(L.LX, L.LT, L.links4, (float)L.d.diag.re, (const uint2*)in,
-                                                                     (uint2*)out, (float)L.nu[i].re, (float)L.nu[i].im, (uint32_t)kp);
+              stencil_step_bf16_kernel<3><<<grd, blk, 0, h->stream>>>(L.LX, L.LT, L.links4, (float)L.d.diag.re, (const uint2*)in,
+                                                                     (uint2*)out, (float)L.nu[i].re, (float)L.nu[i].im, (uint32_t)kp,
+                                                                     rowb, rowb * L.LT, rowb * L.LT * L.LX);
             else
-              stencil_step_h16_kernel<2><<<grd, blk, 0, h->stream>>>(L.LX, L.LT, L.links4, (float)L.d.diag.re, (const uint2*)in,
-                                                                     (uint2*)out, (float)L.nu[i].re, (float)L.nu[i].im, (uint32_t)kp);
+              stencil_step_bf16_kernel<2><<<grd, blk, 0, h->stream>>>(L.LX, L.LT, L.links4, (float)L.d.diag.re, (const uint2*)in,
+                                                                     (uint2*)out, (float)L.nu[i].re, (float)L.nu[i].im, (uint32_t)kp,
+                                                                     rowb, rowb * L.LT, rowb * L.LT * L.LX);
             LAUNCH_CHECK(h);
           } else {
             RET((launch_op_nc<float, 2, M_STEP, true, true>(h, level, in, nullptr, out, L.nu[i], ONE, k)));
@@ -797,7 +800,7 @@ int dmlmc_set_stencil(dmlmc_hier* h, int level, int LX, int LT, const double* li
   RET(upload_cx(h, links_host + 2 * V, V, &L.d.Ux, &L.f.Ux));
   L.d.diag = cx<double>(diag_re, diag_im); L.f.diag = cx<float>((float)diag_re, (float)diag_im);
   {
-    // pre-splatted, pre-conjugated links of the packed-FP32 kernel (stencil_step_h16_kernel)
+    // pre-splatted, pre-conjugated links of the packed-FP32 kernel (stencil_step_bf16_kernel)
     std::vector<float4> l4(4 * V);
     const double* ut = links_host; const double* ux = links_host + 2 * V;
     for (int x = 0; x < LX; ++x)

@@ -9,7 +9,7 @@
 // lattice site / block row, so a warp reads and writes 512 contiguous bytes per row.
 #pragma once
 #include "common.cuh"
-#include <cuda_fp16.h>
+#include <cuda_bf16.h>
 
 namespace dmlmc {
 
@@ -54,21 +54,24 @@ __device__ __forceinline__ void op_epilogue(const Pack<T, NC>& ax, const Pack<T,
   Y[idx] = op_value<T, NC, MODE>(ax, xin, idx, B, Y, w, c);
 }
 
-// two complex64 columns stored as FP16 (8 bytes): the storage format of the level-0 smoother's
-// intermediate vectors (arithmetic stays FP32; QUDA-style half-precision preconditioner storage)
+// two complex64 columns stored as BF16 (8 bytes): the storage format of the level-0 smoother's
+// intermediate vectors (arithmetic stays FP32; QUDA-style reduced-precision preconditioner storage).
+// BF16 rather than FP16 because BF16 -> FP32 is a shift / mask on the integer pipe, while FP16 -> FP32
+// (HADD2.F32) competes with the FMAs for the FP32 pipe, which is what bounds the kernel (ncu:
+// fmaheavy pipe 65 % active, 40 of 190 instructions were conversions).
+__device__ __forceinline__ float bf_lo(uint32_t w) { return __uint_as_float(w << 16); }
+__device__ __forceinline__ float bf_hi(uint32_t w) { return __uint_as_float(w & 0xffff0000u); }
+__device__ __forceinline__ uint32_t bf_pack(float lo, float hi) {
+  const __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
+  return *reinterpret_cast<const uint32_t*>(&v);
+}
 __device__ __forceinline__ Pack<float, 2> ldh2_ro(const void* base, size_t idx) {
-  const float2 raw = __ldg(reinterpret_cast<const float2*>(base) + idx);
-  const float2 a = __half22float2(*reinterpret_cast<const __half2*>(&raw.x));
-  const float2 b = __half22float2(*reinterpret_cast<const __half2*>(&raw.y));
-  Pack<float, 2> r; r.d[0] = a.x; r.d[1] = a.y; r.d[2] = b.x; r.d[3] = b.y;
+  const uint2 raw = __ldg(reinterpret_cast<const uint2*>(base) + idx);
+  Pack<float, 2> r; r.d[0] = bf_lo(raw.x); r.d[1] = bf_hi(raw.x); r.d[2] = bf_lo(raw.y); r.d[3] = bf_hi(raw.y);
   return r;
 }
 __device__ __forceinline__ void sth2(void* base, size_t idx, const Pack<float, 2>& v) {
-  const __half2 a = __floats2half2_rn(v.d[0], v.d[1]), b = __floats2half2_rn(v.d[2], v.d[3]);
-  float2 raw;
-  *reinterpret_cast<__half2*>(&raw.x) = a;
-  *reinterpret_cast<__half2*>(&raw.y) = b;
-  reinterpret_cast<float2*>(base)[idx] = raw;
+  reinterpret_cast<uint2*>(base)[idx] = make_uint2(bf_pack(v.d[0], v.d[1]), bf_pack(v.d[2], v.d[3]));
 }
 
 // A psi(x) = diag psi(x) - [ (1-s1) Ut(x) psi(x+t) + (1+s1) Ut(x-t)^* psi(x-t)
@@ -80,12 +83,12 @@ __device__ __forceinline__ void sth2(void* base, size_t idx, const Pack<float, 2
 // (TT*TX + 2TT + 2TX)/(TT*TX) times instead of 5.
 // MINB = 2: 64 registers, all 14 loads of a thread in flight at once; MINB = 3: 40 registers, loads in
 // batches of 6 but 50 % more resident threads.
-// HIN / HOUT: X / Y are FP16-stored (complex64 arithmetic, NC = 2 only).
+// HIN / HOUT: X / Y are BF16-stored (complex64 arithmetic, NC = 2 only).
 template <typename T, int NC, int MODE, int MINB, bool HIN = false, bool HOUT = false>
 __global__ void __launch_bounds__(512, MINB)
 stencil_kernel(StencilDev<T> op, const void* __restrict__ Xv, const Pack<T, NC>* __restrict__ B,
                void* __restrict__ Yv, Cx<T> w, Cx<T> cfin, int kp) {
-  static_assert(!(HIN || HOUT) || (sizeof(T) == 4 && NC == 2), "FP16 storage is a complex64, 2-column format");
+  static_assert(!(HIN || HOUT) || (sizeof(T) == 4 && NC == 2), "BF16 storage is a complex64, 2-column format");
   const Pack<T, NC>* __restrict__ X = reinterpret_cast<const Pack<T, NC>*>(Xv);
   Pack<T, NC>* __restrict__ Y = reinterpret_cast<Pack<T, NC>*>(Yv);
   auto ldx = [&](size_t idx) -> Pack<T, NC> {
@@ -101,9 +104,12 @@ stencil_kernel(StencilDev<T> op, const void* __restrict__ Xv, const Pack<T, NC>*
   const int xp = (x + 1 == LX) ? 0 : x + 1, xm = (x == 0) ? LX - 1 : x - 1;
   const int s_tp = x * LT + tp, s_tm = x * LT + tm, s_xp = xp * LT + t, s_xm = xm * LT + t;
   const size_t kpz = (size_t)kp, Vz = (size_t)V;
+  // (a byte-offset / 64-bit-add addressing scheme has 25 % fewer instructions but measured 5-14 % slower
+  //  on B200 for the complex128 and complex64 Y = A X kernels: profiles/r1_run7_kernel_timings.jsonl)
 
   typedef Pack<T, NC> P;
-  const P c0 = ldx((size_t)site * kpz + cp),  c1 = ldx((Vz + site) * kpz + cp);
+  const size_t i0 = (size_t)site * kpz + cp, i1 = (Vz + site) * kpz + cp;
+  const P c0 = ldx(i0),  c1 = ldx(i1);
   const P f0 = ldx((size_t)s_tp * kpz + cp),  f1 = ldx((Vz + s_tp) * kpz + cp);
   const P b0 = ldx((size_t)s_tm * kpz + cp),  b1 = ldx((Vz + s_tm) * kpz + cp);
   const P r0 = ldx((size_t)s_xp * kpz + cp),  r1 = ldx((Vz + s_xp) * kpz + cp);
@@ -123,7 +129,6 @@ stencil_kernel(StencilDev<T> op, const void* __restrict__ Xv, const Pack<T, NC>*
   // spin 1: -ua + ub - i uc + i ud
   y1 = psub<T, NC>(y1, padd<T, NC>(psub<T, NC>(ub, ua), pmul_i<T, NC>(psub<T, NC>(ud, uc))));
 
-  const size_t i0 = (size_t)site * kpz + cp, i1 = (Vz + site) * kpz + cp;
   const P o0 = op_value<T, NC, MODE>(y0, c0, i0, B, Y, w, cfin);
   const P o1 = op_value<T, NC, MODE>(y1, c1, i1, B, Y, w, cfin);
   if constexpr (HOUT) { sth2(Yv, i0, o0); sth2(Yv, i1, o1); } else { Y[i0] = o0; Y[i1] = o1; }
@@ -131,8 +136,8 @@ stencil_kernel(StencilDev<T> op, const void* __restrict__ Xv, const Pack<T, NC>*
 
 // ------------------------------------------------------------------------------------------
 // The hot kernel of the complex64 V-cycle: one factor Y = X - w A X of the level-0 smoother with
-// FP16-stored vectors.  The generic stencil_kernel is instruction-issue bound (ncu: 80 % issue-active,
-// 313 instructions per thread, DRAM and L2 below 20 % because the FP16 ping-pong vectors live in L2),
+// BF16-stored vectors.  The generic stencil_kernel is instruction-issue bound (ncu: 80 % issue-active,
+// 313 instructions per thread, DRAM and L2 below 20 % because the 16-bit ping-pong vectors live in L2),
 // so this version minimises instructions:
 //   * the two columns of a thread are held as (re0,re1) / (im0,im1) register pairs, so every
 //     complex operation is packed FP32 (FADD2 / FMUL2 / FFMA2, Blackwell) for both columns at once;
@@ -143,18 +148,13 @@ struct C2 { float2 re, im; };     // two complex64 columns
 
 __device__ __forceinline__ C2 ldh_c2(const uint2* __restrict__ base, uint32_t idx) {
   const uint2 raw = __ldg(base + idx);
-  const __half2 a = *reinterpret_cast<const __half2*>(&raw.x), b = *reinterpret_cast<const __half2*>(&raw.y);
   C2 r;
-  r.re = make_float2(__low2float(a), __low2float(b));
-  r.im = make_float2(__high2float(a), __high2float(b));
+  r.re = make_float2(bf_lo(raw.x), bf_lo(raw.y));
+  r.im = make_float2(bf_hi(raw.x), bf_hi(raw.y));
   return r;
 }
 __device__ __forceinline__ void sth_c2(uint2* __restrict__ base, uint32_t idx, const C2& v) {
-  const __half2 a = __floats2half2_rn(v.re.x, v.im.x), b = __floats2half2_rn(v.re.y, v.im.y);
-  uint2 raw;
-  raw.x = *reinterpret_cast<const uint32_t*>(&a);
-  raw.y = *reinterpret_cast<const uint32_t*>(&b);
-  base[idx] = raw;
+  base[idx] = make_uint2(bf_pack(v.re.x, v.im.x), bf_pack(v.re.y, v.im.y));
 }
 __device__ __forceinline__ float2 neg2(float2 a) { return make_float2(-a.x, -a.y); }
 // u * v with u = (ur,ur,ui,ui)
@@ -168,27 +168,31 @@ __device__ __forceinline__ C2 cmul_splat(const float4& u, const C2& v) {
 
 template <int MINB>
 __global__ void __launch_bounds__(512, MINB)
-stencil_step_h16_kernel(int LX, int LT, const float4* __restrict__ L4, float diag,
-                        const uint2* __restrict__ X, uint2* __restrict__ Y, float wr, float wi, uint32_t kp) {
+stencil_step_bf16_kernel(int LX, int LT, const float4* __restrict__ L4, float diag,
+                        const uint2* __restrict__ X, uint2* __restrict__ Y, float wr, float wi, uint32_t kp,
+                        long long rowb, long long ltb, long long spb) {   // bytes per row / per x-slice / per spin component
   const uint32_t cp = blockIdx.x * blockDim.x + threadIdx.x;
   const uint32_t t = blockIdx.y * blockDim.y + threadIdx.y;
   const uint32_t x = blockIdx.z * blockDim.z + threadIdx.z;
   if (cp >= kp || t >= (uint32_t)LT || x >= (uint32_t)LX) return;
   const uint32_t V = (uint32_t)LX * LT;
   const uint32_t site = x * LT + t;
-  const uint32_t s_tp = (t + 1 == (uint32_t)LT) ? site + 1 - LT : site + 1;
-  const uint32_t s_tm = (t == 0) ? site + LT - 1 : site - 1;
-  const uint32_t s_xp = (x + 1 == (uint32_t)LX) ? t : site + LT;
-  const uint32_t s_xm = (x == 0) ? site + V - LT : site - LT;
-  const uint32_t sp = V * kp;                        // offset of the second spin component
-
-  const uint32_t ic = site * kp + cp, itp = s_tp * kp + cp, itm = s_tm * kp + cp, ixp = s_xp * kp + cp, ixm = s_xm * kp + cp;
-  const C2 c0 = ldh_c2(X, ic),  c1 = ldh_c2(X, ic + sp);
-  const C2 f0 = ldh_c2(X, itp), f1 = ldh_c2(X, itp + sp);
-  const C2 b0 = ldh_c2(X, itm), b1 = ldh_c2(X, itm + sp);
-  const C2 r0 = ldh_c2(X, ixp), r1 = ldh_c2(X, ixp + sp);
-  const C2 l0 = ldh_c2(X, ixm), l1 = ldh_c2(X, ixm + sp);
-  const float4 ut = __ldg(L4 + site), utb = __ldg(L4 + V + site), ux = __ldg(L4 + 2 * V + site), uxb = __ldg(L4 + 3 * V + site);
+  // neighbour rows as byte offsets from the centre row (adds on the integer pipe; the FP32 pipe, which also
+  // executes IMAD, is the one that bounds this kernel)
+  const long long d_tp = (t + 1 == (uint32_t)LT) ? rowb - ltb : rowb;
+  const long long d_tm = (t == 0) ? ltb - rowb : -rowb;
+  const long long d_xp = (x + 1 == (uint32_t)LX) ? ltb - spb : ltb;
+  const long long d_xm = (x == 0) ? spb - ltb : -ltb;
+  const uint32_t ic = site * kp + cp;
+  const char* pc = reinterpret_cast<const char*>(X) + (size_t)ic * 8;
+  auto ld = [](const char* p) { return ldh_c2(reinterpret_cast<const uint2*>(p), 0u); };
+  const C2 c0 = ld(pc),        c1 = ld(pc + spb);
+  const C2 f0 = ld(pc + d_tp), f1 = ld(pc + d_tp + spb);
+  const C2 b0 = ld(pc + d_tm), b1 = ld(pc + d_tm + spb);
+  const C2 r0 = ld(pc + d_xp), r1 = ld(pc + d_xp + spb);
+  const C2 l0 = ld(pc + d_xm), l1 = ld(pc + d_xm + spb);
+  const float4* lp = L4 + site;
+  const float4 ut = __ldg(lp), utb = __ldg(lp + V), ux = __ldg(lp + 2 * V), uxb = __ldg(lp + 3 * V);
 
   C2 a, b, c, d;                                     // spin projections (see stencil_kernel)
   a.re = __fadd2_rn(f0.re, neg2(f1.re)); a.im = __fadd2_rn(f0.im, neg2(f1.im));      // f0 - f1
@@ -216,8 +220,9 @@ stencil_step_h16_kernel(int LX, int LT, const float4* __restrict__ L4, float dia
   o0.im = __ffma2_rn(neg2(w_i), y0.re, __ffma2_rn(neg2(w_r), y0.im, c0.im));
   o1.re = __ffma2_rn(w_i, y1.im, __ffma2_rn(neg2(w_r), y1.re, c1.re));
   o1.im = __ffma2_rn(neg2(w_i), y1.re, __ffma2_rn(neg2(w_r), y1.im, c1.im));
-  sth_c2(Y, ic, o0);
-  sth_c2(Y, ic + sp, o1);
+  char* py = reinterpret_cast<char*>(Y) + (size_t)ic * 8;
+  sth_c2(reinterpret_cast<uint2*>(py), 0u, o0);
+  sth_c2(reinterpret_cast<uint2*>(py + spb), 0u, o1);
 }
 
 // ------------------------------------------------------------------------------------------

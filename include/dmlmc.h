@@ -140,7 +140,8 @@ int dmlmc_level_sample_host(dmlmc_hier* h, int method, int level_f, int level_c,
  *   "dense_tensor_min_n"  dense inverses with n >= this (default 1024) are applied on the tensor cores
  *                  inside the complex64 V-cycle (BF16 operands, FP32 accumulation); smaller ones by the FP32 kernel
  *   "smoother_half" 1 (default): inside the complex64 V-cycle the level-0 smoother keeps the intermediate
- *                  vectors of the polynomial product in FP16 (FP32 arithmetic); 0: FP32 storage
+ *                  vectors of the polynomial product in BF16 (FP32 arithmetic); 0: FP32 storage
+ *   "stencil_fast"  1 (default): packed-FP32 (FFMA2) kernel for those BF16-stored factors; 0: generic kernel
  *   "dense_direct_exact"  1 (default): a V-cycle that STARTS on a dense level (that level's own solve) uses
  *                  the FP32 copy of the inverse when there is one; 0: tensor cores there as well
  *   "stencil_by", "stencil_bz"   site tile (t, x) of the level-0 kernel's thread block (default 4 x 4)

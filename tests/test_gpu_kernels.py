@@ -135,12 +135,12 @@ def test_smoother_is_the_polynomial(mg128, dtype):
             r = r - wi * (Al @ r)
         tol = 1e-11 if dtype == torch.complex128 else 2e-3
         if dtype == torch.complex64 and lvl == 0:
-            # level 0 keeps the intermediate vectors of the product in FP16 (FP32 arithmetic)
-            assert relerr(host(E), e) < 2e-2, lvl
-            mg.dev.set_option("stencil_fast", 0)            # generic kernel on the same FP16-stored data
+            # level 0 keeps the intermediate vectors of the product in BF16 (FP32 arithmetic)
+            assert relerr(host(E), e) < 1e-1, lvl
+            mg.dev.set_option("stencil_fast", 0)            # generic kernel on the same BF16-stored data
             Eg = mg.dev.smooth(lvl, R)
             mg.dev.set_option("stencil_fast", 1)
-            assert relerr(host(Eg), e) < 2e-2 and relerr(host(Eg), host(E)) < 1e-2, lvl
+            assert relerr(host(Eg), e) < 1e-1 and relerr(host(Eg), host(E)) < 5e-2, lvl
             mg.dev.set_option("smoother_half", 0)
             E = mg.dev.smooth(lvl, R)
             mg.dev.set_option("smoother_half", 1)
@@ -191,7 +191,7 @@ def test_vcycle_matches_numpy_restatement(mg128, l0):
     bf16 = (l0 < first and (mg.dense_levels[first] == "tensor" or mg.level_shapes[first] >= 1024)) or \
            (l0 == first and mg.dense_levels[first] == "tensor")
     Xf = mg.dev.vcycle(l0, B.to(torch.complex64))
-    assert relerr(host(Xf), _vcycle_numpy(mg, host(B), l0, first)) < (3e-2 if bf16 else 5e-3)
+    assert relerr(host(Xf), _vcycle_numpy(mg, host(B), l0, first)) < (1e-1 if (bf16 or l0 == 0) else 5e-3)
 
 
 def _bf16_round(a):
@@ -231,7 +231,7 @@ def test_vcycle_column_chunks(mg128, dtype, k):
     cols = [0, 1, 63, 64, k - 1]
     first = min(mg.dense_levels)
     ref = _vcycle_numpy(mg, host(B)[:, cols], 0, None if dtype == torch.complex128 else first)
-    assert relerr(host(X)[:, cols], ref) < (1e-8 if dtype == torch.complex128 else 3e-2)
+    assert relerr(host(X)[:, cols], ref) < (1e-8 if dtype == torch.complex128 else 1e-1)
     if k % 2 == 0:      # same kernel variants whatever the chunking: bitwise identical
         mg.dev.set_option("chunk_cols", 100000)
         X1 = mg.dev.vcycle(0, B)
