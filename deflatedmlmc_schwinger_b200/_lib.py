@@ -45,6 +45,10 @@ _SIGS = {
     "dmlmc_dotc": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_void_p]),
     "dmlmc_deflate": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p, ctypes.c_int]),
     "dmlmc_probe_expand": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_void_p]),
+    "dmlmc_mt19937_bits": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_longlong,
+                                          ctypes.c_longlong, ctypes.c_longlong, ctypes.c_void_p]),
+    "dmlmc_probe_expand_bytes": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_void_p]),
+    "dmlmc_rng_sync": (ctypes.c_int, [ctypes.c_void_p]),
     "dmlmc_apply_perm": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int]),
     "dmlmc_workspace_bytes": (ctypes.c_size_t, [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_int]),
     "dmlmc_set_workspace": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t]),
@@ -276,6 +280,24 @@ class Hierarchy:
         X0 = self.empty(n, k, C128)
         _check(self.lib.dmlmc_probe_expand(self.h, ctypes.c_void_p(bits_dev.data_ptr()), n, k, self._chk(X0)))
         return X0
+
+    def mt19937_bits(self, state, skip_before, count, skip_after, out=None, backup=None):
+        """state: int32 CUDA tensor [625] (key + position, bit pattern of uint32); out: uint8 CUDA tensor [count]"""
+        if out is None and count > 0:
+            out = self.torch.empty(int(count), dtype=self.torch.uint8, device=self.device)
+        _check(self.lib.dmlmc_mt19937_bits(self.h, ctypes.c_void_p(state.data_ptr()),
+                                           ctypes.c_void_p(backup.data_ptr()) if backup is not None else None,
+                                           int(skip_before), int(count), int(skip_after),
+                                           ctypes.c_void_p(out.data_ptr()) if out is not None else None))
+        return out
+
+    def probe_expand_bytes(self, lsb, n, k):
+        X0 = self.empty(n, k, C128)
+        _check(self.lib.dmlmc_probe_expand_bytes(self.h, ctypes.c_void_p(lsb.data_ptr()), n, k, self._chk(X0)))
+        return X0
+
+    def rng_sync(self):
+        _check(self.lib.dmlmc_rng_sync(self.h))
 
     def apply_perm(self, level, X):
         Y = self.torch.empty_like(X)

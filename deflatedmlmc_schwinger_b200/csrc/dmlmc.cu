@@ -85,6 +85,7 @@ struct dmlmc_hier {
   double l2_budget_mb = 0.0;              // MB the per-chunk working vectors may occupy (0 = no chunking)
   char* ws = nullptr; size_t ws_bytes = 0, ws_off = 0;
   int* h_nactive = nullptr;        // pinned
+  cudaStream_t rng_stream = nullptr; cudaEvent_t rng_done = nullptr;   // the probe stream runs beside the solver
   long long launches = 0;
   std::vector<void*> owned;
 };
@@ -775,6 +776,12 @@ int dmlmc_hier_create(int device, void* cuda_stream, int n_levels, dmlmc_hier** 
   h->device = device; h->stream = (cudaStream_t)cuda_stream; h->n_levels = n_levels;
   cudaError_t e2 = cudaMallocHost(&h->h_nactive, sizeof(int));
   if (e2 != cudaSuccess) { delete h; return fail((int)e2, "cudaMallocHost failed"); }
+  int lo = 0, hi = 0;
+  cudaDeviceGetStreamPriorityRange(&lo, &hi);
+  if (cudaStreamCreateWithPriority(&h->rng_stream, cudaStreamNonBlocking, hi) != cudaSuccess ||
+      cudaEventCreateWithFlags(&h->rng_done, cudaEventDisableTiming) != cudaSuccess) {
+    delete h; return fail(-3, "dmlmc: cannot create the probe-stream CUDA stream");
+  }
   *out = h;
   return 0;
 }
@@ -785,6 +792,8 @@ int dmlmc_hier_destroy(dmlmc_hier* h) {
   cudaStreamSynchronize(h->stream);
   for (void* p : h->owned) cudaFree(p);
   if (h->h_nactive) cudaFreeHost(h->h_nactive);
+  if (h->rng_stream) { cudaStreamSynchronize(h->rng_stream); cudaStreamDestroy(h->rng_stream); }
+  if (h->rng_done) cudaEventDestroy(h->rng_done);
   delete h;
   return 0;
 }
@@ -980,6 +989,31 @@ int dmlmc_probe_expand(dmlmc_hier* h, const uint8_t* bits_dev, int n, int k, voi
   const size_t nk = (size_t)n * k;
   probe_expand_kernel<<<nblocks(nk, 256), 256, 0, h->stream>>>(bits_dev, n, k, (Cx<double>*)X0);
   LAUNCH_CHECK(h);
+  return 0;
+}
+int dmlmc_mt19937_bits(dmlmc_hier* h, uint32_t* state_dev, uint32_t* backup_dev, long long skip_before, long long count,
+                       long long skip_after, uint8_t* lsb_dev) {
+  ENTER(h); CHECK(state_dev && skip_before >= 0 && count >= 0 && skip_after >= 0 && (count == 0 || lsb_dev), "mt19937_bits: bad arguments");
+  // ordered after everything already queued on the solver stream (the buffers may still be in use there),
+  // then asynchronous beside it on a high-priority stream: one CTA
+  CU(cudaEventRecord(h->rng_done, h->stream));
+  CU(cudaStreamWaitEvent(h->rng_stream, h->rng_done, 0));
+  mt19937_bits_kernel<<<1, 256, 0, h->rng_stream>>>(state_dev, backup_dev, skip_before, count, skip_after, lsb_dev);
+  LAUNCH_CHECK(h);
+  CU(cudaEventRecord(h->rng_done, h->rng_stream));
+  return 0;
+}
+int dmlmc_probe_expand_bytes(dmlmc_hier* h, const uint8_t* lsb_dev, int n, int k, void* X0) {
+  ENTER(h); CHECK(lsb_dev && X0 && n >= 1 && k >= 1, "probe_expand_bytes: bad arguments");
+  CU(cudaStreamWaitEvent(h->stream, h->rng_done, 0));          // the generator that filled lsb_dev
+  const size_t nk = (size_t)n * k;
+  probe_expand_bytes_kernel<<<nblocks(nk, 256), 256, 0, h->stream>>>(lsb_dev, n, k, (Cx<double>*)X0);
+  LAUNCH_CHECK(h);
+  return 0;
+}
+int dmlmc_rng_sync(dmlmc_hier* h) {
+  ENTER(h);
+  CU(cudaStreamSynchronize(h->rng_stream));
   return 0;
 }
 int dmlmc_apply_perm(dmlmc_hier* h, int level, const void* X, void* RHS, int k) {

@@ -535,6 +535,81 @@ probe_expand_kernel(const uint8_t* __restrict__ bits, int n, int k, Cx<double>* 
   X0[(size_t)i * k + p] = cx<double>(bit ? 1.0 : -1.0, 0.0);
 }
 
+// ------------------------------------------------------------------------------------------
+// The probe stream on the device.  The reference draws every probe element with
+// np.random.randint(2) from the global legacy generator (utils.py:213-216, 255-258): element j of the
+// stream is the least significant bit of the j-th tempered 32-bit output of MT19937.  This kernel
+// advances that same generator on the GPU: state[0..623] is the MT19937 key, state[624] the position
+// (exactly np.random.get_state()[1:3]), so that the host generator can be re-synchronised afterwards.
+// It skips `skip_before` outputs, writes the LSBs of the next `count` outputs to out[0..count)
+// (one byte each), skips `skip_after` more and stores the new state; `backup` (may be null) receives
+// the state before the call (the rewind point of the sequential stopping rule).
+// One CTA: the twist x[i+624] = x[i+397] ^ f(x[i], x[i+1]) is parallel over i in three runs of <= 227
+// words (double-buffered in shared memory, 3 barriers per 624 outputs).
+__device__ __forceinline__ uint32_t mt_mix(uint32_t a, uint32_t b) {
+  const uint32_t y = (a & 0x80000000u) | (b & 0x7fffffffu);
+  return (y >> 1) ^ ((y & 1u) ? 0x9908b0dfu : 0u);
+}
+__device__ __forceinline__ uint32_t mt_temper(uint32_t y) {
+  y ^= y >> 11;
+  y ^= (y << 7) & 0x9d2c5680u;
+  y ^= (y << 15) & 0xefc60000u;
+  y ^= y >> 18;
+  return y;
+}
+__global__ void __launch_bounds__(256)
+mt19937_bits_kernel(uint32_t* __restrict__ state, uint32_t* __restrict__ backup, long long skip_before, long long count,
+                    long long skip_after, uint8_t* __restrict__ out) {
+  __shared__ uint32_t s[2][624];
+  const int tid = threadIdx.x;
+  for (int i = tid; i < 624; i += 256) { const uint32_t v = state[i]; s[0][i] = v; if (backup) backup[i] = v; }
+  int mti = (int)state[624];
+  if (backup && tid == 0) backup[624] = (uint32_t)mti;
+  int cur = 0;
+  __syncthreads();
+  const long long total = skip_before + count + skip_after;
+  const long long out_end = skip_before + count;
+  long long done = 0;
+  while (done < total) {
+    if (mti >= 624) {
+      const uint32_t* o = s[cur];
+      uint32_t* nw = s[cur ^ 1];
+      if (tid < 227) nw[tid] = o[tid + 397] ^ mt_mix(o[tid], o[tid + 1]);
+      __syncthreads();
+      if (tid < 227) nw[227 + tid] = nw[tid] ^ mt_mix(o[227 + tid], o[228 + tid]);
+      __syncthreads();
+      if (tid < 169) nw[454 + tid] = nw[227 + tid] ^ mt_mix(o[454 + tid], o[455 + tid]);
+      if (tid == 255) nw[623] = nw[396] ^ mt_mix(o[623], nw[0]);
+      __syncthreads();
+      cur ^= 1;
+      mti = 0;
+    }
+    const long long left = total - done;
+    const int take = (int)((left < (long long)(624 - mti)) ? left : (long long)(624 - mti));
+    if (done + take > skip_before && done < out_end) {       // this run of outputs overlaps the wanted range
+      for (int i = mti + tid; i < mti + take; i += 256) {
+        const long long g = done + (i - mti);
+        if (g >= skip_before && g < out_end) out[g - skip_before] = (uint8_t)(mt_temper(s[cur][i]) & 1u);
+      }
+    }
+    done += take;
+    mti += take;
+  }
+  __syncthreads();
+  for (int i = tid; i < 624; i += 256) state[i] = s[cur][i];
+  if (tid == 0) state[624] = (uint32_t)mti;
+}
+
+// element i of probe p = 2*lsb[p*n+i] - 1 (one byte per element, as written by mt19937_bits_kernel)
+__global__ void __launch_bounds__(256)
+probe_expand_bytes_kernel(const uint8_t* __restrict__ lsb, int n, int k, Cx<double>* __restrict__ X0) {
+  const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const int i = (int)(gid / k);
+  const int p = (int)(gid - (long long)i * k);
+  if (i >= n) return;
+  X0[(size_t)i * k + p] = cx<double>(__ldg(lsb + (size_t)p * n + i) ? 1.0 : -1.0, 0.0);
+}
+
 // Out[r][c] = (Tout) In[r][c], r < n, c < w: copies / converts a block of w columns between two
 // row-major batches with leading dimensions ld_in / ld_out (complex elements).  This is how a column
 // chunk of the FGMRES basis (complex128, [n][k]) becomes the compact, L2-resident [n][w] working

@@ -111,20 +111,106 @@ def _round_bits(comm, n, k):
     return bits
 
 
-def run_sampling(sample_fn, n, k, tol, max_nr_ests, comm=None, fixed_count=None):
+class HostProbeSource:
+    """Probes drawn on the host from the global numpy stream (one MT19937 word per element)."""
+
+    def begin(self):
+        pass
+
+    def next_round(self, comm, n, k):
+        """this rank's k probes of the next round as k*n 0/1 values; the stream advances by the whole round"""
+        self._start_state = np.random.get_state()
+        return _round_bits(comm, n, k)
+
+    def rewind(self, used_in_round, n):
+        """leave the stream just after the `used_in_round`-th probe of the last round"""
+        np.random.set_state(self._start_state)
+        skip_probe_words(used_in_round * n)
+
+    def end(self):
+        pass
+
+
+class DeviceProbeSource:
+    """The same stream advanced ON THE GPU (dmlmc_mt19937_bits): bit-identical to np.random, no host RNG work and
+    no host->device copy of probes.  begin() uploads the numpy generator's state, end() writes the final state
+    back, so the global numpy RNG -- part of the reference's interface -- ends where the reference leaves it.
+    The generator of round r+1 runs on a side stream while round r is being solved."""
+
+    def __init__(self, dev):
+        self.dev = dev
+        self.torch = dev.torch
+        self.state = None
+        self.prefetched = None
+        self.last_backup = None
+
+    def begin(self):
+        st = np.random.get_state()
+        if st[0] != 'MT19937':
+            raise Exception("the probe stream is numpy's legacy MT19937 generator")
+        words = np.concatenate([np.asarray(st[1], dtype=np.uint32), np.array([st[2]], dtype=np.uint32)])
+        self._gauss = (st[3], st[4])
+        self.state = self.torch.from_numpy(words.view(np.int32).copy()).to(self.dev.device)
+        self.prefetched = None
+        self.last_backup = None
+
+    def _issue(self, comm, n, k):
+        G, g = comm.world, comm.rank
+        backup = self.torch.empty(625, dtype=self.torch.int32, device=self.dev.device)
+        lsb = self.dev.mt19937_bits(self.state, g * k * n, k * n, (G - 1 - g) * k * n, backup=backup)
+        self.prefetched = (lsb, backup, n, k)
+
+    def next_round(self, comm, n, k):
+        if self.prefetched is None or self.prefetched[2:] != (n, k):
+            if self.prefetched is not None:        # shape changed: discard the prefetch, go back to its start
+                self._restore(self.prefetched[1])
+            self._issue(comm, n, k)
+        lsb, backup, _, _ = self.prefetched
+        self.prefetched = None
+        X0 = self.dev.probe_expand_bytes(lsb, n, k)
+        self.last_backup = backup
+        self._keep = lsb                            # alive until the expand kernel has run
+        self._issue(comm, n, k)                     # next round, beside the solve of this one
+        return X0
+
+    def _restore(self, backup):
+        self.dev.rng_sync()
+        self.torch.cuda.current_stream(self.dev.device).synchronize()
+        self.state.copy_(backup)
+
+    def rewind(self, used_in_round, n):
+        self._restore(self.last_backup)
+        self.prefetched = None
+        if used_in_round > 0:
+            self.dev.mt19937_bits(self.state, used_in_round * n, 0, 0)
+
+    def end(self):
+        if self.prefetched is not None:
+            self._restore(self.prefetched[1])
+            self.prefetched = None
+        self.dev.rng_sync()
+        self.torch.cuda.current_stream(self.dev.device).synchronize()
+        words = self.state.cpu().numpy().view(np.uint32)
+        np.random.set_state(('MT19937', words[:624].copy(), int(words[624]), self._gauss[0], self._gauss[1]))
+
+
+def run_sampling(sample_fn, n, k, tol, max_nr_ests, comm=None, fixed_count=None, probe_source=None):
     """Sampling loop of one level with the reference's sequential stopping rule.
     Returns dict(ests, j_stop, avg, dev, iters_sum, rounds, evaluated).
-    fixed_count: take exactly that many samples (no stop rule; used for the rough estimate)."""
+    fixed_count: take exactly that many samples (no stop rule; used for the rough estimate).
+    probe_source: HostProbeSource (default; sample_fn gets k*n 0/1 values) or DeviceProbeSource (sample_fn gets
+    the probes as a complex128 CUDA tensor [n, k])."""
     comm = comm or Comm()
+    src = probe_source or HostProbeSource()
     G = comm.world
     ests = np.zeros(0, dtype=np.complex128)
     iters_all = np.zeros(0, dtype=np.int64)
     rounds = 0
+    src.begin()
     while True:
-        start_state = np.random.get_state()
         base = ests.shape[0]
-        bits = _round_bits(comm, n, k)
-        e_loc, it_loc = sample_fn(bits)
+        probes = src.next_round(comm, n, k)
+        e_loc, it_loc = sample_fn(probes)
         rounds += 1
         payload = np.concatenate([np.real(e_loc), np.imag(e_loc), np.asarray(it_loc, dtype=np.float64)])
         allp = comm.all_gather(payload).reshape(G, 3, k)
@@ -142,32 +228,32 @@ def run_sampling(sample_fn, n, k, tol, max_nr_ests, comm=None, fixed_count=None)
             j = max_nr_ests - 1
             break
     # rewind the stream to just after probe j (the reference never draws the overshoot)
-    used_in_round = (j + 1) - base
-    np.random.set_state(start_state)
-    skip_probe_words(used_in_round * n)
+    src.rewind((j + 1) - base, n)
+    src.end()
     avg, dev, _ = reference_stats(ests, j)
     return {"ests": ests[:j + 1], "j_stop": j, "avg": avg, "dev": dev,
             "iters_sum": int(iters_all[:j + 1].sum()), "rounds": rounds, "evaluated": int(ests.shape[0])}
 
 
-def run_sampling_fixed(sample_fn, n, k, tol, max_nr_ests, comm=None):
+def run_sampling_fixed(sample_fn, n, k, tol, max_nr_ests, comm=None, probe_source=None):
     """Throughput mode (sequential_stop=False): the sample count is fixed from a pilot round,
     N = max(6, ceil((sigma_pilot / tol)^2)) rounded up to whole rounds; after the pilot there is no
     communication until the single all_reduce of [sum Re e, sum Im e, sum |e|^2, N] at the end."""
     comm = comm or Comm()
+    src = probe_source or HostProbeSource()
     G = comm.world
-    bits = _round_bits(comm, n, k)
-    e_loc, it_loc = sample_fn(bits)
+    src.begin()
+    e_loc, it_loc = sample_fn(src.next_round(comm, n, k))
     mean, dev, N = reduce_level_sums(e_loc, comm)
     target = int(min(max_nr_ests, max(6, np.ceil((dev / tol) ** 2))))
     n_rounds = max(1, -(-target // (G * k)))
     es = [np.asarray(e_loc, dtype=np.complex128)]
     it_sum = int(np.sum(it_loc))
     for _ in range(n_rounds - 1):
-        bits = _round_bits(comm, n, k)
-        e_loc, it_loc = sample_fn(bits)
+        e_loc, it_loc = sample_fn(src.next_round(comm, n, k))
         es.append(np.asarray(e_loc, dtype=np.complex128))
         it_sum += int(np.sum(it_loc))
+    src.end()
     mean, dev, N = reduce_level_sums(np.concatenate(es), comm)
     it_sum = int(comm.all_reduce_sum(np.array([float(it_sum)]))[0]) if n_rounds > 0 else it_sum
     return {"ests": np.concatenate(es), "j_stop": N - 1, "avg": mean, "dev": dev, "iters_sum": it_sum,

@@ -48,12 +48,22 @@ def _make_solver(A, params):
 
 
 def _sampler(mg_solver, params, method, nr_deflat_vctrs, Vx, level, k):
-    def fn(bits01):
-        e, iters = defl_Hutch_batch(mg_solver, params, method, nr_deflat_vctrs, Vx, level, k, bits01=bits01)
+    def fn(probes):
+        if isinstance(probes, np.ndarray):      # k*n 0/1 values drawn on the host
+            e, iters = defl_Hutch_batch(mg_solver, params, method, nr_deflat_vctrs, Vx, level, k, bits01=probes)
+        else:                                   # the probes themselves, generated on the device
+            e, iters = defl_Hutch_batch(mg_solver, params, method, nr_deflat_vctrs, Vx, level, k, X0=probes)
         fn.coarse_iters += int(iters[1].sum())
         return e, iters[0]
     fn.coarse_iters = 0
     return fn
+
+
+def _probe_source(mg_solver, params):
+    """params['device_probe_stream'] (default True): advance the MT19937 probe stream on the GPU"""
+    if params.get('device_probe_stream', True):
+        return sampling.DeviceProbeSource(mg_solver.dev)
+    return sampling.HostProbeSource()
 
 
 def _rough_trace(A, mg_solver, params, nr_deflat_vctrs, Vx, tr1, comm, k):
@@ -61,7 +71,8 @@ def _rough_trace(A, mg_solver, params, nr_deflat_vctrs, Vx, tr1, comm, k):
     np.random.seed(123456)
     nr_rough_iters = 5
     fn = _sampler(mg_solver, params, "hutchinson", nr_deflat_vctrs, Vx, 0, min(k, 8))
-    res = sampling.run_sampling(fn, A.shape[0], min(k, 8), 0.0, nr_rough_iters, comm, fixed_count=nr_rough_iters)
+    res = sampling.run_sampling(fn, A.shape[0], min(k, 8), 0.0, nr_rough_iters, comm, fixed_count=nr_rough_iters,
+                                probe_source=_probe_source(mg_solver, params))
     return np.sum(res["ests"][0:nr_rough_iters]) / nr_rough_iters + tr1
 
 
@@ -97,9 +108,11 @@ def hutchinson(A, params):
     mg_solver.coarsest_lev_iters[0] = 0
     fn = _sampler(mg_solver, params, "hutchinson", nr_deflat_vctrs, Vx, 0, k)
     if params.get('sequential_stop', True):
-        res = sampling.run_sampling(fn, N, k, rough_trace_tol, params['max_nr_ests'], comm)
+        res = sampling.run_sampling(fn, N, k, rough_trace_tol, params['max_nr_ests'], comm,
+                                    probe_source=_probe_source(mg_solver, params))
     else:
-        res = sampling.run_sampling_fixed(fn, N, k, rough_trace_tol, params['max_nr_ests'], comm)
+        res = sampling.run_sampling_fixed(fn, N, k, rough_trace_tol, params['max_nr_ests'], comm,
+                                          probe_source=_probe_source(mg_solver, params))
     end = time.time()
     _say(params, " done. Time : " + str(end - start) + " seconds")
 
@@ -208,9 +221,11 @@ def mlmc(A, params):
         n_i = mg_solver.ml.levels[i].A.shape[0]
         fn = _sampler(mg_solver, params, "mlmc", nr_deflat_vctrs[i], Vxs[i], i, k)
         if params.get('sequential_stop', True):
-            res = sampling.run_sampling(fn, n_i, k, level_trace_tol, params['max_nr_ests'], comm)
+            res = sampling.run_sampling(fn, n_i, k, level_trace_tol, params['max_nr_ests'], comm,
+                                        probe_source=_probe_source(mg_solver, params))
         else:
-            res = sampling.run_sampling_fixed(fn, n_i, k, level_trace_tol, params['max_nr_ests'], comm)
+            res = sampling.run_sampling_fixed(fn, n_i, k, level_trace_tol, params['max_nr_ests'], comm,
+                                              probe_source=_probe_source(mg_solver, params))
         output_params['results'][i]['nr_ests'] += res["j_stop"]
         output_params['results'][i]['ests_avg'] = res["avg"] + tr1s[i]
         output_params['results'][i]['ests_dev'] = res["dev"]

@@ -58,7 +58,7 @@ def print_post_results(A, params, result, example):
 
 # ---- utils.py:73-125 ------------------------------------------------------------------------------
 _B200_KEYS = ('probe_batch', 'smoother_degree', 'fgmres_restart', 'inner_precision', 'test_vectors',
-              'deflation_eigpairs', 'mlmc_deflation_eigpairs', 'verbose', 'sequential_stop')
+              'deflation_eigpairs', 'mlmc_deflation_eigpairs', 'verbose', 'sequential_stop', 'device_probe_stream')
 
 
 def trace_params_from_params(params, example):
@@ -164,11 +164,12 @@ def _set_level_deflation(mg_solver, level, Vx, nr_deflat_vctrs):
         cache[("ref", level)] = Vx          # keep the array alive so id() stays unique
 
 
-def defl_Hutch_batch(mg_solver, params, method, nr_deflat_vctrs, Vx, i, k, bits01=None, host_path=True):
+def defl_Hutch_batch(mg_solver, params, method, nr_deflat_vctrs, Vx, i, k, bits01=None, host_path=True, X0=None):
     """k samples of one_defl_Hutch_step in one device call.  bits01: k*n_i 0/1 values (probe-major);
-    drawn from the global numpy stream if None.  Returns (e[k] complex128, iters[2][k])."""
+    drawn from the global numpy stream if None.  X0: the probes as a complex128 CUDA tensor [n_i, k]
+    (device-generated stream) instead of bits.  Returns (e[k] complex128, iters[2][k])."""
     n = mg_solver.level_shapes[i if method == "mlmc" else 0]
-    if bits01 is None:
+    if bits01 is None and X0 is None:
         bits01 = draw_probe_bits(k * n)
     lf = i if method == "mlmc" else 0
     if method == "mlmc":
@@ -180,6 +181,10 @@ def defl_Hutch_batch(mg_solver, params, method, nr_deflat_vctrs, Vx, i, k, bits0
     nlev = mg_solver.level_shapes[lf]
     maxiter = nlev if nlev < 1000 else 1000
     restart = min(mg_solver.restart, maxiter)
+    if X0 is not None:
+        e, iters = mg_solver.dev.level_sample(0 if method == "hutchinson" else 1, lf, lc, X0, tol, restart=restart,
+                                              maxiter=maxiter)
+        return e.cpu().numpy(), iters
     e, iters = mg_solver.dev.level_sample_host(0 if method == "hutchinson" else 1, lf, lc, pack_bits(bits01), k,
                                                tol, restart=restart, maxiter=maxiter)
     return e, iters

@@ -102,6 +102,18 @@ int dmlmc_deflate(dmlmc_hier* h, int level, void* X, int k);
  * 2*bit(p*n+i)-1 where bit(j) = (bits[j>>3] >> (j&7)) & 1 (numpy packbits, bitorder='little');
  * X0[n][k] complex128 */
 int dmlmc_probe_expand(dmlmc_hier* h, const uint8_t* bits_dev, int n, int k, void* X0);
+/* The reference's probe stream on the device: advance the legacy numpy generator (MT19937) whose state is
+ * state_dev[625] = np.random.get_state() key[624] + position.  Skips skip_before 32-bit outputs, writes the
+ * least significant bit of each of the next `count` outputs to lsb_dev[count] (one byte each -- element j of
+ * np.random.randint(2, size=...) is exactly that bit), skips skip_after more.  backup_dev[625] (or NULL)
+ * receives the state before the call.  Runs on an internal high-priority stream beside the solver;
+ * dmlmc_probe_expand_bytes / dmlmc_rng_sync order after it. */
+int dmlmc_mt19937_bits(dmlmc_hier* h, uint32_t* state_dev, uint32_t* backup_dev, long long skip_before,
+                       long long count, long long skip_after, uint8_t* lsb_dev);
+/* X0[i][p] = 2*lsb[p*n+i] - 1, complex128 [n][k] (utils.py:213-216) */
+int dmlmc_probe_expand_bytes(dmlmc_hier* h, const uint8_t* lsb_dev, int n, int k, void* X0);
+/* wait for the probe-stream generator (before reading its state back to the host) */
+int dmlmc_rng_sync(dmlmc_hier* h);
 /* RHS = Bblock_perm_level * roll(X, +shift_level)   utils.py:232,288-290 (identity if no perm set) */
 int dmlmc_apply_perm(dmlmc_hier* h, int level, const void* X, void* RHS, int k);
 

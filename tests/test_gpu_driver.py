@@ -81,3 +81,56 @@ def test_mlmc_128_level2_and_coarsest(mg128, g128):
     err = res["dev"] / np.sqrt(res["j_stop"] + 1)
     print("level-2: N =", res["j_stop"] + 1, "mean", res["avg"], "exact", exact_l2, "std", res["dev"])
     assert err < 0.5 and abs(res["avg"] - exact_l2) < 5 * err
+
+
+@pytest.mark.parametrize("consumed,skip,count,after", [(0, 0, 5000, 0), (7, 0, 1000, 0), (623, 5, 700, 11),
+                                                      (624, 1300, 4096, 977), (100, 0, 0, 2000)])
+def test_device_probe_stream_is_numpy_mt19937(mg16, consumed, skip, count, after):
+    """dmlmc_mt19937_bits: element j of the device stream == np.random.randint(2) element j, and the state
+    written back equals the host generator's state after the same number of draws."""
+    import torch
+    mg, tp, A = mg16
+    dev = mg.dev
+    np.random.seed(123456)
+    if consumed:
+        np.random.randint(2, size=consumed)
+    st = np.random.get_state()
+    words = np.concatenate([np.asarray(st[1], dtype=np.uint32), np.array([st[2]], dtype=np.uint32)])
+    state = torch.from_numpy(words.view(np.int32).copy()).cuda()
+    backup = torch.zeros(625, dtype=torch.int32, device="cuda")
+    out = dev.mt19937_bits(state, skip, count, after, backup=backup)
+    dev.rng_sync()
+    ref_all = np.random.randint(2, size=skip + count + after)
+    if count:
+        assert np.array_equal(out.cpu().numpy(), ref_all[skip:skip + count].astype(np.uint8))
+    st2 = np.random.get_state()
+    got = state.cpu().numpy().view(np.uint32)
+    # same stream position: compare what both generate next (the key arrays can differ by an un-applied twist)
+    state2 = torch.from_numpy(got.view(np.int32).copy()).cuda()
+    nxt = dev.mt19937_bits(state2, 0, 1500, 0)
+    dev.rng_sync()
+    assert np.array_equal(nxt.cpu().numpy(), np.random.randint(2, size=1500).astype(np.uint8))
+    assert np.array_equal(backup.cpu().numpy().view(np.uint32), words)
+    assert st2[0] == 'MT19937'
+
+
+def test_device_and_host_probe_streams_give_the_same_run(g16):
+    """the whole MLMC driver with the device-generated stream == with the host-generated stream, including the
+    final state of the global numpy generator (the rewind of the sequential stopping rule)"""
+    from conftest import params16
+    from deflatedmlmc_schwinger_b200 import matrix, stoch_trace, utils
+    out = []
+    for dev_stream in (True, False):
+        p = params16()
+        p["test_vectors"] = [g16["tv0"], g16["tv1"]]
+        p["probe_batch"] = 16
+        p["smoother_degree"] = 8
+        p["device_probe_stream"] = dev_stream
+        tp = utils.trace_params_from_params(p, "mlmc")
+        A = matrix.loadMatrix(p["matrix"], p["matrix_params"])
+        res = stoch_trace.mlmc(A, tp)
+        out.append((res, np.random.randint(1 << 30, size=8)))
+    (ra, na), (rb, nb) = out
+    assert [r["nr_ests"] for r in ra["results"]] == [r["nr_ests"] for r in rb["results"]]
+    assert abs(ra["trace"] - rb["trace"]) < 1e-9 * abs(rb["trace"])
+    assert np.array_equal(na, nb)
