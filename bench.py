@@ -166,7 +166,9 @@ class ClockSampler(threading.Thread):
                 self.reasons.add(nm)
 
     def run(self):
+        self.call_ms = []
         while not self._halt.is_set():
+            t = time.time()
             try:
                 if self.nvml is not None:
                     self._sample_nvml()
@@ -174,14 +176,16 @@ class ClockSampler(threading.Thread):
                     self._sample_smi()
             except Exception:
                 pass
-            self._halt.wait(0.05 if self.nvml is not None else 0.5)
+            self.call_ms.append(1e3 * (time.time() - t))
+            self._halt.wait(1.0)
 
     def stop(self):
         self._halt.set()
         self.join(timeout=6)
         med = float(np.median(self.samples)) if self.samples else None
         return {"sm_mhz": med, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons), "samples": len(self.samples),
-                "source": "nvml" if self.nvml is not None else "nvidia-smi"}
+                "source": "nvml" if self.nvml is not None else "nvidia-smi",
+                "query_ms_max": max(self.call_ms) if getattr(self, "call_ms", None) else None}
 
 
 def main():
@@ -258,13 +262,14 @@ def main():
         dist.all_reduce(torch.zeros(4, device="cuda", dtype=torch.float64))
     sampler = ClockSampler(local)
     barrier()
-    sampler.start()
     torch.cuda.profiler.start()      # `ncu --profile-from-start off` captures the timed region only
     l0 = dev.launch_count()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     ev0.record(stream)
     es, its = [], []
     for s in range(args.warmup, total_steps):
+        if s == args.warmup + 1 or total_steps - args.warmup == 1:
+            sampler.start()          # first NVML query (and then one per second) while the GPU is under load
         e, it = step_device(s)
         es.append(e); its.append(it)
     e_all = torch.cat(es)

@@ -14,12 +14,15 @@ os.environ.setdefault("OMP_NUM_THREADS", "1")
 import numpy as np
 
 EXACT_DISPLACED = -8.748242701374695 + 50.215154098005584j      # gateway.py:104
+EXACT_PLAIN = 8326.432059538896 + 0j                             # tr(A^-1), not permuted (SURVEY.md 8c pin 2)
 
 ap = argparse.ArgumentParser()
 ap.add_argument("--golden-tvs", action="store_true")
 ap.add_argument("--skip-hutchinson", action="store_true")
 ap.add_argument("--batch", type=int, default=256)
 ap.add_argument("--fixed", action="store_true", help="sequential_stop=False: sample count from a pilot round, one all_reduce per level")
+ap.add_argument("--deflated", action="store_true",
+                help="the valid deflated-MLMC variant of SURVEY.md 8d cfg-2: not permuted, mlmc_deflat_vctrs=[16,0,16]")
 args = ap.parse_args()
 
 import torch
@@ -42,6 +45,9 @@ def run(method):
     p["verbose"] = False
     p["probe_batch"] = args.batch
     p["sequential_stop"] = not args.fixed
+    if args.deflated:
+        p["use_permuted"] = False
+        p["mlmc_deflat_vctrs"] = [16, 0, 16]
     tp = utils.trace_params_from_params(p, method)
     if args.golden_tvs:
         g = np.load(os.path.join(ROOT, "tests", "golden", "schwinger128.npz"))
@@ -51,10 +57,12 @@ def run(method):
     res = (stoch_trace.mlmc if method == "mlmc" else stoch_trace.hutchinson)(A, tp)
     torch.cuda.synchronize()
     wall = time.time() - t0
-    out = {"experiment": "G202 (mlmc)" if method == "mlmc" else "G102 (hutchinson)", "n_gpus": world,
+    exact = EXACT_PLAIN if args.deflated else EXACT_DISPLACED
+    out = {"experiment": ("G202 (mlmc)" if method == "mlmc" else "G102 (hutchinson)") +
+                         (", not permuted, mlmc_deflat_vctrs=[16,0,16]" if args.deflated else ""), "n_gpus": world,
            "trace": [float(np.real(res["trace"])), float(np.imag(res["trace"]))],
-           "exact": [EXACT_DISPLACED.real, EXACT_DISPLACED.imag],
-           "abs_err": float(abs(res["trace"] - EXACT_DISPLACED)),
+           "exact": [exact.real, exact.imag],
+           "abs_err": float(abs(res["trace"] - exact)),
            "target_err": float(abs(1e-2 * res["rough_trace"])),
            "rough_trace": [float(np.real(res["rough_trace"])), float(np.imag(res["rough_trace"]))],
            "wall_s": wall, "sampling_s": float(res["sampling_seconds"]), "probes_evaluated": res["probes_evaluated"],
