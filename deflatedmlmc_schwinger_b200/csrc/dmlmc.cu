@@ -152,7 +152,29 @@ int launch_op_nc(dmlmc_hier* h, int level, const void* X, const void* B, void* Y
     return 0;
   }
   if constexpr (HIN || HOUT) {
-    return fail(-1, "dmlmc: BF16 vector storage is implemented for the level-0 stencil only");
+    // BF16-stored vectors on a coarse level: the packed-FP32 BSR kernel only
+    if constexpr (std::is_same<T, float>::value && NC == 2) {
+      if (L.kind == 1 && L.bs >= 2) {
+        const int PPT = (L.bs <= 4) ? 2 : 1;
+        const int need = (kp + PPT - 1) / PPT;
+        int tpr = 1;
+        if (need >= 32) tpr = std::min(128, ((need + 31) / 32) * 32); else while (tpr < need) tpr *= 2;
+        const size_t per_row = (size_t)L.bpr * L.bs * L.bs * sizeof(float4) + (size_t)L.bpr * sizeof(int);
+        int RB = std::max(1, 128 / tpr);
+        RB = (int)std::max<size_t>(1, std::min<size_t>(RB, 40960 / per_row));
+        const size_t smem = RB * per_row + 16;
+        if (smem <= 48 * 1024) {
+          dim3 blk(tpr, RB), grd((L.nb + RB - 1) / RB, (kp + tpr * PPT - 1) / (tpr * PPT));
+#define BSR2H(BS_, PPT_) bsr_f32x2_kernel<BS_, PPT_, MODE, HIN, HOUT><<<grd, blk, smem, h->stream>>>(L.nb, L.bpr, L.bsr_col, L.bsr_vals4, \
+              X, (const P*)B, Y, wt, ct, kp)
+          if (L.bs == 2) BSR2H(2, 2); else if (L.bs == 4) BSR2H(4, 2); else BSR2H(8, 1);
+#undef BSR2H
+          LAUNCH_CHECK(h);
+          return 0;
+        }
+      }
+    }
+    return fail(-1, "dmlmc: BF16 vector storage is not implemented for this operator format");
   } else {
   if (L.kind == 1) {
     if constexpr (std::is_same<T, float>::value && NC == 2) {
@@ -361,7 +383,9 @@ int smooth_apply(dmlmc_hier* h, int level, const void* R, void* E, bool acc, voi
     // complex64 cycle on the level-0 stencil: the intermediate vectors of the product are stored as BF16
     // (FP32 arithmetic), which halves the bytes every factor kernel moves and keeps them L2-resident.
     // (HS is a harmless power-of-two pre-scale kept from the FP16 variant of this path.)
-    if (h->smoother_half && L.kind == 0 && (k % 2) == 0 && m >= 2) {
+    const bool bsr_half = L.kind == 1 && L.bs >= 2 &&
+                          ((size_t)L.bpr * L.bs * L.bs * sizeof(float4) + (size_t)L.bpr * sizeof(int) + 16) <= 48 * 1024;
+    if (h->smoother_half && (L.kind == 0 || bsr_half) && (k % 2) == 0 && m >= 2) {
       const double HS = 64.0;
       const Cx<double> cfirst = {HS, 0.0}, clast = {L.p0.re / HS, L.p0.im / HS};
       for (int i = 0; i < m; ++i) {
@@ -373,7 +397,7 @@ int smooth_apply(dmlmc_hier* h, int level, const void* R, void* E, bool acc, voi
           else     RET((launch_op_nc<float, 2, M_STEP, true, false>(h, level, in, nullptr, E, L.nu[i], clast, k)));
         } else {
           void* out = pp[i & 1];
-          if (h->stencil_fast && L.d.diag.im == 0.0 && (size_t)L.n * (k / 2) < (1ull << 32)) {
+          if (L.kind == 0 && h->stencil_fast && L.d.diag.im == 0.0 && (size_t)L.n * (k / 2) < (1ull << 32)) {
             const int kp = k / 2;
             const long long rowb = (long long)kp * 8;
             int bx = 1; while (bx < 32 && bx < kp) bx *= 2;

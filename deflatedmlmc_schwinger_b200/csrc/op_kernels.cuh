@@ -279,11 +279,14 @@ __device__ __forceinline__ void fma2x(float4& acc, float2 m, const float4& x) {
   acc = make_float4(lo.x, lo.y, hi.x, hi.y);
 }
 
-template <int BS, int PPT, int MODE>
+// HIN / HOUT: X / Y are BF16-stored (the smoother's intermediate vectors, as on level 0).
+template <int BS, int PPT, int MODE, bool HIN = false, bool HOUT = false>
 __global__ void __launch_bounds__(128)
 bsr_f32x2_kernel(int nb, int bpr, const int* __restrict__ col, const float4* __restrict__ vals4,
-                 const Pack<float, 2>* __restrict__ X, const Pack<float, 2>* __restrict__ B,
-                 Pack<float, 2>* __restrict__ Y, Cx<float> w, Cx<float> cfin, int kp) {
+                 const void* __restrict__ Xv, const Pack<float, 2>* __restrict__ B,
+                 void* __restrict__ Yv, Cx<float> w, Cx<float> cfin, int kp) {
+  const Pack<float, 2>* __restrict__ X = reinterpret_cast<const Pack<float, 2>*>(Xv);
+  Pack<float, 2>* __restrict__ Y = reinterpret_cast<Pack<float, 2>*>(Yv);
   extern __shared__ float4 bsr_smem[];
   const int tpr = blockDim.x, RB = blockDim.y;
   const int tx = threadIdx.x, rb = threadIdx.y;
@@ -326,7 +329,15 @@ bsr_f32x2_kernel(int nb, int bpr, const int* __restrict__ col, const float4* __r
 #pragma unroll
     for (int c = 0; c < BS; ++c)
 #pragma unroll
-      for (int p = 0; p < PPT; ++p) xv[c][p] = __ldg(X4 + ((size_t)J * BS + c) * kpz + cp[p]);
+      for (int p = 0; p < PPT; ++p) {
+        const size_t xi = ((size_t)J * BS + c) * kpz + cp[p];
+        if constexpr (HIN) {
+          const Pack<float, 2> v = ldh2_ro(Xv, xi);
+          xv[c][p] = make_float4(v.d[0], v.d[1], v.d[2], v.d[3]);
+        } else {
+          xv[c][p] = __ldg(X4 + xi);
+        }
+      }
     const float4* vb = vrow + blk * (BS * BS);
 #pragma unroll
     for (int r = 0; r < BS; ++r) {
@@ -349,8 +360,9 @@ bsr_f32x2_kernel(int nb, int bpr, const int* __restrict__ col, const float4* __r
       ax.d[2] = a[r][p].z - b[r][p].w; ax.d[3] = a[r][p].w + b[r][p].z;
       const size_t idx = ((size_t)I * BS + r) * kpz + cp[p];
       Pack<float, 2> xin = pzero<float, 2>();
-      if constexpr (MODE >= M_STEP) xin = ldp_ro<float, 2>(X, idx);
-      op_epilogue<float, 2, MODE>(ax, xin, idx, B, Y, w, cfin);
+      if constexpr (MODE >= M_STEP) { if constexpr (HIN) xin = ldh2_ro(Xv, idx); else xin = ldp_ro<float, 2>(X, idx); }
+      const Pack<float, 2> o = op_value<float, 2, MODE>(ax, xin, idx, B, Y, w, cfin);
+      if constexpr (HOUT) sth2(Yv, idx, o); else Y[idx] = o;
     }
   }
 }
