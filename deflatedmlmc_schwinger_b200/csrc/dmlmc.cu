@@ -79,7 +79,8 @@ struct dmlmc_hier {
   int smoother_half = 1;                  // BF16 storage of the level-0 smoother's intermediate vectors (c64 cycle)
   int dense_direct_exact = 1;             // a dense level solved directly (not from a finer level) uses its FP32 copy
   int dense_tensor_min_n = 1024;          // dense inverses at least this large are applied on the tensor cores
-  bool umma_attr_set = false;
+  bool umma_attr_set = false, dmma_attr_set = false;
+  int defl_tensor = 1;                    // deflation projections on the FP64 tensor cores (d % 4 == 0, d <= 64)
   int stencil_minb = 3;                   // resident 512-thread blocks per SM the stencil kernel is compiled for
   int chunk_cols = 0;                     // V-cycle column chunk (0 = sized from l2_budget_mb)
   double l2_budget_mb = 0.0;              // MB the per-chunk working vectors may occupy (0 = no chunking)
@@ -674,11 +675,32 @@ int deflate(dmlmc_hier* h, int level, Z* X, int k) {
   RET(ws_get<Z>(h, partial_count(n, d, k), &partial));
   RET(ws_get<Z>(h, (size_t)d * k, &C));
   const int nchunks = (n + ROWS_PER_CHUNK - 1) / ROWS_PER_CHUNK;
-  dim3 blk(DOT_TX, DOT_TY), grd((k + DOT_TX - 1) / DOT_TX, nchunks);
-  defl_dot_kernel<<<grd, blk, 0, h->stream>>>(L.defl_V, d, X, n, k, ROWS_PER_CHUNK, partial); LAUNCH_CHECK(h);
-  sum_partials_kernel<<<nblocks((size_t)d * k, 256), 256, 0, h->stream>>>(partial, nchunks, d * k, C, 0); LAUNCH_CHECK(h);
   const size_t nk = (size_t)n * k;
-  defl_axpy_kernel<<<nblocks(nk, 256), 256, 0, h->stream>>>(L.defl_V, d, C, X, nk, k); LAUNCH_CHECK(h);
+  if (h->defl_tensor && d % 4 == 0 && d <= 64) {
+    // FP64 tensor cores (DMMA m8n8k4): both projections as real GEMMs on the interleaved arrays
+    const size_t sm1 = (size_t)DD_KB * (2 * d + 4 + 2 * DD_NT + 4) * sizeof(double);
+    const size_t sm2 = ((size_t)64 * (2 * d + 4) + (size_t)2 * d * (2 * DD_NT + 4)) * sizeof(double);
+    if (!h->dmma_attr_set) {
+      CU(cudaFuncSetAttribute(defl_dot_dmma_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
+      CU(cudaFuncSetAttribute(defl_dot_dmma_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
+      CU(cudaFuncSetAttribute(defl_dot_dmma_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
+      CU(cudaFuncSetAttribute(defl_axpy_dmma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
+      h->dmma_attr_set = true;
+    }
+    dim3 g1((k + DD_NT - 1) / DD_NT, nchunks);
+    if (d <= 16)      defl_dot_dmma_kernel<4><<<g1, 256, sm1, h->stream>>>(L.defl_V, d, X, n, k, ROWS_PER_CHUNK, partial);
+    else if (d <= 32) defl_dot_dmma_kernel<8><<<g1, 256, sm1, h->stream>>>(L.defl_V, d, X, n, k, ROWS_PER_CHUNK, partial);
+    else              defl_dot_dmma_kernel<16><<<g1, 256, sm1, h->stream>>>(L.defl_V, d, X, n, k, ROWS_PER_CHUNK, partial);
+    LAUNCH_CHECK(h);
+    sum_partials_kernel<<<nblocks((size_t)d * k, 256), 256, 0, h->stream>>>(partial, nchunks, d * k, C, 0); LAUNCH_CHECK(h);
+    dim3 g2((k + DD_NT - 1) / DD_NT, (n + 63) / 64);
+    defl_axpy_dmma_kernel<<<g2, 256, sm2, h->stream>>>(L.defl_V, d, C, X, n, k); LAUNCH_CHECK(h);
+  } else {
+    dim3 blk(DOT_TX, DOT_TY), grd((k + DOT_TX - 1) / DOT_TX, nchunks);
+    defl_dot_kernel<<<grd, blk, 0, h->stream>>>(L.defl_V, d, X, n, k, ROWS_PER_CHUNK, partial); LAUNCH_CHECK(h);
+    sum_partials_kernel<<<nblocks((size_t)d * k, 256), 256, 0, h->stream>>>(partial, nchunks, d * k, C, 0); LAUNCH_CHECK(h);
+    defl_axpy_kernel<<<nblocks(nk, 256), 256, 0, h->stream>>>(L.defl_V, d, C, X, nk, k); LAUNCH_CHECK(h);
+  }
   h->ws_off = mark;
   return 0;
 }
@@ -1104,6 +1126,7 @@ int dmlmc_set_option(dmlmc_hier* h, const char* name, double value) {
   if (std::strcmp(name, "chunk_cols") == 0) { h->chunk_cols = (int)value; return 0; }
   if (std::strcmp(name, "l2_budget_mb") == 0) { CHECK(value >= 0, "l2_budget_mb must be >= 0"); h->l2_budget_mb = value; return 0; }
   if (std::strcmp(name, "stencil_by") == 0) { CHECK(value >= 1, "stencil_by must be >= 1"); h->stencil_by = (int)value; return 0; }
+  if (std::strcmp(name, "defl_tensor") == 0) { h->defl_tensor = value != 0.0; return 0; }
   if (std::strcmp(name, "stencil_fast") == 0) { h->stencil_fast = value != 0.0; return 0; }
   if (std::strcmp(name, "smoother_half") == 0) { h->smoother_half = value != 0.0; return 0; }
   if (std::strcmp(name, "dense_direct_exact") == 0) { h->dense_direct_exact = value != 0.0; return 0; }

@@ -144,6 +144,123 @@ defl_axpy_kernel(const Z* __restrict__ Vd, int d, const Z* __restrict__ C, Z* __
 }
 
 // ------------------------------------------------------------------------------------------
+// The deflation projections on the FP64 tensor cores (mma.sync.m8n8k4.f64, "DMMA"): the only dense
+// contractions of the estimator itself (utils.py:224,266), complex128 because they enter the estimate.
+// A complex product is done as a real GEMM on the interleaved (re,im) arrays:
+//   G[2d][2k] = Vr^T Xr   gives  C = V^H X :  C_re[i][c] = G[2i][2c] + G[2i+1][2c+1],  C_im = G[2i][2c+1] - G[2i+1][2c]
+//   Xr[n][2k] -= Vr[n][2d] C'[2d][2k]  with  C'[2i][2c] = cr, C'[2i+1][2c] = -ci, C'[2i][2c+1] = ci, C'[2i+1][2c+1] = cr
+// Fragment layout of m8n8k4 (row.col): A[m][kk]: m = lane/4, kk = lane%4;  B[kk][n]: kk = lane%4, n = lane/4;
+// D[m][n]: m = lane/4, n = 2*(lane%4) + {0,1}.  Shared-memory rows are padded by 4 doubles (conflict-free
+// 64-bit fragment reads for row lengths that are multiples of 8).
+__device__ __forceinline__ void dmma_884(double& c0, double& c1, double a, double b) {
+  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+               : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
+}
+
+constexpr int DD_KB = 32;     // rows per shared-memory stage of the dot kernel
+constexpr int DD_NT = 32;     // complex columns per CTA (8 warps x 4)
+
+// partial[chunk][i][col] = sum_{r in chunk} conj(V[r][i]) X[r][col];  grid (ceil(k/32), nchunks), 256 threads
+template <int MTMAX>          // M tiles available: 2d/8 <= MTMAX
+__global__ void __launch_bounds__(256)
+defl_dot_dmma_kernel(const Z* __restrict__ Vd, int d, const Z* __restrict__ X, int n, int k, int rows_per_chunk,
+                     Z* __restrict__ partial) {
+  extern __shared__ double dd_smem[];
+  const int ldv = 2 * d + 4, ldx = 2 * DD_NT + 4;
+  double* Vs = dd_smem;                       // [DD_KB][ldv]
+  double* Xs = dd_smem + DD_KB * ldv;         // [DD_KB][ldx]
+  const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+  const int col0 = blockIdx.x * DD_NT;
+  const int r0 = blockIdx.y * rows_per_chunk, r1 = min(n, r0 + rows_per_chunk);
+  const int mtn = (2 * d) / 8;
+  double acc[MTMAX][2];
+#pragma unroll
+  for (int mt = 0; mt < MTMAX; ++mt) { acc[mt][0] = 0.0; acc[mt][1] = 0.0; }
+  for (int rb = r0; rb < r1; rb += DD_KB) {
+    for (int i = tid; i < DD_KB * d; i += 256) {
+      const int rr = i / d, ii = i - rr * d;
+      Z v = cx<double>(0.0, 0.0);
+      if (rb + rr < r1) v = ldc_ro<double>(Vd, (size_t)(rb + rr) * d + ii);
+      Vs[rr * ldv + 2 * ii] = v.re; Vs[rr * ldv + 2 * ii + 1] = v.im;
+    }
+    for (int i = tid; i < DD_KB * DD_NT; i += 256) {
+      const int rr = i / DD_NT, cc = i - rr * DD_NT;
+      Z v = cx<double>(0.0, 0.0);
+      if (rb + rr < r1 && col0 + cc < k) v = ldc_ro<double>(X, (size_t)(rb + rr) * k + col0 + cc);
+      Xs[rr * ldx + 2 * cc] = v.re; Xs[rr * ldx + 2 * cc + 1] = v.im;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int ks = 0; ks < DD_KB / 4; ++ks) {
+      const int kr = ks * 4 + (lane & 3);
+      const double b = Xs[kr * ldx + w * 8 + (lane >> 2)];
+#pragma unroll
+      for (int mt = 0; mt < MTMAX; ++mt)
+        if (mt < mtn) dmma_884(acc[mt][0], acc[mt][1], Vs[kr * ldv + mt * 8 + (lane >> 2)], b);
+    }
+    __syncthreads();
+  }
+  const int col = col0 + w * 4 + (lane & 3);
+#pragma unroll
+  for (int mt = 0; mt < MTMAX; ++mt) {
+    if (mt < mtn) {
+      const double p0 = __shfl_xor_sync(0xffffffffu, acc[mt][0], 4);
+      const double p1 = __shfl_xor_sync(0xffffffffu, acc[mt][1], 4);
+      const int row = mt * 8 + (lane >> 2);            // row of G: 2i (Re part of V) or 2i+1 (Im part)
+      if ((row & 1) == 0 && col < k)
+        partial[((size_t)blockIdx.y * d + (row >> 1)) * k + col] = cx<double>(acc[mt][0] + p1, acc[mt][1] - p0);
+    }
+  }
+}
+
+// X[r][col] -= sum_i V[r][i] C[i][col];  grid (ceil(k/32), ceil(n/64)), 256 threads (warp = 8 rows)
+__global__ void __launch_bounds__(256)
+defl_axpy_dmma_kernel(const Z* __restrict__ Vd, int d, const Z* __restrict__ C, Z* __restrict__ X, int n, int k) {
+  extern __shared__ double dd_smem[];
+  const int ldv = 2 * d + 4, ldc = 2 * DD_NT + 4;
+  double* Vs = dd_smem;                       // [64][ldv]
+  double* Cs = dd_smem + 64 * ldv;            // [2d][ldc]   the real 2x2-block expansion of C
+  const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+  const int col0 = blockIdx.x * DD_NT, rbase = blockIdx.y * 64;
+  for (int i = tid; i < 64 * d; i += 256) {
+    const int rr = i / d, ii = i - rr * d;
+    Z v = cx<double>(0.0, 0.0);
+    if (rbase + rr < n) v = ldc_ro<double>(Vd, (size_t)(rbase + rr) * d + ii);
+    Vs[rr * ldv + 2 * ii] = v.re; Vs[rr * ldv + 2 * ii + 1] = v.im;
+  }
+  for (int i = tid; i < d * DD_NT; i += 256) {
+    const int ii = i / DD_NT, cc = i - ii * DD_NT;
+    Z c = cx<double>(0.0, 0.0);
+    if (col0 + cc < k) c = ldc_ro<double>(C, (size_t)ii * k + col0 + cc);
+    Cs[(2 * ii) * ldc + 2 * cc] = c.re;      Cs[(2 * ii + 1) * ldc + 2 * cc] = -c.im;
+    Cs[(2 * ii) * ldc + 2 * cc + 1] = c.im;  Cs[(2 * ii + 1) * ldc + 2 * cc + 1] = c.re;
+  }
+  __syncthreads();
+  double acc[8][2];
+#pragma unroll
+  for (int nt = 0; nt < 8; ++nt) { acc[nt][0] = 0.0; acc[nt][1] = 0.0; }
+  const int ksn = (2 * d) / 4;
+  for (int ks = 0; ks < ksn; ++ks) {
+    const double a = Vs[(w * 8 + (lane >> 2)) * ldv + ks * 4 + (lane & 3)];
+    const double* crow = Cs + (ks * 4 + (lane & 3)) * ldc + (lane >> 2);
+#pragma unroll
+    for (int nt = 0; nt < 8; ++nt) dmma_884(acc[nt][0], acc[nt][1], a, crow[nt * 8]);
+  }
+  const int row = rbase + w * 8 + (lane >> 2);
+  if (row < n) {
+#pragma unroll
+    for (int nt = 0; nt < 8; ++nt) {
+      const int col = col0 + nt * 4 + (lane & 3);
+      if (col < k) {
+        Z x = X[(size_t)row * k + col];
+        x.re -= acc[nt][0]; x.im -= acc[nt][1];
+        X[(size_t)row * k + col] = x;
+      }
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------
 // per-column FGMRES state (all arrays column-contiguous)
 struct GmresState {
   int k, m;            // columns, restart length

@@ -154,6 +154,8 @@ int dmlmc_level_sample_host(dmlmc_hier* h, int method, int level_f, int level_c,
  *   "smoother_half" 1 (default): inside the complex64 V-cycle the level-0 smoother keeps the intermediate
  *                  vectors of the polynomial product in BF16 (FP32 arithmetic); 0: FP32 storage
  *   "stencil_fast"  1 (default): packed-FP32 (FFMA2) kernel for those BF16-stored factors; 0: generic kernel
+ *   "defl_tensor"  1 (default): the deflation projections V^H x and x - V(.) run on the FP64 tensor cores
+ *                  (mma.sync m8n8k4.f64) when d is a multiple of 4 and <= 64; 0: SIMT kernels
  *   "dense_direct_exact"  1 (default): a V-cycle that STARTS on a dense level (that level's own solve) uses
  *                  the FP32 copy of the inverse when there is one; 0: tensor cores there as well
  *   "stencil_by", "stencil_bz"   site tile (t, x) of the level-0 kernel's thread block (default 4 x 4)

@@ -58,5 +58,18 @@ for name, dt, s in (("c64", torch.complex64, 8), ("c128", torch.complex128, 16))
 X = rnd(32768, torch.complex128); Y = rnd(32768, torch.complex128)
 us = timeit(lambda: dev.dotc(X, Y))
 out.append({"kernel": "dotc", "us": us, "GBps": 2 * 32768 * k * 16 / us / 1e3})
+# deflation projections x - V (V^H x): FP64 tensor cores (DMMA) vs SIMT, bytes 2 n s (d + k) + n s k, flops 16 n d k
+for d in (8, 16, 64):
+    rs = np.random.RandomState(d)
+    V, _ = np.linalg.qr(rs.standard_normal((32768, d)) + 1j * rs.standard_normal((32768, d)))
+    dev.set_deflation(0, V)
+    Xd = rnd(32768, torch.complex128)
+    for tens in (1, 0):
+        dev.set_option("defl_tensor", tens)
+        us = timeit(lambda: dev.deflate(0, Xd), reps=10)
+        out.append({"kernel": "deflate (dot + axpy)", "d": d, "tensor_cores": bool(tens), "us": us,
+                    "GBps": (2 * 32768 * 16 * (d + k) + 32768 * 16 * k) / us / 1e3, "TFLOPs": 16 * 32768 * d * k / us / 1e6})
+    dev.set_option("defl_tensor", 1)
+    dev.set_deflation(0, None)
 for o in out:
     print(json.dumps(o))

@@ -119,6 +119,27 @@ def test_dotc_and_deflate(mg16, g16):
     mg.__dict__.pop("_defl_cache", None)
 
 
+@pytest.mark.parametrize("d", [4, 8, 16, 36, 64, 6])
+@pytest.mark.parametrize("k", [1, 30, 256])
+def test_deflation_projection_tensor_cores(mg128, d, k):
+    """x - V (V^H x), complex128: FP64 tensor-core kernels (d % 4 == 0) and the SIMT kernels (d = 6, or
+    option defl_tensor = 0) against numpy, ragged column counts included"""
+    mg, tp, A = mg128
+    n = mg.level_shapes[0]
+    rs = np.random.RandomState(d)
+    V, _ = np.linalg.qr(rs.standard_normal((n, d)) + 1j * rs.standard_normal((n, d)))
+    X = rnd(n, k, torch.complex128, 90 + k)
+    ref = host(X) - V @ (V.conj().T @ host(X))
+    mg.dev.set_deflation(0, V)
+    Xt = X.clone(); mg.dev.deflate(0, Xt)
+    mg.dev.set_option("defl_tensor", 0)
+    Xs = X.clone(); mg.dev.deflate(0, Xs)
+    mg.dev.set_option("defl_tensor", 1)
+    mg.dev.set_deflation(0, None)
+    mg.__dict__.pop("_defl_cache", None)
+    assert relerr(host(Xt), ref) < 1e-13 and relerr(host(Xs), ref) < 1e-13
+
+
 @pytest.mark.parametrize("dtype", [torch.complex128, torch.complex64])
 def test_smoother_is_the_polynomial(mg128, dtype):
     from deflatedmlmc_schwinger_b200.multigrid import harmonic_ritz_inv_roots
