@@ -256,33 +256,44 @@ def main():
         torch.cuda.synchronize()
 
     # ---- device-resident timing ------------------------------------------------------------------
-    for s in range(args.warmup):
-        step_device(s)
-    if world > 1:   # the level's collective once outside the timed region (NCCL sets up its channels on first use)
-        dist.all_reduce(torch.zeros(4, device="cuda", dtype=torch.float64))
+    def level_sums(e_list):
+        """the single collective of the level: all_reduce of [sum Re e, sum Im e, sum |e|^2, N]"""
+        e_all = torch.cat(e_list)
+        sums = torch.stack([e_all.real.sum(), e_all.imag.sum(), (e_all.abs() ** 2).sum(),
+                            torch.tensor(float(e_all.numel()), device=e_all.device, dtype=torch.float64)])
+        if world > 1:
+            dist.all_reduce(sums)
+        return sums
+
+    warm = [step_device(s)[0] for s in range(args.warmup)]
+    if warm:             # also outside the timed region once: torch loads its kernels lazily (first call of each op
+        level_sums(warm)  # costs ~10-50 ms) and NCCL sets up its channels on first use
+    del warm
     sampler = ClockSampler(local)
     barrier()
     torch.cuda.profiler.start()      # `ncu --profile-from-start off` captures the timed region only
     l0 = dev.launch_count()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     ev0.record(stream)
+    dbg = [] if os.environ.get("BENCH_DEBUG") else None
     es, its = [], []
     for s in range(args.warmup, total_steps):
         if s == args.warmup + 1 or total_steps - args.warmup == 1:
             sampler.start()          # first NVML query (and then one per second) while the GPU is under load
         e, it = step_device(s)
         es.append(e); its.append(it)
-    e_all = torch.cat(es)
-    if world > 1:   # the single collective of the level: [sum Re e, sum Im e, sum |e|^2, N]
-        sums = torch.stack([e_all.real.sum(), e_all.imag.sum(), (e_all.abs() ** 2).sum(),
-                            torch.tensor(float(e_all.numel()), device=e_all.device, dtype=torch.float64)])
-        dist.all_reduce(sums)
+        if dbg is not None:
+            evs = torch.cuda.Event(enable_timing=True); evs.record(stream); dbg.append(evs)
+    sums = level_sums(es)
     ev1.record(stream)
     barrier()
     torch.cuda.profiler.stop()
     launches = dev.launch_count() - l0
     clocks = sampler.stop()
     ms = ev0.elapsed_time(ev1)
+    if dbg:
+        print("[rank %d] timed region: steps end at %s ms, total %.1f ms" %
+              (rank, ["%.1f" % ev0.elapsed_time(x) for x in dbg], ms), file=sys.stderr, flush=True)
     if world > 1:
         t = torch.tensor([ms], device="cuda", dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
