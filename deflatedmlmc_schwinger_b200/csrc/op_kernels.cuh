@@ -166,8 +166,8 @@ __device__ __forceinline__ C2 cmul_splat(const float4& u, const C2& v) {
   return p;
 }
 
-template <int MINB>
-__global__ void __launch_bounds__(512, MINB)
+template <int MINB>     // 2 / 3: 512-thread blocks (64 / 40 registers); 5: 256-thread blocks, 48 registers
+__global__ void __launch_bounds__(MINB == 5 ? 256 : 512, MINB)
 stencil_step_bf16_kernel(int LX, int LT, const float4* __restrict__ L4, float diag,
                         const uint2* __restrict__ X, uint2* __restrict__ Y, float wr, float wi, uint32_t kp,
                         long long rowb, long long ltb, long long spb) {   // bytes per row / per x-slice / per spin component
@@ -177,6 +177,10 @@ stencil_step_bf16_kernel(int LX, int LT, const float4* __restrict__ L4, float di
   if (cp >= kp || t >= (uint32_t)LT || x >= (uint32_t)LX) return;
   const uint32_t V = (uint32_t)LX * LT;
   const uint32_t site = x * LT + t;
+  // links first: ncu's source view showed the first use of each link (the FMUL2 of cmul_splat) as a top
+  // long-scoreboard stall when these loads were issued after the ten vector loads
+  const float4* lp = L4 + site;
+  const float4 ut = __ldg(lp), utb = __ldg(lp + V), ux = __ldg(lp + 2 * V), uxb = __ldg(lp + 3 * V);
   // neighbour rows as byte offsets from the centre row (adds on the integer pipe; the FP32 pipe, which also
   // executes IMAD, is the one that bounds this kernel)
   const long long d_tp = (t + 1 == (uint32_t)LT) ? rowb - ltb : rowb;
@@ -191,9 +195,6 @@ stencil_step_bf16_kernel(int LX, int LT, const float4* __restrict__ L4, float di
   const C2 b0 = ld(pc + d_tm), b1 = ld(pc + d_tm + spb);
   const C2 r0 = ld(pc + d_xp), r1 = ld(pc + d_xp + spb);
   const C2 l0 = ld(pc + d_xm), l1 = ld(pc + d_xm + spb);
-  const float4* lp = L4 + site;
-  const float4 ut = __ldg(lp), utb = __ldg(lp + V), ux = __ldg(lp + 2 * V), uxb = __ldg(lp + 3 * V);
-
   C2 a, b, c, d;                                     // spin projections (see stencil_kernel)
   a.re = __fadd2_rn(f0.re, neg2(f1.re)); a.im = __fadd2_rn(f0.im, neg2(f1.im));      // f0 - f1
   b.re = __fadd2_rn(b0.re, b1.re);       b.im = __fadd2_rn(b0.im, b1.im);            // b0 + b1
