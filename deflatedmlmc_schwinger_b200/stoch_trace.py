@@ -268,3 +268,33 @@ def mlmc(A, params):
     output_params['sampling_seconds'] = sampling_seconds
     output_params['probes_evaluated'] = probes_evaluated
     return output_params
+
+
+# exact-trace validator (not in the reference, which only quotes the number, gateway.py:100-104)
+def exact_trace(A, params):
+    """EXACT tr(A^{-1} C) level by level: the hierarchy of mlmc(A, params), but every level's estimator is summed
+    over all unit vectors instead of sampled (n_l batched device solves per level).  Returns the same dictionary
+    layout as mlmc() with 'ests_avg' = the exact level values and 'ests_dev' = 0."""
+    from .utils import exact_level_trace
+    skip_level = len(params['mlmc_levels_to_skip']) == 1
+    mg_solver = _make_solver(A, params)
+    nr_levels = len(mg_solver.ml.levels)
+    mg_solver.skip_level = skip_level
+    k = int(params.get('probe_batch', 256))
+    out = {'nr_levels': nr_levels, 'trace': 0.0, 'std_dev': 0.0, 'total_complexity': 0.0, 'results': []}
+    for i in range(nr_levels):
+        out['results'].append({'function_iters': 0, 'nr_ests': 0, 'ests_avg': 0.0, 'ests_dev': 0.0, 'level_complexity': 0.0})
+    for i in range(nr_levels - 1):
+        if skip_level and i == 1:
+            continue
+        n_i = mg_solver.ml.levels[i].A.shape[0]
+        out['results'][i]['ests_avg'] = exact_level_trace(mg_solver, params, "mlmc", i, k=k)
+        out['results'][i]['nr_ests'] = n_i
+    crst_mat = mg_solver.coarsest_inv
+    if params["use_permuted"]:
+        crst_mat = mg_solver.ml.levels[nr_levels - 1].Pperm.transpose().conjugate() * \
+                   (crst_mat * mg_solver.ml.levels[nr_levels - 1].Bblock_perm)
+    out['results'][nr_levels - 1]['ests_avg'] = np.trace(crst_mat)
+    out['results'][nr_levels - 1]['nr_ests'] = 1
+    out['trace'] = sum(r['ests_avg'] for r in out['results'])
+    return out

@@ -190,6 +190,36 @@ def defl_Hutch_batch(mg_solver, params, method, nr_deflat_vctrs, Vx, i, k, bits0
     return e, iters
 
 
+def exact_level_trace(mg_solver, params, method, i, k=256, nr_deflat_vctrs=0, Vx=None):
+    """The EXACT value of what one_defl_Hutch_step estimates on level i: unit vectors instead of Rademacher
+    probes through the same fused device call, e_j^H Op e_j summed over all j (the exact-trace validator of
+    SURVEY.md 8f-4; gateway.py:100-104 quotes such a number for the shipped 128^2 set).
+      method "hutchinson": tr(A_0^{-1} C (I - V V^H))
+      method "mlmc"      : tr((A_i^{-1} - P A_c^{-1} R) C_i (I - V V^H)),  c = i+1 (or i+2 when level 1 is skipped)
+    n_i solves in batches of k; returns a complex."""
+    import torch
+    dev = mg_solver.dev
+    lf = i if method == "mlmc" else 0
+    n = mg_solver.level_shapes[lf]
+    if method == "mlmc":
+        lc = lf + 2 if (mg_solver.skip_level and lf == 0) else lf + 1
+    else:
+        lc = lf
+    _set_level_deflation(mg_solver, lf, Vx, nr_deflat_vctrs)
+    tol = params['function_params']['tol']
+    maxiter = n if n < 1000 else 1000
+    restart = min(mg_solver.restart, maxiter)
+    total = 0.0 + 0.0j
+    for c0 in range(0, n, k):
+        w = min(k, n - c0)
+        X0 = torch.zeros((n, w), dtype=torch.complex128, device=dev.device)
+        X0[c0:c0 + w, :] = torch.eye(w, dtype=torch.complex128, device=dev.device)
+        e, _ = dev.level_sample(0 if method == "hutchinson" else 1, lf, lc, X0, tol, restart=restart, maxiter=maxiter)
+        total += complex(e.sum().item())
+        del X0
+    return total
+
+
 # ---- utils.py:207-361 ---------------------------------------------------------------------------------
 def one_defl_Hutch_step(Af, Ac, mg_solver, params, method, nr_deflat_vctrs, Vx, Ux, i=0,
                         output_params=None, P=None, R=None, Pn=None, Rn=None):

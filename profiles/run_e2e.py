@@ -21,6 +21,7 @@ ap.add_argument("--golden-tvs", action="store_true")
 ap.add_argument("--skip-hutchinson", action="store_true")
 ap.add_argument("--batch", type=int, default=256)
 ap.add_argument("--fixed", action="store_true", help="sequential_stop=False: sample count from a pilot round, one all_reduce per level")
+ap.add_argument("--exact", action="store_true", help="also compute the EXACT level values with unit vectors (stoch_trace.exact_trace)")
 ap.add_argument("--deflated", action="store_true",
                 help="the valid deflated-MLMC variant of SURVEY.md 8d cfg-2: not permuted, mlmc_deflat_vctrs=[16,0,16]")
 args = ap.parse_args()
@@ -79,6 +80,22 @@ def run(method):
 
 
 run("mlmc")
+if args.exact and rank == 0:
+    p = gateway.set_params("schwinger128"); p["function_tol"] = 1e-12; p["verbose"] = False
+    if args.deflated:
+        p["use_permuted"] = False
+    tp = utils.trace_params_from_params(p, "mlmc")
+    if args.golden_tvs:
+        g = np.load(os.path.join(ROOT, "tests", "golden", "schwinger128.npz"))
+        tp["test_vectors"] = [g["tv0"], g["tv1"], g["tv2"]]
+    A = matrix.loadMatrix(p["matrix"], p["matrix_params"])
+    t0 = time.time()
+    ex = stoch_trace.exact_trace(A, tp)
+    exact = EXACT_PLAIN if args.deflated else EXACT_DISPLACED
+    print(json.dumps({"experiment": "exact level traces (unit vectors through the batched solver)",
+                      "levels": [[float(np.real(r["ests_avg"])), float(np.imag(r["ests_avg"]))] for r in ex["results"]],
+                      "trace": [float(np.real(ex["trace"])), float(np.imag(ex["trace"]))], "reference_exact": [exact.real, exact.imag],
+                      "abs_diff": float(abs(ex["trace"] - exact)), "wall_s": time.time() - t0}), flush=True)
 if not args.skip_hutchinson:
     run("hutchinson")
 if world > 1:

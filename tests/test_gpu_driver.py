@@ -134,3 +134,23 @@ def test_device_and_host_probe_streams_give_the_same_run(g16):
     assert [r["nr_ests"] for r in ra["results"]] == [r["nr_ests"] for r in rb["results"]]
     assert abs(ra["trace"] - rb["trace"]) < 1e-9 * abs(rb["trace"])
     assert np.array_equal(na, nb)
+
+
+def test_exact_trace_of_the_shipped_128_set(mg128, g128):
+    """Unit vectors through the fused device sample = the exact value of every MLMC level; their telescoping
+    sum must be the exact displaced trace the reference quotes (gateway.py:100-104).  32768 + 2048 solves."""
+    from deflatedmlmc_schwinger_b200 import utils
+    mg, tp, A = mg128
+    assert mg.skip_level
+    l0 = utils.exact_level_trace(mg, tp, "mlmc", 0, k=256)
+    l2 = utils.exact_level_trace(mg, tp, "mlmc", 2, k=256)
+    lv = mg.ml.levels
+    crst = np.trace(lv[3].Pperm.transpose().conjugate() * (mg.coarsest_inv * lv[3].Bblock_perm))
+    total = l0 + l2 + crst
+    exact = -8.748242701374695 + 50.215154098005584j
+    print("exact level traces:", l0, l2, crst, "sum", total)
+    assert abs(total - exact) < 1e-8 * abs(exact)
+    # level 2 against dense algebra
+    A2inv = np.linalg.inv(lv[2].A.toarray())
+    C2 = (lv[2].Bblock_perm @ lv[2].Pperm.transpose()).toarray()
+    assert abs(l2 - (np.trace(A2inv @ C2) - crst)) < 1e-8 * abs(l2)
