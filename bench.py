@@ -195,7 +195,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--probes", type=int, default=256, help="probes per step per GPU")
     ap.add_argument("--impl", default="b200")
-    ap.add_argument("--degree", type=int, default=64)
+    ap.add_argument("--degree", type=int, default=80)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":
@@ -396,8 +396,8 @@ def main():
             "vs_baseline": None, "dtype": "c128 (FGMRES, transfers, dots) + c64 (V-cycle)",
             "data": "schwinger128 gauge field (reference input) + MT19937(123456) Rademacher probes",
             "config": {"workload": WORKLOAD, "probes_per_step_per_gpu": k, "solver_tol": tol,
-                       "smoother": "fixed GMRES polynomial in product form, degree %d per level; dense inverse at level %d"
-                                   % (args.degree, mg.dense_level),
+                       "smoother": "V-cycle = dense tcgen05 coarse solve at level %d + fixed GMRES polynomial of degree %d in "
+                                   "product form as post-smoother" % (mg.dense_level, args.degree),
                        "fgmres_restart": restart, "l2_flush": "inputs larger than L2 (Krylov basis %.1f GB per step)"
                        % (2 * 26 * n0 * k * 16 / 1e9), "parallelism": "probes sharded x%d" % world},
             "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,

@@ -33,6 +33,7 @@ _SIGS = {
     "dmlmc_set_dense_inverse_device": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_void_p]),
     "dmlmc_set_smoother": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_void_p,
                                           ctypes.c_double, ctypes.c_double]),
+    "dmlmc_set_smoother_storage": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.c_int]),
     "dmlmc_set_perm": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_void_p,
                                       ctypes.c_void_p]),
     "dmlmc_set_deflation": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_void_p]),
@@ -174,11 +175,12 @@ class Hierarchy:
         _check(self.lib.dmlmc_set_dense_inverse_device(self.h, level, minv_dev.shape[0], ctypes.c_void_p(minv_dev.data_ptr())))
         self.torch.cuda.current_stream(self.device).synchronize()
 
-    def set_smoother(self, level, nu, p0):
-        """p(A) = p0 * prod_i (I - nu[i] A)"""
+    def set_smoother(self, level, nu, p0, storage16=True):
+        """p(A) = p0 * prod_i (I - nu[i] A); storage16: the complex64 cycle may keep the intermediates in BF16"""
         nu, p = _host_c128(np.asarray(nu).reshape(-1))
         _check(self.lib.dmlmc_set_smoother(self.h, level, nu.shape[0], p if nu.shape[0] else None,
                                            float(np.real(p0)), float(np.imag(p0))))
+        _check(self.lib.dmlmc_set_smoother_storage(self.h, level, 1 if storage16 else 0))
 
     def set_perm(self, level, shift, cols=None, vals=None):
         if cols is None:

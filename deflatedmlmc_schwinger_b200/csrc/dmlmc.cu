@@ -50,7 +50,7 @@ struct Level {
   float4* links4 = nullptr;          // [4][V] (ur,ur,ui,ui): U_t(x), U_t(x-t)^*, U_x(x), U_x(x-x)^*
   bool has_transfer = false; int aggr = 0, dofi = 0, nvec = 0, n_c = 0;
   // smoother polynomial in product form: p(A) = p0 * prod_i (I - nu_i A)
-  bool has_smoother = false; std::vector<Cx<double>> nu; Cx<double> p0;
+  bool has_smoother = false; std::vector<Cx<double>> nu; Cx<double> p0; bool smoother16 = true;
   bool has_perm = false; int shift = 0, perm_nnz = 0; int* perm_cols = nullptr;
   int defl_d = 0; Cx<double>* defl_V = nullptr;
   bool has_dense = false; Cx<double>* minv_d = nullptr; Cx<float>* minv_f = nullptr; float4* minv4 = nullptr;
@@ -76,6 +76,7 @@ struct dmlmc_hier {
   int reorth = 0;
   int stencil_by = 4, stencil_bz = 4;     // site tile (t, x) of the stencil kernel's thread block
   int stencil_fast = 1;                   // packed-FP32 (FFMA2) kernel for the BF16-stored smoother factors
+  int pre_smooth = 0;                     // 0: V-cycle = coarse correction + post-smoothing (default), 1: pre- and post-smoothing
   int smoother_half = 1;                  // BF16 storage of the level-0 smoother's intermediate vectors (c64 cycle)
   int dense_direct_exact = 1;             // a dense level solved directly (not from a finer level) uses its FP32 copy
   int dense_tensor_min_n = 1024;          // dense inverses at least this large are applied on the tensor cores
@@ -386,7 +387,7 @@ int smooth_apply(dmlmc_hier* h, int level, const void* R, void* E, bool acc, voi
     // (HS is a harmless power-of-two pre-scale kept from the FP16 variant of this path.)
     const bool bsr_half = L.kind == 1 && L.bs >= 2 &&
                           ((size_t)L.bpr * L.bs * L.bs * sizeof(float4) + (size_t)L.bpr * sizeof(int) + 16) <= 48 * 1024;
-    if (h->smoother_half && (L.kind == 0 || bsr_half) && (k % 2) == 0 && m >= 2) {
+    if (h->smoother_half && L.smoother16 && (L.kind == 0 || bsr_half) && (k % 2) == 0 && m >= 2) {
       const double HS = 64.0;
       const Cx<double> cfirst = {HS, 0.0}, clast = {L.p0.re / HS, L.p0.im / HS};
       for (int i = 0; i < m; ++i) {
@@ -481,9 +482,15 @@ int vcycle_level(dmlmc_hier* h, int l, int level0, int lb, std::vector<VcBuf<T>>
       const size_t coff = (size_t)C0 * nc + (col0 - C0);
       if (phase == 0) {
         if (l == level0) RET((cvt_cols<TIO, T>(h, Bio + col0, (size_t)k, bc, (size_t)w, n, w)));
-        RET(smooth_apply<T>(h, l, bc, xc, false, me.t0, me.t1, w));
-        RET((launch_op<T, M_RES>(h, l, xc, bc, me.t0, ZERO, ZERO, w)));
-        RET(launch_restrict<T>(h, l, me.t0, co.b + coff, w, w, wC));
+        if (h->pre_smooth) {
+          RET(smooth_apply<T>(h, l, bc, xc, false, me.t0, me.t1, w));
+          RET((launch_op<T, M_RES>(h, l, xc, bc, me.t0, ZERO, ZERO, w)));
+          RET(launch_restrict<T>(h, l, me.t0, co.b + coff, w, w, wC));
+        } else {
+          // post-smoothing only: x = 0, the coarse level sees R b directly
+          RET(launch_restrict<T>(h, l, bc, co.b + coff, w, w, wC));
+          CU(cudaMemsetAsync(xc, 0, (size_t)n * w * sizeof(Cx<T>), h->stream));
+        }
       } else {
         RET(launch_prolong<T>(h, l, co.x + coff, xc, w, w, wC));
         RET((launch_op<T, M_RES>(h, l, xc, bc, me.t0, ZERO, ZERO, w)));
@@ -957,6 +964,12 @@ int dmlmc_set_smoother(dmlmc_hier* h, int level, int nfactors, const double* nu_
   return 0;
 }
 
+int dmlmc_set_smoother_storage(dmlmc_hier* h, int level, int allow16) {
+  CHECK(h && level >= 0 && level < h->n_levels, "set_smoother_storage: bad handle/level");
+  h->lv[level].smoother16 = allow16 != 0;
+  return 0;
+}
+
 int dmlmc_set_perm(dmlmc_hier* h, int level, int shift, int nnz_per_row, const int32_t* cols_host, const double* vals_host) {
   CHECK(h && level >= 0 && level < h->n_levels, "set_perm: bad handle/level");
   Level& L = h->lv[level];
@@ -1128,6 +1141,7 @@ int dmlmc_set_option(dmlmc_hier* h, const char* name, double value) {
   if (std::strcmp(name, "stencil_by") == 0) { CHECK(value >= 1, "stencil_by must be >= 1"); h->stencil_by = (int)value; return 0; }
   if (std::strcmp(name, "defl_tensor") == 0) { h->defl_tensor = value != 0.0; return 0; }
   if (std::strcmp(name, "stencil_fast") == 0) { h->stencil_fast = value != 0.0; return 0; }
+  if (std::strcmp(name, "pre_smooth") == 0) { h->pre_smooth = value != 0.0; return 0; }
   if (std::strcmp(name, "smoother_half") == 0) { h->smoother_half = value != 0.0; return 0; }
   if (std::strcmp(name, "dense_direct_exact") == 0) { h->dense_direct_exact = value != 0.0; return 0; }
   if (std::strcmp(name, "dense_tensor_min_n") == 0) { h->dense_tensor_min_n = (int)value; return 0; }

@@ -182,6 +182,42 @@ def smoother_product_form(omega):
     return nu, p0
 
 
+def _bf16_round(z):
+    """complex64 array with real and imaginary parts rounded to BF16 (round to nearest even), as the device stores
+    the smoother's intermediate vectors"""
+    z = np.ascontiguousarray(z, dtype=np.complex64)
+    u = z.view(np.uint32).astype(np.uint64)
+    u = (u + 0x7FFF + ((u >> 16) & 1)) & 0xFFFF0000
+    return u.astype(np.uint32).view(np.complex64)
+
+
+def smoother_storage_error(A, omega, nu, p0, storage):
+    """Relative error of the product-form smoother  p0 prod (I - nu_i A) b  evaluated like the device does
+    (complex64 arithmetic, intermediate vectors stored as `storage` = 'bf16' or 'f32') against the Richardson form
+    in complex128, for one random vector.  High degrees on small levels can be unstable in 16-bit storage; the setup
+    uses this to pick the storage (or lower the degree) per level."""
+    n = A.shape[0]
+    rs = np.random.RandomState(11)
+    b = rs.standard_normal(n) + 1j * rs.standard_normal(n)
+    b /= np.linalg.norm(b)
+    r = b.copy()
+    e = np.zeros_like(b)
+    for i, wi in enumerate(omega):
+        e = e + wi * r
+        if i < len(omega) - 1:
+            r = r - wi * (A @ r)
+    A32 = A.astype(np.complex64)
+    y = (64.0 * b).astype(np.complex64)
+    for i, v in enumerate(nu):
+        y = (y - np.complex64(v) * (A32 @ y)).astype(np.complex64)
+        if storage == 'bf16' and i < len(nu) - 1:
+            y = _bf16_round(y)
+        if not np.all(np.isfinite(y)):
+            return np.inf
+    y = (p0 / 64.0) * y.astype(np.complex128)
+    return float(np.linalg.norm(y - e) / np.linalg.norm(e))
+
+
 def bsr_padded(A, bs):
     """scipy matrix -> (colidx[nb][bpr] with -1 padding, vals[nb][bpr][bs][bs])."""
     B = csr_matrix(A).tobsr(blocksize=(bs, bs))
@@ -219,8 +255,8 @@ def ell_padded(M):
 class MG:
     """Same public surface as the reference's MG (multigrid.py:56-557)."""
 
-    def __init__(self, A, smooth_iters=2, smoother_degree=64, restart=40, inner_precision="c64",
-                 device=None, dense_coarse_threshold=8192):
+    def __init__(self, A, smooth_iters=2, smoother_degree=80, restart=40, inner_precision="c64",
+                 device=None, dense_coarse_threshold=8192, pre_smooth=False):
         self.level_nr = 0
         self.ml = []
         self.A = A
@@ -244,6 +280,7 @@ class MG:
         self.inner_precision = inner_precision
         self.device = device
         self.dense_coarse_threshold = dense_coarse_threshold
+        self.pre_smooth = bool(pre_smooth)   # False: V-cycle = coarse correction + polynomial post-smoother
         self.dense_level = None              # level at which the V-cycle bottoms out with a dense inverse
         self.dev = None                      # _lib.Hierarchy
         self.test_vectors = []
@@ -354,11 +391,24 @@ class MG:
         dev.set_coarsest_inverse(self.coarsest_inv)
         self.smoother_polys = []
         self.smoother_degrees_used = []
+        self.smoother_storage = []
         for i in range(nl - 1):
             d = self.level_degree(i)
-            while True:      # the product form is checked against the Richardson form; lower the degree if it is off
+            Ai = csr_matrix(lv[i].A)
+            while True:
+                # the product form is checked against the Richardson form (exact arithmetic) and its evaluation in the
+                # device's precisions against complex128 (a high degree on a small level can be unstable with BF16-
+                # stored intermediates): fall back to FP32 storage, then to a lower degree
                 try:
-                    nu, p0 = smoother_product_form(harmonic_ritz_inv_roots(csr_matrix(lv[i].A), d))
+                    omega = harmonic_ritz_inv_roots(Ai, d)
+                    nu, p0 = smoother_product_form(omega)
+                    storage = None
+                    for st in ('bf16', 'f32'):
+                        if smoother_storage_error(Ai, omega, nu, p0, st) < 0.15:
+                            storage = st
+                            break
+                    if storage is None:
+                        raise Exception("smoother polynomial unstable in complex64")
                     break
                 except Exception:
                     if d <= 4:
@@ -366,7 +416,8 @@ class MG:
                     d = max(4, (3 * d) // 4)
             self.smoother_polys.append((nu, p0))
             self.smoother_degrees_used.append(d)
-            dev.set_smoother(i, nu, p0)
+            self.smoother_storage.append(storage)
+            dev.set_smoother(i, nu, p0, storage16=(storage == 'bf16'))
         if use_permuted:
             for i in range(nl):
                 if i == 0:
@@ -375,6 +426,7 @@ class MG:
                     cols, vals = ell_padded(lv[i].Bblock_perm)
                     dev.set_perm(i, lv[i].perm_shift, cols, vals)
         dev.set_inner_precision(_lib.C64 if self.inner_precision == "c64" else _lib.C128)
+        dev.set_option("pre_smooth", 1 if self.pre_smooth else 0)
         self.dev = dev
         # V-cycle bottom: every intermediate level small enough gets a dense inverse, computed with the
         # batched device solver itself (A_l X = I), coarser levels first so that finer ones already use them.

@@ -22,8 +22,8 @@ def _say(params, *a, **kw):
 
 
 def _make_solver(A, params):
-    mg_solver = MG(A, smoother_degree=params.get('smoother_degree', 64), restart=params.get('fgmres_restart', 40),
-                   inner_precision=params.get('inner_precision', 'c64'))
+    mg_solver = MG(A, smoother_degree=params.get('smoother_degree', 80), restart=params.get('fgmres_restart', 40),
+                   inner_precision=params.get('inner_precision', 'c64'), pre_smooth=params.get('pre_smooth', False))
     mg_solver.coarsest_iters = 0
     mg_solver.coarsest_iters_tot = 0
     mg_solver.coarsest_iters_avg = 0

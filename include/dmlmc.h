@@ -74,6 +74,9 @@ int dmlmc_set_dense_inverse_device(dmlmc_hier* h, int level, int n, const void* 
  * multigrid.py:393-394 / 438-439 (FGMRES is flexible: parity is on the converged solve). */
 int dmlmc_set_smoother(dmlmc_hier* h, int level, int nfactors, const double* nu_host,
                        double p0_re, double p0_im);
+/* allow16 = 0: this level's smoother keeps its intermediate vectors in FP32 even when option "smoother_half"
+ * is on (the setup sets it when the polynomial is not stable enough for BF16 storage on that level) */
+int dmlmc_set_smoother_storage(dmlmc_hier* h, int level, int allow16);
 /* permutation data of a level (multigrid.py:142-155, 320-331): x_perm = roll(x, +shift),
  * then Bblock_perm (nnz_per_row == 0: identity) in padded row form cols/vals[n][nnz_per_row] */
 int dmlmc_set_perm(dmlmc_hier* h, int level, int shift, int nnz_per_row,
@@ -151,6 +154,9 @@ int dmlmc_level_sample_host(dmlmc_hier* h, int method, int level_f, int level_c,
  *                  over the smoother's kernels); 0 (default) = one chunk
  *   "dense_tensor_min_n"  dense inverses with n >= this (default 1024) are applied on the tensor cores
  *                  inside the complex64 V-cycle (BF16 operands, FP32 accumulation); smaller ones by the FP32 kernel
+ *   "pre_smooth"   0 (default): the V-cycle is coarse-grid correction followed by the polynomial post-smoother;
+ *                  1: polynomial pre- and post-smoothing as in multigrid.py:369-447 (measured: 13 outer iterations
+ *                  at degree 64+64 against 14 at degree 0+96, which is 30 % less smoothing work)
  *   "smoother_half" 1 (default): inside the complex64 V-cycle the level-0 smoother keeps the intermediate
  *                  vectors of the polynomial product in BF16 (FP32 arithmetic); 0: FP32 storage
  *   "stencil_fast"  1 (default): packed-FP32 (FFMA2) kernel for those BF16-stored factors; 0: generic kernel

@@ -189,8 +189,9 @@ def _vcycle_numpy(mg, b, l0, dense_from=None):
     Al = csr_matrix(lv[l0].A)
     w = harmonic_ritz_inv_roots(Al, mg.level_degree(l0))
     r = b.copy(); x = np.zeros_like(b)
-    for wi in w:
-        x = x + wi * r; r = r - wi * (Al @ r)
+    if mg.pre_smooth:
+        for wi in w:
+            x = x + wi * r; r = r - wi * (Al @ r)
     x = x + lv[l0].P @ _vcycle_numpy(mg, lv[l0].R @ r, l0 + 1, dense_from)
     r = b - Al @ x
     for wi in w:
@@ -198,9 +199,20 @@ def _vcycle_numpy(mg, b, l0, dense_from=None):
     return x
 
 
+@pytest.mark.parametrize("pre", [False, True])
 @pytest.mark.parametrize("l0", [0, 1, 2, 3])
-def test_vcycle_matches_numpy_restatement(mg128, l0):
+def test_vcycle_matches_numpy_restatement(mg128, l0, pre):
     mg, tp, A = mg128
+    mg.pre_smooth = pre
+    mg.dev.set_option("pre_smooth", 1 if pre else 0)
+    try:
+        _check_vcycle(mg, l0)
+    finally:
+        mg.pre_smooth = False
+        mg.dev.set_option("pre_smooth", 0)
+
+
+def _check_vcycle(mg, l0):
     n = mg.level_shapes[l0]
     B = rnd(n, 3, torch.complex128, 60 + l0)
     X = mg.dev.vcycle(l0, B)
