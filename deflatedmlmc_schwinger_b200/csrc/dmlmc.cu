@@ -76,6 +76,7 @@ struct dmlmc_hier {
   int reorth = 0;
   int stencil_by = 4, stencil_bz = 4;     // site tile (t, x) of the stencil kernel's thread block
   int stencil_fast = 1;                   // packed-FP32 (FFMA2) kernel for the BF16-stored smoother factors
+  int prefetch_slices = 16;               // Y = A X / B - A X on level 0: L2 prefetch distance in x-slices (0, 8, 16)
   int pre_smooth = 0;                     // 0: V-cycle = coarse correction + post-smoothing (default), 1: pre- and post-smoothing
   int smoother_half = 1;                  // BF16 storage of the level-0 smoother's intermediate vectors (c64 cycle)
   int dense_direct_exact = 1;             // a dense level solved directly (not from a finer level) uses its FP32 copy
@@ -148,6 +149,10 @@ int launch_op_nc(dmlmc_hier* h, int level, const void* X, const void* B, void* Y
     while (bx * by * bz > 512) { if (bz > 1) bz /= 2; else by /= 2; }
     while (bx * by * bz < 256 && by < L.LT) by *= 2;
     dim3 blk(bx, by, bz), grd((kp + bx - 1) / bx, (L.LT + by - 1) / by, (L.LX + bz - 1) / bz);
+    if constexpr (!HIN && !HOUT && (MODE == M_AX || MODE == M_RES)) {
+      if (h->prefetch_slices == 8) { stencil_kernel<T, NC, MODE, 3, false, false, 8><<<grd, blk, 0, h->stream>>>(op, X, (const P*)B, Y, wt, ct, kp); LAUNCH_CHECK(h); return 0; }
+      if (h->prefetch_slices == 16) { stencil_kernel<T, NC, MODE, 3, false, false, 16><<<grd, blk, 0, h->stream>>>(op, X, (const P*)B, Y, wt, ct, kp); LAUNCH_CHECK(h); return 0; }
+    }
     if (h->stencil_minb == 3) stencil_kernel<T, NC, MODE, 3, HIN, HOUT><<<grd, blk, 0, h->stream>>>(op, X, (const P*)B, Y, wt, ct, kp);
     else                      stencil_kernel<T, NC, MODE, 2, HIN, HOUT><<<grd, blk, 0, h->stream>>>(op, X, (const P*)B, Y, wt, ct, kp);
     LAUNCH_CHECK(h);
@@ -1141,6 +1146,7 @@ int dmlmc_set_option(dmlmc_hier* h, const char* name, double value) {
   if (std::strcmp(name, "stencil_by") == 0) { CHECK(value >= 1, "stencil_by must be >= 1"); h->stencil_by = (int)value; return 0; }
   if (std::strcmp(name, "defl_tensor") == 0) { h->defl_tensor = value != 0.0; return 0; }
   if (std::strcmp(name, "stencil_fast") == 0) { h->stencil_fast = value != 0.0; return 0; }
+  if (std::strcmp(name, "prefetch_slices") == 0) { h->prefetch_slices = (int)value; return 0; }
   if (std::strcmp(name, "pre_smooth") == 0) { h->pre_smooth = value != 0.0; return 0; }
   if (std::strcmp(name, "smoother_half") == 0) { h->smoother_half = value != 0.0; return 0; }
   if (std::strcmp(name, "dense_direct_exact") == 0) { h->dense_direct_exact = value != 0.0; return 0; }

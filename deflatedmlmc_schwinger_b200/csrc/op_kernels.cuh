@@ -84,7 +84,7 @@ __device__ __forceinline__ void sth2(void* base, size_t idx, const Pack<float, 2
 // MINB = 2: 64 registers, all 14 loads of a thread in flight at once; MINB = 3: 40 registers, loads in
 // batches of 6 but 50 % more resident threads.
 // HIN / HOUT: X / Y are BF16-stored (complex64 arithmetic, NC = 2 only).
-template <typename T, int NC, int MODE, int MINB, bool HIN = false, bool HOUT = false>
+template <typename T, int NC, int MODE, int MINB, bool HIN = false, bool HOUT = false, int PFD = 0>
 __global__ void __launch_bounds__(512, MINB)
 stencil_kernel(StencilDev<T> op, const void* __restrict__ Xv, const Pack<T, NC>* __restrict__ B,
                void* __restrict__ Yv, Cx<T> w, Cx<T> cfin, int kp) {
@@ -109,6 +109,16 @@ stencil_kernel(StencilDev<T> op, const void* __restrict__ Xv, const Pack<T, NC>*
 
   typedef Pack<T, NC> P;
   const size_t i0 = (size_t)site * kpz + cp, i1 = (Vz + site) * kpz + cp;
+  if constexpr (PFD > 0) {
+    // software prefetch into L2 of the rows that the blocks PFD x-slices ahead will read (streaming kernels:
+    // the loads of a thread then find their lines in L2 instead of waiting for HBM)
+    const int xq = x + PFD;
+    if (xq < LX) {
+      const size_t q0 = ((size_t)xq * LT + t) * kpz + cp;
+      asm volatile("prefetch.global.L2 [%0];" ::"l"(X + q0));
+      asm volatile("prefetch.global.L2 [%0];" ::"l"(X + q0 + Vz * kpz));
+    }
+  }
   const P c0 = ldx(i0),  c1 = ldx(i1);
   const P f0 = ldx((size_t)s_tp * kpz + cp),  f1 = ldx((Vz + s_tp) * kpz + cp);
   const P b0 = ldx((size_t)s_tm * kpz + cp),  b1 = ldx((Vz + s_tm) * kpz + cp);

@@ -154,6 +154,8 @@ int dmlmc_level_sample_host(dmlmc_hier* h, int method, int level_f, int level_c,
  *                  over the smoother's kernels); 0 (default) = one chunk
  *   "dense_tensor_min_n"  dense inverses with n >= this (default 1024) are applied on the tensor cores
  *                  inside the complex64 V-cycle (BF16 operands, FP32 accumulation); smaller ones by the FP32 kernel
+ *   "prefetch_slices"  0 | 8 | 16 (default): the level-0 Y = A X / B - A X kernels prefetch into L2 the rows that the
+ *                  thread blocks this many x-slices ahead will read (+3 % on the complex128 SpMM)
  *   "pre_smooth"   0 (default): the V-cycle is coarse-grid correction followed by the polynomial post-smoother;
  *                  1: polynomial pre- and post-smoothing as in multigrid.py:369-447 (measured: 13 outer iterations
  *                  at degree 64+64 against 14 at degree 0+96, which is 30 % less smoothing work)
