@@ -558,7 +558,7 @@ int multi_dot(dmlmc_hier* h, const Z* Vbase, size_t vstride, int nv, const Z* W,
   dim3 blk(DOT_TX, DOT_TY), grd((k + DOT_TX - 1) / DOT_TX, nchunks);
   multi_dot_kernel<<<grd, blk, 0, h->stream>>>(Vbase, vstride, nv, W, n, k, ROWS_PER_CHUNK, partial);
   LAUNCH_CHECK(h);
-  sum_partials_kernel<<<nblocks((size_t)nv * k, 256), 256, 0, h->stream>>>(partial, nchunks, nv * k, out, accumulate);
+  sum_partials_kernel<<<nblocks((size_t)nv * k, 32), dim3(32, 8), 0, h->stream>>>(partial, nchunks, nv * k, out, accumulate);
   LAUNCH_CHECK(h);
   return 0;
 }
@@ -567,6 +567,17 @@ size_t partial_count(int n, int nv, int k) { return (size_t)((n + ROWS_PER_CHUNK
 int multi_axpy(dmlmc_hier* h, const Z* Vbase, size_t vstride, int nv, const Z* hc, Z* W, int n, int k, double sgn) {
   const size_t nk = (size_t)n * k;
   multi_axpy_kernel<<<nblocks(nk, 256), 256, 0, h->stream>>>(Vbase, vstride, nv, hc, W, nk, k, sgn);
+  LAUNCH_CHECK(h);
+  return 0;
+}
+
+// W -= sum_i hc[i] V_i and nrm2[col] = ||W[:, col]||^2 (deterministic chunked reduction)
+int multi_axpy_norm(dmlmc_hier* h, const Z* Vbase, size_t vstride, int nv, const Z* hc, Z* W, int n, int k, Z* partial, Z* nrm2) {
+  const int nchunks = (n + ROWS_PER_CHUNK - 1) / ROWS_PER_CHUNK;
+  dim3 blk(DOT_TX, DOT_TY), grd((k + DOT_TX - 1) / DOT_TX, nchunks);
+  multi_axpy_norm_kernel<<<grd, blk, 0, h->stream>>>(Vbase, vstride, nv, hc, W, n, k, ROWS_PER_CHUNK, partial);
+  LAUNCH_CHECK(h);
+  sum_partials_kernel<<<nblocks((size_t)k, 32), dim3(32, 8), 0, h->stream>>>(partial, nchunks, k, nrm2, 0);
   LAUNCH_CHECK(h);
   return 0;
 }
@@ -639,15 +650,17 @@ int fgmres(dmlmc_hier* h, int level, const Z* B, Z* X, int k, double tol, int re
       RET((launch_op<double, M_AX>(h, level, Zj, nullptr, W, ZERO, ZERO, k)));
       // classical Gram-Schmidt, optionally with one re-orthogonalisation pass
       RET(multi_dot(h, Vb, nk, j + 1, W, n, k, partial, s.hsum, 0));
-      RET(multi_axpy(h, Vb, nk, j + 1, s.hsum, W, n, k, -1.0));
       if (h->reorth) {
+        RET(multi_axpy(h, Vb, nk, j + 1, s.hsum, W, n, k, -1.0));
         RET(multi_dot(h, Vb, nk, j + 1, W, n, k, partial, s.y, 0));       // s.y used as scratch [(j+1)][k]
-        RET(multi_axpy(h, Vb, nk, j + 1, s.y, W, n, k, -1.0));
+        RET(multi_axpy_norm(h, Vb, nk, j + 1, s.y, W, n, k, partial, s.nrm2));
         // hsum += second-pass coefficients
         const int cnt = (j + 1) * k;
-        sum_partials_kernel<<<nblocks(cnt, 256), 256, 0, h->stream>>>(s.y, 1, cnt, s.hsum, 1); LAUNCH_CHECK(h);
+        sum_partials_kernel<<<nblocks(cnt, 32), dim3(32, 8), 0, h->stream>>>(s.y, 1, cnt, s.hsum, 1); LAUNCH_CHECK(h);
+      } else {
+        // w -= V h and ||w||^2 in one pass over W
+        RET(multi_axpy_norm(h, Vb, nk, j + 1, s.hsum, W, n, k, partial, s.nrm2));
       }
-      RET(multi_dot(h, W, 0, 1, W, n, k, partial, s.nrm2, 0));
       CU(cudaMemsetAsync(s.n_active, 0, sizeof(int), h->stream));
       gmres_step_kernel<<<gk, 128, 0, h->stream>>>(s, j, tol); LAUNCH_CHECK(h);
       ++total_it;
@@ -704,13 +717,13 @@ int deflate(dmlmc_hier* h, int level, Z* X, int k) {
     else if (d <= 32) defl_dot_dmma_kernel<8><<<g1, 256, sm1, h->stream>>>(L.defl_V, d, X, n, k, ROWS_PER_CHUNK, partial);
     else              defl_dot_dmma_kernel<16><<<g1, 256, sm1, h->stream>>>(L.defl_V, d, X, n, k, ROWS_PER_CHUNK, partial);
     LAUNCH_CHECK(h);
-    sum_partials_kernel<<<nblocks((size_t)d * k, 256), 256, 0, h->stream>>>(partial, nchunks, d * k, C, 0); LAUNCH_CHECK(h);
+    sum_partials_kernel<<<nblocks((size_t)d * k, 32), dim3(32, 8), 0, h->stream>>>(partial, nchunks, d * k, C, 0); LAUNCH_CHECK(h);
     dim3 g2((k + DD_NT - 1) / DD_NT, (n + 63) / 64);
     defl_axpy_dmma_kernel<<<g2, 256, sm2, h->stream>>>(L.defl_V, d, C, X, n, k); LAUNCH_CHECK(h);
   } else {
     dim3 blk(DOT_TX, DOT_TY), grd((k + DOT_TX - 1) / DOT_TX, nchunks);
     defl_dot_kernel<<<grd, blk, 0, h->stream>>>(L.defl_V, d, X, n, k, ROWS_PER_CHUNK, partial); LAUNCH_CHECK(h);
-    sum_partials_kernel<<<nblocks((size_t)d * k, 256), 256, 0, h->stream>>>(partial, nchunks, d * k, C, 0); LAUNCH_CHECK(h);
+    sum_partials_kernel<<<nblocks((size_t)d * k, 32), dim3(32, 8), 0, h->stream>>>(partial, nchunks, d * k, C, 0); LAUNCH_CHECK(h);
     defl_axpy_kernel<<<nblocks(nk, 256), 256, 0, h->stream>>>(L.defl_V, d, C, X, nk, k); LAUNCH_CHECK(h);
   }
   h->ws_off = mark;

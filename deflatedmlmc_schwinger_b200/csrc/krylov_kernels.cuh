@@ -64,15 +64,25 @@ multi_dot_kernel(const Z* __restrict__ Vbase, size_t vstride, int nv, const Z* _
   }
 }
 
-// out[idx] (+)= sum_chunk partial[chunk*count + idx]
+// out[idx] (+)= sum_chunk partial[chunk*count + idx].  Block (32, 8): 8 lanes share the chunks of an output, then a
+// fixed-order shared-memory reduction (deterministic; the order depends on nchunks only).
 __global__ void __launch_bounds__(256)
 sum_partials_kernel(const Z* __restrict__ partial, int nchunks, int count, Z* __restrict__ out, int accumulate) {
-  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx >= count) return;
+  __shared__ Z red[8][33];
+  const int tx = threadIdx.x, ty = threadIdx.y;
+  const int idx = blockIdx.x * 32 + tx;
   Z s = cx<double>(0.0, 0.0);
-  for (int c = 0; c < nchunks; ++c) s = zadd(s, partial[(size_t)c * count + idx]);
-  if (accumulate) s = zadd(s, out[idx]);
-  out[idx] = s;
+  if (idx < count)
+    for (int c = ty; c < nchunks; c += 8) s = zadd(s, ldc_ro<double>(partial, (size_t)c * count + idx));
+  red[ty][tx] = s;
+  __syncthreads();
+  if (ty == 0 && idx < count) {
+    Z t = red[0][tx];
+#pragma unroll
+    for (int y = 1; y < 8; ++y) t = zadd(t, red[y][tx]);
+    if (accumulate) t = zadd(t, out[idx]);
+    out[idx] = t;
+  }
 }
 
 // W[r][col] += sgn * sum_i h[i][col] * V_i[r][col]
@@ -88,6 +98,39 @@ multi_axpy_kernel(const Z* __restrict__ Vbase, size_t vstride, int nv, const Z* 
   w.re = fma(sgn, acc.re, w.re);
   w.im = fma(sgn, acc.im, w.im);
   W[idx] = w;
+}
+
+// Gram-Schmidt update fused with the norm of its result:
+//   W[r][col] -= sum_i h[i][col] V_i[r][col];   partial[chunk][col] = sum_{r in chunk} |W[r][col]|^2   (as a complex, im = 0)
+// same (32, 8) x row-chunk decomposition as multi_dot_kernel, so the norm is deterministic and needs no extra pass over W.
+__global__ void __launch_bounds__(256)
+multi_axpy_norm_kernel(const Z* __restrict__ Vbase, size_t vstride, int nv, const Z* __restrict__ h,
+                       Z* __restrict__ W, int n, int k, int rows_per_chunk, Z* __restrict__ partial) {
+  __shared__ double red[DOT_TY][DOT_TX + 1];
+  const int tx = threadIdx.x, ty = threadIdx.y;
+  const int col = blockIdx.x * DOT_TX + tx;
+  const int r0 = blockIdx.y * rows_per_chunk;
+  const int r1 = min(n, r0 + rows_per_chunk);
+  double sq = 0.0;
+  if (col < k) {
+    for (int r = r0 + ty; r < r1; r += DOT_TY) {
+      const size_t off = (size_t)r * k + col;
+      Z acc = cx<double>(0.0, 0.0);
+      for (int i = 0; i < nv; ++i) zfma(acc, ldc_ro<double>(h, (size_t)i * k + col), ldc_ro<double>(Vbase, (size_t)i * vstride + off));
+      Z w = W[off];
+      w.re -= acc.re; w.im -= acc.im;
+      W[off] = w;
+      sq = fma(w.re, w.re, fma(w.im, w.im, sq));
+    }
+  }
+  red[ty][tx] = sq;
+  __syncthreads();
+  if (ty == 0 && col < k) {
+    double t = red[0][tx];
+#pragma unroll
+    for (int y = 1; y < DOT_TY; ++y) t += red[y][tx];
+    partial[(size_t)blockIdx.y * k + col] = cx<double>(t, 0.0);
+  }
 }
 
 // Out[r][col] = In[r][col] * scale[col]
