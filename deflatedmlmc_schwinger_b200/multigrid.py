@@ -125,29 +125,28 @@ def harmonic_ritz_inv_roots(A, degree, seed=7):
     em = np.zeros(degree)
     em[-1] = 1.0
     f = np.linalg.solve(Hm.conj().T, em)
-    theta = list(np.linalg.eigvals(Hm + (abs(H[degree, degree - 1]) ** 2) * np.outer(f, em)))
-    out = [max(theta, key=abs)]
-    theta.remove(out[0])
-    while theta:
-        arr = np.array(out)
-        nxt = max(theta, key=lambda t: np.sum(np.log(np.abs(t - arr) + 1e-300)))
-        out.append(nxt)
-        theta.remove(nxt)
+    theta = np.linalg.eigvals(Hm + (abs(H[degree, degree - 1]) ** 2) * np.outer(f, em))
+    out = leja_order(theta)
     return 1.0 / np.array(out, dtype=np.complex128)
 
 
 def leja_order(points):
     """Leja ordering of complex points: start from the largest modulus, then repeatedly take the point
-    that maximises the product of distances to the points already chosen."""
-    pts = list(points)
-    out = [max(pts, key=abs)]
-    pts.remove(out[0])
-    while pts:
-        arr = np.array(out)
-        nxt = max(pts, key=lambda t: np.sum(np.log(np.abs(t - arr) + 1e-300)))
-        out.append(nxt)
-        pts.remove(nxt)
-    return np.array(out, dtype=np.complex128)
+    that maximises the product of distances to the points already chosen (running log-products, O(d^2))."""
+    pts = np.asarray(points, dtype=np.complex128).reshape(-1)
+    m = pts.shape[0]
+    left = np.ones(m, dtype=bool)
+    first = int(np.argmax(np.abs(pts)))
+    order = [first]
+    left[first] = False
+    logp = np.log(np.abs(pts - pts[first]) + 1e-300)
+    for _ in range(m - 1):
+        cand = np.where(left, logp, -np.inf)
+        nxt = int(np.argmax(cand))
+        order.append(nxt)
+        left[nxt] = False
+        logp = logp + np.log(np.abs(pts - pts[nxt]) + 1e-300)
+    return pts[order]
 
 
 def smoother_product_form(omega):

@@ -141,6 +141,44 @@ def golden_16(ref, rec):
     np.savez_compressed(os.path.join(OUT, "schwinger16.npz"), **g)
 
 
+def golden_16_deflated_mlmc(ref, rec):
+    """Deflated MLMC on 16^2 (mlmc_deflat_vctrs = [16, 16], the variant SURVEY.md 8d calls the valid deflated one):
+    the reference's own deflation_pre_computations(method="mlmc") on its difference-level operator diff_op_Q
+    (utils.py:141-158, multigrid.py:461-549) and 8 deflated level samples per level (utils.py:252-357 with
+    nr_deflat_vctrs > 0).  Written to a separate file so that the other goldens stay byte-identical."""
+    from scipy.sparse.linalg import LinearOperator
+    g0 = np.load(os.path.join(OUT, "schwinger16.npz"))
+    g = {}
+    p = ref_shim.params_16(permuted=False, nr_deflat_vctrs=0, mlmc_deflat_vctrs=(16, 16))
+    rec2 = ref_shim.EigRecorder(replay=[("eigs", np.zeros(2), g0["tv0"]), ("eigs", np.zeros(2), g0["tv1"])])
+    ref_shim.load_reference(rec2)
+    A, tp, mg, tvs = _ref_setup(ref, rec2, p, "mlmc")
+    ref_shim.load_reference(rec)
+    mg.skip_level = False
+    mp = refport.MGPort(refport.load_matrix(p["matrix"], p["matrix_params"]["mass"]))
+    mp.setup(tp["dof"], tp["aggrs"], tp["max_nr_levels"], tp["accuracy_mg_eigvs"], tp, test_vectors=[g0["tv0"], g0["tv1"]])
+    for ix in range(2):
+        mg.level_for_diff_op = ix
+        lop = LinearOperator(mg.ml.levels[ix].A.shape, matvec=mg.diff_op_Q, dtype=np.complex128)
+        rec.calls.clear()
+        with _quiet():
+            Vx, Ux, tr1 = ref["utils"].deflation_pre_computations(A, 16, tp["defl_eigvs_tol_MLMC"], "mlmc", mg.timer, tp,
+                                                                  mg, lop, level_nr=ix)
+        g[f"l{ix}_Sy"], g[f"l{ix}_eigvecs"] = rec.calls[0][1], rec.calls[0][2]     # raw eigsh output (injectable)
+        g[f"l{ix}_Vx"], g[f"l{ix}_Ux"], g[f"l{ix}_tr1"] = Vx, Ux, tr1
+        np.random.seed(123456 + ix)
+        rs = np.random.RandomState(123456 + ix)
+        el = []
+        for q in range(8):
+            e, _ = _ref_probe(ref, mg, tp, "mlmc", ix, 16, Vx, Ux, False)
+            e2, _ = refport.one_defl_hutch_step(mp.levels[ix].A, mp.levels[ix + 1].A, mp, tp, "mlmc", 16, Vx, Ux, rs, ix)
+            assert abs(e - e2) <= 1e-8 * max(abs(e), 1.0), (e, e2)
+            el.append(e)
+        g[f"l{ix}_e"] = np.array(el)
+        print(f"16^2 deflated mlmc level {ix}: tr1 = {tr1}, first estimates {el[:2]}", file=sys.stderr)
+    np.savez_compressed(os.path.join(OUT, "schwinger16_defl_mlmc.npz"), **g)
+
+
 def golden_128(ref, rec):
     g = {}
     p = ref_shim.params_128()
@@ -200,6 +238,8 @@ def main():
         golden_16(ref, rec)
     if "128" in which:
         golden_128(ref, rec)
+    if "16defl" in which:
+        golden_16_deflated_mlmc(ref, rec)
     print("golden written to", OUT, file=sys.stderr)
 
 

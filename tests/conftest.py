@@ -38,6 +38,12 @@ def g16():
 
 
 @pytest.fixture(scope="session")
+def g16defl():
+    """deflated MLMC on 16^2 from the unmodified reference (oracle.make_golden 16defl)"""
+    return np.load(os.path.join(GOLDEN, "schwinger16_defl_mlmc.npz"))
+
+
+@pytest.fixture(scope="session")
 def g128():
     return np.load(os.path.join(GOLDEN, "schwinger128.npz"))
 

@@ -181,3 +181,24 @@ def test_mg_object_api(mg16, port16):
     mg.diff_op_Q(v)
     assert np.array_equal(v, b)              # input not mutated (the reference's quirk is not replicated)
     assert "size(A) = (512, 512)" in str(mg)
+
+
+def test_deflated_mlmc_level_samples_16_match_reference(mg16, g16defl):
+    """the deflated-MLMC branch: x_def = x - V V^H x on the device, then the same fused sample; estimates against
+    the unmodified reference's for identical deflation vectors and probes (tolerance 1e-8), and the host part of
+    deflation_pre_computations (sign fix, gamma3, tr1; utils.py:145-176) from the same raw eigensolver output"""
+    from deflatedmlmc_schwinger_b200 import utils
+    mg, tp, A = mg16
+    mg.skip_level = False
+    tp = dict(tp); tp["defl_type"] = "exact"; tp["diff_lev_op_tol"] = 1e-3
+    for ix in range(2):
+        Vx, Ux, tr1 = utils.deflation_pre_computations(A, 16, 1e-1, "mlmc", mg.timer, tp, mg, None, level_nr=ix,
+                                                       eigpairs=(g16defl["l%d_Sy" % ix], g16defl["l%d_eigvecs" % ix]))
+        assert np.abs(Vx - g16defl["l%d_Vx" % ix]).max() < 1e-12 and np.abs(Ux - g16defl["l%d_Ux" % ix]).max() < 1e-12
+        assert abs(tr1 - g16defl["l%d_tr1" % ix]) < 1e-10 * abs(tr1)
+        np.random.seed(123456 + ix)
+        e, it = utils.defl_Hutch_batch(mg, tp, "mlmc", 16, Vx, ix, 8)
+        ref = g16defl["l%d_e" % ix]
+        assert np.abs(e - ref).max() < 1e-8 * max(np.abs(ref).max(), 1.0), ix
+    mg.dev.set_deflation(0, None); mg.dev.set_deflation(1, None)
+    mg.__dict__.pop("_defl_cache", None)

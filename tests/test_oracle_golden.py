@@ -131,3 +131,17 @@ def test_exact_level_split_sums_to_gateway_golden(port128, g128):
     t2 = np.trace(A2inv @ C2) - t3
     # the level-2 probes of the golden stream scatter around t2 with std ~19.5
     assert abs(np.mean(g128["mlmc_l2_e"]) - t2) < 5 * 19.5 / np.sqrt(16) + 1.0
+
+
+def test_port16_deflated_mlmc_probes_match_reference(port16, g16defl):
+    """deflated MLMC level samples (utils.py:252-357 with nr_deflat_vctrs = 16) of the port against the unmodified
+    reference, deflation vectors from the reference's own deflation_pre_computations on diff_op_Q"""
+    mp, tp = port16
+    mp.skip_level = False
+    for ix in range(2):
+        rs = np.random.RandomState(123456 + ix)
+        ref = g16defl["l%d_e" % ix]
+        for q in range(8):
+            e, _ = refport.one_defl_hutch_step(mp.levels[ix].A, mp.levels[ix + 1].A, mp, tp, "mlmc", 16,
+                                               g16defl["l%d_Vx" % ix], g16defl["l%d_Ux" % ix], rs, ix)
+            assert abs(e - ref[q]) < 1e-8 * max(abs(ref[q]), 1.0), (ix, q)
