@@ -75,6 +75,7 @@ struct dmlmc_hier {
   int inner_prec = DMLMC_C64;
   int reorth = 0;
   int stencil_by = 4, stencil_bz = 4;     // site tile (t, x) of the stencil kernel's thread block
+  int stencil_smem = 0;                   // shared-memory-tiled variant of the packed-FP32 factor kernel
   int stencil_fast = 1;                   // packed-FP32 (FFMA2) kernel for the BF16-stored smoother factors
   int prefetch_slices = 16;               // Y = A X / B - A X on level 0: L2 prefetch distance in x-slices (0, 8, 16)
   int pre_smooth = 0;                     // 0: V-cycle = coarse correction + post-smoothing (default), 1: pre- and post-smoothing
@@ -406,6 +407,14 @@ int smooth_apply(dmlmc_hier* h, int level, const void* R, void* E, bool acc, voi
           void* out = pp[i & 1];
           if (L.kind == 0 && h->stencil_fast && L.d.diag.im == 0.0 && (size_t)L.n * (k / 2) < (1ull << 32)) {
             const int kp = k / 2;
+            if (h->stencil_smem && (kp % 2) == 0) {
+              dim3 grd((kp + 15) / 16, (L.LT + 7) / 8, (L.LX + 7) / 8);
+              stencil_step_bf16_smem_kernel<8, 8><<<grd, 512, 0, h->stream>>>(L.LX, L.LT, L.links4, (float)L.d.diag.re, (const uint2*)in,
+                                                                           (uint2*)out, (float)L.nu[i].re, (float)L.nu[i].im, (uint32_t)kp);
+              LAUNCH_CHECK(h);
+              in = out;
+              continue;
+            }
             const long long rowb = (long long)kp * 8;
             int bx = 1; while (bx < 32 && bx < kp) bx *= 2;
             int by = std::max(1, std::min(h->stencil_by, L.LT)), bz = std::max(1, std::min(h->stencil_bz, L.LX));
@@ -1158,6 +1167,7 @@ int dmlmc_set_option(dmlmc_hier* h, const char* name, double value) {
   if (std::strcmp(name, "l2_budget_mb") == 0) { CHECK(value >= 0, "l2_budget_mb must be >= 0"); h->l2_budget_mb = value; return 0; }
   if (std::strcmp(name, "stencil_by") == 0) { CHECK(value >= 1, "stencil_by must be >= 1"); h->stencil_by = (int)value; return 0; }
   if (std::strcmp(name, "defl_tensor") == 0) { h->defl_tensor = value != 0.0; return 0; }
+  if (std::strcmp(name, "stencil_smem") == 0) { h->stencil_smem = value != 0.0; return 0; }
   if (std::strcmp(name, "stencil_fast") == 0) { h->stencil_fast = value != 0.0; return 0; }
   if (std::strcmp(name, "prefetch_slices") == 0) { h->prefetch_slices = (int)value; return 0; }
   if (std::strcmp(name, "pre_smooth") == 0) { h->pre_smooth = value != 0.0; return 0; }

@@ -236,6 +236,80 @@ stencil_step_bf16_kernel(int LX, int LT, const float4* __restrict__ L4, float di
   sth_c2(reinterpret_cast<uint2*>(py + spb), 0u, o1);
 }
 
+// Shared-memory-tiled variant of the same factor kernel (option "stencil_smem", OFF by default: measured on B200 at
+// k = 256 it needs 26.5 us per launch against 20.5 us for the L1-cached direct-load kernel above -- the load / barrier /
+// compute phases of a CTA do not overlap as well as 48 independent warps per SM do; profiles/r1_run17_*).
+// A CTA stages the (TX+2) x (TT+2) halo'd site tile of
+// 32 columns (both spin components, BF16: 128 bytes per site row) with three coalesced LDG.128 per thread -- all
+// global loads of the CTA are in flight at once and every vector row is read from L2 1.5 times instead of ~3 --
+// and computes from shared memory (LDS.64, conflict-free: a warp reads two 128-byte rows).
+template <int TX, int TT>
+__global__ void __launch_bounds__(512, 3)
+stencil_step_bf16_smem_kernel(int LX, int LT, const float4* __restrict__ L4, float diag,
+                              const uint2* __restrict__ X, uint2* __restrict__ Y, float wr, float wi, uint32_t kp) {
+  constexpr int SX = TX + 2, ST = TT + 2;
+  __shared__ __align__(16) uint2 S[2][SX][ST][16];
+  const int tid = threadIdx.x;
+  const int x0 = blockIdx.z * TX, t0 = blockIdx.y * TT;
+  const uint32_t p0 = blockIdx.x * 16;
+  const uint32_t V = (uint32_t)LX * LT;
+  for (int c = tid; c < 2 * SX * ST * 8; c += 512) {
+    const int q = c & 7, row = c >> 3;
+    const int tt = row % ST, r2 = row / ST;
+    const int xx = r2 % SX, sp = r2 / SX;
+    const bool corner = (xx == 0 || xx == SX - 1) && (tt == 0 || tt == ST - 1);
+    if (corner) continue;
+    int x = x0 + xx - 1; x = (x < 0) ? x + LX : ((x >= LX) ? x - LX : x);
+    int t = t0 + tt - 1; t = (t < 0) ? t + LT : ((t >= LT) ? t - LT : t);
+    uint4 v = make_uint4(0u, 0u, 0u, 0u);
+    if (p0 + 2 * q + 1 < kp && x < LX && t < LT)
+      v = __ldg(reinterpret_cast<const uint4*>(X + ((size_t)(sp * V + (uint32_t)x * LT + t) * kp + p0 + 2 * q)));
+    *reinterpret_cast<uint4*>(&S[sp][xx][tt][2 * q]) = v;
+  }
+  __syncthreads();
+  const float2 dg = make_float2(diag, diag);
+  const float2 w_r = make_float2(wr, wr), w_i = make_float2(wi, wi);
+  auto cvt = [](const uint2 raw) { C2 r; r.re = make_float2(bf_lo(raw.x), bf_lo(raw.y)); r.im = make_float2(bf_hi(raw.x), bf_hi(raw.y)); return r; };
+#pragma unroll
+  for (int it = tid; it < TX * TT * 16; it += 512) {
+    const int p = it & 15, sidx = it >> 4;
+    const int tl = sidx % TT, xl = sidx / TT;
+    const int x = x0 + xl, t = t0 + tl;
+    if (x >= LX || t >= LT || p0 + p >= kp) continue;
+    const uint32_t site = (uint32_t)x * LT + t;
+    const float4* lp = L4 + site;
+    const float4 ut = __ldg(lp), utb = __ldg(lp + V), ux = __ldg(lp + 2 * V), uxb = __ldg(lp + 3 * V);
+    const C2 c0 = cvt(S[0][xl + 1][tl + 1][p]), c1 = cvt(S[1][xl + 1][tl + 1][p]);
+    const C2 f0 = cvt(S[0][xl + 1][tl + 2][p]), f1 = cvt(S[1][xl + 1][tl + 2][p]);
+    const C2 b0 = cvt(S[0][xl + 1][tl][p]),     b1 = cvt(S[1][xl + 1][tl][p]);
+    const C2 r0 = cvt(S[0][xl + 2][tl + 1][p]), r1 = cvt(S[1][xl + 2][tl + 1][p]);
+    const C2 l0 = cvt(S[0][xl][tl + 1][p]),     l1 = cvt(S[1][xl][tl + 1][p]);
+    C2 a, b, c, d;
+    a.re = __fadd2_rn(f0.re, neg2(f1.re)); a.im = __fadd2_rn(f0.im, neg2(f1.im));
+    b.re = __fadd2_rn(b0.re, b1.re);       b.im = __fadd2_rn(b0.im, b1.im);
+    c.re = __fadd2_rn(r0.re, neg2(r1.im)); c.im = __fadd2_rn(r0.im, r1.re);
+    d.re = __fadd2_rn(l0.re, l1.im);       d.im = __fadd2_rn(l0.im, neg2(l1.re));
+    const C2 ua = cmul_splat(ut, a), ub = cmul_splat(utb, b), uc = cmul_splat(ux, c), ud = cmul_splat(uxb, d);
+    C2 s_, q_, tt_, y0, y1;
+    s_.re = __fadd2_rn(__fadd2_rn(ua.re, ub.re), __fadd2_rn(uc.re, ud.re));
+    s_.im = __fadd2_rn(__fadd2_rn(ua.im, ub.im), __fadd2_rn(uc.im, ud.im));
+    q_.re = __fadd2_rn(ua.re, neg2(ub.re));  q_.im = __fadd2_rn(ua.im, neg2(ub.im));
+    tt_.re = __fadd2_rn(uc.re, neg2(ud.re)); tt_.im = __fadd2_rn(uc.im, neg2(ud.im));
+    y0.re = __ffma2_rn(dg, c0.re, neg2(s_.re));
+    y0.im = __ffma2_rn(dg, c0.im, neg2(s_.im));
+    y1.re = __ffma2_rn(dg, c1.re, __fadd2_rn(q_.re, neg2(tt_.im)));
+    y1.im = __ffma2_rn(dg, c1.im, __fadd2_rn(q_.im, tt_.re));
+    C2 o0, o1;
+    o0.re = __ffma2_rn(w_i, y0.im, __ffma2_rn(neg2(w_r), y0.re, c0.re));
+    o0.im = __ffma2_rn(neg2(w_i), y0.re, __ffma2_rn(neg2(w_r), y0.im, c0.im));
+    o1.re = __ffma2_rn(w_i, y1.im, __ffma2_rn(neg2(w_r), y1.re, c1.re));
+    o1.im = __ffma2_rn(neg2(w_i), y1.re, __ffma2_rn(neg2(w_r), y1.im, c1.im));
+    uint2* py = Y + ((size_t)site * kp + p0 + p);
+    sth_c2(py, 0u, o0);
+    sth_c2(py + (size_t)V * kp, 0u, o1);
+  }
+}
+
 // ------------------------------------------------------------------------------------------
 template <typename T> struct BsrDev {
   int nb, bpr;

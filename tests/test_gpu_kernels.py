@@ -162,6 +162,11 @@ def test_smoother_is_the_polynomial(mg128, dtype):
             Eg = mg.dev.smooth(lvl, R)
             mg.dev.set_option("stencil_fast", 1)
             assert relerr(host(Eg), e) < 1e-1 and relerr(host(Eg), host(E)) < 5e-2, lvl
+            if lvl == 0:                                    # shared-memory-tiled variant: same arithmetic
+                mg.dev.set_option("stencil_smem", 1)
+                Es = mg.dev.smooth(lvl, R)
+                mg.dev.set_option("stencil_smem", 0)
+                assert relerr(host(Es), host(E)) < 1e-6, "smem variant"
             mg.dev.set_option("smoother_half", 0)
             E = mg.dev.smooth(lvl, R)
             mg.dev.set_option("smoother_half", 1)
