@@ -18,8 +18,16 @@ ap.add_argument("--degree", type=int, default=64)
 args = ap.parse_args()
 
 import torch
+import torch.distributed as dist
+rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1")); local = int(os.environ.get("LOCAL_RANK", "0"))
+torch.cuda.set_device(local)
+if world > 1:                      # one process per GPU, probes sharded: rank g takes the g-th block of k probes
+    dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 import __graft_entry__ as ge
-ge.build()
+if rank == 0:
+    ge.build()
+if world > 1:
+    dist.barrier()
 from deflatedmlmc_schwinger_b200 import lattice, multigrid, sampling, utils
 
 L = args.L
@@ -52,6 +60,7 @@ dev = mg.dev
 k = args.probes
 restart, maxiter = 40, 1000
 np.random.seed(123456)
+sampling.skip_probe_words(rank * k * n0)
 bits = torch.from_numpy(utils.pack_bits(sampling.draw_probe_bits(k * n0))).cuda()
 X0 = dev.probe_expand(bits, n0, k)
 # one solve with residual check
@@ -61,17 +70,31 @@ true_rel = float((torch.linalg.vector_norm(R, dim=0) / torch.linalg.vector_norm(
 del Xs, R
 e, it = dev.level_sample(1, 0, 1, X0, 1e-12, restart, maxiter)      # warm-up
 torch.cuda.synchronize()
+if world > 1:
+    dist.barrier()
 l0 = dev.launch_count(); t = time.time()
 for _ in range(args.steps):
     e, it = dev.level_sample(1, 0, 1, X0, 1e-12, restart, maxiter)
 torch.cuda.synchronize()
 dt = (time.time() - t) / args.steps
-print(json.dumps({"workload": "synthetic random-U(1) Schwinger %dx%d, m=%g, level-0 MLMC difference samples (coarse level 1)" % (L, L, args.mass),
+if world > 1:                      # the level's single collective + max time over ranks
+    red = torch.tensor([e.real.sum().item(), e.imag.sum().item(), float(e.numel())], device="cuda", dtype=torch.float64)
+    dist.all_reduce(red)
+    tt = torch.tensor([dt], device="cuda", dtype=torch.float64)
+    dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+    dt = float(tt.item())
+    mean_est = [float(red[0] / red[2]), float(red[1] / red[2])]
+else:
+    mean_est = [float(e.real.mean()), float(e.imag.mean())]
+if rank == 0:
+  print(json.dumps({"n_gpus": world, "workload": "synthetic random-U(1) Schwinger %dx%d, m=%g, level-0 MLMC difference samples (coarse level 1)" % (L, L, args.mass),
                   "levels": mg.level_shapes, "dense_levels": {str(a): b for a, b in mg.dense_levels.items()},
-                  "smoother_degrees": mg.smoother_degrees_used, "probes": k, "ms_per_batch": 1e3 * dt,
-                  "probes_per_s": k / dt, "fgmres_iters_level0": [int(it[0].min()), int(it[0].max())],
+                  "smoother_degrees": mg.smoother_degrees_used, "probes_per_gpu": k, "ms_per_batch": 1e3 * dt,
+                  "probes_per_s": world * k / dt, "fgmres_iters_level0": [int(it[0].min()), int(it[0].max())],
                   "fgmres_iters_level1": [int(it[1].min()), int(it[1].max())],
                   "solve_iters": [int(iters.min()), int(iters.max())], "max_true_relres": true_rel,
                   "launches_per_batch": (dev.launch_count() - l0) // args.steps, "setup_s": setup_s,
                   "test_vectors": "cache" if tvs is not None else "host eigs",
-                  "mean_estimate": [float(e.real.mean()), float(e.imag.mean())]}), flush=True)
+                  "mean_estimate": mean_est}), flush=True)
+if world > 1:
+    dist.destroy_process_group()
