@@ -75,6 +75,7 @@ struct dmlmc_hier {
   int inner_prec = DMLMC_C64;
   int reorth = 0;
   int stencil_by = 4, stencil_bz = 4;     // site tile (t, x) of the stencil kernel's thread block
+  int bsr_threads = 128;                  // threads per CTA of the packed-FP32 BSR kernel (block rows per CTA = this / threads per row)
   int stencil_smem = 0;                   // shared-memory-tiled variant of the packed-FP32 factor kernel
   int stencil_fast = 1;                   // packed-FP32 (FFMA2) kernel for the BF16-stored smoother factors
   int prefetch_slices = 16;               // Y = A X / B - A X on level 0: L2 prefetch distance in x-slices (0, 8, 16)
@@ -168,13 +169,14 @@ int launch_op_nc(dmlmc_hier* h, int level, const void* X, const void* B, void* Y
         int tpr = 1;
         if (need >= 32) tpr = std::min(128, ((need + 31) / 32) * 32); else while (tpr < need) tpr *= 2;
         const size_t per_row = (size_t)L.bpr * L.bs * L.bs * sizeof(float4) + (size_t)L.bpr * sizeof(int);
-        int RB = std::max(1, 128 / tpr);
+        int RB = std::max(1, (HIN ? h->bsr_threads : 128) / tpr);
         RB = (int)std::max<size_t>(1, std::min<size_t>(RB, 40960 / per_row));
         const size_t smem = RB * per_row + 16;
         if (smem <= 48 * 1024) {
           dim3 blk(tpr, RB), grd((L.nb + RB - 1) / RB, (kp + tpr * PPT - 1) / (tpr * PPT));
-#define BSR2H(BS_, PPT_) bsr_f32x2_kernel<BS_, PPT_, MODE, HIN, HOUT><<<grd, blk, smem, h->stream>>>(L.nb, L.bpr, L.bsr_col, L.bsr_vals4, \
-              X, (const P*)B, Y, wt, ct, kp)
+#define BSR2H(BS_, PPT_) do { if constexpr (HIN) bsr_f32x2_soa_kernel<BS_, PPT_, MODE, HIN, HOUT><<<grd, blk, smem, h->stream>>>(L.nb, L.bpr, L.bsr_col, L.bsr_vals4, \
+              X, (const P*)B, Y, wt, ct, kp); else bsr_f32x2_kernel<BS_, PPT_, MODE, HIN, HOUT><<<grd, blk, smem, h->stream>>>(L.nb, L.bpr, L.bsr_col, L.bsr_vals4, \
+              X, (const P*)B, Y, wt, ct, kp); } while (0)
           if (L.bs == 2) BSR2H(2, 2); else if (L.bs == 4) BSR2H(4, 2); else BSR2H(8, 1);
 #undef BSR2H
           LAUNCH_CHECK(h);
@@ -1167,6 +1169,7 @@ int dmlmc_set_option(dmlmc_hier* h, const char* name, double value) {
   if (std::strcmp(name, "l2_budget_mb") == 0) { CHECK(value >= 0, "l2_budget_mb must be >= 0"); h->l2_budget_mb = value; return 0; }
   if (std::strcmp(name, "stencil_by") == 0) { CHECK(value >= 1, "stencil_by must be >= 1"); h->stencil_by = (int)value; return 0; }
   if (std::strcmp(name, "defl_tensor") == 0) { h->defl_tensor = value != 0.0; return 0; }
+  if (std::strcmp(name, "bsr_threads") == 0) { CHECK(value >= 32 && value <= 256, "bsr_threads must be in [32, 256]"); h->bsr_threads = (int)value; return 0; }
   if (std::strcmp(name, "stencil_smem") == 0) { h->stencil_smem = value != 0.0; return 0; }
   if (std::strcmp(name, "stencil_fast") == 0) { h->stencil_fast = value != 0.0; return 0; }
   if (std::strcmp(name, "prefetch_slices") == 0) { h->prefetch_slices = (int)value; return 0; }

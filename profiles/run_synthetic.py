@@ -14,7 +14,7 @@ ap.add_argument("--L", type=int, default=256)
 ap.add_argument("--probes", type=int, default=64)
 ap.add_argument("--mass", type=float, default=-0.062)
 ap.add_argument("--steps", type=int, default=2)
-ap.add_argument("--degree", type=int, default=64)
+ap.add_argument("--degree", type=int, default=80)
 args = ap.parse_args()
 
 import torch
