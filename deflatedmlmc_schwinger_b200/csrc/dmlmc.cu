@@ -91,8 +91,13 @@ struct dmlmc_hier {
   char* ws = nullptr; size_t ws_bytes = 0, ws_off = 0;
   int* h_nactive = nullptr;        // pinned
   cudaStream_t rng_stream = nullptr; cudaEvent_t rng_done = nullptr;   // the probe stream runs beside the solver
+  cudaStream_t cap_stream = nullptr;                                   // capture stream of the V-cycle graphs
   long long launches = 0;
   std::vector<void*> owned;
+  // CUDA graphs of the V-cycle for small batches (launch-bound there: ~90 kernels of a few microseconds each)
+  struct GraphEntry { int level, k, prec; char* ws; size_t ws_off; cudaGraphExec_t exec; long long launches; };
+  std::vector<GraphEntry> graphs;
+  int use_graphs = 1, graph_max_k = 64;
 };
 
 namespace {
@@ -593,9 +598,67 @@ int multi_axpy_norm(dmlmc_hier* h, const Z* Vbase, size_t vstride, int nv, const
   return 0;
 }
 
-int precond(dmlmc_hier* h, int level, const Z* V, Z* Zout, int k) {
+void invalidate_graphs(dmlmc_hier* h) {
+  for (auto& g : h->graphs) if (g.exec) cudaGraphExecDestroy(g.exec);
+  h->graphs.clear();
+}
+
+int precond_eager(dmlmc_hier* h, int level, const Z* V, Z* Zout, int k) {
   if (h->inner_prec == DMLMC_C128) return vcycle<double, double>(h, level, V, Zout, k);
   return vcycle<float, double>(h, level, V, Zout, k);
+}
+
+// Z = V-cycle(V).  For small batches the cycle is a fixed sequence of ~90 launches of a few microseconds each and
+// the solve is launch-bound (measured: 8.4 us per launch at k = 1), so the sequence is captured once per
+// (level, k, precision, work-space position) into a CUDA graph and replayed; V and Z, whose addresses change with the
+// Krylov index, go through two fixed staging buffers.  First call: eager (one-time attribute / descriptor set-up),
+// second call: capture, then replay.  Any set_* / option call drops the graphs.
+int precond(dmlmc_hier* h, int level, const Z* V, Z* Zout, int k) {
+  if (!h->use_graphs || k > h->graph_max_k) return precond_eager(h, level, V, Zout, k);
+  const size_t nk = (size_t)h->lv[level].n * k;
+  const size_t mark = h->ws_off;
+  Z *sb, *sx;
+  RET(ws_get<Z>(h, nk, &sb)); RET(ws_get<Z>(h, nk, &sx));
+  dmlmc_hier::GraphEntry* e = nullptr;
+  for (auto& g : h->graphs)
+    if (g.level == level && g.k == k && g.prec == h->inner_prec && g.ws == h->ws && g.ws_off == mark) { e = &g; break; }
+  CU(cudaMemcpyAsync(sb, V, nk * sizeof(Z), cudaMemcpyDeviceToDevice, h->stream));
+  int rc = 0;
+  if (e == nullptr) {
+    h->graphs.push_back({level, k, h->inner_prec, h->ws, mark, nullptr, 0});
+    rc = precond_eager(h, level, sb, sx, k);
+  } else if (e->exec == nullptr) {
+    const long long l0 = h->launches;
+    cudaGraph_t graph = nullptr;
+    // capture on an internal stream (the caller's may be the legacy default stream, which cannot capture); the
+    // instantiated graph is launched on the caller's stream like every other kernel
+    cudaStream_t user = h->stream;
+    cudaError_t ce = cudaStreamBeginCapture(h->cap_stream, cudaStreamCaptureModeRelaxed);
+    if (ce == cudaSuccess) {
+      h->stream = h->cap_stream;
+      rc = precond_eager(h, level, sb, sx, k);
+      h->stream = user;
+      ce = cudaStreamEndCapture(h->cap_stream, &graph);
+      if (rc == 0 && ce == cudaSuccess && graph) ce = cudaGraphInstantiate(&e->exec, graph, 0);
+      if (graph) cudaGraphDestroy(graph);
+    }
+    if (rc != 0 || ce != cudaSuccess || e->exec == nullptr) {      // capture not possible here: stay eager from now on
+      cudaGetLastError();
+      h->use_graphs = 0;
+      if (e->exec) { cudaGraphExecDestroy(e->exec); e->exec = nullptr; }
+      h->launches = l0;
+      rc = precond_eager(h, level, sb, sx, k);
+    } else {
+      e->launches = h->launches - l0;
+      CU(cudaGraphLaunch(e->exec, h->stream));
+    }
+  } else {
+    CU(cudaGraphLaunch(e->exec, h->stream));
+    h->launches += e->launches;
+  }
+  if (rc == 0) CU(cudaMemcpyAsync(Zout, sx, nk * sizeof(Z), cudaMemcpyDeviceToDevice, h->stream));
+  h->ws_off = mark;
+  return rc;
 }
 
 int read_nactive(dmlmc_hier* h, int* dev_counter, int* out) {
@@ -835,6 +898,7 @@ size_t fgmres_bytes(dmlmc_hier* h, int level, int k, int m) {
   b += align_up(partial_count((int)n, m + 1, k) * z);
   b += align_up((size_t)m * m * k * z) + 6 * align_up((size_t)(m + 1) * k * z) + 16 * align_up((size_t)k * 16);
   b += vcycle_bytes(h, level, k, sizeof(Z));
+  b += 2 * align_up(nk * z);          // staging buffers of the graph-replayed V-cycle
   return b + (1 << 16);
 }
 
@@ -860,7 +924,8 @@ int dmlmc_hier_create(int device, void* cuda_stream, int n_levels, dmlmc_hier** 
   if (e2 != cudaSuccess) { delete h; return fail((int)e2, "cudaMallocHost failed"); }
   int lo = 0, hi = 0;
   cudaDeviceGetStreamPriorityRange(&lo, &hi);
-  if (cudaStreamCreateWithPriority(&h->rng_stream, cudaStreamNonBlocking, hi) != cudaSuccess ||
+  if (cudaStreamCreateWithFlags(&h->cap_stream, cudaStreamNonBlocking) != cudaSuccess ||
+      cudaStreamCreateWithPriority(&h->rng_stream, cudaStreamNonBlocking, hi) != cudaSuccess ||
       cudaEventCreateWithFlags(&h->rng_done, cudaEventDisableTiming) != cudaSuccess) {
     delete h; return fail(-3, "dmlmc: cannot create the probe-stream CUDA stream");
   }
@@ -872,15 +937,18 @@ int dmlmc_hier_destroy(dmlmc_hier* h) {
   if (!h) return 0;
   cudaSetDevice(h->device);
   cudaStreamSynchronize(h->stream);
+  invalidate_graphs(h);
   for (void* p : h->owned) cudaFree(p);
   if (h->h_nactive) cudaFreeHost(h->h_nactive);
   if (h->rng_stream) { cudaStreamSynchronize(h->rng_stream); cudaStreamDestroy(h->rng_stream); }
   if (h->rng_done) cudaEventDestroy(h->rng_done);
+  if (h->cap_stream) cudaStreamDestroy(h->cap_stream);
   delete h;
   return 0;
 }
 
 int dmlmc_set_stencil(dmlmc_hier* h, int level, int LX, int LT, const double* links_host, double diag_re, double diag_im) {
+  if (h) invalidate_graphs(h);
   CHECK(h && level >= 0 && level < h->n_levels, "set_stencil: bad handle/level");
   CHECK(LX >= 2 && LT >= 2 && links_host, "set_stencil: bad lattice");
   CU(cudaSetDevice(h->device));
@@ -910,6 +978,7 @@ int dmlmc_set_stencil(dmlmc_hier* h, int level, int LX, int LT, const double* li
 }
 
 int dmlmc_set_bsr(dmlmc_hier* h, int level, int n, int bs, int bpr, const int32_t* colidx_host, const double* vals_host) {
+  if (h) invalidate_graphs(h);
   CHECK(h && level >= 0 && level < h->n_levels, "set_bsr: bad handle/level");
   CHECK(bs == 1 || bs == 2 || bs == 4 || bs == 8, "set_bsr: block size must be 1, 2, 4 or 8");
   CHECK(n > 0 && n % bs == 0 && bpr >= 1 && colidx_host && vals_host, "set_bsr: bad arguments");
@@ -932,6 +1001,7 @@ int dmlmc_set_bsr(dmlmc_hier* h, int level, int n, int bs, int bpr, const int32_
 }
 
 int dmlmc_set_transfer(dmlmc_hier* h, int level, int n_f, int aggr_size, int dofi, int nvec, const double* pvals_host) {
+  if (h) invalidate_graphs(h);
   CHECK(h && level >= 0 && level < h->n_levels - 1, "set_transfer: bad handle/level");
   CHECK(nvec == 1 || nvec == 2 || nvec == 4 || nvec == 8, "set_transfer: nvec must be 1, 2, 4 or 8");
   CHECK(n_f > 0 && aggr_size > 0 && dofi >= 2 && dofi % 2 == 0 && aggr_size % dofi == 0 && n_f % aggr_size == 0 && pvals_host,
@@ -945,6 +1015,7 @@ int dmlmc_set_transfer(dmlmc_hier* h, int level, int n_f, int aggr_size, int dof
 }
 
 int dmlmc_set_dense_inverse(dmlmc_hier* h, int level, int n, const double* minv_host) {
+  if (h) invalidate_graphs(h);
   CHECK(h && level >= 0 && level < h->n_levels && n > 0 && minv_host, "set_dense_inverse: bad arguments");
   CU(cudaSetDevice(h->device));
   Level& L = h->lv[level];
@@ -966,6 +1037,7 @@ int dmlmc_set_dense_inverse(dmlmc_hier* h, int level, int n, const double* minv_
 }
 
 int dmlmc_set_dense_inverse_device(dmlmc_hier* h, int level, int n, const void* minv_dev) {
+  if (h) invalidate_graphs(h);
   CHECK(h && level >= 0 && level < h->n_levels && n > 0 && minv_dev, "set_dense_inverse_device: bad arguments");
   CHECK(n % 8 == 0, "set_dense_inverse_device: n must be a multiple of 8");
   CU(cudaSetDevice(h->device));
@@ -983,6 +1055,7 @@ int dmlmc_set_coarsest_inverse(dmlmc_hier* h, int n, const double* minv_host) {
 }
 
 int dmlmc_set_smoother(dmlmc_hier* h, int level, int nfactors, const double* nu_host, double p0_re, double p0_im) {
+  if (h) invalidate_graphs(h);
   CHECK(h && level >= 0 && level < h->n_levels, "set_smoother: bad handle/level");
   CHECK(nfactors >= 0 && (nfactors == 0 || nu_host), "set_smoother: bad factors");
   Level& L = h->lv[level];
@@ -994,12 +1067,14 @@ int dmlmc_set_smoother(dmlmc_hier* h, int level, int nfactors, const double* nu_
 }
 
 int dmlmc_set_smoother_storage(dmlmc_hier* h, int level, int allow16) {
+  if (h) invalidate_graphs(h);
   CHECK(h && level >= 0 && level < h->n_levels, "set_smoother_storage: bad handle/level");
   h->lv[level].smoother16 = allow16 != 0;
   return 0;
 }
 
 int dmlmc_set_perm(dmlmc_hier* h, int level, int shift, int nnz_per_row, const int32_t* cols_host, const double* vals_host) {
+  if (h) invalidate_graphs(h);
   CHECK(h && level >= 0 && level < h->n_levels, "set_perm: bad handle/level");
   Level& L = h->lv[level];
   CHECK(L.n > 0, "set_perm: set the level's operator first");
@@ -1119,11 +1194,13 @@ size_t dmlmc_workspace_bytes(dmlmc_hier* h, int level, int k, int restart) {
   return b + (1 << 20);
 }
 int dmlmc_set_workspace(dmlmc_hier* h, void* ws_dev, size_t bytes) {
+  if (h) invalidate_graphs(h);
   CHECK(h != nullptr, "NULL handle");
   h->ws = (char*)ws_dev; h->ws_bytes = bytes; h->ws_off = 0;
   return 0;
 }
 int dmlmc_set_inner_precision(dmlmc_hier* h, int prec) {
+  if (h) invalidate_graphs(h);
   CHECK(h != nullptr, "NULL handle"); CHECK_PREC(prec);
   h->inner_prec = prec;
   return 0;
@@ -1163,7 +1240,10 @@ int dmlmc_level_sample_host(dmlmc_hier* h, int method, int level_f, int level_c,
   return rc;
 }
 int dmlmc_set_option(dmlmc_hier* h, const char* name, double value) {
+  if (h) invalidate_graphs(h);
   CHECK(h != nullptr && name != nullptr, "set_option: bad arguments");
+  if (std::strcmp(name, "use_graphs") == 0) { h->use_graphs = value != 0.0; return 0; }
+  if (std::strcmp(name, "graph_max_k") == 0) { h->graph_max_k = (int)value; return 0; }
   if (std::strcmp(name, "reorth") == 0) { h->reorth = value != 0.0 ? 1 : 0; return 0; }
   if (std::strcmp(name, "chunk_cols") == 0) { h->chunk_cols = (int)value; return 0; }
   if (std::strcmp(name, "l2_budget_mb") == 0) { CHECK(value >= 0, "l2_budget_mb must be >= 0"); h->l2_budget_mb = value; return 0; }

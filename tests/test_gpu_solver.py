@@ -202,3 +202,20 @@ def test_deflated_mlmc_level_samples_16_match_reference(mg16, g16defl):
         assert np.abs(e - ref).max() < 1e-8 * max(np.abs(ref).max(), 1.0), ix
     mg.dev.set_deflation(0, None); mg.dev.set_deflation(1, None)
     mg.__dict__.pop("_defl_cache", None)
+
+
+@pytest.mark.parametrize("k", [1, 8, 48])
+def test_cuda_graph_replay_of_the_vcycle_is_bit_identical(mg128, k):
+    """small batches replay the V-cycle's launch sequence as a CUDA graph (eager, capture, replay, replay ...):
+    the solutions and iteration counts must equal the eager path's bit for bit, on levels 0 and 2"""
+    mg, tp, A = mg128
+    for lvl, n in ((0, 32768), (2, 2048)):
+        B = torch.from_numpy(np.ascontiguousarray(probes(n, k, seed=77 + k))).cuda()
+        mg.dev.set_option("use_graphs", 0)
+        X0, it0, rr0 = mg.dev.fgmres(lvl, B, 1e-12)
+        mg.dev.set_option("use_graphs", 1)
+        X1, it1, rr1 = mg.dev.fgmres(lvl, B, 1e-12)
+        X2, it2, rr2 = mg.dev.fgmres(lvl, B, 1e-12)          # graphs already instantiated: replay from the first iteration
+        assert torch.equal(X0, X1) and torch.equal(X0, X2)
+        assert np.array_equal(it0, it1) and np.array_equal(it0, it2)
+        assert np.all(rr1 < 1.3e-12)
