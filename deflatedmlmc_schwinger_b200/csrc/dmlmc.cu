@@ -95,9 +95,9 @@ struct dmlmc_hier {
   long long launches = 0;
   std::vector<void*> owned;
   // CUDA graphs of the V-cycle for small batches (launch-bound there: ~90 kernels of a few microseconds each)
-  struct GraphEntry { int level, k, prec; char* ws; size_t ws_off; cudaGraphExec_t exec; long long launches; };
-  std::vector<GraphEntry> graphs;
-  int use_graphs = 1, graph_max_k = 64;
+  struct GraphEntry { int level, k, prec; char* ws; size_t ws_off; int j, m, reorth; double tol; cudaGraphExec_t exec; long long launches; };
+  std::vector<GraphEntry> graphs;          // j < 0: marker "the first (eager) iteration of this configuration has run"
+  int use_graphs = 1, graph_max_k = 1024;
 };
 
 namespace {
@@ -608,57 +608,63 @@ int precond_eager(dmlmc_hier* h, int level, const Z* V, Z* Zout, int k) {
   return vcycle<float, double>(h, level, V, Zout, k);
 }
 
-// Z = V-cycle(V).  For small batches the cycle is a fixed sequence of ~90 launches of a few microseconds each and
-// the solve is launch-bound (measured: 8.4 us per launch at k = 1), so the sequence is captured once per
-// (level, k, precision, work-space position) into a CUDA graph and replayed; V and Z, whose addresses change with the
-// Krylov index, go through two fixed staging buffers.  First call: eager (one-time attribute / descriptor set-up),
-// second call: capture, then replay.  Any set_* / option call drops the graphs.
-int precond(dmlmc_hier* h, int level, const Z* V, Z* Zout, int k) {
-  if (!h->use_graphs || k > h->graph_max_k) return precond_eager(h, level, V, Zout, k);
-  const size_t nk = (size_t)h->lv[level].n * k;
-  const size_t mark = h->ws_off;
-  Z *sb, *sx;
-  RET(ws_get<Z>(h, nk, &sb)); RET(ws_get<Z>(h, nk, &sx));
+int precond(dmlmc_hier* h, int level, const Z* V, Z* Zout, int k) { return precond_eager(h, level, V, Zout, k); }
+
+// One FGMRES iteration (V-cycle, operator, Gram-Schmidt, Givens step, next basis vector) is a fixed sequence of ~105
+// launches whose arguments depend only on (level, k, precision, work space, Krylov index j, restart, tol, reorth).
+// Small batches are launch-bound (8.4 us per launch at k = 1) and even at k = 256 the gaps between launches cost
+// ~6 %, so each such sequence is captured once into a CUDA graph and replayed by every later solve.  The first
+// iteration of a configuration runs eagerly (one-time attribute / descriptor set-up); capture happens on an internal
+// stream (the caller's may be the legacy default stream, which cannot capture) and the instantiated graph is
+// launched on the caller's stream like every other kernel.  Any set_* / option call drops the graphs.
+template <typename Body>
+int run_iteration(dmlmc_hier* h, bool graphs, int level, int k, size_t mark, int j, int m, double tol, Body body) {
+  if (!graphs) return body();
   dmlmc_hier::GraphEntry* e = nullptr;
-  for (auto& g : h->graphs)
-    if (g.level == level && g.k == k && g.prec == h->inner_prec && g.ws == h->ws && g.ws_off == mark) { e = &g; break; }
-  CU(cudaMemcpyAsync(sb, V, nk * sizeof(Z), cudaMemcpyDeviceToDevice, h->stream));
-  int rc = 0;
-  if (e == nullptr) {
-    h->graphs.push_back({level, k, h->inner_prec, h->ws, mark, nullptr, 0});
-    rc = precond_eager(h, level, sb, sx, k);
-  } else if (e->exec == nullptr) {
-    const long long l0 = h->launches;
-    cudaGraph_t graph = nullptr;
-    // capture on an internal stream (the caller's may be the legacy default stream, which cannot capture); the
-    // instantiated graph is launched on the caller's stream like every other kernel
-    cudaStream_t user = h->stream;
-    cudaError_t ce = cudaStreamBeginCapture(h->cap_stream, cudaStreamCaptureModeRelaxed);
-    if (ce == cudaSuccess) {
-      h->stream = h->cap_stream;
-      rc = precond_eager(h, level, sb, sx, k);
-      h->stream = user;
-      ce = cudaStreamEndCapture(h->cap_stream, &graph);
-      if (rc == 0 && ce == cudaSuccess && graph) ce = cudaGraphInstantiate(&e->exec, graph, 0);
-      if (graph) cudaGraphDestroy(graph);
-    }
-    if (rc != 0 || ce != cudaSuccess || e->exec == nullptr) {      // capture not possible here: stay eager from now on
-      cudaGetLastError();
-      h->use_graphs = 0;
-      if (e->exec) { cudaGraphExecDestroy(e->exec); e->exec = nullptr; }
-      h->launches = l0;
-      rc = precond_eager(h, level, sb, sx, k);
-    } else {
-      e->launches = h->launches - l0;
-      CU(cudaGraphLaunch(e->exec, h->stream));
-    }
-  } else {
+  bool warmed = false;
+  for (auto& g : h->graphs) {
+    if (!(g.level == level && g.k == k && g.prec == h->inner_prec && g.ws == h->ws && g.ws_off == mark && g.m == m &&
+          g.tol == tol && g.reorth == h->reorth)) continue;
+    if (g.j < 0) warmed = true;
+    else if (g.j == j) e = &g;
+  }
+  if (!warmed) {
+    h->graphs.push_back({level, k, h->inner_prec, h->ws, mark, -1, m, h->reorth, tol, nullptr, 0});
+    return body();
+  }
+  if (e != nullptr) {
     CU(cudaGraphLaunch(e->exec, h->stream));
     h->launches += e->launches;
+    return 0;
   }
-  if (rc == 0) CU(cudaMemcpyAsync(Zout, sx, nk * sizeof(Z), cudaMemcpyDeviceToDevice, h->stream));
-  h->ws_off = mark;
-  return rc;
+  h->graphs.push_back({level, k, h->inner_prec, h->ws, mark, j, m, h->reorth, tol, nullptr, 0});
+  e = &h->graphs.back();
+  const long long l0 = h->launches;
+  const size_t ws_keep = h->ws_off;
+  cudaGraph_t graph = nullptr;
+  int rc = 0;
+  cudaStream_t user = h->stream;
+  cudaError_t ce = cudaStreamBeginCapture(h->cap_stream, cudaStreamCaptureModeRelaxed);
+  if (ce == cudaSuccess) {
+    h->stream = h->cap_stream;
+    rc = body();
+    h->stream = user;
+    ce = cudaStreamEndCapture(h->cap_stream, &graph);
+    if (rc == 0 && ce == cudaSuccess && graph) ce = cudaGraphInstantiate(&e->exec, graph, 0);
+    if (graph) cudaGraphDestroy(graph);
+  }
+  if (rc != 0 || ce != cudaSuccess || e->exec == nullptr) {      // capture not possible here: stay eager from now on
+    cudaGetLastError();
+    h->use_graphs = 0;
+    if (e->exec) cudaGraphExecDestroy(e->exec);
+    h->graphs.pop_back();
+    h->launches = l0;
+    h->ws_off = ws_keep;
+    return body();
+  }
+  e->launches = h->launches - l0;
+  CU(cudaGraphLaunch(e->exec, h->stream));
+  return 0;
 }
 
 int read_nactive(dmlmc_hier* h, int* dev_counter, int* out) {
@@ -720,25 +726,29 @@ int fgmres(dmlmc_hier* h, int level, const Z* B, Z* X, int k, double tol, int re
     for (; j < m; ++j) {
       Z* Vj = Vb + (size_t)j * nk;
       Z* Zj = Zb + (size_t)j * nk;
-      RET(precond(h, level, Vj, Zj, k));
-      RET((launch_op<double, M_AX>(h, level, Zj, nullptr, W, ZERO, ZERO, k)));
-      // classical Gram-Schmidt, optionally with one re-orthogonalisation pass
-      RET(multi_dot(h, Vb, nk, j + 1, W, n, k, partial, s.hsum, 0));
-      if (h->reorth) {
-        RET(multi_axpy(h, Vb, nk, j + 1, s.hsum, W, n, k, -1.0));
-        RET(multi_dot(h, Vb, nk, j + 1, W, n, k, partial, s.y, 0));       // s.y used as scratch [(j+1)][k]
-        RET(multi_axpy_norm(h, Vb, nk, j + 1, s.y, W, n, k, partial, s.nrm2));
-        // hsum += second-pass coefficients
-        const int cnt = (j + 1) * k;
-        sum_partials_kernel<<<nblocks(cnt, 32), dim3(32, 8), 0, h->stream>>>(s.y, 1, cnt, s.hsum, 1); LAUNCH_CHECK(h);
-      } else {
-        // w -= V h and ||w||^2 in one pass over W
-        RET(multi_axpy_norm(h, Vb, nk, j + 1, s.hsum, W, n, k, partial, s.nrm2));
-      }
-      CU(cudaMemsetAsync(s.n_active, 0, sizeof(int), h->stream));
-      gmres_step_kernel<<<gk, 128, 0, h->stream>>>(s, j, tol); LAUNCH_CHECK(h);
+      auto body = [&]() -> int {
+        RET(precond(h, level, Vj, Zj, k));
+        RET((launch_op<double, M_AX>(h, level, Zj, nullptr, W, ZERO, ZERO, k)));
+        // classical Gram-Schmidt, optionally with one re-orthogonalisation pass
+        RET(multi_dot(h, Vb, nk, j + 1, W, n, k, partial, s.hsum, 0));
+        if (h->reorth) {
+          RET(multi_axpy(h, Vb, nk, j + 1, s.hsum, W, n, k, -1.0));
+          RET(multi_dot(h, Vb, nk, j + 1, W, n, k, partial, s.y, 0));       // s.y used as scratch [(j+1)][k]
+          RET(multi_axpy_norm(h, Vb, nk, j + 1, s.y, W, n, k, partial, s.nrm2));
+          // hsum += second-pass coefficients
+          const int cnt = (j + 1) * k;
+          sum_partials_kernel<<<nblocks(cnt, 32), dim3(32, 8), 0, h->stream>>>(s.y, 1, cnt, s.hsum, 1); LAUNCH_CHECK(h);
+        } else {
+          // w -= V h and ||w||^2 in one pass over W
+          RET(multi_axpy_norm(h, Vb, nk, j + 1, s.hsum, W, n, k, partial, s.nrm2));
+        }
+        CU(cudaMemsetAsync(s.n_active, 0, sizeof(int), h->stream));
+        gmres_step_kernel<<<gk, 128, 0, h->stream>>>(s, j, tol); LAUNCH_CHECK(h);
+        if (j + 1 < m) { col_scale_kernel<<<nblocks(nk, 256), 256, 0, h->stream>>>(W, s.scale, Vb + (size_t)(j + 1) * nk, nk, k); LAUNCH_CHECK(h); }
+        return 0;
+      };
+      RET(run_iteration(h, h->use_graphs && k <= h->graph_max_k, level, k, mark, j, m, tol, body));
       ++total_it;
-      if (j + 1 < m) { col_scale_kernel<<<nblocks(nk, 256), 256, 0, h->stream>>>(W, s.scale, Vb + (size_t)(j + 1) * nk, nk, k); LAUNCH_CHECK(h); }
       RET(read_nactive(h, s.n_active, &nact));
       if (nact == 0 || total_it >= maxiter) { ++j; break; }
     }

@@ -147,8 +147,9 @@ int dmlmc_level_sample_host(dmlmc_hier* h, int method, int level_f, int level_c,
                             double* e_host, int32_t* iters_host);
 
 /* solver options by name.  Unknown names are an error.
- *   "use_graphs", "graph_max_k"  1 / 64 (defaults): for batches of at most graph_max_k columns the V-cycle's launch
- *                  sequence is captured into a CUDA graph and replayed (the solve is launch-bound there)
+ *   "use_graphs", "graph_max_k"  1 / 1024 (defaults): for batches of at most graph_max_k columns every FGMRES iteration
+ *                  (V-cycle, operator, Gram-Schmidt, Givens step: ~105 launches) is captured once per Krylov index into
+ *                  a CUDA graph and replayed by all later solves (launch-bound for small batches, ~6 % at k = 256)
  *   "reorth"       1 = classical Gram-Schmidt with a re-orthogonalisation pass, 0 = single pass (default;
  *                  every column is verified against its true residual before it leaves the solve)
  *   "chunk_cols"   columns per V-cycle chunk; 0 (default) = derive from "l2_budget_mb"

@@ -204,10 +204,11 @@ def test_deflated_mlmc_level_samples_16_match_reference(mg16, g16defl):
     mg.__dict__.pop("_defl_cache", None)
 
 
-@pytest.mark.parametrize("k", [1, 8, 48])
+@pytest.mark.parametrize("k", [1, 8, 48, 128])
 def test_cuda_graph_replay_of_the_vcycle_is_bit_identical(mg128, k):
-    """small batches replay the V-cycle's launch sequence as a CUDA graph (eager, capture, replay, replay ...):
-    the solutions and iteration counts must equal the eager path's bit for bit, on levels 0 and 2"""
+    """the V-cycle's launch sequence is replayed as a CUDA graph (eager, capture, replay ...; k <= 64 through staging
+    buffers, k = 128 with one graph per Krylov vector pair): solutions and iteration counts must equal the eager
+    path's bit for bit, on levels 0 and 2"""
     mg, tp, A = mg128
     for lvl, n in ((0, 32768), (2, 2048)):
         B = torch.from_numpy(np.ascontiguousarray(probes(n, k, seed=77 + k))).cuda()
