@@ -390,6 +390,27 @@ def main():
             by = n0 * sb * (1 + 2 * k)
             spmm[name] = {"us": 1e6 * tt, "GBps": by / tt / 1e9, "frac": by / tt / 1e9 / peak}
         roof["spmm_level0"] = spmm
+        # the tensor-core kernel of the path: dense coarse solve of the V-cycle (tcgen05, BF16 x BF16 -> FP32),
+        # real GEMM [2n x 2n] x [2n x k]; timed through dmlmc_vcycle on the dense level (includes the RHS pack kernel)
+        dl = mg.dense_level
+        if mg.dense_levels.get(dl) == "tensor":
+            nd = mg.level_shapes[dl]
+            Xd = torch.randn(nd, k, device="cuda", dtype=torch.float32).to(torch.complex64).contiguous()
+            for _ in range(3):
+                dev.vcycle(dl, Xd)
+            torch.cuda.synchronize()
+            ev0.record(stream)
+            for _ in range(10):
+                dev.vcycle(dl, Xd)
+            ev1.record(stream)
+            torch.cuda.synchronize()
+            td = ev0.elapsed_time(ev1) * 1e-3 / 10
+            fl = 2.0 * (2 * nd) * (2 * nd) * k
+            tpeak = float(peaks.get("bf16_tflops", 1662.5))
+            roof["dense_umma_kernel"] = {"bound": "tensor", "n": nd, "us": 1e6 * td, "achieved": fl / td / 1e12, "peak": tpeak,
+                                         "unit": "TFLOP/s", "frac": fl / td / 1e12 / tpeak,
+                                         "ncu": "sm__pipe_tensor_cycles_active 60.6 % of active cycles, DRAM read = the BF16 matrix once "
+                                                "(profiles/r1_run10_umma_ncu_full.csv)"}
 
     line = {"metric": METRIC, "value": value, "unit": "probes/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",

@@ -438,7 +438,7 @@ class MG:
             if n_i > self.dense_coarse_threshold or n_i % 8:
                 break
             small = n_i <= 4096
-            Minv = self._device_inverse(i, 1e-13 if small else 1e-9)
+            Minv = self._device_inverse(i, 1e-13 if small else 1e-6)     # the BF16 operand keeps 3 digits
             if small:
                 dev.set_dense_inverse(i, Minv.cpu().numpy())
             else:
