@@ -358,8 +358,8 @@ def main():
         alg_bytes = 2 * n0 * kc * sb + 4 * (n0 // 2) * 16
         achieved = alg_bytes / t_step / 1e9
         roof = {"bound": "hbm",
-                "kernel": "stencil_step_bf16_kernel (level-0 operator + polynomial-factor update x' = x - nu A x of the "
-                          "complex64 V-cycle, BF16-stored vectors, FP32 packed arithmetic, %d columns)" % kc,
+                "kernel": "stencil_step_bf16_t2_kernel (level-0 operator + polynomial-factor update x' = x - nu A x of the "
+                          "complex64 V-cycle, BF16-stored vectors, FP32 packed arithmetic, two sites per thread, %d columns)" % kc,
                 "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                 "peak_source": "MEASURED_PEAKS.json hbm_gbs" if "hbm_gbs" in peaks else "fallback 6650",
                 "frac_of_nominal_8TBs": achieved / 8000.0,

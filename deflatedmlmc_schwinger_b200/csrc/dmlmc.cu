@@ -76,6 +76,8 @@ struct dmlmc_hier {
   int reorth = 0;
   int stencil_by = 4, stencil_bz = 4;     // site tile (t, x) of the stencil kernel's thread block
   int bsr_threads = 128;                  // threads per CTA of the packed-FP32 BSR kernel (block rows per CTA = this / threads per row)
+  int stencil_t2 = 1;                     // two t-adjacent sites per thread in the factor kernel
+  int stencil_t2_by = 2, stencil_t2_bz = 2;   // its thread-block tile: (32 packs, 2 thread rows = 4 sites in t, 2 in x)
   int stencil_smem = 0;                   // shared-memory-tiled variant of the packed-FP32 factor kernel
   int stencil_fast = 1;                   // packed-FP32 (FFMA2) kernel for the BF16-stored smoother factors
   int prefetch_slices = 16;               // Y = A X / B - A X on level 0: L2 prefetch distance in x-slices (0, 8, 16)
@@ -423,6 +425,18 @@ int smooth_apply(dmlmc_hier* h, int level, const void* R, void* E, bool acc, voi
               continue;
             }
             const long long rowb = (long long)kp * 8;
+            if (h->stencil_t2 && (L.LT % 2) == 0) {
+              int bx2 = 1; while (bx2 < 32 && bx2 < kp) bx2 *= 2;
+              int by2 = std::max(1, std::min(h->stencil_t2_by, L.LT / 2)), bz2 = std::max(1, std::min(h->stencil_t2_bz, L.LX));
+              while (bx2 * by2 * bz2 > 256) { if (bz2 > 1) bz2 /= 2; else by2 /= 2; }
+              dim3 blk2(bx2, by2, bz2), grd2((kp + bx2 - 1) / bx2, (L.LT / 2 + by2 - 1) / by2, (L.LX + bz2 - 1) / bz2);
+              stencil_step_bf16_t2_kernel<<<grd2, blk2, 0, h->stream>>>(L.LX, L.LT, L.links4, (float)L.d.diag.re, (const uint2*)in,
+                                                                      (uint2*)out, (float)L.nu[i].re, (float)L.nu[i].im, (uint32_t)kp,
+                                                                      rowb, rowb * L.LT, rowb * L.LT * L.LX);
+              LAUNCH_CHECK(h);
+              in = out;
+              continue;
+            }
             int bx = 1; while (bx < 32 && bx < kp) bx *= 2;
             int by = std::max(1, std::min(h->stencil_by, L.LT)), bz = std::max(1, std::min(h->stencil_bz, L.LX));
             while (bx * by * bz > 512) { if (bz > 1) bz /= 2; else by /= 2; }
@@ -1260,6 +1274,9 @@ int dmlmc_set_option(dmlmc_hier* h, const char* name, double value) {
   if (std::strcmp(name, "stencil_by") == 0) { CHECK(value >= 1, "stencil_by must be >= 1"); h->stencil_by = (int)value; return 0; }
   if (std::strcmp(name, "defl_tensor") == 0) { h->defl_tensor = value != 0.0; return 0; }
   if (std::strcmp(name, "bsr_threads") == 0) { CHECK(value >= 32 && value <= 256, "bsr_threads must be in [32, 256]"); h->bsr_threads = (int)value; return 0; }
+  if (std::strcmp(name, "stencil_t2") == 0) { h->stencil_t2 = value != 0.0; return 0; }
+  if (std::strcmp(name, "stencil_t2_by") == 0) { CHECK(value >= 1, "stencil_t2_by must be >= 1"); h->stencil_t2_by = (int)value; return 0; }
+  if (std::strcmp(name, "stencil_t2_bz") == 0) { CHECK(value >= 1, "stencil_t2_bz must be >= 1"); h->stencil_t2_bz = (int)value; return 0; }
   if (std::strcmp(name, "stencil_smem") == 0) { h->stencil_smem = value != 0.0; return 0; }
   if (std::strcmp(name, "stencil_fast") == 0) { h->stencil_fast = value != 0.0; return 0; }
   if (std::strcmp(name, "prefetch_slices") == 0) { h->prefetch_slices = (int)value; return 0; }

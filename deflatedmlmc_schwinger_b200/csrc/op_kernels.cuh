@@ -236,6 +236,75 @@ stencil_step_bf16_kernel(int LX, int LT, const float4* __restrict__ L4, float di
   sth_c2(reinterpret_cast<uint2*>(py + spb), 0u, o1);
 }
 
+// site arithmetic shared by the factor-kernel variants: o = c - w (A c) for both spin components
+__device__ __forceinline__ void wilson_step_site(const C2& c0, const C2& c1, const C2& f0, const C2& f1, const C2& b0, const C2& b1,
+                                                 const C2& r0, const C2& r1, const C2& l0, const C2& l1,
+                                                 const float4& ut, const float4& utb, const float4& ux, const float4& uxb,
+                                                 float2 dg, float2 w_r, float2 w_i, C2& o0, C2& o1) {
+  C2 a, b, c, d;
+  a.re = __fadd2_rn(f0.re, neg2(f1.re)); a.im = __fadd2_rn(f0.im, neg2(f1.im));
+  b.re = __fadd2_rn(b0.re, b1.re);       b.im = __fadd2_rn(b0.im, b1.im);
+  c.re = __fadd2_rn(r0.re, neg2(r1.im)); c.im = __fadd2_rn(r0.im, r1.re);
+  d.re = __fadd2_rn(l0.re, l1.im);       d.im = __fadd2_rn(l0.im, neg2(l1.re));
+  const C2 ua = cmul_splat(ut, a), ub = cmul_splat(utb, b), uc = cmul_splat(ux, c), ud = cmul_splat(uxb, d);
+  C2 s, q, tt, y0, y1;
+  s.re = __fadd2_rn(__fadd2_rn(ua.re, ub.re), __fadd2_rn(uc.re, ud.re));
+  s.im = __fadd2_rn(__fadd2_rn(ua.im, ub.im), __fadd2_rn(uc.im, ud.im));
+  q.re = __fadd2_rn(ua.re, neg2(ub.re));  q.im = __fadd2_rn(ua.im, neg2(ub.im));
+  tt.re = __fadd2_rn(uc.re, neg2(ud.re)); tt.im = __fadd2_rn(uc.im, neg2(ud.im));
+  y0.re = __ffma2_rn(dg, c0.re, neg2(s.re));
+  y0.im = __ffma2_rn(dg, c0.im, neg2(s.im));
+  y1.re = __ffma2_rn(dg, c1.re, __fadd2_rn(q.re, neg2(tt.im)));
+  y1.im = __ffma2_rn(dg, c1.im, __fadd2_rn(q.im, tt.re));
+  o0.re = __ffma2_rn(w_i, y0.im, __ffma2_rn(neg2(w_r), y0.re, c0.re));
+  o0.im = __ffma2_rn(neg2(w_i), y0.re, __ffma2_rn(neg2(w_r), y0.im, c0.im));
+  o1.re = __ffma2_rn(w_i, y1.im, __ffma2_rn(neg2(w_r), y1.re, c1.re));
+  o1.im = __ffma2_rn(neg2(w_i), y1.re, __ffma2_rn(neg2(w_r), y1.im, c1.im));
+}
+
+// Two t-adjacent sites per thread (option "stencil_t2", default): site t's forward neighbour is site t+1's centre and
+// vice versa, so the pair needs 8 site rows instead of 10 (-20 % loads and BF16 conversions) and shares the address
+// arithmetic: 20.5 -> ~17 us per launch at k = 256, the bench step 42.7 -> 38.1 ms.  (A 2 x 2 sites-per-thread variant,
+// 12 rows for 4 sites but 138 registers, measured the same 39.0 ms and was dropped; profiles/r1_run19_*.)
+__global__ void __launch_bounds__(256, 2)
+stencil_step_bf16_t2_kernel(int LX, int LT, const float4* __restrict__ L4, float diag,
+                            const uint2* __restrict__ X, uint2* __restrict__ Y, float wr, float wi, uint32_t kp,
+                            long long rowb, long long ltb, long long spb) {
+  const uint32_t cp = blockIdx.x * blockDim.x + threadIdx.x;
+  const uint32_t t = 2 * (blockIdx.y * blockDim.y + threadIdx.y);
+  const uint32_t x = blockIdx.z * blockDim.z + threadIdx.z;
+  if (cp >= kp || t >= (uint32_t)LT || x >= (uint32_t)LX) return;
+  const uint32_t V = (uint32_t)LX * LT;
+  const uint32_t site = x * LT + t;
+  const float4* lp = L4 + site;
+  const float4 ut0 = __ldg(lp), utb0 = __ldg(lp + V), ux0 = __ldg(lp + 2 * V), uxb0 = __ldg(lp + 3 * V);
+  const float4 ut1 = __ldg(lp + 1), utb1 = __ldg(lp + V + 1), ux1 = __ldg(lp + 2 * V + 1), uxb1 = __ldg(lp + 3 * V + 1);
+  const long long d_tp2 = (t + 2 == (uint32_t)LT) ? 2 * rowb - ltb : 2 * rowb;     // row of site t+2
+  const long long d_tm = (t == 0) ? ltb - rowb : -rowb;
+  const long long d_xp = (x + 1 == (uint32_t)LX) ? ltb - spb : ltb;
+  const long long d_xm = (x == 0) ? spb - ltb : -ltb;
+  const uint32_t ic = site * kp + cp;
+  const char* pc = reinterpret_cast<const char*>(X) + (size_t)ic * 8;
+  auto ld = [](const char* p) { return ldh_c2(reinterpret_cast<const uint2*>(p), 0u); };
+  const C2 a0 = ld(pc),          a1 = ld(pc + spb);                  // site t
+  const C2 e0 = ld(pc + rowb),   e1 = ld(pc + rowb + spb);           // site t+1
+  const C2 m0 = ld(pc + d_tm),   m1 = ld(pc + d_tm + spb);           // site t-1
+  const C2 p0 = ld(pc + d_tp2),  p1 = ld(pc + d_tp2 + spb);          // site t+2
+  const C2 ra0 = ld(pc + d_xp),  ra1 = ld(pc + d_xp + spb);          // x+1 of site t
+  const C2 re0 = ld(pc + d_xp + rowb), re1 = ld(pc + d_xp + rowb + spb);
+  const C2 la0 = ld(pc + d_xm),  la1 = ld(pc + d_xm + spb);          // x-1 of site t
+  const C2 le0 = ld(pc + d_xm + rowb), le1 = ld(pc + d_xm + rowb + spb);
+  const float2 dg = make_float2(diag, diag), w_r = make_float2(wr, wr), w_i = make_float2(wi, wi);
+  C2 o0, o1, q0, q1;
+  wilson_step_site(a0, a1, e0, e1, m0, m1, ra0, ra1, la0, la1, ut0, utb0, ux0, uxb0, dg, w_r, w_i, o0, o1);
+  wilson_step_site(e0, e1, p0, p1, a0, a1, re0, re1, le0, le1, ut1, utb1, ux1, uxb1, dg, w_r, w_i, q0, q1);
+  char* py = reinterpret_cast<char*>(Y) + (size_t)ic * 8;
+  sth_c2(reinterpret_cast<uint2*>(py), 0u, o0);
+  sth_c2(reinterpret_cast<uint2*>(py + spb), 0u, o1);
+  sth_c2(reinterpret_cast<uint2*>(py + rowb), 0u, q0);
+  sth_c2(reinterpret_cast<uint2*>(py + rowb + spb), 0u, q1);
+}
+
 // Shared-memory-tiled variant of the same factor kernel (option "stencil_smem", OFF by default: measured on B200 at
 // k = 256 it needs 26.5 us per launch against 20.5 us for the L1-cached direct-load kernel above -- the load / barrier /
 // compute phases of a CTA do not overlap as well as 48 independent warps per SM do; profiles/r1_run17_*).

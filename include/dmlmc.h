@@ -169,6 +169,8 @@ int dmlmc_level_sample_host(dmlmc_hier* h, int method, int level_f, int level_c,
  *                  (mma.sync m8n8k4.f64) when d is a multiple of 4 and <= 64; 0: SIMT kernels
  *   "dense_direct_exact"  1 (default): a V-cycle that STARTS on a dense level (that level's own solve) uses
  *                  the FP32 copy of the inverse when there is one; 0: tensor cores there as well
+ *   "stencil_t2"   1 (default): the BF16 factor kernel computes two t-adjacent sites per thread (8 row loads per pair
+ *                  instead of 10); "stencil_t2_by", "stencil_t2_bz": its thread-block tile (default 2 x 2)
  *   "stencil_by", "stencil_bz"   site tile (t, x) of the level-0 kernel's thread block (default 4 x 4)
  *   "stencil_minb" 2 | 3 (default): resident 512-thread blocks per SM the level-0 kernel is compiled for */
 int dmlmc_set_option(dmlmc_hier* h, const char* name, double value);

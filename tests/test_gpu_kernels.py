@@ -167,6 +167,11 @@ def test_smoother_is_the_polynomial(mg128, dtype):
                 Es = mg.dev.smooth(lvl, R)
                 mg.dev.set_option("stencil_smem", 0)
                 assert relerr(host(Es), host(E)) < 1e-6, "smem variant"
+                for t2 in (0, 1):                               # 1 / 2 sites per thread: same arithmetic
+                    mg.dev.set_option("stencil_t2", t2)
+                    Et = mg.dev.smooth(lvl, R)
+                    assert relerr(host(Et), host(E)) < 1e-6, "sites-per-thread variant %d" % t2
+                mg.dev.set_option("stencil_t2", 1)
             mg.dev.set_option("smoother_half", 0)
             E = mg.dev.smooth(lvl, R)
             mg.dev.set_option("smoother_half", 1)
