@@ -28,6 +28,9 @@ _SIGS = {
                                      ctypes.c_void_p, ctypes.c_void_p]),
     "dmlmc_set_transfer": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int,
                                           ctypes.c_int, ctypes.c_void_p]),
+    "dmlmc_set_transfer_indexed": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int,
+                                                  ctypes.c_void_p, ctypes.c_void_p]),
+    "dmlmc_set_preconditioner": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p, ctypes.c_int]),
     "dmlmc_set_coarsest_inverse": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p]),
     "dmlmc_set_dense_inverse": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_void_p]),
     "dmlmc_set_dense_inverse_device": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_void_p]),
@@ -84,7 +87,7 @@ def load():
         fn = getattr(lib, name)          # AttributeError if the ABI is incomplete
         fn.restype = res
         fn.argtypes = args
-    if lib.dmlmc_abi_version() != 2:
+    if lib.dmlmc_abi_version() != 3:
         raise RuntimeError("libdmlmc_sm100.so ABI version mismatch")
     _lib = lib
     return lib
@@ -159,6 +162,20 @@ class Hierarchy:
         pvals, p = _host_c128(pvals)
         assert pvals.shape == (n_f, nvec)
         _check(self.lib.dmlmc_set_transfer(self.h, level, n_f, aggr_size, dofi, nvec, p))
+
+    def set_transfer_indexed(self, level, n_f, nvec, pvals, cblk):
+        """aggregation prolongator on arbitrary equal-sized aggregates: fine row r -> coarse block cblk[r]"""
+        pvals, p = _host_c128(pvals)
+        cblk, pc = _host_i32(cblk)
+        assert pvals.shape == (n_f, nvec) and cblk.shape == (n_f,)
+        _check(self.lib.dmlmc_set_transfer_indexed(self.h, level, n_f, int(cblk.max()) + 1, nvec, p, pc))
+
+    def set_preconditioner(self, level, other, other_level=0):
+        """FGMRES solves of `level` are preconditioned by the V-cycle of hierarchy `other` from its `other_level`"""
+        _check(self.lib.dmlmc_set_preconditioner(self.h, level, None if other is None else other.h, other_level))
+        self._prec_keepalive = getattr(self, "_prec_keepalive", {})
+        self._prec_keepalive[level] = other
+        self._ws_key = None          # the work space may have to grow
 
     def set_coarsest_inverse(self, minv):
         minv, p = _host_c128(minv)

@@ -49,6 +49,7 @@ struct Level {
   int bs = 0, bpr = 0, nb = 0; int* bsr_col = nullptr; float4* bsr_vals4 = nullptr;   // (mr,mr,mi,mi) per entry
   float4* links4 = nullptr;          // [4][V] (ur,ur,ui,ui): U_t(x), U_t(x-t)^*, U_x(x), U_x(x-x)^*
   bool has_transfer = false; int aggr = 0, dofi = 0, nvec = 0, n_c = 0;
+  int* tr_rows = nullptr; int* tr_cblk = nullptr; int tr_m = 0;     // indexed (geometric) aggregates, else closed form
   // smoother polynomial in product form: p(A) = p0 * prod_i (I - nu_i A)
   bool has_smoother = false; std::vector<Cx<double>> nu; Cx<double> p0; bool smoother16 = true;
   bool has_perm = false; int shift = 0, perm_nnz = 0; int* perm_cols = nullptr;
@@ -100,6 +101,9 @@ struct dmlmc_hier {
   struct GraphEntry { int level, k, prec; char* ws; size_t ws_off; int j, m, reorth; double tol; cudaGraphExec_t exec; long long launches; };
   std::vector<GraphEntry> graphs;          // j < 0: marker "the first (eager) iteration of this configuration has run"
   int use_graphs = 1, graph_max_k = 1024;
+  // optional separate preconditioner hierarchy per level (dmlmc_set_preconditioner): the V-cycle that preconditions
+  // this level's FGMRES runs on (prec_hier[level], prec_level[level]) instead of on this hierarchy's own levels
+  dmlmc_hier* prec_hier[MAX_LEVELS] = {}; int prec_level[MAX_LEVELS] = {};
 };
 
 namespace {
@@ -246,7 +250,7 @@ template <typename T, int NC>
 int launch_restrict_nc(dmlmc_hier* h, int level, const void* Xf, void* Xc, int k, int ldf, int ldc) {
   Level& L = h->lv[level];
   TransferDev<T> tr; tr.n_f = L.n; tr.n_c = L.n_c; tr.aggr = L.aggr; tr.dofi = L.dofi; tr.h = L.dofi / 2; tr.nvec = L.nvec;
-  tr.pv = Sel<T>::get(L).pv;
+  tr.pv = Sel<T>::get(L).pv; tr.rows = L.tr_rows; tr.cblk = L.tr_cblk; tr.m = L.tr_m;
   const int kp = k / NC; typedef Pack<T, NC> P;
   const size_t total = (size_t)(L.n_c / L.nvec) * kp;
   const unsigned g = nblocks(total, 128);
@@ -275,7 +279,7 @@ template <typename T, int NC>
 int launch_prolong_nc(dmlmc_hier* h, int level, const void* Xc, void* Xf, int k, int ldf, int ldc) {
   Level& L = h->lv[level];
   TransferDev<T> tr; tr.n_f = L.n; tr.n_c = L.n_c; tr.aggr = L.aggr; tr.dofi = L.dofi; tr.h = L.dofi / 2; tr.nvec = L.nvec;
-  tr.pv = Sel<T>::get(L).pv;
+  tr.pv = Sel<T>::get(L).pv; tr.rows = L.tr_rows; tr.cblk = L.tr_cblk; tr.m = L.tr_m;
   const int kp = k / NC; typedef Pack<T, NC> P;
   const size_t total = (size_t)L.n * kp;
   const unsigned g = nblocks(total, 256);
@@ -618,6 +622,18 @@ void invalidate_graphs(dmlmc_hier* h) {
 }
 
 int precond_eager(dmlmc_hier* h, int level, const Z* V, Z* Zout, int k) {
+  if (dmlmc_hier* hp = h->prec_hier[level]) {
+    // the preconditioner hierarchy works on the caller's stream (the capture stream while a graph is recorded)
+    // and in the caller's work space
+    cudaStream_t keep_stream = hp->stream; char* keep_ws = hp->ws; const size_t keep_bytes = hp->ws_bytes, keep_off = hp->ws_off;
+    const long long l0 = hp->launches;
+    hp->stream = h->stream; hp->ws = h->ws; hp->ws_bytes = h->ws_bytes; hp->ws_off = h->ws_off;
+    const int pl = h->prec_level[level];
+    const int rc = hp->inner_prec == DMLMC_C128 ? vcycle<double, double>(hp, pl, V, Zout, k) : vcycle<float, double>(hp, pl, V, Zout, k);
+    h->launches += hp->launches - l0;
+    hp->stream = keep_stream; hp->ws = keep_ws; hp->ws_bytes = keep_bytes; hp->ws_off = keep_off;
+    return rc;
+  }
   if (h->inner_prec == DMLMC_C128) return vcycle<double, double>(h, level, V, Zout, k);
   return vcycle<float, double>(h, level, V, Zout, k);
 }
@@ -921,7 +937,9 @@ size_t fgmres_bytes(dmlmc_hier* h, int level, int k, int m) {
   b += align_up(nk * (m + 1) * z) + align_up(nk * m * z) + 2 * align_up(nk * z);
   b += align_up(partial_count((int)n, m + 1, k) * z);
   b += align_up((size_t)m * m * k * z) + 6 * align_up((size_t)(m + 1) * k * z) + 16 * align_up((size_t)k * 16);
-  b += vcycle_bytes(h, level, k, sizeof(Z));
+  size_t vb = vcycle_bytes(h, level, k, sizeof(Z));
+  if (h->prec_hier[level]) vb = std::max(vb, vcycle_bytes(h->prec_hier[level], h->prec_level[level], k, sizeof(Z)) + (size_t)(1 << 16));
+  b += vb;
   b += 2 * align_up(nk * z);          // staging buffers of the graph-replayed V-cycle
   return b + (1 << 16);
 }
@@ -1035,6 +1053,41 @@ int dmlmc_set_transfer(dmlmc_hier* h, int level, int n_f, int aggr_size, int dof
   CHECK(L.n == 0 || L.n == n_f, "set_transfer: n_f does not match the level's operator");
   L.n = n_f; L.has_transfer = true; L.aggr = aggr_size; L.dofi = dofi; L.nvec = nvec; L.n_c = (n_f / aggr_size) * 2 * nvec;
   RET(upload_cx(h, pvals_host, (size_t)n_f * nvec, &L.d.pv, &L.f.pv));
+  return 0;
+}
+
+int dmlmc_set_transfer_indexed(dmlmc_hier* h, int level, int n_f, int n_blocks, int nvec, const double* pvals_host,
+                               const int32_t* cblk_host) {
+  if (h) invalidate_graphs(h);
+  CHECK(h && level >= 0 && level < h->n_levels - 1, "set_transfer_indexed: bad handle/level");
+  CHECK(nvec == 1 || nvec == 2 || nvec == 4 || nvec == 8, "set_transfer_indexed: nvec must be 1, 2, 4 or 8");
+  CHECK(n_f > 0 && n_blocks > 0 && n_f % n_blocks == 0 && pvals_host && cblk_host, "set_transfer_indexed: inconsistent aggregation");
+  CU(cudaSetDevice(h->device));
+  Level& L = h->lv[level];
+  CHECK(L.n == 0 || L.n == n_f, "set_transfer_indexed: n_f does not match the level's operator");
+  // every coarse block must own exactly m = n_f / n_blocks fine rows; rows[] lists them in increasing order
+  const int m = n_f / n_blocks;
+  std::vector<int> fill(n_blocks, 0), rows((size_t)n_f);
+  for (int r = 0; r < n_f; ++r) {
+    const int g = cblk_host[r];
+    CHECK(g >= 0 && g < n_blocks && fill[g] < m, "set_transfer_indexed: coarse blocks must all have n_f / n_blocks rows");
+    rows[(size_t)g * m + fill[g]++] = r;
+  }
+  L.n = n_f; L.has_transfer = true; L.aggr = 0; L.dofi = 2; L.nvec = nvec; L.n_c = n_blocks * nvec; L.tr_m = m;
+  RET(upload<int>(h, rows.data(), rows.size(), &L.tr_rows));
+  RET(upload<int>(h, cblk_host, (size_t)n_f, &L.tr_cblk));
+  RET(upload_cx(h, pvals_host, (size_t)n_f * nvec, &L.d.pv, &L.f.pv));
+  return 0;
+}
+
+int dmlmc_set_preconditioner(dmlmc_hier* h, int level, dmlmc_hier* hp, int level_p) {
+  if (h) invalidate_graphs(h);
+  CHECK(h && level >= 0 && level < h->n_levels, "set_preconditioner: bad handle/level");
+  if (hp == nullptr) { h->prec_hier[level] = nullptr; return 0; }
+  CHECK(hp != h && level_p >= 0 && level_p < hp->n_levels, "set_preconditioner: bad preconditioner hierarchy/level");
+  CHECK(hp->device == h->device, "set_preconditioner: both hierarchies must live on the same device");
+  CHECK(hp->lv[level_p].n == h->lv[level].n && h->lv[level].n > 0, "set_preconditioner: level sizes differ");
+  h->prec_hier[level] = hp; h->prec_level[level] = level_p;
   return 0;
 }
 

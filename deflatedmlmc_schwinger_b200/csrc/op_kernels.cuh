@@ -622,9 +622,12 @@ bsr_f32x2_soa_kernel(int nb, int bpr, const int* __restrict__ col, const float4*
 // ------------------------------------------------------------------------------------------
 // aggregation transfer operators.  Row r of P_l: aggregate j = r / aggr, half = ((r % aggr) % dofi) >= h,
 // columns (2j + half)*NV + [0,NV).                                   (multigrid.py:203-227)
+// Indexed form (geometric aggregates of the preconditioner hierarchy, dmlmc_set_transfer_indexed): the coarse block
+// of fine row r is cblk[r] (columns cblk[r]*NV + [0,NV)), and coarse block g owns the m fine rows rows[g*m + (0..m)).
 template <typename T> struct TransferDev {
   int n_f, n_c, aggr, dofi, h, nvec;
   const Cx<T>* pv;     // [n_f][nvec]
+  const int* rows = nullptr; const int* cblk = nullptr; int m = 0;
 };
 
 template <typename T, int NC, int NV>
@@ -641,6 +644,18 @@ restrict_kernel(TransferDev<T> tr, const Pack<T, NC>* __restrict__ Xf, Pack<T, N
   P acc[NV];
 #pragma unroll
   for (int v = 0; v < NV; ++v) acc[v] = pzero<T, NC>();
+  if (tr.rows != nullptr) {
+    const int* rr = tr.rows + (size_t)g * tr.m;
+    for (int q = 0; q < tr.m; ++q) {
+      const int r = __ldg(rr + q);
+      const P x = ldp_ro<T, NC>(Xf, (size_t)r * ldfz + cp);
+#pragma unroll
+      for (int v = 0; v < NV; ++v) pfma_conj<T, NC>(acc[v], ldc_ro<T>(tr.pv, (size_t)r * NV + v), x);
+    }
+#pragma unroll
+    for (int v = 0; v < NV; ++v) Xc[((size_t)g * NV + v) * ldcz + cp] = acc[v];
+    return;
+  }
   const int nw = tr.aggr / tr.dofi;
   for (int wq = 0; wq < nw; ++wq) {
     for (int z = 0; z < tr.h; ++z) {
@@ -662,9 +677,14 @@ prolong_add_kernel(TransferDev<T> tr, const Pack<T, NC>* __restrict__ Xc, Pack<T
   const int r = (int)(gid / kp);
   const int cp = (int)(gid - (long long)r * kp);
   if (r >= tr.n_f) return;
-  const int j = r / tr.aggr;
-  const int q = (r - j * tr.aggr) % tr.dofi;
-  const int g = 2 * j + (q >= tr.h ? 1 : 0);
+  int g;
+  if (tr.cblk != nullptr) {
+    g = __ldg(tr.cblk + r);
+  } else {
+    const int j = r / tr.aggr;
+    const int q = (r - j * tr.aggr) % tr.dofi;
+    g = 2 * j + (q >= tr.h ? 1 : 0);
+  }
   const size_t ldfz = (size_t)ldf, ldcz = (size_t)ldc;
   typedef Pack<T, NC> P;
   P acc = Xf[(size_t)r * ldfz + cp];

@@ -102,6 +102,46 @@ def prolongator_csr(pvals, aggr_size, dofi, nvec):
     return csr_matrix((pvals.ravel(), indices, indptr), shape=(n, n_c))
 
 
+# ---- geometric aggregates of the preconditioner hierarchy ---------------------------------------
+# The estimator's levels are the reference's (aggregates = runs of consecutive rows, multigrid.py:203-227).  The
+# V-cycle that PRECONDITIONS the level-0 solve is free to use any hierarchy (FGMRES is flexible, parity is on the
+# converged solution): with aggregates that are bx x bt blocks of lattice sites, split by spin, and the SAME test
+# vectors, the two-grid method needs 8 outer iterations with a degree-32 smoother where the reference's
+# aggregation needs 16 with degree 80 (128^2, tol 1e-12; CPU experiment profiles/exp_geometric_aggregation.py).
+
+def geometric_blocks_level0(LX, LT, bx, bt):
+    """coarse block of every level-0 row i = s*V + x*LT + t: ((x/bx)*(LT/bt) + t/bt)*2 + s"""
+    s, x, t = np.meshgrid(np.arange(2), np.arange(LX), np.arange(LT), indexing='ij')
+    return (((x // bx) * (LT // bt) + t // bt) * 2 + s).ravel().astype(np.int32)
+
+
+def geometric_blocks_coarse(LXc, LTc, nv, bx, bt):
+    """coarse block of every row ((X*LTc + T)*2 + half)*nv + v of a geometric coarse level"""
+    X, T, h, v = np.meshgrid(np.arange(LXc), np.arange(LTc), np.arange(2), np.arange(nv), indexing='ij')
+    return (((X // bx) * (LTc // bt) + T // bt) * 2 + h).ravel().astype(np.int32)
+
+
+def block_orthonormal_values(vecs, cblk, nvec):
+    """pvals[n][nvec]: the first nvec columns of `vecs` orthonormalised within every coarse block (batched QR)"""
+    vecs = np.asarray(vecs)[:, :nvec]
+    n = vecs.shape[0]
+    nb = int(cblk.max()) + 1
+    m = n // nb
+    order = np.argsort(cblk, kind='stable').reshape(nb, m)
+    if m < nvec:
+        raise Exception("geometric aggregation: aggregates smaller than the number of test vectors")
+    Q, _ = np.linalg.qr(vecs[order])               # [nb, m, nvec]
+    pv = np.zeros((n, nvec), dtype=np.complex128)
+    pv[order.ravel()] = Q.reshape(nb * m, nvec)
+    return pv
+
+
+def prolongator_csr_indexed(pvals, cblk):
+    n, nvec = pvals.shape
+    indices = (cblk.astype(np.int64)[:, None] * nvec + np.arange(nvec)[None, :]).ravel()
+    return csr_matrix((pvals.ravel(), indices, np.arange(n + 1) * nvec), shape=(n, (int(cblk.max()) + 1) * nvec))
+
+
 def harmonic_ritz_inv_roots(A, degree, seed=7):
     """Inverse roots 1/theta_i of the degree-`degree` GMRES residual polynomial of A for a fixed
     random vector (harmonic Ritz values of an Arnoldi run), in Leja order for stability."""
@@ -255,7 +295,8 @@ class MG:
     """Same public surface as the reference's MG (multigrid.py:56-557)."""
 
     def __init__(self, A, smooth_iters=2, smoother_degree=80, restart=40, inner_precision="c64",
-                 device=None, dense_coarse_threshold=8192, pre_smooth=False):
+                 device=None, dense_coarse_threshold=8192, pre_smooth=False, aggregation="reference",
+                 geometric_precond=True, precond_degree=32, precond_blocks=(4, 4)):
         self.level_nr = 0
         self.ml = []
         self.A = A
@@ -284,6 +325,20 @@ class MG:
         self.dev = None                      # _lib.Hierarchy
         self.test_vectors = []
         self.level_shapes = []
+        # "reference": the aggregates of multigrid.py:203-227 (the estimator's levels).  "geometric": blocks of lattice
+        # sites split by spin -- only for the hierarchy that preconditions the level-0 solve (self.precond_mg), which
+        # the reference-aggregation instance builds for itself when geometric_precond is on and level 0 is a stencil.
+        self.aggregation = aggregation
+        self.geometric_precond = bool(geometric_precond) and aggregation == "reference"
+        self.precond_degree = precond_degree
+        self.precond_blocks = tuple(precond_blocks)
+        self.precond_mg = None
+
+    def set_option(self, name, value):
+        """kernel / cycle option on this hierarchy and on its preconditioner hierarchy"""
+        if self.precond_mg is not None:
+            self.precond_mg.dev.set_option(name, value)
+        self.dev.set_option(name, value)        # (also drops this hierarchy's CUDA graphs, which embed the preconditioner's kernels)
 
     # ---- multigrid.py:100-344 ---------------------------------------------------------------
     def setup(self, dof=[2, 8, 8], aggrs=[2 * 2, 2 * 2], max_levels=3, dim=2, acc_eigvs='low',
@@ -303,6 +358,15 @@ class MG:
         ml.levels[0].A = Al.copy()
         self.test_vectors = []
         self._transfer_meta = []
+        self._setup_args = dict(dof=list(dof), aggrs=list(aggrs), max_levels=max_levels, acc_eigvs=acc_eigvs)
+        geometric = self.aggregation == "geometric"
+        if geometric:
+            use_permuted = False
+            dims = params.get('latt_dims', None)
+            if dims is None:
+                Ls = int(round(np.sqrt(Al.shape[0] / 2)))
+                dims = [Ls, Ls]
+            geo = [dims[1] if len(dims) > 1 else dims[0], dims[0]]       # (LX, LT) of the current level's site lattice
 
         for i in range(max_levels - 1):
             dofi = dof[i] if i == 0 else int(dof[i] / 2)
@@ -327,11 +391,38 @@ class MG:
             else:
                 raise Exception("<accuracy_mg_eigvs> does not have a possible value.")
 
-            if test_vectors is not None:
+            if test_vectors is not None and i < len(test_vectors) and test_vectors[i] is not None:
                 eig_vecs = np.asarray(test_vectors[i])
+            elif geometric and i > 0:
+                # the fine test vectors lie in range(P), so their restrictions are eigenvectors of R A P for the
+                # same eigenvalues: no eigensolve on the coarse levels of the preconditioner hierarchy
+                eig_vecs = ml.levels[i - 1].R @ self.test_vectors[i - 1]
             else:
                 _, eig_vecs = eigs(Al, k=dofip1, which='LM', tol=tolx, maxiter=1000000, sigma=0.0, ncv=ncvx)
             self.test_vectors.append(eig_vecs)
+
+            if geometric:
+                bx, bt = self.precond_blocks if i == 0 else (2, 2)
+                dofip1 = min(dofip1, eig_vecs.shape[1])
+                if geo[0] % bx or geo[1] % bt:
+                    raise Exception("geometric aggregation: lattice %dx%d is not divisible into %dx%d blocks" % (geo[0], geo[1], bx, bt))
+                if i == 0:
+                    cblk = geometric_blocks_level0(geo[0], geo[1], bx, bt)
+                else:
+                    cblk = geometric_blocks_coarse(geo[0], geo[1], n // (2 * geo[0] * geo[1]), bx, bt)
+                if cblk.shape[0] != n:
+                    raise Exception("geometric aggregation: level size does not match the lattice")
+                pvals = block_orthonormal_values(eig_vecs, cblk, dofip1)
+                Pl = prolongator_csr_indexed(pvals, cblk)
+                self._transfer_meta.append(("indexed", cblk, dofip1, pvals))
+                geo = [geo[0] // bx, geo[1] // bt]
+                ml.levels[i].P = Pl
+                Rl = Pl.conjugate().transpose().tocsr()
+                ml.levels[i].R = Rl
+                Al = (Rl * Al * Pl).tocsr()
+                ml.levels.append(LevelML())
+                ml.levels[i + 1].A = Al.copy()
+                continue
 
             aggr_size = aggrs[i] * dofi if i == 0 else aggrs[i] * dofi * 2
             if dofi < 2 or dofi % 2 or aggr_size % dofi or n % aggr_size or dofip1 < 1:
@@ -382,8 +473,12 @@ class MG:
             dev.set_bsr(0, n0, 1, col, vals)
             self.level0_format = "bsr1"
         for i in range(nl - 1):
-            aggr_size, dofi, nvec, pvals = self._transfer_meta[i]
-            dev.set_transfer(i, lv[i].A.shape[0], aggr_size, dofi, nvec, pvals)
+            if self._transfer_meta[i][0] == "indexed":
+                _, cblk, nvec, pvals = self._transfer_meta[i]
+                dev.set_transfer_indexed(i, lv[i].A.shape[0], nvec, pvals, cblk)
+            else:
+                aggr_size, dofi, nvec, pvals = self._transfer_meta[i]
+                dev.set_transfer(i, lv[i].A.shape[0], aggr_size, dofi, nvec, pvals)
             if i + 1 < nl - 1:
                 col, vals = bsr_padded(lv[i + 1].A, nvec)
                 dev.set_bsr(i + 1, lv[i + 1].A.shape[0], nvec, col, vals)
@@ -450,6 +545,46 @@ class MG:
         dev._ws_key = None
         import torch
         torch.cuda.empty_cache()
+        if self.geometric_precond and self.level0_format == "stencil":
+            self._build_geometric_preconditioner(params)
+
+    def _build_geometric_preconditioner(self, params):
+        """A second hierarchy on geometric aggregates (precond_blocks sites at level 0, then 2 x 2, split by spin; same
+        number of test vectors per level, level-0 test vectors shared with the estimator's hierarchy) whose V-cycle
+        preconditions the level-0 FGMRES.  Skipped (the estimator's own hierarchy preconditions) when the lattice does
+        not divide into the blocks."""
+        dims = params.get('latt_dims', None)
+        n0 = self.ml.levels[0].A.shape[0]
+        if dims is None:
+            Ls = int(round(np.sqrt(n0 / 2)))
+            dims = [Ls, Ls]
+        LX, LT = (dims[1] if len(dims) > 1 else dims[0]), dims[0]
+        bx, bt = self.precond_blocks
+        sa = self._setup_args
+        if LX % bx or LT % bt or 2 * LX * LT != n0 or (bx * bt) < sa['dof'][1] // 2:
+            return
+        # levels: blocks of bx x bt sites, then 2 x 2, until the level is small enough for a host-side dense inverse
+        nv = [int(d // 2) for d in sa['dof'][1:]]
+        gx, gt = LX // bx, LT // bt
+        levels = 2
+        while True:
+            nvl = nv[min(levels - 2, len(nv) - 1)]
+            if 2 * gx * gt * nvl <= 1024 or gx % 2 or gt % 2 or gx < 4 or gt < 4:
+                break
+            gx, gt = gx // 2, gt // 2
+            levels += 1
+        dof = [2] + [2 * nv[min(j, len(nv) - 1)] for j in range(levels - 1)]
+        degs = [self.precond_degree] + [self.level_degree(j) for j in range(1, levels)]
+        pm = MG(self.A, smoother_degree=degs, restart=self.restart, inner_precision=self.inner_precision,
+                device=self.device, dense_coarse_threshold=self.dense_coarse_threshold, pre_smooth=self.pre_smooth,
+                aggregation="geometric", precond_blocks=self.precond_blocks)
+        p2 = dict(params)
+        p2['use_permuted'] = False
+        p2['latt_dims'] = [LT, LX]
+        pm.setup(dof=dof, aggrs=[bx * bt] + [4] * (levels - 2), max_levels=levels, acc_eigvs=sa['acc_eigvs'],
+                 params=p2, test_vectors=[self.test_vectors[0]])
+        self.precond_mg = pm
+        self.dev.set_preconditioner(0, pm.dev, 0)
 
     def _device_inverse(self, level, tol, batch=1024):
         """A_level^{-1} as a torch complex128 CUDA tensor [n, n], solved in column batches on the device"""

@@ -32,7 +32,7 @@
 extern "C" {
 #endif
 
-#define DMLMC_ABI_VERSION 2
+#define DMLMC_ABI_VERSION 3
 
 enum { DMLMC_C128 = 0, DMLMC_C64 = 1 };
 
@@ -59,6 +59,16 @@ int dmlmc_set_bsr(dmlmc_hier* h, int level, int n, int bs, int bpr, const int32_
  * pvals_host[n_f][nvec] complex128.  R_l = P_l^H (multigrid.py:267-274). */
 int dmlmc_set_transfer(dmlmc_hier* h, int level, int n_f, int aggr_size, int dofi, int nvec,
                        const double* pvals_host);
+/* the same kind of prolongator on arbitrary equal-sized aggregates: fine row r belongs to coarse block
+ * cblk_host[r] in [0, n_blocks) and has its nvec entries in columns cblk_host[r]*nvec + [0,nvec).
+ * Used by the geometric (4 x 4 sites, spin-split) hierarchy that preconditions the level-0 solve; the
+ * estimator's own transfers (utils.py:299-303,337-341) stay the reference's, dmlmc_set_transfer. */
+int dmlmc_set_transfer_indexed(dmlmc_hier* h, int level, int n_f, int n_blocks, int nvec,
+                               const double* pvals_host, const int32_t* cblk_host);
+/* precondition the FGMRES solves of `level` (multigrid.py:347-366, the M= argument of pyamg fgmres at :362)
+ * with the V-cycle of another hierarchy `hp` started at its level `level_p` (same operator size, same device;
+ * hp == NULL removes it).  hp runs on h's stream and in h's work space; it must outlive h's use of it. */
+int dmlmc_set_preconditioner(dmlmc_hier* h, int level, dmlmc_hier* hp, int level_p);
 /* dense inverse of the coarsest operator (multigrid.py:342-344), row-major n x n complex128 */
 int dmlmc_set_coarsest_inverse(dmlmc_hier* h, int n, const double* minv_host);
 /* optional dense inverse of an intermediate level: the V-cycle then bottoms out there (exact coarse

@@ -314,3 +314,28 @@ def test_argument_errors_are_reported(mg16):
         _lib._check(mg.dev.lib.dmlmc_spmm(mg.dev.h, 7, 0, X.data_ptr(), X.data_ptr(), 2))
     with pytest.raises(_lib.DmlmcError):
         _lib._check(mg.dev.lib.dmlmc_fgmres(mg.dev.h, 2, X.data_ptr(), X.data_ptr(), 2, 1e-8, 10, 10, None, None))
+
+
+@pytest.mark.parametrize("dtype", [torch.complex128, torch.complex64])
+@pytest.mark.parametrize("k", [1, 6, 32])
+def test_indexed_transfers_of_the_geometric_hierarchy(mg128, dtype, k):
+    """restrict / prolong on the geometric (4 x 4 sites, spin-split; then 2 x 2) aggregates of the preconditioner
+    hierarchy against its scipy P, R"""
+    mg, tp, A = mg128
+    pm = mg.precond_mg
+    assert pm is not None and pm.level_shapes == [32768, 8192, 2048, 512]
+    for lvl in range(3):
+        P, R = pm.ml.levels[lvl].P, pm.ml.levels[lvl].R
+        Xf = rnd(P.shape[0], k, dtype, 40 + lvl)
+        Xc = pm.dev.restrict(lvl, Xf)
+        assert relerr(host(Xc), R @ host(Xf)) < TOL[dtype]
+        Yc = rnd(P.shape[1], k, dtype, 50 + lvl)
+        Yf = rnd(P.shape[0], k, dtype, 60 + lvl)
+        ref = host(Yf) + P @ host(Yc)
+        pm.dev.prolong_add(lvl, Yc, Yf)
+        assert relerr(host(Yf), ref) < TOL[dtype]
+    # Galerkin operators of the geometric levels (BSR on the device) against scipy
+    for lvl in (1, 2):
+        Al = pm.ml.levels[lvl].A
+        X = rnd(Al.shape[0], k, dtype, 70 + lvl)
+        assert relerr(host(pm.dev.spmm(lvl, X)), Al @ host(X)) < TOL[dtype]

@@ -220,3 +220,28 @@ def test_cuda_graph_replay_of_the_vcycle_is_bit_identical(mg128, k):
         assert torch.equal(X0, X1) and torch.equal(X0, X2)
         assert np.array_equal(it0, it1) and np.array_equal(it0, it2)
         assert np.all(rr1 < 1.3e-12)
+
+
+def test_geometric_preconditioner_128(mg128):
+    """the level-0 solve preconditioned by the geometric hierarchy: same solutions as with the estimator's own
+    hierarchy as preconditioner (both to the true residual 1e-12), in far fewer outer iterations"""
+    mg, tp, A = mg128
+    assert mg.precond_mg is not None
+    A0 = mg.ml.levels[0].A
+    B = probes(A0.shape[0], 16, seed=3)
+    Bd = torch.from_numpy(np.ascontiguousarray(B)).cuda()
+    X, it, relres = mg.dev.fgmres(0, Bd, 1e-12)
+    res = np.linalg.norm(B - A0 @ host(X), axis=0) / np.linalg.norm(B, axis=0)
+    assert res.max() < 1e-11 and relres.max() < 1e-12
+    mg.dev.set_preconditioner(0, None)
+    try:
+        X2, it2, relres2 = mg.dev.fgmres(0, Bd, 1e-12)
+    finally:
+        mg.dev.set_preconditioner(0, mg.precond_mg.dev, 0)
+    print("outer iterations: geometric", it.min(), it.max(), " reference aggregation", it2.min(), it2.max())
+    assert relres2.max() < 1e-12
+    assert np.abs(host(X) - host(X2)).max() < 1e-8 * np.abs(host(X2)).max()
+    assert it.max() < it2.min()
+    # a probe's solution does not depend on its batch with the second hierarchy either
+    X3, it3, _ = mg.dev.fgmres(0, Bd[:, 3:9].contiguous(), 1e-12)
+    assert np.array_equal(it[3:9], it3) and torch.equal(X[:, 3:9], X3)

@@ -209,3 +209,39 @@ def test_smoother_product_form_matches_richardson(port128):
         for v in nu:
             y = y - v * (A @ y)
         assert np.linalg.norm(p0 * y - e) / np.linalg.norm(e) < 1e-12
+
+
+def test_geometric_aggregates_of_the_preconditioner_hierarchy():
+    """blocks of lattice sites split by spin: equal-sized aggregates, P^H P = I, chirality preserved, and the
+    restricted test vectors are eigenvectors of the Galerkin operator (so the coarse levels need no eigensolve)"""
+    import os
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "schwinger128.npz"))
+    L = 128
+    n = 2 * L * L
+    cb = mgm.geometric_blocks_level0(L, L, 4, 4)
+    assert cb.dtype == np.int32 and cb.shape == (n,)
+    cnt = np.bincount(cb)
+    assert cnt.shape[0] == 2 * (L // 4) ** 2 and np.all(cnt == 16)
+    # row i = s*V + x*L + t
+    i = 1 * L * L + 37 * L + 102
+    assert cb[i] == ((37 // 4) * (L // 4) + 102 // 4) * 2 + 1
+    tv = g["tv0"]
+    pv = mgm.block_orthonormal_values(tv, cb, 4)
+    P = mgm.prolongator_csr_indexed(pv, cb)
+    assert P.shape == (n, 8192)
+    PhP = (P.conj().T @ P).toarray()
+    assert np.abs(PhP - np.eye(8192)).max() < 1e-13
+    # the test vectors lie in range(P)
+    assert np.linalg.norm(P @ (P.conj().T @ tv) - tv) < 1e-12 * np.linalg.norm(tv)
+    A = refport.load_matrix("schwinger128", -0.1320).tocsr()
+    Ac = (P.conj().T @ A @ P).tocsr()
+    tc = P.conj().T @ tv
+    lam = np.einsum("ij,ij->j", tv.conj(), A @ tv) / np.einsum("ij,ij->j", tv.conj(), tv)
+    assert np.linalg.norm(Ac @ tc - tc * lam[None, :]) < 1e-7 * np.linalg.norm(tc)
+    # coarse level: rows ((X*LT + T)*2 + half)*nv + v, 2 x 2 blocks
+    cb1 = mgm.geometric_blocks_coarse(32, 32, 4, 2, 2)
+    assert cb1.shape == (8192,) and np.all(np.bincount(cb1) == 16)
+    r = ((5 * 32 + 9) * 2 + 1) * 4 + 3
+    assert cb1[r] == ((5 // 2) * 16 + 9 // 2) * 2 + 1
+    # chirality: spin-0 rows only feed even coarse blocks
+    assert np.all(cb[: L * L] % 2 == 0) and np.all(cb[L * L:] % 2 == 1)
