@@ -195,7 +195,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--probes", type=int, default=256, help="probes per step per GPU")
     ap.add_argument("--impl", default="b200")
-    ap.add_argument("--degree", type=int, default=0, help="smoother degree of the level-0 V-cycle (0: 32 geometric / 80 reference)")
+    ap.add_argument("--degree", type=int, default=0, help="smoother degree of the level-0 V-cycle (0: 36 geometric / 80 reference)")
     ap.add_argument("--precond", default="geometric", choices=["geometric", "reference"],
                     help="hierarchy of the V-cycle that preconditions the level-0 solve: geometric 4x4-site aggregates "
                          "(default) or the estimator's own (reference aggregation)")
@@ -226,7 +226,7 @@ def main():
     t0 = time.time()
     geo = args.precond == "geometric"
     if args.degree <= 0:
-        args.degree = 32 if geo else 80
+        args.degree = 36 if geo else 80
     mg = multigrid.MG(A, smoother_degree=80, precond_degree=args.degree, geometric_precond=True) if geo else \
         multigrid.MG(A, smoother_degree=args.degree, geometric_precond=False)
     mg.setup(dof=tp["dof"], aggrs=tp["aggrs"], max_levels=tp["max_nr_levels"], acc_eigvs=tp["accuracy_mg_eigvs"],

@@ -120,7 +120,8 @@ __device__ __forceinline__ void tmem_ld_32x32b_x32(uint32_t taddr, uint32_t (&v)
 //   tmA: Mt[two_n][two_n] BF16, box 64 x 128;  tmB: Bt[k][two_n] BF16, box 64 x 256 (rows >= k read as 0)
 __global__ void __launch_bounds__(UM_THREADS, 1)
 dense_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-                  float* __restrict__ Y, int ldy, int two_n, int k) {
+                  float* __restrict__ Y, int ldy, int two_n, int k, int kdim) {   // kdim: length of the contraction (two_n, or
+                                                                                  // 3 * two_n for the split-BF16 operands)
   extern __shared__ uint8_t um_smem_raw[];
   const uint32_t base = (smem_u32(um_smem_raw) + 1023u) & ~1023u;
   uint8_t* smem = um_smem_raw + (base - smem_u32(um_smem_raw));
@@ -136,7 +137,7 @@ dense_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   const int col0 = blockIdx.y * UM_BN;                  // first column
   const int ncols = min(UM_BN, k - col0);
   const int bn = (ncols + 15) & ~15;                    // UMMA N: multiple of 16 for M = 128
-  const int num_kb = (two_n + UM_BK - 1) / UM_BK;
+  const int num_kb = (kdim + UM_BK - 1) / UM_BK;
 
   if (warp == 0 && lane == 0) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmA)) : "memory");
@@ -241,6 +242,63 @@ umma_expand_matrix_kernel(const Cx<double>* __restrict__ Minv, int n, __nv_bfloa
   bot.x = __float2bfloat16_rn((float)m.im); bot.y = __float2bfloat16_rn((float)m.re);
   *reinterpret_cast<__nv_bfloat162*>(Mt + (2 * i) * two_n + 2 * j) = top;
   *reinterpret_cast<__nv_bfloat162*>(Mt + (2 * i + 1) * two_n + 2 * j) = bot;
+}
+
+// Split-BF16 operands (FP32-class accuracy from BF16 tensor cores): m = hi + lo with hi = bf16(m), lo = bf16(m - hi),
+// likewise the right-hand side, and  M B ~= M_hi B_hi + M_lo B_hi + M_hi B_lo  (the dropped lo x lo term is 2^-16
+// relative) as ONE GEMM over the concatenated contraction:  Mt3[2n][6n] = [hi | lo | hi],  Bt3[k][6n] = [hi | hi | lo].
+// Used where a small level's dense inverse is itself the preconditioner of that level's solve (the MLMC coarse
+// solve at n = 2048): 3 outer iterations like the FP32 SIMT kernel, at a third of its time.
+__device__ __forceinline__ void bf16_split(float v, __nv_bfloat16& hi, __nv_bfloat16& lo) {
+  hi = __float2bfloat16_rn(v);
+  lo = __float2bfloat16_rn(v - __bfloat162float(hi));
+}
+__global__ void __launch_bounds__(256)
+umma_expand_matrix_split_kernel(const Cx<double>* __restrict__ Minv, int n, __nv_bfloat16* __restrict__ Mt3) {
+  const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (size_t)n * n) return;
+  const size_t i = idx / n, j = idx - i * n;
+  const Cx<double> m = ldc_ro<double>(Minv, idx);
+  const size_t two_n = 2 * (size_t)n, ld = 3 * two_n;
+  __nv_bfloat16 rh, rl, ih, il;
+  bf16_split((float)m.re, rh, rl); bf16_split((float)m.im, ih, il);
+  const __nv_bfloat16 nih = __hneg(ih), nil = __hneg(il);
+  __nv_bfloat16* top = Mt3 + (2 * i) * ld + 2 * j;
+  __nv_bfloat16* bot = Mt3 + (2 * i + 1) * ld + 2 * j;
+  __nv_bfloat162 t;
+  t.x = rh; t.y = nih; *reinterpret_cast<__nv_bfloat162*>(top) = t; *reinterpret_cast<__nv_bfloat162*>(top + 2 * two_n) = t;
+  t.x = rl; t.y = nil; *reinterpret_cast<__nv_bfloat162*>(top + two_n) = t;
+  t.x = ih; t.y = rh;  *reinterpret_cast<__nv_bfloat162*>(bot) = t; *reinterpret_cast<__nv_bfloat162*>(bot + 2 * two_n) = t;
+  t.x = il; t.y = rl;  *reinterpret_cast<__nv_bfloat162*>(bot + two_n) = t;
+}
+// Bt3[c][0:2n] = Bt3[c][2n:4n] = hi, Bt3[c][4n:6n] = lo of the interleaved (Re, Im) column c of X
+template <typename T>
+__global__ void __launch_bounds__(256)
+umma_pack_rhs_split_kernel(const Cx<T>* __restrict__ X, int ldx, int n, int k, __nv_bfloat16* __restrict__ Bt3) {
+  __shared__ uint32_t thi[32][33], tlo[32][33];
+  const int j0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
+  const int tx = threadIdx.x, ty = threadIdx.y;          // block (32, 8)
+#pragma unroll
+  for (int r = 0; r < 4; ++r) {
+    const int j = j0 + ty + 8 * r, c = c0 + tx;
+    uint32_t ph = 0, pl = 0;
+    if (j < n && c < k) {
+      const Cx<T> v = ldc_ro<T>(X, (size_t)j * ldx + c);
+      __nv_bfloat162 bh, bl;
+      bf16_split((float)v.re, bh.x, bl.x); bf16_split((float)v.im, bh.y, bl.y);
+      ph = *reinterpret_cast<uint32_t*>(&bh); pl = *reinterpret_cast<uint32_t*>(&bl);
+    }
+    thi[ty + 8 * r][tx] = ph; tlo[ty + 8 * r][tx] = pl;
+  }
+  __syncthreads();
+#pragma unroll
+  for (int r = 0; r < 4; ++r) {
+    const int c = c0 + ty + 8 * r, j = j0 + tx;
+    if (j < n && c < k) {
+      uint32_t* row = reinterpret_cast<uint32_t*>(Bt3) + (size_t)c * 3 * n;
+      row[j] = thi[tx][ty + 8 * r]; row[n + j] = thi[tx][ty + 8 * r]; row[2 * n + j] = tlo[tx][ty + 8 * r];
+    }
+  }
 }
 
 // Bt[c][2j], Bt[c][2j+1] = BF16(Re, Im) of X[j][c]: transpose through a 32 x 32 shared-memory tile

@@ -58,6 +58,9 @@ struct Level {
   // tensor-core operand of the dense inverse: Mt[2n][2n] BF16 (2x2 real block per complex entry) + its TMA map
   bool has_umma = false; __nv_bfloat16* minv_bf16 = nullptr; CUtensorMap tmA;
   const void* tmB_ptr = nullptr; int tmB_k = 0; CUtensorMap tmB;
+  // split-BF16 operand [2n][6n] = [hi | lo | hi] of a small level's inverse (FP32-class accuracy on the tensor cores)
+  bool has_umma3 = false; __nv_bfloat16* minv_bf16x3 = nullptr; CUtensorMap tmA3;
+  const void* tmB3_ptr = nullptr; int tmB3_k = 0; CUtensorMap tmB3;
   LevelT<double> d;
   LevelT<float> f;
 };
@@ -85,6 +88,8 @@ struct dmlmc_hier {
   int pre_smooth = 0;                     // 0: V-cycle = coarse correction + post-smoothing (default), 1: pre- and post-smoothing
   int smoother_half = 1;                  // BF16 storage of the level-0 smoother's intermediate vectors (c64 cycle)
   int dense_direct_exact = 1;             // a dense level solved directly (not from a finer level) uses its FP32 copy
+  int fuse_io = 1;                        // V-cycle input / output conversions fused into the neighbouring kernels (bit-identical)
+  int dense_split_bf16 = 1;               // such a level (1024 <= n <= 4096) is applied as a split-BF16 tensor-core GEMM instead
   int dense_tensor_min_n = 1024;          // dense inverses at least this large are applied on the tensor cores
   bool umma_attr_set = false, dmma_attr_set = false;
   int defl_tensor = 1;                    // deflation projections on the FP64 tensor cores (d % 4 == 0, d <= 64)
@@ -276,7 +281,7 @@ template <typename T> int launch_restrict(dmlmc_hier* h, int level, const void* 
   return launch_restrict<T>(h, level, Xf, Xc, k, k, k);
 }
 template <typename T, int NC>
-int launch_prolong_nc(dmlmc_hier* h, int level, const void* Xc, void* Xf, int k, int ldf, int ldc) {
+int launch_prolong_nc(dmlmc_hier* h, int level, const void* Xc, void* Xf, int k, int ldf, int ldc, int add) {
   Level& L = h->lv[level];
   TransferDev<T> tr; tr.n_f = L.n; tr.n_c = L.n_c; tr.aggr = L.aggr; tr.dofi = L.dofi; tr.h = L.dofi / 2; tr.nvec = L.nvec;
   tr.pv = Sel<T>::get(L).pv; tr.rows = L.tr_rows; tr.cblk = L.tr_cblk; tr.m = L.tr_m;
@@ -284,19 +289,19 @@ int launch_prolong_nc(dmlmc_hier* h, int level, const void* Xc, void* Xf, int k,
   const size_t total = (size_t)L.n * kp;
   const unsigned g = nblocks(total, 256);
   switch (L.nvec) {
-    case 1: prolong_add_kernel<T, NC, 1><<<g, 256, 0, h->stream>>>(tr, (const P*)Xc, (P*)Xf, kp, ldf / NC, ldc / NC); break;
-    case 2: prolong_add_kernel<T, NC, 2><<<g, 256, 0, h->stream>>>(tr, (const P*)Xc, (P*)Xf, kp, ldf / NC, ldc / NC); break;
-    case 4: prolong_add_kernel<T, NC, 4><<<g, 256, 0, h->stream>>>(tr, (const P*)Xc, (P*)Xf, kp, ldf / NC, ldc / NC); break;
-    case 8: prolong_add_kernel<T, NC, 8><<<g, 256, 0, h->stream>>>(tr, (const P*)Xc, (P*)Xf, kp, ldf / NC, ldc / NC); break;
+    case 1: prolong_add_kernel<T, NC, 1><<<g, 256, 0, h->stream>>>(tr, (const P*)Xc, (P*)Xf, kp, ldf / NC, ldc / NC, add); break;
+    case 2: prolong_add_kernel<T, NC, 2><<<g, 256, 0, h->stream>>>(tr, (const P*)Xc, (P*)Xf, kp, ldf / NC, ldc / NC, add); break;
+    case 4: prolong_add_kernel<T, NC, 4><<<g, 256, 0, h->stream>>>(tr, (const P*)Xc, (P*)Xf, kp, ldf / NC, ldc / NC, add); break;
+    case 8: prolong_add_kernel<T, NC, 8><<<g, 256, 0, h->stream>>>(tr, (const P*)Xc, (P*)Xf, kp, ldf / NC, ldc / NC, add); break;
     default: return fail(-1, "dmlmc: unsupported number of test vectors");
   }
   LAUNCH_CHECK(h);
   return 0;
 }
-template <typename T> int launch_prolong(dmlmc_hier* h, int level, const void* Xc, void* Xf, int k, int ldf, int ldc) {
+template <typename T> int launch_prolong(dmlmc_hier* h, int level, const void* Xc, void* Xf, int k, int ldf, int ldc, int add = 1) {
   if (!h->lv[level].has_transfer) return fail(-1, "dmlmc: transfer operator of this level not set");
-  if (max_nc<T>() == 2 && pack2_ok(Xf, Xc, k, ldf, ldc)) return launch_prolong_nc<T, max_nc<T>()>(h, level, Xc, Xf, k, ldf, ldc);
-  return launch_prolong_nc<T, 1>(h, level, Xc, Xf, k, ldf, ldc);
+  if (max_nc<T>() == 2 && pack2_ok(Xf, Xc, k, ldf, ldc)) return launch_prolong_nc<T, max_nc<T>()>(h, level, Xc, Xf, k, ldf, ldc, add);
+  return launch_prolong_nc<T, 1>(h, level, Xc, Xf, k, ldf, ldc, add);
 }
 template <typename T> int launch_prolong(dmlmc_hier* h, int level, const void* Xc, void* Xf, int k) {
   return launch_prolong<T>(h, level, Xc, Xf, k, k, k);
@@ -324,7 +329,31 @@ int launch_dense_umma(dmlmc_hier* h, int level, const Cx<float>* B, Cx<float>* X
     h->umma_attr_set = true;
   }
   dim3 grd((2 * n + UM_BM - 1) / UM_BM, (k + UM_BN - 1) / UM_BN);
-  dense_umma_kernel<<<grd, UM_THREADS, UM_SMEM, h->stream>>>(L.tmA, L.tmB, reinterpret_cast<float*>(X), k, 2 * n, k);
+  dense_umma_kernel<<<grd, UM_THREADS, UM_SMEM, h->stream>>>(L.tmA, L.tmB, reinterpret_cast<float*>(X), k, 2 * n, k, 2 * n);
+  LAUNCH_CHECK(h);
+  h->ws_off = mark;
+  return 0;
+}
+
+// the same with split-BF16 operands (hi/lo of the matrix and of the right-hand side, one GEMM over 6n): FP32-class accuracy
+int launch_dense_umma_split(dmlmc_hier* h, int level, const Cx<float>* B, Cx<float>* X, int k) {
+  Level& L = h->lv[level];
+  const int n = L.n;
+  const size_t mark = h->ws_off;
+  __nv_bfloat16* Bt;
+  RET(ws_get<__nv_bfloat16>(h, (size_t)k * 6 * n, &Bt));
+  dim3 pblk(32, 8), pgrd((n + 31) / 32, (k + 31) / 32);
+  umma_pack_rhs_split_kernel<float><<<pgrd, pblk, 0, h->stream>>>(B, k, n, k, Bt); LAUNCH_CHECK(h);
+  if (L.tmB3_ptr != Bt || L.tmB3_k != k) {
+    if (make_tmap_bf16(&L.tmB3, Bt, (uint64_t)k, (uint64_t)6 * n, UM_BN) != 0) return fail(-4, "dmlmc: cuTensorMapEncodeTiled failed (split rhs)");
+    L.tmB3_ptr = Bt; L.tmB3_k = k;
+  }
+  if (!h->umma_attr_set) {
+    CU(cudaFuncSetAttribute(dense_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)UM_SMEM));
+    h->umma_attr_set = true;
+  }
+  dim3 grd((2 * n + UM_BM - 1) / UM_BM, (k + UM_BN - 1) / UM_BN);
+  dense_umma_kernel<<<grd, UM_THREADS, UM_SMEM, h->stream>>>(L.tmA3, L.tmB3, reinterpret_cast<float*>(X), k, 2 * n, k, 6 * n);
   LAUNCH_CHECK(h);
   h->ws_off = mark;
   return 0;
@@ -338,6 +367,8 @@ template <typename T> int launch_dense(dmlmc_hier* h, int level, const void* B, 
   if constexpr (std::is_same<T, float>::value) {
     if (L.has_umma && (L.minv4 == nullptr || (!prefer_exact && n >= h->dense_tensor_min_n)))
       return launch_dense_umma(h, level, (const Cx<float>*)B, (Cx<float>*)X, k);
+    if (prefer_exact && L.has_umma3 && h->dense_split_bf16)
+      return launch_dense_umma_split(h, level, (const Cx<float>*)B, (Cx<float>*)X, k);
   }
   if (minv_of<T>(L) == nullptr) return fail(-1, "dmlmc: this level's dense inverse exists only as the tensor-core (complex64) operand");
   dim3 blk(32, 8);
@@ -371,6 +402,20 @@ int build_umma_operand(dmlmc_hier* h, int level, const Cx<double>* minv_dev) {
   return 0;
 }
 
+int build_umma_split_operand(dmlmc_hier* h, int level, const Cx<double>* minv_dev) {
+  Level& L = h->lv[level];
+  const size_t n = L.n;
+  if (n % 8 != 0) return 0;
+  __nv_bfloat16* mt = nullptr;
+  CU(cudaMalloc(&mt, 12 * n * n * sizeof(__nv_bfloat16)));
+  h->owned.push_back(mt);
+  umma_expand_matrix_split_kernel<<<nblocks(n * n, 256), 256, 0, h->stream>>>(minv_dev, (int)n, mt); LAUNCH_CHECK(h);
+  CU(cudaStreamSynchronize(h->stream));
+  if (make_tmap_bf16(&L.tmA3, mt, 2 * n, 6 * n, UM_BM) != 0) return fail(-4, "dmlmc: cuTensorMapEncodeTiled failed (split matrix)");
+  L.minv_bf16x3 = mt; L.has_umma3 = true; L.tmB3_ptr = nullptr;
+  return 0;
+}
+
 // Out[:, 0:w] = (Tout) In[:, 0:w] between batches with leading dimensions ld_in / ld_out
 template <typename Tin, typename Tout>
 int cvt_cols(dmlmc_hier* h, const Cx<Tin>* in, size_t ld_in, Cx<Tout>* out, size_t ld_out, int n, int w) {
@@ -380,11 +425,18 @@ int cvt_cols(dmlmc_hier* h, const Cx<Tin>* in, size_t ld_in, Cx<Tout>* out, size
   return 0;
 }
 
+// the complex64 BF16-storage path of smooth_apply on the level-0 stencil can write its (accumulated) result as complex128
+bool smoother_dout_ok(dmlmc_hier* h, int level, int k) {
+  Level& L = h->lv[level];
+  return h->fuse_io && h->smoother_half && L.has_smoother && L.smoother16 && L.kind == 0 && (k % 2) == 0 && L.nu.size() >= 2;
+}
+
 // ---- smoother: E (+)= p(A) R with p in product form, p(A) = p0 prod_i (I - nu_i A) ---------------
 // One fused kernel per factor (operator + update: read x, write x'), no reductions, no host
 // synchronisation.  R, E, t0, t1: compact [n_level][k]; R may alias t0; E must not alias R, t0, t1.
 template <typename T>
-int smooth_apply(dmlmc_hier* h, int level, const void* R, void* E, bool acc, void* t0, void* t1, int k) {
+int smooth_apply(dmlmc_hier* h, int level, const void* R, void* E, bool acc, void* t0, void* t1, int k, Cx<double>* Ed = nullptr) {
+  // Ed (only with smoother_dout_ok): the accumulated result E + p(A) R goes to Ed[n][k] as complex128, E is left unchanged
   Level& L = h->lv[level];
   if (!L.has_smoother) return fail(-1, "dmlmc: smoother of this level not set");
   const int m = (int)L.nu.size();
@@ -414,7 +466,21 @@ int smooth_apply(dmlmc_hier* h, int level, const void* R, void* E, bool acc, voi
           RET((launch_op_nc<float, 2, M_STEP, false, true>(h, level, in, nullptr, pp[0], L.nu[i], cfirst, k)));
           in = pp[0];
         } else if (i == m - 1) {
-          if (acc) RET((launch_op_nc<float, 2, M_STEP_ACC, true, false>(h, level, in, nullptr, E, L.nu[i], clast, k)));
+          if (acc && Ed != nullptr) {
+            CHECK(L.kind == 0, "complex128 smoother output: level-0 stencil only");
+            StencilDev<float> op; op.LX = L.LX; op.LT = L.LT; op.Ut = L.f.Ut; op.Ux = L.f.Ux; op.diag = L.f.diag;
+            const int kp = k / 2;
+            int bx = 1; while (bx < 32 && bx < kp) bx *= 2;
+            int by = std::max(1, std::min(h->stencil_by, L.LT)), bz = std::max(1, std::min(h->stencil_bz, L.LX));
+            while (bx * by * bz > 512) { if (bz > 1) bz /= 2; else by /= 2; }
+            while (bx * by * bz < 256 && by < L.LT) by *= 2;
+            dim3 blk(bx, by, bz), grd((kp + bx - 1) / bx, (L.LT + by - 1) / by, (L.LX + bz - 1) / bz);
+            stencil_kernel<float, 2, M_STEP_ACC, 3, true, false, 0, true><<<grd, blk, 0, h->stream>>>(
+                op, in, (const Pack<float, 2>*)Ed, E, cx<float>((float)L.nu[i].re, (float)L.nu[i].im),
+                cx<float>((float)clast.re, (float)clast.im), kp);
+            LAUNCH_CHECK(h);
+          }
+          else if (acc) RET((launch_op_nc<float, 2, M_STEP_ACC, true, false>(h, level, in, nullptr, E, L.nu[i], clast, k)));
           else     RET((launch_op_nc<float, 2, M_STEP, true, false>(h, level, in, nullptr, E, L.nu[i], clast, k)));
         } else {
           void* out = pp[i & 1];
@@ -499,7 +565,8 @@ int chunk_cols(dmlmc_hier* h, int level, int k, size_t elem) {
 template <typename T> struct VcBuf { Cx<T>* b = nullptr; Cx<T>* x = nullptr; Cx<T>* t0 = nullptr; Cx<T>* t1 = nullptr; int kc = 0; };
 
 template <typename T, typename TIO>
-int vcycle_level(dmlmc_hier* h, int l, int level0, int lb, std::vector<VcBuf<T>>& vb, const Cx<TIO>* Bio, Cx<TIO>* Xio, int k) {
+int vcycle_level(dmlmc_hier* h, int l, int level0, int lb, std::vector<VcBuf<T>>& vb, const Cx<TIO>* Bio, Cx<TIO>* Xio, int k,
+                 bool b_ready = false) {   // b_ready: vb[level0].b already holds the input in T (no conversion pass)
   Level& L = h->lv[l];
   const int n = L.n;
   VcBuf<T>& me = vb[l];
@@ -520,7 +587,7 @@ int vcycle_level(dmlmc_hier* h, int l, int level0, int lb, std::vector<VcBuf<T>>
       const int C0 = (col0 / co.kc) * co.kc, wC = std::min(co.kc, k - C0);
       const size_t coff = (size_t)C0 * nc + (col0 - C0);
       if (phase == 0) {
-        if (l == level0) RET((cvt_cols<TIO, T>(h, Bio + col0, (size_t)k, bc, (size_t)w, n, w)));
+        if (l == level0 && !b_ready) RET((cvt_cols<TIO, T>(h, Bio + col0, (size_t)k, bc, (size_t)w, n, w)));
         if (h->pre_smooth) {
           RET(smooth_apply<T>(h, l, bc, xc, false, me.t0, me.t1, w));
           RET((launch_op<T, M_RES>(h, l, xc, bc, me.t0, ZERO, ZERO, w)));
@@ -528,22 +595,33 @@ int vcycle_level(dmlmc_hier* h, int l, int level0, int lb, std::vector<VcBuf<T>>
         } else {
           // post-smoothing only: x = 0, the coarse level sees R b directly
           RET(launch_restrict<T>(h, l, bc, co.b + coff, w, w, wC));
-          CU(cudaMemsetAsync(xc, 0, (size_t)n * w * sizeof(Cx<T>), h->stream));
+          if (!h->fuse_io) CU(cudaMemsetAsync(xc, 0, (size_t)n * w * sizeof(Cx<T>), h->stream));
         }
       } else {
-        RET(launch_prolong<T>(h, l, co.x + coff, xc, w, w, wC));
+        // x = 0 before the coarse correction when there is no pre-smoothing: x = P x_c without reading x
+        RET(launch_prolong<T>(h, l, co.x + coff, xc, w, w, wC, (h->pre_smooth || !h->fuse_io) ? 1 : 0));
         RET((launch_op<T, M_RES>(h, l, xc, bc, me.t0, ZERO, ZERO, w)));
-        RET(smooth_apply<T>(h, l, me.t0, xc, true, me.t0, me.t1, w));
-        if (l == level0) RET((cvt_cols<T, TIO>(h, xc, (size_t)w, Xio + col0, (size_t)k, n, w)));
+        bool dout = false;
+        if constexpr (std::is_same<T, float>::value && std::is_same<TIO, double>::value)
+          dout = (l == level0 && w == k && smoother_dout_ok(h, l, w));
+        if (dout) {
+          if constexpr (std::is_same<TIO, double>::value)
+            RET(smooth_apply<T>(h, l, me.t0, xc, true, me.t0, me.t1, w, Xio));
+        } else {
+          RET(smooth_apply<T>(h, l, me.t0, xc, true, me.t0, me.t1, w));
+          if (l == level0) RET((cvt_cols<T, TIO>(h, xc, (size_t)w, Xio + col0, (size_t)k, n, w)));
+        }
       }
     }
-    if (phase == 0) RET((vcycle_level<T, TIO>(h, l + 1, level0, lb, vb, Bio, Xio, k)));
+    if (phase == 0) RET((vcycle_level<T, TIO>(h, l + 1, level0, lb, vb, Bio, Xio, k, b_ready)));
   }
   return 0;
 }
 
+// B32 (optional): the input already converted to complex64 [n][k] by the caller (fgmres: written by the kernel that
+// produced the basis vector); used in place of the conversion pass when the cycle computes in complex64 on one chunk
 template <typename T, typename TIO>
-int vcycle(dmlmc_hier* h, int level0, const void* Bin, void* Xout, int k) {
+int vcycle(dmlmc_hier* h, int level0, const void* Bin, void* Xout, int k, const Cx<float>* B32 = nullptr) {
   const int nl = h->n_levels;
   CHECK(level0 >= 0 && level0 < nl, "vcycle: bad level");
   // the cycle bottoms out at the first level (from level0 down) that owns a dense inverse usable in
@@ -581,7 +659,11 @@ int vcycle(dmlmc_hier* h, int level0, const void* Bin, void* Xout, int k) {
     RET(ws_get<Cx<T>>(h, n * k, &vb[l].b)); RET(ws_get<Cx<T>>(h, n * k, &vb[l].x));
     if (l < lb) { RET(ws_get<Cx<T>>(h, n * vb[l].kc, &vb[l].t0)); RET(ws_get<Cx<T>>(h, n * vb[l].kc, &vb[l].t1)); }
   }
-  int rc = vcycle_level<T, TIO>(h, level0, level0, lb, vb, (const Cx<TIO>*)Bin, (Cx<TIO>*)Xout, k);
+  bool b_ready = false;
+  if constexpr (std::is_same<T, float>::value) {
+    if (B32 != nullptr && h->fuse_io && vb[level0].kc >= k) { vb[level0].b = const_cast<Cx<float>*>(B32); b_ready = true; }
+  }
+  int rc = vcycle_level<T, TIO>(h, level0, level0, lb, vb, (const Cx<TIO>*)Bin, (Cx<TIO>*)Xout, k, b_ready);
   h->ws_off = mark;
   return rc;
 }
@@ -621,7 +703,7 @@ void invalidate_graphs(dmlmc_hier* h) {
   h->graphs.clear();
 }
 
-int precond_eager(dmlmc_hier* h, int level, const Z* V, Z* Zout, int k) {
+int precond_eager(dmlmc_hier* h, int level, const Z* V, Z* Zout, int k, const Cx<float>* V32) {
   if (dmlmc_hier* hp = h->prec_hier[level]) {
     // the preconditioner hierarchy works on the caller's stream (the capture stream while a graph is recorded)
     // and in the caller's work space
@@ -629,16 +711,16 @@ int precond_eager(dmlmc_hier* h, int level, const Z* V, Z* Zout, int k) {
     const long long l0 = hp->launches;
     hp->stream = h->stream; hp->ws = h->ws; hp->ws_bytes = h->ws_bytes; hp->ws_off = h->ws_off;
     const int pl = h->prec_level[level];
-    const int rc = hp->inner_prec == DMLMC_C128 ? vcycle<double, double>(hp, pl, V, Zout, k) : vcycle<float, double>(hp, pl, V, Zout, k);
+    const int rc = hp->inner_prec == DMLMC_C128 ? vcycle<double, double>(hp, pl, V, Zout, k) : vcycle<float, double>(hp, pl, V, Zout, k, V32);
     h->launches += hp->launches - l0;
     hp->stream = keep_stream; hp->ws = keep_ws; hp->ws_bytes = keep_bytes; hp->ws_off = keep_off;
     return rc;
   }
   if (h->inner_prec == DMLMC_C128) return vcycle<double, double>(h, level, V, Zout, k);
-  return vcycle<float, double>(h, level, V, Zout, k);
+  return vcycle<float, double>(h, level, V, Zout, k, V32);
 }
 
-int precond(dmlmc_hier* h, int level, const Z* V, Z* Zout, int k) { return precond_eager(h, level, V, Zout, k); }
+int precond(dmlmc_hier* h, int level, const Z* V, Z* Zout, int k, const Cx<float>* V32 = nullptr) { return precond_eager(h, level, V, Zout, k, V32); }
 
 // One FGMRES iteration (V-cycle, operator, Gram-Schmidt, Givens step, next basis vector) is a fixed sequence of ~105
 // launches whose arguments depend only on (level, k, precision, work space, Krylov index j, restart, tol, reorth).
@@ -735,6 +817,12 @@ int fgmres(dmlmc_hier* h, int level, const Z* B, Z* X, int k, double tol, int re
   RET(ws_get<int>(h, (size_t)k, &s.it_cycle));
   RET(ws_get<int>(h, (size_t)k, &s.it_total));
   RET(ws_get<int>(h, 1, &s.n_active));
+  // complex64 copy of the current basis vector = the V-cycle's input, written by the kernel that normalises it
+  Cx<float>* V32 = nullptr;
+  {
+    dmlmc_hier* hv = h->prec_hier[level] ? h->prec_hier[level] : h;
+    if (h->fuse_io && hv->fuse_io && hv->inner_prec == DMLMC_C64) RET(ws_get<Cx<float>>(h, nk, &V32));
+  }
 
   CU(cudaMemsetAsync(X, 0, nk * sizeof(Z), h->stream));
   const Z* Rsrc = B;
@@ -751,13 +839,13 @@ int fgmres(dmlmc_hier* h, int level, const Z* B, Z* X, int k, double tol, int re
     mode = 2;
     RET(read_nactive(h, s.n_active, &nact));
     if (nact == 0 || total_it >= maxiter) break;
-    col_scale_kernel<<<nblocks(nk, 256), 256, 0, h->stream>>>(Rsrc, s.scale, Vb, nk, k); LAUNCH_CHECK(h);
+    col_scale_kernel<<<nblocks(nk, 256), 256, 0, h->stream>>>(Rsrc, s.scale, Vb, nk, k, V32); LAUNCH_CHECK(h);
     int j = 0;
     for (; j < m; ++j) {
       Z* Vj = Vb + (size_t)j * nk;
       Z* Zj = Zb + (size_t)j * nk;
       auto body = [&]() -> int {
-        RET(precond(h, level, Vj, Zj, k));
+        RET(precond(h, level, Vj, Zj, k, V32));
         RET((launch_op<double, M_AX>(h, level, Zj, nullptr, W, ZERO, ZERO, k)));
         // classical Gram-Schmidt, optionally with one re-orthogonalisation pass
         RET(multi_dot(h, Vb, nk, j + 1, W, n, k, partial, s.hsum, 0));
@@ -774,7 +862,7 @@ int fgmres(dmlmc_hier* h, int level, const Z* B, Z* X, int k, double tol, int re
         }
         CU(cudaMemsetAsync(s.n_active, 0, sizeof(int), h->stream));
         gmres_step_kernel<<<gk, 128, 0, h->stream>>>(s, j, tol); LAUNCH_CHECK(h);
-        if (j + 1 < m) { col_scale_kernel<<<nblocks(nk, 256), 256, 0, h->stream>>>(W, s.scale, Vb + (size_t)(j + 1) * nk, nk, k); LAUNCH_CHECK(h); }
+        if (j + 1 < m) { col_scale_kernel<<<nblocks(nk, 256), 256, 0, h->stream>>>(W, s.scale, Vb + (size_t)(j + 1) * nk, nk, k, V32); LAUNCH_CHECK(h); }
         return 0;
       };
       RET(run_iteration(h, h->use_graphs && k <= h->graph_max_k, level, k, mark, j, m, tol, body));
@@ -940,6 +1028,7 @@ size_t fgmres_bytes(dmlmc_hier* h, int level, int k, int m) {
   size_t vb = vcycle_bytes(h, level, k, sizeof(Z));
   if (h->prec_hier[level]) vb = std::max(vb, vcycle_bytes(h->prec_hier[level], h->prec_level[level], k, sizeof(Z)) + (size_t)(1 << 16));
   b += vb;
+  b += align_up(nk * sizeof(Cx<float>));   // complex64 copy of the current basis vector
   b += 2 * align_up(nk * z);          // staging buffers of the graph-replayed V-cycle
   return b + (1 << 16);
 }
@@ -1110,6 +1199,7 @@ int dmlmc_set_dense_inverse(dmlmc_hier* h, int level, int n, const double* minv_
   }
   L.has_dense = true;
   if (n >= 256) RET(build_umma_operand(h, level, L.minv_d));
+  if (n >= 1024 && n <= 4096) RET(build_umma_split_operand(h, level, L.minv_d));
   return 0;
 }
 
@@ -1319,6 +1409,8 @@ int dmlmc_level_sample_host(dmlmc_hier* h, int method, int level_f, int level_c,
 int dmlmc_set_option(dmlmc_hier* h, const char* name, double value) {
   if (h) invalidate_graphs(h);
   CHECK(h != nullptr && name != nullptr, "set_option: bad arguments");
+  if (std::strcmp(name, "fuse_io") == 0) { h->fuse_io = value != 0.0; return 0; }
+  if (std::strcmp(name, "dense_split_bf16") == 0) { h->dense_split_bf16 = value != 0.0; return 0; }
   if (std::strcmp(name, "use_graphs") == 0) { h->use_graphs = value != 0.0; return 0; }
   if (std::strcmp(name, "graph_max_k") == 0) { h->graph_max_k = (int)value; return 0; }
   if (std::strcmp(name, "reorth") == 0) { h->reorth = value != 0.0 ? 1 : 0; return 0; }

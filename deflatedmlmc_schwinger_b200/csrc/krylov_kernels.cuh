@@ -133,13 +133,17 @@ multi_axpy_norm_kernel(const Z* __restrict__ Vbase, size_t vstride, int nv, cons
   }
 }
 
-// Out[r][col] = In[r][col] * scale[col]
+// Out[r][col] = In[r][col] * scale[col]; Out32 (optional): the same values as complex64 -- the next V-cycle's input,
+// written here instead of by a separate conversion pass over Out
 __global__ void __launch_bounds__(256)
-col_scale_kernel(const Z* __restrict__ In, const double* __restrict__ scale, Z* __restrict__ Out, size_t nk, int k) {
+col_scale_kernel(const Z* __restrict__ In, const double* __restrict__ scale, Z* __restrict__ Out, size_t nk, int k,
+                 Cx<float>* __restrict__ Out32) {
   const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= nk) return;
   const double s = __ldg(scale + (idx % k));
-  Out[idx] = zscale(s, ldc_ro<double>(In, idx));
+  const Z v = zscale(s, ldc_ro<double>(In, idx));
+  Out[idx] = v;
+  if (Out32 != nullptr) Out32[idx] = cx<float>((float)v.re, (float)v.im);
 }
 
 // deflation with a dense V[n][d] shared by all columns:  C[i][col] = sum_r conj(V[r][i]) X[r][col]

@@ -84,7 +84,10 @@ __device__ __forceinline__ void sth2(void* base, size_t idx, const Pack<float, 2
 // MINB = 2: 64 registers, all 14 loads of a thread in flight at once; MINB = 3: 40 registers, loads in
 // batches of 6 but 50 % more resident threads.
 // HIN / HOUT: X / Y are BF16-stored (complex64 arithmetic, NC = 2 only).
-template <typename T, int NC, int MODE, int MINB, bool HIN = false, bool HOUT = false, int PFD = 0>
+// DOUT (last factor of the post-smoother, MODE = M_STEP_ACC, complex64): the result Yold + c (X - w A X) is written as
+// complex128 to the array passed in the (otherwise unused) B argument instead of back to Y -- the V-cycle's output
+// lands in the outer solver's complex128 vector without a separate conversion pass.
+template <typename T, int NC, int MODE, int MINB, bool HIN = false, bool HOUT = false, int PFD = 0, bool DOUT = false>
 __global__ void __launch_bounds__(512, MINB)
 stencil_kernel(StencilDev<T> op, const void* __restrict__ Xv, const Pack<T, NC>* __restrict__ B,
                void* __restrict__ Yv, Cx<T> w, Cx<T> cfin, int kp) {
@@ -141,7 +144,12 @@ stencil_kernel(StencilDev<T> op, const void* __restrict__ Xv, const Pack<T, NC>*
 
   const P o0 = op_value<T, NC, MODE>(y0, c0, i0, B, Y, w, cfin);
   const P o1 = op_value<T, NC, MODE>(y1, c1, i1, B, Y, w, cfin);
-  if constexpr (HOUT) { sth2(Yv, i0, o0); sth2(Yv, i1, o1); } else { Y[i0] = o0; Y[i1] = o1; }
+  if constexpr (DOUT) {
+    static_assert(MODE == M_STEP_ACC && sizeof(T) == 4 && NC == 2 && !HOUT, "complex128 output: last complex64 factor only");
+    double2* Yd = reinterpret_cast<double2*>(const_cast<Pack<T, NC>*>(B));
+    Yd[2 * i0] = make_double2((double)o0.d[0], (double)o0.d[1]); Yd[2 * i0 + 1] = make_double2((double)o0.d[2], (double)o0.d[3]);
+    Yd[2 * i1] = make_double2((double)o1.d[0], (double)o1.d[1]); Yd[2 * i1 + 1] = make_double2((double)o1.d[2], (double)o1.d[3]);
+  } else if constexpr (HOUT) { sth2(Yv, i0, o0); sth2(Yv, i1, o1); } else { Y[i0] = o0; Y[i1] = o1; }
 }
 
 // ------------------------------------------------------------------------------------------
@@ -672,7 +680,7 @@ restrict_kernel(TransferDev<T> tr, const Pack<T, NC>* __restrict__ Xf, Pack<T, N
 template <typename T, int NC, int NV>
 __global__ void __launch_bounds__(256)
 prolong_add_kernel(TransferDev<T> tr, const Pack<T, NC>* __restrict__ Xc, Pack<T, NC>* __restrict__ Xf, int kp,
-                   int ldf, int ldc) {
+                   int ldf, int ldc, int add) {   // add = 0: Xf = P Xc (Xf is not read)
   const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   const int r = (int)(gid / kp);
   const int cp = (int)(gid - (long long)r * kp);
@@ -687,7 +695,7 @@ prolong_add_kernel(TransferDev<T> tr, const Pack<T, NC>* __restrict__ Xc, Pack<T
   }
   const size_t ldfz = (size_t)ldf, ldcz = (size_t)ldc;
   typedef Pack<T, NC> P;
-  P acc = Xf[(size_t)r * ldfz + cp];
+  P acc = add ? Xf[(size_t)r * ldfz + cp] : pzero<T, NC>();
 #pragma unroll
   for (int v = 0; v < NV; ++v)
     pfma<T, NC>(acc, ldc_ro<T>(tr.pv, (size_t)r * NV + v), ldp_ro<T, NC>(Xc, ((size_t)g * NV + v) * ldcz + cp));

@@ -296,7 +296,7 @@ class MG:
 
     def __init__(self, A, smooth_iters=2, smoother_degree=80, restart=40, inner_precision="c64",
                  device=None, dense_coarse_threshold=8192, pre_smooth=False, aggregation="reference",
-                 geometric_precond=True, precond_degree=32, precond_blocks=(4, 4)):
+                 geometric_precond=True, precond_degree=36, precond_blocks=(4, 4)):
         self.level_nr = 0
         self.ml = []
         self.A = A

@@ -258,8 +258,16 @@ def test_tensor_core_dense_apply(mg128, k):
     ref = _bf16_round(Minv) @ _bf16_round(host(B))
     assert relerr(host(X), ref) < 2e-5
     assert relerr(host(X), Minv @ host(B)) < 2e-2
-    Xs = mg.dev.vcycle(lvl, B)                             # direct solve of the level: FP32 kernel
-    assert relerr(host(Xs), Minv @ host(B)) < 2e-5
+    exact = Minv @ host(B)
+    Xs = mg.dev.vcycle(lvl, B)                # direct solve of the level: split-BF16 tensor-core GEMM
+    e_split = relerr(host(Xs), exact)
+    mg.dev.set_option("dense_split_bf16", 0)
+    Xf = mg.dev.vcycle(lvl, B)                # FP32 SIMT kernel
+    mg.dev.set_option("dense_split_bf16", 1)
+    e_f32 = relerr(host(Xf), exact)
+    print("k", k, "split-BF16 error", e_split, "FP32 error", e_f32)
+    assert e_f32 < 2e-5 and e_split < 5e-5
+    assert not torch.equal(Xs, Xf)            # the tensor-core path was taken
 
 
 @pytest.mark.parametrize("dtype", [torch.complex128, torch.complex64])

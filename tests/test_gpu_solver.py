@@ -245,3 +245,18 @@ def test_geometric_preconditioner_128(mg128):
     # a probe's solution does not depend on its batch with the second hierarchy either
     X3, it3, _ = mg.dev.fgmres(0, Bd[:, 3:9].contiguous(), 1e-12)
     assert np.array_equal(it[3:9], it3) and torch.equal(X[:, 3:9], X3)
+
+
+@pytest.mark.parametrize("k", [2, 16])
+def test_fused_vcycle_io_is_bit_identical(mg128, k):
+    """option fuse_io (complex64 copy of the basis vector written by the normalisation kernel, complex128 output
+    written by the last smoother factor, prolongation without the zero read) changes no bit of the solve"""
+    mg, tp, A = mg128
+    B = torch.from_numpy(np.ascontiguousarray(probes(mg.level_shapes[0], k, seed=11))).cuda()
+    X1, it1, _ = mg.dev.fgmres(0, B, 1e-12)
+    mg.set_option("fuse_io", 0)
+    try:
+        X0, it0, _ = mg.dev.fgmres(0, B, 1e-12)
+    finally:
+        mg.set_option("fuse_io", 1)
+    assert np.array_equal(it0, it1) and torch.equal(X0, X1)
