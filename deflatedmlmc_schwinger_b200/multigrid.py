@@ -296,7 +296,8 @@ class MG:
 
     def __init__(self, A, smooth_iters=2, smoother_degree=80, restart=40, inner_precision="c64",
                  device=None, dense_coarse_threshold=8192, pre_smooth=False, aggregation="reference",
-                 geometric_precond=True, precond_degree=36, precond_blocks=(4, 4)):
+                 geometric_precond=True, precond_degree=36, precond_blocks=(4, 4), precond_coarse_degree=None,
+                 level0_block=1):
         self.level_nr = 0
         self.ml = []
         self.A = A
@@ -332,12 +333,16 @@ class MG:
         self.geometric_precond = bool(geometric_precond) and aggregation == "reference"
         self.precond_degree = precond_degree
         self.precond_blocks = tuple(precond_blocks)
-        self.precond_mg = None
+        self.precond_coarse_degree = 16 if precond_coarse_degree is None else precond_coarse_degree
+        self.level0_block = int(level0_block)    # BSR block size of level 0 when it is not a Wilson stencil
+        self.precond_mg = None                   # geometric hierarchy preconditioning the level-0 solve
+        self.precond_mg1 = None                  # ... and the level-1 solve (lattices whose level 1 has no dense inverse)
 
     def set_option(self, name, value):
         """kernel / cycle option on this hierarchy and on its preconditioner hierarchy"""
-        if self.precond_mg is not None:
-            self.precond_mg.dev.set_option(name, value)
+        for pm in (self.precond_mg, self.precond_mg1):
+            if pm is not None:
+                pm.dev.set_option(name, value)
         self.dev.set_option(name, value)        # (also drops this hierarchy's CUDA graphs, which embed the preconditioner's kernels)
 
     # ---- multigrid.py:100-344 ---------------------------------------------------------------
@@ -367,6 +372,9 @@ class MG:
                 Ls = int(round(np.sqrt(Al.shape[0] / 2)))
                 dims = [Ls, Ls]
             geo = [dims[1] if len(dims) > 1 else dims[0], dims[0]]       # (LX, LT) of the current level's site lattice
+            # level 0 of this hierarchy is not the spin-major site lattice (it is a coarse operator of the estimator):
+            # the caller passes the blocks of its rows and the lattice of the resulting coarse blocks
+            first = params.get('geometric_first', None)
 
         for i in range(max_levels - 1):
             dofi = dof[i] if i == 0 else int(dof[i] / 2)
@@ -404,9 +412,12 @@ class MG:
             if geometric:
                 bx, bt = self.precond_blocks if i == 0 else (2, 2)
                 dofip1 = min(dofip1, eig_vecs.shape[1])
-                if geo[0] % bx or geo[1] % bt:
+                if i == 0 and first is not None:
+                    cblk = np.asarray(first['cblk'], dtype=np.int32)
+                    geo = [first['coarse_dims'][0] * bx, first['coarse_dims'][1] * bt]
+                elif geo[0] % bx or geo[1] % bt:
                     raise Exception("geometric aggregation: lattice %dx%d is not divisible into %dx%d blocks" % (geo[0], geo[1], bx, bt))
-                if i == 0:
+                elif i == 0:
                     cblk = geometric_blocks_level0(geo[0], geo[1], bx, bt)
                 else:
                     cblk = geometric_blocks_coarse(geo[0], geo[1], n // (2 * geo[0] * geo[1]), bx, bt)
@@ -469,9 +480,9 @@ class MG:
             dev.set_stencil(0, links, diag)
             self.level0_format = "stencil"
         except Exception:
-            col, vals = bsr_padded(A0, 1)
-            dev.set_bsr(0, n0, 1, col, vals)
-            self.level0_format = "bsr1"
+            col, vals = bsr_padded(A0, self.level0_block)
+            dev.set_bsr(0, n0, self.level0_block, col, vals)
+            self.level0_format = "bsr%d" % self.level0_block
         for i in range(nl - 1):
             if self._transfer_meta[i][0] == "indexed":
                 _, cblk, nvec, pvals = self._transfer_meta[i]
@@ -574,17 +585,66 @@ class MG:
             gx, gt = gx // 2, gt // 2
             levels += 1
         dof = [2] + [2 * nv[min(j, len(nv) - 1)] for j in range(levels - 1)]
-        degs = [self.precond_degree] + [self.level_degree(j) for j in range(1, levels)]
+        degs = [self.precond_degree] + [self.precond_coarse_degree] * (levels - 1)
         pm = MG(self.A, smoother_degree=degs, restart=self.restart, inner_precision=self.inner_precision,
                 device=self.device, dense_coarse_threshold=self.dense_coarse_threshold, pre_smooth=self.pre_smooth,
                 aggregation="geometric", precond_blocks=self.precond_blocks)
         p2 = dict(params)
         p2['use_permuted'] = False
         p2['latt_dims'] = [LT, LX]
+        p2.pop('geometric_first', None)
         pm.setup(dof=dof, aggrs=[bx * bt] + [4] * (levels - 2), max_levels=levels, acc_eigvs=sa['acc_eigvs'],
                  params=p2, test_vectors=[self.test_vectors[0]])
         self.precond_mg = pm
         self.dev.set_preconditioner(0, pm.dev, 0)
+        self._build_level1_preconditioner(params, LX, LT)
+
+    def _build_level1_preconditioner(self, params, LX, LT):
+        """The same for the estimator's level-1 solves on lattices whose level 1 is too large for a dense inverse.  A row of
+        A_1 is (strip j, half, v): strip j = s V/a + x LT/a + q is the run of a = aggr_size consecutive rows (spin s,
+        lattice column x, t in [q a, (q+1) a)) of multigrid.py:203-227.  Geometric blocks: 2 neighbouring strips in x,
+        both halves, split by the spin s; then 2 x 2.  CPU experiment at 128^2 (exact two-grid method on A_1): 11 outer
+        iterations at degree 32 against 33 (18 at degree 80) with the estimator's own level-2 aggregates."""
+        lv = self.ml.levels
+        sa = self._setup_args
+        if len(lv) < 3 or 1 in self.dense_levels or self._transfer_meta[0][0] == "indexed":
+            return
+        aggr, dofi, nv1, _ = self._transfer_meta[0]
+        a_sites = aggr                          # rows of one spin component per strip (dofi = 2: rows = sites of one spin)
+        n1 = lv[1].A.shape[0]
+        V = LX * LT
+        if dofi != 2 or LT % a_sites or LX % 2 or n1 != (2 * V // aggr) * 2 * nv1:
+            return
+        nq = LT // a_sites
+        r = np.arange(n1)
+        half = (r // nv1) % 2
+        j = r // (2 * nv1)
+        s = j // (V // a_sites)
+        x = (j % (V // a_sites)) // nq
+        q = j % nq
+        cblk = (((x // 2) * nq + q) * 2 + s).astype(np.int32)
+        gx, gt = LX // 2, nq
+        nvs = [int(d // 2) for d in sa['dof'][2:]] or [nv1]
+        levels = 2
+        while True:
+            nvl = nvs[min(levels - 2, len(nvs) - 1)]
+            if 2 * gx * gt * nvl <= 1024 or gx % 2 or gt % 2 or gx < 4 or gt < 4:
+                break
+            gx, gt = gx // 2, gt // 2
+            levels += 1
+        dof = [2 * nv1] + [2 * nvs[min(jj, len(nvs) - 1)] for jj in range(levels - 1)]
+        degs = [self.precond_degree] + [self.precond_coarse_degree] * (levels - 1)
+        pm = MG(lv[1].A, smoother_degree=degs, restart=self.restart, inner_precision=self.inner_precision,
+                device=self.device, dense_coarse_threshold=self.dense_coarse_threshold, pre_smooth=self.pre_smooth,
+                aggregation="geometric", precond_blocks=(1, 1), level0_block=nv1)
+        p2 = dict(params)
+        p2['use_permuted'] = False
+        p2['latt_dims'] = [LT, LX]
+        p2['geometric_first'] = {'cblk': cblk, 'coarse_dims': (LX // 2, nq)}
+        pm.setup(dof=dof, aggrs=[4] * (levels - 1), max_levels=levels, acc_eigvs=sa['acc_eigvs'], params=p2,
+                 test_vectors=[self.test_vectors[1]])
+        self.precond_mg1 = pm
+        self.dev.set_preconditioner(1, pm.dev, 0)
 
     def _device_inverse(self, level, tol, batch=1024):
         """A_level^{-1} as a torch complex128 CUDA tensor [n, n], solved in column batches on the device"""

@@ -23,7 +23,8 @@ def _say(params, *a, **kw):
 
 def _make_solver(A, params):
     mg_solver = MG(A, smoother_degree=params.get('smoother_degree', 80), restart=params.get('fgmres_restart', 40),
-                   inner_precision=params.get('inner_precision', 'c64'), pre_smooth=params.get('pre_smooth', False))
+                   inner_precision=params.get('inner_precision', 'c64'), pre_smooth=params.get('pre_smooth', False),
+                   geometric_precond=params.get('geometric_precond', True), precond_degree=params.get('precond_degree', 36))
     mg_solver.coarsest_iters = 0
     mg_solver.coarsest_iters_tot = 0
     mg_solver.coarsest_iters_avg = 0

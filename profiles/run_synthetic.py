@@ -14,7 +14,10 @@ ap.add_argument("--L", type=int, default=256)
 ap.add_argument("--probes", type=int, default=64)
 ap.add_argument("--mass", type=float, default=-0.062)
 ap.add_argument("--steps", type=int, default=2)
-ap.add_argument("--degree", type=int, default=80)
+ap.add_argument("--degree", type=int, default=80, help="smoother degree on the estimator's own hierarchy")
+ap.add_argument("--precond-degree", type=int, default=36)
+ap.add_argument("--coarse-degree", type=int, default=0, help="smoother degree on the coarse levels of the geometric hierarchies (0: the default, 16)")
+ap.add_argument("--no-geometric", action="store_true")
 args = ap.parse_args()
 
 import torch
@@ -52,7 +55,8 @@ if os.path.isfile(cache):
 params = {"use_permuted": False, "latt_dims": [L, L], "x_displacement": 2, "test_vectors_type": "EVs",
           "function_params": {"tol": 1e-12}}
 t0 = time.time()
-mg = multigrid.MG(A, smoother_degree=args.degree)
+mg = multigrid.MG(A, smoother_degree=args.degree, geometric_precond=not args.no_geometric, precond_degree=args.precond_degree,
+                  precond_coarse_degree=args.coarse_degree or None)
 mg.setup(dof=dof, aggrs=aggrs, max_levels=nlev, acc_eigvs="low", params=params, test_vectors=tvs)
 torch.cuda.synchronize()
 setup_s = time.time() - t0
@@ -68,6 +72,18 @@ Xs, iters, relres = dev.fgmres(0, X0, 1e-12, restart=restart, maxiter=maxiter)
 R = X0 - dev.spmm(0, Xs)
 true_rel = float((torch.linalg.vector_norm(R, dim=0) / torch.linalg.vector_norm(X0, dim=0)).max())
 del Xs, R
+# time of the two solves of a sample separately (level 0: geometric preconditioner; level 1: the estimator's own hierarchy)
+def _time_solve(level, B, reps=2):
+    dev.fgmres(level, B, 1e-12, restart=restart, maxiter=maxiter)
+    torch.cuda.synchronize(); t_ = time.time()
+    for _ in range(reps):
+        _, it_, _ = dev.fgmres(level, B, 1e-12, restart=restart, maxiter=maxiter)
+    torch.cuda.synchronize()
+    return 1e3 * (time.time() - t_) / reps, [int(it_.min()), int(it_.max())]
+ms_solve0, it_solve0 = _time_solve(0, X0)
+X1 = dev.restrict(0, X0)
+ms_solve1, it_solve1 = _time_solve(1, X1)
+del X1
 e, it = dev.level_sample(1, 0, 1, X0, 1e-12, restart, maxiter)      # warm-up
 torch.cuda.synchronize()
 if world > 1:
@@ -92,7 +108,12 @@ if rank == 0:
                   "smoother_degrees": mg.smoother_degrees_used, "probes_per_gpu": k, "ms_per_batch": 1e3 * dt,
                   "probes_per_s": world * k / dt, "fgmres_iters_level0": [int(it[0].min()), int(it[0].max())],
                   "fgmres_iters_level1": [int(it[1].min()), int(it[1].max())],
-                  "solve_iters": [int(iters.min()), int(iters.max())], "max_true_relres": true_rel,
+                  "solve_iters": [int(iters.min()), int(iters.max())], "ms_solve_level0": ms_solve0, "ms_solve_level1": ms_solve1,
+                  "precond_levels": mg.precond_mg.level_shapes if mg.precond_mg is not None else None,
+                  "precond_dense_levels": {str(a): b for a, b in mg.precond_mg.dense_levels.items()} if mg.precond_mg is not None else None,
+                  "precond_degrees": mg.precond_mg.smoother_degrees_used if mg.precond_mg is not None else None,
+                  "precond1_levels": mg.precond_mg1.level_shapes if mg.precond_mg1 is not None else None,
+                  "precond1_degrees": mg.precond_mg1.smoother_degrees_used if mg.precond_mg1 is not None else None, "max_true_relres": true_rel,
                   "launches_per_batch": (dev.launch_count() - l0) // args.steps, "setup_s": setup_s,
                   "test_vectors": "cache" if tvs is not None else "host eigs",
                   "mean_estimate": mean_est}), flush=True)

@@ -260,3 +260,31 @@ def test_fused_vcycle_io_is_bit_identical(mg128, k):
     finally:
         mg.set_option("fuse_io", 1)
     assert np.array_equal(it0, it1) and torch.equal(X0, X1)
+
+
+def test_geometric_preconditioner_of_the_level1_solve(g128):
+    """lattices whose level 1 is too large for a dense inverse get a geometric hierarchy for the level-1 solve as well
+    (2 strips in x, both halves, split by spin); forced here on 128^2 with dense_coarse_threshold = 2048"""
+    from conftest import make_mg, params128
+    mg, tp, A = make_mg(params128(), "mlmc", [g128["tv0"], g128["tv1"], g128["tv2"]], smoother_degree=32,
+                        dense_coarse_threshold=2048)
+    assert mg.precond_mg1 is not None and mg.precond_mg1.level_shapes == [8192, 2048, 512]
+    assert mg.precond_mg1.level0_format == "bsr4" and 1 not in mg.dense_levels
+    A1 = mg.ml.levels[1].A
+    B = probes(A1.shape[0], 12, seed=21)
+    Bd = torch.from_numpy(np.ascontiguousarray(B)).cuda()
+    X, it, relres = mg.dev.fgmres(1, Bd, 1e-12)
+    res = np.linalg.norm(B - A1 @ host(X), axis=0) / np.linalg.norm(B, axis=0)
+    assert res.max() < 1e-11 and relres.max() < 1e-12
+    mg.dev.set_preconditioner(1, None)
+    X2, it2, relres2 = mg.dev.fgmres(1, Bd, 1e-12)
+    print("level-1 outer iterations: geometric", it.min(), it.max(), " estimator's hierarchy", it2.min(), it2.max())
+    assert relres2.max() < 1e-12
+    assert np.abs(host(X) - host(X2)).max() < 1e-8 * np.abs(host(X2)).max()
+    assert it.max() < it2.min()
+    # the level-0 solve of this hierarchy (its geometric level 1 is not dense either: BSR smoother level inside the cycle)
+    A0 = mg.ml.levels[0].A
+    B0 = probes(A0.shape[0], 4, seed=22)
+    X0, it0, rr0 = mg.dev.fgmres(0, torch.from_numpy(np.ascontiguousarray(B0)).cuda(), 1e-12)
+    res0 = np.linalg.norm(B0 - A0 @ host(X0), axis=0) / np.linalg.norm(B0, axis=0)
+    assert res0.max() < 1e-11 and it0.max() <= 14
