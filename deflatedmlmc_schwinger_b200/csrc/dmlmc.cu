@@ -88,6 +88,10 @@ struct dmlmc_hier {
   int pre_smooth = 0;                     // 0: V-cycle = coarse correction + post-smoothing (default), 1: pre- and post-smoothing
   int smoother_half = 1;                  // BF16 storage of the level-0 smoother's intermediate vectors (c64 cycle)
   int dense_direct_exact = 1;             // a dense level solved directly (not from a finer level) uses its FP32 copy
+  int fuse_res = 1;                       // the V-cycle's residual before the post-smoother is written as BF16 (level-0 stencil)
+  int adaptive_poll = 1;                  // skip the per-iteration convergence poll until one iteration before the count the
+                                          // previous solve of the level needed (columns that are done do no work, so this is safe)
+  int expect_it[MAX_LEVELS] = {}; double expect_tol[MAX_LEVELS] = {}; int expect_k[MAX_LEVELS] = {};
   int fuse_io = 1;                        // V-cycle input / output conversions fused into the neighbouring kernels (bit-identical)
   int dense_split_bf16 = 1;               // such a level (1024 <= n <= 4096) is applied as a split-BF16 tensor-core GEMM instead
   int dense_tensor_min_n = 1024;          // dense inverses at least this large are applied on the tensor cores
@@ -425,6 +429,28 @@ int cvt_cols(dmlmc_hier* h, const Cx<Tin>* in, size_t ld_in, Cx<Tout>* out, size
   return 0;
 }
 
+// thread-block / grid shape of the generic stencil kernel for kp packs per row
+void stencil_dims(dmlmc_hier* h, const Level& L, int kp, dim3& blk, dim3& grd) {
+  int bx = 1; while (bx < 32 && bx < kp) bx *= 2;
+  int by = std::max(1, std::min(h->stencil_by, L.LT)), bz = std::max(1, std::min(h->stencil_bz, L.LX));
+  while (bx * by * bz > 512) { if (bz > 1) bz /= 2; else by /= 2; }
+  while (bx * by * bz < 256 && by < L.LT) by *= 2;
+  blk = dim3(bx, by, bz); grd = dim3((kp + bx - 1) / bx, (L.LT + by - 1) / by, (L.LX + bz - 1) / bz);
+}
+
+// R16 = B - A X with X, B complex64 and the result stored as BF16: the post-smoother's input on the level-0 stencil, so that
+// ALL of its factors but the last run in the packed-FP32 BF16 -> BF16 kernel (option fuse_res)
+int launch_residual_half(dmlmc_hier* h, int level, const void* X, const void* B, void* R16, int k) {
+  Level& L = h->lv[level];
+  StencilDev<float> op; op.LX = L.LX; op.LT = L.LT; op.Ut = L.f.Ut; op.Ux = L.f.Ux; op.diag = L.f.diag;
+  const int kp = k / 2;
+  dim3 blk, grd; stencil_dims(h, L, kp, blk, grd);
+  stencil_kernel<float, 2, M_RES, 3, false, true><<<grd, blk, 0, h->stream>>>(op, X, (const Pack<float, 2>*)B, R16, cx<float>(0.f, 0.f),
+                                                                               cx<float>(0.f, 0.f), kp);
+  LAUNCH_CHECK(h);
+  return 0;
+}
+
 // the complex64 BF16-storage path of smooth_apply on the level-0 stencil can write its (accumulated) result as complex128
 bool smoother_dout_ok(dmlmc_hier* h, int level, int k) {
   Level& L = h->lv[level];
@@ -435,7 +461,8 @@ bool smoother_dout_ok(dmlmc_hier* h, int level, int k) {
 // One fused kernel per factor (operator + update: read x, write x'), no reductions, no host
 // synchronisation.  R, E, t0, t1: compact [n_level][k]; R may alias t0; E must not alias R, t0, t1.
 template <typename T>
-int smooth_apply(dmlmc_hier* h, int level, const void* R, void* E, bool acc, void* t0, void* t1, int k, Cx<double>* Ed = nullptr) {
+int smooth_apply(dmlmc_hier* h, int level, const void* R, void* E, bool acc, void* t0, void* t1, int k, Cx<double>* Ed = nullptr,
+                 bool r_half = false) {   // r_half (only with smoother_dout_ok): R is already BF16-stored (launch_residual_half)
   // Ed (only with smoother_dout_ok): the accumulated result E + p(A) R goes to Ed[n][k] as complex128, E is left unchanged
   Level& L = h->lv[level];
   if (!L.has_smoother) return fail(-1, "dmlmc: smoother of this level not set");
@@ -459,10 +486,10 @@ int smooth_apply(dmlmc_hier* h, int level, const void* R, void* E, bool acc, voi
     const bool bsr_half = L.kind == 1 && L.bs >= 2 &&
                           ((size_t)L.bpr * L.bs * L.bs * sizeof(float4) + (size_t)L.bpr * sizeof(int) + 16) <= 48 * 1024;
     if (h->smoother_half && L.smoother16 && (L.kind == 0 || bsr_half) && (k % 2) == 0 && m >= 2) {
-      const double HS = 64.0;
+      const double HS = r_half ? 1.0 : 64.0;
       const Cx<double> cfirst = {HS, 0.0}, clast = {L.p0.re / HS, L.p0.im / HS};
       for (int i = 0; i < m; ++i) {
-        if (i == 0) {
+        if (i == 0 && !r_half) {
           RET((launch_op_nc<float, 2, M_STEP, false, true>(h, level, in, nullptr, pp[0], L.nu[i], cfirst, k)));
           in = pp[0];
         } else if (i == m - 1) {
@@ -470,11 +497,7 @@ int smooth_apply(dmlmc_hier* h, int level, const void* R, void* E, bool acc, voi
             CHECK(L.kind == 0, "complex128 smoother output: level-0 stencil only");
             StencilDev<float> op; op.LX = L.LX; op.LT = L.LT; op.Ut = L.f.Ut; op.Ux = L.f.Ux; op.diag = L.f.diag;
             const int kp = k / 2;
-            int bx = 1; while (bx < 32 && bx < kp) bx *= 2;
-            int by = std::max(1, std::min(h->stencil_by, L.LT)), bz = std::max(1, std::min(h->stencil_bz, L.LX));
-            while (bx * by * bz > 512) { if (bz > 1) bz /= 2; else by /= 2; }
-            while (bx * by * bz < 256 && by < L.LT) by *= 2;
-            dim3 blk(bx, by, bz), grd((kp + bx - 1) / bx, (L.LT + by - 1) / by, (L.LX + bz - 1) / bz);
+            dim3 blk, grd; stencil_dims(h, L, kp, blk, grd);
             stencil_kernel<float, 2, M_STEP_ACC, 3, true, false, 0, true><<<grd, blk, 0, h->stream>>>(
                 op, in, (const Pack<float, 2>*)Ed, E, cx<float>((float)L.nu[i].re, (float)L.nu[i].im),
                 cx<float>((float)clast.re, (float)clast.im), kp);
@@ -483,7 +506,7 @@ int smooth_apply(dmlmc_hier* h, int level, const void* R, void* E, bool acc, voi
           else if (acc) RET((launch_op_nc<float, 2, M_STEP_ACC, true, false>(h, level, in, nullptr, E, L.nu[i], clast, k)));
           else     RET((launch_op_nc<float, 2, M_STEP, true, false>(h, level, in, nullptr, E, L.nu[i], clast, k)));
         } else {
-          void* out = pp[i & 1];
+          void* out = (in == pp[i & 1]) ? pp[(i + 1) & 1] : pp[i & 1];
           if (L.kind == 0 && h->stencil_fast && L.d.diag.im == 0.0 && (size_t)L.n * (k / 2) < (1ull << 32)) {
             const int kp = k / 2;
             if (h->stencil_smem && (kp % 2) == 0) {
@@ -600,13 +623,19 @@ int vcycle_level(dmlmc_hier* h, int l, int level0, int lb, std::vector<VcBuf<T>>
       } else {
         // x = 0 before the coarse correction when there is no pre-smoothing: x = P x_c without reading x
         RET(launch_prolong<T>(h, l, co.x + coff, xc, w, w, wC, (h->pre_smooth || !h->fuse_io) ? 1 : 0));
-        RET((launch_op<T, M_RES>(h, l, xc, bc, me.t0, ZERO, ZERO, w)));
-        bool dout = false;
-        if constexpr (std::is_same<T, float>::value && std::is_same<TIO, double>::value)
-          dout = (l == level0 && w == k && smoother_dout_ok(h, l, w));
+        bool dout = false, rhalf = false;
+        if constexpr (std::is_same<T, float>::value) {
+          rhalf = h->fuse_res && smoother_dout_ok(h, l, w) && h->lv[l].nu.size() >= 3;
+          if constexpr (std::is_same<TIO, double>::value) dout = (l == level0 && w == k && smoother_dout_ok(h, l, w));
+        }
+        if (rhalf) RET(launch_residual_half(h, l, xc, bc, me.t0, w));
+        else       RET((launch_op<T, M_RES>(h, l, xc, bc, me.t0, ZERO, ZERO, w)));
         if (dout) {
           if constexpr (std::is_same<TIO, double>::value)
-            RET(smooth_apply<T>(h, l, me.t0, xc, true, me.t0, me.t1, w, Xio));
+            RET(smooth_apply<T>(h, l, me.t0, xc, true, me.t0, me.t1, w, Xio, rhalf));
+        } else if (rhalf) {
+          RET(smooth_apply<T>(h, l, me.t0, xc, true, me.t0, me.t1, w, nullptr, true));
+          if (l == level0) RET((cvt_cols<T, TIO>(h, xc, (size_t)w, Xio + col0, (size_t)k, n, w)));
         } else {
           RET(smooth_apply<T>(h, l, me.t0, xc, true, me.t0, me.t1, w));
           if (l == level0) RET((cvt_cols<T, TIO>(h, xc, (size_t)w, Xio + col0, (size_t)k, n, w)));
@@ -826,6 +855,7 @@ int fgmres(dmlmc_hier* h, int level, const Z* B, Z* X, int k, double tol, int re
 
   CU(cudaMemsetAsync(X, 0, nk * sizeof(Z), h->stream));
   const Z* Rsrc = B;
+  const int expect = (h->expect_tol[level] == tol && h->expect_k[level] == k) ? h->expect_it[level] : 0;
   int total_it = 0, nact = 0;
   int mode = 1;                      // 1: first cycle (r = b), 2: later cycles (true residual of every column)
   const unsigned gk = nblocks(k, 128);
@@ -867,7 +897,9 @@ int fgmres(dmlmc_hier* h, int level, const Z* B, Z* X, int k, double tol, int re
       };
       RET(run_iteration(h, h->use_graphs && k <= h->graph_max_k, level, k, mark, j, m, tol, body));
       ++total_it;
-      RET(read_nactive(h, s.n_active, &nact));
+      // (also every 4th iteration, so that a stale expectation wastes at most 3 iterations)
+      if (!h->adaptive_poll || total_it + 1 >= expect || (total_it & 3) == 0 || j + 1 == m || total_it >= maxiter)
+        RET(read_nactive(h, s.n_active, &nact));
       if (nact == 0 || total_it >= maxiter) { ++j; break; }
     }
     const int steps = std::min(j, m);
@@ -876,6 +908,7 @@ int fgmres(dmlmc_hier* h, int level, const Z* B, Z* X, int k, double tol, int re
     RET((launch_op<double, M_RES>(h, level, X, B, Rb, ZERO, ZERO, k)));
     Rsrc = Rb;
   }
+  h->expect_it[level] = total_it; h->expect_tol[level] = tol; h->expect_k[level] = k;
   if (iters_host) CU(cudaMemcpyAsync(iters_host, s.it_total, sizeof(int) * k, cudaMemcpyDeviceToHost, h->stream));
   if (relres_host) CU(cudaMemcpyAsync(relres_host, s.relres, sizeof(double) * k, cudaMemcpyDeviceToHost, h->stream));
   if (iters_host || relres_host) CU(cudaStreamSynchronize(h->stream));
@@ -1409,6 +1442,8 @@ int dmlmc_level_sample_host(dmlmc_hier* h, int method, int level_f, int level_c,
 int dmlmc_set_option(dmlmc_hier* h, const char* name, double value) {
   if (h) invalidate_graphs(h);
   CHECK(h != nullptr && name != nullptr, "set_option: bad arguments");
+  if (std::strcmp(name, "fuse_res") == 0) { h->fuse_res = value != 0.0; return 0; }
+  if (std::strcmp(name, "adaptive_poll") == 0) { h->adaptive_poll = value != 0.0; return 0; }
   if (std::strcmp(name, "fuse_io") == 0) { h->fuse_io = value != 0.0; return 0; }
   if (std::strcmp(name, "dense_split_bf16") == 0) { h->dense_split_bf16 = value != 0.0; return 0; }
   if (std::strcmp(name, "use_graphs") == 0) { h->use_graphs = value != 0.0; return 0; }

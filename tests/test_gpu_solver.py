@@ -253,13 +253,18 @@ def test_fused_vcycle_io_is_bit_identical(mg128, k):
     written by the last smoother factor, prolongation without the zero read) changes no bit of the solve"""
     mg, tp, A = mg128
     B = torch.from_numpy(np.ascontiguousarray(probes(mg.level_shapes[0], k, seed=11))).cuda()
-    X1, it1, _ = mg.dev.fgmres(0, B, 1e-12)
-    mg.set_option("fuse_io", 0)
+    X2, it2, _ = mg.dev.fgmres(0, B, 1e-12)          # default: also fuse_res (the residual stored as BF16: not bit-identical)
+    mg.set_option("fuse_res", 0)
     try:
+        X1, it1, _ = mg.dev.fgmres(0, B, 1e-12)
+        mg.set_option("fuse_io", 0)
         X0, it0, _ = mg.dev.fgmres(0, B, 1e-12)
     finally:
         mg.set_option("fuse_io", 1)
+        mg.set_option("fuse_res", 1)
     assert np.array_equal(it0, it1) and torch.equal(X0, X1)
+    assert np.abs(it2.astype(int) - it1.astype(int)).max() <= 1
+    assert np.abs(host(X2) - host(X1)).max() < 1e-9 * np.abs(host(X1)).max()
 
 
 def test_geometric_preconditioner_of_the_level1_solve(g128):
