@@ -373,14 +373,14 @@ def main():
                 "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                 "peak_source": "MEASURED_PEAKS.json hbm_gbs" if "hbm_gbs" in peaks else "fallback 6650",
                 "frac_of_nominal_8TBs": achieved / 8000.0,
-                "avg_launch_us": 1e6 * t_step, "alg_bytes_per_launch": alg_bytes, "traffic": 36.67e6,
-                "traffic_source": "ncu --set full, profiles/r1_run10_step_bf16_ncu_full.csv: dram__bytes_read.sum (34.66 MB) + "
-                                  "dram__bytes_write.sum (2.02 MB) per launch, k = 256 (ncu replays each launch cold: the "
+                "avg_launch_us": 1e6 * t_step, "alg_bytes_per_launch": alg_bytes, "traffic": 36.8e6,
+                "traffic_source": "ncu --set full, profiles/r1_run22_step_t2_ncu.md: dram__bytes_read.sum (34.6 MB) + "
+                                  "dram__bytes_write.sum (1.8-3.1 MB) per launch, k = 256 (ncu replays each launch cold: the "
                                   "input comes from DRAM there, the output stays in L2)",
-                "limiter": "FP32 pipe, not HBM: the two %.1f MB ping-pong vectors of the polynomial product stay in the "
-                           "126 MB L2 across the %d consecutive launches (DRAM traffic per launch is about half the "
-                           "algorithmic bytes, DRAM 19 %% busy) and ncu shows issue slots 60 %%, FP32 pipe 44 %% + integer pipe 40 %% busy, "
-                           "L2-latency stalls dominating the rest; "
+                "limiter": "instruction issue / integer ALU pipe, not HBM: the two %.1f MB ping-pong vectors of the polynomial "
+                           "product stay in the 126 MB L2 across the %d consecutive launches (DRAM traffic per launch is about "
+                           "half the algorithmic bytes) and ncu shows issue slots 62 %%, integer ALU pipe 51 %% (BF16 <-> FP32 "
+                           "conversions), FMA pipe 26 %%, L2 26 %% busy, 78 registers, 31 %% of the warp slots; "
                            "spmm_level0 below is the same operator streaming complex128 / complex64 from HBM"
                            % (n0 * kc * sb / 1e6, m - 1),
                 "smooth_call_us": 1e6 * t_full, "chunk_cols": kc}

@@ -88,6 +88,9 @@ struct dmlmc_hier {
   int pre_smooth = 0;                     // 0: V-cycle = coarse correction + post-smoothing (default), 1: pre- and post-smoothing
   int smoother_half = 1;                  // BF16 storage of the level-0 smoother's intermediate vectors (c64 cycle)
   int dense_direct_exact = 1;             // a dense level solved directly (not from a finer level) uses its FP32 copy
+  int dot32 = 0;                          // Gram-Schmidt coefficients from complex64 copies of the basis vectors: OFF -- measured on
+                                          // B200 (profiles/r1_run32_tune_dot32.jsonl): the basis loses orthogonality at the 1e-7
+                                          // level, a cycle then stagnates near 1e-7 and the solve needs 43 iterations instead of 8
   int fuse_res = 1;                       // the V-cycle's residual before the post-smoother is written as BF16 (level-0 stencil)
   int adaptive_poll = 1;                  // skip the per-iteration convergence poll until one iteration before the count the
                                           // previous solve of the level needed (columns that are done do no work, so this is safe)
@@ -701,9 +704,19 @@ int vcycle(dmlmc_hier* h, int level0, const void* Bin, void* Xout, int k, const 
 int multi_dot(dmlmc_hier* h, const Z* Vbase, size_t vstride, int nv, const Z* W, int n, int k, Z* partial, Z* out, int accumulate) {
   const int nchunks = (n + ROWS_PER_CHUNK - 1) / ROWS_PER_CHUNK;
   dim3 blk(DOT_TX, DOT_TY), grd((k + DOT_TX - 1) / DOT_TX, nchunks);
-  multi_dot_kernel<<<grd, blk, 0, h->stream>>>(Vbase, vstride, nv, W, n, k, ROWS_PER_CHUNK, partial);
+  multi_dot_kernel<double><<<grd, blk, 0, h->stream>>>(Vbase, vstride, nv, W, n, k, ROWS_PER_CHUNK, partial);
   LAUNCH_CHECK(h);
   sum_partials_kernel<<<nblocks((size_t)nv * k, 32), dim3(32, 8), 0, h->stream>>>(partial, nchunks, nv * k, out, accumulate);
+  LAUNCH_CHECK(h);
+  return 0;
+}
+// the same with the V_i read from their complex64 copies
+int multi_dot32(dmlmc_hier* h, const Cx<float>* Vbase, size_t vstride, int nv, const Z* W, int n, int k, Z* partial, Z* out) {
+  const int nchunks = (n + ROWS_PER_CHUNK - 1) / ROWS_PER_CHUNK;
+  dim3 blk(DOT_TX, DOT_TY), grd((k + DOT_TX - 1) / DOT_TX, nchunks);
+  multi_dot_kernel<float><<<grd, blk, 0, h->stream>>>(Vbase, vstride, nv, W, n, k, ROWS_PER_CHUNK, partial);
+  LAUNCH_CHECK(h);
+  sum_partials_kernel<<<nblocks((size_t)nv * k, 32), dim3(32, 8), 0, h->stream>>>(partial, nchunks, nv * k, out, 0);
   LAUNCH_CHECK(h);
   return 0;
 }
@@ -850,8 +863,10 @@ int fgmres(dmlmc_hier* h, int level, const Z* B, Z* X, int k, double tol, int re
   Cx<float>* V32 = nullptr;
   {
     dmlmc_hier* hv = h->prec_hier[level] ? h->prec_hier[level] : h;
-    if (h->fuse_io && hv->fuse_io && hv->inner_prec == DMLMC_C64) RET(ws_get<Cx<float>>(h, nk, &V32));
+    if (h->fuse_io && hv->fuse_io && hv->inner_prec == DMLMC_C64) RET(ws_get<Cx<float>>(h, h->dot32 ? nk * (m + 1) : nk, &V32));
   }
+  const bool dot32 = V32 != nullptr && h->dot32;       // complex64 copies of ALL basis vectors, read by the Gram-Schmidt dots
+  auto v32 = [&](int j) -> Cx<float>* { return V32 == nullptr ? nullptr : (dot32 ? V32 + (size_t)j * nk : V32); };
 
   CU(cudaMemsetAsync(X, 0, nk * sizeof(Z), h->stream));
   const Z* Rsrc = B;
@@ -869,16 +884,17 @@ int fgmres(dmlmc_hier* h, int level, const Z* B, Z* X, int k, double tol, int re
     mode = 2;
     RET(read_nactive(h, s.n_active, &nact));
     if (nact == 0 || total_it >= maxiter) break;
-    col_scale_kernel<<<nblocks(nk, 256), 256, 0, h->stream>>>(Rsrc, s.scale, Vb, nk, k, V32); LAUNCH_CHECK(h);
+    col_scale_kernel<<<nblocks(nk, 256), 256, 0, h->stream>>>(Rsrc, s.scale, Vb, nk, k, v32(0)); LAUNCH_CHECK(h);
     int j = 0;
     for (; j < m; ++j) {
       Z* Vj = Vb + (size_t)j * nk;
       Z* Zj = Zb + (size_t)j * nk;
       auto body = [&]() -> int {
-        RET(precond(h, level, Vj, Zj, k, V32));
+        RET(precond(h, level, Vj, Zj, k, v32(j)));
         RET((launch_op<double, M_AX>(h, level, Zj, nullptr, W, ZERO, ZERO, k)));
         // classical Gram-Schmidt, optionally with one re-orthogonalisation pass
-        RET(multi_dot(h, Vb, nk, j + 1, W, n, k, partial, s.hsum, 0));
+        if (dot32) RET(multi_dot32(h, V32, nk, j + 1, W, n, k, partial, s.hsum));
+        else       RET(multi_dot(h, Vb, nk, j + 1, W, n, k, partial, s.hsum, 0));
         if (h->reorth) {
           RET(multi_axpy(h, Vb, nk, j + 1, s.hsum, W, n, k, -1.0));
           RET(multi_dot(h, Vb, nk, j + 1, W, n, k, partial, s.y, 0));       // s.y used as scratch [(j+1)][k]
@@ -892,7 +908,7 @@ int fgmres(dmlmc_hier* h, int level, const Z* B, Z* X, int k, double tol, int re
         }
         CU(cudaMemsetAsync(s.n_active, 0, sizeof(int), h->stream));
         gmres_step_kernel<<<gk, 128, 0, h->stream>>>(s, j, tol); LAUNCH_CHECK(h);
-        if (j + 1 < m) { col_scale_kernel<<<nblocks(nk, 256), 256, 0, h->stream>>>(W, s.scale, Vb + (size_t)(j + 1) * nk, nk, k, V32); LAUNCH_CHECK(h); }
+        if (j + 1 < m) { col_scale_kernel<<<nblocks(nk, 256), 256, 0, h->stream>>>(W, s.scale, Vb + (size_t)(j + 1) * nk, nk, k, v32(j + 1)); LAUNCH_CHECK(h); }
         return 0;
       };
       RET(run_iteration(h, h->use_graphs && k <= h->graph_max_k, level, k, mark, j, m, tol, body));
@@ -1061,7 +1077,7 @@ size_t fgmres_bytes(dmlmc_hier* h, int level, int k, int m) {
   size_t vb = vcycle_bytes(h, level, k, sizeof(Z));
   if (h->prec_hier[level]) vb = std::max(vb, vcycle_bytes(h->prec_hier[level], h->prec_level[level], k, sizeof(Z)) + (size_t)(1 << 16));
   b += vb;
-  b += align_up(nk * sizeof(Cx<float>));   // complex64 copy of the current basis vector
+  b += align_up(nk * (h->dot32 ? m + 1 : 1) * sizeof(Cx<float>));   // complex64 copy of the current basis vector (all: dot32)
   b += 2 * align_up(nk * z);          // staging buffers of the graph-replayed V-cycle
   return b + (1 << 16);
 }
@@ -1442,6 +1458,7 @@ int dmlmc_level_sample_host(dmlmc_hier* h, int method, int level_f, int level_c,
 int dmlmc_set_option(dmlmc_hier* h, const char* name, double value) {
   if (h) invalidate_graphs(h);
   CHECK(h != nullptr && name != nullptr, "set_option: bad arguments");
+  if (std::strcmp(name, "dot32") == 0) { h->dot32 = value != 0.0; return 0; }
   if (std::strcmp(name, "fuse_res") == 0) { h->fuse_res = value != 0.0; return 0; }
   if (std::strcmp(name, "adaptive_poll") == 0) { h->adaptive_poll = value != 0.0; return 0; }
   if (std::strcmp(name, "fuse_io") == 0) { h->fuse_io = value != 0.0; return 0; }

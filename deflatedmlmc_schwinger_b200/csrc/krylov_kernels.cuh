@@ -30,8 +30,12 @@ constexpr int DOT_TX = 32, DOT_TY = 8;
 // partial[chunk][i][col] = sum_{r in chunk} conj(V_i[r][col]) * W[r][col],  V_i = Vbase + i*vstride
 // grid (ceil(k/32), nchunks), block (32, 8).  Deterministic: fixed row chunking, no atomics, so a
 // column's result does not depend on which batch it is part of.
+// VT = float (option dot32, OFF): the V_i are read from complex64 copies (arithmetic stays complex128) for the Gram-Schmidt
+// coefficients only.  Half the bytes of the pass, but the basis then loses orthogonality at the 1e-7 level and a GMRES
+// cycle stagnates near that relative residual: measured 43 outer iterations instead of 8 -- kept as a recorded negative.
+template <typename VT>
 __global__ void __launch_bounds__(256)
-multi_dot_kernel(const Z* __restrict__ Vbase, size_t vstride, int nv, const Z* __restrict__ W,
+multi_dot_kernel(const Cx<VT>* __restrict__ Vbase, size_t vstride, int nv, const Z* __restrict__ W,
                  int n, int k, int rows_per_chunk, Z* __restrict__ partial) {
   __shared__ Z red[DOT_TY][DOT_NI][DOT_TX + 1];
   const int tx = threadIdx.x, ty = threadIdx.y;
@@ -49,7 +53,10 @@ multi_dot_kernel(const Z* __restrict__ Vbase, size_t vstride, int nv, const Z* _
         const Z w = ldc_ro<double>(W, off);
 #pragma unroll
         for (int i = 0; i < DOT_NI; ++i)
-          if (i0 + i < nv) zfma_conj(acc[i], ldc_ro<double>(Vbase, (size_t)(i0 + i) * vstride + off), w);
+          if (i0 + i < nv) {
+            const Cx<VT> v = ldc_ro<VT>(Vbase, (size_t)(i0 + i) * vstride + off);
+            zfma_conj(acc[i], cx<double>((double)v.re, (double)v.im), w);
+          }
       }
     }
 #pragma unroll

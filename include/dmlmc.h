@@ -182,7 +182,18 @@ int dmlmc_level_sample_host(dmlmc_hier* h, int method, int level_f, int level_c,
  *   "stencil_t2"   1 (default): the BF16 factor kernel computes two t-adjacent sites per thread (8 row loads per pair
  *                  instead of 10); "stencil_t2_by", "stencil_t2_bz": its thread-block tile (default 2 x 2)
  *   "stencil_by", "stencil_bz"   site tile (t, x) of the level-0 kernel's thread block (default 4 x 4)
- *   "stencil_minb" 2 | 3 (default): resident 512-thread blocks per SM the level-0 kernel is compiled for */
+ *   "stencil_minb" 2 | 3 (default): resident 512-thread blocks per SM the level-0 kernel is compiled for
+ *   "dense_split_bf16"  1 (default): where a small level's (1024 <= n <= 4096) dense inverse is the preconditioner of that
+ *                  level's own solve it is applied as ONE tcgen05 GEMM on split-BF16 operands ([hi|lo|hi] x [hi;hi;lo],
+ *                  error ~1e-5) instead of the FP32 SIMT kernel (75 us against 305 us at n = 2048, k = 256)
+ *   "fuse_io"      1 (default): the complex64 copy of a Krylov vector (the V-cycle's input) is written by the kernel that
+ *                  normalises it, the last smoother factor writes complex128 straight into Z_j, the prolongation after the
+ *                  coarse solve does not read the zero vector (bit-identical to 0)
+ *   "fuse_res"     1 (default, needs fuse_io): the V-cycle's residual before the post-smoother is stored as BF16, so that
+ *                  every factor but the last runs in the packed BF16 -> BF16 kernel
+ *   "adaptive_poll" 1 (default): the per-iteration convergence poll (a host read) is skipped until one iteration before the
+ *                  count the previous solve with the same (level, k, tol) needed, and done every 4th iteration at least
+ *   "dot32"        0 (default; 1 measured harmful): Gram-Schmidt coefficients from complex64 copies of the basis */
 int dmlmc_set_option(dmlmc_hier* h, const char* name, double value);
 
 /* number of kernels launched by this handle since creation (bench.py's gpu_launches) */

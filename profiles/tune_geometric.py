@@ -22,7 +22,7 @@ for cfg in configs:
     mg.setup(dof=tp["dof"], aggrs=tp["aggrs"], max_levels=tp["max_nr_levels"], acc_eigvs=tp["accuracy_mg_eigvs"], params=tp, test_vectors=tvs)
     setup_s = time.time() - t0
     mg.skip_level = True
-    for name in ("smoother_half", "dense_tensor_min_n", "fuse_io", "dense_split_bf16", "fuse_res", "adaptive_poll"):
+    for name in ("smoother_half", "dense_tensor_min_n", "fuse_io", "dense_split_bf16", "fuse_res", "adaptive_poll", "dot32"):
         if name in cfg:
             mg.set_option(name, cfg[name])
     dev = mg.dev
