@@ -36,6 +36,8 @@ _SIGS = {
     "dmlmc_set_dense_inverse_device": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_void_p]),
     "dmlmc_set_smoother": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_void_p,
                                           ctypes.c_double, ctypes.c_double]),
+    "dmlmc_set_smoother_eo": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_void_p,
+                                             ctypes.c_double, ctypes.c_double]),
     "dmlmc_set_smoother_storage": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.c_int]),
     "dmlmc_set_perm": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_void_p,
                                       ctypes.c_void_p]),
@@ -46,6 +48,7 @@ _SIGS = {
     "dmlmc_coarsest_apply": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int]),
     "dmlmc_smooth": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int]),
     "dmlmc_vcycle": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int]),
+    "dmlmc_precondition": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int]),
     "dmlmc_dotc": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_void_p]),
     "dmlmc_deflate": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p, ctypes.c_int]),
     "dmlmc_probe_expand": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_void_p]),
@@ -199,6 +202,12 @@ class Hierarchy:
                                            float(np.real(p0)), float(np.imag(p0))))
         _check(self.lib.dmlmc_set_smoother_storage(self.h, level, 1 if storage16 else 0))
 
+    def set_smoother_eo(self, level, nu, p0):
+        """polynomial p(S) = p0 * prod_i (I - nu[i] S) in the even-odd Schur complement S of a stencil level"""
+        nu, p = _host_c128(np.asarray(nu).reshape(-1))
+        _check(self.lib.dmlmc_set_smoother_eo(self.h, level, nu.shape[0], p if nu.shape[0] else None,
+                                              float(np.real(p0)), float(np.imag(p0))))
+
     def set_perm(self, level, shift, cols=None, vals=None):
         if cols is None:
             _check(self.lib.dmlmc_set_perm(self.h, level, int(shift), 0, None, None))
@@ -282,6 +291,14 @@ class Hierarchy:
         X = self.torch.empty_like(B)
         _check(self.lib.dmlmc_vcycle(self.h, level, self._prec(B), self._chk(B, self.sizes[level]), self._chk(X), B.shape[1]))
         return X
+
+    def precondition(self, level, V):
+        """Z = M^{-1} V (complex128): the preconditioner of the level's FGMRES, as the solver applies it"""
+        assert V.dtype == self.torch.complex128
+        self.ensure_workspace(level, V.shape[1], 1)
+        Z = self.torch.empty_like(V)
+        _check(self.lib.dmlmc_precondition(self.h, level, self._chk(V, self.sizes[level]), self._chk(Z), V.shape[1]))
+        return Z
 
     def dotc(self, X, Y):
         self.ensure_workspace(0, X.shape[1], 1)

@@ -52,6 +52,8 @@ struct Level {
   int* tr_rows = nullptr; int* tr_cblk = nullptr; int tr_m = 0;     // indexed (geometric) aggregates, else closed form
   // smoother polynomial in product form: p(A) = p0 * prod_i (I - nu_i A)
   bool has_smoother = false; std::vector<Cx<double>> nu; Cx<double> p0; bool smoother16 = true;
+  // the same for the even-odd Schur complement S = c - H_eo H_oe / c of a stencil level (dmlmc_set_smoother_eo)
+  bool has_eo = false; std::vector<Cx<double>> nu_eo; Cx<double> p0_eo;
   bool has_perm = false; int shift = 0, perm_nnz = 0; int* perm_cols = nullptr;
   int defl_d = 0; Cx<double>* defl_V = nullptr;
   bool has_dense = false; Cx<double>* minv_d = nullptr; Cx<float>* minv_f = nullptr; float4* minv4 = nullptr;
@@ -81,6 +83,8 @@ struct dmlmc_hier {
   int stencil_by = 4, stencil_bz = 4;     // site tile (t, x) of the stencil kernel's thread block
   int bsr_threads = 128;                  // threads per CTA of the packed-FP32 BSR kernel (block rows per CTA = this / threads per row)
   int stencil_t2 = 1;                     // two t-adjacent sites per thread in the factor kernel
+  int eo_packs = 2;                           // column packs per thread of that kernel (2: 16-byte loads, four columns share the links)
+  int eo_by = 2, eo_bz = 2;                   // thread-block tile (t/2, x) of the even-odd hop kernel
   int stencil_t2_by = 2, stencil_t2_bz = 2;   // its thread-block tile: (32 packs, 2 thread rows = 4 sites in t, 2 in x)
   int stencil_smem = 0;                   // shared-memory-tiled variant of the packed-FP32 factor kernel
   int stencil_fast = 1;                   // packed-FP32 (FFMA2) kernel for the BF16-stored smoother factors
@@ -88,6 +92,7 @@ struct dmlmc_hier {
   int pre_smooth = 0;                     // 0: V-cycle = coarse correction + post-smoothing (default), 1: pre- and post-smoothing
   int smoother_half = 1;                  // BF16 storage of the level-0 smoother's intermediate vectors (c64 cycle)
   int dense_direct_exact = 1;             // a dense level solved directly (not from a finer level) uses its FP32 copy
+  int smoother_eo = 1;                    // even-odd (Schur complement) form of the level-0 post-smoother when one is set
   int dot32 = 0;                          // Gram-Schmidt coefficients from complex64 copies of the basis vectors: OFF -- measured on
                                           // B200 (profiles/r1_run32_tune_dot32.jsonl): the basis loses orthogonality at the 1e-7
                                           // level, a cycle then stagnates near 1e-7 and the solve needs 43 iterations instead of 8
@@ -454,6 +459,73 @@ int launch_residual_half(dmlmc_hier* h, int level, const void* X, const void* B,
   return 0;
 }
 
+// ---- even-odd post-smoother of a stencil level (see wilson_hop_eo_kernel) ---------------------------------------------
+// Z[n][k] (complex128) = Xc + S_eo(B - A Xc):  Xc, B complex64 full-lattice vectors, t0 / t1 the level's two work vectors
+// (n k complex64 each = eight BF16 half-lattice buffers).
+template <bool HAS2, bool HOUT, bool ZOUT>
+int launch_hop_eo(dmlmc_hier* h, const Level& L, int p, const uint2* Inq, const uint2* In2, uint2* Outp, Cx<double> a, Cx<double> b,
+                  int kp, const void* Xc, void* Z) {
+  const bool two = h->eo_packs == 2 && (kp % 2) == 0;
+  const int kt = two ? kp / 2 : kp;                      // threads along the columns
+  int bx = 1; while (bx < 32 && bx < kt) bx *= 2;
+  int by = std::max(1, std::min(h->eo_by, L.LT / 2)), bz = std::max(1, std::min(h->eo_bz, L.LX));
+  while (bx * by * bz > 256) { if (bz > 1) bz /= 2; else by /= 2; }
+  dim3 blk(bx, by, bz), grd((kt + bx - 1) / bx, (L.LT / 2 + by - 1) / by, (L.LX + bz - 1) / bz);
+  if (two)
+    wilson_hop_eo_kernel<HAS2, HOUT, ZOUT, 2><<<grd, blk, 0, h->stream>>>(L.LX, L.LT, p, L.links4, Inq, In2, Outp, (float)a.re, (float)a.im,
+                                                                          (float)b.re, (float)b.im, (uint32_t)kp,
+                                                                          (const Pack<float, 2>*)Xc, (double2*)Z);
+  else
+    wilson_hop_eo_kernel<HAS2, HOUT, ZOUT, 1><<<grd, blk, 0, h->stream>>>(L.LX, L.LT, p, L.links4, Inq, In2, Outp, (float)a.re, (float)a.im,
+                                                                          (float)b.re, (float)b.im, (uint32_t)kp,
+                                                                          (const Pack<float, 2>*)Xc, (double2*)Z);
+  LAUNCH_CHECK(h);
+  return 0;
+}
+bool smoother_eo_ok(dmlmc_hier* h, int level, int k) {
+  Level& L = h->lv[level];
+  return h->smoother_eo && h->fuse_io && h->smoother_half && L.has_eo && L.smoother16 && L.kind == 0 && (k % 2) == 0 &&
+         !L.nu_eo.empty() && (L.LT % 2) == 0 && (L.LX % 2) == 0 && L.d.diag.im == 0.0 && L.links4 != nullptr;
+}
+int smooth_eo(dmlmc_hier* h, int level, const void* Xc, const void* B, void* t0, void* t1, Cx<double>* Z, int k) {
+  Level& L = h->lv[level];
+  const int kp = k / 2, m = (int)L.nu_eo.size();
+  const size_t H = (size_t)(L.n / 2) * kp;                // uint2 elements of one half-lattice buffer
+  uint2* T0 = reinterpret_cast<uint2*>(t0); uint2* T1 = reinterpret_cast<uint2*>(t1);
+  uint2 *Re = T0, *Ro = T0 + H, *W = T0 + 2 * H, *Y[2] = {T1, T1 + H};
+  const double c = L.d.diag.re;
+  const Cx<double> ONE = {1.0, 0.0}, NIC = {-1.0 / c, 0.0}, IC = {1.0 / c, 0.0};
+  // r = B - A Xc, BF16, checkerboard layout [even | odd]
+  {
+    StencilDev<float> op; op.LX = L.LX; op.LT = L.LT; op.Ut = L.f.Ut; op.Ux = L.f.Ux; op.diag = L.f.diag;
+    dim3 blk, grd; stencil_dims(h, L, kp, blk, grd);
+    stencil_kernel<float, 2, M_RES, 3, false, true, 0, false, true><<<grd, blk, 0, h->stream>>>(op, Xc, (const Pack<float, 2>*)B, Re,
+                                                                                                 cx<float>(0.f, 0.f), cx<float>(0.f, 0.f), kp);
+    LAUNCH_CHECK(h);
+  }
+  // r^_e = r_e - H_eo r_o / c
+  RET((launch_hop_eo<true, true, false>(h, L, 0, Ro, Re, Y[0], ONE, NIC, kp, nullptr, nullptr)));
+  int cur = 0;
+  for (int i = 0; i < m; ++i) {
+    const Cx<double> nu = L.nu_eo[i];
+    Cx<double> a = {1.0 - nu.re * c, -nu.im * c}, b = {nu.re / c, nu.im / c};
+    RET((launch_hop_eo<false, true, false>(h, L, 1, Y[cur], nullptr, W, ONE, ONE, kp, nullptr, nullptr)));     // w_o = H_oe y_e
+    if (i < m - 1) {
+      RET((launch_hop_eo<true, true, false>(h, L, 0, W, Y[cur], Y[cur ^ 1], a, b, kp, nullptr, nullptr)));      // y_e' = a y_e + b H_eo w_o
+    } else {
+      // last factor carries p0: x_e (BF16, for x_o) and Z_e = Xc_e + x_e
+      const Cx<double> p0 = L.p0_eo;
+      const Cx<double> ap = {a.re * p0.re - a.im * p0.im, a.re * p0.im + a.im * p0.re};
+      const Cx<double> bp = {b.re * p0.re - b.im * p0.im, b.re * p0.im + b.im * p0.re};
+      RET((launch_hop_eo<true, true, true>(h, L, 0, W, Y[cur], Y[cur ^ 1], ap, bp, kp, Xc, Z)));
+    }
+    cur ^= 1;
+  }
+  // Z_o = Xc_o + (r_o - H_oe x_e) / c
+  RET((launch_hop_eo<true, false, true>(h, L, 1, Y[cur], Ro, nullptr, IC, NIC, kp, Xc, Z)));
+  return 0;
+}
+
 // the complex64 BF16-storage path of smooth_apply on the level-0 stencil can write its (accumulated) result as complex128
 bool smoother_dout_ok(dmlmc_hier* h, int level, int k) {
   Level& L = h->lv[level];
@@ -630,6 +702,12 @@ int vcycle_level(dmlmc_hier* h, int l, int level0, int lb, std::vector<VcBuf<T>>
         if constexpr (std::is_same<T, float>::value) {
           rhalf = h->fuse_res && smoother_dout_ok(h, l, w) && h->lv[l].nu.size() >= 3;
           if constexpr (std::is_same<TIO, double>::value) dout = (l == level0 && w == k && smoother_dout_ok(h, l, w));
+        }
+        bool eo = false;
+        if constexpr (std::is_same<T, float>::value && std::is_same<TIO, double>::value) eo = dout && smoother_eo_ok(h, l, w);
+        if (eo) {
+          if constexpr (std::is_same<TIO, double>::value) RET(smooth_eo(h, l, xc, bc, me.t0, me.t1, Xio, w));
+          continue;
         }
         if (rhalf) RET(launch_residual_half(h, l, xc, bc, me.t0, w));
         else       RET((launch_op<T, M_RES>(h, l, xc, bc, me.t0, ZERO, ZERO, w)));
@@ -1282,6 +1360,19 @@ int dmlmc_set_smoother(dmlmc_hier* h, int level, int nfactors, const double* nu_
   return 0;
 }
 
+int dmlmc_set_smoother_eo(dmlmc_hier* h, int level, int nfactors, const double* nu_host, double p0_re, double p0_im) {
+  if (h) invalidate_graphs(h);
+  CHECK(h && level >= 0 && level < h->n_levels, "set_smoother_eo: bad handle/level");
+  CHECK(nfactors >= 0 && (nfactors == 0 || nu_host), "set_smoother_eo: bad factors");
+  Level& L = h->lv[level];
+  CHECK(nfactors == 0 || L.kind == 0, "set_smoother_eo: the level's operator must be a Wilson stencil (dmlmc_set_stencil)");
+  L.nu_eo.resize(nfactors);
+  for (int i = 0; i < nfactors; ++i) L.nu_eo[i] = cx<double>(nu_host[2 * i], nu_host[2 * i + 1]);
+  L.p0_eo = cx<double>(p0_re, p0_im);
+  L.has_eo = nfactors > 0;
+  return 0;
+}
+
 int dmlmc_set_smoother_storage(dmlmc_hier* h, int level, int allow16) {
   if (h) invalidate_graphs(h);
   CHECK(h && level >= 0 && level < h->n_levels, "set_smoother_storage: bad handle/level");
@@ -1350,6 +1441,10 @@ int dmlmc_smooth(dmlmc_hier* h, int level, int prec, const void* R, void* E, int
 int dmlmc_vcycle(dmlmc_hier* h, int level, int prec, const void* B, void* X, int k) {
   ENTER(h); CHECK_LEVEL(h, level); CHECK_PREC(prec); CHECK(B && X && B != X && k >= 1, "vcycle: bad arguments");
   return prec == DMLMC_C128 ? vcycle<double, double>(h, level, B, X, k) : vcycle<float, float>(h, level, B, X, k);
+}
+int dmlmc_precondition(dmlmc_hier* h, int level, const void* V, void* Zout, int k) {
+  ENTER(h); CHECK_LEVEL(h, level); CHECK(V && Zout && V != Zout && k >= 1, "precondition: bad arguments");
+  return precond_eager(h, level, (const Z*)V, (Z*)Zout, k, nullptr);
 }
 int dmlmc_dotc(dmlmc_hier* h, const void* X, const void* Y, int n, int k, void* out_dev) {
   ENTER(h); CHECK(X && Y && out_dev && n >= 1 && k >= 1, "dotc: bad arguments");
@@ -1458,6 +1553,7 @@ int dmlmc_level_sample_host(dmlmc_hier* h, int method, int level_f, int level_c,
 int dmlmc_set_option(dmlmc_hier* h, const char* name, double value) {
   if (h) invalidate_graphs(h);
   CHECK(h != nullptr && name != nullptr, "set_option: bad arguments");
+  if (std::strcmp(name, "smoother_eo") == 0) { h->smoother_eo = value != 0.0; return 0; }
   if (std::strcmp(name, "dot32") == 0) { h->dot32 = value != 0.0; return 0; }
   if (std::strcmp(name, "fuse_res") == 0) { h->fuse_res = value != 0.0; return 0; }
   if (std::strcmp(name, "adaptive_poll") == 0) { h->adaptive_poll = value != 0.0; return 0; }
@@ -1472,6 +1568,9 @@ int dmlmc_set_option(dmlmc_hier* h, const char* name, double value) {
   if (std::strcmp(name, "defl_tensor") == 0) { h->defl_tensor = value != 0.0; return 0; }
   if (std::strcmp(name, "bsr_threads") == 0) { CHECK(value >= 32 && value <= 256, "bsr_threads must be in [32, 256]"); h->bsr_threads = (int)value; return 0; }
   if (std::strcmp(name, "stencil_t2") == 0) { h->stencil_t2 = value != 0.0; return 0; }
+  if (std::strcmp(name, "eo_packs") == 0) { CHECK(value == 1 || value == 2, "eo_packs must be 1 or 2"); h->eo_packs = (int)value; return 0; }
+  if (std::strcmp(name, "eo_by") == 0) { CHECK(value >= 1, "eo_by must be >= 1"); h->eo_by = (int)value; return 0; }
+  if (std::strcmp(name, "eo_bz") == 0) { CHECK(value >= 1, "eo_bz must be >= 1"); h->eo_bz = (int)value; return 0; }
   if (std::strcmp(name, "stencil_t2_by") == 0) { CHECK(value >= 1, "stencil_t2_by must be >= 1"); h->stencil_t2_by = (int)value; return 0; }
   if (std::strcmp(name, "stencil_t2_bz") == 0) { CHECK(value >= 1, "stencil_t2_bz must be >= 1"); h->stencil_t2_bz = (int)value; return 0; }
   if (std::strcmp(name, "stencil_smem") == 0) { h->stencil_smem = value != 0.0; return 0; }

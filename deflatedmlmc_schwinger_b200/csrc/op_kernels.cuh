@@ -87,7 +87,9 @@ __device__ __forceinline__ void sth2(void* base, size_t idx, const Pack<float, 2
 // DOUT (last factor of the post-smoother, MODE = M_STEP_ACC, complex64): the result Yold + c (X - w A X) is written as
 // complex128 to the array passed in the (otherwise unused) B argument instead of back to Y -- the V-cycle's output
 // lands in the outer solver's complex128 vector without a separate conversion pass.
-template <typename T, int NC, int MODE, int MINB, bool HIN = false, bool HOUT = false, int PFD = 0, bool DOUT = false>
+// EOUT (with HOUT): the BF16 output goes to the checkerboard-compressed half-lattice layout of wilson_hop_eo_kernel
+// (parity p = (x + t) & 1 array first the even, then the odd sites: [p][s][x][t/2][kp]).
+template <typename T, int NC, int MODE, int MINB, bool HIN = false, bool HOUT = false, int PFD = 0, bool DOUT = false, bool EOUT = false>
 __global__ void __launch_bounds__(512, MINB)
 stencil_kernel(StencilDev<T> op, const void* __restrict__ Xv, const Pack<T, NC>* __restrict__ B,
                void* __restrict__ Yv, Cx<T> w, Cx<T> cfin, int kp) {
@@ -149,6 +151,10 @@ stencil_kernel(StencilDev<T> op, const void* __restrict__ Xv, const Pack<T, NC>*
     double2* Yd = reinterpret_cast<double2*>(const_cast<Pack<T, NC>*>(B));
     Yd[2 * i0] = make_double2((double)o0.d[0], (double)o0.d[1]); Yd[2 * i0 + 1] = make_double2((double)o0.d[2], (double)o0.d[3]);
     Yd[2 * i1] = make_double2((double)o1.d[0], (double)o1.d[1]); Yd[2 * i1 + 1] = make_double2((double)o1.d[2], (double)o1.d[3]);
+  } else if constexpr (HOUT && EOUT) {
+    const size_t par = (size_t)((x + t) & 1), half = (size_t)(V >> 1);
+    const size_t e0 = ((par * 2) * half + (size_t)x * (LT >> 1) + (t >> 1)) * kpz + cp;
+    sth2(Yv, e0, o0); sth2(Yv, e0 + half * kpz, o1);
   } else if constexpr (HOUT) { sth2(Yv, i0, o0); sth2(Yv, i1, o1); } else { Y[i0] = o0; Y[i1] = o1; }
 }
 
@@ -311,6 +317,117 @@ stencil_step_bf16_t2_kernel(int LX, int LT, const float4* __restrict__ L4, float
   sth_c2(reinterpret_cast<uint2*>(py + spb), 0u, o1);
   sth_c2(reinterpret_cast<uint2*>(py + rowb), 0u, q0);
   sth_c2(reinterpret_cast<uint2*>(py + rowb + spb), 0u, q1);
+}
+
+// ------------------------------------------------------------------------------------------
+// Even-odd (red-black) form of the level-0 smoother.  A = c I + H with H coupling sites of opposite parity only, so
+//   A^{-1} r :  r^_e = r_e - H_eo r_o / c ;  x_e = S^{-1} r^_e ,  S = c - H_eo H_oe / c ;  x_o = (r_o - H_oe x_e) / c
+// and the polynomial approximates the inverse of the Schur complement S on the even sites: the spectrum of S is the
+// quadratic image lambda (2c - lambda) / c of A's, and a polynomial of degree d in S does what one of degree 2d in A does
+// at the cost of d applications of A (two half-lattice sweeps each): 8 outer iterations at degree 16 in S against
+// degree 36 in A (CPU experiment with the exact two-grid method, then measured on B200).
+// Half-lattice vectors are checkerboard-compressed and BF16-stored: V_p[s][x][th][kp], site t = 2 th + ((x + p) & 1).
+// One kernel does every sweep:   Out_p[site] = a * In2_p[site] + b * (H In_q)[site],   q = 1 - p
+//   * w_o  = H_oe y_e                                (a = 0: HAS2 = false)
+//   * y_e' = (1 - nu c) y_e + (nu / c) H_eo w_o      (one factor of the polynomial in S)
+//   * r^_e and x_o                                   (the two ends)
+// ZOUT: the result plus the coarse-grid correction Xc (complex64, full lattice) at the same site is written as
+// complex128 into the full-lattice vector Z (the outer solver's Z_j); HOUT: the BF16 half-lattice output is written.
+// NP = packs (of two columns) per thread: 2 -> 16-byte loads / stores and the four link loads shared by four columns.
+template <int NP> __device__ __forceinline__ void ldh_packs(const uint2* __restrict__ p, C2 (&out)[NP]) {
+  if constexpr (NP == 2) {
+    const uint4 raw = __ldg(reinterpret_cast<const uint4*>(p));
+    out[0].re = make_float2(bf_lo(raw.x), bf_lo(raw.y)); out[0].im = make_float2(bf_hi(raw.x), bf_hi(raw.y));
+    out[1].re = make_float2(bf_lo(raw.z), bf_lo(raw.w)); out[1].im = make_float2(bf_hi(raw.z), bf_hi(raw.w));
+  } else {
+    out[0] = ldh_c2(p, 0u);
+  }
+}
+template <int NP> __device__ __forceinline__ void sth_packs(uint2* __restrict__ p, const C2 (&v)[NP]) {
+  if constexpr (NP == 2) {
+    *reinterpret_cast<uint4*>(p) = make_uint4(bf_pack(v[0].re.x, v[0].im.x), bf_pack(v[0].re.y, v[0].im.y),
+                                              bf_pack(v[1].re.x, v[1].im.x), bf_pack(v[1].re.y, v[1].im.y));
+  } else {
+    sth_c2(p, 0u, v[0]);
+  }
+}
+
+template <bool HAS2, bool HOUT, bool ZOUT, int NP>
+__global__ void __launch_bounds__(256, NP == 2 ? 2 : 3)
+wilson_hop_eo_kernel(int LX, int LT, int p, const float4* __restrict__ L4, const uint2* __restrict__ Inq,
+                     const uint2* __restrict__ In2, uint2* __restrict__ Outp, float ar, float ai, float br, float bi,
+                     uint32_t kp, const Pack<float, 2>* __restrict__ Xc, double2* __restrict__ Z) {
+  const uint32_t cp = (blockIdx.x * blockDim.x + threadIdx.x) * NP;
+  const uint32_t th = blockIdx.y * blockDim.y + threadIdx.y;
+  const uint32_t x = blockIdx.z * blockDim.z + threadIdx.z;
+  const uint32_t LH = (uint32_t)LT >> 1;
+  if (cp >= kp || th >= LH || x >= (uint32_t)LX) return;
+  const uint32_t V = (uint32_t)LX * LT, VH = V >> 1;
+  const uint32_t a = (x + (uint32_t)p) & 1u;               // t offset of parity p in row x (the other parity: 1 - a)
+  const uint32_t t = 2 * th + a;
+  const uint32_t site = x * LT + t;
+  const float4* lp = L4 + site;
+  const float4 ut = __ldg(lp), utb = __ldg(lp + V), ux = __ldg(lp + 2 * V), uxb = __ldg(lp + 3 * V);
+  // neighbours, all of parity q.  Same row: th or th +- 1; rows x +- 1: the same th
+  const uint32_t th_f = a ? ((th + 1 == LH) ? 0u : th + 1) : th;          // t + 1
+  const uint32_t th_b = a ? th : ((th == 0) ? LH - 1 : th - 1);           // t - 1
+  const uint32_t xp = (x + 1 == (uint32_t)LX) ? 0u : x + 1, xm = (x == 0) ? (uint32_t)LX - 1 : x - 1;
+  const size_t kpz = kp, sp = (size_t)VH * kpz;            // spin stride
+  const uint2* qf = Inq + ((size_t)x * LH + th_f) * kpz + cp;
+  const uint2* qb = Inq + ((size_t)x * LH + th_b) * kpz + cp;
+  const uint2* qr = Inq + ((size_t)xp * LH + th) * kpz + cp;
+  const uint2* ql = Inq + ((size_t)xm * LH + th) * kpz + cp;
+  C2 f0[NP], f1[NP], b0[NP], b1[NP], r0[NP], r1[NP], l0[NP], l1[NP], c0[NP], c1[NP];
+  ldh_packs<NP>(qf, f0); ldh_packs<NP>(qf + sp, f1);
+  ldh_packs<NP>(qb, b0); ldh_packs<NP>(qb + sp, b1);
+  ldh_packs<NP>(qr, r0); ldh_packs<NP>(qr + sp, r1);
+  ldh_packs<NP>(ql, l0); ldh_packs<NP>(ql + sp, l1);
+  const size_t ic = ((size_t)x * LH + th) * kpz + cp;      // this site in the parity-p arrays
+  if constexpr (HAS2) { ldh_packs<NP>(In2 + ic, c0); ldh_packs<NP>(In2 + ic + sp, c1); }
+  const float2 b_r = make_float2(br, br), b_i = make_float2(bi, bi);
+  const float2 a_r = make_float2(ar, ar), a_i = make_float2(ai, ai);
+  C2 o0[NP], o1[NP];
+#pragma unroll
+  for (int u = 0; u < NP; ++u) {
+    // spin projections and link products as in wilson_step_site
+    C2 pa, pb, pc, pd;
+    pa.re = __fadd2_rn(f0[u].re, neg2(f1[u].re)); pa.im = __fadd2_rn(f0[u].im, neg2(f1[u].im));
+    pb.re = __fadd2_rn(b0[u].re, b1[u].re);       pb.im = __fadd2_rn(b0[u].im, b1[u].im);
+    pc.re = __fadd2_rn(r0[u].re, neg2(r1[u].im)); pc.im = __fadd2_rn(r0[u].im, r1[u].re);
+    pd.re = __fadd2_rn(l0[u].re, l1[u].im);       pd.im = __fadd2_rn(l0[u].im, neg2(l1[u].re));
+    const C2 ua = cmul_splat(ut, pa), ub = cmul_splat(utb, pb), uc = cmul_splat(ux, pc), ud = cmul_splat(uxb, pd);
+    // (H v)_0 = -(ua + ub + uc + ud);   (H v)_1 = (ua - ub) + i (uc - ud)
+    C2 h0, h1, q, tt;
+    h0.re = neg2(__fadd2_rn(__fadd2_rn(ua.re, ub.re), __fadd2_rn(uc.re, ud.re)));
+    h0.im = neg2(__fadd2_rn(__fadd2_rn(ua.im, ub.im), __fadd2_rn(uc.im, ud.im)));
+    q.re = __fadd2_rn(ua.re, neg2(ub.re));  q.im = __fadd2_rn(ua.im, neg2(ub.im));
+    tt.re = __fadd2_rn(uc.re, neg2(ud.re)); tt.im = __fadd2_rn(uc.im, neg2(ud.im));
+    h1.re = __fadd2_rn(q.re, neg2(tt.im));
+    h1.im = __fadd2_rn(q.im, tt.re);
+    // o = a c + b h
+    o0[u].re = __ffma2_rn(neg2(b_i), h0.im, __fmul2_rn(b_r, h0.re));
+    o0[u].im = __ffma2_rn(b_i, h0.re, __fmul2_rn(b_r, h0.im));
+    o1[u].re = __ffma2_rn(neg2(b_i), h1.im, __fmul2_rn(b_r, h1.re));
+    o1[u].im = __ffma2_rn(b_i, h1.re, __fmul2_rn(b_r, h1.im));
+    if constexpr (HAS2) {
+      o0[u].re = __ffma2_rn(neg2(a_i), c0[u].im, __ffma2_rn(a_r, c0[u].re, o0[u].re));
+      o0[u].im = __ffma2_rn(a_i, c0[u].re, __ffma2_rn(a_r, c0[u].im, o0[u].im));
+      o1[u].re = __ffma2_rn(neg2(a_i), c1[u].im, __ffma2_rn(a_r, c1[u].re, o1[u].re));
+      o1[u].im = __ffma2_rn(a_i, c1[u].re, __ffma2_rn(a_r, c1[u].im, o1[u].im));
+    }
+  }
+  if constexpr (HOUT) { sth_packs<NP>(Outp + ic, o0); sth_packs<NP>(Outp + ic + sp, o1); }
+  if constexpr (ZOUT) {
+    const size_t j0 = (size_t)site * kpz + cp, j1 = ((size_t)V + site) * kpz + cp;     // full-lattice rows of the site
+#pragma unroll
+    for (int u = 0; u < NP; ++u) {
+      const Pack<float, 2> e0 = Xc[j0 + u], e1 = Xc[j1 + u];
+      Z[2 * (j0 + u)]     = make_double2((double)e0.d[0] + (double)o0[u].re.x, (double)e0.d[1] + (double)o0[u].im.x);
+      Z[2 * (j0 + u) + 1] = make_double2((double)e0.d[2] + (double)o0[u].re.y, (double)e0.d[3] + (double)o0[u].im.y);
+      Z[2 * (j1 + u)]     = make_double2((double)e1.d[0] + (double)o1[u].re.x, (double)e1.d[1] + (double)o1[u].im.x);
+      Z[2 * (j1 + u) + 1] = make_double2((double)e1.d[2] + (double)o1[u].re.y, (double)e1.d[3] + (double)o1[u].im.y);
+    }
+  }
 }
 
 // Shared-memory-tiled variant of the same factor kernel (option "stencil_smem", OFF by default: measured on B200 at

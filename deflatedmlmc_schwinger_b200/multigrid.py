@@ -142,6 +142,20 @@ def prolongator_csr_indexed(pvals, cblk):
     return csr_matrix((pvals.ravel(), indices, np.arange(n + 1) * nvec), shape=(n, (int(cblk.max()) + 1) * nvec))
 
 
+def even_odd_schur(A0, LX, LT):
+    """S = c - H_eo H_oe / c of the level-0 operator A = c I + H (row i = s*V + x*LT + t, parity (x + t) & 1): the even-odd
+    Schur complement whose inverse the even-odd smoother approximates.  Returns (S as csr on the even sites, c)."""
+    A0 = csr_matrix(A0)
+    s, x, t = np.meshgrid(np.arange(2), np.arange(LX), np.arange(LT), indexing='ij')
+    par = ((x + t) & 1).ravel()
+    ie, io = np.where(par == 0)[0], np.where(par == 1)[0]
+    c = A0.diagonal()[0]
+    Aee = A0[ie][:, ie]
+    if abs(Aee - c * identity(len(ie), format='csr')).max() > 1e-13 or abs(c.imag) > 0 or LX % 2 or LT % 2:
+        raise Exception("even-odd smoother: the operator does not have the form c I + H with H odd-even")
+    return (c * identity(len(ie), format='csr') - (A0[ie][:, io] @ A0[io][:, ie]) / c).tocsr(), c.real
+
+
 def harmonic_ritz_inv_roots(A, degree, seed=7):
     """Inverse roots 1/theta_i of the degree-`degree` GMRES residual polynomial of A for a fixed
     random vector (harmonic Ritz values of an Arnoldi run), in Leja order for stability."""
@@ -297,7 +311,7 @@ class MG:
     def __init__(self, A, smooth_iters=2, smoother_degree=80, restart=40, inner_precision="c64",
                  device=None, dense_coarse_threshold=8192, pre_smooth=False, aggregation="reference",
                  geometric_precond=True, precond_degree=36, precond_blocks=(4, 4), precond_coarse_degree=None,
-                 level0_block=1):
+                 level0_block=1, precond_eo_degree=16, eo_degree=None):
         self.level_nr = 0
         self.ml = []
         self.A = A
@@ -335,6 +349,11 @@ class MG:
         self.precond_blocks = tuple(precond_blocks)
         self.precond_coarse_degree = 16 if precond_coarse_degree is None else precond_coarse_degree
         self.level0_block = int(level0_block)    # BSR block size of level 0 when it is not a Wilson stencil
+        # even-odd (Schur complement) form of the level-0 post-smoother: degree of its polynomial on THIS hierarchy
+        # (eo_degree) and on the geometric preconditioner hierarchy of level 0 (precond_eo_degree); None / 0 = not used
+        self.eo_degree = eo_degree
+        self.precond_eo_degree = precond_eo_degree
+        self.eo_poly = None
         self.precond_mg = None                   # geometric hierarchy preconditioning the level-0 solve
         self.precond_mg1 = None                  # ... and the level-1 solve (lattices whose level 1 has no dense inverse)
 
@@ -523,6 +542,21 @@ class MG:
             self.smoother_degrees_used.append(d)
             self.smoother_storage.append(storage)
             dev.set_smoother(i, nu, p0, storage16=(storage == 'bf16'))
+            if i == 0 and self.eo_degree and self.level0_format == "stencil" and storage == 'bf16':
+                # polynomial in the even-odd Schur complement: degree d there ~ degree 2d in A at the cost of d applications
+                try:
+                    S, _c = even_odd_schur(lv[0].A, dims[1] if len(dims) > 1 else dims[0], dims[0])
+                    de = int(self.eo_degree)
+                    while de >= 2:
+                        om = harmonic_ritz_inv_roots(S, de)
+                        nue, p0e = smoother_product_form(om)
+                        if smoother_storage_error(S, om, nue, p0e, 'bf16') < 0.15:
+                            dev.set_smoother_eo(0, nue, p0e)
+                            self.eo_poly = (nue, p0e)
+                            break
+                        de = (3 * de) // 4
+                except Exception:
+                    self.eo_poly = None
         if use_permuted:
             for i in range(nl):
                 if i == 0:
@@ -588,7 +622,7 @@ class MG:
         degs = [self.precond_degree] + [self.precond_coarse_degree] * (levels - 1)
         pm = MG(self.A, smoother_degree=degs, restart=self.restart, inner_precision=self.inner_precision,
                 device=self.device, dense_coarse_threshold=self.dense_coarse_threshold, pre_smooth=self.pre_smooth,
-                aggregation="geometric", precond_blocks=self.precond_blocks)
+                aggregation="geometric", precond_blocks=self.precond_blocks, eo_degree=self.precond_eo_degree)
         p2 = dict(params)
         p2['use_permuted'] = False
         p2['latt_dims'] = [LT, LX]

@@ -84,6 +84,12 @@ int dmlmc_set_dense_inverse_device(dmlmc_hier* h, int level, int n, const void* 
  * multigrid.py:393-394 / 438-439 (FGMRES is flexible: parity is on the converged solve). */
 int dmlmc_set_smoother(dmlmc_hier* h, int level, int nfactors, const double* nu_host,
                        double p0_re, double p0_im);
+/* the same polynomial form for the even-odd Schur complement S = c - H_eo H_oe / c of a stencil level (A = c I + H, H couples
+ * sites of opposite parity): p(S) = p0 * prod_i (I - nu_i S).  When set (and option "smoother_eo" = 1, default) the complex64
+ * V-cycle's post-smoother on that level is  x += [x_e ; x_o],  r^_e = r_e - H_eo r_o / c,  x_e = p(S) r^_e,
+ * x_o = (r_o - H_oe x_e) / c  -- a polynomial of degree d in S does the work of one of degree 2d in A at the cost of d
+ * operator applications (replaces lgmres, multigrid.py:393-394,438-439, like dmlmc_set_smoother). nfactors = 0 removes it. */
+int dmlmc_set_smoother_eo(dmlmc_hier* h, int level, int nfactors, const double* nu_host, double p0_re, double p0_im);
 /* allow16 = 0: this level's smoother keeps its intermediate vectors in FP32 even when option "smoother_half"
  * is on (the setup sets it when the polynomial is not stable enough for BF16 storage on that level) */
 int dmlmc_set_smoother_storage(dmlmc_hier* h, int level, int allow16);
@@ -107,6 +113,10 @@ int dmlmc_coarsest_apply(dmlmc_hier* h, int prec, const void* B, void* X, int k)
 int dmlmc_smooth(dmlmc_hier* h, int level, int prec, const void* R, void* E, int k);
 /* X = V-cycle(B) from `level` down to the coarsest   MG.one_mg_step (multigrid.py:369-447) */
 int dmlmc_vcycle(dmlmc_hier* h, int level, int prec, const void* B, void* X, int k);
+/* Z = M^{-1} V, complex128 in and out: exactly the preconditioner the level's FGMRES applies (the M= argument of pyamg
+ * fgmres at multigrid.py:362, i.e. one_mg_step, :369-447) -- the V-cycle in the inner precision on this hierarchy, or on
+ * the hierarchy attached with dmlmc_set_preconditioner. */
+int dmlmc_precondition(dmlmc_hier* h, int level, const void* V, void* Z, int k);
 /* out[c] = sum_r conj(X[r][c]) Y[r][c]   np.vdot (utils.py:249,336,353); out = k complex128 (device) */
 int dmlmc_dotc(dmlmc_hier* h, const void* X, const void* Y, int n, int k, void* out_dev);
 /* X -= V (V^H X) with the level's deflation vectors   utils.py:224,266 */

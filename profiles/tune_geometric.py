@@ -17,12 +17,13 @@ configs = [dict(degree=d) for d in (28, 32, 36, 40)] + [dict(degree=32, smoother
 if len(sys.argv) > 1:
     configs = json.loads(sys.argv[1])
 for cfg in configs:
-    mg = multigrid.MG(A, smoother_degree=80, precond_degree=cfg["degree"], precond_blocks=tuple(cfg.get("blocks", (4, 4))))
+    mg = multigrid.MG(A, smoother_degree=80, precond_degree=cfg["degree"], precond_blocks=tuple(cfg.get("blocks", (4, 4))),
+                      precond_eo_degree=cfg.get("eo_degree", 16))
     t0 = time.time()
     mg.setup(dof=tp["dof"], aggrs=tp["aggrs"], max_levels=tp["max_nr_levels"], acc_eigvs=tp["accuracy_mg_eigvs"], params=tp, test_vectors=tvs)
     setup_s = time.time() - t0
     mg.skip_level = True
-    for name in ("smoother_half", "dense_tensor_min_n", "fuse_io", "dense_split_bf16", "fuse_res", "adaptive_poll", "dot32"):
+    for name in ("smoother_half", "dense_tensor_min_n", "fuse_io", "dense_split_bf16", "fuse_res", "adaptive_poll", "dot32", "smoother_eo", "eo_by", "eo_bz", "eo_packs"):
         if name in cfg:
             mg.set_option(name, cfg[name])
     dev = mg.dev

@@ -245,3 +245,25 @@ def test_geometric_aggregates_of_the_preconditioner_hierarchy():
     assert cb1[r] == ((5 // 2) * 16 + 9 // 2) * 2 + 1
     # chirality: spin-0 rows only feed even coarse blocks
     assert np.all(cb[: L * L] % 2 == 0) and np.all(cb[L * L:] % 2 == 1)
+
+
+def test_even_odd_schur_complement_reproduces_the_inverse():
+    """A^{-1} r through the even-odd factorisation the device smoother uses: r^_e = r_e - H_eo r_o / c,
+    x_e = S^{-1} r^_e, x_o = (r_o - H_oe x_e) / c  with  S = c - H_eo H_oe / c  (16^2, dense algebra)"""
+    import scipy.sparse.linalg as spla
+    L = 16
+    A = sp.csr_matrix(refport.load_matrix("schwinger16", -1.00690114 * 0.99))
+    S, c = mgm.even_odd_schur(A, L, L)
+    s, x, t = np.meshgrid(np.arange(2), np.arange(L), np.arange(L), indexing="ij")
+    par = ((x + t) & 1).ravel()
+    ie, io = np.where(par == 0)[0], np.where(par == 1)[0]
+    assert S.shape == (L * L, L * L)
+    rs = np.random.RandomState(3)
+    r = rs.standard_normal(2 * L * L) + 1j * rs.standard_normal(2 * L * L)
+    Heo, Hoe = A[ie][:, io], A[io][:, ie]
+    re_hat = r[ie] - Heo @ r[io] / c
+    xe = spla.spsolve(S.tocsc(), re_hat)
+    xo = (r[io] - Hoe @ xe) / c
+    xfull = np.zeros_like(r); xfull[ie] = xe; xfull[io] = xo
+    ref = spla.spsolve(A.tocsc(), r)
+    assert np.linalg.norm(xfull - ref) < 1e-10 * np.linalg.norm(ref)
