@@ -193,7 +193,7 @@ def main():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=8)
     ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--probes", type=int, default=256, help="probes per step per GPU")
+    ap.add_argument("--probes", type=int, default=512, help="probes per step per GPU (batch of the fused level sample)")
     ap.add_argument("--impl", default="b200")
     ap.add_argument("--degree", type=int, default=0, help="smoother degree of the level-0 V-cycle (0: 36 geometric / 80 reference)")
     ap.add_argument("--precond", default="geometric", choices=["geometric", "reference"],
@@ -384,6 +384,73 @@ def main():
                            "spmm_level0 below is the same operator streaming complex128 / complex64 from HBM"
                            % (n0 * kc * sb / 1e6, m - 1),
                 "smooth_call_us": 1e6 * t_full, "chunk_cols": kc}
+        if getattr(pmg, "eo_poly", None) is not None and mg.precond_mg is not None:
+            # The dominant kernel of the step is now wilson_hop_eo_kernel (the even-odd post-smoother: every sweep of the
+            # polynomial in the Schur complement S).  One application of S = two half-lattice sweeps; isolated as
+            # [t(m factors) - t(1 factor)] / (m - 1) of the preconditioner call the solver itself makes.
+            t2_entry = roof
+            nue, p0e = pmg.eo_poly
+            me = len(nue)
+            Vz = torch.randn(n0, k, device="cuda", dtype=torch.float64).to(torch.complex128).contiguous()
+
+            def time_precond(reps=5):
+                for _ in range(2):
+                    dev.precondition(0, Vz)
+                torch.cuda.synchronize()
+                ev0.record(stream)
+                for _ in range(reps):
+                    dev.precondition(0, Vz)
+                ev1.record(stream)
+                torch.cuda.synchronize()
+                return ev0.elapsed_time(ev1) * 1e-3 / reps
+
+            tp_full = time_precond()
+            pdev.set_smoother_eo(0, nue[:1], p0e)
+            tp_one = time_precond()
+            pdev.set_smoother_eo(0, nue, p0e)
+            dev.set_option("use_graphs", 1)
+            t_pair = (tp_full - tp_one) / max(me - 1, 1)
+            half = (n0 // 2) * k * 4                      # one BF16 half-lattice vector of k columns (4 B per complex)
+            links = 4 * (n0 // 4) * 16                    # 4 pre-splatted links for each of the V/2 sites of a sweep
+            # sweep 1: w_o = H_oe y_e (read 1, write 1); sweep 2: y_e' = a y_e + b H_eo w_o (read 2, write 1)
+            pair_bytes = 5 * half + 2 * links
+            ach = pair_bytes / t_pair / 1e9
+            roof = {"bound": "hbm",
+                    "kernel": "wilson_hop_eo_kernel (even-odd post-smoother of the complex64 V-cycle: Out_p = a In2_p + b H In_q on "
+                              "BF16 checkerboard half-lattice vectors, packed FP32 arithmetic, four columns per thread; figures "
+                              "per sweep, averaged over the two sweeps of one Schur-complement application, %d columns)" % k,
+                    "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
+                    "peak_source": "MEASURED_PEAKS.json hbm_gbs" if "hbm_gbs" in peaks else "fallback 6650",
+                    "frac_of_nominal_8TBs": ach / 8000.0,
+                    "avg_launch_us": 1e6 * t_pair / 2, "alg_bytes_per_launch": pair_bytes / 2, "traffic": 26.3e6,
+                    "traffic_source": "ncu --set full, profiles/r1_run36_hop_eo_ncu.md (k = 256): dram__bytes_read.sum 34.6 MB (sweep with "
+                                      "In2) / 17.8 MB (sweep without) + dram__bytes_write.sum < 0.1 MB per launch, averaged over the "
+                                      "two sweeps (ncu replays each launch cold: the inputs come from DRAM there, the output stays in "
+                                      "L2; un-profiled the vectors stay in L2 at k = 256)",
+                    "limiter": "the five %.1f MB half-lattice vectors of a Schur-complement application stay in the 126 MB L2 "
+                               "across the %d consecutive sweeps, so the kernel is bound by instruction issue / L2 latency, not "
+                               "by HBM; gram_schmidt and spmm_level0 below are the HBM-streaming kernels of the step"
+                               % (half / 1e6, 2 * me + 2),
+                    "precondition_call_us": 1e6 * tp_full, "sweeps_per_vcycle": 2 * me + 2,
+                    "stencil_step_bf16_t2_kernel": {kk: t2_entry[kk] for kk in ("achieved", "frac", "avg_launch_us",
+                                                                                "alg_bytes_per_launch", "traffic", "traffic_source")}}
+            roof["stencil_step_bf16_t2_kernel"]["note"] = ("the factor kernel of the polynomial in A itself (option smoother_eo = 0, "
+                                                           "and the estimator's own hierarchy)")
+            # Gram-Schmidt kernels (29 % of the step, HBM-streaming complex128): per-column dot of two vectors = multi_dot_kernel, nv = 1
+            Wz = torch.randn(n0, k, device="cuda", dtype=torch.float64).to(torch.complex128).contiguous()
+            for _ in range(3):
+                dev.dotc(Vz, Wz)
+            torch.cuda.synchronize()
+            ev0.record(stream)
+            for _ in range(20):
+                dev.dotc(Vz, Wz)
+            ev1.record(stream)
+            torch.cuda.synchronize()
+            tdot = ev0.elapsed_time(ev1) * 1e-3 / 20
+            roof["gram_schmidt_dot"] = {"kernel": "multi_dot_kernel (+ sum_partials_kernel), nv = 1: conj(V)^T W per column, complex128",
+                                        "us": 1e6 * tdot, "GBps": 2 * n0 * k * 16 / tdot / 1e9, "frac": 2 * n0 * k * 16 / tdot / 1e9 / peak,
+                                        "ncu": "profiles/r1_run33_gs_umma_ncu.md"}
+            del Vz, Wz
         # plain SpMM Y = A X (config 3), c128 and c64, bytes n0*s*(2k) + links
         spmm = {}
         for name, dt, sb in (("c128", torch.complex128, 16), ("c64", torch.complex64, 8)):
@@ -429,8 +496,11 @@ def main():
             "config": {"workload": WORKLOAD, "probes_per_step_per_gpu": k, "solver_tol": tol,
                        "preconditioner": ("geometric hierarchy (4x4-site spin-split aggregates, the estimator's level-0 test "
                                           "vectors)" if mg.precond_mg is not None else "the estimator's hierarchy (reference aggregation)"),
-                       "smoother": "V-cycle = dense tcgen05 coarse solve at level %d + fixed GMRES polynomial of degree %d in "
-                                   "product form as post-smoother" % (pmg.dense_level, args.degree),
+                       "smoother": ("V-cycle = dense tcgen05 coarse solve at level %d + even-odd post-smoother: fixed GMRES polynomial of "
+                                    "degree %d in the Schur complement, product form" % (pmg.dense_level, len(pmg.eo_poly[0]) + 1))
+                                   if getattr(pmg, "eo_poly", None) is not None else
+                                   ("V-cycle = dense tcgen05 coarse solve at level %d + fixed GMRES polynomial of degree %d in "
+                                    "product form as post-smoother" % (pmg.dense_level, args.degree)),
                        "fgmres_restart": restart, "l2_flush": "inputs larger than L2 (Krylov basis %.1f GB per step)"
                        % (2 * (int(iters[0].max()) + 1) * n0 * k * 16 / 1e9), "parallelism": "probes sharded x%d" % world},
             "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
