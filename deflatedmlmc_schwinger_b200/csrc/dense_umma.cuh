@@ -133,8 +133,10 @@ dense_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(accum_full + 1);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int row0 = blockIdx.x * UM_BM;                  // first row of D of this CTA
-  const int col0 = blockIdx.y * UM_BN;                  // first column
+  // grid = (column tiles, row tiles): the CTAs that share a 128-row slab of the matrix are neighbours in launch order, run at
+  // the same time and the slab comes from DRAM once (the matrix, 537 MB at n = 8192, does not fit in L2)
+  const int row0 = blockIdx.y * UM_BM;                  // first row of D of this CTA
+  const int col0 = blockIdx.x * UM_BN;                  // first column
   const int ncols = min(UM_BN, k - col0);
   const int bn = (ncols + 15) & ~15;                    // UMMA N: multiple of 16 for M = 128
   const int num_kb = (kdim + UM_BK - 1) / UM_BK;

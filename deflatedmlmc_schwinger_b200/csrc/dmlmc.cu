@@ -340,7 +340,7 @@ int launch_dense_umma(dmlmc_hier* h, int level, const Cx<float>* B, Cx<float>* X
     CU(cudaFuncSetAttribute(dense_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)UM_SMEM));
     h->umma_attr_set = true;
   }
-  dim3 grd((2 * n + UM_BM - 1) / UM_BM, (k + UM_BN - 1) / UM_BN);
+  dim3 grd((k + UM_BN - 1) / UM_BN, (2 * n + UM_BM - 1) / UM_BM);
   dense_umma_kernel<<<grd, UM_THREADS, UM_SMEM, h->stream>>>(L.tmA, L.tmB, reinterpret_cast<float*>(X), k, 2 * n, k, 2 * n);
   LAUNCH_CHECK(h);
   h->ws_off = mark;
@@ -364,7 +364,7 @@ int launch_dense_umma_split(dmlmc_hier* h, int level, const Cx<float>* B, Cx<flo
     CU(cudaFuncSetAttribute(dense_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)UM_SMEM));
     h->umma_attr_set = true;
   }
-  dim3 grd((2 * n + UM_BM - 1) / UM_BM, (k + UM_BN - 1) / UM_BN);
+  dim3 grd((k + UM_BN - 1) / UM_BN, (2 * n + UM_BM - 1) / UM_BM);
   dense_umma_kernel<<<grd, UM_THREADS, UM_SMEM, h->stream>>>(L.tmA3, L.tmB3, reinterpret_cast<float*>(X), k, 2 * n, k, 6 * n);
   LAUNCH_CHECK(h);
   h->ws_off = mark;

@@ -203,6 +203,8 @@ int dmlmc_level_sample_host(dmlmc_hier* h, int method, int level_f, int level_c,
  *                  every factor but the last runs in the packed BF16 -> BF16 kernel
  *   "adaptive_poll" 1 (default): the per-iteration convergence poll (a host read) is skipped until one iteration before the
  *                  count the previous solve with the same (level, k, tol) needed, and done every 4th iteration at least
+ *   "smoother_eo"  1 (default): use the even-odd post-smoother on a stencil level that has one (dmlmc_set_smoother_eo);
+ *                  "eo_packs" 2 (default) | 1: column packs per thread of its kernel; "eo_by", "eo_bz": thread-block tile (2 x 2)
  *   "dot32"        0 (default; 1 measured harmful): Gram-Schmidt coefficients from complex64 copies of the basis */
 int dmlmc_set_option(dmlmc_hier* h, const char* name, double value);
 
