@@ -121,6 +121,22 @@ def geometric_blocks_coarse(LXc, LTc, nv, bx, bt):
     return (((X // bx) * (LTc // bt) + T // bt) * 2 + h).ravel().astype(np.int32)
 
 
+def geometric_blocks_level1(LX, LT, a_sites, nv1, bx=2):
+    """coarse block of every row of the ESTIMATOR's level-1 operator (reference aggregation, multigrid.py:203-227, dofi = 2).
+    Row r = (2 j + half) nv1 + v; strip j = s V/a + x LT/a + q is the run of a = a_sites consecutive rows (spin s, lattice
+    column x, t in [q a, (q+1) a)), half = odd/even t.  Blocks: bx neighbouring strips in x, both halves, split by the spin s:
+    ((x / bx) (LT / a) + q) 2 + s.  Returns (cblk, (LX / bx, LT / a))."""
+    V = LX * LT
+    nq = LT // a_sites
+    n1 = (2 * V // a_sites) * 2 * nv1
+    r = np.arange(n1)
+    j = r // (2 * nv1)
+    s = j // (V // a_sites)
+    x = (j % (V // a_sites)) // nq
+    q = j % nq
+    return (((x // bx) * nq + q) * 2 + s).astype(np.int32), (LX // bx, nq)
+
+
 def block_orthonormal_values(vecs, cblk, nvec):
     """pvals[n][nvec]: the first nvec columns of `vecs` orthonormalised within every coarse block (batched QR)"""
     vecs = np.asarray(vecs)[:, :nvec]
@@ -649,15 +665,8 @@ class MG:
         V = LX * LT
         if dofi != 2 or LT % a_sites or LX % 2 or n1 != (2 * V // aggr) * 2 * nv1:
             return
-        nq = LT // a_sites
-        r = np.arange(n1)
-        half = (r // nv1) % 2
-        j = r // (2 * nv1)
-        s = j // (V // a_sites)
-        x = (j % (V // a_sites)) // nq
-        q = j % nq
-        cblk = (((x // 2) * nq + q) * 2 + s).astype(np.int32)
-        gx, gt = LX // 2, nq
+        cblk, (gx, gt) = geometric_blocks_level1(LX, LT, a_sites, nv1, 2)
+        nq = gt
         nvs = [int(d // 2) for d in sa['dof'][2:]] or [nv1]
         levels = 2
         while True:

@@ -267,3 +267,29 @@ def test_even_odd_schur_complement_reproduces_the_inverse():
     xfull = np.zeros_like(r); xfull[ie] = xe; xfull[io] = xo
     ref = spla.spsolve(A.tocsc(), r)
     assert np.linalg.norm(xfull - ref) < 1e-10 * np.linalg.norm(ref)
+
+
+def test_geometric_blocks_of_the_estimators_level1():
+    """the block map used to precondition the estimator's level-1 solves: every block must be the set of level-1 rows
+    whose level-0 support (through the reference's own P_0) is one spin component of 2 neighbouring lattice columns x
+    and one run of 32 sites in t -- checked against the oracle's P_0 on 128^2"""
+    import os
+    from deflatedmlmc_schwinger_b200 import gateway
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "schwinger128.npz"))
+    L, nv = 128, 4
+    cb, (gx, gt) = mgm.geometric_blocks_level1(L, L, 32, nv, 2)
+    n1 = 8192
+    assert cb.shape == (n1,) and (gx, gt) == (64, 4) and np.all(np.bincount(cb) == 16) and cb.max() + 1 == 2 * gx * gt
+    # support of every level-1 row from the closed-form structure of P_0 (bit-exact with the reference, tested above)
+    half, first = mgm.aggregation_maps(2 * L * L, 32, 2, nv)
+    i = np.arange(2 * L * L)
+    s, x, t = i // (L * L), (i % (L * L)) // L, i % L
+    for v in range(nv):
+        col = first + v                                   # level-1 row fed by fine row i (vector v)
+        blk = cb[col]
+        assert np.array_equal(blk, ((x // 2) * gt + t // 32) * 2 + s)
+    # with the golden level-1 test vectors: orthonormal prolongator, test vectors in its range
+    tv1 = g["tv1"]
+    P = mgm.prolongator_csr_indexed(mgm.block_orthonormal_values(tv1, cb, nv), cb)
+    assert abs((P.conj().T @ P) - sp.identity(P.shape[1])).max() < 1e-13
+    assert np.linalg.norm(P @ (P.conj().T @ tv1) - tv1) < 1e-12 * np.linalg.norm(tv1)
