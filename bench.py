@@ -422,15 +422,16 @@ def main():
                     "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
                     "peak_source": "MEASURED_PEAKS.json hbm_gbs" if "hbm_gbs" in peaks else "fallback 6650",
                     "frac_of_nominal_8TBs": ach / 8000.0,
-                    "avg_launch_us": 1e6 * t_pair / 2, "alg_bytes_per_launch": pair_bytes / 2, "traffic": 26.3e6,
+                    "avg_launch_us": 1e6 * t_pair / 2, "alg_bytes_per_launch": pair_bytes / 2, "traffic": 26.3e6 * k / 256.0,
                     "traffic_source": "ncu --set full, profiles/r1_run36_hop_eo_ncu.md (k = 256): dram__bytes_read.sum 34.6 MB (sweep with "
                                       "In2) / 17.8 MB (sweep without) + dram__bytes_write.sum < 0.1 MB per launch, averaged over the "
-                                      "two sweeps (ncu replays each launch cold: the inputs come from DRAM there, the output stays in "
-                                      "L2; un-profiled the vectors stay in L2 at k = 256)",
-                    "limiter": "the five %.1f MB half-lattice vectors of a Schur-complement application stay in the 126 MB L2 "
-                               "across the %d consecutive sweeps, so the kernel is bound by instruction issue / L2 latency, not "
-                               "by HBM; gram_schmidt and spmm_level0 below are the HBM-streaming kernels of the step"
-                               % (half / 1e6, 2 * me + 2),
+                                      "two sweeps and scaled by k / 256 to this run's batch (ncu replays each launch cold: the inputs "
+                                      "come from DRAM there, the output stays in L2)",
+                    "limiter": "the five %.1f MB half-lattice vectors of a Schur-complement application %s the 126 MB L2 across the "
+                               "%d consecutive sweeps; ncu (k = 256): issue slots 56-58 %%, integer ALU pipe 47-51 %% (BF16 <-> FP32 "
+                               "conversions), FMA pipe 24-26 %%, 70-72 registers, 35-39 %% of the warp slots -- instruction issue / "
+                               "L2 latency, not HBM; gram_schmidt_dot and spmm_level0 below are the HBM-streaming kernels of the step"
+                               % (half / 1e6, "stay in" if 5 * half < 120e6 else "no longer all fit in", 2 * me + 2),
                     "precondition_call_us": 1e6 * tp_full, "sweeps_per_vcycle": 2 * me + 2,
                     "stencil_step_bf16_t2_kernel": {kk: t2_entry[kk] for kk in ("achieved", "frac", "avg_launch_us",
                                                                                 "alg_bytes_per_launch", "traffic", "traffic_source")}}
