@@ -1,7 +1,7 @@
 import sys, numpy as np, scipy.sparse as sp, scipy.sparse.linalg as spla
-sys.path.insert(0, '/tmp/exp')
-import geo
-from geo import A, gmres_poly_omega, fgmres, probes, smoother_product_form
+import os; sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+import exp_geometric_aggregation as geo
+from exp_geometric_aggregation import A, gmres_poly_omega, fgmres, probes, smoother_product_form
 L = 128; V = L * L; n = 2 * V
 tv = geo.g['tv0']
 P = geo.geo_P(tv, 4, 4, 4); R = P.conj().T.tocsr(); A1 = (R @ A @ P).tocsc(); lu = spla.splu(A1)

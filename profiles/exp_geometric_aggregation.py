@@ -1,9 +1,12 @@
+"""CPU experiment (dev tool, uses the oracle for the operator): outer FGMRES iterations of the exact two-grid method on
+Schwinger 128^2 with geometric aggregates (bx x bt sites, split by spin) for several smoother degrees.  Also the shared
+helpers of the other exp_*.py scripts.   python profiles/exp_geometric_aggregation.py"""
 import sys, time, numpy as np, scipy.sparse as sp, scipy.sparse.linalg as spla
-sys.path.insert(0, '/root/repo'); sys.path.insert(0, '/tmp/exp')
+import os; sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from oracle import refport
 from deflatedmlmc_schwinger_b200.multigrid import leja_order, smoother_product_form
 A = refport.load_matrix('schwinger128', -0.1320).tocsr()
-g = np.load('/root/repo/tests/golden/schwinger128.npz')
+g = np.load(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), 'tests', 'golden', 'schwinger128.npz'))
 n = A.shape[0]; L = 128; V = L * L
 def geo_P(tv, bx, bt, nv):
     tv = tv[:, :nv]
