@@ -181,16 +181,19 @@ def harmonic_ritz_inv_roots(A, degree, seed=7):
     b = rs.standard_normal(n) + 1j * rs.standard_normal(n)
     b /= np.linalg.norm(b)
     V = np.zeros((degree + 1, n), dtype=np.complex128)
+    Vc = np.zeros((degree + 1, n), dtype=np.complex128)      # conj(V), kept so that no conjugated copy is made per step
     H = np.zeros((degree + 1, degree), dtype=np.complex128)
     V[0] = b
+    Vc[0] = np.conj(b)
     for j in range(degree):
         w = A @ V[j]
         for _ in range(2):
-            hh = np.conj(V[:j + 1]) @ w
+            hh = Vc[:j + 1] @ w
             H[:j + 1, j] += hh
             w = w - hh @ V[:j + 1]
         H[j + 1, j] = np.linalg.norm(w)
         V[j + 1] = w / H[j + 1, j]
+        Vc[j + 1] = np.conj(V[j + 1])
     Hm = H[:degree, :degree]
     em = np.zeros(degree)
     em[-1] = 1.0
