@@ -92,6 +92,8 @@ struct dmlmc_hier {
   int pre_smooth = 0;                     // 0: V-cycle = coarse correction + post-smoothing (default), 1: pre- and post-smoothing
   int smoother_half = 1;                  // BF16 storage of the level-0 smoother's intermediate vectors (c64 cycle)
   int dense_direct_exact = 1;             // a dense level solved directly (not from a finer level) uses its FP32 copy
+  int outer_eo = 0;                       // UNVALIDATED (round 2): outer FGMRES of a stencil level on the even-odd Schur complement
+  int eo_zhalf = 0;                       // (internal) the even-odd smoother writes only Z_e, into a half-lattice array
   int smoother_eo = 1;                    // even-odd (Schur complement) form of the level-0 post-smoother when one is set
   int dot32 = 0;                          // Gram-Schmidt coefficients from complex64 copies of the basis vectors: OFF -- measured on
                                           // B200 (profiles/r1_run32_tune_dot32.jsonl): the basis loses orthogonality at the 1e-7
@@ -474,11 +476,11 @@ int launch_hop_eo(dmlmc_hier* h, const Level& L, int p, const uint2* Inq, const 
   if (two)
     wilson_hop_eo_kernel<HAS2, HOUT, ZOUT, 2><<<grd, blk, 0, h->stream>>>(L.LX, L.LT, p, L.links4, Inq, In2, Outp, (float)a.re, (float)a.im,
                                                                           (float)b.re, (float)b.im, (uint32_t)kp,
-                                                                          (const Pack<float, 2>*)Xc, (double2*)Z);
+                                                                          (const Pack<float, 2>*)Xc, (double2*)Z, h->eo_zhalf);
   else
     wilson_hop_eo_kernel<HAS2, HOUT, ZOUT, 1><<<grd, blk, 0, h->stream>>>(L.LX, L.LT, p, L.links4, Inq, In2, Outp, (float)a.re, (float)a.im,
                                                                           (float)b.re, (float)b.im, (uint32_t)kp,
-                                                                          (const Pack<float, 2>*)Xc, (double2*)Z);
+                                                                          (const Pack<float, 2>*)Xc, (double2*)Z, h->eo_zhalf);
   LAUNCH_CHECK(h);
   return 0;
 }
@@ -521,8 +523,8 @@ int smooth_eo(dmlmc_hier* h, int level, const void* Xc, const void* B, void* t0,
     }
     cur ^= 1;
   }
-  // Z_o = Xc_o + (r_o - H_oe x_e) / c
-  RET((launch_hop_eo<true, false, true>(h, L, 1, Y[cur], Ro, nullptr, IC, NIC, kp, Xc, Z)));
+  // Z_o = Xc_o + (r_o - H_oe x_e) / c   (not needed when only the even part of the cycle's output is used)
+  if (!h->eo_zhalf) RET((launch_hop_eo<true, false, true>(h, L, 1, Y[cur], Ro, nullptr, IC, NIC, kp, Xc, Z)));
   return 0;
 }
 
@@ -906,11 +908,16 @@ int read_nactive(dmlmc_hier* h, int* dev_counter, int* out) {
   return 0;
 }
 
+bool outer_eo_ok(dmlmc_hier* h, int level, int k);
+int fgmres_eo(dmlmc_hier* h, int level, const Z* B, Z* X, int k, double tol, int restart, int maxiter,
+              int32_t* iters_host, double* relres_host);
+
 // ---- batched FGMRES (multigrid.py:347-366 / pyamg.krylov.fgmres) ------------------------------
 int fgmres(dmlmc_hier* h, int level, const Z* B, Z* X, int k, double tol, int restart, int maxiter,
            int32_t* iters_host, double* relres_host) {
   CHECK(level >= 0 && level < h->n_levels, "fgmres: bad level");
   CHECK(k >= 1 && restart >= 1 && maxiter >= 1, "fgmres: bad k / restart / maxiter");
+  if (outer_eo_ok(h, level, k)) return fgmres_eo(h, level, B, X, k, tol, restart, maxiter, iters_host, relres_host);
   Level& L = h->lv[level];
   const int n = L.n, m = restart;
   const size_t nk = (size_t)n * k;
@@ -1002,6 +1009,127 @@ int fgmres(dmlmc_hier* h, int level, const Z* B, Z* X, int k, double tol, int re
     RET((launch_op<double, M_RES>(h, level, X, B, Rb, ZERO, ZERO, k)));
     Rsrc = Rb;
   }
+  h->expect_it[level] = total_it; h->expect_tol[level] = tol; h->expect_k[level] = k;
+  if (iters_host) CU(cudaMemcpyAsync(iters_host, s.it_total, sizeof(int) * k, cudaMemcpyDeviceToHost, h->stream));
+  if (relres_host) CU(cudaMemcpyAsync(relres_host, s.relres, sizeof(double) * k, cudaMemcpyDeviceToHost, h->stream));
+  if (iters_host || relres_host) CU(cudaStreamSynchronize(h->stream));
+  h->ws_off = mark;
+  return 0;
+}
+
+// ---- UNVALIDATED on hardware (written at the end of round 1 without GPU time; option "outer_eo", default 0) ----------------
+// Batched FGMRES of a stencil level on the even-odd Schur complement:  S x_e = b^_e = b_e - H_eo b_o / c,  S = c - H_eo H_oe / c,
+// x_o = (b_o - H_oe x_e) / c.  All Krylov vectors are half-lattice (checkerboard) arrays, so Gram-Schmidt, normalisation and
+// the final update move half the bytes; the preconditioner is the even part of the V-cycle applied to (v_e, 0).  CPU experiment
+// (profiles/exp_schur_outer_solve.py): the same 8 outer iterations to 1e-12 as the solve on A.  The residual of the full
+// system is (r^_e, 0), so convergence is measured as ||r^_e|| / ||b||.
+template <bool HAS2>
+int launch_hop_z(dmlmc_hier* h, const Level& L, int p, const Z* Inq, const Z* In2, Z* Out, Cx<double> a, Cx<double> b, int k) {
+  StencilDev<double> op; op.LX = L.LX; op.LT = L.LT; op.Ut = L.d.Ut; op.Ux = L.d.Ux; op.diag = L.d.diag;
+  int bx = 1; while (bx < 32 && bx < k) bx *= 2;
+  dim3 blk(bx, 4, 2), grd((k + bx - 1) / bx, (L.LT / 2 + 3) / 4, (L.LX + 1) / 2);
+  wilson_hop_eo_z_kernel<HAS2><<<grd, blk, 0, h->stream>>>(op, p, Inq, In2, Out, a, b, k);
+  LAUNCH_CHECK(h);
+  return 0;
+}
+bool outer_eo_ok(dmlmc_hier* h, int level, int k) {
+  if (!h->outer_eo || !h->fuse_io) return false;
+  Level& L = h->lv[level];
+  if (L.kind != 0 || (L.LT % 2) || (L.LX % 2) || L.d.diag.im != 0.0) return false;
+  dmlmc_hier* hv = h->prec_hier[level] ? h->prec_hier[level] : h;
+  const int pl = h->prec_hier[level] ? h->prec_level[level] : level;
+  return hv->inner_prec == DMLMC_C64 && smoother_dout_ok(hv, pl, k) && smoother_eo_ok(hv, pl, k) && !hv->pre_smooth &&
+         chunk_cols(hv, pl, k, sizeof(Cx<float>)) >= k;
+}
+int fgmres_eo(dmlmc_hier* h, int level, const Z* B, Z* X, int k, double tol, int restart, int maxiter,
+              int32_t* iters_host, double* relres_host) {
+  Level& L = h->lv[level];
+  dmlmc_hier* hv = h->prec_hier[level] ? h->prec_hier[level] : h;
+  const int n = L.n, nh = n / 2, m = restart;
+  const size_t nk = (size_t)n * k, nkh = (size_t)nh * k;
+  const double c = L.d.diag.re;
+  const Cx<double> ONE = {1.0, 0.0}, CC = {c, 0.0}, NIC = {-1.0 / c, 0.0}, IC = {1.0 / c, 0.0};
+  const size_t mark = h->ws_off;
+  GmresState s; s.k = k; s.m = m;
+  Z *Vb, *Zb, *W, *Wo, *Rb, *Be, *Bo, *Bhat, *Xe, *Xo, *partial;
+  RET(ws_get<Z>(h, nkh * (m + 1), &Vb));
+  RET(ws_get<Z>(h, nkh * m, &Zb));
+  RET(ws_get<Z>(h, nkh, &W)); RET(ws_get<Z>(h, nkh, &Wo)); RET(ws_get<Z>(h, nkh, &Rb));
+  RET(ws_get<Z>(h, nkh, &Be)); RET(ws_get<Z>(h, nkh, &Bo)); RET(ws_get<Z>(h, nkh, &Bhat));
+  RET(ws_get<Z>(h, nkh, &Xe)); RET(ws_get<Z>(h, nkh, &Xo));
+  RET(ws_get<Z>(h, partial_count(n, m + 1, k), &partial));
+  RET(ws_get<Z>(h, (size_t)(m + 1) * k, &s.hsum));
+  RET(ws_get<Z>(h, (size_t)k, &s.nrm2));
+  RET(ws_get<Z>(h, (size_t)m * m * k, &s.Rm));
+  RET(ws_get<double>(h, (size_t)m * k, &s.cs));
+  RET(ws_get<Z>(h, (size_t)m * k, &s.sn));
+  RET(ws_get<Z>(h, (size_t)(m + 1) * k, &s.g));
+  RET(ws_get<Z>(h, (size_t)m * k, &s.y));
+  RET(ws_get<double>(h, (size_t)k, &s.normb));
+  RET(ws_get<double>(h, (size_t)k, &s.scale));
+  RET(ws_get<double>(h, (size_t)k, &s.relres));
+  RET(ws_get<int>(h, (size_t)k, &s.active));
+  RET(ws_get<int>(h, (size_t)k, &s.done));
+  RET(ws_get<int>(h, (size_t)k, &s.it_cycle));
+  RET(ws_get<int>(h, (size_t)k, &s.it_total));
+  RET(ws_get<int>(h, 1, &s.n_active));
+  Cx<float>* V32;                                        // (v_e, 0) as complex64 on the full lattice: the V-cycle's input
+  RET(ws_get<Cx<float>>(h, nk, &V32));
+  CU(cudaMemsetAsync(V32, 0, nk * sizeof(Cx<float>), h->stream));
+  const unsigned gk = nblocks(k, 128);
+  // ||b|| of the full system, b_e, b_o, b^_e
+  RET(multi_dot(h, B, 0, 1, B, n, k, partial, s.nrm2, 0));
+  set_normb_kernel<<<gk, 128, 0, h->stream>>>(s.nrm2, s.normb, k); LAUNCH_CHECK(h);
+  eo_split_merge_kernel<<<nblocks(nk, 256), 256, 0, h->stream>>>(L.LX, L.LT, k, 0, const_cast<Z*>(B), Be, Bo); LAUNCH_CHECK(h);
+  RET((launch_hop_z<true>(h, L, 0, Bo, Be, Bhat, ONE, NIC, k)));
+  CU(cudaMemsetAsync(Xe, 0, nkh * sizeof(Z), h->stream));
+  const Z* Rsrc = Bhat;
+  const int expect = (h->expect_tol[level] == tol && h->expect_k[level] == k) ? h->expect_it[level] : 0;
+  int total_it = 0, nact = 0, mode = 3;
+  while (true) {
+    RET(multi_dot(h, Rsrc, 0, 1, Rsrc, nh, k, partial, s.nrm2, 0));
+    CU(cudaMemsetAsync(s.n_active, 0, sizeof(int), h->stream));
+    gmres_init_kernel<<<nblocks(k, 256), 256, 0, h->stream>>>(s, tol, mode); LAUNCH_CHECK(h);
+    mode = 2;
+    RET(read_nactive(h, s.n_active, &nact));
+    if (nact == 0 || total_it >= maxiter) break;
+    col_scale_eo_kernel<<<nblocks(nkh, 256), 256, 0, h->stream>>>(L.LX, L.LT, Rsrc, s.scale, Vb, k, V32); LAUNCH_CHECK(h);
+    int j = 0;
+    for (; j < m; ++j) {
+      Z* Vj = Vb + (size_t)j * nkh;
+      Z* Zj = Zb + (size_t)j * nkh;
+      auto body = [&]() -> int {
+        hv->eo_zhalf = 1;
+        const int rcp = precond(h, level, Vj, Zj, k, V32);         // Z_j = even part of M^{-1} (v_e, 0), half-lattice layout
+        hv->eo_zhalf = 0;
+        RET(rcp);
+        RET((launch_hop_z<false>(h, L, 1, Zj, nullptr, Wo, ONE, ONE, k)));        // w_o = H_oe z
+        RET((launch_hop_z<true>(h, L, 0, Wo, Zj, W, CC, NIC, k)));                // w = c z - H_eo w_o / c
+        RET(multi_dot(h, Vb, nkh, j + 1, W, nh, k, partial, s.hsum, 0));
+        RET(multi_axpy_norm(h, Vb, nkh, j + 1, s.hsum, W, nh, k, partial, s.nrm2));
+        CU(cudaMemsetAsync(s.n_active, 0, sizeof(int), h->stream));
+        gmres_step_kernel<<<gk, 128, 0, h->stream>>>(s, j, tol); LAUNCH_CHECK(h);
+        if (j + 1 < m) { col_scale_eo_kernel<<<nblocks(nkh, 256), 256, 0, h->stream>>>(L.LX, L.LT, W, s.scale, Vb + (size_t)(j + 1) * nkh, k, V32); LAUNCH_CHECK(h); }
+        return 0;
+      };
+      RET(run_iteration(h, h->use_graphs && k <= h->graph_max_k, level + 64, k, mark, j, m, tol, body));
+      ++total_it;
+      if (!h->adaptive_poll || total_it + 1 >= expect || (total_it & 3) == 0 || j + 1 == m || total_it >= maxiter)
+        RET(read_nactive(h, s.n_active, &nact));
+      if (nact == 0 || total_it >= maxiter) { ++j; break; }
+    }
+    const int steps = std::min(j, m);
+    gmres_solve_kernel<<<gk, 128, 0, h->stream>>>(s, steps); LAUNCH_CHECK(h);
+    RET(multi_axpy(h, Zb, nkh, steps, s.y, Xe, nh, k, +1.0));
+    // true residual of the Schur system (= the residual of the full system, whose odd part is zero by construction)
+    RET((launch_hop_z<false>(h, L, 1, Xe, nullptr, Wo, ONE, ONE, k)));
+    RET((launch_hop_z<true>(h, L, 0, Wo, Xe, W, CC, NIC, k)));
+    vec_sub_kernel<<<nblocks(nkh, 256), 256, 0, h->stream>>>(Bhat, W, Rb, nkh); LAUNCH_CHECK(h);
+    Rsrc = Rb;
+  }
+  // x_o = (b_o - H_oe x_e) / c, then the full-lattice layout
+  RET((launch_hop_z<true>(h, L, 1, Xe, Bo, Xo, IC, NIC, k)));
+  eo_split_merge_kernel<<<nblocks(nk, 256), 256, 0, h->stream>>>(L.LX, L.LT, k, 1, X, Xe, Xo); LAUNCH_CHECK(h);
   h->expect_it[level] = total_it; h->expect_tol[level] = tol; h->expect_k[level] = k;
   if (iters_host) CU(cudaMemcpyAsync(iters_host, s.it_total, sizeof(int) * k, cudaMemcpyDeviceToHost, h->stream));
   if (relres_host) CU(cudaMemcpyAsync(relres_host, s.relres, sizeof(double) * k, cudaMemcpyDeviceToHost, h->stream));
@@ -1553,6 +1681,7 @@ int dmlmc_level_sample_host(dmlmc_hier* h, int method, int level_f, int level_c,
 int dmlmc_set_option(dmlmc_hier* h, const char* name, double value) {
   if (h) invalidate_graphs(h);
   CHECK(h != nullptr && name != nullptr, "set_option: bad arguments");
+  if (std::strcmp(name, "outer_eo") == 0) { h->outer_eo = value != 0.0; return 0; }
   if (std::strcmp(name, "smoother_eo") == 0) { h->smoother_eo = value != 0.0; return 0; }
   if (std::strcmp(name, "dot32") == 0) { h->dot32 = value != 0.0; return 0; }
   if (std::strcmp(name, "fuse_res") == 0) { h->fuse_res = value != 0.0; return 0; }

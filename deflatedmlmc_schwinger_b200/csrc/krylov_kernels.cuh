@@ -349,6 +349,8 @@ gmres_init_kernel(GmresState s, double tol, int mode) {
   if (mode == 1) {
     s.normb[col] = (nr == 0.0) ? 1.0 : nr;
     s.it_total[col] = 0;
+  } else if (mode == 3) {         // first cycle, normb supplied by the caller (the even-odd solve measures against ||b|| of the full system)
+    s.it_total[col] = 0;
   } else {
     accept = 1.25 * tol + 1e-14;
   }
@@ -435,6 +437,18 @@ gmres_solve_kernel(GmresState s, int jmax) {
     if (d2 > 0.0) { zfma_conj(yi, d, acc); yi = zscale(1.0 / d2, yi); }   // acc / d
     s.y[(size_t)i * k + col] = yi;
   }
+}
+
+// Out[i] = A[i] - B[i]
+__global__ void __launch_bounds__(256)
+vec_sub_kernel(const Z* __restrict__ A, const Z* __restrict__ Bv, Z* __restrict__ Out, size_t count) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < count) Out[i] = zsub(ldc_ro<double>(A, i), ldc_ro<double>(Bv, i));
+}
+// normb[col] = sqrt(nrm2[col]) (1 for a zero column)
+__global__ void set_normb_kernel(const Z* __restrict__ nrm2, double* __restrict__ normb, int k) {
+  const int col = blockIdx.x * blockDim.x + threadIdx.x;
+  if (col < k) { const double v = sqrt(fmax(nrm2[col].re, 0.0)); normb[col] = (v == 0.0) ? 1.0 : v; }
 }
 
 // e[col] = a[col] - b[col]
