@@ -25,7 +25,8 @@ import time
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 os.environ.setdefault("OMP_NUM_THREADS", "1")
-os.environ["NCCL_DEBUG"] = "WARN"          # keep NCCL's version banner off stdout: rank 0 prints ONE JSON line
+# NCCL's log (whatever level the caller asks for through NCCL_DEBUG) goes to stderr: rank 0 prints ONE JSON line on stdout
+os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
 
 import numpy as np  # noqa: E402
 
@@ -44,6 +45,25 @@ def params128():
     p["function_tol"] = 1e-12
     p["verbose"] = False
     return p, utils.trace_params_from_params(p, "mlmc")
+
+
+def build_solver(precond="geometric", degree=0, options=()):
+    """The hierarchy of the bench workload, exactly as the timed run builds it (tests/test_gpu_parity_round2.py checks
+    this very object against the reference's golden samples).  Returns (mg, tp, A, degree)."""
+    from deflatedmlmc_schwinger_b200 import matrix, multigrid
+    p, tp = params128()
+    A = matrix.loadMatrix(p["matrix"], p["matrix_params"])
+    geo = precond == "geometric"
+    if degree <= 0:
+        degree = 36 if geo else 80
+    mg = multigrid.MG(A, smoother_degree=80, precond_degree=degree, geometric_precond=True) if geo else \
+        multigrid.MG(A, smoother_degree=degree, geometric_precond=False)
+    mg.setup(dof=tp["dof"], aggrs=tp["aggrs"], max_levels=tp["max_nr_levels"], acc_eigvs=tp["accuracy_mg_eigvs"],
+             params=tp, test_vectors=golden_tvs())
+    mg.skip_level = True
+    for name, value in options:
+        mg.set_option(name, value)
+    return mg, tp, A, degree
 
 
 # ------------------------------------------------------------------------------------------------
@@ -200,6 +220,7 @@ def main():
                     help="hierarchy of the V-cycle that preconditions the level-0 solve: geometric 4x4-site aggregates "
                          "(default) or the estimator's own (reference aggregation)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--opt", action="append", default=[], metavar="NAME=VALUE", help="solver option (dmlmc_set_option), repeatable")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference_arm(args)
@@ -219,19 +240,11 @@ def main():
         ge.build()
     if world > 1:
         dist.barrier()
-    from deflatedmlmc_schwinger_b200 import matrix, multigrid, sampling, utils, _lib
+    from deflatedmlmc_schwinger_b200 import sampling, utils, _lib
 
-    p, tp = params128()
-    A = matrix.loadMatrix(p["matrix"], p["matrix_params"])
     t0 = time.time()
-    geo = args.precond == "geometric"
-    if args.degree <= 0:
-        args.degree = 36 if geo else 80
-    mg = multigrid.MG(A, smoother_degree=80, precond_degree=args.degree, geometric_precond=True) if geo else \
-        multigrid.MG(A, smoother_degree=args.degree, geometric_precond=False)
-    mg.setup(dof=tp["dof"], aggrs=tp["aggrs"], max_levels=tp["max_nr_levels"], acc_eigvs=tp["accuracy_mg_eigvs"],
-             params=tp, test_vectors=golden_tvs())
-    mg.skip_level = True
+    options = [(o.split("=")[0], float(o.split("=")[1])) for o in args.opt]
+    mg, tp, A, args.degree = build_solver(args.precond, args.degree, options)
     setup_s = time.time() - t0
     dev = mg.dev
     pmg = mg.precond_mg if mg.precond_mg is not None else mg     # the hierarchy whose V-cycle preconditions level 0

@@ -69,6 +69,10 @@ _SIGS = {
                                                ctypes.c_int, ctypes.c_double, ctypes.c_int, ctypes.c_int, ctypes.c_void_p,
                                                ctypes.c_void_p]),
     "dmlmc_set_option": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_char_p, ctypes.c_double]),
+    "dmlmc_hop_eo": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p,
+                                    ctypes.c_double, ctypes.c_double, ctypes.c_double, ctypes.c_double, ctypes.c_int,
+                                    ctypes.c_void_p, ctypes.c_void_p]),
+    "dmlmc_unconverged_columns": (ctypes.c_int, [ctypes.c_void_p]),
     "dmlmc_launch_count": (ctypes.c_longlong, [ctypes.c_void_p]),
     "dmlmc_vcycle_chunk_cols": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_int]),
 }
@@ -90,7 +94,7 @@ def load():
         fn = getattr(lib, name)          # AttributeError if the ABI is incomplete
         fn.restype = res
         fn.argtypes = args
-    if lib.dmlmc_abi_version() != 3:
+    if lib.dmlmc_abi_version() != 4:
         raise RuntimeError("libdmlmc_sm100.so ABI version mismatch")
     _lib = lib
     return lib
@@ -225,9 +229,11 @@ class Hierarchy:
 
     def set_option(self, name, value):
         _check(self.lib.dmlmc_set_option(self.h, name.encode(), float(value)))
+        self._ws_key = None          # the work-space size depends on options
 
     def set_inner_precision(self, prec):
         _check(self.lib.dmlmc_set_inner_precision(self.h, prec))
+        self._ws_key = None
 
     # ---- helpers -------------------------------------------------------------------
     def _dtype(self, prec):
@@ -250,14 +256,26 @@ class Hierarchy:
         return self.torch.empty((n, k), dtype=self._dtype(prec), device=self.device)
 
     def ensure_workspace(self, level, k, restart):
+        """The library keeps the pointer it is given: it is re-registered whenever the tensor behind it changes (the
+        size query depends on options as well as on (level, k, restart)), never only when the key changes."""
         key = (level, k, restart)
         need = self.lib.dmlmc_workspace_bytes(self.h, level, k, restart)
         if self._ws is None or self._ws.numel() < need:
             self._ws = None
+            self._ws_reg = None
             self._ws = self.torch.empty(need, dtype=self.torch.uint8, device=self.device)
-        if self._ws_key != key:
-            _check(self.lib.dmlmc_set_workspace(self.h, ctypes.c_void_p(self._ws.data_ptr()), self._ws.numel()))
+        reg = (self._ws.data_ptr(), self._ws.numel())
+        if self._ws_key != key or getattr(self, "_ws_reg", None) != reg:
+            _check(self.lib.dmlmc_set_workspace(self.h, ctypes.c_void_p(reg[0]), reg[1]))
             self._ws_key = key
+            self._ws_reg = reg
+
+    def release_workspace(self):
+        """drop the work space (the library forgets the pointer before the tensor is freed)"""
+        _check(self.lib.dmlmc_set_workspace(self.h, None, 0))
+        self._ws = None
+        self._ws_key = None
+        self._ws_reg = None
 
     # ---- operators -------------------------------------------------------------------
     def spmm(self, level, X, Y=None):
@@ -335,6 +353,17 @@ class Hierarchy:
     def rng_sync(self):
         _check(self.lib.dmlmc_rng_sync(self.h))
 
+    def hop_eo(self, level, parity, in_q, in2, out_p, a, b, k, xc=None, z=None):
+        """one half-lattice sweep of the even-odd smoother (dmlmc_hop_eo); BF16 arrays as torch.bfloat16 tensors
+        [2, LX, LT/2, k, 2]"""
+        ptr = lambda t: None if t is None else ctypes.c_void_p(t.data_ptr())
+        a, b = complex(a), complex(b)
+        _check(self.lib.dmlmc_hop_eo(self.h, level, int(parity), ptr(in_q), ptr(in2), ptr(out_p), a.real, a.imag, b.real, b.imag,
+                                     int(k), ptr(xc), ptr(z)))
+
+    def unconverged_columns(self):
+        return int(self.lib.dmlmc_unconverged_columns(self.h))
+
     def apply_perm(self, level, X):
         Y = self.torch.empty_like(X)
         _check(self.lib.dmlmc_apply_perm(self.h, level, self._chk(X, self.sizes[level]), self._chk(Y), X.shape[1]))
@@ -360,6 +389,7 @@ class Hierarchy:
         _check(self.lib.dmlmc_level_sample(self.h, method, level_f, level_c, self._chk(X0, self.sizes[level_f]), k,
                                            float(tol), int(restart), int(maxiter), ctypes.c_void_p(e.data_ptr()),
                                            iters.ctypes.data_as(ctypes.c_void_p)))
+        self._check_converged(tol, maxiter)
         return e, iters.reshape(2, k)
 
     def level_sample_host(self, method, level_f, level_c, bits_host, k, tol, restart=40, maxiter=1000):
@@ -372,7 +402,13 @@ class Hierarchy:
         _check(self.lib.dmlmc_level_sample_host(self.h, method, level_f, level_c, bits_host.ctypes.data_as(ctypes.c_void_p),
                                                 k, float(tol), int(restart), int(maxiter),
                                                 e.ctypes.data_as(ctypes.c_void_p), iters.ctypes.data_as(ctypes.c_void_p)))
+        self._check_converged(tol, maxiter)
         return e, iters.reshape(2, k)
+
+    def _check_converged(self, tol, maxiter):
+        bad = self.unconverged_columns()
+        if bad:
+            raise DmlmcError("%d probe column(s) did not reach the relative residual %g within %d iterations" % (bad, tol, maxiter))
 
     def launch_count(self):
         return int(self.lib.dmlmc_launch_count(self.h))

@@ -115,6 +115,7 @@ struct dmlmc_hier {
   cudaStream_t rng_stream = nullptr; cudaEvent_t rng_done = nullptr;   // the probe stream runs beside the solver
   cudaStream_t cap_stream = nullptr;                                   // capture stream of the V-cycle graphs
   long long launches = 0;
+  int unconverged = 0;                    // columns the solves of the last fgmres / level_sample call left above tol at maxiter
   std::vector<void*> owned;
   // CUDA graphs of the V-cycle for small batches (launch-bound there: ~90 kernels of a few microseconds each)
   struct GraphEntry { int level, k, prec; char* ws; size_t ws_off; int j, m, reorth; double tol; cudaGraphExec_t exec; long long launches; };
@@ -162,6 +163,13 @@ int ws_alloc(dmlmc_hier* h, size_t bytes, void** out) {
   h->ws_off = off + bytes;
   return 0;
 }
+// restores the bump allocator on every exit path of a function (error returns included)
+struct WsScope {
+  dmlmc_hier* h; size_t mark;
+  explicit WsScope(dmlmc_hier* h_) : h(h_), mark(h_->ws_off) {}
+  ~WsScope() { h->ws_off = mark; }
+  WsScope(const WsScope&) = delete; WsScope& operator=(const WsScope&) = delete;
+};
 template <typename T> int ws_get(dmlmc_hier* h, size_t count, T** out) {
   void* p; RET(ws_alloc(h, count * sizeof(T), &p)); *out = reinterpret_cast<T*>(p); return 0;
 }
@@ -329,7 +337,7 @@ template <> Cx<float>*  minv_of<float>(Level& L)  { return L.minv_f; }
 int launch_dense_umma(dmlmc_hier* h, int level, const Cx<float>* B, Cx<float>* X, int k) {
   Level& L = h->lv[level];
   const int n = L.n;
-  const size_t mark = h->ws_off;
+  WsScope ws_scope(h); const size_t mark = ws_scope.mark;
   __nv_bfloat16* Bt;
   RET(ws_get<__nv_bfloat16>(h, (size_t)k * 2 * n, &Bt));
   dim3 pblk(32, 8), pgrd((n + 31) / 32, (k + 31) / 32);
@@ -353,7 +361,7 @@ int launch_dense_umma(dmlmc_hier* h, int level, const Cx<float>* B, Cx<float>* X
 int launch_dense_umma_split(dmlmc_hier* h, int level, const Cx<float>* B, Cx<float>* X, int k) {
   Level& L = h->lv[level];
   const int n = L.n;
-  const size_t mark = h->ws_off;
+  WsScope ws_scope(h); const size_t mark = ws_scope.mark;
   __nv_bfloat16* Bt;
   RET(ws_get<__nv_bfloat16>(h, (size_t)k * 6 * n, &Bt));
   dim3 pblk(32, 8), pgrd((n + 31) / 32, (k + 31) / 32);
@@ -744,7 +752,7 @@ int vcycle(dmlmc_hier* h, int level0, const void* Bin, void* Xout, int k, const 
   int lb = level0;
   while (lb < nl - 1 && !usable(h->lv[lb])) ++lb;
   CHECK(usable(h->lv[lb]), "vcycle: no dense inverse at the bottom of the cycle");
-  const size_t mark = h->ws_off;
+  WsScope ws_scope(h); const size_t mark = ws_scope.mark;
   if (lb == level0) {
     // the dense inverse IS the preconditioner of this level's own solve: use the most accurate copy
     // (a BF16 inverse costs ~20 FGMRES iterations at 1e-12 instead of 3)
@@ -921,7 +929,7 @@ int fgmres(dmlmc_hier* h, int level, const Z* B, Z* X, int k, double tol, int re
   Level& L = h->lv[level];
   const int n = L.n, m = restart;
   const size_t nk = (size_t)n * k;
-  const size_t mark = h->ws_off;
+  WsScope ws_scope(h); const size_t mark = ws_scope.mark;
   GmresState s; s.k = k; s.m = m;
   Z *Vb, *Zb, *W, *Rb, *partial;
   RET(ws_get<Z>(h, nk * (m + 1), &Vb));
@@ -968,7 +976,7 @@ int fgmres(dmlmc_hier* h, int level, const Z* B, Z* X, int k, double tol, int re
     gmres_init_kernel<<<nblocks(k, 256), 256, 0, h->stream>>>(s, tol, mode); LAUNCH_CHECK(h);
     mode = 2;
     RET(read_nactive(h, s.n_active, &nact));
-    if (nact == 0 || total_it >= maxiter) break;
+    if (nact == 0 || total_it >= maxiter) { h->unconverged += nact; break; }
     col_scale_kernel<<<nblocks(nk, 256), 256, 0, h->stream>>>(Rsrc, s.scale, Vb, nk, k, v32(0)); LAUNCH_CHECK(h);
     int j = 0;
     for (; j < m; ++j) {
@@ -1049,7 +1057,7 @@ int fgmres_eo(dmlmc_hier* h, int level, const Z* B, Z* X, int k, double tol, int
   const size_t nk = (size_t)n * k, nkh = (size_t)nh * k;
   const double c = L.d.diag.re;
   const Cx<double> ONE = {1.0, 0.0}, CC = {c, 0.0}, NIC = {-1.0 / c, 0.0}, IC = {1.0 / c, 0.0};
-  const size_t mark = h->ws_off;
+  WsScope ws_scope(h); const size_t mark = ws_scope.mark;
   GmresState s; s.k = k; s.m = m;
   Z *Vb, *Zb, *W, *Wo, *Rb, *Be, *Bo, *Bhat, *Xe, *Xo, *partial;
   RET(ws_get<Z>(h, nkh * (m + 1), &Vb));
@@ -1092,7 +1100,7 @@ int fgmres_eo(dmlmc_hier* h, int level, const Z* B, Z* X, int k, double tol, int
     gmres_init_kernel<<<nblocks(k, 256), 256, 0, h->stream>>>(s, tol, mode); LAUNCH_CHECK(h);
     mode = 2;
     RET(read_nactive(h, s.n_active, &nact));
-    if (nact == 0 || total_it >= maxiter) break;
+    if (nact == 0 || total_it >= maxiter) { h->unconverged += nact; break; }
     col_scale_eo_kernel<<<nblocks(nkh, 256), 256, 0, h->stream>>>(L.LX, L.LT, Rsrc, s.scale, Vb, k, V32); LAUNCH_CHECK(h);
     int j = 0;
     for (; j < m; ++j) {
@@ -1152,7 +1160,7 @@ int deflate(dmlmc_hier* h, int level, Z* X, int k) {
   Level& L = h->lv[level];
   if (L.defl_d == 0) return 0;
   const int n = L.n, d = L.defl_d;
-  const size_t mark = h->ws_off;
+  WsScope ws_scope(h); const size_t mark = ws_scope.mark;
   Z *partial, *C;
   RET(ws_get<Z>(h, partial_count(n, d, k), &partial));
   RET(ws_get<Z>(h, (size_t)d * k, &C));
@@ -1199,7 +1207,7 @@ int level_sample(dmlmc_hier* h, int method, int lf, int lc, const Z* X0, int k, 
   Level& Lf = h->lv[lf];
   const int nf = Lf.n;
   const size_t nkf = (size_t)nf * k;
-  const size_t mark = h->ws_off;
+  WsScope ws_scope(h); const size_t mark = ws_scope.mark;
   Z *Xdef, *RHS, *Zs, *partial, *e1;
   RET(ws_get<Z>(h, nkf, &Xdef));
   RET(ws_get<Z>(h, nkf, &RHS));
@@ -1254,7 +1262,7 @@ int level_sample(dmlmc_hier* h, int method, int lf, int lc, const Z* X0, int k, 
 
 template <typename T>
 int smooth_chunked(dmlmc_hier* h, int level, const Cx<T>* R, Cx<T>* E, int k) {
-  const size_t mark = h->ws_off;
+  WsScope ws_scope(h); const size_t mark = ws_scope.mark;
   const int n = h->lv[level].n;
   const int kc = chunk_cols(h, level, k, sizeof(Cx<T>));
   Cx<T>*rc, *ec, *t0, *t1;
@@ -1576,7 +1584,7 @@ int dmlmc_precondition(dmlmc_hier* h, int level, const void* V, void* Zout, int 
 }
 int dmlmc_dotc(dmlmc_hier* h, const void* X, const void* Y, int n, int k, void* out_dev) {
   ENTER(h); CHECK(X && Y && out_dev && n >= 1 && k >= 1, "dotc: bad arguments");
-  const size_t mark = h->ws_off;
+  WsScope ws_scope(h); const size_t mark = ws_scope.mark;
   Z* partial; RET(ws_get<Z>(h, partial_count(n, 1, k), &partial));
   int rc = multi_dot(h, (const Z*)X, 0, 1, (const Z*)Y, n, k, partial, (Z*)out_dev, 0);
   h->ws_off = mark;
@@ -1618,6 +1626,22 @@ int dmlmc_rng_sync(dmlmc_hier* h) {
   CU(cudaStreamSynchronize(h->rng_stream));
   return 0;
 }
+int dmlmc_hop_eo(dmlmc_hier* h, int level, int parity, const void* in_q, const void* in2, void* out_p,
+                 double a_re, double a_im, double b_re, double b_im, int k, const void* xc, void* z) {
+  ENTER(h); CHECK_LEVEL(h, level);
+  Level& L = h->lv[level];
+  CHECK(L.kind == 0 && L.links4 != nullptr && (L.LT % 2) == 0 && (L.LX % 2) == 0, "hop_eo: the level must be a Wilson stencil on an even lattice");
+  CHECK(in_q && k >= 2 && (k % 2) == 0 && (parity == 0 || parity == 1), "hop_eo: bad arguments (k must be even)");
+  CHECK((z == nullptr) == (xc == nullptr), "hop_eo: xc and z go together");
+  const Cx<double> a = {a_re, a_im}, b = {b_re, b_im};
+  const uint2* Q = (const uint2*)in_q; const uint2* I2 = (const uint2*)in2; uint2* O = (uint2*)out_p;
+  const int kp = k / 2;
+  if (in2 && out_p && !z)  return launch_hop_eo<true, true, false>(h, L, parity, Q, I2, O, a, b, kp, nullptr, nullptr);
+  if (!in2 && out_p && !z) return launch_hop_eo<false, true, false>(h, L, parity, Q, nullptr, O, a, b, kp, nullptr, nullptr);
+  if (in2 && out_p && z)   return launch_hop_eo<true, true, true>(h, L, parity, Q, I2, O, a, b, kp, xc, z);
+  if (in2 && !out_p && z)  return launch_hop_eo<true, false, true>(h, L, parity, Q, I2, nullptr, a, b, kp, xc, z);
+  return fail(-1, "hop_eo: this combination of inputs / outputs is not one the solver uses");
+}
 int dmlmc_apply_perm(dmlmc_hier* h, int level, const void* X, void* RHS, int k) {
   ENTER(h); CHECK_LEVEL(h, level); CHECK(X && RHS && X != RHS && k >= 1, "apply_perm: bad arguments");
   return apply_perm(h, level, (const Z*)X, (Z*)RHS, k);
@@ -1649,11 +1673,13 @@ int dmlmc_fgmres(dmlmc_hier* h, int level, const void* B, void* X, int k, double
   ENTER(h); CHECK_LEVEL(h, level); CHECK(B && X && B != X, "fgmres: bad arguments");
   if (level == h->n_levels - 1) return fail(-1, "fgmres: the coarsest level is solved by dmlmc_coarsest_apply");
   if (h->lv[level].kind < 0) return fail(-1, "fgmres: operator of this level not set");
+  h->unconverged = 0;
   return fgmres(h, level, (const Z*)B, (Z*)X, k, tol, restart, maxiter, iters_host, relres_host);
 }
 int dmlmc_level_sample(dmlmc_hier* h, int method, int level_f, int level_c, const void* X0, int k, double tol,
                        int restart, int maxiter, void* e_dev, int32_t* iters_host) {
   ENTER(h); CHECK(X0 && e_dev && k >= 1, "level_sample: bad arguments");
+  h->unconverged = 0;
   return level_sample(h, method, level_f, level_c, (const Z*)X0, k, tol, restart, maxiter, (Z*)e_dev, iters_host);
 }
 int dmlmc_level_sample_host(dmlmc_hier* h, int method, int level_f, int level_c, const uint8_t* bits_host, int k,
@@ -1661,8 +1687,9 @@ int dmlmc_level_sample_host(dmlmc_hier* h, int method, int level_f, int level_c,
   ENTER(h); CHECK(bits_host && e_host && k >= 1, "level_sample_host: bad arguments");
   CHECK(level_f >= 0 && level_f < h->n_levels && h->lv[level_f].n > 0, "level_sample_host: bad level");
   const int n = h->lv[level_f].n;
+  h->unconverged = 0;
   const size_t nbits = (size_t)n * k, nbytes = (nbits + 7) / 8;
-  const size_t mark = h->ws_off;
+  WsScope ws_scope(h); const size_t mark = ws_scope.mark;
   uint8_t* bits_dev; Z* X0; Z* e_dev;
   RET(ws_get<uint8_t>(h, nbytes, &bits_dev));
   RET(ws_get<Z>(h, (size_t)n * k, &X0));
@@ -1714,6 +1741,7 @@ int dmlmc_set_option(dmlmc_hier* h, const char* name, double value) {
   return fail(-1, std::string("dmlmc: unknown option ") + name);
 }
 long long dmlmc_launch_count(dmlmc_hier* h) { return h ? h->launches : 0; }
+int dmlmc_unconverged_columns(dmlmc_hier* h) { return h ? h->unconverged : 0; }
 int dmlmc_vcycle_chunk_cols(dmlmc_hier* h, int level, int prec, int k) {
   if (!h || level < 0 || level >= h->n_levels || k < 1) return 0;
   return chunk_cols(h, level, k, prec == DMLMC_C128 ? sizeof(Cx<double>) : sizeof(Cx<float>));

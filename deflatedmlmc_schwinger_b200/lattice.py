@@ -11,6 +11,10 @@ import numpy as np
 import scipy.sparse as sp
 
 
+class NotAStencil(Exception):
+    """the matrix is not a 2-D Wilson-Dirac stencil on the given lattice in the reference's index layout"""
+
+
 def wilson_matrix(links, mass=0.0):
     """Assemble A = S + m I (CSC, complex128) from links[2][LX][LT]."""
     links = np.asarray(links, dtype=np.complex128)
@@ -50,7 +54,7 @@ def links_from_matrix(A, LX, LT):
     A = sp.csr_matrix(A)
     V = LX * LT
     if A.shape != (2 * V, 2 * V):
-        raise Exception("matrix size does not match the lattice dimensions")
+        raise NotAStencil("matrix size does not match the lattice dimensions")
     site = np.arange(V).reshape(LX, LT)
     tp = np.roll(site, -1, axis=1).ravel()
     xp = np.roll(site, -1, axis=0).ravel()
@@ -59,12 +63,12 @@ def links_from_matrix(A, LX, LT):
     Ux = -np.asarray(A[s, xp]).ravel().reshape(LX, LT)
     diag = A.diagonal()
     if not np.all(diag == diag[0]):
-        raise Exception("matrix diagonal is not constant: not a Wilson-Dirac stencil")
+        raise NotAStencil("matrix diagonal is not constant: not a Wilson-Dirac stencil")
     links = np.stack([Ut, Ux])
     B = wilson_matrix(links, 0.0) + (diag[0] - 4.0) * sp.identity(2 * V, dtype=np.complex128, format="csc")
     D = (B - sp.csc_matrix(A))
     if D.nnz and np.abs(D.data).max() > 1e-13:
-        raise Exception("matrix is not a 2-D Wilson-Dirac stencil in the expected layout")
+        raise NotAStencil("matrix is not a 2-D Wilson-Dirac stencil in the expected layout")
     return links, diag[0]
 
 
@@ -75,3 +79,10 @@ def random_u1_links(L, seed, sigma=0.204, LT=None):
     rng = np.random.default_rng(seed)
     theta = rng.normal(0.0, sigma, size=(2, L, LT))
     return np.exp(1j * theta)
+
+
+def unpack_bf16_vectors(a):
+    """uint16 [n][c][2] (real, imaginary parts as BF16 bit patterns: the top 16 bits of a float32) -> complex128 [n][c].
+    The compact storage of the synthetic-lattice test vectors (tests/golden/synthetic256.npz)."""
+    f = (np.asarray(a).astype(np.uint32) << 16).view(np.float32).astype(np.float64)
+    return f[..., 0] + 1j * f[..., 1]

@@ -13,6 +13,8 @@ flexible and parity is on the converged solution, so the V-cycle 
 reduction-free fixed polynomial of A (Leja-ordered harmonic-Ritz roots of a degree-`smoother_degree`
 GMRES polynomial computed at setup), applied as fused operator+update Richardson steps.
 """
+import sys
+
 import numpy as np
 from scipy.sparse import csr_matrix, identity, diags
 from scipy.sparse.linalg import eigs
@@ -20,6 +22,11 @@ from scipy.sparse.linalg import eigs
 from .utils import CustomTimer
 from . import lattice
 from . import _lib
+
+
+def _warn(msg):
+    """to stderr, not through `warnings`: loadMatrix silences that module globally, as the reference does (matrix.py:16)"""
+    print("[deflatedmlmc_schwinger_b200] WARNING: " + msg, file=sys.stderr, flush=True)
 
 
 class LevelML:
@@ -203,6 +210,10 @@ def harmonic_ritz_inv_roots(A, degree, seed=7):
     return 1.0 / np.array(out, dtype=np.complex128)
 
 
+class SmootherPolynomialError(Exception):
+    """the product form of a smoother polynomial cannot be evaluated accurately at this degree / in this precision"""
+
+
 def leja_order(points):
     """Leja ordering of complex points: start from the largest modulus, then repeatedly take the point
     that maximises the product of distances to the points already chosen (running log-products, O(d^2))."""
@@ -250,7 +261,7 @@ def smoother_product_form(omega):
     val = p0 * np.prod(1.0 - np.outer(z, nu), axis=1)
     err = np.max(np.abs(val - ref) / np.abs(ref))
     if not err < 1e-6:
-        raise Exception("smoother polynomial: product form is inaccurate (%.2e); lower the degree" % err)
+        raise SmootherPolynomialError("smoother polynomial: product form is inaccurate (%.2e); lower the degree" % err)
     return nu, p0
 
 
@@ -515,9 +526,16 @@ class MG:
             dims = [L, L]
         try:
             links, diag = lattice.links_from_matrix(A0, dims[1] if len(dims) > 1 else dims[0], dims[0])
+        except lattice.NotAStencil as why:
+            links = None
+            if params.get('geometric_first') is None:
+                # the caller's own matrix: say that the link-form kernels are not in use (orders of magnitude slower)
+                _warn("level 0 is not a Wilson-Dirac stencil on the %s lattice (%s): generic block-sparse kernels are used"
+                              % (dims, why))
+        if links is not None:
             dev.set_stencil(0, links, diag)
             self.level0_format = "stencil"
-        except Exception:
+        else:
             col, vals = bsr_padded(A0, self.level0_block)
             dev.set_bsr(0, n0, self.level0_block, col, vals)
             self.level0_format = "bsr%d" % self.level0_block
@@ -551,9 +569,9 @@ class MG:
                             storage = st
                             break
                     if storage is None:
-                        raise Exception("smoother polynomial unstable in complex64")
+                        raise SmootherPolynomialError("smoother polynomial unstable in complex64")
                     break
-                except Exception:
+                except SmootherPolynomialError:
                     if d <= 4:
                         raise
                     d = max(4, (3 * d) // 4)
@@ -563,19 +581,27 @@ class MG:
             dev.set_smoother(i, nu, p0, storage16=(storage == 'bf16'))
             if i == 0 and self.eo_degree and self.level0_format == "stencil" and storage == 'bf16':
                 # polynomial in the even-odd Schur complement: degree d there ~ degree 2d in A at the cost of d applications
-                try:
-                    S, _c = even_odd_schur(lv[0].A, dims[1] if len(dims) > 1 else dims[0], dims[0])
+                LXs, LTs = (dims[1] if len(dims) > 1 else dims[0]), dims[0]
+                self.eo_poly = None
+                if LXs % 2 or LTs % 2 or abs(complex(diag).imag) > 0:
+                    _warn("even-odd smoother not used: odd lattice extent or complex mass")
+                else:
+                    S, _c = even_odd_schur(lv[0].A, LXs, LTs)
                     de = int(self.eo_degree)
                     while de >= 2:
                         om = harmonic_ritz_inv_roots(S, de)
-                        nue, p0e = smoother_product_form(om)
+                        try:
+                            nue, p0e = smoother_product_form(om)
+                        except SmootherPolynomialError:
+                            de = (3 * de) // 4
+                            continue
                         if smoother_storage_error(S, om, nue, p0e, 'bf16') < 0.15:
                             dev.set_smoother_eo(0, nue, p0e)
                             self.eo_poly = (nue, p0e)
                             break
                         de = (3 * de) // 4
-                except Exception:
-                    self.eo_poly = None
+                    if self.eo_poly is None:
+                        _warn("even-odd smoother not used: no stable polynomial of degree <= %d" % int(self.eo_degree))
         if use_permuted:
             for i in range(nl):
                 if i == 0:
@@ -605,8 +631,7 @@ class MG:
             self.dense_levels[i] = "host" if small else "tensor"
             self.dense_level = i
             del Minv
-        dev._ws = None
-        dev._ws_key = None
+        dev.release_workspace()
         import torch
         torch.cuda.empty_cache()
         if self.geometric_precond and self.level0_format == "stencil":

@@ -32,7 +32,7 @@
 extern "C" {
 #endif
 
-#define DMLMC_ABI_VERSION 3
+#define DMLMC_ABI_VERSION 4
 
 enum { DMLMC_C128 = 0, DMLMC_C64 = 1 };
 
@@ -137,6 +137,15 @@ int dmlmc_mt19937_bits(dmlmc_hier* h, uint32_t* state_dev, uint32_t* backup_dev,
 int dmlmc_probe_expand_bytes(dmlmc_hier* h, const uint8_t* lsb_dev, int n, int k, void* X0);
 /* wait for the probe-stream generator (before reading its state back to the host) */
 int dmlmc_rng_sync(dmlmc_hier* h);
+/* one half-lattice sweep of the even-odd smoother on a stencil level, as the V-cycle launches it (the operator inside the
+ * lgmres smoother call of multigrid.py:393-394, restricted to one checkerboard colour):
+ *   Out_p = a * In2_p + b * (H In_q),   H = A_level - diag,  q = 1 - parity
+ * In_q / In2_p / Out_p: BF16 checkerboard half-lattice arrays [2 spins][LX][LT/2][k] of (re, im) BF16 pairs, site
+ * t = 2 th + ((x + p) & 1); in2 == NULL: a = 0; out_p == NULL: no half-lattice output; z != NULL: additionally
+ * Z[site][:] = Xc[site][:] + result at the sites of parity p (Xc complex64, Z complex128, full-lattice [n][k]).
+ * k must be even.  The four combinations the solver uses are available: (in2, out_p, z) = (y,y,n), (n,y,n), (y,y,y), (y,n,y). */
+int dmlmc_hop_eo(dmlmc_hier* h, int level, int parity, const void* in_q, const void* in2, void* out_p,
+                 double a_re, double a_im, double b_re, double b_im, int k, const void* xc, void* z);
 /* RHS = Bblock_perm_level * roll(X, +shift_level)   utils.py:232,288-290 (identity if no perm set) */
 int dmlmc_apply_perm(dmlmc_hier* h, int level, const void* X, void* RHS, int k);
 
@@ -208,6 +217,9 @@ int dmlmc_level_sample_host(dmlmc_hier* h, int method, int level_f, int level_c,
  *   "dot32"        0 (default; 1 measured harmful): Gram-Schmidt coefficients from complex64 copies of the basis */
 int dmlmc_set_option(dmlmc_hier* h, const char* name, double value);
 
+/* columns that the solves of the last dmlmc_fgmres / dmlmc_level_sample[_host] call left above the tolerance when
+ * maxiter was reached (the reference ignores pyamg's exit code at multigrid.py:362; here it can be checked) */
+int dmlmc_unconverged_columns(dmlmc_hier* h);
 /* number of kernels launched by this handle since creation (bench.py's gpu_launches) */
 long long dmlmc_launch_count(dmlmc_hier* h);
 /* columns per chunk the V-cycle uses on `level` for a batch of k columns of precision prec */

@@ -86,6 +86,13 @@ def wilson_from_links(links):
     return S
 
 
+def synthetic_links(L, seed, sigma=0.204):
+    """SURVEY.md 8d cfg-5: theta_mu(x) ~ N(0, sigma^2) i.i.d. from numpy default_rng(seed), U = exp(i theta);
+    links[mu][x][t], mu = 0 <-> t, 1 <-> x (the generator the synthetic-lattice parity fixtures are built from)"""
+    rng = np.random.default_rng(seed)
+    return np.exp(1j * rng.normal(0.0, sigma, size=(2, L, L)))
+
+
 def load_matrix(matrix_name, mass):
     """matrix.py:14-31: A = S + m I.  The 16^2 file stores gamma3*S and the reference
     flips it back (matrix.py:25-27); the link fixture already describes S itself."""

@@ -388,3 +388,77 @@ def test_even_odd_smoother_cycle_matches_numpy(mg128):
     print("even-odd cycle vs restatement", err, " vs the degree-36 cycle in A", relerr(Z2, ref))
     assert err < 3e-2                      # BF16-grade (storage of the intermediates, BF16 coarse operand)
     assert not np.array_equal(Z, Z2)       # the even-odd path was taken
+
+
+# ---- bit-exact test of the even-odd hop kernel --------------------------------------------------
+def _hop_case(LX, LT, seed):
+    """a stencil level whose links are fourth roots of unity (products with small integers are exact in BF16 / FP32) and
+    the matching scipy operator H = A - diag"""
+    from deflatedmlmc_schwinger_b200 import _lib, lattice
+    rs = np.random.RandomState(seed)
+    links = (1j ** rs.randint(4, size=(2, LX, LT))).astype(np.complex128)
+    diag = 4.0 - 0.25
+    dev = _lib.Hierarchy(2)
+    dev.set_stencil(0, links, diag)
+    H = (lattice.wilson_matrix(links, -0.25) - diag * __import__("scipy.sparse").sparse.identity(2 * LX * LT)).tocsr()
+    return dev, H
+
+
+def _eo_rows(LX, LT, p):
+    """full-lattice row of entry [s][x][th] of the parity-p half-lattice layout (t = 2 th + ((x + p) & 1))"""
+    s, x, th = np.meshgrid(np.arange(2), np.arange(LX), np.arange(LT // 2), indexing="ij")
+    t = 2 * th + ((x + p) & 1)
+    return (s * LX * LT + x * LT + t).ravel()
+
+
+def _int_cplx(rs, shape, lim=3):
+    return (rs.randint(-lim, lim + 1, size=shape) + 1j * rs.randint(-lim, lim + 1, size=shape)).astype(np.complex128)
+
+
+def _to_bf16_half(v, LX, LT, k):
+    """complex [nh][k] -> torch.bfloat16 [2, LX, LT/2, k, 2] on the device"""
+    a = np.stack([v.real, v.imag], axis=-1).astype(np.float32).reshape(2, LX, LT // 2, k, 2)
+    return torch.from_numpy(a).cuda().to(torch.bfloat16).contiguous()
+
+
+@pytest.mark.parametrize("LX,LT", [(4, 4), (6, 8), (16, 12)])
+@pytest.mark.parametrize("k", [2, 4, 6, 64])
+@pytest.mark.parametrize("variant", ["y,y,n", "n,y,n", "y,y,y", "y,n,y"])
+@pytest.mark.parametrize("parity", [0, 1])
+def test_wilson_hop_eo_kernel_is_bit_exact_on_integer_data(LX, LT, k, variant, parity):
+    """wilson_hop_eo_kernel, every template variant the solver launches (k % 4 == 0: four columns per thread, else two), both
+    checkerboard colours, lattices small enough that every row is a wrap row in x or t for some thread: small Gaussian
+    integers, links in {1, i, -1, -i}, a, b in {0, +-1, +-i} -- every product and sum is exact in BF16 storage / FP32
+    arithmetic, so the output must EQUAL the scipy operator's, bit for bit, and an indexing error anywhere shows."""
+    dev, H = _hop_case(LX, LT, 100 * LX + LT)
+    n, nh = 2 * LX * LT, LX * LT
+    has2, hout, zout = [c == "y" for c in variant.split(",")]
+    rows_p, rows_q = _eo_rows(LX, LT, parity), _eo_rows(LX, LT, 1 - parity)
+    rs = np.random.RandomState(7 * k + parity)
+    units = [1, -1, 1j, -1j]
+    for trial, (a, b) in enumerate([(units[rs.randint(4)], units[rs.randint(4)]), (0, units[rs.randint(4)]), (1, -1), (-1j, 1j)]):
+        if not has2:
+            a = 0
+        vq, v2 = _int_cplx(rs, (nh, k)), _int_cplx(rs, (nh, k))
+        full = np.zeros((n, k), dtype=np.complex128)
+        full[rows_q] = vq
+        ref = b * (H @ full)[rows_p] + (a * v2 if has2 else 0)
+        inq, in2 = _to_bf16_half(vq, LX, LT, k), (_to_bf16_half(v2, LX, LT, k) if has2 else None)
+        out = torch.full((2, LX, LT // 2, k, 2), 777.0, dtype=torch.bfloat16, device="cuda") if hout else None
+        xc = z = None
+        if zout:
+            xcn = _int_cplx(rs, (n, k), 5)
+            xc = torch.from_numpy(xcn.astype(np.complex64)).cuda().contiguous()
+            z = torch.full((n, k), 1234.5 + 0j, dtype=torch.complex128, device="cuda")
+        dev.hop_eo(0, parity, inq, in2, out, a, b, k, xc, z)
+        torch.cuda.synchronize()
+        if hout:
+            o = out.float().cpu().numpy().reshape(nh, k, 2)
+            got = o[..., 0] + 1j * o[..., 1]
+            assert np.array_equal(got, ref), (variant, parity, trial, np.argwhere(got != ref)[:4])
+        if zout:
+            zz = z.cpu().numpy()
+            want = np.full((n, k), 1234.5 + 0j)
+            want[rows_p] = xcn[rows_p] + ref
+            assert np.array_equal(zz, want), (variant, parity, trial)
+    dev.close()

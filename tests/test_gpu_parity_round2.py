@@ -1,0 +1,131 @@
+"""GPU tier, parity cases added in round 2 ("what's weak" #1): the bench configuration itself at
+k = 512 against the unmodified reference's samples, the valid deflated 128^2 variant with the reference's own
+difference-operator eigenvectors, and BASELINE config 5 (synthetic random-U(1) lattice) against the oracle port.
+Tolerances (north_star): estimates within 1e-8 relative, true residual <= 1.3e-12 (see tests/test_gpu_solver.py)."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+GOLDEN = os.path.join(ROOT, "tests", "golden")
+RES_MAX = 1.3e-12
+
+
+def host(t):
+    return t.cpu().numpy().astype(np.complex128)
+
+
+@pytest.fixture(scope="module")
+def g128ext():
+    return np.load(os.path.join(GOLDEN, "schwinger128_ext.npz"))
+
+
+@pytest.fixture(scope="module")
+def gsynth():
+    return np.load(os.path.join(GOLDEN, "synthetic256.npz"))
+
+
+def test_level0_samples_128_sixteen_probes(mg128, g128ext):
+    """16 level-0 difference samples of the shipped set against utils.py:252-357 run by the unmodified reference"""
+    from deflatedmlmc_schwinger_b200 import utils
+    mg, tp, A = mg128
+    np.random.seed(123456)
+    e, it = utils.defl_Hutch_batch(mg, tp, "mlmc", 0, None, 0, 16)
+    ref = g128ext["shipped_l0_e"]
+    assert np.abs(e - ref).max() < 1e-8 * np.abs(ref).max()
+    assert mg.dev.unconverged_columns() == 0
+
+
+@pytest.mark.parametrize("outer_eo", [0, 1])
+def test_bench_configuration_k512_matches_reference_samples(g128ext, outer_eo):
+    """bench.py's own solver object (bench.build_solver: geometric preconditioner hierarchy, even-odd smoother, tcgen05 coarse
+    solves, CUDA graphs) at the bench's batch size k = 512 through the host-buffer C-ABI call the bench times: the first 16
+    columns are the probes the reference's golden samples were drawn from.  Also with the outer solve on the even-odd Schur
+    complement (option outer_eo)."""
+    import bench
+    from deflatedmlmc_schwinger_b200 import sampling, utils
+    mg, tp, A, _ = bench.build_solver(options=[("outer_eo", outer_eo)])
+    n0, k = mg.level_shapes[0], 512
+    np.random.seed(123456)
+    bits = sampling.draw_probe_bits(k * n0)
+    e, it = mg.dev.level_sample_host(1, 0, 2, utils.pack_bits(bits), k, 1e-12, 40, 1000)
+    ref = g128ext["shipped_l0_e"]
+    assert np.abs(e[:16] - ref).max() < 1e-8 * np.abs(ref).max()
+    assert mg.dev.unconverged_columns() == 0
+    # every column: the level-0 solve again through dmlmc_fgmres, true residual on the host in complex128
+    X0 = (bits.reshape(k, n0).T.astype(np.float64) * 2 - 1).astype(np.complex128)
+    rhs = np.roll(X0, 512, axis=0)
+    Z, iters, relres = mg.solve_batch(0, torch.from_numpy(np.ascontiguousarray(rhs)).cuda(), 1e-12)
+    res = np.linalg.norm(rhs - A @ host(Z), axis=0) / np.linalg.norm(rhs, axis=0)
+    print("k = 512, outer_eo =", outer_eo, ": iterations", iters.min(), iters.max(), " max true residual", res.max())
+    assert res.max() <= RES_MAX
+    mg.dev.close()
+    if mg.precond_mg is not None:
+        mg.precond_mg.dev.close()
+
+
+def test_deflated_variant_128_matches_reference(g128, g128ext):
+    """SURVEY.md 8d cfg-2, the valid deflated variant: not permuted, mlmc_deflat_vctrs = [16, 0, 16].  The reference's own eigsh
+    vectors of diff_op_Q (stored as complex64) are injected on both sides; tr1 and 8 deflated samples per level against the
+    unmodified reference (utils.py:130-201, 252-357)."""
+    from deflatedmlmc_schwinger_b200 import utils
+    from conftest import make_mg, params128
+    p = params128()
+    p["use_permuted"] = False
+    p["mlmc_deflat_vctrs"] = [16, 0, 16]
+    mg, tp, A = make_mg(p, "mlmc", [g128["tv0"], g128["tv1"], g128["tv2"]], smoother_degree=32)
+    mg.skip_level = True
+    for ix in (0, 2):
+        V = g128ext["defl_l%d_eigvecs_c64" % ix].astype(np.complex128)
+        Vx, Ux, tr1 = utils.deflation_pre_computations(A, 16, tp["defl_eigvs_tol_MLMC"], "mlmc", mg.timer, tp, mg, None, level_nr=ix,
+                                                       eigpairs=(g128ext["defl_l%d_Sy" % ix], V))
+        ref_tr1 = g128ext["defl_l%d_tr1" % ix]
+        assert abs(tr1 - ref_tr1) < 1e-10 * abs(ref_tr1)
+        np.random.seed(123456 + ix)
+        e, it = utils.defl_Hutch_batch(mg, tp, "mlmc", 16, Vx, ix, 8)
+        ref = g128ext["defl_l%d_e" % ix]
+        print("deflated variant level", ix, "iterations", it[0].max(), it[1].max(), "max rel diff", np.abs(e - ref).max() / np.abs(ref).max())
+        assert np.abs(e - ref).max() < 1e-8 * np.abs(ref).max(), ix
+    mg.dev.close()
+
+
+def test_synthetic_256_matches_oracle(gsynth):
+    """BASELINE config 5 at 256^2: random-U(1) lattice, 4 levels, BOTH solves preconditioned by geometric hierarchies (the level-1
+    operator has no dense inverse here), BSR BF16 smoother on the coarse levels -- 8 level-0 difference samples (fine 0, coarse 1)
+    against oracle/refport.py on the same lattice, test vectors and probes; solutions against the oracle's, true residuals."""
+    from deflatedmlmc_schwinger_b200 import lattice, multigrid, sampling, utils
+    g = gsynth
+    L, mass = int(g["L"]), float(g["mass"])
+    A = lattice.wilson_matrix(lattice.random_u1_links(L, int(g["seed"]), float(g["sigma"])), mass)
+    tvs = [lattice.unpack_bf16_vectors(g["tv%d_bf16" % i]) for i in range(3)]
+    tp = {"use_permuted": False, "latt_dims": [L, L], "x_displacement": 2, "test_vectors_type": "EVs", "function_params": {"tol": 1e-12}}
+    mg = multigrid.MG(A, smoother_degree=80, geometric_precond=True)
+    mg.setup(dof=list(g["dof"]), aggrs=list(g["aggrs"]), max_levels=4, acc_eigvs="low", params=tp, test_vectors=tvs)
+    assert mg.level_shapes == list(g["level_sizes"])
+    assert mg.precond_mg is not None and mg.precond_mg1 is not None        # the configuration-5 solver, not a fallback
+    n0, k = mg.level_shapes[0], 8
+    np.random.seed(123456)
+    bits = sampling.draw_probe_bits(k * n0)
+    e, it = utils.defl_Hutch_batch(mg, tp, "mlmc", 0, None, 0, k, bits01=bits)
+    ref = g["l0_e"]
+    print("synthetic 256^2: iterations", it[0].max(), it[1].max(), "(oracle:", g["l0_iters"][0], ") max rel diff", np.abs(e - ref).max() / np.abs(ref).max())
+    assert np.abs(e - ref).max() < 1e-8 * np.abs(ref).max()
+    assert mg.dev.unconverged_columns() == 0
+    X0 = (bits.reshape(k, n0).T.astype(np.float64) * 2 - 1).astype(np.complex128)
+    Z, iters, relres = mg.solve_batch(0, torch.from_numpy(np.ascontiguousarray(X0)).cuda(), 1e-12)
+    z = host(Z)
+    res = np.linalg.norm(X0 - A @ z, axis=0) / np.linalg.norm(X0, axis=0)
+    assert res.max() <= RES_MAX
+    zsub = g["l0_z_sub"]
+    assert np.abs(z[::256].T - zsub).max() < 1e-8 * np.abs(zsub).max()
+    X1 = mg.dev.restrict(0, torch.from_numpy(np.ascontiguousarray(X0)).cuda())
+    Y, iters1, relres1 = mg.solve_batch(1, X1, 1e-12)
+    A1 = mg.ml.levels[1].A
+    res1 = np.linalg.norm(host(X1) - A1 @ host(Y), axis=0) / np.linalg.norm(host(X1), axis=0)
+    assert res1.max() <= RES_MAX
+    for m in (mg.precond_mg, mg.precond_mg1, mg):
+        m.dev.close()

@@ -9,6 +9,10 @@ from oracle import refport
 
 pytestmark = pytest.mark.gpu
 
+# every column leaves the solve on its TRUE complex128 residual: <= tol on the Arnoldi estimate in the first cycle, and
+# <= 1.25 tol + 1e-14 when a later cycle re-checks it against b - A x (gmres_init_kernel) -- so with tol = 1e-12:
+RES_MAX = 1.3e-12
+
 
 def host(t):
     return t.cpu().numpy().astype(np.complex128)
@@ -29,7 +33,7 @@ def test_fgmres_16_solutions_match_reference(mg16, g16, prec):
     x = host(X)
     assert np.all(relres < 1e-12) and np.all(iters > 0)
     res = np.linalg.norm(B - A @ x, axis=0) / np.linalg.norm(B, axis=0)
-    assert res.max() < 1e-11
+    assert res.max() <= RES_MAX
     for q in range(8):                       # the reference's own solutions for the same probes
         z = g16["plain_hutch_z"][q]
         assert np.linalg.norm(x[:, q] - z) / np.linalg.norm(z) < 1e-8
@@ -42,7 +46,7 @@ def test_fgmres_restart_and_maxiter(mg16):
     Bd = torch.from_numpy(np.ascontiguousarray(B)).cuda()
     X, iters, relres = mg.dev.fgmres(0, Bd, 1e-12, restart=3, maxiter=512)     # forces restarts
     res = np.linalg.norm(B - A @ host(X), axis=0) / np.linalg.norm(B, axis=0)
-    assert res.max() < 1e-11
+    assert res.max() <= RES_MAX
     X, iters, relres = mg.dev.fgmres(0, Bd, 1e-12, restart=40, maxiter=2)      # hits maxiter
     assert np.all(iters == 2) and np.all(relres > 1e-12)
     Z = torch.zeros_like(Bd)                                                    # zero rhs -> zero solution
@@ -69,7 +73,7 @@ def test_fgmres_128_all_levels(mg128, g128):
         X, iters, relres = mg.solve_batch(lvl, torch.from_numpy(np.ascontiguousarray(B)).cuda(), 1e-12)
         res = np.linalg.norm(B - Al @ host(X), axis=0) / np.linalg.norm(B, axis=0)
         print("level", lvl, "iters", iters.min(), iters.max(), "true relres", res.max())
-        assert res.max() < 1e-11 and relres.max() < 1e-12
+        assert res.max() <= RES_MAX and relres.max() <= RES_MAX
 
 
 def test_level_samples_16_match_reference(mg16, g16):
@@ -149,7 +153,7 @@ def test_full_size_batch_properties_128(mg128):
     rhs = np.roll(X0, 512, axis=0)
     Z, iters, relres = mg.solve_batch(0, torch.from_numpy(np.ascontiguousarray(rhs)).cuda(), 1e-12)
     res = np.linalg.norm(rhs - A @ host(Z), axis=0) / np.linalg.norm(rhs, axis=0)
-    assert res.max() < 1e-11
+    assert res.max() <= RES_MAX
     lv = mg.ml.levels
     xc = lv[1].R @ (lv[0].R @ rhs)
     Y, _, _ = mg.solve_batch(2, torch.from_numpy(np.ascontiguousarray(xc)).cuda(), 1e-12)
@@ -232,7 +236,7 @@ def test_geometric_preconditioner_128(mg128):
     Bd = torch.from_numpy(np.ascontiguousarray(B)).cuda()
     X, it, relres = mg.dev.fgmres(0, Bd, 1e-12)
     res = np.linalg.norm(B - A0 @ host(X), axis=0) / np.linalg.norm(B, axis=0)
-    assert res.max() < 1e-11 and relres.max() < 1e-12
+    assert res.max() <= RES_MAX and relres.max() <= RES_MAX
     mg.dev.set_preconditioner(0, None)
     try:
         X2, it2, relres2 = mg.dev.fgmres(0, Bd, 1e-12)
@@ -282,7 +286,7 @@ def test_geometric_preconditioner_of_the_level1_solve(g128):
     Bd = torch.from_numpy(np.ascontiguousarray(B)).cuda()
     X, it, relres = mg.dev.fgmres(1, Bd, 1e-12)
     res = np.linalg.norm(B - A1 @ host(X), axis=0) / np.linalg.norm(B, axis=0)
-    assert res.max() < 1e-11 and relres.max() < 1e-12
+    assert res.max() <= RES_MAX and relres.max() <= RES_MAX
     mg.dev.set_preconditioner(1, None)
     X2, it2, relres2 = mg.dev.fgmres(1, Bd, 1e-12)
     print("level-1 outer iterations: geometric", it.min(), it.max(), " estimator's hierarchy", it2.min(), it2.max())
@@ -294,7 +298,7 @@ def test_geometric_preconditioner_of_the_level1_solve(g128):
     B0 = probes(A0.shape[0], 4, seed=22)
     X0, it0, rr0 = mg.dev.fgmres(0, torch.from_numpy(np.ascontiguousarray(B0)).cuda(), 1e-12)
     res0 = np.linalg.norm(B0 - A0 @ host(X0), axis=0) / np.linalg.norm(B0, axis=0)
-    assert res0.max() < 1e-11 and it0.max() <= 14
+    assert res0.max() <= RES_MAX and it0.max() <= 14
 
 
 @pytest.mark.parametrize("k", [2, 16])
@@ -313,6 +317,6 @@ def test_outer_solve_on_the_even_odd_schur_complement(mg128, k):
         mg.set_option("outer_eo", 0)
     res = np.linalg.norm(B - A0 @ host(X1), axis=0) / np.linalg.norm(B, axis=0)
     print("outer_eo iterations", it1.min(), it1.max(), "full", it0.min(), it0.max(), "true relres", res.max())
-    assert res.max() < 1e-11
+    assert res.max() <= RES_MAX
     assert np.abs(host(X1) - host(X0)).max() < 1e-8 * np.abs(host(X0)).max()
     assert np.abs(it1.astype(int) - it0.astype(int)).max() <= 2

@@ -145,3 +145,66 @@ def test_port16_deflated_mlmc_probes_match_reference(port16, g16defl):
             e, _ = refport.one_defl_hutch_step(mp.levels[ix].A, mp.levels[ix + 1].A, mp, tp, "mlmc", 16,
                                                g16defl["l%d_Vx" % ix], g16defl["l%d_Ux" % ix], rs, ix)
             assert abs(e - ref[q]) < 1e-8 * max(abs(ref[q]), 1.0), (ix, q)
+
+
+# ---- round 2 fixtures ------------------------------------------------------------------------------------------------------
+def test_port128_deflated_variant_level2_matches_reference(g128):
+    """schwinger128_ext.npz, deflated variant (not permuted, mlmc_deflat_vctrs = [16, 0, 16]): tr1 and the 8 deflated level-2
+    samples the UNMODIFIED reference produced from the stored (complex64) eigsh vectors of diff_op_Q -- reproduced by the
+    port from the same stored vectors (utils.py:145-176, 252-357)"""
+    import os
+    from conftest import GOLDEN, params128
+    from deflatedmlmc_schwinger_b200 import utils
+    ge = np.load(os.path.join(GOLDEN, "schwinger128_ext.npz"))
+    p = params128()
+    p["use_permuted"] = False
+    p["mlmc_deflat_vctrs"] = [16, 0, 16]
+    tp = utils.trace_params_from_params(p, "mlmc")
+    mp = refport.MGPort(refport.load_matrix(p["matrix"], p["matrix_params"]["mass"]))
+    mp.setup(tp["dof"], tp["aggrs"], tp["max_nr_levels"], tp["accuracy_mg_eigvs"], tp, test_vectors=[g128["tv0"], g128["tv1"], g128["tv2"]])
+    mp.skip_level = True
+    V = ge["defl_l2_eigvecs_c64"].astype(np.complex128)
+    Vx, Ux, tr1 = refport.deflation_pre_computations(mp.levels[0].A, 16, 1e-1, "mlmc", tp, mp, None, level_nr=2, eigpairs=(ge["defl_l2_Sy"], V))
+    assert abs(tr1 - ge["defl_l2_tr1"]) < 1e-10 * abs(ge["defl_l2_tr1"])
+    rs = np.random.RandomState(123456 + 2)
+    for q in range(8):
+        e, _ = refport.one_defl_hutch_step(mp.levels[2].A, mp.levels[3].A, mp, tp, "mlmc", 16, Vx, Ux, rs, 2)
+        assert abs(e - ge["defl_l2_e"][q]) < 1e-8 * abs(ge["defl_l2_e"][q]), q
+
+
+def test_synthetic_fixture_header_and_generators():
+    """synthetic256.npz: the oracle's and the product's generators of the random-U(1) lattice agree bit for bit, both decode the
+    BF16-stored test vectors identically, and the stored vectors are what the fixture says (4 per level, level sizes)"""
+    import os
+    from conftest import GOLDEN
+    from oracle import make_golden
+    from deflatedmlmc_schwinger_b200 import lattice
+    g = np.load(os.path.join(GOLDEN, "synthetic256.npz"))
+    L = int(g["L"])
+    assert np.array_equal(refport.synthetic_links(L, int(g["seed"]), float(g["sigma"])), lattice.random_u1_links(L, int(g["seed"]), float(g["sigma"])))
+    for i, n in enumerate(g["level_sizes"][:3]):
+        a = make_golden.bf16_unpack(g["tv%d_bf16" % i])
+        assert a.shape == (n, 4) and np.array_equal(a, lattice.unpack_bf16_vectors(g["tv%d_bf16" % i]))
+        assert np.array_equal(make_golden.bf16_pack(a), g["tv%d_bf16" % i])           # decode/encode round trip
+        assert np.all(np.abs(np.linalg.norm(a, axis=0) - 1.0) < 1e-2)                  # eigs returns unit vectors
+    assert list(g["level_sizes"]) == [2 * L * L // 4 ** i for i in range(4)]
+
+
+def test_packaged_links_equal_the_reference_mat_files():
+    """deflatedmlmc_schwinger_b200/data/*_links.npy rebuild both reference matrices bit for bit (runs where /root/reference is
+    present, i.e. in the authoring container; the GPU box has no reference tree)"""
+    import os
+    from oracle import ref_shim
+    if not ref_shim.reference_available():
+        pytest.skip("reference tree not present")
+    import scipy.io as sio
+    from deflatedmlmc_schwinger_b200 import lattice
+    data = os.path.join(os.path.dirname(os.path.abspath(lattice.__file__)), "data")
+    for name in ("schwinger16", "schwinger128"):
+        S = sio.loadmat(os.path.join(ref_shim.REF_DIR, name + ".mat"))["S"].tocsc()
+        if name == "schwinger16":                        # matrix.py:25-27: the 16^2 file stores gamma3 S
+            h = S.shape[0] // 2
+            S = S.tolil(); S[h:, :] = -S[h:, :]; S = S.tocsc()
+        D = (lattice.wilson_matrix(np.load(os.path.join(data, name + "_links.npy")), 0.0) - S).tocsc()
+        D.eliminate_zeros()
+        assert D.nnz == 0, name
