@@ -54,6 +54,7 @@ _SIGS = {
     "dmlmc_probe_expand": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_void_p]),
     "dmlmc_mt19937_bits": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_longlong,
                                           ctypes.c_longlong, ctypes.c_longlong, ctypes.c_void_p]),
+    "dmlmc_set_mt_jump_table": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int]),
     "dmlmc_probe_expand_bytes": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_void_p]),
     "dmlmc_rng_sync": (ctypes.c_int, [ctypes.c_void_p]),
     "dmlmc_apply_perm": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int]),
@@ -94,7 +95,7 @@ def load():
         fn = getattr(lib, name)          # AttributeError if the ABI is incomplete
         fn.restype = res
         fn.argtypes = args
-    if lib.dmlmc_abi_version() != 4:
+    if lib.dmlmc_abi_version() != 5:
         raise RuntimeError("libdmlmc_sm100.so ABI version mismatch")
     _lib = lib
     return lib
@@ -339,6 +340,11 @@ class Hierarchy:
         """state: int32 CUDA tensor [625] (key + position, bit pattern of uint32); out: uint8 CUDA tensor [count]"""
         if out is None and count > 0:
             out = self.torch.empty(int(count), dtype=self.torch.uint8, device=self.device)
+        if not getattr(self, "_mt_table_set", False):
+            from . import mtjump
+            tab = np.ascontiguousarray(mtjump.table())
+            _check(self.lib.dmlmc_set_mt_jump_table(self.h, tab.ctypes.data_as(ctypes.c_void_p), int(tab.shape[0])))
+            self._mt_table_set = True
         _check(self.lib.dmlmc_mt19937_bits(self.h, ctypes.c_void_p(state.data_ptr()),
                                            ctypes.c_void_p(backup.data_ptr()) if backup is not None else None,
                                            int(skip_before), int(count), int(skip_after),

@@ -92,7 +92,7 @@ struct dmlmc_hier {
   int pre_smooth = 0;                     // 0: V-cycle = coarse correction + post-smoothing (default), 1: pre- and post-smoothing
   int smoother_half = 1;                  // BF16 storage of the level-0 smoother's intermediate vectors (c64 cycle)
   int dense_direct_exact = 1;             // a dense level solved directly (not from a finer level) uses its FP32 copy
-  int outer_eo = 0;                       // UNVALIDATED (round 2): outer FGMRES of a stencil level on the even-odd Schur complement
+  int outer_eo = 1;                       // outer FGMRES of a stencil level on the even-odd Schur complement (fgmres_eo)
   int eo_zhalf = 0;                       // (internal) the even-odd smoother writes only Z_e, into a half-lattice array
   int smoother_eo = 1;                    // even-odd (Schur complement) form of the level-0 post-smoother when one is set
   int dot32 = 0;                          // Gram-Schmidt coefficients from complex64 copies of the basis vectors: OFF -- measured on
@@ -113,6 +113,10 @@ struct dmlmc_hier {
   char* ws = nullptr; size_t ws_bytes = 0, ws_off = 0;
   int* h_nactive = nullptr;        // pinned
   cudaStream_t rng_stream = nullptr; cudaEvent_t rng_done = nullptr;   // the probe stream runs beside the solver
+  uint32_t* mt_tab = nullptr; int mt_tab_rows = 0;    // jump polynomials t^(2^b) mod phi (dmlmc_set_mt_jump_table)
+  uint32_t* mt_state_out = nullptr;                   // [625] state written by the jump kernel, copied over the caller's afterwards
+  int mt_jump = 1;                                    // option: 0 = the sequential one-CTA generator
+  bool mtj_attr_set = false;
   cudaStream_t cap_stream = nullptr;                                   // capture stream of the V-cycle graphs
   long long launches = 0;
   int unconverged = 0;                    // columns the solves of the last fgmres / level_sample call left above tol at maxiter
@@ -1025,7 +1029,7 @@ int fgmres(dmlmc_hier* h, int level, const Z* B, Z* X, int k, double tol, int re
   return 0;
 }
 
-// ---- UNVALIDATED on hardware (written at the end of round 1 without GPU time; option "outer_eo", default 0) ----------------
+// ---- outer solve on the even-odd Schur complement (option "outer_eo", default 1; profiles/r2_run1_*: 27.97k -> 34.21k probes/s) ----
 // Batched FGMRES of a stencil level on the even-odd Schur complement:  S x_e = b^_e = b_e - H_eo b_o / c,  S = c - H_eo H_oe / c,
 // x_o = (b_o - H_oe x_e) / c.  All Krylov vectors are half-lattice (checkerboard) arrays, so Gram-Schmidt, normalisation and
 // the final update move half the bytes; the preconditioner is the even part of the V-cycle applied to (v_e, 0).  CPU experiment
@@ -1335,6 +1339,8 @@ int dmlmc_hier_destroy(dmlmc_hier* h) {
   for (void* p : h->owned) cudaFree(p);
   if (h->h_nactive) cudaFreeHost(h->h_nactive);
   if (h->rng_stream) { cudaStreamSynchronize(h->rng_stream); cudaStreamDestroy(h->rng_stream); }
+  if (h->mt_tab) cudaFree(h->mt_tab);
+  if (h->mt_state_out) cudaFree(h->mt_state_out);
   if (h->rng_done) cudaEventDestroy(h->rng_done);
   if (h->cap_stream) cudaStreamDestroy(h->cap_stream);
   delete h;
@@ -1601,15 +1607,42 @@ int dmlmc_probe_expand(dmlmc_hier* h, const uint8_t* bits_dev, int n, int k, voi
   LAUNCH_CHECK(h);
   return 0;
 }
+int dmlmc_set_mt_jump_table(dmlmc_hier* h, const uint32_t* tab_host, int rows) {
+  ENTER(h); CHECK(tab_host && rows >= 11 && rows <= 64, "set_mt_jump_table: bad arguments");
+  if (h->mt_tab) { CU(cudaFree(h->mt_tab)); h->mt_tab = nullptr; }
+  CU(cudaMalloc(&h->mt_tab, (size_t)rows * 624 * sizeof(uint32_t)));
+  CU(cudaMemcpy(h->mt_tab, tab_host, (size_t)rows * 624 * sizeof(uint32_t), cudaMemcpyHostToDevice));
+  if (!h->mt_state_out) CU(cudaMalloc(&h->mt_state_out, 625 * sizeof(uint32_t)));
+  h->mt_tab_rows = rows;
+  return 0;
+}
 int dmlmc_mt19937_bits(dmlmc_hier* h, uint32_t* state_dev, uint32_t* backup_dev, long long skip_before, long long count,
                        long long skip_after, uint8_t* lsb_dev) {
   ENTER(h); CHECK(state_dev && skip_before >= 0 && count >= 0 && skip_after >= 0 && (count == 0 || lsb_dev), "mt19937_bits: bad arguments");
   // ordered after everything already queued on the solver stream (the buffers may still be in use there),
-  // then asynchronous beside it on a high-priority stream: one CTA
+  // then asynchronous beside it on a high-priority stream
   CU(cudaEventRecord(h->rng_done, h->stream));
   CU(cudaStreamWaitEvent(h->rng_stream, h->rng_done, 0));
-  mt19937_bits_kernel<<<1, 256, 0, h->rng_stream>>>(state_dev, backup_dev, skip_before, count, skip_after, lsb_dev);
-  LAUNCH_CHECK(h);
+  const long long total = skip_before + count + skip_after;
+  if (h->mt_jump && h->mt_tab != nullptr && total + 1024 < (1ll << (h->mt_tab_rows - 1))) {
+    // jump-ahead: one CTA per chunk of the wanted outputs + one for the end state; chunk = a power of two (few set bits in
+    // the jump distances), about one chunk per SM
+    long long chunk = 1 << 14;
+    while (chunk * 144 < count) chunk <<= 1;
+    const int nchunk = (int)((count + chunk - 1) / chunk);
+    const size_t smem = (size_t)(MTJ_BUF + 624) * sizeof(uint32_t);
+    if (!h->mtj_attr_set) {
+      CU(cudaFuncSetAttribute(mt19937_jump_bits_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      h->mtj_attr_set = true;
+    }
+    mt19937_jump_bits_kernel<<<nchunk + 1, MTJ_THREADS, smem, h->rng_stream>>>(state_dev, h->mt_state_out, backup_dev, h->mt_tab,
+                                                                             skip_before, count, total, chunk, lsb_dev);
+    LAUNCH_CHECK(h);
+    CU(cudaMemcpyAsync(state_dev, h->mt_state_out, 625 * sizeof(uint32_t), cudaMemcpyDeviceToDevice, h->rng_stream));
+  } else {
+    mt19937_bits_kernel<<<1, 256, 0, h->rng_stream>>>(state_dev, backup_dev, skip_before, count, skip_after, lsb_dev);
+    LAUNCH_CHECK(h);
+  }
   CU(cudaEventRecord(h->rng_done, h->rng_stream));
   return 0;
 }
@@ -1709,6 +1742,7 @@ int dmlmc_set_option(dmlmc_hier* h, const char* name, double value) {
   if (h) invalidate_graphs(h);
   CHECK(h != nullptr && name != nullptr, "set_option: bad arguments");
   if (std::strcmp(name, "outer_eo") == 0) { h->outer_eo = value != 0.0; return 0; }
+  if (std::strcmp(name, "mt_jump") == 0) { h->mt_jump = value != 0.0; return 0; }
   if (std::strcmp(name, "smoother_eo") == 0) { h->smoother_eo = value != 0.0; return 0; }
   if (std::strcmp(name, "dot32") == 0) { h->dot32 = value != 0.0; return 0; }
   if (std::strcmp(name, "fuse_res") == 0) { h->fuse_res = value != 0.0; return 0; }

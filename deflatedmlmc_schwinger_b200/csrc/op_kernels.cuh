@@ -1097,6 +1097,122 @@ mt19937_bits_kernel(uint32_t* __restrict__ state, uint32_t* __restrict__ backup,
   if (tid == 0) state[624] = (uint32_t)mti;
 }
 
+// ---- the same stream with jump-ahead: many CTAs per call, none of them walks over another rank's probes ----------------
+// The MT19937 transition is linear over GF(2), so the raw word sequence X[t] obeys  X[J + w] = XOR_{i: g_i = 1} X[i + w]
+// with g(t) = t^J mod phi(t) (phi: the characteristic polynomial, degree 19937).  `tab` holds g for J = 2^b, b = 0..47
+// (deflatedmlmc_schwinger_b200/mtjump.py builds and pins it against np.random).  CTA c < gridDim.x - 1 produces the outputs
+// [c * chunk, (c + 1) * chunk) of the wanted range: it jumps from the call's start state by its own distance -- one
+// polynomial per set bit >= 10 of the distance, the low 10 bits are walked -- and then generates.  One polynomial =
+// 32 twists (20592 consecutive raw words in shared memory) + a 19937 x 624 bit-by-word convolution, one output word per
+// thread (all reads from shared memory, ~0.15 ms per CTA).  The last CTA writes the state the sequential generator would
+// leave behind (numpy's alignment: origin a multiple of 624 words from the start state's, position in [1, 624]) to
+// `state_out`, and the call's start state to `backup`.
+constexpr int MTJ_THREADS = 640;
+constexpr int MTJ_BLOCKS = 32;                       // twists per fill
+constexpr int MTJ_BUF = 624 * (MTJ_BLOCKS + 1);      // words
+constexpr int MTJ_DEG = 19937;
+
+// X[624 (r + 1) + i] for r < nb, i < 624, from X[0..623]:  X[t + 624] = X[t + 397] ^ mix(X[t], X[t + 1]), 227 words per barrier
+__device__ __forceinline__ void mtj_fill(uint32_t* __restrict__ X, int nb, int tid) {
+  for (int r = 0; r < nb; ++r) {
+    uint32_t* o = X + 624 * r;
+    if (tid < 227) o[624 + tid] = o[397 + tid] ^ mt_mix(o[tid], o[tid + 1]);
+    __syncthreads();
+    if (tid < 227) o[851 + tid] = o[624 + tid] ^ mt_mix(o[227 + tid], o[228 + tid]);
+    __syncthreads();
+    if (tid < 170) o[1078 + tid] = o[851 + tid] ^ mt_mix(o[454 + tid], o[455 + tid]);
+    __syncthreads();
+  }
+}
+// X[0..623] <- the 624 words J = 2^b positions further on (g = row b of the table)
+__device__ __forceinline__ void mtj_apply(uint32_t* __restrict__ X, uint32_t* __restrict__ P, const uint32_t* __restrict__ g, int tid) {
+  for (int i = tid; i < 624; i += MTJ_THREADS) P[i] = __ldg(g + i);
+  mtj_fill(X, MTJ_BLOCKS, tid);
+  uint32_t acc = 0;
+  if (tid < 624) {
+    for (int iw = 0; iw < 624; ++iw) {
+      const uint32_t gw = P[iw];
+      const uint32_t* xp = X + iw * 32 + tid;
+#pragma unroll
+      for (int b = 0; b < 32; ++b) acc ^= xp[b] & (0u - ((gw >> b) & 1u));
+    }
+  }
+  __syncthreads();
+  if (tid < 624) X[tid] = acc;
+  __syncthreads();
+}
+__global__ void __launch_bounds__(MTJ_THREADS)
+mt19937_jump_bits_kernel(const uint32_t* __restrict__ state, uint32_t* __restrict__ state_out, uint32_t* __restrict__ backup,
+                         const uint32_t* __restrict__ tab, long long skip_before, long long count, long long total,
+                         long long chunk, uint8_t* __restrict__ out) {
+  extern __shared__ uint32_t mtj_smem[];
+  uint32_t* X = mtj_smem;
+  uint32_t* P = mtj_smem + MTJ_BUF;
+  const int tid = threadIdx.x;
+  const int c = blockIdx.x;
+  const bool last = c == (int)gridDim.x - 1;
+  const int pos = (int)state[624];
+  for (int i = tid; i < 624; i += MTJ_THREADS) { const uint32_t v = state[i]; X[i] = v; if (last && backup) backup[i] = v; }
+  if (last && backup && tid == 0) backup[624] = (uint32_t)pos;
+  __syncthreads();
+  long long skip, q = 0, T = 0;
+  if (last) {
+    q = (long long)pos + total;
+    T = total == 0 ? 0 : 624 * ((q - 1) / 624);
+    if (T == 0) {                                   // still inside the start state's own block of 624 words
+      for (int i = tid; i < 624; i += MTJ_THREADS) state_out[i] = X[i];
+      if (tid == 0) state_out[624] = (uint32_t)q;
+      return;
+    }
+    skip = T - pos;
+  } else {
+    skip = skip_before + (long long)c * chunk;
+  }
+  // the low 31 bits of word 0 of a freshly seeded state are not part of the sequence: work on the window one word further on
+  const int base = pos >= 1 ? 1 : 0;
+  if (base) {
+    mtj_fill(X, 1, tid);
+    const uint32_t v = tid < 624 ? X[tid + 1] : 0u;
+    __syncthreads();
+    if (tid < 624) X[tid] = v;
+    __syncthreads();
+  }
+  const long long J = (long long)(pos - base) + skip;
+  const int lo = (int)(J & 1023);
+  {
+    long long hi = J >> 10;
+    for (int b = 10; hi != 0; ++b, hi >>= 1)
+      if (hi & 1) mtj_apply(X, P, tab + (size_t)b * 624, tid);
+  }
+  if (last) {
+    mtj_fill(X, 2, tid);                            // lo + 624 <= 1647 < 1872
+    for (int i = tid; i < 624; i += MTJ_THREADS) state_out[i] = X[lo + i];
+    if (tid == 0) state_out[624] = (uint32_t)(q - T);
+    return;
+  }
+  long long n_out = count - (long long)c * chunk;
+  if (n_out > chunk) n_out = chunk;
+  uint8_t* o = out + (size_t)c * chunk;
+  long long done = 0;
+  int p = lo;
+  while (done < n_out) {
+    const long long need = (long long)p + (n_out - done) - 624;          // words wanted beyond the 624 in the buffer
+    const int nb = need <= 0 ? 0 : (need >= (long long)624 * MTJ_BLOCKS ? MTJ_BLOCKS : (int)((need + 623) / 624));
+    mtj_fill(X, nb, tid);
+    const int have = 624 * (nb + 1) - p;
+    const int take = (n_out - done) < (long long)have ? (int)(n_out - done) : have;
+    for (int i = tid; i < take; i += MTJ_THREADS) o[done + i] = (uint8_t)(mt_temper(X[p + i]) & 1u);
+    done += take;
+    if (done < n_out) {                             // the newest 624 words become the front of the next pass (all of them used)
+      const uint32_t v = tid < 624 ? X[624 * nb + tid] : 0u;
+      __syncthreads();
+      if (tid < 624) X[tid] = v;
+      __syncthreads();
+      p = 624;
+    }
+  }
+}
+
 // element i of probe p = 2*lsb[p*n+i] - 1 (one byte per element, as written by mt19937_bits_kernel)
 __global__ void __launch_bounds__(256)
 probe_expand_bytes_kernel(const uint8_t* __restrict__ lsb, int n, int k, Cx<double>* __restrict__ X0) {

@@ -32,7 +32,7 @@
 extern "C" {
 #endif
 
-#define DMLMC_ABI_VERSION 4
+#define DMLMC_ABI_VERSION 5
 
 enum { DMLMC_C128 = 0, DMLMC_C64 = 1 };
 
@@ -133,6 +133,13 @@ int dmlmc_probe_expand(dmlmc_hier* h, const uint8_t* bits_dev, int n, int k, voi
  * dmlmc_probe_expand_bytes / dmlmc_rng_sync order after it. */
 int dmlmc_mt19937_bits(dmlmc_hier* h, uint32_t* state_dev, uint32_t* backup_dev, long long skip_before,
                        long long count, long long skip_after, uint8_t* lsb_dev);
+/* Jump-ahead table of that generator: tab_host[rows][624] = the polynomials t^(2^b) mod phi(t), b = 0..rows-1, packed 32
+ * coefficients per word (phi: characteristic polynomial of the MT19937 transition; mtjump.py computes the table from the
+ * generator's own output).  Once set, dmlmc_mt19937_bits runs one CTA per 2^14..-word chunk of the wanted outputs, each
+ * jumping over everything before its chunk (skip_before included: the blocks of the other ranks, stoch_trace.py:288 has one
+ * stream for all probes) instead of one CTA generating and discarding it; same outputs, same final state (option
+ * "mt_jump" = 0 restores the sequential kernel). */
+int dmlmc_set_mt_jump_table(dmlmc_hier* h, const uint32_t* tab_host, int rows);
 /* X0[i][p] = 2*lsb[p*n+i] - 1, complex128 [n][k] (utils.py:213-216) */
 int dmlmc_probe_expand_bytes(dmlmc_hier* h, const uint8_t* lsb_dev, int n, int k, void* X0);
 /* wait for the probe-stream generator (before reading its state back to the host) */

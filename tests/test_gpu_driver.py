@@ -114,6 +114,50 @@ def test_device_probe_stream_is_numpy_mt19937(mg16, consumed, skip, count, after
     assert st2[0] == 'MT19937'
 
 
+@pytest.mark.parametrize("consumed,skip,count,after", [(0, 0, 70000, 0), (7, 3 * 32768, 2 * 32768 + 5, 4 * 32768 - 5),
+                                                      (624, (1 << 24) + 12345, 40000, (1 << 20) + 3),
+                                                      (100, 5 * (1 << 21), 0, 0), (333, 0, 1 << 21, 7 * (1 << 21))])
+def test_probe_stream_jump_ahead_equals_the_sequential_generator(mg16, consumed, skip, count, after):
+    """dmlmc_mt19937_bits with the jump-ahead table (many CTAs, nobody generates the skipped words) == the sequential
+    one-CTA kernel (option mt_jump = 0): same output bits, and EXACTLY the same state words (numpy's alignment of the
+    key array and position), so the generator handed back to np.random is the one the reference would leave."""
+    import torch
+    mg, tp, A = mg16
+    dev = mg.dev
+    np.random.seed(123456)
+    if consumed:
+        np.random.randint(2, size=consumed)
+    st = np.random.get_state()
+    words = np.concatenate([np.asarray(st[1], dtype=np.uint32), np.array([st[2]], dtype=np.uint32)])
+    res = []
+    for jump in (1, 0):
+        dev.set_option("mt_jump", jump)
+        try:
+            state = torch.from_numpy(words.view(np.int32).copy()).cuda()
+            backup = torch.zeros(625, dtype=torch.int32, device="cuda")
+            out = dev.mt19937_bits(state, skip, count, after, backup=backup)
+            dev.rng_sync()
+            res.append((None if out is None else out.cpu().numpy(), state.cpu().numpy().view(np.uint32).copy(),
+                        backup.cpu().numpy().view(np.uint32).copy()))
+        finally:
+            dev.set_option("mt_jump", 1)
+    (oj, sj, bj), (os_, ss, bs) = res
+    if count:
+        assert np.array_equal(oj, os_)
+    assert np.array_equal(bj, words) and np.array_equal(bs, words)
+    total = skip + count + after
+    if total > 0 and int(words[624]) + total > 624:
+        assert np.array_equal(sj, ss), "state after the jump differs from the sequential generator's"
+    else:
+        assert sj[624] == ss[624] and np.array_equal(sj[1:624], ss[1:624])
+    # and against numpy itself on a sample of the range (the host walks the skipped words)
+    if count and skip + count <= (1 << 25):
+        sampling_skip = skip
+        while sampling_skip > 0:
+            c = min(sampling_skip, 1 << 22); np.random.bytes(4 * c); sampling_skip -= c
+        assert np.array_equal(oj, np.random.randint(2, size=count).astype(np.uint8))
+
+
 def test_device_and_host_probe_streams_give_the_same_run(g16):
     """the whole MLMC driver with the device-generated stream == with the host-generated stream, including the
     final state of the global numpy generator (the rewind of the sequential stopping rule)"""

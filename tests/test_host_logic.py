@@ -293,3 +293,26 @@ def test_geometric_blocks_of_the_estimators_level1():
     P = mgm.prolongator_csr_indexed(mgm.block_orthonormal_values(tv1, cb, nv), cb)
     assert abs((P.conj().T @ P) - sp.identity(P.shape[1])).max() < 1e-13
     assert np.linalg.norm(P @ (P.conj().T @ tv1) - tv1) < 1e-12 * np.linalg.norm(tv1)
+
+
+def test_mt19937_jump_table_is_pinned_against_numpy():
+    """mtjump: the characteristic polynomial recovered by Berlekamp-Massey has degree 19937 and 135 terms; the shipped table
+    t^(2^b) mod phi equals a fresh computation; jumping with it lands on the words np.random itself produces."""
+    from deflatedmlmc_schwinger_b200 import mtjump as mj
+    phi = mj.char_poly()
+    assert phi.bit_length() - 1 == mj.DEG and bin(phi).count("1") == 135
+    tab = mj.table()
+    p = 2
+    for b in range(14):
+        assert np.array_equal(tab[b], mj.poly_to_words(p))
+        p = mj._reduce(mj._square(p), phi)
+    rs = np.random.RandomState(123456)
+    rs.bytes(4 * 77)
+    st = rs.get_state()
+    for skip in (0, 623, 1024, 3 * 32768 + 17, (1 << 22) + 999):
+        arr, q = mj.jump_host(st[1], st[2], skip)
+        r2 = np.random.RandomState()
+        r2.set_state(st)
+        if skip:
+            r2.bytes(4 * skip)
+        assert np.array_equal(np.frombuffer(r2.bytes(4 * 600), dtype=np.uint32), mj.temper(arr[q:q + 600]))
