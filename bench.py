@@ -93,15 +93,23 @@ def _cpu_probe(seed):
     return time.time() - t, complex(e)
 
 
-def cpu_baseline_single(n_probes=2):
+def cpu_baseline_pool(min_probes=16):
+    """the in-line cpu_baseline of the GPU arm: >= 16 level-0 MLMC samples of the same workload with the oracle port of the
+    reference algorithm on all host cores (one probe per process at a time), SURVEY.md 8d"""
+    import multiprocessing as mpx
+    cores = max(1, (os.cpu_count() or 1))
+    cores = min(cores, int(os.environ.get("DMLMC_REF_CORES", cores)))
+    n_probes = cores * max(1, -(-min_probes // cores))
     _cpu_setup()
-    t = time.time()
-    for q in range(n_probes):
-        _cpu_probe(1000 + q)
-    dt = time.time() - t
-    return {"value": n_probes / dt, "unit": "probes/s", "cores": 1, "kind": "port",
-            "sample": "%d level-0 MLMC samples of the same workload (oracle port of the reference algorithm: "
-                      "pyamg-style FGMRES + V-cycle with scipy lgmres(30,3)x2 smoother, tol 1e-12), 1 thread" % n_probes}
+    with mpx.get_context("fork").Pool(cores) as pool:
+        pool.map(_cpu_probe, list(range(900, 900 + cores)))            # warm-up (page-in, scipy imports)
+        t = time.time()
+        pool.map(_cpu_probe, list(range(1000, 1000 + n_probes)), chunksize=1)
+        dt = time.time() - t
+    return {"value": n_probes / dt, "unit": "probes/s", "cores": cores, "kind": "port",
+            "sample": "%d level-0 MLMC samples of the same workload on %d processes (oracle port of the reference algorithm: "
+                      "pyamg-style FGMRES + V-cycle with scipy lgmres(30,3)x2 smoother, tol 1e-12; the Python reference itself "
+                      "cannot travel to the GPU box)" % (n_probes, cores)}
 
 
 def run_reference_arm(args):
@@ -138,6 +146,87 @@ def run_reference_arm(args):
 
 
 # ------------------------------------------------------------------------------------------------
+EXACT_DISPLACED = -8.748242701374695 + 50.215154098005584j      # /root/reference gateway.py:104
+
+
+def run_experiment(mg, A, k, world, runs=2):
+    """The reference's shipped experiment G202 (gateway.py:52-59 -> stoch_trace.mlmc: rough trace, level-0 and level-2
+    difference samples with the sequential stopping rule of stoch_trace.py:386-406 up to the variance target trace_tol = 1e-2,
+    coarsest term directly) on the solver just timed, probes from the device MT19937 stream INSIDE the timed region, the probes
+    of every round sharded over the ranks: total work is fixed, so this is the STRONG-scaling figure of the run.  The hierarchy
+    (injected test vectors) is not rebuilt.  Returns the record of the last of `runs` runs (+ the first run's time)."""
+    import torch
+    import torch.distributed as dist
+    from deflatedmlmc_schwinger_b200 import stoch_trace
+    recs = []
+    for _ in range(runs):
+        p, tp = params128()
+        tp.update({"mg_solver": mg, "probe_batch": k, "device_probe_stream": True, "sequential_stop": True})
+        torch.cuda.synchronize()
+        t0 = time.time()
+        res = stoch_trace.mlmc(A, tp)
+        torch.cuda.synchronize()
+        wall = time.time() - t0
+        ts = torch.tensor([res["sampling_seconds"], wall], device="cuda", dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(ts, op=dist.ReduceOp.MAX)
+        recs.append((res, float(ts[0].item()), float(ts[1].item())))
+    res, samp, wall = recs[-1]
+    used = [int(r["nr_ests"]) + 1 for i, r in enumerate(res["results"][:-1]) if r["nr_ests"] > 0]
+    return {"name": "G202: schwinger128.mat deflated MLMC to the reference variance target (trace_tol 1e-2, sequential stop rule, "
+                    "device probe stream, levels 0 and 2 sampled, level 1 skipped, coarsest term direct)",
+            "scaling": "strong", "n_gpus": world, "probe_batch_per_gpu": k,
+            "sampling_s": samp, "sampling_s_first_run": recs[0][1], "wall_s_without_hierarchy_setup": wall,
+            "stop_indices": [int(r["nr_ests"]) for r in res["results"]],
+            "probes_used": used, "probes_evaluated": [int(x) for x in res["probes_evaluated"]],
+            "probes_per_s": float(sum(used) / samp), "evaluated_probes_per_s": float(sum(res["probes_evaluated"]) / samp),
+            "trace": [float(np.real(res["trace"])), float(np.imag(res["trace"]))],
+            "abs_err_vs_exact": float(abs(res["trace"] - EXACT_DISPLACED)),
+            "target_err": float(abs(1e-2 * res["rough_trace"])),
+            "exact": [EXACT_DISPLACED.real, EXACT_DISPLACED.imag]}
+
+
+def spmm_sweep(mg, peak, ks=(1, 8, 32, 128, 256, 512)):
+    """BASELINE.json configs[2] ("batched multi-RHS probe sweep ... measuring SpMV/SpMM HBM roofline fraction"): Y = A_l X for
+    the estimator's levels 0 (link-form stencil), 1, 2 (padded BSR), the restriction R_0 and the prolongation P_0 on k
+    Rademacher columns, complex128, CUDA events, a 256 MB buffer overwritten between timed calls (L2 flush: below k ~ 64 the
+    operands fit in L2).  Algorithmic bytes per call as SURVEY.md 8d: level 0 n0 s (1 + 2k), level 1 n1 s (36 + 2k) + 9 n1,
+    level 2 n2 s (48 + 2k) + 3 n2, restrict n0 s (4 + 1.25 k), prolong n0 s (4 + 2.25 k), s = 16 B."""
+    import torch
+    dev = mg.dev
+    stream = torch.cuda.current_stream()
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
+    n = mg.level_shapes
+    s = 16
+
+    def timeit(fn, reps=7):
+        fn(); fn()
+        ts = []
+        for _ in range(reps):
+            flush.fill_(1)
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(stream); fn(); e1.record(stream); torch.cuda.synchronize()
+            ts.append(e0.elapsed_time(e1) * 1e3)
+        return float(np.median(ts))
+    rows = []
+    g = torch.Generator(device="cuda"); g.manual_seed(7)
+    for k in ks:
+        X0 = (torch.randint(0, 2, (n[0], k), device="cuda", generator=g).to(torch.float64) * 2 - 1).to(torch.complex128).contiguous()
+        row = {"k": k}
+        for lvl, by in ((0, n[0] * s * (1 + 2 * k)), (1, n[1] * s * (36 + 2 * k) + 9 * n[1]), (2, n[2] * s * (48 + 2 * k) + 3 * n[2])):
+            X = X0[:n[lvl]].contiguous(); Y = torch.empty_like(X)
+            us = timeit(lambda: dev.spmm(lvl, X, Y))
+            row["A%d" % lvl] = {"us": round(us, 2), "GBps": round(by / us / 1e3, 1), "frac": round(by / us / 1e3 / peak, 3)}
+        Xc = dev.restrict(0, X0)
+        us = timeit(lambda: dev.restrict(0, X0)); by = n[0] * s * (4 + 1.25 * k)
+        row["R0"] = {"us": round(us, 2), "GBps": round(by / us / 1e3, 1), "frac": round(by / us / 1e3 / peak, 3)}
+        us = timeit(lambda: dev.prolong_add(0, Xc, X0)); by = n[0] * s * (4 + 2.25 * k)
+        row["P0"] = {"us": round(us, 2), "GBps": round(by / us / 1e3, 1), "frac": round(by / us / 1e3 / peak, 3)}
+        rows.append(row)
+        del X0, Xc
+    del flush
+    return rows
+
 
 class ClockSampler(threading.Thread):
     """SM clock and throttle reasons DURING the timed region, through NVML in-process (an `nvidia-smi`
@@ -220,6 +309,7 @@ def main():
                     help="hierarchy of the V-cycle that preconditions the level-0 solve: geometric 4x4-site aggregates "
                          "(default) or the estimator's own (reference aggregation)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-experiment", action="store_true", help="skip the strong-scaling G202 run")
     ap.add_argument("--opt", action="append", default=[], metavar="NAME=VALUE", help="solver option (dmlmc_set_option), repeatable")
     args = ap.parse_args()
     if args.impl == "reference":
@@ -342,6 +432,36 @@ def main():
            "api": "dmlmc_level_sample_host (utils.defl_Hutch_batch)"}
     same = float(np.abs(e_h - es[-1].cpu().numpy()).max())
 
+    # ---- the product's default path: probes drawn by the device MT19937 stream (utils.py:255-258 is part of the reference's
+    # one_defl_Hutch_step), rank g jumping over the other ranks' blocks, estimates read back to the host every step
+    src = sampling.DeviceProbeSource(dev)
+    comm = sampling.Comm(dev.device)
+    np.random.seed(123456)
+    src.begin()
+    for s in range(min(args.warmup, 2)):
+        dev.level_sample(1, 0, 2, src.next_round(comm, n0, k), tol, restart, maxiter)[0].cpu()
+    barrier()
+    ev0.record(stream)
+    for s in range(args.steps):
+        e_s = dev.level_sample(1, 0, 2, src.next_round(comm, n0, k), tol, restart, maxiter)[0].cpu()
+    ev1.record(stream)
+    barrier()
+    src.end()
+    ms_ds = ev0.elapsed_time(ev1)
+    if world > 1:
+        t = torch.tensor([ms_ds], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms_ds = float(t.item())
+    e2e["device_stream"] = {"value": world * k * args.steps / (ms_ds * 1e-3), "unit": "probes/s", "h2d_bytes_per_step": 0,
+                            "d2h_bytes_per_step": int(16 * k + 8 * k),
+                            "api": "sampling.DeviceProbeSource + dmlmc_level_sample (the drivers' default: probe generation "
+                                   "by dmlmc_mt19937_bits with jump-ahead inside the timed region, next round's probes "
+                                   "generated beside the solve)"}
+
+    # ---- the whole experiment (strong scaling): G202 to the reference variance target ----------------------------
+    experiment = None if args.no_experiment else run_experiment(mg, A, k, world)
+    dev.ensure_workspace(0, k, restart)
+
     # ---- roofline of the dominant kernel: the level-0 fused stencil + Richardson-update step (c64) ------
     roof = None
     if rank == 0:
@@ -418,11 +538,30 @@ def main():
                 return ev0.elapsed_time(ev1) * 1e-3 / reps
 
             tp_full = time_precond()
-            pdev.set_smoother_eo(0, nue[:1], p0e)
-            tp_one = time_precond()
-            pdev.set_smoother_eo(0, nue, p0e)
-            dev.set_option("use_graphs", 1)
-            t_pair = (tp_full - tp_one) / max(me - 1, 1)
+            # the sweeps themselves, launched through dmlmc_hop_eo exactly as smooth_eo launches them (w_o = H_oe y_e, then
+            # y_e' = a y_e + b H_eo w_o with the factor's own a, b; ping-pong buffers), CUDA events around the launches
+            LXl = LTl = int(round((n0 // 2) ** 0.5))
+            cdiag = float(np.real(pmg.ml.levels[0].A.diagonal()[0]))
+            Yb = [torch.randn(2, LXl, LTl // 2, k, 2, device="cuda", dtype=torch.float32).to(torch.bfloat16).contiguous() for _ in range(2)]
+            Wb = torch.empty_like(Yb[0])
+
+            def sweeps():
+                cur = 0
+                for nu_i in nue:
+                    pdev.hop_eo(0, 1, Yb[cur], None, Wb, 1.0, 1.0, k)
+                    pdev.hop_eo(0, 0, Wb, Yb[cur], Yb[cur ^ 1], 1.0 - nu_i * cdiag, nu_i / cdiag, k)
+                    cur ^= 1
+            for _ in range(2):
+                sweeps()
+            torch.cuda.synchronize()
+            ev0.record(stream)
+            reps_h = 5
+            for _ in range(reps_h):
+                sweeps()
+            ev1.record(stream)
+            torch.cuda.synchronize()
+            t_pair = ev0.elapsed_time(ev1) * 1e-3 / (reps_h * me)
+            del Yb, Wb
             half = (n0 // 2) * k * 4                      # one BF16 half-lattice vector of k columns (4 B per complex)
             links = 4 * (n0 // 4) * 16                    # 4 pre-splatted links for each of the V/2 sites of a sweep
             # sweep 1: w_o = H_oe y_e (read 1, write 1); sweep 2: y_e' = a y_e + b H_eo w_o (read 2, write 1)
@@ -435,15 +574,20 @@ def main():
                     "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
                     "peak_source": "MEASURED_PEAKS.json hbm_gbs" if "hbm_gbs" in peaks else "fallback 6650",
                     "frac_of_nominal_8TBs": ach / 8000.0,
-                    "avg_launch_us": 1e6 * t_pair / 2, "alg_bytes_per_launch": pair_bytes / 2, "traffic": 26.3e6 * k / 256.0,
-                    "traffic_source": "ncu --set full, profiles/r1_run36_hop_eo_ncu.md (k = 256): dram__bytes_read.sum 34.6 MB (sweep with "
-                                      "In2) / 17.8 MB (sweep without) + dram__bytes_write.sum < 0.1 MB per launch, averaged over the "
-                                      "two sweeps and scaled by k / 256 to this run's batch (ncu replays each launch cold: the inputs "
-                                      "come from DRAM there, the output stays in L2)",
+                    "avg_launch_us": 1e6 * t_pair / 2, "alg_bytes_per_launch": pair_bytes / 2,
+                    "timing": "CUDA events around %d consecutive launches through dmlmc_hop_eo (the V-cycle's own launch "
+                              "configuration and coefficients)" % (2 * me * 5),
+                    "traffic": {512: 56.96e6, 256: 26.3e6}.get(k),
+                    "traffic_source": ("ncu --set full of this command at k = 512 (profiles/r2_run1_ncu_full_k512.md, 20 launches "
+                                       "each): dram__bytes_read.sum + dram__bytes_write.sum = 68.6 + 8.9 MB (sweep with In2) / 34.6 + "
+                                       "1.8 MB (sweep without), averaged over the two sweeps; k = 256: profiles/r1_run36_hop_eo_ncu.md; "
+                                       "no capture at other batch sizes (null).  ncu replays each launch cold: the inputs come from "
+                                       "DRAM there, most of the output stays in L2"),
                     "limiter": "the five %.1f MB half-lattice vectors of a Schur-complement application %s the 126 MB L2 across the "
-                               "%d consecutive sweeps; ncu (k = 256): issue slots 56-58 %%, integer ALU pipe 47-51 %% (BF16 <-> FP32 "
-                               "conversions), FMA pipe 24-26 %%, 70-72 registers, 35-39 %% of the warp slots -- instruction issue / "
-                               "L2 latency, not HBM; gram_schmidt_dot and spmm_level0 below are the HBM-streaming kernels of the step"
+                               "%d consecutive sweeps; ncu (k = 512): issue slots 58-61 %%, integer ALU pipe 51-54 %% (BF16 <-> FP32 "
+                               "conversions), FMA pipe 46-48 %%, 70-72 registers, 36-37 %% of the warp slots, L2 hit 22-30 %% -- "
+                               "instruction issue / L2 latency, not HBM; gram_schmidt_dot and spmm_level0 below are the HBM-streaming "
+                               "kernels of the step"
                                % (half / 1e6, "stay in" if 5 * half < 120e6 else "no longer all fit in", 2 * me + 2),
                     "precondition_call_us": 1e6 * tp_full, "sweeps_per_vcycle": 2 * me + 2,
                     "stencil_step_bf16_t2_kernel": {kk: t2_entry[kk] for kk in ("achieved", "frac", "avg_launch_us",
@@ -481,6 +625,7 @@ def main():
             by = n0 * sb * (1 + 2 * k)
             spmm[name] = {"us": 1e6 * tt, "GBps": by / tt / 1e9, "frac": by / tt / 1e9 / peak}
         roof["spmm_level0"] = spmm
+        roof["spmm_sweep_c128"] = spmm_sweep(mg, peak)
         # the tensor-core kernel of the path: dense coarse solve of the V-cycle (tcgen05, BF16 x BF16 -> FP32),
         # real GEMM [2n x 2n] x [2n x k]; timed through dmlmc_vcycle on the dense level (includes the RHS pack kernel)
         dl = pmg.dense_level
@@ -521,10 +666,12 @@ def main():
             "fgmres_iters": {"level0": [int(iters[0].min()), int(iters[0].max())],
                              "level2": [int(iters[1].min()), int(iters[1].max())]},
             "setup_s": setup_s, "e2e_vs_device_max_abs_diff": same}
+    if experiment is not None:
+        line["experiment"] = experiment
     if roof is not None:
         line["roofline"] = roof
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        line["cpu_baseline"] = cpu_baseline_single(2)
+        line["cpu_baseline"] = cpu_baseline_pool(16)
     if rank == 0:
         print(json.dumps(line), flush=True)
     if world > 1:

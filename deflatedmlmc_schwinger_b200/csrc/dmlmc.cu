@@ -113,6 +113,7 @@ struct dmlmc_hier {
   char* ws = nullptr; size_t ws_bytes = 0, ws_off = 0;
   int* h_nactive = nullptr;        // pinned
   cudaStream_t rng_stream = nullptr; cudaEvent_t rng_done = nullptr;   // the probe stream runs beside the solver
+  cudaStream_t rng_stream_lo = nullptr; cudaEvent_t rng_order = nullptr; // (jump-ahead kernel: many CTAs, no priority over the solver)
   uint32_t* mt_tab = nullptr; int mt_tab_rows = 0;    // jump polynomials t^(2^b) mod phi (dmlmc_set_mt_jump_table)
   uint32_t* mt_state_out = nullptr;                   // [625] state written by the jump kernel, copied over the caller's afterwards
   int mt_jump = 1;                                    // option: 0 = the sequential one-CTA generator
@@ -1324,6 +1325,8 @@ int dmlmc_hier_create(int device, void* cuda_stream, int n_levels, dmlmc_hier** 
   cudaDeviceGetStreamPriorityRange(&lo, &hi);
   if (cudaStreamCreateWithFlags(&h->cap_stream, cudaStreamNonBlocking) != cudaSuccess ||
       cudaStreamCreateWithPriority(&h->rng_stream, cudaStreamNonBlocking, hi) != cudaSuccess ||
+      cudaStreamCreateWithPriority(&h->rng_stream_lo, cudaStreamNonBlocking, lo) != cudaSuccess ||
+      cudaEventCreateWithFlags(&h->rng_order, cudaEventDisableTiming) != cudaSuccess ||
       cudaEventCreateWithFlags(&h->rng_done, cudaEventDisableTiming) != cudaSuccess) {
     delete h; return fail(-3, "dmlmc: cannot create the probe-stream CUDA stream");
   }
@@ -1339,6 +1342,8 @@ int dmlmc_hier_destroy(dmlmc_hier* h) {
   for (void* p : h->owned) cudaFree(p);
   if (h->h_nactive) cudaFreeHost(h->h_nactive);
   if (h->rng_stream) { cudaStreamSynchronize(h->rng_stream); cudaStreamDestroy(h->rng_stream); }
+  if (h->rng_stream_lo) { cudaStreamSynchronize(h->rng_stream_lo); cudaStreamDestroy(h->rng_stream_lo); }
+  if (h->rng_order) cudaEventDestroy(h->rng_order);
   if (h->mt_tab) cudaFree(h->mt_tab);
   if (h->mt_state_out) cudaFree(h->mt_state_out);
   if (h->rng_done) cudaEventDestroy(h->rng_done);
@@ -1619,14 +1624,18 @@ int dmlmc_set_mt_jump_table(dmlmc_hier* h, const uint32_t* tab_host, int rows) {
 int dmlmc_mt19937_bits(dmlmc_hier* h, uint32_t* state_dev, uint32_t* backup_dev, long long skip_before, long long count,
                        long long skip_after, uint8_t* lsb_dev) {
   ENTER(h); CHECK(state_dev && skip_before >= 0 && count >= 0 && skip_after >= 0 && (count == 0 || lsb_dev), "mt19937_bits: bad arguments");
-  // ordered after everything already queued on the solver stream (the buffers may still be in use there),
-  // then asynchronous beside it on a high-priority stream
-  CU(cudaEventRecord(h->rng_done, h->stream));
-  CU(cudaStreamWaitEvent(h->rng_stream, h->rng_done, 0));
+  // ordered after everything already queued on the solver stream (the buffers may still be in use there) and after the
+  // previous generator call, then asynchronous beside the solver: the one-CTA sequential kernel on a high-priority stream
+  // (it is the critical path of the next round), the jump-ahead kernel (~130 CTAs for ~2 ms) without priority over the solver
   const long long total = skip_before + count + skip_after;
-  if (h->mt_jump && h->mt_tab != nullptr && total + 1024 < (1ll << (h->mt_tab_rows - 1))) {
-    // jump-ahead: one CTA per chunk of the wanted outputs + one for the end state; chunk = a power of two (few set bits in
-    // the jump distances), about one chunk per SM
+  const bool jump = h->mt_jump && h->mt_tab != nullptr && total + 1024 < (1ll << (h->mt_tab_rows - 1));
+  cudaStream_t rs = jump ? h->rng_stream_lo : h->rng_stream;
+  CU(cudaEventRecord(h->rng_order, h->stream));
+  CU(cudaStreamWaitEvent(rs, h->rng_order, 0));
+  CU(cudaStreamWaitEvent(rs, h->rng_done, 0));
+  if (jump) {
+    // one CTA per chunk of the wanted outputs + one for the end state; chunk = a power of two (few set bits in the jump
+    // distances), about one chunk per SM
     long long chunk = 1 << 14;
     while (chunk * 144 < count) chunk <<= 1;
     const int nchunk = (int)((count + chunk - 1) / chunk);
@@ -1635,15 +1644,15 @@ int dmlmc_mt19937_bits(dmlmc_hier* h, uint32_t* state_dev, uint32_t* backup_dev,
       CU(cudaFuncSetAttribute(mt19937_jump_bits_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
       h->mtj_attr_set = true;
     }
-    mt19937_jump_bits_kernel<<<nchunk + 1, MTJ_THREADS, smem, h->rng_stream>>>(state_dev, h->mt_state_out, backup_dev, h->mt_tab,
-                                                                             skip_before, count, total, chunk, lsb_dev);
+    mt19937_jump_bits_kernel<<<nchunk + 1, MTJ_THREADS, smem, rs>>>(state_dev, h->mt_state_out, backup_dev, h->mt_tab,
+                                                                   skip_before, count, total, chunk, lsb_dev);
     LAUNCH_CHECK(h);
-    CU(cudaMemcpyAsync(state_dev, h->mt_state_out, 625 * sizeof(uint32_t), cudaMemcpyDeviceToDevice, h->rng_stream));
+    CU(cudaMemcpyAsync(state_dev, h->mt_state_out, 625 * sizeof(uint32_t), cudaMemcpyDeviceToDevice, rs));
   } else {
-    mt19937_bits_kernel<<<1, 256, 0, h->rng_stream>>>(state_dev, backup_dev, skip_before, count, skip_after, lsb_dev);
+    mt19937_bits_kernel<<<1, 256, 0, rs>>>(state_dev, backup_dev, skip_before, count, skip_after, lsb_dev);
     LAUNCH_CHECK(h);
   }
-  CU(cudaEventRecord(h->rng_done, h->rng_stream));
+  CU(cudaEventRecord(h->rng_done, rs));
   return 0;
 }
 int dmlmc_probe_expand_bytes(dmlmc_hier* h, const uint8_t* lsb_dev, int n, int k, void* X0) {
@@ -1657,6 +1666,7 @@ int dmlmc_probe_expand_bytes(dmlmc_hier* h, const uint8_t* lsb_dev, int n, int k
 int dmlmc_rng_sync(dmlmc_hier* h) {
   ENTER(h);
   CU(cudaStreamSynchronize(h->rng_stream));
+  CU(cudaStreamSynchronize(h->rng_stream_lo));
   return 0;
 }
 int dmlmc_hop_eo(dmlmc_hier* h, int level, int parity, const void* in_q, const void* in2, void* out_p,

@@ -1124,21 +1124,32 @@ __device__ __forceinline__ void mtj_fill(uint32_t* __restrict__ X, int nb, int t
     __syncthreads();
   }
 }
-// X[0..623] <- the 624 words J = 2^b positions further on (g = row b of the table)
+// X[0..623] <- the 624 words J = 2^b positions further on (g = row b of the table).  Two output words per thread (one 64-bit
+// shared-memory load serves two polynomial bits), the 19937 coefficients split between the two halves of the CTA; the
+// coefficient word is warp-uniform, so a zero bit costs a not-taken branch only.
 __device__ __forceinline__ void mtj_apply(uint32_t* __restrict__ X, uint32_t* __restrict__ P, const uint32_t* __restrict__ g, int tid) {
   for (int i = tid; i < 624; i += MTJ_THREADS) P[i] = __ldg(g + i);
   mtj_fill(X, MTJ_BLOCKS, tid);
-  uint32_t acc = 0;
-  if (tid < 624) {
-    for (int iw = 0; iw < 624; ++iw) {
+  const int grp = tid / 320, t = tid - grp * 320;
+  uint32_t a0 = 0, a1 = 0;
+  if (t < 312) {
+    for (int iw = grp * 312; iw < (grp + 1) * 312; ++iw) {
       const uint32_t gw = P[iw];
-      const uint32_t* xp = X + iw * 32 + tid;
+      const uint2* xp = reinterpret_cast<const uint2*>(X + iw * 32 + 2 * t);
+      uint2 cur = xp[0];
 #pragma unroll
-      for (int b = 0; b < 32; ++b) acc ^= xp[b] & (0u - ((gw >> b) & 1u));
+      for (int b = 0; b < 32; b += 2) {
+        const uint2 nxt = xp[b / 2 + 1];
+        if (gw & (1u << b)) { a0 ^= cur.x; a1 ^= cur.y; }
+        if (gw & (2u << b)) { a0 ^= cur.y; a1 ^= nxt.x; }
+        cur = nxt;
+      }
     }
   }
   __syncthreads();
-  if (tid < 624) X[tid] = acc;
+  if (grp == 1 && t < 312) { P[2 * t] = a0; P[2 * t + 1] = a1; }
+  __syncthreads();
+  if (grp == 0 && t < 312) { X[2 * t] = a0 ^ P[2 * t]; X[2 * t + 1] = a1 ^ P[2 * t + 1]; }
   __syncthreads();
 }
 __global__ void __launch_bounds__(MTJ_THREADS)

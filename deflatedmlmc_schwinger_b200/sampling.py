@@ -95,10 +95,9 @@ def first_stop_index(ests, start, tol, min_index=5):
     err = np.sqrt(var / idx)
     lo = max(start, min_index)
     # a generous band around the threshold, then exact confirmation in order
-    for j in range(lo, n):
-        if err[j] < tol * (1.0 + 1e-9) + 1e-300:
-            if reference_stats(ests, j)[2] < tol:
-                return j
+    for j in lo + np.nonzero(err[lo:] < tol * (1.0 + 1e-9) + 1e-300)[0]:
+        if reference_stats(ests, int(j))[2] < tol:
+            return int(j)
     return None
 
 

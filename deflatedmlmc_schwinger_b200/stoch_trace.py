@@ -22,20 +22,26 @@ def _say(params, *a, **kw):
 
 
 def _make_solver(A, params):
-    mg_solver = MG(A, smoother_degree=params.get('smoother_degree', 80), restart=params.get('fgmres_restart', 40),
-                   inner_precision=params.get('inner_precision', 'c64'), pre_smooth=params.get('pre_smooth', False),
-                   geometric_precond=params.get('geometric_precond', True), precond_degree=params.get('precond_degree', 36))
+    """params['mg_solver'] (not in the reference): a hierarchy that is already set up for A (bench.py times the sampling of
+    the whole experiment on the solver it has just timed); otherwise MG(...).setup(...) as stoch_trace.py:55-75."""
+    mg_solver = params.get('mg_solver')
+    prebuilt = mg_solver is not None
+    if not prebuilt:
+        mg_solver = MG(A, smoother_degree=params.get('smoother_degree', 80), restart=params.get('fgmres_restart', 40),
+                       inner_precision=params.get('inner_precision', 'c64'), pre_smooth=params.get('pre_smooth', False),
+                       geometric_precond=params.get('geometric_precond', True), precond_degree=params.get('precond_degree', 36))
     mg_solver.coarsest_iters = 0
     mg_solver.coarsest_iters_tot = 0
     mg_solver.coarsest_iters_avg = 0
     mg_solver.nr_calls = 0
-    _say(params, "MG setup phase ...", end='', flush=True)
-    start = time.time()
-    mg_solver.setup(dof=params['dof'], aggrs=params['aggrs'], max_levels=params['max_nr_levels'], dim=2,
-                    acc_eigvs=params['accuracy_mg_eigvs'], sys_type=params['problem_name'], params=params)
-    end = time.time()
-    _say(params, " done. Time : " + str(end - start) + " seconds")
-    _say(params, mg_solver)
+    if not prebuilt:
+        _say(params, "MG setup phase ...", end='', flush=True)
+        start = time.time()
+        mg_solver.setup(dof=params['dof'], aggrs=params['aggrs'], max_levels=params['max_nr_levels'], dim=2,
+                        acc_eigvs=params['accuracy_mg_eigvs'], sys_type=params['problem_name'], params=params)
+        end = time.time()
+        _say(params, " done. Time : " + str(end - start) + " seconds")
+        _say(params, mg_solver)
     nr_levels = len(mg_solver.ml.levels)
     mg_solver.total_levels = nr_levels
     if nr_levels < 3:

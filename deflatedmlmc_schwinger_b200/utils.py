@@ -58,7 +58,8 @@ def print_post_results(A, params, result, example):
 
 # ---- utils.py:73-125 ------------------------------------------------------------------------------
 _B200_KEYS = ('probe_batch', 'smoother_degree', 'fgmres_restart', 'inner_precision', 'test_vectors',
-              'deflation_eigpairs', 'mlmc_deflation_eigpairs', 'verbose', 'sequential_stop', 'device_probe_stream', 'pre_smooth')
+              'deflation_eigpairs', 'mlmc_deflation_eigpairs', 'verbose', 'sequential_stop', 'device_probe_stream', 'pre_smooth',
+              'mg_solver', 'geometric_precond', 'precond_degree')
 
 
 def trace_params_from_params(params, example):
