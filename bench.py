@@ -54,6 +54,7 @@ def build_solver(precond="geometric", degree=0, options=()):
     p, tp = params128()
     A = matrix.loadMatrix(p["matrix"], p["matrix_params"])
     geo = precond == "geometric"
+    tp["skip_unused_inverses"] = True
     if degree <= 0:
         degree = 36 if geo else 80
     mg = multigrid.MG(A, smoother_degree=80, precond_degree=degree, geometric_precond=True) if geo else \
@@ -100,21 +101,84 @@ def cpu_baseline_pool(min_probes=16):
     cores = max(1, (os.cpu_count() or 1))
     cores = min(cores, int(os.environ.get("DMLMC_REF_CORES", cores)))
     n_probes = cores * max(1, -(-min_probes // cores))
-    _cpu_setup()
+    real = _ref_available() and not os.environ.get("DMLMC_REF_PORT")
+    if real:
+        try:
+            _ref_setup()
+        except Exception as why:
+            print("[bench] reference set-up failed (%s); timing the oracle port instead" % why, file=sys.stderr, flush=True)
+            real = False
+    if not real:
+        _cpu_setup()
+    probe = _ref_probe if real else _cpu_probe
     with mpx.get_context("fork").Pool(cores) as pool:
-        pool.map(_cpu_probe, list(range(900, 900 + cores)))            # warm-up (page-in, scipy imports)
+        pool.map(probe, list(range(900, 900 + cores)))            # warm-up (page-in, scipy imports)
         t = time.time()
-        pool.map(_cpu_probe, list(range(1000, 1000 + n_probes)), chunksize=1)
+        pool.map(probe, list(range(1000, 1000 + n_probes)), chunksize=1)
         dt = time.time() - t
-    return {"value": n_probes / dt, "unit": "probes/s", "cores": cores, "kind": "port",
-            "sample": "%d level-0 MLMC samples of the same workload on %d processes (oracle port of the reference algorithm: "
-                      "pyamg-style FGMRES + V-cycle with scipy lgmres(30,3)x2 smoother, tol 1e-12; the Python reference itself "
-                      "cannot travel to the GPU box)" % (n_probes, cores)}
+    what = ("the unmodified reference from oracle/_ref (multigrid.MG.setup + utils.one_defl_Hutch_step: pyamg-style FGMRES + "
+            "V-cycle with scipy lgmres smoother, tol 1e-12; golden test vectors replayed into its eigs calls)" if real else
+            "oracle port of the reference algorithm (oracle/_ref did not travel)")
+    return {"value": n_probes / dt, "unit": "probes/s", "cores": cores, "kind": "reference" if real else "port",
+            "sample": "%d level-0 MLMC samples of the same workload on %d processes: %s" % (n_probes, cores, what)}
+
+
+_REF = {}
+
+
+def _ref_available():
+    try:
+        from oracle import ref_shim
+        return ref_shim.reference_available()
+    except Exception:
+        return False
+
+
+def _ref_setup():
+    """The UNMODIFIED reference (oracle/_ref, a byte-for-byte copy made by oracle/vendor_reference.py; loaded through
+    oracle/ref_shim.py): MG(A).setup(...) of gateway.set_params('schwinger128') with the golden test vectors replayed into its
+    eigs calls (same hierarchy as the GPU arm and the golden fixtures; skips minutes of ARPACK)."""
+    if "mg" not in _REF:
+        import contextlib, io
+        from scipy.sparse import csr_matrix
+        from oracle import ref_shim
+        tv = golden_tvs()
+        rec = ref_shim.EigRecorder(replay=[("eigs", np.zeros(t.shape[1]), t) for t in tv])
+        ref = ref_shim.load_reference(rec)
+        p = ref_shim.params_128()
+        with ref_shim.in_reference_dir():
+            A = ref["matrix"].loadMatrix(p["matrix"], p["matrix_params"])
+        tp = ref["utils"].trace_params_from_params(p, "mlmc")
+        mg = ref["multigrid"].MG(A)
+        with contextlib.redirect_stdout(io.StringIO()):
+            mg.setup(dof=tp["dof"], aggrs=tp["aggrs"], max_levels=tp["max_nr_levels"], dim=2, acc_eigvs=tp["accuracy_mg_eigvs"],
+                     sys_type="schwinger", params=tp)
+        mg.total_levels = len(mg.ml.levels)
+        for i in range(mg.total_levels - 1):                       # stoch_trace.py:262-264
+            mg.ml.levels[i].P = csr_matrix(mg.ml.levels[i].P)
+            mg.ml.levels[i].R = csr_matrix(mg.ml.levels[i].R)
+        mg.skip_level = True
+        _REF.update({"ref": ref, "mg": mg, "tp": tp})
+    return _REF["ref"], _REF["mg"], _REF["tp"]
+
+
+def _ref_probe(seed):
+    """one level-0 MLMC sample by the reference's own utils.one_defl_Hutch_step (utils.py:207-361), probe drawn inside"""
+    import contextlib, io
+    ref, mg, tp = _ref_setup()
+    lv = mg.ml.levels
+    out = {"results": [{"function_iters": 0} for _ in range(len(lv))]}
+    np.random.seed(seed)
+    t = time.time()
+    with contextlib.redirect_stdout(io.StringIO()):
+        e, _ = ref["utils"].one_defl_Hutch_step(lv[0].A, lv[2].A, mg, tp, "mlmc", 0, None, None, 0, out,
+                                                lv[0].P, lv[0].R, lv[1].P, lv[1].R)
+    return time.time() - t, complex(e)
 
 
 def run_reference_arm(args):
-    """--impl reference: the reference algorithm (oracle port; the Python reference itself is not
-    present on the GPU box) on all host cores, one probe per core per step."""
+    """--impl reference: the reference's own CPU implementation of the path on all host cores, one probe per core per step:
+    the unmodified reference from oracle/_ref when it travelled with the snapshot (kind "reference"), else the oracle port."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
@@ -122,24 +186,34 @@ def run_reference_arm(args):
     cores = max(1, (os.cpu_count() or 1))
     cores = min(cores, int(os.environ.get("DMLMC_REF_CORES", cores)))
     ctx = mpx.get_context("fork")
-    _cpu_setup()
+    real = _ref_available() and not os.environ.get("DMLMC_REF_PORT")
+    if real:
+        try:
+            _ref_setup()
+        except Exception as why:                 # e.g. not enough host memory for the reference's dense prolongator
+            print("[bench] reference set-up failed (%s); timing the oracle port instead" % why, file=sys.stderr, flush=True)
+            real = False
+    if not real:
+        _cpu_setup()
+    probe = _ref_probe if real else _cpu_probe
     with ctx.Pool(cores) as pool:
         step = 0
         for _ in range(args.warmup):
-            pool.map(_cpu_probe, [step * cores + c for c in range(cores)]); step += 1
+            pool.map(probe, [step * cores + c for c in range(cores)]); step += 1
         t = time.time()
         for _ in range(args.steps):
-            pool.map(_cpu_probe, [step * cores + c for c in range(cores)]); step += 1
+            pool.map(probe, [step * cores + c for c in range(cores)]); step += 1
         dt = time.time() - t
     value = args.steps * cores / dt
+    what = ("the unmodified reference (oracle/_ref: multigrid.MG.setup + utils.one_defl_Hutch_step, golden test vectors replayed "
+            "into its eigs calls)" if real else "oracle port of the reference algorithm (oracle/_ref did not travel)")
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": "probes/s", "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "c128",
             "data": "schwinger128 gauge field (reference input) + MT19937 Rademacher probes",
             "config": {"workload": WORKLOAD, "probes_per_step": cores},
-            "cpu_baseline": {"value": value, "unit": "probes/s", "cores": cores, "kind": "port",
-                             "sample": "%d level-0 MLMC samples per step, one per core (oracle port of the reference "
-                                       "algorithm; the Python reference cannot travel to the GPU box)" % cores},
+            "cpu_baseline": {"value": value, "unit": "probes/s", "cores": cores, "kind": "reference" if real else "port",
+                             "sample": "%d level-0 MLMC samples per step, one per core: %s" % (cores, what)},
             "e2e": {"value": value, "unit": "probes/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
     print(json.dumps(line), flush=True)

@@ -34,6 +34,7 @@ _SIGS = {
     "dmlmc_set_coarsest_inverse": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p]),
     "dmlmc_set_dense_inverse": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_void_p]),
     "dmlmc_set_dense_inverse_device": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_void_p]),
+    "dmlmc_set_dense_inverse_device_full": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_void_p]),
     "dmlmc_set_smoother": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_void_p,
                                           ctypes.c_double, ctypes.c_double]),
     "dmlmc_set_smoother_eo": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_void_p,
@@ -194,10 +195,13 @@ class Hierarchy:
         minv, p = _host_c128(minv)
         _check(self.lib.dmlmc_set_dense_inverse(self.h, level, minv.shape[0], p))
 
-    def set_dense_inverse_device(self, level, minv_dev):
-        """minv_dev: torch complex128 CUDA tensor [n, n] (row-major inverse)"""
+    def set_dense_inverse_device(self, level, minv_dev, full=False):
+        """minv_dev: torch complex128 CUDA tensor [n, n] (row-major inverse); full: keep it in all precisions (else only as
+        the BF16 tensor-core operand of the complex64 V-cycle)"""
         assert minv_dev.is_cuda and minv_dev.is_contiguous() and minv_dev.dtype == self.torch.complex128
-        _check(self.lib.dmlmc_set_dense_inverse_device(self.h, level, minv_dev.shape[0], ctypes.c_void_p(minv_dev.data_ptr())))
+        fn = self.lib.dmlmc_set_dense_inverse_device_full if full else self.lib.dmlmc_set_dense_inverse_device
+        _check(fn(self.h, level, minv_dev.shape[0], ctypes.c_void_p(minv_dev.data_ptr())))
+        self.sizes[level] = minv_dev.shape[0]
         self.torch.cuda.current_stream(self.device).synchronize()
 
     def set_smoother(self, level, nu, p0, storage16=True):

@@ -117,6 +117,8 @@ struct dmlmc_hier {
   uint32_t* mt_tab = nullptr; int mt_tab_rows = 0;    // jump polynomials t^(2^b) mod phi (dmlmc_set_mt_jump_table)
   uint32_t* mt_state_out = nullptr;                   // [625] state written by the jump kernel, copied over the caller's afterwards
   int mt_jump = 1;                                    // option: 0 = the sequential one-CTA generator
+  int smoother_only = 0;                              // option "precond_smoother_only": M^{-1} = the level's smoother polynomial
+                                                      // (the bootstrap solver of the set-up phase, before a hierarchy exists)
   bool mtj_attr_set = false;
   cudaStream_t cap_stream = nullptr;                                   // capture stream of the V-cycle graphs
   long long launches = 0;
@@ -838,7 +840,10 @@ void invalidate_graphs(dmlmc_hier* h) {
   h->graphs.clear();
 }
 
+template <typename T> int smooth_chunked(dmlmc_hier* h, int level, const Cx<T>* R, Cx<T>* E, int k);
+
 int precond_eager(dmlmc_hier* h, int level, const Z* V, Z* Zout, int k, const Cx<float>* V32) {
+  if (h->smoother_only) return smooth_chunked<double>(h, level, V, Zout, k);
   if (dmlmc_hier* hp = h->prec_hier[level]) {
     // the preconditioner hierarchy works on the caller's stream (the capture stream while a graph is recorded)
     // and in the caller's work space
@@ -1046,7 +1051,7 @@ int launch_hop_z(dmlmc_hier* h, const Level& L, int p, const Z* Inq, const Z* In
   return 0;
 }
 bool outer_eo_ok(dmlmc_hier* h, int level, int k) {
-  if (!h->outer_eo || !h->fuse_io) return false;
+  if (!h->outer_eo || !h->fuse_io || h->smoother_only) return false;
   Level& L = h->lv[level];
   if (L.kind != 0 || (L.LT % 2) || (L.LX % 2) || L.d.diag.im != 0.0) return false;
   dmlmc_hier* hv = h->prec_hier[level] ? h->prec_hier[level] : h;
@@ -1490,6 +1495,28 @@ int dmlmc_set_dense_inverse_device(dmlmc_hier* h, int level, int n, const void* 
   return 0;
 }
 
+int dmlmc_set_dense_inverse_device_full(dmlmc_hier* h, int level, int n, const void* minv_dev) {
+  if (h) invalidate_graphs(h);
+  CHECK(h && level >= 0 && level < h->n_levels && n > 0 && minv_dev, "set_dense_inverse_device_full: bad arguments");
+  CU(cudaSetDevice(h->device));
+  Level& L = h->lv[level];
+  CHECK(L.n == 0 || L.n == n, "set_dense_inverse_device_full: size does not match the level");
+  L.n = n;
+  const size_t cnt = (size_t)n * n;
+  Cx<double>* md = nullptr; Cx<float>* mf = nullptr; float4* m4 = nullptr;
+  CU(cudaMalloc(&md, cnt * sizeof(Cx<double>))); h->owned.push_back(md);
+  CU(cudaMalloc(&mf, cnt * sizeof(Cx<float>))); h->owned.push_back(mf);
+  CU(cudaMalloc(&m4, cnt * sizeof(float4))); h->owned.push_back(m4);
+  CU(cudaMemcpyAsync(md, minv_dev, cnt * sizeof(Cx<double>), cudaMemcpyDeviceToDevice, h->stream));
+  dense_formats_kernel<<<nblocks(cnt, 256), 256, 0, h->stream>>>(md, cnt, mf, m4); LAUNCH_CHECK(h);
+  L.minv_d = md; L.minv_f = mf; L.minv4 = m4;
+  L.has_dense = true;
+  if (n >= 256 && n % 8 == 0) RET(build_umma_operand(h, level, L.minv_d));
+  if (n >= 1024 && n <= 4096 && n % 8 == 0) RET(build_umma_split_operand(h, level, L.minv_d));
+  CU(cudaStreamSynchronize(h->stream));
+  return 0;
+}
+
 int dmlmc_set_coarsest_inverse(dmlmc_hier* h, int n, const double* minv_host) {
   CHECK(h != nullptr, "NULL handle");
   return dmlmc_set_dense_inverse(h, h->n_levels - 1, n, minv_host);
@@ -1635,9 +1662,11 @@ int dmlmc_mt19937_bits(dmlmc_hier* h, uint32_t* state_dev, uint32_t* backup_dev,
   CU(cudaStreamWaitEvent(rs, h->rng_done, 0));
   if (jump) {
     // one CTA per chunk of the wanted outputs + one for the end state; chunk = a power of two (few set bits in the jump
-    // distances), about one chunk per SM
+    // distances).  At most 32 chunks: the kernel shares the GPU with the solve of the previous round and is issue-bound like
+    // the solver's own kernels, so what matters is its total work (one polynomial per set bit of every CTA's distance:
+    // ~80 applications with 32 chunks against ~450 with 128; measured 2.5 ms -> 0.x ms lost per round), not its latency
     long long chunk = 1 << 14;
-    while (chunk * 144 < count) chunk <<= 1;
+    while (chunk * 32 < count) chunk <<= 1;
     const int nchunk = (int)((count + chunk - 1) / chunk);
     const size_t smem = (size_t)(MTJ_BUF + 624) * sizeof(uint32_t);
     if (!h->mtj_attr_set) {
@@ -1753,6 +1782,7 @@ int dmlmc_set_option(dmlmc_hier* h, const char* name, double value) {
   CHECK(h != nullptr && name != nullptr, "set_option: bad arguments");
   if (std::strcmp(name, "outer_eo") == 0) { h->outer_eo = value != 0.0; return 0; }
   if (std::strcmp(name, "mt_jump") == 0) { h->mt_jump = value != 0.0; return 0; }
+  if (std::strcmp(name, "precond_smoother_only") == 0) { h->smoother_only = value != 0.0; return 0; }
   if (std::strcmp(name, "smoother_eo") == 0) { h->smoother_eo = value != 0.0; return 0; }
   if (std::strcmp(name, "dot32") == 0) { h->dot32 = value != 0.0; return 0; }
   if (std::strcmp(name, "fuse_res") == 0) { h->fuse_res = value != 0.0; return 0; }

@@ -1249,6 +1249,17 @@ cvt_cols_kernel(const Cx<Tin>* __restrict__ in, size_t ld_in, Cx<Tout>* __restri
   out[r * ld_out + c] = cx<Tout>((Tout)v.re, (Tout)v.im);
 }
 
+// the complex64 and the splatted (re, re, im, im) copies of a complex128 dense inverse (dmlmc_set_dense_inverse_device_full)
+__global__ void __launch_bounds__(256) dense_formats_kernel(const Cx<double>* __restrict__ M, size_t count, Cx<float>* __restrict__ F,
+                                                            float4* __restrict__ F4) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= count) return;
+  const Cx<double> m = M[i];
+  const float mr = (float)m.re, mi = (float)m.im;
+  F[i] = cx<float>(mr, mi);
+  F4[i] = make_float4(mr, mr, mi, mi);
+}
+
 // Y = c X (elementwise) / Y += c X
 template <typename T, int ACC>
 __global__ void __launch_bounds__(256) scale_kernel(Cx<T> c, const Cx<T>* __restrict__ X, Cx<T>* __restrict__ Y, size_t count) {

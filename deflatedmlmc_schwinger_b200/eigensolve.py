@@ -49,9 +49,11 @@ def _sort_smallest(theta, rel=1e-5):
     return np.array(out)
 
 
-def smallest_eigenpairs(apply_A, apply_Ainv, X0, k, tol=1e-9, max_blocks=10, max_restarts=12, verbose=False):
-    """X0: torch [n, p] start block (p >= k; extra columns are guard vectors).  Returns (theta[k] numpy complex,
-    X [n, k] torch with unit columns, residuals[k], info)."""
+def smallest_eigenpairs(apply_A, apply_Ainv, X0, k, tol=1e-9, max_blocks=10, max_restarts=12, min_blocks=1, verbose=False):
+    """X0: torch [n, p] start block (p >= k; extra columns are guard vectors).  min_blocks: block steps taken before the
+    convergence test (a warm start from an invariant subspace passes it at once; a few steps let the guard vectors
+    show whether a smaller eigenvalue exists).  Returns (theta[k] numpy complex, X [n, k] torch with unit columns,
+    residuals[k], info)."""
     import torch
     p = X0.shape[1]
     assert p >= k
@@ -83,7 +85,7 @@ def smallest_eigenpairs(apply_A, apply_Ainv, X0, k, tol=1e-9, max_blocks=10, max
             est = np.array([np.linalg.norm(Hh[m * p:, (m - 1) * p:] @ S[(m - 1) * p:, i]) * abs(theta[i]) for i in order[:k]])
             if verbose:
                 print("  restart %d block %d: theta %s est %s" % (restart, m, np.round(theta[order[:k]], 8), est), flush=True)
-            if est.max() < tol or m == max_blocks:
+            if (est.max() < tol and m >= min_blocks) or m == max_blocks:
                 Vall = torch.cat(V[:m], dim=1)
                 Sx = torch.from_numpy(np.ascontiguousarray(S[:, order])).to(Vall.dtype).to(Vall.device)
                 X = Vall @ Sx

@@ -201,6 +201,10 @@ def harmonic_ritz_inv_roots(A, degree, seed=7):
         H[j + 1, j] = np.linalg.norm(w)
         V[j + 1] = w / H[j + 1, j]
         Vc[j + 1] = np.conj(V[j + 1])
+    return _harmonic_ritz_from_hessenberg(H, degree)
+
+
+def _harmonic_ritz_from_hessenberg(H, degree):
     Hm = H[:degree, :degree]
     em = np.zeros(degree)
     em[-1] = 1.0
@@ -208,6 +212,30 @@ def harmonic_ritz_inv_roots(A, degree, seed=7):
     theta = np.linalg.eigvals(Hm + (abs(H[degree, degree - 1]) ** 2) * np.outer(f, em))
     out = leja_order(theta)
     return 1.0 / np.array(out, dtype=np.complex128)
+
+
+def harmonic_ritz_inv_roots_device(apply, n, degree, device, seed=7):
+    """The same Arnoldi run with the operator applied on the device (`apply`: torch complex128 [n, 1] -> [n, 1], the level's
+    SpMM kernel) and the basis kept there; the start vector is the host version's, so both give the same polynomial up to
+    rounding.  The (degree + 1) x degree Hessenberg matrix comes back once at the end."""
+    import torch
+    degree = int(min(degree, n - 1))
+    rs = np.random.RandomState(seed)
+    b = rs.standard_normal(n) + 1j * rs.standard_normal(n)
+    b /= np.linalg.norm(b)
+    V = torch.zeros((degree + 1, n), dtype=torch.complex128, device=device)
+    H = torch.zeros((degree + 1, degree), dtype=torch.complex128, device=device)
+    V[0] = torch.from_numpy(b).to(device)
+    for j in range(degree):
+        w = apply(V[j].reshape(n, 1)).reshape(n)
+        for _ in range(2):
+            hh = V[:j + 1].conj() @ w
+            H[:j + 1, j] += hh
+            w = w - hh @ V[:j + 1]
+        nw = torch.linalg.vector_norm(w)
+        H[j + 1, j] = nw
+        V[j + 1] = w / nw
+    return _harmonic_ritz_from_hessenberg(H.cpu().numpy(), degree)
 
 
 class SmootherPolynomialError(Exception):
@@ -299,6 +327,24 @@ def smoother_storage_error(A, omega, nu, p0, storage):
             return np.inf
     y = (p0 / 64.0) * y.astype(np.complex128)
     return float(np.linalg.norm(y - e) / np.linalg.norm(e))
+
+
+def smoother_storage_error_device(dev, level, nu, p0, storage):
+    """The same measurement with the device's own smoother kernels: p(A) b in the complex64 cycle's arithmetic with the
+    intermediates stored as `storage` against the complex128 evaluation of the same product form (whose agreement with the
+    Richardson form smoother_product_form has already checked)."""
+    import torch
+    n = dev.sizes[level]
+    rs = np.random.RandomState(11)
+    b = rs.standard_normal(n) + 1j * rs.standard_normal(n)
+    b /= np.linalg.norm(b)
+    B = torch.from_numpy(b.reshape(n, 1).repeat(2, axis=1)).to(dev.device).contiguous()      # two columns: the BF16 kernels pack pairs
+    dev.set_smoother(level, nu, p0, storage16=(storage == 'bf16'))
+    E = dev.smooth(level, B.to(torch.complex64).contiguous()).to(torch.complex128)
+    Eref = dev.smooth(level, B)
+    if not bool(torch.isfinite(E.real).all()) or not bool(torch.isfinite(E.imag).all()):
+        return np.inf
+    return float((torch.linalg.vector_norm(E - Eref) / torch.linalg.vector_norm(Eref)).item())
 
 
 def bsr_padded(A, bs):
@@ -454,8 +500,15 @@ class MG:
                 # the fine test vectors lie in range(P), so their restrictions are eigenvectors of R A P for the
                 # same eigenvalues: no eigensolve on the coarse levels of the preconditioner hierarchy
                 eig_vecs = ml.levels[i - 1].R @ self.test_vectors[i - 1]
-            else:
+            elif params.get('host_eigensolver', False):
                 _, eig_vecs = eigs(Al, k=dofip1, which='LM', tol=tolx, maxiter=1000000, sigma=0.0, ncv=ncvx)
+            else:
+                hint = None
+                if i > 0 and self.test_vectors[i - 1].shape[1] >= dofip1:
+                    # A fine eigenvector lies in range(P), so its restriction is an eigenvector of R A P for the same
+                    # eigenvalue: the start block of the coarse eigensolve (which then only has to confirm it)
+                    hint = ml.levels[i - 1].R @ self.test_vectors[i - 1][:, :dofip1]
+                eig_vecs = self.device_test_vectors(Al, dofip1, tolx, params, i, hint)
             self.test_vectors.append(eig_vecs)
 
             if geometric:
@@ -512,6 +565,81 @@ class MG:
         self.level_shapes = [l.A.shape[0] for l in ml.levels]
         self._upload(params, use_permuted)
 
+    def device_test_vectors(self, Al, nvec, tol, params, level, hint=None):
+        """multigrid.py:174 (`eigs(Al, k=nvec, which='LM', sigma=0.0, tol)`) on the device: block Arnoldi on A_l^{-1}
+        (eigensolve.smallest_eigenpairs), every block step one batched FGMRES solve of p columns.  No hierarchy exists yet
+        when the test vectors of a level are wanted, so the solver is the bootstrap one: FGMRES preconditioned by the
+        level's own smoother polynomial (option precond_smoother_only).  Deterministic: seeded start block, conjugate
+        pairs cut by nvec keep the member with Im > 0 (scipy's eigs starts from a random vector and may return either).
+        Returns eig_vecs[n][nvec] (numpy); self.test_vector_info[level] holds eigenvalues, residuals and solve counts."""
+        import torch
+        from . import eigensolve
+        n = Al.shape[0]
+        dims = params.get('latt_dims', None)
+        dev = _lib.Hierarchy(2, self.device)
+        fmt = None
+        if level == 0 and self.aggregation == "reference":
+            if dims is None:
+                Ls = int(round(np.sqrt(n / 2)))
+                dims = [Ls, Ls]
+            try:
+                links, diag = lattice.links_from_matrix(Al, dims[1] if len(dims) > 1 else dims[0], dims[0])
+                dev.set_stencil(0, links, diag)
+                fmt = "stencil"
+            except lattice.NotAStencil:
+                fmt = None
+        if fmt is None:
+            bs = 1
+            if level > 0 and self._transfer_meta and self._transfer_meta[level - 1][0] != "indexed":
+                bs = self._transfer_meta[level - 1][2]
+            col, vals = bsr_padded(Al, bs)
+            dev.set_bsr(0, n, bs, col, vals)
+        deg = int(params.get('bootstrap_degree', 80))
+        Ai = csr_matrix(Al)
+        while True:
+            try:
+                nu, p0 = smoother_product_form(harmonic_ritz_inv_roots(Ai, deg))
+                break
+            except SmootherPolynomialError:
+                if deg <= 4:
+                    raise
+                deg = max(4, (3 * deg) // 4)
+        dev.set_smoother(0, nu, p0, storage16=False)
+        dev.set_inner_precision(_lib.C128)
+        dev.set_option("precond_smoother_only", 1)
+        p = int(params.get('eigensolver_block', max(4 * nvec, 16)))
+        p = max(nvec, min(p, n // 4))
+        gen = torch.Generator().manual_seed(20240531 + level)
+        X0 = torch.complex(torch.randn(n, p, dtype=torch.float64, generator=gen), torch.randn(n, p, dtype=torch.float64, generator=gen))
+        if hint is not None:
+            X0[:, :hint.shape[1]] = torch.from_numpy(np.ascontiguousarray(hint))
+        X0 = X0.to(dev.device)
+        maxit = n if n < 4000 else 4000
+        restart = min(self.restart, maxit)
+        solve_tol = min(1e-10, 1e-2 * tol)
+        stats = {"solves": 0, "iters": 0}
+
+        def apply_Ainv(V):
+            X, it, rr = dev.fgmres(0, V.contiguous(), solve_tol, restart=restart, maxiter=maxit)
+            stats["solves"] += 1
+            stats["iters"] += int(it.max())
+            return X
+
+        def apply_A(V):
+            return dev.spmm(0, V.contiguous())
+        theta, X, res, info = eigensolve.smallest_eigenpairs(apply_A, apply_Ainv, X0, nvec, tol=max(tol, 1e-11),
+                                                             max_blocks=int(params.get('eigensolver_blocks', 16)),
+                                                             min_blocks=3 if hint is not None else 1)
+        if not info["converged"]:
+            raise Exception("test-vector eigensolver did not converge on level %d (residuals %s)" % (level, res))
+        info.update({"theta": theta, "residuals": res, "fgmres_iters": stats["iters"], "block": p, "bootstrap_degree": deg})
+        self.test_vector_info = getattr(self, "test_vector_info", {})
+        self.test_vector_info[level] = info
+        out = X.cpu().numpy()
+        dev.release_workspace()
+        dev.close()
+        return out
+
     def _upload(self, params, use_permuted):
         """Re-lay out the hierarchy for the device kernels and copy it to the GPU once."""
         lv = self.ml.levels
@@ -561,11 +689,17 @@ class MG:
                 # device's precisions against complex128 (a high degree on a small level can be unstable with BF16-
                 # stored intermediates): fall back to FP32 storage, then to a lower degree
                 try:
-                    omega = harmonic_ritz_inv_roots(Ai, d)
+                    on_device = Ai.shape[0] >= 4096 and not params.get('host_smoother_setup', False)
+                    if on_device:       # the level's operator is already on the device: Arnoldi and the storage check there
+                        omega = harmonic_ritz_inv_roots_device(lambda X, _i=i: dev.spmm(_i, X.contiguous()), Ai.shape[0], d, dev.device)
+                    else:
+                        omega = harmonic_ritz_inv_roots(Ai, d)
                     nu, p0 = smoother_product_form(omega)
                     storage = None
                     for st in ('bf16', 'f32'):
-                        if smoother_storage_error(Ai, omega, nu, p0, st) < 0.15:
+                        err = smoother_storage_error_device(dev, i, nu, p0, st) if on_device else \
+                            smoother_storage_error(Ai, omega, nu, p0, st)
+                        if err < 0.15:
                             storage = st
                             break
                     if storage is None:
@@ -618,16 +752,19 @@ class MG:
         # operand of the complex64 V-cycle (dmlmc_set_dense_inverse_device).
         self.dense_level = nl - 1
         self.dense_levels = {nl - 1: "host"}
+        # params['skip_unused_inverses'] (the drivers set it): level 1 is neither sampled (mlmc_levels_to_skip = [1]) nor part of
+        # the V-cycle that preconditions level 0 (the geometric hierarchy does that), so its dense inverse -- n_1 device solves
+        # and n_1^2 BF16 numbers -- is not built; a solve on level 1, should one be asked for, cycles down to level 2 instead
+        unused1 = bool(params.get('skip_unused_inverses', False)) and self.geometric_precond and self.level0_format == "stencil" \
+            and list(params.get('mlmc_levels_to_skip', [])) == [1] and nl >= 4 and self._geometric_precond_possible(params)
+        self.level1_unused = unused1
         for i in range(nl - 2, 0, -1):
             n_i = lv[i].A.shape[0]
-            if n_i > self.dense_coarse_threshold or n_i % 8:
+            if n_i > self.dense_coarse_threshold or n_i % 8 or (i == 1 and unused1):
                 break
             small = n_i <= 4096
             Minv = self._device_inverse(i, 1e-13 if small else 1e-6)     # the BF16 operand keeps 3 digits
-            if small:
-                dev.set_dense_inverse(i, Minv.cpu().numpy())
-            else:
-                dev.set_dense_inverse_device(i, Minv)
+            dev.set_dense_inverse_device(i, Minv, full=small)
             self.dense_levels[i] = "host" if small else "tensor"
             self.dense_level = i
             del Minv
@@ -636,6 +773,16 @@ class MG:
         torch.cuda.empty_cache()
         if self.geometric_precond and self.level0_format == "stencil":
             self._build_geometric_preconditioner(params)
+
+    def _geometric_precond_possible(self, params):
+        dims = params.get('latt_dims', None)
+        n0 = self.ml.levels[0].A.shape[0]
+        if dims is None:
+            Ls = int(round(np.sqrt(n0 / 2)))
+            dims = [Ls, Ls]
+        LX, LT = (dims[1] if len(dims) > 1 else dims[0]), dims[0]
+        bx, bt = self.precond_blocks
+        return not (LX % bx or LT % bt or 2 * LX * LT != n0 or (bx * bt) < self._setup_args['dof'][1] // 2)
 
     def _build_geometric_preconditioner(self, params):
         """A second hierarchy on geometric aggregates (precond_blocks sites at level 0, then 2 x 2, split by spin; same
@@ -650,7 +797,7 @@ class MG:
         LX, LT = (dims[1] if len(dims) > 1 else dims[0]), dims[0]
         bx, bt = self.precond_blocks
         sa = self._setup_args
-        if LX % bx or LT % bt or 2 * LX * LT != n0 or (bx * bt) < sa['dof'][1] // 2:
+        if not self._geometric_precond_possible(params):
             return
         # levels: blocks of bx x bt sites, then 2 x 2, until the level is small enough for a host-side dense inverse
         nv = [int(d // 2) for d in sa['dof'][1:]]
@@ -685,7 +832,7 @@ class MG:
         iterations at degree 32 against 33 (18 at degree 80) with the estimator's own level-2 aggregates."""
         lv = self.ml.levels
         sa = self._setup_args
-        if len(lv) < 3 or 1 in self.dense_levels or self._transfer_meta[0][0] == "indexed":
+        if len(lv) < 3 or 1 in self.dense_levels or self._transfer_meta[0][0] == "indexed" or getattr(self, "level1_unused", False):
             return
         aggr, dofi, nv1, _ = self._transfer_meta[0]
         a_sites = aggr                          # rows of one spin component per strip (dofi = 2: rows = sites of one spin)
@@ -793,11 +940,23 @@ class MG:
 
     def diff_op(self, v):
         """( Af^{-1} - P Ac^{-1} R ) v at tolerance self.solve_tol, on the device."""
+        V = self._to_dev(np.asarray(v).reshape(-1))
+        return self.diff_op_batch(V).cpu().numpy().reshape(-1)
+
+    def diff_op_Q_batch(self, V):
+        """diff_op_Q on a block: V torch complex128 CUDA tensor [n_l, p] -> [n_l, p]"""
+        h = V.shape[0] // 2
+        Vx = V.clone()
+        Vx[h:] = -Vx[h:]
+        return self.diff_op_batch(Vx)
+
+    def diff_op_batch(self, V):
+        """( Af^{-1} - P Ac^{-1} R ) V for a block of columns (torch CUDA tensor in and out)"""
         l = self.level_for_diff_op
         nl = len(self.ml.levels)
         skip = self.skip_level and l == 0
         lc = l + 2 if skip else l + 1
-        V = self._to_dev(np.asarray(v).reshape(-1))
+        V = V.contiguous()
         self.level_nr = l
         T1, _, _ = self.solve_batch(l, V, self.solve_tol)
         Vc = self.dev.restrict(l, V)
@@ -809,12 +968,12 @@ class MG:
             self.level_nr = lc
             T2, _, _ = self.solve_batch(lc, Vc, self.solve_tol)
         if skip:
-            Tm = self.dev.torch.zeros((self.level_shapes[l + 1], 1), dtype=T2.dtype, device=T2.device)
+            Tm = self.dev.torch.zeros((self.level_shapes[l + 1], V.shape[1]), dtype=T2.dtype, device=T2.device)
             self.dev.prolong_add(l + 1, T2, Tm)
             T2 = Tm
         W = self.dev.torch.zeros_like(T1)
         self.dev.prolong_add(l, T2, W)
-        return (T1 - W).cpu().numpy().reshape(-1)
+        return T1 - W
 
     # ---- multigrid.py:552-557 -----------------------------------------------------------------------
     def matvec(self, x):

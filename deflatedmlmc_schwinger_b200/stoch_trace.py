@@ -37,6 +37,7 @@ def _make_solver(A, params):
     if not prebuilt:
         _say(params, "MG setup phase ...", end='', flush=True)
         start = time.time()
+        params.setdefault('skip_unused_inverses', True)
         mg_solver.setup(dof=params['dof'], aggrs=params['aggrs'], max_levels=params['max_nr_levels'], dim=2,
                         acc_eigvs=params['accuracy_mg_eigvs'], sys_type=params['problem_name'], params=params)
         end = time.time()

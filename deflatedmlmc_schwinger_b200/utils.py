@@ -99,6 +99,47 @@ def trace_params_from_params(params, example):
     return trace_params
 
 
+def device_deflation_eigenpairs(mg_solver, params, method, k, tolx, level_nr):
+    """The eigensolves of utils.py:140,143 as block Lanczos on the device (eigensolve.largest_hermitian_eigenpairs): one
+    operator application = one batched solve of p columns, where scipy's eigsh feeds the batched solver one vector at a time.
+      "hutchinson": eigsh(Q, k, which='LM', sigma=0.0), Q = g3 A  ->  the k eigenvalues of Q closest to zero = largest of
+                    Q^{-1} = A^{-1} g3, solved to 1e-2 * tolx;
+      "mlmc":       eigsh(LinearOperator(diff_op_Q), k, which='LM')  ->  largest of (A_f^{-1} - P A_c^{-1} R) g3 with the
+                    solves at diff_lev_op_tol, as the reference applies it.
+    Deterministic (seeded start block).  Returns (Sy[k] ascending, Vx[n][k]) like eigsh."""
+    import torch
+    from . import eigensolve
+    dev = mg_solver.dev
+    lvl = 0 if method == "hutchinson" else level_nr
+    n = mg_solver.level_shapes[lvl]
+    p = int(params.get('deflation_block', min(max(k, 8), 32)))
+    p = max(1, min(p, n // 4))
+    gen = torch.Generator().manual_seed(777 + 13 * lvl + (0 if method == "hutchinson" else 1))
+    X0 = torch.complex(torch.randn(n, p, dtype=torch.float64, generator=gen),
+                       torch.randn(n, p, dtype=torch.float64, generator=gen)).to(dev.device)
+    if method == "hutchinson":
+        stol = min(1e-10, 1e-2 * tolx)
+        h = n // 2
+
+        def op(V):
+            Vx = V.clone()
+            Vx[h:] = -Vx[h:]
+            X, _, _ = mg_solver.solve_batch(0, Vx.contiguous(), stol)
+            return X
+        lam, X, res, info = eigensolve.largest_hermitian_eigenpairs(op, X0, k, tol=tolx)
+        Sy = 1.0 / lam
+    else:
+        mg_solver.level_for_diff_op = level_nr
+        lam, X, res, info = eigensolve.largest_hermitian_eigenpairs(mg_solver.diff_op_Q_batch, X0, k, tol=tolx)
+        Sy = lam
+    if not info["converged"]:
+        raise Exception("deflation eigensolver did not converge (%s, level %d): residuals %s" % (method, lvl, res))
+    order = np.argsort(Sy, kind='stable')
+    mg_solver.deflation_info = getattr(mg_solver, "deflation_info", {})
+    mg_solver.deflation_info[(method, lvl)] = dict(info, residuals=res)
+    return Sy[order], X.cpu().numpy()[:, order]
+
+
 # ---- utils.py:130-201 -----------------------------------------------------------------------------
 def deflation_pre_computations(A, nr_deflat_vctrs, tolx, method, timer, params, mg_solver, lop=None, level_nr=0,
                                eigpairs=None):
@@ -109,11 +150,17 @@ def deflation_pre_computations(A, nr_deflat_vctrs, tolx, method, timer, params, 
         if eigpairs is not None:
             Sy, Vx = np.array(eigpairs[0]), np.array(eigpairs[1])
         elif method == "hutchinson":
-            Q = mg_solver.ml.levels[0].g3 * A
-            Sy, Vx = eigsh(Q, k=nr_deflat_vctrs, which='LM', tol=tolx, sigma=0.0)
+            if params.get('host_eigensolver', False):
+                Q = mg_solver.ml.levels[0].g3 * A
+                Sy, Vx = eigsh(Q, k=nr_deflat_vctrs, which='LM', tol=tolx, sigma=0.0)
+            else:
+                Sy, Vx = device_deflation_eigenpairs(mg_solver, params, "hutchinson", nr_deflat_vctrs, tolx, 0)
         elif method == "mlmc":
             mg_solver.solve_tol = params['diff_lev_op_tol']
-            Sy, Vx = eigsh(lop, k=nr_deflat_vctrs, which='LM', tol=tolx)
+            if params.get('host_eigensolver', False):
+                Sy, Vx = eigsh(lop, k=nr_deflat_vctrs, which='LM', tol=tolx)
+            else:
+                Sy, Vx = device_deflation_eigenpairs(mg_solver, params, "mlmc", nr_deflat_vctrs, tolx, level_nr)
         else:
             raise Exception("unknown method")
         sgnS = np.where(np.asarray(Sy) > 0, 1.0, -1.0)
@@ -134,8 +181,15 @@ def deflation_pre_computations(A, nr_deflat_vctrs, tolx, method, timer, params, 
         else:
             if params['defl_type'] == "exact":
                 tr1 = np.sum(d * Sy)
-            elif params['defl_type'] in ("inexact_01", "inexact_02", "inexact_03"):
-                raise Exception("deflation type " + params['defl_type'] + " is disabled in the reference set")
+            elif params['defl_type'] == "inexact_01":
+                # utils.py:177-183: tr(Vx^H diff_op(Vx)) with the operator at the function tolerance, all columns in one batch
+                mg_solver.level_for_diff_op = level_nr
+                Vd = mg_solver._to_dev(np.ascontiguousarray(Vx))
+                tr1 = complex((Vd.conj() * mg_solver.diff_op_batch(Vd)).sum().item())
+            elif params['defl_type'] == "inexact_02":
+                raise Exception("deflation type inexact_02 under construction")          # utils.py:184-185
+            elif params['defl_type'] == "inexact_03":
+                tr1 = 0.0                                                                # utils.py:186-187
             else:
                 raise Exception("unknown deflation type")
     else:

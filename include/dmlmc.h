@@ -78,6 +78,10 @@ int dmlmc_set_dense_inverse(dmlmc_hier* h, int level, int n, const double* minv_
  * tensor-core operand is kept: BF16 [2n][2n], every complex entry as the real block [[re,-im],[im,re]],
  * applied by the tcgen05 kernel with FP32 accumulation.  Such a level serves the complex64 V-cycle only. */
 int dmlmc_set_dense_inverse_device(dmlmc_hier* h, int level, int n, const void* minv_dev);
+/* The same hand-over for an inverse kept in ALL precisions (what dmlmc_set_dense_inverse makes from a host array: the
+ * complex128 and complex64 copies, the splatted FP32 operand and the tensor-core operands), from a complex128 device
+ * array [n][n] -- the inverse never visits the host (multigrid.py:342-344 of the reference inverts on the host). */
+int dmlmc_set_dense_inverse_device_full(dmlmc_hier* h, int level, int n, const void* minv_dev);
 /* smoother on `level`: e = p(A_level) r with the fixed polynomial p in product form,
  *   p(A) = p0 * prod_{i<nfactors} (I - nu_i A)       (nu_host: nfactors complex128, applied in order),
  * one fused operator+update kernel per factor, no inner products.  Replaces the lgmres call of

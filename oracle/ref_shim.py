@@ -1,8 +1,8 @@
-"""TEST INFRASTRUCTURE ONLY -- loads the UNMODIFIED reference modules from /root/reference.
+"""TEST INFRASTRUCTURE ONLY -- loads the UNMODIFIED reference modules from /root/reference (authoring container) or
+from its byte-for-byte copy oracle/_ref/ (oracle/vendor_reference.py; that copy travels to the GPU box).
 
-Only usable in the authoring container (the GPU box has no /root/reference); it is
-used to (a) validate oracle/refport.py and (b) generate tests/golden/* through
-oracle/make_golden.py.  Nothing in the product imports this file.
+Used to (a) validate oracle/refport.py, (b) generate tests/golden/* through oracle/make_golden.py and (c) time the
+reference itself in `bench.py --impl reference`.  Nothing in the product imports this file.
 
 What has to be patched for the reference to run here:
   1. `pyamg` and `matplotlib` are absent            -> oracle/shims on sys.path
@@ -21,9 +21,11 @@ import sys
 
 import numpy as np
 
-REF_DIR = "/root/reference"
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _SHIMS = os.path.join(_HERE, "shims")
+# the read-only reference tree of the authoring container, else the byte-for-byte copy made by oracle/vendor_reference.py
+# (oracle/_ref/, git-ignored, travels to the GPU box)
+REF_DIR = "/root/reference" if os.path.isfile("/root/reference/multigrid.py") else os.path.join(_HERE, "_ref")
 
 
 def reference_available():

@@ -1,0 +1,142 @@
+"""Set-up eigensolvers: the block algorithms against scipy on the CPU, and the device path
+(bootstrap FGMRES / batched solver as the operator) against the reference's own eigenvectors in tests/golden."""
+import numpy as np
+import pytest
+
+from conftest import params16, params128
+
+
+def _cos_min(X, Y):
+    Q1, _ = np.linalg.qr(np.asarray(X))
+    Q2, _ = np.linalg.qr(np.asarray(Y))
+    return float(np.linalg.svd(Q1.conj().T @ Q2, compute_uv=False).min())
+
+
+def _matrix16():
+    from deflatedmlmc_schwinger_b200 import matrix
+    p = params16()
+    return matrix.loadMatrix(p["matrix"], p["matrix_params"]).tocsc()
+
+
+def _start(n, p, seed):
+    import torch
+    gen = torch.Generator().manual_seed(seed)
+    return torch.complex(torch.randn(n, p, dtype=torch.float64, generator=gen), torch.randn(n, p, dtype=torch.float64, generator=gen))
+
+
+def test_block_arnoldi_shift_invert_matches_scipy_eigs(g16):
+    """smallest_eigenpairs (what multigrid.py:174 asks of eigs): same invariant subspace as the reference's test vectors
+    (golden tv0 of 16^2 are that call's output), residual below the tolerance, conjugate pairs ordered Im > 0 first"""
+    import torch
+    import scipy.sparse.linalg as spla
+    from deflatedmlmc_schwinger_b200 import eigensolve
+    A = _matrix16()
+    n = A.shape[0]
+    lu = spla.splu(A)
+    aA = lambda X: torch.from_numpy(A @ X.numpy())
+    aI = lambda X: torch.from_numpy(lu.solve(np.ascontiguousarray(X.numpy())))
+    k = g16["tv0"].shape[1]
+    th, X, res, info = eigensolve.smallest_eigenpairs(aA, aI, _start(n, 8, 3), k, tol=1e-9)
+    assert info["converged"] and res.max() <= 1e-9
+    assert _cos_min(X.numpy(), g16["tv0"]) > 1 - 1e-8
+    ref = np.sort(np.abs(spla.eigs(A, k=6, sigma=0.0, which='LM', tol=1e-12)[0]))[:k]
+    assert np.allclose(np.sort(np.abs(th)), ref, rtol=1e-8)
+    assert list(eigensolve._sort_smallest(np.array([0.5, 0.2 - 0.1j, 0.2 + 0.1j, 0.1]))) == [3, 2, 1, 0]
+
+
+def test_block_lanczos_matches_scipy_eigsh(g16):
+    """largest_hermitian_eigenpairs on Q^{-1} (utils.py:140 `eigsh(Q, k, which='LM', sigma=0.0)`): the reference's 16
+    deflation vectors of 16^2 (golden defl_Vx) span the same subspace, eigenvalues agree"""
+    import torch
+    import scipy.sparse.linalg as spla
+    from scipy.sparse import diags
+    from deflatedmlmc_schwinger_b200 import eigensolve
+    A = _matrix16()
+    n = A.shape[0]
+    g3 = np.ones(n)
+    g3[n // 2:] = -1
+    Q = (diags([g3], [0]) @ A).tocsc()
+    lu = spla.splu(Q)
+    op = lambda X: torch.from_numpy(lu.solve(np.ascontiguousarray(X.numpy())))
+    k = 16
+    lam, X, res, info = eigensolve.largest_hermitian_eigenpairs(op, _start(n, 8, 5), k, tol=1e-9)
+    assert info["converged"]
+    Sy = np.sort(np.abs(1.0 / lam))
+    assert np.allclose(Sy, np.sort(np.abs(g16["defl_Sy"])), rtol=1e-7)
+    assert _cos_min(X.numpy(), g16["defl_Vx"]) > 1 - 1e-7
+
+
+# ---- device path -----------------------------------------------------------------------------------------------------------
+
+@pytest.mark.gpu
+def test_device_test_vectors_128_span_the_reference_subspace(g128):
+    """MG.device_test_vectors on level 0 of 128^2 (no hierarchy yet: FGMRES preconditioned by the smoother polynomial) returns
+    the invariant subspace of the reference's eigs call (golden tv0, whose 4th eigenvalue is the Im > 0 member of a pair) with
+    ||A v - theta v|| <= 1e-9."""
+    from deflatedmlmc_schwinger_b200 import matrix, multigrid, utils
+    p = params128()
+    tp = utils.trace_params_from_params(p, "mlmc")
+    A = matrix.loadMatrix(p["matrix"], p["matrix_params"])
+    mg = multigrid.MG(A)
+    mg._transfer_meta = []
+    V = mg.device_test_vectors(A.tocsr(), 4, 1e-9, tp, 0)
+    info = mg.test_vector_info[0]
+    print("level-0 test vectors:", info["theta"], "residuals", info["residuals"], "block solves", info["block_solves"],
+          "FGMRES iterations", info["fgmres_iters"])
+    assert info["residuals"].max() <= 1e-9
+    assert np.all(np.abs(A @ V - V * info["theta"][None, :]).max(axis=0) < 1e-8)
+    assert info["theta"][3].imag > 0
+    assert _cos_min(V, g128["tv0"]) > 1 - 1e-8
+
+
+@pytest.mark.gpu
+def test_uninjected_setup_16_reproduces_the_reference_hierarchy(g16):
+    """MG.setup without injected test vectors (device eigensolver on every level): the level operators equal those built
+    from the reference's own test vectors, because they depend on the test vectors only through their span."""
+    from deflatedmlmc_schwinger_b200 import matrix, multigrid, utils
+    p = params16()
+    tp = utils.trace_params_from_params(p, "mlmc")
+    A = matrix.loadMatrix(p["matrix"], p["matrix_params"])
+    out = []
+    for tvs in (None, [g16["tv0"], g16["tv1"]]):
+        mg = multigrid.MG(A, smoother_degree=8)
+        mg.setup(dof=tp["dof"], aggrs=tp["aggrs"], max_levels=tp["max_nr_levels"], acc_eigvs=tp["accuracy_mg_eigvs"], params=tp,
+                 test_vectors=tvs)
+        out.append(mg)
+    a, b = out
+    assert _cos_min(a.test_vectors[0], b.test_vectors[0]) > 1 - 1e-7
+    # coarse coordinates depend on the phases of the fine test vectors (per-aggregate Gram-Schmidt), the prolongated coarse test
+    # vectors and the range of P do not
+    assert _cos_min(a.ml.levels[0].P @ a.test_vectors[1], b.ml.levels[0].P @ b.test_vectors[1]) > 1 - 1e-7
+    Pa, Pb = a.ml.levels[0].P.toarray(), b.ml.levels[0].P.toarray()
+    assert np.abs(Pa @ Pa.conj().T - Pb @ Pb.conj().T).max() < 1e-6          # same range of P  <=>  same projector P P^H
+    PPa, PPb = Pa @ a.ml.levels[1].P.toarray(), Pb @ b.ml.levels[1].P.toarray()
+    assert np.abs(PPa @ PPa.conj().T - PPb @ PPb.conj().T).max() < 1e-6
+    # the MLMC level operator P A_c^{-1} R of level 0 is the same
+    la, lb = a.ml.levels, b.ml.levels
+    Ma = la[0].P @ np.linalg.solve(la[1].A.toarray(), la[0].R.toarray())
+    Mb = lb[0].P @ np.linalg.solve(lb[1].A.toarray(), lb[0].R.toarray())
+    assert np.abs(Ma - Mb).max() < 1e-6 * np.abs(Mb).max()
+
+
+@pytest.mark.gpu
+def test_device_deflation_eigensolvers_16(mg16, g16, g16defl):
+    """deflation_pre_computations without injected eigenpairs: block Lanczos on the batched solver.  Hutchinson: the reference's
+    16 vectors of Q (golden defl_Vx) and tr1; MLMC: the dominant subspace of diff_op_Q against the reference's l*_eigvecs
+    (eigsh there ran at tol 1e-1 with solves at 1e-3, so the comparison is on tr1 and on principal angles)."""
+    from deflatedmlmc_schwinger_b200 import utils
+    mg, tp, A = mg16
+    tp = dict(tp)
+    tp["nr_deflat_vctrs"] = 16
+    Ux, tr1 = utils.deflation_pre_computations(A, 16, 1e-9, "hutchinson", mg.timer, tp, mg)
+    assert abs(tr1 - g16["defl_tr1"]) < 1e-7 * abs(g16["defl_tr1"])
+    assert _cos_min(Ux, g16["defl_Ux"]) > 1 - 1e-7
+    for ix in range(2):
+        mg.level_for_diff_op = ix
+        Vx, Ux2, tr1m = utils.deflation_pre_computations(A, 16, tp["defl_eigvs_tol_MLMC"], "mlmc", mg.timer, tp, mg, None, level_nr=ix)
+        ref_tr1 = g16defl["l%d_tr1" % ix]
+        # the largest eigenvalues dominate tr1; both eigensolves are loose (tol 1e-1), so is the comparison
+        print("level", ix, "tr1", tr1m, "reference", ref_tr1, "cos", _cos_min(Vx[:, -4:], g16defl["l%d_Vx" % ix]))
+        assert abs(tr1m - ref_tr1) < 0.05 * abs(ref_tr1)
+        cos = np.linalg.svd(np.linalg.qr(Vx)[0].conj().T @ np.linalg.qr(g16defl["l%d_Vx" % ix])[0], compute_uv=False)
+        assert cos[:8].min() > 0.99          # the 8 dominant directions agree
