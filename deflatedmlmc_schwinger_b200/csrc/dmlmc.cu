@@ -1687,8 +1687,7 @@ int dmlmc_mt19937_bits(dmlmc_hier* h, uint32_t* state_dev, uint32_t* backup_dev,
 int dmlmc_probe_expand_bytes(dmlmc_hier* h, const uint8_t* lsb_dev, int n, int k, void* X0) {
   ENTER(h); CHECK(lsb_dev && X0 && n >= 1 && k >= 1, "probe_expand_bytes: bad arguments");
   CU(cudaStreamWaitEvent(h->stream, h->rng_done, 0));          // the generator that filled lsb_dev
-  const size_t nk = (size_t)n * k;
-  probe_expand_bytes_kernel<<<nblocks(nk, 256), 256, 0, h->stream>>>(lsb_dev, n, k, (Cx<double>*)X0);
+  probe_expand_bytes_kernel<<<dim3((k + 31) / 32, (n + 127) / 128), dim3(32, 8), 0, h->stream>>>(lsb_dev, n, k, (Cx<double>*)X0);
   LAUNCH_CHECK(h);
   return 0;
 }

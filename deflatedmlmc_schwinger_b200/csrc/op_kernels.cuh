@@ -1224,14 +1224,32 @@ mt19937_jump_bits_kernel(const uint32_t* __restrict__ state, uint32_t* __restric
   }
 }
 
-// element i of probe p = 2*lsb[p*n+i] - 1 (one byte per element, as written by mt19937_bits_kernel)
+// element i of probe p = 2*lsb[p*n+i] - 1 (one byte per element, as written by mt19937_bits_kernel).  The generator's order is
+// probe-major, X0 is element-major: a 32-probe x 128-element tile goes through shared memory so that both the byte reads (along
+// i) and the complex128 writes (along p) are coalesced.  block (32, 8), grid (ceil(k / 32), ceil(n / 128)).
 __global__ void __launch_bounds__(256)
 probe_expand_bytes_kernel(const uint8_t* __restrict__ lsb, int n, int k, Cx<double>* __restrict__ X0) {
-  const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  const int i = (int)(gid / k);
-  const int p = (int)(gid - (long long)i * k);
-  if (i >= n) return;
-  X0[(size_t)i * k + p] = cx<double>(__ldg(lsb + (size_t)p * n + i) ? 1.0 : -1.0, 0.0);
+  __shared__ uint8_t tile[32][132];
+  const int tx = threadIdx.x, ty = threadIdx.y;
+  const int p0 = blockIdx.x * 32, i0 = blockIdx.y * 128;
+  for (int r = ty; r < 32; r += 8) {
+    const int p = p0 + r;
+    if (p >= k) continue;
+    const size_t base = (size_t)p * n + i0;
+    if (i0 + 128 <= n && ((base & 3) == 0)) {
+      const uint32_t v = __ldg(reinterpret_cast<const uint32_t*>(lsb + base) + tx);
+      *reinterpret_cast<uint32_t*>(&tile[r][4 * tx]) = v;
+    } else {
+      for (int q = 0; q < 4; ++q) { const int i = i0 + 4 * tx + q; tile[r][4 * tx + q] = i < n ? __ldg(lsb + (size_t)p * n + i) : 0; }
+    }
+  }
+  __syncthreads();
+  const int p = p0 + tx;
+  if (p >= k) return;
+  for (int ii = ty; ii < 128; ii += 8) {
+    const int i = i0 + ii;
+    if (i < n) X0[(size_t)i * k + p] = cx<double>(tile[tx][ii] ? 1.0 : -1.0, 0.0);
+  }
 }
 
 // Out[r][c] = (Tout) In[r][c], r < n, c < w: copies / converts a block of w columns between two

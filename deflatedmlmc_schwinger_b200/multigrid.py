@@ -598,7 +598,11 @@ class MG:
         Ai = csr_matrix(Al)
         while True:
             try:
-                nu, p0 = smoother_product_form(harmonic_ritz_inv_roots(Ai, deg))
+                if n >= 4096:
+                    om = harmonic_ritz_inv_roots_device(lambda X: dev.spmm(0, X.contiguous()), n, deg, dev.device)
+                else:
+                    om = harmonic_ritz_inv_roots(Ai, deg)
+                nu, p0 = smoother_product_form(om)
                 break
             except SmootherPolynomialError:
                 if deg <= 4:

@@ -110,8 +110,16 @@ def test_uninjected_setup_16_reproduces_the_reference_hierarchy(g16):
     assert _cos_min(a.ml.levels[0].P @ a.test_vectors[1], b.ml.levels[0].P @ b.test_vectors[1]) > 1 - 1e-7
     Pa, Pb = a.ml.levels[0].P.toarray(), b.ml.levels[0].P.toarray()
     assert np.abs(Pa @ Pa.conj().T - Pb @ Pb.conj().T).max() < 1e-6          # same range of P  <=>  same projector P P^H
-    PPa, PPb = Pa @ a.ml.levels[1].P.toarray(), Pb @ b.ml.levels[1].P.toarray()
-    assert np.abs(PPa @ PPa.conj().T - PPb @ PPb.conj().T).max() < 1e-6
+    # range(P_0 P_1) is NOT comparable: with dof = [2, 4, 4] the "halves" of a level-1 aggregate are the test-vector indices of
+    # level 0 (multigrid.py:203-227 with dofi = dof[1] / 2), the first coarse test vector has no component on the second
+    # index by construction of the Gram-Schmidt of level 0, and multigrid.py:232-259 normalises that rounding noise into a
+    # column of P_1 -- in the reference too (its level-2 operator depends on the noise of its eigs call).  What is determined:
+    # orthonormal columns, and the coarse test vectors lie in range(P_1).
+    for m in (a, b):
+        P1 = m.ml.levels[1].P.toarray()
+        assert np.abs(P1.conj().T @ P1 - np.eye(P1.shape[1])).max() < 1e-12
+        t1 = m.test_vectors[1] / np.linalg.norm(m.test_vectors[1], axis=0)
+        assert np.abs(t1 - P1 @ (P1.conj().T @ t1)).max() < 1e-8
     # the MLMC level operator P A_c^{-1} R of level 0 is the same
     la, lb = a.ml.levels, b.ml.levels
     Ma = la[0].P @ np.linalg.solve(la[1].A.toarray(), la[0].R.toarray())
