@@ -33,6 +33,13 @@ def G202():
     return EXAMPLE_002(params)
 
 
+def G302(L=512):
+    """configs[4] of BASELINE.json: deflated MLMC on a synthetic random-U(1) lattice (not in the reference)"""
+    params = set_params('synthetic%d' % L)
+    params['function_tol'] = 1e-12
+    return EXAMPLE_002(params)
+
+
 def set_params(example_name):
     if example_name == 'schwinger16':
         np.random.seed(51234)
@@ -90,6 +97,41 @@ def set_params(example_name):
         params['x_displacement'] = 2
         matrix_params['problem_name'] = 'schwinger'
         params['matrix'] = 'schwinger128.mat'
+        params['matrix_params'] = matrix_params
+        return params
+
+    elif example_name.startswith('synthetic'):
+        # BASELINE.json configs[4] (not in the reference): random-U(1) Schwinger lattice of extent L = 256 / 512 / 1024,
+        # `synthetic<L>`; the shipped 128^2 parameter set with one more multigrid level per factor 4 in volume, the mass
+        # retuned to the synthetic ensemble (sigma = 0.204: critical mass near -0.07)
+        L = int(example_name[len('synthetic'):])
+        if L % 32 or L < 64:
+            raise Exception("synthetic lattice extent must be a multiple of 32")
+        np.random.seed(51234)
+        params = dict()
+        matrix_params = dict()
+        nlev = len([i for i in range(16) if (2 * L * L) // 4 ** i >= 2048])
+        params['trace_tol'] = 1.0e-2
+        params['aggrs'] = [4 * 4] + [2 * 2] * (nlev - 2)
+        params['dof'] = [2] + [8] * (nlev - 1)
+        params['max_nr_levels'] = nlev
+        params['coarsest_level_directly'] = True
+        params['accuracy_mg_eigvs'] = 'low'
+        params['check_quality_MG'] = False
+        params['test_vectors_type'] = 'EVs'
+        params['mlmc_levels_to_skip'] = [1]
+        params['nr_deflat_vctrs'] = 8
+        params['mlmc_deflat_vctrs'] = [0] * (nlev - 1)
+        params['defl_type'] = "exact"
+        params['defl_eigvs_tol_Hutch'] = 1.0e-9
+        params['defl_eigvs_tol_MLMC'] = 1.0e-1
+        params['diff_lev_op_tol'] = 1.0e-3
+        matrix_params['mass'] = -0.062
+        params['use_permuted'] = True
+        params['latt_dims'] = [L, L]
+        params['x_displacement'] = 2
+        matrix_params['problem_name'] = 'schwinger'
+        params['matrix'] = 'synthetic:%d:%d' % (L, L)
         params['matrix_params'] = matrix_params
         return params
 

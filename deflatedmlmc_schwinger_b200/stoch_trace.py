@@ -41,6 +41,7 @@ def _make_solver(A, params):
         mg_solver.setup(dof=params['dof'], aggrs=params['aggrs'], max_levels=params['max_nr_levels'], dim=2,
                         acc_eigvs=params['accuracy_mg_eigvs'], sys_type=params['problem_name'], params=params)
         end = time.time()
+        mg_solver.setup_seconds = end - start
         _say(params, " done. Time : " + str(end - start) + " seconds")
         _say(params, mg_solver)
     nr_levels = len(mg_solver.ml.levels)
@@ -275,6 +276,8 @@ def mlmc(A, params):
     output_params['rough_trace'] = rough_trace
     output_params['sampling_seconds'] = sampling_seconds
     output_params['probes_evaluated'] = probes_evaluated
+    output_params['level_shapes'] = list(mg_solver.level_shapes)
+    output_params['setup_seconds'] = getattr(mg_solver, 'setup_seconds', None)
     return output_params
 
 

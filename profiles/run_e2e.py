@@ -22,6 +22,7 @@ ap.add_argument("--skip-hutchinson", action="store_true")
 ap.add_argument("--batch", type=int, default=256)
 ap.add_argument("--fixed", action="store_true", help="sequential_stop=False: sample count from a pilot round, one all_reduce per level")
 ap.add_argument("--exact", action="store_true", help="also compute the EXACT level values with unit vectors (stoch_trace.exact_trace)")
+ap.add_argument("--set", default="schwinger128", help="gateway.set_params name: schwinger128 (G202/G102) or synthetic<L> (BASELINE configs[4])")
 ap.add_argument("--deflated", action="store_true",
                 help="the valid deflated-MLMC variant of SURVEY.md 8d cfg-2: not permuted, mlmc_deflat_vctrs=[16,0,16]")
 args = ap.parse_args()
@@ -41,7 +42,7 @@ from deflatedmlmc_schwinger_b200 import gateway, matrix, stoch_trace, utils
 
 
 def run(method):
-    p = gateway.set_params("schwinger128")
+    p = gateway.set_params(args.set)
     p["function_tol"] = 1e-12
     p["verbose"] = False
     p["probe_batch"] = args.batch
@@ -59,8 +60,12 @@ def run(method):
     torch.cuda.synchronize()
     wall = time.time() - t0
     exact = EXACT_PLAIN if args.deflated else EXACT_DISPLACED
-    out = {"experiment": ("G202 (mlmc)" if method == "mlmc" else "G102 (hutchinson)") +
+    if args.set != "schwinger128":
+        exact = complex("nan")
+    out = {"experiment": (("G202 (mlmc)" if method == "mlmc" else "G102 (hutchinson)") if args.set == "schwinger128" else
+                          args.set + " (" + method + ")") +
                          (", not permuted, mlmc_deflat_vctrs=[16,0,16]" if args.deflated else ""), "n_gpus": world,
+           "level_shapes": res.get("level_shapes"), "setup_s": res.get("setup_seconds"),
            "trace": [float(np.real(res["trace"])), float(np.imag(res["trace"]))],
            "exact": [exact.real, exact.imag],
            "abs_err": float(abs(res["trace"] - exact)),
@@ -81,7 +86,8 @@ def run(method):
 
 run("mlmc")
 if args.exact and rank == 0:
-    p = gateway.set_params("schwinger128"); p["function_tol"] = 1e-12; p["verbose"] = False
+    p = gateway.set_params(args.set); p["function_tol"] = 1e-12; p["verbose"] = False
+    p["probe_batch"] = args.batch
     if args.deflated:
         p["use_permuted"] = False
     tp = utils.trace_params_from_params(p, "mlmc")
@@ -91,7 +97,7 @@ if args.exact and rank == 0:
     A = matrix.loadMatrix(p["matrix"], p["matrix_params"])
     t0 = time.time()
     ex = stoch_trace.exact_trace(A, tp)
-    exact = EXACT_PLAIN if args.deflated else EXACT_DISPLACED
+    exact = (EXACT_PLAIN if args.deflated else EXACT_DISPLACED) if args.set == "schwinger128" else complex("nan")
     print(json.dumps({"experiment": "exact level traces (unit vectors through the batched solver)",
                       "levels": [[float(np.real(r["ests_avg"])), float(np.imag(r["ests_avg"]))] for r in ex["results"]],
                       "trace": [float(np.real(ex["trace"])), float(np.imag(ex["trace"]))], "reference_exact": [exact.real, exact.imag],
