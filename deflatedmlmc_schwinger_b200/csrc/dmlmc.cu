@@ -93,6 +93,10 @@ struct dmlmc_hier {
   int smoother_half = 1;                  // BF16 storage of the level-0 smoother's intermediate vectors (c64 cycle)
   int dense_direct_exact = 1;             // a dense level solved directly (not from a finer level) uses its FP32 copy
   int outer_eo = 1;                       // outer FGMRES of a stencil level on the even-odd Schur complement (fgmres_eo)
+  int outer_c64 = 1;                      // ... with the Krylov vectors V_j, Z_j, w STORED in complex64 (coefficients, solution and true
+                                          // residual in complex128; a cycle runs until its estimate has dropped by outer_drop)
+  double outer_drop = 1e-5;
+  std::vector<int> expect_cyc[MAX_LEVELS];   // iterations per cycle of the previous Schur-complement solve of (expect_tol, expect_k)
   int eo_zhalf = 0;                       // (internal) the even-odd smoother writes only Z_e, into a half-lattice array
   int smoother_eo = 1;                    // even-odd (Schur complement) form of the level-0 post-smoother when one is set
   int dot32 = 0;                          // Gram-Schmidt coefficients from complex64 copies of the basis vectors: OFF -- measured on
@@ -795,11 +799,12 @@ int vcycle(dmlmc_hier* h, int level0, const void* Bin, void* Xout, int k, const 
   return rc;
 }
 
-// ---- complex128 reductions ---------------------------------------------------------------------
-int multi_dot(dmlmc_hier* h, const Z* Vbase, size_t vstride, int nv, const Z* W, int n, int k, Z* partial, Z* out, int accumulate) {
+// ---- reductions (complex128 accumulation; the vectors complex128, or complex64 in the mixed-precision Schur solve) ---------
+template <typename VT = double, typename WT = double>
+int multi_dot(dmlmc_hier* h, const Cx<VT>* Vbase, size_t vstride, int nv, const Cx<WT>* W, int n, int k, Z* partial, Z* out, int accumulate) {
   const int nchunks = (n + ROWS_PER_CHUNK - 1) / ROWS_PER_CHUNK;
   dim3 blk(DOT_TX, DOT_TY), grd((k + DOT_TX - 1) / DOT_TX, nchunks);
-  multi_dot_kernel<double><<<grd, blk, 0, h->stream>>>(Vbase, vstride, nv, W, n, k, ROWS_PER_CHUNK, partial);
+  multi_dot_kernel<VT, WT><<<grd, blk, 0, h->stream>>>(Vbase, vstride, nv, W, n, k, ROWS_PER_CHUNK, partial);
   LAUNCH_CHECK(h);
   sum_partials_kernel<<<nblocks((size_t)nv * k, 32), dim3(32, 8), 0, h->stream>>>(partial, nchunks, nv * k, out, accumulate);
   LAUNCH_CHECK(h);
@@ -807,28 +812,24 @@ int multi_dot(dmlmc_hier* h, const Z* Vbase, size_t vstride, int nv, const Z* W,
 }
 // the same with the V_i read from their complex64 copies
 int multi_dot32(dmlmc_hier* h, const Cx<float>* Vbase, size_t vstride, int nv, const Z* W, int n, int k, Z* partial, Z* out) {
-  const int nchunks = (n + ROWS_PER_CHUNK - 1) / ROWS_PER_CHUNK;
-  dim3 blk(DOT_TX, DOT_TY), grd((k + DOT_TX - 1) / DOT_TX, nchunks);
-  multi_dot_kernel<float><<<grd, blk, 0, h->stream>>>(Vbase, vstride, nv, W, n, k, ROWS_PER_CHUNK, partial);
-  LAUNCH_CHECK(h);
-  sum_partials_kernel<<<nblocks((size_t)nv * k, 32), dim3(32, 8), 0, h->stream>>>(partial, nchunks, nv * k, out, 0);
-  LAUNCH_CHECK(h);
-  return 0;
+  return multi_dot<float, double>(h, Vbase, vstride, nv, W, n, k, partial, out, 0);
 }
 size_t partial_count(int n, int nv, int k) { return (size_t)((n + ROWS_PER_CHUNK - 1) / ROWS_PER_CHUNK) * nv * k; }
 
-int multi_axpy(dmlmc_hier* h, const Z* Vbase, size_t vstride, int nv, const Z* hc, Z* W, int n, int k, double sgn) {
+template <typename VT = double>
+int multi_axpy(dmlmc_hier* h, const Cx<VT>* Vbase, size_t vstride, int nv, const Z* hc, Z* W, int n, int k, double sgn) {
   const size_t nk = (size_t)n * k;
-  multi_axpy_kernel<<<nblocks(nk, 256), 256, 0, h->stream>>>(Vbase, vstride, nv, hc, W, nk, k, sgn);
+  multi_axpy_kernel<VT><<<nblocks(nk, 256), 256, 0, h->stream>>>(Vbase, vstride, nv, hc, W, nk, k, sgn);
   LAUNCH_CHECK(h);
   return 0;
 }
 
 // W -= sum_i hc[i] V_i and nrm2[col] = ||W[:, col]||^2 (deterministic chunked reduction)
-int multi_axpy_norm(dmlmc_hier* h, const Z* Vbase, size_t vstride, int nv, const Z* hc, Z* W, int n, int k, Z* partial, Z* nrm2) {
+template <typename VT = double>
+int multi_axpy_norm(dmlmc_hier* h, const Cx<VT>* Vbase, size_t vstride, int nv, const Z* hc, Cx<VT>* W, int n, int k, Z* partial, Z* nrm2) {
   const int nchunks = (n + ROWS_PER_CHUNK - 1) / ROWS_PER_CHUNK;
   dim3 blk(DOT_TX, DOT_TY), grd((k + DOT_TX - 1) / DOT_TX, nchunks);
-  multi_axpy_norm_kernel<<<grd, blk, 0, h->stream>>>(Vbase, vstride, nv, hc, W, n, k, ROWS_PER_CHUNK, partial);
+  multi_axpy_norm_kernel<VT><<<grd, blk, 0, h->stream>>>(Vbase, vstride, nv, hc, W, n, k, ROWS_PER_CHUNK, partial);
   LAUNCH_CHECK(h);
   sum_partials_kernel<<<nblocks((size_t)k, 32), dim3(32, 8), 0, h->stream>>>(partial, nchunks, k, nrm2, 0);
   LAUNCH_CHECK(h);
@@ -957,6 +958,7 @@ int fgmres(dmlmc_hier* h, int level, const Z* B, Z* X, int k, double tol, int re
   RET(ws_get<double>(h, (size_t)k, &s.normb));
   RET(ws_get<double>(h, (size_t)k, &s.scale));
   RET(ws_get<double>(h, (size_t)k, &s.relres));
+  RET(ws_get<double>(h, (size_t)k, &s.tolc));
   RET(ws_get<int>(h, (size_t)k, &s.active));
   RET(ws_get<int>(h, (size_t)k, &s.done));
   RET(ws_get<int>(h, (size_t)k, &s.it_cycle));
@@ -1041,12 +1043,15 @@ int fgmres(dmlmc_hier* h, int level, const Z* B, Z* X, int k, double tol, int re
 // the final update move half the bytes; the preconditioner is the even part of the V-cycle applied to (v_e, 0).  CPU experiment
 // (profiles/exp_schur_outer_solve.py): the same 8 outer iterations to 1e-12 as the solve on A.  The residual of the full
 // system is (r^_e, 0), so convergence is measured as ||r^_e|| / ||b||.
-template <bool HAS2>
-int launch_hop_z(dmlmc_hier* h, const Level& L, int p, const Z* Inq, const Z* In2, Z* Out, Cx<double> a, Cx<double> b, int k) {
-  StencilDev<double> op; op.LX = L.LX; op.LT = L.LT; op.Ut = L.d.Ut; op.Ux = L.d.Ux; op.diag = L.d.diag;
-  int bx = 1; while (bx < 32 && bx < k) bx *= 2;
-  dim3 blk(bx, 4, 2), grd((k + bx - 1) / bx, (L.LT / 2 + 3) / 4, (L.LX + 1) / 2);
-  wilson_hop_eo_z_kernel<HAS2><<<grd, blk, 0, h->stream>>>(op, p, Inq, In2, Out, a, b, k);
+template <typename T, bool HAS2>
+int launch_hop_z(dmlmc_hier* h, const Level& L, int p, const Cx<T>* Inq, const Cx<T>* In2, Cx<T>* Out, Cx<double> a, Cx<double> b, int k) {
+  StencilDev<T> op; op.LX = L.LX; op.LT = L.LT; op.diag = cx<T>((T)L.d.diag.re, (T)L.d.diag.im);
+  if constexpr (std::is_same<T, double>::value) { op.Ut = L.d.Ut; op.Ux = L.d.Ux; } else { op.Ut = L.f.Ut; op.Ux = L.f.Ux; }
+  constexpr int NC = std::is_same<T, double>::value ? 1 : 2;       // complex64: two columns per thread (k is even on this path)
+  const int kp = k / NC;
+  int bx = 1; while (bx < 32 && bx < kp) bx *= 2;
+  dim3 blk(bx, 4, 2), grd((kp + bx - 1) / bx, (L.LT / 2 + 3) / 4, (L.LX + 1) / 2);
+  wilson_hop_eo_z_kernel<T, NC, HAS2><<<grd, blk, 0, h->stream>>>(op, p, Inq, In2, Out, cx<T>((T)a.re, (T)a.im), cx<T>((T)b.re, (T)b.im), kp);
   LAUNCH_CHECK(h);
   return 0;
 }
@@ -1059,20 +1064,32 @@ bool outer_eo_ok(dmlmc_hier* h, int level, int k) {
   return hv->inner_prec == DMLMC_C64 && smoother_dout_ok(hv, pl, k) && smoother_eo_ok(hv, pl, k) && !hv->pre_smooth &&
          chunk_cols(hv, pl, k, sizeof(Cx<float>)) >= k;
 }
-int fgmres_eo(dmlmc_hier* h, int level, const Z* B, Z* X, int k, double tol, int restart, int maxiter,
-              int32_t* iters_host, double* relres_host) {
+// VT = double: every Krylov vector complex128.  VT = float (option outer_c64, the default): V_j, Z_j and w are STORED in complex64
+// -- Gram-Schmidt, the normalisation, S z_j and the solution update move half the bytes again -- while the coefficients are
+// accumulated in FP64 and x_e, b^_e and the true residual r = b^_e - S x_e stay complex128.  The Arnoldi relation then holds to
+// ~1e-7 of the cycle's starting residual only, so a cycle stops once its estimate has dropped by `outer_drop` (1e-5) and the next
+// starts from the true residual: iterative refinement with FGMRES as the inner solver.  CPU experiment
+// (profiles/exp_mixed_precision_ir.py): the same 8 preconditioner applications to 1e-12 in 2-3 cycles.
+template <typename VT>
+int fgmres_eo_t(dmlmc_hier* h, int level, const Z* B, Z* X, int k, double tol, int restart, int maxiter,
+                int32_t* iters_host, double* relres_host) {
+  typedef Cx<VT> C;
+  constexpr bool MIXED = std::is_same<VT, float>::value;
   Level& L = h->lv[level];
   dmlmc_hier* hv = h->prec_hier[level] ? h->prec_hier[level] : h;
   const int n = L.n, nh = n / 2, m = restart;
   const size_t nk = (size_t)n * k, nkh = (size_t)nh * k;
   const double c = L.d.diag.re;
   const Cx<double> ONE = {1.0, 0.0}, CC = {c, 0.0}, NIC = {-1.0 / c, 0.0}, IC = {1.0 / c, 0.0};
+  const double drop = MIXED ? h->outer_drop : 0.0;
   WsScope ws_scope(h); const size_t mark = ws_scope.mark;
   GmresState s; s.k = k; s.m = m;
-  Z *Vb, *Zb, *W, *Wo, *Rb, *Be, *Bo, *Bhat, *Xe, *Xo, *partial;
-  RET(ws_get<Z>(h, nkh * (m + 1), &Vb));
-  RET(ws_get<Z>(h, nkh * m, &Zb));
-  RET(ws_get<Z>(h, nkh, &W)); RET(ws_get<Z>(h, nkh, &Wo)); RET(ws_get<Z>(h, nkh, &Rb));
+  C *Vb, *Zb, *W, *Wv;
+  Z *Wo, *Wd, *Rb, *Be, *Bo, *Bhat, *Xe, *Xo, *partial;
+  RET(ws_get<C>(h, nkh * (m + 1), &Vb));
+  RET(ws_get<C>(h, nkh * m, &Zb));
+  RET(ws_get<C>(h, nkh, &W)); RET(ws_get<C>(h, nkh, &Wv));
+  RET(ws_get<Z>(h, nkh, &Wo)); RET(ws_get<Z>(h, nkh, &Wd)); RET(ws_get<Z>(h, nkh, &Rb));
   RET(ws_get<Z>(h, nkh, &Be)); RET(ws_get<Z>(h, nkh, &Bo)); RET(ws_get<Z>(h, nkh, &Bhat));
   RET(ws_get<Z>(h, nkh, &Xe)); RET(ws_get<Z>(h, nkh, &Xo));
   RET(ws_get<Z>(h, partial_count(n, m + 1, k), &partial));
@@ -1086,6 +1103,7 @@ int fgmres_eo(dmlmc_hier* h, int level, const Z* B, Z* X, int k, double tol, int
   RET(ws_get<double>(h, (size_t)k, &s.normb));
   RET(ws_get<double>(h, (size_t)k, &s.scale));
   RET(ws_get<double>(h, (size_t)k, &s.relres));
+  RET(ws_get<double>(h, (size_t)k, &s.tolc));
   RET(ws_get<int>(h, (size_t)k, &s.active));
   RET(ws_get<int>(h, (size_t)k, &s.done));
   RET(ws_get<int>(h, (size_t)k, &s.it_cycle));
@@ -1099,54 +1117,65 @@ int fgmres_eo(dmlmc_hier* h, int level, const Z* B, Z* X, int k, double tol, int
   RET(multi_dot(h, B, 0, 1, B, n, k, partial, s.nrm2, 0));
   set_normb_kernel<<<gk, 128, 0, h->stream>>>(s.nrm2, s.normb, k); LAUNCH_CHECK(h);
   eo_split_merge_kernel<<<nblocks(nk, 256), 256, 0, h->stream>>>(L.LX, L.LT, k, 0, const_cast<Z*>(B), Be, Bo); LAUNCH_CHECK(h);
-  RET((launch_hop_z<true>(h, L, 0, Bo, Be, Bhat, ONE, NIC, k)));
+  RET((launch_hop_z<double, true>(h, L, 0, Bo, Be, Bhat, ONE, NIC, k)));
   CU(cudaMemsetAsync(Xe, 0, nkh * sizeof(Z), h->stream));
   const Z* Rsrc = Bhat;
-  const int expect = (h->expect_tol[level] == tol && h->expect_k[level] == k) ? h->expect_it[level] : 0;
-  int total_it = 0, nact = 0, mode = 3;
+  // Host polls (a blocking read of the active-column count) only where the previous solve of the same shape ended a cycle: its
+  // iteration counts per cycle are the expectation; a stale one costs wasted iterations on finished (zeroed) columns, not errors
+  const bool have_exp = h->adaptive_poll && h->expect_tol[level] == tol && h->expect_k[level] == k && !h->expect_cyc[level].empty();
+  const std::vector<int> exp_cyc = have_exp ? h->expect_cyc[level] : std::vector<int>();
+  std::vector<int> cyc_len;
+  int total_it = 0, nact = 0, mode = 3, cycles = 0;
   while (true) {
     RET(multi_dot(h, Rsrc, 0, 1, Rsrc, nh, k, partial, s.nrm2, 0));
     CU(cudaMemsetAsync(s.n_active, 0, sizeof(int), h->stream));
-    gmres_init_kernel<<<nblocks(k, 256), 256, 0, h->stream>>>(s, tol, mode); LAUNCH_CHECK(h);
+    gmres_init_kernel<<<nblocks(k, 256), 256, 0, h->stream>>>(s, tol, mode, drop); LAUNCH_CHECK(h);
     mode = 2;
-    RET(read_nactive(h, s.n_active, &nact));
-    if (nact == 0 || total_it >= maxiter) { h->unconverged += nact; break; }
-    col_scale_eo_kernel<<<nblocks(nkh, 256), 256, 0, h->stream>>>(L.LX, L.LT, Rsrc, s.scale, Vb, k, V32); LAUNCH_CHECK(h);
+    if (!have_exp || cycles >= (int)exp_cyc.size() || total_it >= maxiter) {
+      RET(read_nactive(h, s.n_active, &nact));
+      if (nact == 0 || total_it >= maxiter) { h->unconverged += nact; break; }
+    }
+    const int this_exp = (have_exp && cycles < (int)exp_cyc.size()) ? exp_cyc[cycles] : 1;
+    col_scale_eo_kernel<double, VT><<<nblocks(nkh, 256), 256, 0, h->stream>>>(L.LX, L.LT, Rsrc, s.scale, Vb, k, V32); LAUNCH_CHECK(h);
     int j = 0;
     for (; j < m; ++j) {
-      Z* Vj = Vb + (size_t)j * nkh;
-      Z* Zj = Zb + (size_t)j * nkh;
+      C* Vj = Vb + (size_t)j * nkh;
+      C* Zj = Zb + (size_t)j * nkh;
       auto body = [&]() -> int {
-        hv->eo_zhalf = 1;
-        const int rcp = precond(h, level, Vj, Zj, k, V32);         // Z_j = even part of M^{-1} (v_e, 0), half-lattice layout
+        hv->eo_zhalf = MIXED ? 2 : 1;
+        const int rcp = precond(h, level, reinterpret_cast<const Z*>(Vj), reinterpret_cast<Z*>(Zj), k, V32);   // Z_j = even part of M^{-1} (v_e, 0), half-lattice layout
         hv->eo_zhalf = 0;
         RET(rcp);
-        RET((launch_hop_z<false>(h, L, 1, Zj, nullptr, Wo, ONE, ONE, k)));        // w_o = H_oe z
-        RET((launch_hop_z<true>(h, L, 0, Wo, Zj, W, CC, NIC, k)));                // w = c z - H_eo w_o / c
-        RET(multi_dot(h, Vb, nkh, j + 1, W, nh, k, partial, s.hsum, 0));
-        RET(multi_axpy_norm(h, Vb, nkh, j + 1, s.hsum, W, nh, k, partial, s.nrm2));
+        RET((launch_hop_z<VT, false>(h, L, 1, Zj, nullptr, Wv, ONE, ONE, k)));        // w_o = H_oe z
+        RET((launch_hop_z<VT, true>(h, L, 0, Wv, Zj, W, CC, NIC, k)));                // w = c z - H_eo w_o / c
+        RET((multi_dot<VT, VT>(h, Vb, nkh, j + 1, W, nh, k, partial, s.hsum, 0)));
+        RET((multi_axpy_norm<VT>(h, Vb, nkh, j + 1, s.hsum, W, nh, k, partial, s.nrm2)));
         CU(cudaMemsetAsync(s.n_active, 0, sizeof(int), h->stream));
         gmres_step_kernel<<<gk, 128, 0, h->stream>>>(s, j, tol); LAUNCH_CHECK(h);
-        if (j + 1 < m) { col_scale_eo_kernel<<<nblocks(nkh, 256), 256, 0, h->stream>>>(L.LX, L.LT, W, s.scale, Vb + (size_t)(j + 1) * nkh, k, V32); LAUNCH_CHECK(h); }
+        if (j + 1 < m) { col_scale_eo_kernel<VT, VT><<<nblocks(nkh, 256), 256, 0, h->stream>>>(L.LX, L.LT, W, s.scale, Vb + (size_t)(j + 1) * nkh, k, V32); LAUNCH_CHECK(h); }
         return 0;
       };
-      RET(run_iteration(h, h->use_graphs && k <= h->graph_max_k, level + 64, k, mark, j, m, tol, body));
+      // (the kernel arguments of iteration j are the same in every cycle: one graph per j serves all cycles)
+      RET(run_iteration(h, h->use_graphs && k <= h->graph_max_k, level + 64 + (MIXED ? 64 : 0), k, mark, j, m, tol, body));
       ++total_it;
-      if (!h->adaptive_poll || total_it + 1 >= expect || (total_it & 3) == 0 || j + 1 == m || total_it >= maxiter)
-        RET(read_nactive(h, s.n_active, &nact));
+      if (j + 1 >= this_exp || j + 1 == m || total_it >= maxiter) RET(read_nactive(h, s.n_active, &nact));
+      else nact = 1;
       if (nact == 0 || total_it >= maxiter) { ++j; break; }
     }
     const int steps = std::min(j, m);
+    cyc_len.push_back(steps);
     gmres_solve_kernel<<<gk, 128, 0, h->stream>>>(s, steps); LAUNCH_CHECK(h);
-    RET(multi_axpy(h, Zb, nkh, steps, s.y, Xe, nh, k, +1.0));
+    RET((multi_axpy<VT>(h, Zb, nkh, steps, s.y, Xe, nh, k, +1.0)));
     // true residual of the Schur system (= the residual of the full system, whose odd part is zero by construction)
-    RET((launch_hop_z<false>(h, L, 1, Xe, nullptr, Wo, ONE, ONE, k)));
-    RET((launch_hop_z<true>(h, L, 0, Wo, Xe, W, CC, NIC, k)));
-    vec_sub_kernel<<<nblocks(nkh, 256), 256, 0, h->stream>>>(Bhat, W, Rb, nkh); LAUNCH_CHECK(h);
+    RET((launch_hop_z<double, false>(h, L, 1, Xe, nullptr, Wo, ONE, ONE, k)));
+    RET((launch_hop_z<double, true>(h, L, 0, Wo, Xe, Wd, CC, NIC, k)));
+    vec_sub_kernel<<<nblocks(nkh, 256), 256, 0, h->stream>>>(Bhat, Wd, Rb, nkh); LAUNCH_CHECK(h);
     Rsrc = Rb;
+    ++cycles;
   }
+  h->expect_cyc[level] = cyc_len;
   // x_o = (b_o - H_oe x_e) / c, then the full-lattice layout
-  RET((launch_hop_z<true>(h, L, 1, Xe, Bo, Xo, IC, NIC, k)));
+  RET((launch_hop_z<double, true>(h, L, 1, Xe, Bo, Xo, IC, NIC, k)));
   eo_split_merge_kernel<<<nblocks(nk, 256), 256, 0, h->stream>>>(L.LX, L.LT, k, 1, X, Xe, Xo); LAUNCH_CHECK(h);
   h->expect_it[level] = total_it; h->expect_tol[level] = tol; h->expect_k[level] = k;
   if (iters_host) CU(cudaMemcpyAsync(iters_host, s.it_total, sizeof(int) * k, cudaMemcpyDeviceToHost, h->stream));
@@ -1154,6 +1183,11 @@ int fgmres_eo(dmlmc_hier* h, int level, const Z* B, Z* X, int k, double tol, int
   if (iters_host || relres_host) CU(cudaStreamSynchronize(h->stream));
   h->ws_off = mark;
   return 0;
+}
+int fgmres_eo(dmlmc_hier* h, int level, const Z* B, Z* X, int k, double tol, int restart, int maxiter,
+              int32_t* iters_host, double* relres_host) {
+  if (h->outer_c64 && (k % 2) == 0) return fgmres_eo_t<float>(h, level, B, X, k, tol, restart, maxiter, iters_host, relres_host);
+  return fgmres_eo_t<double>(h, level, B, X, k, tol, restart, maxiter, iters_host, relres_host);
 }
 
 int apply_perm(dmlmc_hier* h, int level, const Z* X, Z* Y, int k) {
@@ -1780,6 +1814,8 @@ int dmlmc_set_option(dmlmc_hier* h, const char* name, double value) {
   if (h) invalidate_graphs(h);
   CHECK(h != nullptr && name != nullptr, "set_option: bad arguments");
   if (std::strcmp(name, "outer_eo") == 0) { h->outer_eo = value != 0.0; return 0; }
+  if (std::strcmp(name, "outer_c64") == 0) { h->outer_c64 = value != 0.0; return 0; }
+  if (std::strcmp(name, "outer_drop") == 0) { h->outer_drop = value; return 0; }
   if (std::strcmp(name, "mt_jump") == 0) { h->mt_jump = value != 0.0; return 0; }
   if (std::strcmp(name, "precond_smoother_only") == 0) { h->smoother_only = value != 0.0; return 0; }
   if (std::strcmp(name, "smoother_eo") == 0) { h->smoother_eo = value != 0.0; return 0; }

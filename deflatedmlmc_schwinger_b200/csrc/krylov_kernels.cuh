@@ -33,9 +33,11 @@ constexpr int DOT_TX = 32, DOT_TY = 8;
 // VT = float (option dot32, OFF): the V_i are read from complex64 copies (arithmetic stays complex128) for the Gram-Schmidt
 // coefficients only.  Half the bytes of the pass, but the basis then loses orthogonality at the 1e-7 level and a GMRES
 // cycle stagnates near that relative residual: measured 43 outer iterations instead of 8 -- kept as a recorded negative.
-template <typename VT>
+// WT: scalar of W (float: the complex64-stored Krylov vectors of the mixed-precision Schur-complement solve; the products are
+// accumulated in FP64 either way).
+template <typename VT, typename WT = double>
 __global__ void __launch_bounds__(256)
-multi_dot_kernel(const Cx<VT>* __restrict__ Vbase, size_t vstride, int nv, const Z* __restrict__ W,
+multi_dot_kernel(const Cx<VT>* __restrict__ Vbase, size_t vstride, int nv, const Cx<WT>* __restrict__ W,
                  int n, int k, int rows_per_chunk, Z* __restrict__ partial) {
   __shared__ Z red[DOT_TY][DOT_NI][DOT_TX + 1];
   const int tx = threadIdx.x, ty = threadIdx.y;
@@ -50,7 +52,8 @@ multi_dot_kernel(const Cx<VT>* __restrict__ Vbase, size_t vstride, int nv, const
     if (ok) {
       for (int r = r0 + ty; r < r1; r += DOT_TY) {
         const size_t off = (size_t)r * k + col;
-        const Z w = ldc_ro<double>(W, off);
+        const Cx<WT> w_ = ldc_ro<WT>(W, off);
+        const Z w = cx<double>((double)w_.re, (double)w_.im);
 #pragma unroll
         for (int i = 0; i < DOT_NI; ++i)
           if (i0 + i < nv) {
@@ -93,14 +96,18 @@ sum_partials_kernel(const Z* __restrict__ partial, int nchunks, int count, Z* __
 }
 
 // W[r][col] += sgn * sum_i h[i][col] * V_i[r][col]
+template <typename VT = double>
 __global__ void __launch_bounds__(256)
-multi_axpy_kernel(const Z* __restrict__ Vbase, size_t vstride, int nv, const Z* __restrict__ h,
+multi_axpy_kernel(const Cx<VT>* __restrict__ Vbase, size_t vstride, int nv, const Z* __restrict__ h,
                   Z* __restrict__ W, size_t nk, int k, double sgn) {
   const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= nk) return;
   const int col = (int)(idx % k);
   Z acc = cx<double>(0.0, 0.0);
-  for (int i = 0; i < nv; ++i) zfma(acc, ldc_ro<double>(h, (size_t)i * k + col), ldc_ro<double>(Vbase, (size_t)i * vstride + idx));
+  for (int i = 0; i < nv; ++i) {
+    const Cx<VT> v = ldc_ro<VT>(Vbase, (size_t)i * vstride + idx);
+    zfma(acc, ldc_ro<double>(h, (size_t)i * k + col), cx<double>((double)v.re, (double)v.im));
+  }
   Z w = W[idx];
   w.re = fma(sgn, acc.re, w.re);
   w.im = fma(sgn, acc.im, w.im);
@@ -110,9 +117,10 @@ multi_axpy_kernel(const Z* __restrict__ Vbase, size_t vstride, int nv, const Z* 
 // Gram-Schmidt update fused with the norm of its result:
 //   W[r][col] -= sum_i h[i][col] V_i[r][col];   partial[chunk][col] = sum_{r in chunk} |W[r][col]|^2   (as a complex, im = 0)
 // same (32, 8) x row-chunk decomposition as multi_dot_kernel, so the norm is deterministic and needs no extra pass over W.
+template <typename VT = double>
 __global__ void __launch_bounds__(256)
-multi_axpy_norm_kernel(const Z* __restrict__ Vbase, size_t vstride, int nv, const Z* __restrict__ h,
-                       Z* __restrict__ W, int n, int k, int rows_per_chunk, Z* __restrict__ partial) {
+multi_axpy_norm_kernel(const Cx<VT>* __restrict__ Vbase, size_t vstride, int nv, const Z* __restrict__ h,
+                       Cx<VT>* __restrict__ W, int n, int k, int rows_per_chunk, Z* __restrict__ partial) {
   __shared__ double red[DOT_TY][DOT_TX + 1];
   const int tx = threadIdx.x, ty = threadIdx.y;
   const int col = blockIdx.x * DOT_TX + tx;
@@ -123,10 +131,15 @@ multi_axpy_norm_kernel(const Z* __restrict__ Vbase, size_t vstride, int nv, cons
     for (int r = r0 + ty; r < r1; r += DOT_TY) {
       const size_t off = (size_t)r * k + col;
       Z acc = cx<double>(0.0, 0.0);
-      for (int i = 0; i < nv; ++i) zfma(acc, ldc_ro<double>(h, (size_t)i * k + col), ldc_ro<double>(Vbase, (size_t)i * vstride + off));
-      Z w = W[off];
-      w.re -= acc.re; w.im -= acc.im;
-      W[off] = w;
+      for (int i = 0; i < nv; ++i) {
+        const Cx<VT> v = ldc_ro<VT>(Vbase, (size_t)i * vstride + off);
+        zfma(acc, ldc_ro<double>(h, (size_t)i * k + col), cx<double>((double)v.re, (double)v.im));
+      }
+      const Cx<VT> w0 = W[off];
+      // the norm is that of the STORED vector (what the next basis vector is made from)
+      const Cx<VT> ws = cx<VT>((VT)((double)w0.re - acc.re), (VT)((double)w0.im - acc.im));
+      W[off] = ws;
+      const Z w = cx<double>((double)ws.re, (double)ws.im);
       sq = fma(w.re, w.re, fma(w.im, w.im, sq));
     }
   }
@@ -328,6 +341,7 @@ struct GmresState {
   double* normb;       // [k]
   double* scale;       // [k]
   double* relres;      // [k]
+  double* tolc;        // [k]         the Arnoldi estimate at which the column's current cycle stops (>= tol)
   int* active;         // [k]
   int* done;           // [k]
   int* it_cycle;       // [k]
@@ -340,8 +354,10 @@ struct GmresState {
 //   mode 2 (later cycles): r is the TRUE residual b - A x of every column, so this is also the
 //   verification of the columns that stopped on the Arnoldi estimate: a column is finished iff its
 //   true relative residual is below tol (with a rounding allowance), otherwise it iterates on.
+// drop > 0 (mixed-precision refinement): a cycle only runs until the estimate has fallen by that factor relative to the
+// residual it started from -- what the complex64-stored basis can resolve -- and the next cycle restarts from the true residual.
 __global__ void __launch_bounds__(256)
-gmres_init_kernel(GmresState s, double tol, int mode) {
+gmres_init_kernel(GmresState s, double tol, int mode, double drop = 0.0) {
   const int col = blockIdx.x * blockDim.x + threadIdx.x;
   if (col >= s.k) return;
   const double nr = sqrt(fmax(s.nrm2[col].re, 0.0));
@@ -357,6 +373,7 @@ gmres_init_kernel(GmresState s, double tol, int mode) {
   const double rel = nr / s.normb[col];
   s.it_cycle[col] = 0;
   s.relres[col] = rel;
+  s.tolc[col] = fmax(tol, drop * rel);
   const int act = (rel < accept || nr == 0.0) ? 0 : 1;
   s.done[col] = !act;
   s.active[col] = act;
@@ -408,7 +425,7 @@ gmres_step_kernel(GmresState s, int j, double tol) {
   s.relres[col] = rel;
   s.it_cycle[col] = j + 1;
   s.it_total[col] += 1;
-  if (rel < tol) {
+  if (rel < s.tolc[col]) {
     s.active[col] = 0; s.done[col] = 1; s.scale[col] = 0.0;
   } else {
     s.scale[col] = (hn > 0.0) ? 1.0 / hn : 0.0;

@@ -356,7 +356,7 @@ template <bool HAS2, bool HOUT, bool ZOUT, int NP>
 __global__ void __launch_bounds__(256, NP == 2 ? 2 : 3)
 wilson_hop_eo_kernel(int LX, int LT, int p, const float4* __restrict__ L4, const uint2* __restrict__ Inq,
                      const uint2* __restrict__ In2, uint2* __restrict__ Outp, float ar, float ai, float br, float bi,
-                     uint32_t kp, const Pack<float, 2>* __restrict__ Xc, double2* __restrict__ Z, int zhalf) {   // zhalf: Z is a half-lattice array
+                     uint32_t kp, const Pack<float, 2>* __restrict__ Xc, double2* __restrict__ Z, int zhalf) {   // zhalf: 1 = Z is a half-lattice complex128 array, 2 = complex64
   const uint32_t cp = (blockIdx.x * blockDim.x + threadIdx.x) * NP;
   const uint32_t th = blockIdx.y * blockDim.y + threadIdx.y;
   const uint32_t x = blockIdx.z * blockDim.z + threadIdx.z;
@@ -419,30 +419,44 @@ wilson_hop_eo_kernel(int LX, int LT, int p, const float4* __restrict__ L4, const
   if constexpr (HOUT) { sth_packs<NP>(Outp + ic, o0); sth_packs<NP>(Outp + ic + sp, o1); }
   if constexpr (ZOUT) {
     const size_t j0 = (size_t)site * kpz + cp, j1 = ((size_t)V + site) * kpz + cp;     // full-lattice rows of the site
-    const size_t z0 = zhalf ? ic : j0, z1 = zhalf ? ic + sp : j1;
+    if (zhalf == 2) {
+      // complex64 half-lattice output (the Z_j of the mixed-precision Schur-complement solve)
+      Pack<float, 2>* Zf = reinterpret_cast<Pack<float, 2>*>(Z);
 #pragma unroll
-    for (int u = 0; u < NP; ++u) {
-      const Pack<float, 2> e0 = Xc[j0 + u], e1 = Xc[j1 + u];
-      Z[2 * (z0 + u)]     = make_double2((double)e0.d[0] + (double)o0[u].re.x, (double)e0.d[1] + (double)o0[u].im.x);
-      Z[2 * (z0 + u) + 1] = make_double2((double)e0.d[2] + (double)o0[u].re.y, (double)e0.d[3] + (double)o0[u].im.y);
-      Z[2 * (z1 + u)]     = make_double2((double)e1.d[0] + (double)o1[u].re.x, (double)e1.d[1] + (double)o1[u].im.x);
-      Z[2 * (z1 + u) + 1] = make_double2((double)e1.d[2] + (double)o1[u].re.y, (double)e1.d[3] + (double)o1[u].im.y);
+      for (int u = 0; u < NP; ++u) {
+        const Pack<float, 2> e0 = Xc[j0 + u], e1 = Xc[j1 + u];
+        Pack<float, 2> q0, q1;
+        q0.d[0] = e0.d[0] + o0[u].re.x; q0.d[1] = e0.d[1] + o0[u].im.x; q0.d[2] = e0.d[2] + o0[u].re.y; q0.d[3] = e0.d[3] + o0[u].im.y;
+        q1.d[0] = e1.d[0] + o1[u].re.x; q1.d[1] = e1.d[1] + o1[u].im.x; q1.d[2] = e1.d[2] + o1[u].re.y; q1.d[3] = e1.d[3] + o1[u].im.y;
+        Zf[ic + u] = q0; Zf[ic + sp + u] = q1;
+      }
+    } else {
+      const size_t z0 = zhalf ? ic : j0, z1 = zhalf ? ic + sp : j1;
+#pragma unroll
+      for (int u = 0; u < NP; ++u) {
+        const Pack<float, 2> e0 = Xc[j0 + u], e1 = Xc[j1 + u];
+        Z[2 * (z0 + u)]     = make_double2((double)e0.d[0] + (double)o0[u].re.x, (double)e0.d[1] + (double)o0[u].im.x);
+        Z[2 * (z0 + u) + 1] = make_double2((double)e0.d[2] + (double)o0[u].re.y, (double)e0.d[3] + (double)o0[u].im.y);
+        Z[2 * (z1 + u)]     = make_double2((double)e1.d[0] + (double)o1[u].re.x, (double)e1.d[1] + (double)o1[u].im.x);
+        Z[2 * (z1 + u) + 1] = make_double2((double)e1.d[2] + (double)o1[u].re.y, (double)e1.d[3] + (double)o1[u].im.y);
+      }
     }
   }
 }
 
-// ---- complex128 sweeps on checkerboard half-lattice vectors [s][x][t/2][k] (the outer solve on the Schur complement) ----
-//   Out_p[site] = a * In2_p[site] + b * (H In_q)[site]      (same conventions as wilson_hop_eo_kernel, one column per thread)
-template <bool HAS2>
+// ---- sweeps on checkerboard half-lattice vectors [s][x][t/2][k] in the outer solver's own precision (the outer solve on the
+// even-odd Schur complement): complex128, or complex64 (two columns per thread) for the complex64-stored Krylov vectors of the
+// mixed-precision refinement.   Out_p[site] = a * In2_p[site] + b * (H In_q)[site]   (same conventions as wilson_hop_eo_kernel)
+template <typename T, int NC, bool HAS2>
 __global__ void __launch_bounds__(256)
-wilson_hop_eo_z_kernel(StencilDev<double> op, int p, const Cx<double>* __restrict__ Inq, const Cx<double>* __restrict__ In2,
-                       Cx<double>* __restrict__ Outp, Cx<double> a, Cx<double> b, int k) {
-  typedef Pack<double, 1> P;
+wilson_hop_eo_z_kernel(StencilDev<T> op, int p, const Cx<T>* __restrict__ Inq, const Cx<T>* __restrict__ In2,
+                       Cx<T>* __restrict__ Outp, Cx<T> a, Cx<T> b, int kp) {    // kp = packs of NC columns per row
+  typedef Pack<T, NC> P;
   const int col = blockIdx.x * blockDim.x + threadIdx.x;
   const int th = blockIdx.y * blockDim.y + threadIdx.y;
   const int x = blockIdx.z * blockDim.z + threadIdx.z;
   const int LX = op.LX, LT = op.LT, LH = LT >> 1;
-  if (col >= k || th >= LH || x >= LX) return;
+  if (col >= kp || th >= LH || x >= LX) return;
   const int off = (x + p) & 1;
   const int t = 2 * th + off;
   const int site = x * LT + t;
@@ -450,32 +464,32 @@ wilson_hop_eo_z_kernel(StencilDev<double> op, int p, const Cx<double>* __restric
   const int xp = (x + 1 == LX) ? 0 : x + 1, xm = (x == 0) ? LX - 1 : x - 1;
   const int th_f = off ? ((th + 1 == LH) ? 0 : th + 1) : th;
   const int th_b = off ? th : ((th == 0) ? LH - 1 : th - 1);
-  const Cx<double> ut = ldc_ro<double>(op.Ut, site), utb = cconj(ldc_ro<double>(op.Ut, x * LT + tm));
-  const Cx<double> ux = ldc_ro<double>(op.Ux, site), uxb = cconj(ldc_ro<double>(op.Ux, xm * LT + t));
-  const size_t kz = (size_t)k, sp = (size_t)(LX * LH) * kz;
+  const Cx<T> ut = ldc_ro<T>(op.Ut, site), utb = cconj(ldc_ro<T>(op.Ut, x * LT + tm));
+  const Cx<T> ux = ldc_ro<T>(op.Ux, site), uxb = cconj(ldc_ro<T>(op.Ux, xm * LT + t));
+  const size_t kz = (size_t)kp, sp = (size_t)(LX * LH) * kz;
   const P* Q = reinterpret_cast<const P*>(Inq);
   const size_t i_f = ((size_t)x * LH + th_f) * kz + col, i_b = ((size_t)x * LH + th_b) * kz + col;
   const size_t i_r = ((size_t)xp * LH + th) * kz + col,  i_l = ((size_t)xm * LH + th) * kz + col;
-  const P f0 = ldp_ro<double, 1>(Q, i_f), f1 = ldp_ro<double, 1>(Q, i_f + sp);
-  const P b0 = ldp_ro<double, 1>(Q, i_b), b1 = ldp_ro<double, 1>(Q, i_b + sp);
-  const P r0 = ldp_ro<double, 1>(Q, i_r), r1 = ldp_ro<double, 1>(Q, i_r + sp);
-  const P l0 = ldp_ro<double, 1>(Q, i_l), l1 = ldp_ro<double, 1>(Q, i_l + sp);
-  const P pa = psub<double, 1>(f0, f1);
-  const P pb = padd<double, 1>(b0, b1);
-  const P pc = padd<double, 1>(r0, pmul_i<double, 1>(r1));
-  const P pd = psub<double, 1>(l0, pmul_i<double, 1>(l1));
-  const P ua = pscale<double, 1>(ut, pa), ub = pscale<double, 1>(utb, pb);
-  const P uc = pscale<double, 1>(ux, pc), ud = pscale<double, 1>(uxb, pd);
+  const P f0 = ldp_ro<T, NC>(Q, i_f), f1 = ldp_ro<T, NC>(Q, i_f + sp);
+  const P b0 = ldp_ro<T, NC>(Q, i_b), b1 = ldp_ro<T, NC>(Q, i_b + sp);
+  const P r0 = ldp_ro<T, NC>(Q, i_r), r1 = ldp_ro<T, NC>(Q, i_r + sp);
+  const P l0 = ldp_ro<T, NC>(Q, i_l), l1 = ldp_ro<T, NC>(Q, i_l + sp);
+  const P pa = psub<T, NC>(f0, f1);
+  const P pb = padd<T, NC>(b0, b1);
+  const P pc = padd<T, NC>(r0, pmul_i<T, NC>(r1));
+  const P pd = psub<T, NC>(l0, pmul_i<T, NC>(l1));
+  const P ua = pscale<T, NC>(ut, pa), ub = pscale<T, NC>(utb, pb);
+  const P uc = pscale<T, NC>(ux, pc), ud = pscale<T, NC>(uxb, pd);
   // (H v)_0 = -(ua + ub + uc + ud);  (H v)_1 = (ua - ub) + i (uc - ud)
-  P h0 = pzero<double, 1>();
-  h0 = psub<double, 1>(h0, padd<double, 1>(padd<double, 1>(ua, ub), padd<double, 1>(uc, ud)));
-  const P h1 = padd<double, 1>(psub<double, 1>(ua, ub), pmul_i<double, 1>(psub<double, 1>(uc, ud)));
-  P o0 = pscale<double, 1>(b, h0), o1 = pscale<double, 1>(b, h1);
+  P h0 = pzero<T, NC>();
+  h0 = psub<T, NC>(h0, padd<T, NC>(padd<T, NC>(ua, ub), padd<T, NC>(uc, ud)));
+  const P h1 = padd<T, NC>(psub<T, NC>(ua, ub), pmul_i<T, NC>(psub<T, NC>(uc, ud)));
+  P o0 = pscale<T, NC>(b, h0), o1 = pscale<T, NC>(b, h1);
   const size_t ic = ((size_t)x * LH + th) * kz + col;
   if constexpr (HAS2) {
     const P* C = reinterpret_cast<const P*>(In2);
-    pfma<double, 1>(o0, a, ldp_ro<double, 1>(C, ic));
-    pfma<double, 1>(o1, a, ldp_ro<double, 1>(C, ic + sp));
+    pfma<T, NC>(o0, a, ldp_ro<T, NC>(C, ic));
+    pfma<T, NC>(o1, a, ldp_ro<T, NC>(C, ic + sp));
   }
   P* O = reinterpret_cast<P*>(Outp);
   O[ic] = o0; O[ic + sp] = o1;
@@ -498,10 +512,12 @@ eo_split_merge_kernel(int LX, int LT, int k, int dir, Cx<double>* __restrict__ X
   if (dir == 0) Hh[hrow * k + col] = X[idx]; else X[idx] = Hh[hrow * k + col];
 }
 
-// Out[r][col] = In[r][col] * scale[col] on even-parity half-lattice vectors, and the same values as complex64 at the even
-// sites of the full-lattice array Out32 (whose odd sites stay zero): the V-cycle's input (v_e, 0)
+// Out[r][col] = In[r][col] * scale[col] on even-parity half-lattice vectors (In complex128 or complex64, Out in the Krylov
+// vectors' storage precision), and the same values as complex64 at the even sites of the full-lattice array Out32 (whose odd
+// sites stay zero): the V-cycle's input (v_e, 0)
+template <typename TI, typename TO>
 __global__ void __launch_bounds__(256)
-col_scale_eo_kernel(int LX, int LT, const Cx<double>* __restrict__ In, const double* __restrict__ scale, Cx<double>* __restrict__ Out,
+col_scale_eo_kernel(int LX, int LT, const Cx<TI>* __restrict__ In, const double* __restrict__ scale, Cx<TO>* __restrict__ Out,
                     int k, Cx<float>* __restrict__ Out32) {
   const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   const size_t nkh = (size_t)LX * LT * k;                  // 2 spins * V/2 sites
@@ -512,8 +528,8 @@ col_scale_eo_kernel(int LX, int LT, const Cx<double>* __restrict__ In, const dou
   const int x = r / LH, th = r - x * LH;
   const int t = 2 * th + (x & 1);
   const double sc = __ldg(scale + col);
-  const Cx<double> v = ldc_ro<double>(In, idx);
-  const Cx<double> o = cx<double>(v.re * sc, v.im * sc);
+  const Cx<TI> v = ldc_ro<TI>(In, idx);
+  const Cx<TO> o = cx<TO>((TO)((double)v.re * sc), (TO)((double)v.im * sc));
   Out[idx] = o;
   if (Out32 != nullptr) Out32[((size_t)s * (LX * LT) + (size_t)x * LT + t) * k + col] = cx<float>((float)o.re, (float)o.im);
 }
