@@ -34,6 +34,8 @@ _SIGS = {
     "dmlmc_set_coarsest_inverse": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p]),
     "dmlmc_set_dense_inverse": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_void_p]),
     "dmlmc_set_dense_inverse_device": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_void_p]),
+    "dmlmc_prolongator_values": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int,
+                                               ctypes.c_int, ctypes.c_void_p]),
     "dmlmc_set_dense_inverse_device_full": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_void_p]),
     "dmlmc_set_smoother": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_void_p,
                                           ctypes.c_double, ctypes.c_double]),
@@ -194,6 +196,16 @@ class Hierarchy:
     def set_dense_inverse(self, level, minv):
         minv, p = _host_c128(minv)
         _check(self.lib.dmlmc_set_dense_inverse(self.h, level, minv.shape[0], p))
+
+    def prolongator_values(self, eig_vecs, aggr_size, dofi, nvec):
+        """multigrid.py:232-259 on the device: eig_vecs numpy or torch complex128 [n, >= nvec] -> pvals torch [n, nvec]"""
+        torch = self.torch
+        ev = eig_vecs if torch.is_tensor(eig_vecs) else torch.from_numpy(np.ascontiguousarray(eig_vecs, dtype=np.complex128))
+        ev = ev.to(self.device).contiguous()
+        pv = torch.empty((ev.shape[0], nvec), dtype=torch.complex128, device=self.device)
+        _check(self.lib.dmlmc_prolongator_values(self.h, ctypes.c_void_p(ev.data_ptr()), int(ev.shape[1]), int(ev.shape[0]),
+                                                 int(aggr_size), int(dofi), int(nvec), ctypes.c_void_p(pv.data_ptr())))
+        return pv
 
     def set_dense_inverse_device(self, level, minv_dev, full=False):
         """minv_dev: torch complex128 CUDA tensor [n, n] (row-major inverse); full: keep it in all precisions (else only as

@@ -95,7 +95,7 @@ struct dmlmc_hier {
   int outer_eo = 1;                       // outer FGMRES of a stencil level on the even-odd Schur complement (fgmres_eo)
   int outer_c64 = 1;                      // ... with the Krylov vectors V_j, Z_j, w STORED in complex64 (coefficients, solution and true
                                           // residual in complex128; a cycle runs until its estimate has dropped by outer_drop)
-  double outer_drop = 1e-5;
+  double outer_drop = 1e-4;               // (measured, run r2_7: 1e-4 -> cycles of 3 + 3 + 2 iterations, 38.5k probes/s; 1e-5 / 1e-6 -> 8-9 iterations, 34.3k / 34.9k)
   std::vector<int> expect_cyc[MAX_LEVELS];   // iterations per cycle of the previous Schur-complement solve of (expect_tol, expect_k)
   int eo_zhalf = 0;                       // (internal) the even-odd smoother writes only Z_e, into a half-lattice array
   int smoother_eo = 1;                    // even-odd (Schur complement) form of the level-0 post-smoother when one is set
@@ -1067,7 +1067,7 @@ bool outer_eo_ok(dmlmc_hier* h, int level, int k) {
 // VT = double: every Krylov vector complex128.  VT = float (option outer_c64, the default): V_j, Z_j and w are STORED in complex64
 // -- Gram-Schmidt, the normalisation, S z_j and the solution update move half the bytes again -- while the coefficients are
 // accumulated in FP64 and x_e, b^_e and the true residual r = b^_e - S x_e stay complex128.  The Arnoldi relation then holds to
-// ~1e-7 of the cycle's starting residual only, so a cycle stops once its estimate has dropped by `outer_drop` (1e-5) and the next
+// ~1e-7 of the cycle's starting residual only, so a cycle stops once its estimate has dropped by `outer_drop` (1e-4) and the next
 // starts from the true residual: iterative refinement with FGMRES as the inner solver.  CPU experiment
 // (profiles/exp_mixed_precision_ir.py): the same 8 preconditioner applications to 1e-12 in 2-3 cycles.
 template <typename VT>
@@ -1526,6 +1526,21 @@ int dmlmc_set_dense_inverse_device(dmlmc_hier* h, int level, int n, const void* 
   L.n = n;
   RET(build_umma_operand(h, level, (const Cx<double>*)minv_dev));
   L.has_dense = true;
+  return 0;
+}
+
+int dmlmc_prolongator_values(dmlmc_hier* h, const void* eig_vecs_dev, int ld, int n, int aggr_size, int dofi, int nvec, void* pvals_dev) {
+  CHECK(h != nullptr, "NULL handle"); CU(cudaSetDevice(h->device));
+  CHECK(eig_vecs_dev && pvals_dev && n > 0 && nvec >= 1 && nvec <= 16 && ld >= nvec, "prolongator_values: bad arguments");
+  CHECK(dofi >= 2 && dofi % 2 == 0 && aggr_size % dofi == 0 && n % aggr_size == 0, "prolongator_values: inconsistent dof / aggregate size");
+  const int mrows = aggr_size / 2;
+  const size_t per_warp = (size_t)mrows * nvec * sizeof(double2);
+  CHECK(per_warp <= 48 * 1024, "prolongator_values: aggregate too large for one warp's shared memory");
+  int wpb = 4; while (wpb > 1 && wpb * per_warp > 48 * 1024) wpb /= 2;
+  const long long nitems = 2ll * (n / aggr_size);
+  prolongator_values_kernel<<<(unsigned)((nitems + wpb - 1) / wpb), 32 * wpb, wpb * per_warp, h->stream>>>(
+      (const Cx<double>*)eig_vecs_dev, ld, n, aggr_size, dofi, nvec, (Cx<double>*)pvals_dev);
+  LAUNCH_CHECK(h);
   return 0;
 }
 

@@ -1283,6 +1283,69 @@ cvt_cols_kernel(const Cx<Tin>* __restrict__ in, size_t ld_in, Cx<Tout>* __restri
   out[r * ld_out + c] = cx<Tout>((Tout)v.re, (Tout)v.im);
 }
 
+// ---- set-up: the values of the aggregation prolongator (multigrid.py:232-259) -----------------------------------------------
+// One warp per (aggregate, half): the nvec test-vector pieces on the half's rows (row q of the half = aggregate row
+// (q / hd) * dofi + q % hd + half * hd, hd = dofi / 2) are orthonormalised by CLASSICAL Gram-Schmidt exactly as the reference
+// does it -- the projections of column c on the finished columns w < c are all taken from the unmodified column, subtracted in
+// the order w = 0, 1, ..., then the column is divided by its norm -- in complex128.  Only the order of the additions inside an
+// inner product differs from numpy's (lanes, then a butterfly), i.e. the values agree with the host builder to ~1e-15.
+// ev: [n][ld] row-major (first nvec columns used), pv: [n][nvec].  Dynamic shared memory: warps_per_block * mrows * nvec complex.
+__global__ void __launch_bounds__(128)
+prolongator_values_kernel(const Cx<double>* __restrict__ ev, int ld, int n, int aggr_size, int dofi, int nvec,
+                          Cx<double>* __restrict__ pv) {
+  extern __shared__ double2 pvk_smem[];
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5, wpb = blockDim.x >> 5;
+  const long long item = (long long)blockIdx.x * wpb + wib;            // (aggregate, half)
+  const int hd = dofi / 2, mrows = aggr_size / 2;
+  const long long nitems = 2ll * (n / aggr_size);
+  if (item >= nitems) return;
+  const int half = (int)(item & 1);
+  const size_t base = (size_t)(item >> 1) * aggr_size;
+  double2* B = pvk_smem + (size_t)wib * mrows * nvec;                  // B[q * nvec + v]
+  for (int idx = lane; idx < mrows * nvec; idx += 32) {
+    const int q = idx / nvec, v = idx - q * nvec;
+    const size_t row = base + (size_t)(q / hd) * dofi + (q % hd) + half * hd;
+    const Cx<double> e = ev[row * ld + v];
+    B[idx] = make_double2(e.re, e.im);
+  }
+  __syncwarp();
+  for (int c = 0; c < nvec; ++c) {
+    // rs[w] = <col_w, col_c> for w < c, from the unmodified column c
+    double2 rs[16];
+    for (int w = 0; w < c; ++w) {
+      double sr = 0.0, si = 0.0;
+      for (int q = lane; q < mrows; q += 32) {
+        const double2 a = B[q * nvec + w], b = B[q * nvec + c];
+        sr += a.x * b.x + a.y * b.y;                                   // conj(a) * b
+        si += a.x * b.y - a.y * b.x;
+      }
+      for (int o = 16; o > 0; o >>= 1) { sr += __shfl_xor_sync(0xffffffffu, sr, o); si += __shfl_xor_sync(0xffffffffu, si, o); }
+      rs[w] = make_double2(sr, si);
+    }
+    for (int w = 0; w < c; ++w) {
+      for (int q = lane; q < mrows; q += 32) {
+        const double2 a = B[q * nvec + w];
+        double2 b = B[q * nvec + c];
+        b.x -= rs[w].x * a.x - rs[w].y * a.y;
+        b.y -= rs[w].x * a.y + rs[w].y * a.x;
+        B[q * nvec + c] = b;
+      }
+      __syncwarp();
+    }
+    double sq = 0.0;
+    for (int q = lane; q < mrows; q += 32) { const double2 b = B[q * nvec + c]; sq += b.x * b.x + b.y * b.y; }
+    for (int o = 16; o > 0; o >>= 1) sq += __shfl_xor_sync(0xffffffffu, sq, o);
+    const double nrm = sqrt(sq);
+    for (int q = lane; q < mrows; q += 32) { double2 b = B[q * nvec + c]; b.x /= nrm; b.y /= nrm; B[q * nvec + c] = b; }
+    __syncwarp();
+  }
+  for (int idx = lane; idx < mrows * nvec; idx += 32) {
+    const int q = idx / nvec, v = idx - q * nvec;
+    const size_t row = base + (size_t)(q / hd) * dofi + (q % hd) + half * hd;
+    pv[row * nvec + v] = cx<double>(B[idx].x, B[idx].y);
+  }
+}
+
 // the complex64 and the splatted (re, re, im, im) copies of a complex128 dense inverse (dmlmc_set_dense_inverse_device_full)
 __global__ void __launch_bounds__(256) dense_formats_kernel(const Cx<double>* __restrict__ M, size_t count, Cx<float>* __restrict__ F,
                                                             float4* __restrict__ F4) {

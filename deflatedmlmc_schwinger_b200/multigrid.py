@@ -558,7 +558,13 @@ class MG:
             aggr_size = aggrs[i] * dofi if i == 0 else aggrs[i] * dofi * 2
             if dofi < 2 or dofi % 2 or aggr_size % dofi or n % aggr_size or dofip1 < 1:
                 raise Exception("inconsistent dof/aggrs for level " + str(i))
-            pvals = build_prolongator_values(eig_vecs, aggr_size, dofi, dofip1)
+            if params.get('host_prolongator', False) or (aggr_size // 2) * dofip1 * 16 > 48 * 1024:
+                pvals = build_prolongator_values(eig_vecs, aggr_size, dofi, dofip1)      # bit-identical to the reference
+            else:
+                # the same classical Gram-Schmidt, all aggregates at once on the device (values agree to ~1e-15)
+                if getattr(self, "_setup_dev", None) is None:
+                    self._setup_dev = _lib.Hierarchy(1, self.device)
+                pvals = self._setup_dev.prolongator_values(eig_vecs, aggr_size, dofi, dofip1).cpu().numpy()
             Pl = prolongator_csr(pvals, aggr_size, dofi, dofip1)
             self._transfer_meta.append((aggr_size, dofi, dofip1, pvals))
             ml.levels[i].P = Pl
@@ -578,6 +584,9 @@ class MG:
                 Bl = (Rl * ml.levels[i].Bblock_perm) * Bl
                 ml.levels[i + 1].Bblock_perm = Bl
 
+        if getattr(self, "_setup_dev", None) is not None:
+            self._setup_dev.close()
+            self._setup_dev = None
         self.ml = ml
         self.coarsest_inv = np.linalg.inv(np.asarray(ml.levels[-1].A.todense()))
         self.level_shapes = [l.A.shape[0] for l in ml.levels]

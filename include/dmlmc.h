@@ -78,6 +78,13 @@ int dmlmc_set_dense_inverse(dmlmc_hier* h, int level, int n, const double* minv_
  * tensor-core operand is kept: BF16 [2n][2n], every complex entry as the real block [[re,-im],[im,re]],
  * applied by the tcgen05 kernel with FP32 accumulation.  Such a level serves the complex64 V-cycle only. */
 int dmlmc_set_dense_inverse_device(dmlmc_hier* h, int level, int n, const void* minv_dev);
+/* Set-up, multigrid.py:232-259: the values of the aggregation prolongator P_l from the test vectors, on the device.
+ * eig_vecs_dev: complex128 [n][ld] row-major (the first nvec columns are the test vectors), pvals_dev: complex128 [n][nvec].
+ * Every (aggregate, half) block -- aggr_size / 2 rows, closed-form row map of multigrid.py:203-227 -- is orthonormalised by
+ * classical Gram-Schmidt in the reference's order of operations (one warp per block); agreement with the host builder
+ * (which is bit-identical to the reference) ~1e-15, the summation order inside an inner product being the only difference. */
+int dmlmc_prolongator_values(dmlmc_hier* h, const void* eig_vecs_dev, int ld, int n, int aggr_size, int dofi, int nvec,
+                             void* pvals_dev);
 /* The same hand-over for an inverse kept in ALL precisions (what dmlmc_set_dense_inverse makes from a host array: the
  * complex128 and complex64 copies, the splatted FP32 operand and the tensor-core operands), from a complex128 device
  * array [n][n] -- the inverse never visits the host (multigrid.py:342-344 of the reference inverts on the host). */
