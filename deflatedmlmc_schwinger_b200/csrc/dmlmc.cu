@@ -7,6 +7,7 @@
 #include "op_kernels.cuh"
 #include "krylov_kernels.cuh"
 #include "dense_umma.cuh"
+#include "hop_tma.cuh"
 
 #include <algorithm>
 #include <cstdio>
@@ -121,6 +122,9 @@ struct dmlmc_hier {
   uint32_t* mt_tab = nullptr; int mt_tab_rows = 0;    // jump polynomials t^(2^b) mod phi (dmlmc_set_mt_jump_table)
   uint32_t* mt_state_out = nullptr;                   // [625] state written by the jump kernel, copied over the caller's afterwards
   int mt_jump = 1;                                    // option: 0 = the sequential one-CTA generator
+  int hop_tma = 1;                                    // option: the even-odd sweeps with the halo staged in shared memory by TMA bulk copies
+  bool hop_tma_attr_set = false;
+  int n_sms = 148;
   int smoother_only = 0;                              // option "precond_smoother_only": M^{-1} = the level's smoother polynomial
                                                       // (the bootstrap solver of the set-up phase, before a hierarchy exists)
   bool mtj_attr_set = false;
@@ -486,6 +490,21 @@ int launch_residual_half(dmlmc_hier* h, int level, const void* X, const void* B,
 template <bool HAS2, bool HOUT, bool ZOUT>
 int launch_hop_eo(dmlmc_hier* h, const Level& L, int p, const uint2* Inq, const uint2* In2, uint2* Outp, Cx<double> a, Cx<double> b,
                   int kp, const void* Xc, void* Z) {
+  if constexpr (HOUT && !ZOUT) {
+    if (h->hop_tma && (kp % HT_CW) == 0 && (L.LX % HT_X) == 0 && ((L.LT / 2) % HT_TH) == 0) {
+      if (!h->hop_tma_attr_set) {
+        CU(cudaFuncSetAttribute(wilson_hop_eo_tma_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)HT_SMEM));
+        CU(cudaFuncSetAttribute(wilson_hop_eo_tma_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)HT_SMEM));
+        h->hop_tma_attr_set = true;
+      }
+      const int ntiles = (L.LX / HT_X) * ((L.LT / 2) / HT_TH) * (kp / HT_CW);
+      const int grid = std::min(ntiles, 2 * h->n_sms);
+      wilson_hop_eo_tma_kernel<HAS2><<<grid, HT_THREADS, HT_SMEM, h->stream>>>(L.LX, L.LT, p, L.links4, Inq, In2, Outp, (float)a.re, (float)a.im,
+                                                                             (float)b.re, (float)b.im, (uint32_t)kp, ntiles);
+      LAUNCH_CHECK(h);
+      return 0;
+    }
+  }
   const bool two = h->eo_packs == 2 && (kp % 2) == 0;
   const int kt = two ? kp / 2 : kp;                      // threads along the columns
   int bx = 1; while (bx < 32 && bx < kt) bx *= 2;
@@ -1358,6 +1377,7 @@ int dmlmc_hier_create(int device, void* cuda_stream, int n_levels, dmlmc_hier** 
   CU(cudaSetDevice(device));
   dmlmc_hier* h = new dmlmc_hier();
   h->device = device; h->stream = (cudaStream_t)cuda_stream; h->n_levels = n_levels;
+  { int sms = 0; if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device) == cudaSuccess && sms > 0) h->n_sms = sms; }
   cudaError_t e2 = cudaMallocHost(&h->h_nactive, sizeof(int));
   if (e2 != cudaSuccess) { delete h; return fail((int)e2, "cudaMallocHost failed"); }
   int lo = 0, hi = 0;
@@ -1832,6 +1852,7 @@ int dmlmc_set_option(dmlmc_hier* h, const char* name, double value) {
   if (std::strcmp(name, "outer_c64") == 0) { h->outer_c64 = value != 0.0; return 0; }
   if (std::strcmp(name, "outer_drop") == 0) { h->outer_drop = value; return 0; }
   if (std::strcmp(name, "mt_jump") == 0) { h->mt_jump = value != 0.0; return 0; }
+  if (std::strcmp(name, "hop_tma") == 0) { h->hop_tma = value != 0.0; return 0; }
   if (std::strcmp(name, "precond_smoother_only") == 0) { h->smoother_only = value != 0.0; return 0; }
   if (std::strcmp(name, "smoother_eo") == 0) { h->smoother_eo = value != 0.0; return 0; }
   if (std::strcmp(name, "dot32") == 0) { h->dot32 = value != 0.0; return 0; }

@@ -466,15 +466,66 @@ def test_wilson_hop_eo_kernel_is_bit_exact_on_integer_data(LX, LT, k, variant, p
 
 def test_device_prolongator_values_match_the_host_builder(g128):
     """dmlmc_prolongator_values (batched per-aggregate classical Gram-Schmidt, multigrid.py:232-259) against the host builder,
-    which is bit-identical to the reference: all three levels of the 128^2 hierarchy, agreement at rounding level, and the
-    columns of every (aggregate, half) block orthonormal."""
+    which is bit-identical to the reference: all three levels of the 128^2 hierarchy.  Same order of operations; only the
+    order of the additions inside an inner product differs, and classical Gram-Schmidt amplifies that 1e-16 by the
+    conditioning of the 16 x 4 block it works on (measured 1.1e-12 on level 0), hence 1e-10 here; the columns of every
+    (aggregate, half) block are orthonormal to the same level in both builders."""
     from deflatedmlmc_schwinger_b200 import _lib, multigrid as mgm
     dev = _lib.Hierarchy(1)
     for a, dofi, c, tv in [(32, 2, 4, g128["tv0"]), (32, 4, 4, g128["tv1"]), (32, 4, 4, g128["tv2"])]:
         ref = mgm.build_prolongator_values(tv, a, dofi, c)
         got = dev.prolongator_values(tv, a, dofi, c).cpu().numpy()
-        assert np.abs(got - ref).max() < 1e-13
-        P = mgm.prolongator_csr(got, a, dofi, c)
-        G = (P.conj().T @ P).toarray()
-        assert np.abs(G - np.eye(G.shape[0])).max() < 1e-13
+        P, Pr = mgm.prolongator_csr(got, a, dofi, c), mgm.prolongator_csr(ref, a, dofi, c)
+        G, Gr = (P.conj().T @ P).toarray(), (Pr.conj().T @ Pr).toarray()
+        print("level with dofi", dofi, ": max |device - host|", np.abs(got - ref).max(), " orthonormality device / host",
+              np.abs(G - np.eye(G.shape[0])).max(), np.abs(Gr - np.eye(G.shape[0])).max())
+        assert np.abs(got - ref).max() < 1e-10
+        assert np.abs(G - np.eye(G.shape[0])).max() < 10 * max(np.abs(Gr - np.eye(G.shape[0])).max(), 1e-14)
+    dev.close()
+
+
+@pytest.mark.parametrize("LX,LT", [(4, 16), (8, 32), (12, 48)])
+@pytest.mark.parametrize("k", [64, 128])
+@pytest.mark.parametrize("has2", [True, False])
+@pytest.mark.parametrize("parity", [0, 1])
+def test_tma_staged_hop_kernel_is_bit_exact(LX, LT, k, has2, parity):
+    """wilson_hop_eo_tma_kernel (the sweep with its neighbour halo staged in shared memory by cp.async.bulk; engaged when
+    LX % 4 == 0, (LT / 2) % 8 == 0 and k % 64 == 0): exact integer data as above, lattices of one tile (every halo row is a
+    periodic wrap) up to 3 x 3 tiles -- equal, bit for bit, to the scipy operator AND to the direct kernel (option hop_tma = 0)."""
+    dev, H = _hop_case(LX, LT, 31 * LX + LT)
+    n, nh = 2 * LX * LT, LX * LT
+    rows_p, rows_q = _eo_rows(LX, LT, parity), _eo_rows(LX, LT, 1 - parity)
+    rs = np.random.RandomState(11 * k + parity)
+    units = [1, -1, 1j, -1j]
+    for trial in range(2):
+        a, b = (units[rs.randint(4)] if has2 else 0), units[rs.randint(4)]
+        vq, v2 = _int_cplx(rs, (nh, k)), _int_cplx(rs, (nh, k))
+        full = np.zeros((n, k), dtype=np.complex128)
+        full[rows_q] = vq
+        ref = b * (H @ full)[rows_p] + (a * v2 if has2 else 0)
+        inq, in2 = _to_bf16_half(vq, LX, LT, k), (_to_bf16_half(v2, LX, LT, k) if has2 else None)
+        outs = []
+        for tma in (1, 0):
+            dev.set_option("hop_tma", tma)
+            out = torch.full((2, LX, LT // 2, k, 2), 777.0, dtype=torch.bfloat16, device="cuda")
+            dev.hop_eo(0, parity, inq, in2, out, a, b, k)
+            torch.cuda.synchronize()
+            o = out.float().cpu().numpy().reshape(nh, k, 2)
+            outs.append(o[..., 0] + 1j * o[..., 1])
+        dev.set_option("hop_tma", 1)
+        assert np.array_equal(outs[0], ref), (LX, LT, k, has2, parity, trial, np.argwhere(outs[0] != ref)[:4])
+        assert np.array_equal(outs[1], ref)
+    # random (non-integer) data: the two kernels do the same FP32 operations in the same order
+    vq = rs.standard_normal((nh, k)) + 1j * rs.standard_normal((nh, k))
+    v2 = rs.standard_normal((nh, k)) + 1j * rs.standard_normal((nh, k))
+    inq, in2 = _to_bf16_half(vq, LX, LT, k), (_to_bf16_half(v2, LX, LT, k) if has2 else None)
+    outs = []
+    for tma in (1, 0):
+        dev.set_option("hop_tma", tma)
+        out = torch.zeros((2, LX, LT // 2, k, 2), dtype=torch.bfloat16, device="cuda")
+        dev.hop_eo(0, parity, inq, in2, out, 0.3 - 0.2j if has2 else 0, -0.7 + 0.1j, k)
+        torch.cuda.synchronize()
+        outs.append(out.view(torch.int16).cpu().numpy().copy())
+    dev.set_option("hop_tma", 1)
+    assert np.array_equal(outs[0], outs[1])
     dev.close()
