@@ -122,7 +122,8 @@ struct dmlmc_hier {
   uint32_t* mt_tab = nullptr; int mt_tab_rows = 0;    // jump polynomials t^(2^b) mod phi (dmlmc_set_mt_jump_table)
   uint32_t* mt_state_out = nullptr;                   // [625] state written by the jump kernel, copied over the caller's afterwards
   int mt_jump = 1;                                    // option: 0 = the sequential one-CTA generator
-  int hop_tma = 1;                                    // option: the even-odd sweeps with the halo staged in shared memory by TMA bulk copies
+  int hop_tma = 0;                                    // option: the even-odd sweeps with the halo staged in shared memory by TMA bulk copies
+                                                      // (OFF: measured 27.8 us per sweep against 18.0 us of the direct kernel, runs r2_9 / r2_10)
   bool hop_tma_attr_set = false;
   int n_sms = 148;
   int smoother_only = 0;                              // option "precond_smoother_only": M^{-1} = the level's smoother polynomial

@@ -11,6 +11,12 @@
 // two-stage ring while the CTA computes the current one out of shared memory; completion is counted in bytes on an mbarrier.
 // L2 -> SM traffic per site falls from ~6 + 1 row fetches to 1.6 + 1, and no thread waits on a global load of vector data.
 //
+// MEASURED (B200, 128^2, k = 512, `bench.py --opt hop_tma=1`, profiles/r2_run9_*, r2_run10_*): bit-identical output
+// (tests/test_gpu_kernels.py::test_tma_staged_hop_kernel_is_bit_exact) but SLOWER than the direct kernel -- 46.3 us per sweep
+// with 256-byte rows (4 x 8 sites x 64 columns per tile, 168 copies), 27.8 us with 1 KB rows (2 x 4 sites x 256 columns, 52
+// copies) against 18.0 us: with two stages and two CTAs per SM ~100 KB are in flight per SM, no more than the direct kernel's
+// 28 warps x 10 outstanding 16-byte loads, and every tile pays the copy latency once more.  The option (hop_tma) is OFF.
+//
 // Tile rows in shared memory (per stage, per spin):  Q[r][64 columns], r =
 //   xl (HT_TH + 1) + j,  j = 0..HT_TH      row x0 + xl of the q-parity array, th = th0 - (1 - a_xl) + j,   a_xl = (x0 + xl + p) & 1
 //                                           (forward neighbour of site thl: j = thl + 1, backward: j = thl, for either a)
@@ -24,7 +30,15 @@
 
 namespace dmlmc {
 
-constexpr int HT_X = 4, HT_TH = 8, HT_CW = 32;                       // tile: 4 x 8 sites, 32 packs of two columns
+#ifndef DMLMC_HT_X
+#define DMLMC_HT_X 2
+#define DMLMC_HT_TH 4
+#define DMLMC_HT_CW 128
+#endif
+// tile: HT_X x HT_TH sites, HT_CW packs of two columns.  Measured at 128^2, k = 512 (sweep with / without In2 averaged):
+// 4 x 8 x 32 (168 copies of 256 B per tile): 46 us against 18 us of the direct kernel -- the TMA unit is request-rate bound
+// (~1 request per 38 cycles per SM); hence 1 KB rows: 2 x 4 x 128 (52 copies of 1 KB).
+constexpr int HT_X = DMLMC_HT_X, HT_TH = DMLMC_HT_TH, HT_CW = DMLMC_HT_CW;
 constexpr int HT_QROWS = HT_X * (HT_TH + 1) + 2 * HT_TH;             // 52
 constexpr int HT_CROWS = HT_X * HT_TH;                               // 32
 constexpr int HT_ROWBYTES = HT_CW * 8;                               // 256 B per row and spin
@@ -94,8 +108,11 @@ wilson_hop_eo_tma_kernel(int LX, int LT, int p, const float4* __restrict__ L4, c
 
   const float2 b_r = make_float2(br, br), b_i = make_float2(bi, bi);
   const float2 a_r = make_float2(ar, ar), a_i = make_float2(ai, ai);
-  const int l16 = tid & 15, st = tid >> 4;                            // 16 lanes x 2 packs per site, 16 sites at a time
-  const int thl = st & 7;
+  constexpr int LPS = HT_CW / 2;                                      // lanes per site (two packs = four columns each)
+  constexpr int SPP = HT_THREADS / LPS;                               // sites per pass
+  constexpr int NPASS = HT_X * HT_TH / SPP;
+  static_assert(HT_THREADS % LPS == 0 && (HT_X * HT_TH) % SPP == 0, "tile shape");
+  const int l16 = tid % LPS, st = tid / LPS;
   uint32_t phase[2] = {0u, 0u};
   int s = 0;
   int tile = blockIdx.x;
@@ -112,8 +129,9 @@ wilson_hop_eo_tma_kernel(int LX, int LT, int p, const float4* __restrict__ L4, c
     const uint2* C = Q + (size_t)HT_QROWS * 2 * HT_CW;
     auto qrow = [&](int r, int spin) { return Q + ((size_t)r * 2 + spin) * HT_CW + 2 * l16; };
 #pragma unroll
-    for (int it = 0; it < 2; ++it) {
-      const int xl = (st >> 3) + 2 * it;
+    for (int it = 0; it < NPASS; ++it) {
+      const int sidx = st + SPP * it;
+      const int xl = sidx / HT_TH, thl = sidx % HT_TH;
       const uint32_t x = x0 + xl, th = th0 + thl;
       const uint32_t a = (x + (uint32_t)p) & 1u;
       const uint32_t t = 2 * th + a;

@@ -4,6 +4,7 @@
 // Replaces pyamg.krylov.fgmres as called at multigrid.py:362 and the np.vdot / np.dot
 // call sites of utils.py:224,249,266,336,353.
 #pragma once
+#include <type_traits>
 #include "common.cuh"
 
 namespace dmlmc {
@@ -53,13 +54,26 @@ multi_dot_kernel(const Cx<VT>* __restrict__ Vbase, size_t vstride, int nv, const
       for (int r = r0 + ty; r < r1; r += DOT_TY) {
         const size_t off = (size_t)r * k + col;
         const Cx<WT> w_ = ldc_ro<WT>(W, off);
-        const Z w = cx<double>((double)w_.re, (double)w_.im);
+        if constexpr (std::is_same<VT, float>::value && std::is_same<WT, float>::value) {
+          // complex64 operands: the product in FP32 (its rounding, 6e-8, is that of the stored operands), the sum in FP64 --
+          // two FP64 adds per term instead of four FP64 FMAs and four conversions (ncu, run r2_8: the all-FP64 form of this
+          // kernel ran at 2.9 TB/s with the FP64 pipe as its top pipe)
 #pragma unroll
-        for (int i = 0; i < DOT_NI; ++i)
-          if (i0 + i < nv) {
-            const Cx<VT> v = ldc_ro<VT>(Vbase, (size_t)(i0 + i) * vstride + off);
-            zfma_conj(acc[i], cx<double>((double)v.re, (double)v.im), w);
-          }
+          for (int i = 0; i < DOT_NI; ++i)
+            if (i0 + i < nv) {
+              const Cx<float> v = ldc_ro<float>(Vbase, (size_t)(i0 + i) * vstride + off);
+              const float pr = fmaf(v.re, w_.re, v.im * w_.im), pi = fmaf(v.re, w_.im, -(v.im * w_.re));
+              acc[i].re += (double)pr; acc[i].im += (double)pi;
+            }
+        } else {
+          const Z w = cx<double>((double)w_.re, (double)w_.im);
+#pragma unroll
+          for (int i = 0; i < DOT_NI; ++i)
+            if (i0 + i < nv) {
+              const Cx<VT> v = ldc_ro<VT>(Vbase, (size_t)(i0 + i) * vstride + off);
+              zfma_conj(acc[i], cx<double>((double)v.re, (double)v.im), w);
+            }
+        }
       }
     }
 #pragma unroll
@@ -130,17 +144,33 @@ multi_axpy_norm_kernel(const Cx<VT>* __restrict__ Vbase, size_t vstride, int nv,
   if (col < k) {
     for (int r = r0 + ty; r < r1; r += DOT_TY) {
       const size_t off = (size_t)r * k + col;
-      Z acc = cx<double>(0.0, 0.0);
-      for (int i = 0; i < nv; ++i) {
-        const Cx<VT> v = ldc_ro<VT>(Vbase, (size_t)i * vstride + off);
-        zfma(acc, ldc_ro<double>(h, (size_t)i * k + col), cx<double>((double)v.re, (double)v.im));
+      if constexpr (std::is_same<VT, float>::value) {
+        // complex64 vectors: the update in FP32 (its result is stored in complex64 anyway), the norm accumulated in FP64
+        float ar = 0.f, ai = 0.f;
+        for (int i = 0; i < nv; ++i) {
+          const Cx<float> v = ldc_ro<float>(Vbase, (size_t)i * vstride + off);
+          const Z hz = ldc_ro<double>(h, (size_t)i * k + col);
+          const float hr = (float)hz.re, hi = (float)hz.im;
+          ar = fmaf(hr, v.re, fmaf(-hi, v.im, ar));
+          ai = fmaf(hr, v.im, fmaf(hi, v.re, ai));
+        }
+        const Cx<float> w0 = W[off];
+        const Cx<float> ws = cx<float>(w0.re - ar, w0.im - ai);
+        W[off] = ws;
+        sq += (double)fmaf(ws.re, ws.re, ws.im * ws.im);
+      } else {
+        Z acc = cx<double>(0.0, 0.0);
+        for (int i = 0; i < nv; ++i) {
+          const Cx<VT> v = ldc_ro<VT>(Vbase, (size_t)i * vstride + off);
+          zfma(acc, ldc_ro<double>(h, (size_t)i * k + col), cx<double>((double)v.re, (double)v.im));
+        }
+        const Cx<VT> w0 = W[off];
+        // the norm is that of the STORED vector (what the next basis vector is made from)
+        const Cx<VT> ws = cx<VT>((VT)((double)w0.re - acc.re), (VT)((double)w0.im - acc.im));
+        W[off] = ws;
+        const Z w = cx<double>((double)ws.re, (double)ws.im);
+        sq = fma(w.re, w.re, fma(w.im, w.im, sq));
       }
-      const Cx<VT> w0 = W[off];
-      // the norm is that of the STORED vector (what the next basis vector is made from)
-      const Cx<VT> ws = cx<VT>((VT)((double)w0.re - acc.re), (VT)((double)w0.im - acc.im));
-      W[off] = ws;
-      const Z w = cx<double>((double)ws.re, (double)ws.im);
-      sq = fma(w.re, w.re, fma(w.im, w.im, sq));
     }
   }
   red[ty][tx] = sq;

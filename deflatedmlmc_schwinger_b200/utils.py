@@ -137,7 +137,9 @@ def device_deflation_eigenpairs(mg_solver, params, method, k, tolx, level_nr):
     order = np.argsort(Sy, kind='stable')
     mg_solver.deflation_info = getattr(mg_solver, "deflation_info", {})
     mg_solver.deflation_info[(method, lvl)] = dict(info, residuals=res)
-    return Sy[order], X.cpu().numpy()[:, order]
+    from .multigrid import _same_on_all_ranks
+    Sy = np.real(_same_on_all_ranks(np.asarray(Sy[order], dtype=np.complex128), mg_solver.device))
+    return Sy, _same_on_all_ranks(X.cpu().numpy()[:, order], mg_solver.device)
 
 
 # ---- utils.py:130-201 -----------------------------------------------------------------------------

@@ -484,14 +484,14 @@ def test_device_prolongator_values_match_the_host_builder(g128):
     dev.close()
 
 
-@pytest.mark.parametrize("LX,LT", [(4, 16), (8, 32), (12, 48)])
-@pytest.mark.parametrize("k", [64, 128])
+@pytest.mark.parametrize("LX,LT", [(2, 8), (4, 16), (6, 24)])
+@pytest.mark.parametrize("k", [256, 512])
 @pytest.mark.parametrize("has2", [True, False])
 @pytest.mark.parametrize("parity", [0, 1])
 def test_tma_staged_hop_kernel_is_bit_exact(LX, LT, k, has2, parity):
-    """wilson_hop_eo_tma_kernel (the sweep with its neighbour halo staged in shared memory by cp.async.bulk; engaged when
-    LX % 4 == 0, (LT / 2) % 8 == 0 and k % 64 == 0): exact integer data as above, lattices of one tile (every halo row is a
-    periodic wrap) up to 3 x 3 tiles -- equal, bit for bit, to the scipy operator AND to the direct kernel (option hop_tma = 0)."""
+    """wilson_hop_eo_tma_kernel (the sweep with its neighbour halo staged in shared memory by cp.async.bulk; option hop_tma,
+    engaged when LX % 2 == 0, (LT / 2) % 4 == 0 and k % 256 == 0): exact integer data as above, lattices of one tile (every
+    halo row is a periodic wrap) up to 3 x 3 tiles -- equal, bit for bit, to the scipy operator AND to the direct kernel (option hop_tma = 0)."""
     dev, H = _hop_case(LX, LT, 31 * LX + LT)
     n, nh = 2 * LX * LT, LX * LT
     rows_p, rows_q = _eo_rows(LX, LT, parity), _eo_rows(LX, LT, 1 - parity)
@@ -512,7 +512,7 @@ def test_tma_staged_hop_kernel_is_bit_exact(LX, LT, k, has2, parity):
             torch.cuda.synchronize()
             o = out.float().cpu().numpy().reshape(nh, k, 2)
             outs.append(o[..., 0] + 1j * o[..., 1])
-        dev.set_option("hop_tma", 1)
+        dev.set_option("hop_tma", 0)
         assert np.array_equal(outs[0], ref), (LX, LT, k, has2, parity, trial, np.argwhere(outs[0] != ref)[:4])
         assert np.array_equal(outs[1], ref)
     # random (non-integer) data: the two kernels do the same FP32 operations in the same order
@@ -526,6 +526,6 @@ def test_tma_staged_hop_kernel_is_bit_exact(LX, LT, k, has2, parity):
         dev.hop_eo(0, parity, inq, in2, out, 0.3 - 0.2j if has2 else 0, -0.7 + 0.1j, k)
         torch.cuda.synchronize()
         outs.append(out.view(torch.int16).cpu().numpy().copy())
-    dev.set_option("hop_tma", 1)
+    dev.set_option("hop_tma", 0)
     assert np.array_equal(outs[0], outs[1])
     dev.close()
