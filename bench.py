@@ -25,6 +25,11 @@ import time
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 os.environ.setdefault("OMP_NUM_THREADS", "1")
+# stdout carries ONE JSON line (rank 0) and nothing else: whatever libraries write to file descriptor 1 (NCCL prints its
+# version banner there, whatever NCCL_DEBUG_FILE says) is sent to stderr, the line itself goes to the saved descriptor
+_JSON_OUT = os.fdopen(os.dup(1), "w")
+sys.stdout.flush()
+os.dup2(2, 1)
 # NCCL's log (whatever level the caller asks for through NCCL_DEBUG) goes to stderr: rank 0 prints ONE JSON line on stdout
 os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
 
@@ -323,6 +328,10 @@ class ClockSampler(threading.Thread):
             self.handle = pynvml.nvmlDeviceGetHandleByIndex(phys)
             self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(self.handle, pynvml.NVML_CLOCK_SM))
             self.nvml = pynvml
+            # the first query of each kind is slow (7 ms on a 1-GPU box, 32 ms with 8 ranks asking at once; measured, run
+            # r2_11) and stalls this process's launches while it lasts: make it here, outside the timed region, and drop it
+            self._sample_nvml()
+            self.samples, self.reasons = [], set()
         except Exception:
             self.nvml = None
 
@@ -747,7 +756,7 @@ def main():
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         line["cpu_baseline"] = cpu_baseline_pool(16)
     if rank == 0:
-        print(json.dumps(line), flush=True)
+        print(json.dumps(line), file=_JSON_OUT, flush=True)
     if world > 1:
         dist.destroy_process_group()
 

@@ -38,8 +38,12 @@ def _worker(rank, world, port, n, k, tol, q):
     np.random.seed(43)
     resf = sampling.run_sampling_fixed(fn, n, k, tol, 5000, comm)
     m, s, N = sampling.reduce_level_sums(np.array([1.0 + rank, 2.0j]), comm)
+    # set-up arrays (test vectors, deflation vectors) are rank 0's on every rank
+    from deflatedmlmc_schwinger_b200 import multigrid
+    mine = (np.arange(12).reshape(6, 2) * (1 + 1j) + 100 * rank).astype(np.complex128)
+    shared = multigrid._same_on_all_ranks(mine)
     q.put((rank, res["j_stop"], complex(res["avg"]), res["dev"], after.tolist(), res["ests"].tolist(),
-           complex(resf["avg"]), resf["dev"], resf["evaluated"], resf["ests"].tolist(), complex(m), s, N))
+           complex(resf["avg"]), resf["dev"], resf["evaluated"], resf["ests"].tolist(), complex(m), s, N, shared.tolist()))
     dist.destroy_process_group()
 
 
@@ -65,6 +69,7 @@ def test_two_ranks_reproduce_single_process():
     ref = sampling.run_sampling(fn1, n, k, tol, 5000)
     after_ref = np.random.randint(2, size=8).tolist()
     for o in out:
+        assert np.array_equal(np.array(o[13]), np.arange(12).reshape(6, 2) * (1 + 1j))     # rank 0's array everywhere
         assert o[1] == ref["j_stop"]                                   # same stop index on every rank
         assert np.array_equal(np.array(o[5]), ref["ests"])             # bit-identical ordered estimates
         assert o[2] == complex(ref["avg"]) and o[3] == ref["dev"]
