@@ -452,7 +452,7 @@ class MG:
 
     def set_option(self, name, value):
         """kernel / cycle option on this hierarchy and on its preconditioner hierarchy"""
-        for pm in (self.precond_mg, self.precond_mg1):
+        for pm in [self.precond_mg, self.precond_mg1] + list(getattr(self, "precond_mg_coarse", {}).values()):
             if pm is not None:
                 pm.dev.set_option(name, value)
         self.dev.set_option(name, value)        # (also drops this hierarchy's CUDA graphs, which embed the preconditioner's kernels)
@@ -856,44 +856,64 @@ class MG:
         self._build_level1_preconditioner(params, LX, LT)
 
     def _build_level1_preconditioner(self, params, LX, LT):
-        """The same for the estimator's level-1 solves on lattices whose level 1 is too large for a dense inverse.  A row of
-        A_1 is (strip j, half, v): strip j = s V/a + x LT/a + q is the run of a = aggr_size consecutive rows (spin s,
-        lattice column x, t in [q a, (q+1) a)) of multigrid.py:203-227.  Geometric blocks: 2 neighbouring strips in x,
-        both halves, split by the spin s; then 2 x 2.  CPU experiment at 128^2 (exact two-grid method on A_1): 11 outer
-        iterations at degree 32 against 33 (18 at degree 80) with the estimator's own level-2 aggregates."""
+        """Geometric preconditioner hierarchies for the estimator's COARSE-level solves on lattices whose level l >= 1 is too
+        large for a dense inverse.  A row of A_l is (strip group j, half, v): j = s V/a_l + x LT/a_l + q is the run of a_l
+        consecutive t-sites (spin s, lattice column x, t in [q a_l, (q+1) a_l)) that the aggregates of multigrid.py:203-227
+        have merged up to level l (a_1 = aggr_size of level 0, a_{l+1} = a_l times the strips per level-l aggregate).
+        Geometric blocks: 2 neighbouring groups in x, both halves, split by the spin s; then 2 x 2.  CPU experiment at 128^2
+        (exact two-grid method on A_1): 11 outer iterations at degree 32 against 33 (18 at degree 80) with the estimator's own
+        level-2 aggregates.  Level 1 -> self.precond_mg1, deeper levels -> self.precond_mg_coarse[l]."""
         lv = self.ml.levels
         sa = self._setup_args
-        if len(lv) < 3 or 1 in self.dense_levels or self._transfer_meta[0][0] == "indexed" or getattr(self, "level1_unused", False):
+        self.precond_mg_coarse = {}
+        if len(lv) < 3 or self._transfer_meta[0][0] == "indexed" or getattr(self, "level1_unused", False) and len(lv) < 4:
             return
-        aggr, dofi, nv1, _ = self._transfer_meta[0]
-        a_sites = aggr                          # rows of one spin component per strip (dofi = 2: rows = sites of one spin)
-        n1 = lv[1].A.shape[0]
+        aggr0, dofi0, _, _ = self._transfer_meta[0]
         V = LX * LT
-        if dofi != 2 or LT % a_sites or LX % 2 or n1 != (2 * V // aggr) * 2 * nv1:
+        if dofi0 != 2 or LX % 2:
             return
-        cblk, (gx, gt) = geometric_blocks_level1(LX, LT, a_sites, nv1, 2)
-        nq = gt
-        nvs = [int(d // 2) for d in sa['dof'][2:]] or [nv1]
-        levels = 2
-        while True:
-            nvl = nvs[min(levels - 2, len(nvs) - 1)]
-            if 2 * gx * gt * nvl <= 1024 or gx % 2 or gt % 2 or gx < 4 or gt < 4:
-                break
-            gx, gt = gx // 2, gt // 2
-            levels += 1
-        dof = [2 * nv1] + [2 * nvs[min(jj, len(nvs) - 1)] for jj in range(levels - 1)]
-        degs = [self.precond_degree] + [self.precond_coarse_degree] * (levels - 1)
-        pm = MG(lv[1].A, smoother_degree=degs, restart=self.restart, inner_precision=self.inner_precision,
-                device=self.device, dense_coarse_threshold=self.dense_coarse_threshold, pre_smooth=self.pre_smooth,
-                aggregation="geometric", precond_blocks=(1, 1), level0_block=nv1)
-        p2 = dict(params)
-        p2['use_permuted'] = False
-        p2['latt_dims'] = [LT, LX]
-        p2['geometric_first'] = {'cblk': cblk, 'coarse_dims': (LX // 2, nq)}
-        pm.setup(dof=dof, aggrs=[4] * (levels - 1), max_levels=levels, acc_eigvs=sa['acc_eigvs'], params=p2,
-                 test_vectors=[self.test_vectors[1]])
-        self.precond_mg1 = pm
-        self.dev.set_preconditioner(1, pm.dev, 0)
+        a_sites = aggr0                         # rows of one spin component per strip (dofi = 2: rows = sites of one spin)
+        max_level = int(params.get('geometric_coarse_levels', 2))
+        for l in range(1, len(lv) - 1):
+            nv_l = self._transfer_meta[l - 1][2]
+            if l > 1:
+                aggr_prev = self._transfer_meta[l - 1][0]
+                if self._transfer_meta[l - 1][0] == "indexed" or aggr_prev % (2 * self._transfer_meta[l - 2][2]):
+                    return
+                a_sites = a_sites * (aggr_prev // (2 * self._transfer_meta[l - 2][2]))
+            if l in self.dense_levels or l > max_level:
+                return
+            if l == 1 and getattr(self, "level1_unused", False):
+                continue
+            n_l = lv[l].A.shape[0]
+            if LT % a_sites or n_l != (2 * V // a_sites) * 2 * nv_l or (LT // a_sites) < 1:
+                return
+            cblk, (gx, gt) = geometric_blocks_level1(LX, LT, a_sites, nv_l, 2)
+            nq = gt
+            nvs = [int(d // 2) for d in sa['dof'][l + 1:]] or [nv_l]
+            levels = 2
+            while True:
+                nvl = nvs[min(levels - 2, len(nvs) - 1)]
+                if 2 * gx * gt * nvl <= 1024 or gx % 2 or gt % 2 or gx < 4 or gt < 4:
+                    break
+                gx, gt = gx // 2, gt // 2
+                levels += 1
+            dof = [2 * nv_l] + [2 * nvs[min(jj, len(nvs) - 1)] for jj in range(levels - 1)]
+            degs = [self.precond_degree] + [self.precond_coarse_degree] * (levels - 1)
+            pm = MG(lv[l].A, smoother_degree=degs, restart=self.restart, inner_precision=self.inner_precision,
+                    device=self.device, dense_coarse_threshold=self.dense_coarse_threshold, pre_smooth=self.pre_smooth,
+                    aggregation="geometric", precond_blocks=(1, 1), level0_block=nv_l)
+            p2 = dict(params)
+            p2['use_permuted'] = False
+            p2['latt_dims'] = [LT, LX]
+            p2['geometric_first'] = {'cblk': cblk, 'coarse_dims': (LX // 2, nq)}
+            pm.setup(dof=dof, aggrs=[4] * (levels - 1), max_levels=levels, acc_eigvs=sa['acc_eigvs'], params=p2,
+                     test_vectors=[self.test_vectors[l]])
+            if l == 1:
+                self.precond_mg1 = pm
+            else:
+                self.precond_mg_coarse[l] = pm
+            self.dev.set_preconditioner(l, pm.dev, 0)
 
     def _device_inverse(self, level, tol, batch=1024):
         """A_level^{-1} as a torch complex128 CUDA tensor [n, n], solved in column batches on the device"""

@@ -23,6 +23,7 @@ ap.add_argument("--batch", type=int, default=256)
 ap.add_argument("--fixed", action="store_true", help="sequential_stop=False: sample count from a pilot round, one all_reduce per level")
 ap.add_argument("--exact", action="store_true", help="also compute the EXACT level values with unit vectors (stoch_trace.exact_trace)")
 ap.add_argument("--set", default="schwinger128", help="gateway.set_params name: schwinger128 (G202/G102) or synthetic<L> (BASELINE configs[4])")
+ap.add_argument("--coarse-geo", type=int, default=-1, help="params['geometric_coarse_levels']: deepest estimator level that gets a geometric preconditioner hierarchy (default: the package's, 2)")
 ap.add_argument("--deflated", action="store_true",
                 help="the valid deflated-MLMC variant of SURVEY.md 8d cfg-2: not permuted, mlmc_deflat_vctrs=[16,0,16]")
 args = ap.parse_args()
@@ -51,6 +52,8 @@ def run(method):
         p["use_permuted"] = False
         p["mlmc_deflat_vctrs"] = [16, 0, 16]
     tp = utils.trace_params_from_params(p, method)
+    if args.coarse_geo >= 0:
+        tp["geometric_coarse_levels"] = args.coarse_geo
     if args.golden_tvs:
         g = np.load(os.path.join(ROOT, "tests", "golden", "schwinger128.npz"))
         tp["test_vectors"] = [g["tv0"], g["tv1"], g["tv2"]]

@@ -316,3 +316,25 @@ def test_mt19937_jump_table_is_pinned_against_numpy():
         if skip:
             r2.bytes(4 * skip)
         assert np.array_equal(np.frombuffer(r2.bytes(4 * 600), dtype=np.uint32), mj.temper(arr[q:q + 600]))
+
+
+def test_geometric_blocks_of_the_coarse_levels_are_local(port128):
+    """geometric_blocks_level1 with a_sites = the t-extent merged up to level l (32 at level 1, 128 at level 2 of the 128^2
+    hierarchy) gives, for every row of the ESTIMATOR's A_l, the block (x pair, t range, spin) its lattice support lies in: the
+    support of a row is read off the reference-aggregation prolongators themselves (|P_0|, |P_0| |P_1|)."""
+    mp, tp = port128
+    LX = LT = 128
+    V = LX * LT
+    P0 = abs(mp.levels[0].P).tocsc()
+    P01 = (abs(mp.levels[0].P) @ abs(mp.levels[1].P)).tocsc()
+    for lvl, Pc, a_sites in ((1, P0, 32), (2, P01, 128)):
+        n_l = Pc.shape[1]
+        cblk, (gx, gt) = mgm.geometric_blocks_level1(LX, LT, a_sites, 4, 2)
+        assert cblk.shape[0] == n_l and (gx, gt) == (LX // 2, LT // a_sites)
+        for r in list(range(0, n_l, 97)) + [n_l - 1]:
+            rows = Pc.indices[Pc.indptr[r]:Pc.indptr[r + 1]]           # level-0 rows i = s V + x LT + t in the support
+            s, x, t = rows // V, (rows % V) // LT, rows % LT
+            b = int(cblk[r])
+            bs, bq, bx = b % 2, (b // 2) % gt, (b // 2) // gt
+            assert np.all(s == bs) and np.all(x // 2 == bx) and np.all(t // a_sites == bq), (lvl, r)
+        assert np.bincount(cblk).min() == np.bincount(cblk).max() == 16      # 2 groups x 2 halves x 4 vectors per block
