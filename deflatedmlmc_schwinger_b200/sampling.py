@@ -204,17 +204,22 @@ def run_sampling(sample_fn, n, k, tol, max_nr_ests, comm=None, fixed_count=None,
     G = comm.world
     ests = np.zeros(0, dtype=np.complex128)
     iters_all = np.zeros(0, dtype=np.int64)
+    coarse_all = np.zeros(0, dtype=np.int64)
     rounds = 0
     src.begin()
     while True:
         base = ests.shape[0]
         probes = src.next_round(comm, n, k)
-        e_loc, it_loc = sample_fn(probes)
+        out = sample_fn(probes)                    # (e[k], fine-level iterations[k] [, coarse-level iterations[k]])
+        e_loc, it_loc = out[0], out[1]
+        itc_loc = out[2] if len(out) > 2 else np.zeros(k)
         rounds += 1
-        payload = np.concatenate([np.real(e_loc), np.imag(e_loc), np.asarray(it_loc, dtype=np.float64)])
-        allp = comm.all_gather(payload).reshape(G, 3, k)
+        payload = np.concatenate([np.real(e_loc), np.imag(e_loc), np.asarray(it_loc, dtype=np.float64),
+                                  np.asarray(itc_loc, dtype=np.float64)])
+        allp = comm.all_gather(payload).reshape(G, 4, k)
         ests = np.concatenate([ests, (allp[:, 0, :] + 1j * allp[:, 1, :]).reshape(-1)])
         iters_all = np.concatenate([iters_all, allp[:, 2, :].reshape(-1).astype(np.int64)])
+        coarse_all = np.concatenate([coarse_all, allp[:, 3, :].reshape(-1).astype(np.int64)])
         if fixed_count is not None:
             if ests.shape[0] >= fixed_count:
                 j = fixed_count - 1
@@ -230,8 +235,10 @@ def run_sampling(sample_fn, n, k, tol, max_nr_ests, comm=None, fixed_count=None,
     src.rewind((j + 1) - base, n)
     src.end()
     avg, dev, _ = reference_stats(ests, j)
+    # iteration counts of the USED samples only, the same on every rank (the overshoot of the last round is not counted)
     return {"ests": ests[:j + 1], "j_stop": j, "avg": avg, "dev": dev,
-            "iters_sum": int(iters_all[:j + 1].sum()), "rounds": rounds, "evaluated": int(ests.shape[0])}
+            "iters_sum": int(iters_all[:j + 1].sum()), "coarse_iters_sum": int(coarse_all[:j + 1].sum()),
+            "rounds": rounds, "evaluated": int(ests.shape[0])}
 
 
 def run_sampling_fixed(sample_fn, n, k, tol, max_nr_ests, comm=None, probe_source=None):
@@ -242,21 +249,24 @@ def run_sampling_fixed(sample_fn, n, k, tol, max_nr_ests, comm=None, probe_sourc
     src = probe_source or HostProbeSource()
     G = comm.world
     src.begin()
-    e_loc, it_loc = sample_fn(src.next_round(comm, n, k))
+    out = sample_fn(src.next_round(comm, n, k))
+    e_loc = out[0]
     mean, dev, N = reduce_level_sums(e_loc, comm)
     target = int(min(max_nr_ests, max(6, np.ceil((dev / tol) ** 2))))
     n_rounds = max(1, -(-target // (G * k)))
     es = [np.asarray(e_loc, dtype=np.complex128)]
-    it_sum = int(np.sum(it_loc))
+    it_sum = int(np.sum(out[1]))
+    itc_sum = int(np.sum(out[2])) if len(out) > 2 else 0
     for _ in range(n_rounds - 1):
-        e_loc, it_loc = sample_fn(src.next_round(comm, n, k))
-        es.append(np.asarray(e_loc, dtype=np.complex128))
-        it_sum += int(np.sum(it_loc))
+        out = sample_fn(src.next_round(comm, n, k))
+        es.append(np.asarray(out[0], dtype=np.complex128))
+        it_sum += int(np.sum(out[1]))
+        itc_sum += int(np.sum(out[2])) if len(out) > 2 else 0
     src.end()
     mean, dev, N = reduce_level_sums(np.concatenate(es), comm)
-    it_sum = int(comm.all_reduce_sum(np.array([float(it_sum)]))[0]) if n_rounds > 0 else it_sum
-    return {"ests": np.concatenate(es), "j_stop": N - 1, "avg": mean, "dev": dev, "iters_sum": it_sum,
-            "rounds": n_rounds, "evaluated": N}
+    sums = comm.all_reduce_sum(np.array([float(it_sum), float(itc_sum)]))
+    return {"ests": np.concatenate(es), "j_stop": N - 1, "avg": mean, "dev": dev, "iters_sum": int(sums[0]),
+            "coarse_iters_sum": int(sums[1]), "rounds": n_rounds, "evaluated": N}
 
 
 def reduce_level_sums(e_local, comm=None):

@@ -63,7 +63,7 @@ def _sampler(mg_solver, params, method, nr_deflat_vctrs, Vx, level, k):
         else:                                   # the probes themselves, generated on the device
             e, iters = defl_Hutch_batch(mg_solver, params, method, nr_deflat_vctrs, Vx, level, k, X0=probes)
         fn.coarse_iters += int(iters[1].sum())
-        return e, iters[0]
+        return e, iters[0], iters[1]
     fn.coarse_iters = 0
     return fn
 
@@ -239,7 +239,7 @@ def mlmc(A, params):
         output_params['results'][i]['ests_avg'] = res["avg"] + tr1s[i]
         output_params['results'][i]['ests_dev'] = res["dev"]
         output_params['results'][i]['function_iters'] += res["iters_sum"]
-        output_params['results'][lc]['function_iters'] += (fn.coarse_iters if lc < nr_levels - 1 else res["j_stop"] + 1)
+        output_params['results'][lc]['function_iters'] += (res["coarse_iters_sum"] if lc < nr_levels - 1 else res["j_stop"] + 1)
         mg_solver.coarsest_lev_iters[i] += res["iters_sum"]
         end = time.time()
         sampling_seconds += end - start
