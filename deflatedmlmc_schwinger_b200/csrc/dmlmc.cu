@@ -122,6 +122,7 @@ struct dmlmc_hier {
   uint32_t* mt_tab = nullptr; int mt_tab_rows = 0;    // jump polynomials t^(2^b) mod phi (dmlmc_set_mt_jump_table)
   uint32_t* mt_state_out = nullptr;                   // [625] state written by the jump kernel, copied over the caller's afterwards
   int mt_jump = 1;                                    // option: 0 = the sequential one-CTA generator
+  int mt_prio = 0;                                    // option: 1 = the jump-ahead kernel on the high-priority stream as well
   int hop_tma = 0;                                    // option: the even-odd sweeps with the halo staged in shared memory by TMA bulk copies
                                                       // (OFF: measured 27.8 us per sweep against 18.0 us of the direct kernel, runs r2_9 / r2_10)
   bool hop_tma_attr_set = false;
@@ -1726,7 +1727,7 @@ int dmlmc_mt19937_bits(dmlmc_hier* h, uint32_t* state_dev, uint32_t* backup_dev,
   // (it is the critical path of the next round), the jump-ahead kernel (~130 CTAs for ~2 ms) without priority over the solver
   const long long total = skip_before + count + skip_after;
   const bool jump = h->mt_jump && h->mt_tab != nullptr && total + 1024 < (1ll << (h->mt_tab_rows - 1));
-  cudaStream_t rs = jump ? h->rng_stream_lo : h->rng_stream;
+  cudaStream_t rs = (jump && !h->mt_prio) ? h->rng_stream_lo : h->rng_stream;
   CU(cudaEventRecord(h->rng_order, h->stream));
   CU(cudaStreamWaitEvent(rs, h->rng_order, 0));
   CU(cudaStreamWaitEvent(rs, h->rng_done, 0));
@@ -1738,12 +1739,7 @@ int dmlmc_mt19937_bits(dmlmc_hier* h, uint32_t* state_dev, uint32_t* backup_dev,
     long long chunk = 1 << 14;
     while (chunk * 32 < count) chunk <<= 1;
     const int nchunk = (int)((count + chunk - 1) / chunk);
-    const size_t smem = (size_t)(MTJ_BUF + 624) * sizeof(uint32_t);
-    if (!h->mtj_attr_set) {
-      CU(cudaFuncSetAttribute(mt19937_jump_bits_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-      h->mtj_attr_set = true;
-    }
-    mt19937_jump_bits_kernel<<<nchunk + 1, MTJ_THREADS, smem, rs>>>(state_dev, h->mt_state_out, backup_dev, h->mt_tab,
+    mt19937_jump_bits_kernel<<<nchunk + 1, MTJ_THREADS, 0, rs>>>(state_dev, h->mt_state_out, backup_dev, h->mt_tab,
                                                                    skip_before, count, total, chunk, lsb_dev);
     LAUNCH_CHECK(h);
     CU(cudaMemcpyAsync(state_dev, h->mt_state_out, 625 * sizeof(uint32_t), cudaMemcpyDeviceToDevice, rs));
@@ -1853,6 +1849,7 @@ int dmlmc_set_option(dmlmc_hier* h, const char* name, double value) {
   if (std::strcmp(name, "outer_c64") == 0) { h->outer_c64 = value != 0.0; return 0; }
   if (std::strcmp(name, "outer_drop") == 0) { h->outer_drop = value; return 0; }
   if (std::strcmp(name, "mt_jump") == 0) { h->mt_jump = value != 0.0; return 0; }
+  if (std::strcmp(name, "mt_prio") == 0) { h->mt_prio = value != 0.0; return 0; }
   if (std::strcmp(name, "hop_tma") == 0) { h->hop_tma = value != 0.0; return 0; }
   if (std::strcmp(name, "precond_smoother_only") == 0) { h->smoother_only = value != 0.0; return 0; }
   if (std::strcmp(name, "smoother_eo") == 0) { h->smoother_eo = value != 0.0; return 0; }

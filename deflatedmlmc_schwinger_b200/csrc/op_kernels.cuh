@@ -1124,8 +1124,9 @@ mt19937_bits_kernel(uint32_t* __restrict__ state, uint32_t* __restrict__ backup,
 // leave behind (numpy's alignment: origin a multiple of 624 words from the start state's, position in [1, 624]) to
 // `state_out`, and the call's start state to `backup`.
 constexpr int MTJ_THREADS = 640;
-constexpr int MTJ_BLOCKS = 32;                       // twists per fill
-constexpr int MTJ_BUF = 624 * (MTJ_BLOCKS + 1);      // words
+constexpr int MTJ_BLOCKS = 8;                        // twists per fill: the buffer holds 624 * 9 = 5616 consecutive raw words
+constexpr int MTJ_BUF = 624 * (MTJ_BLOCKS + 1);      // words (22 KB: static shared memory, the default carve-out)
+constexpr int MTJ_SLABW = 624 * MTJ_BLOCKS / 32;     // polynomial words per slab (156): 4992 coefficients need X[i0 .. i0 + 5616)
 constexpr int MTJ_DEG = 19937;
 
 // X[624 (r + 1) + i] for r < nb, i < 624, from X[0..623]:  X[t + 624] = X[t + 397] ^ mix(X[t], X[t + 1]), 227 words per barrier
@@ -1140,29 +1141,39 @@ __device__ __forceinline__ void mtj_fill(uint32_t* __restrict__ X, int nb, int t
     __syncthreads();
   }
 }
-// X[0..623] <- the 624 words J = 2^b positions further on (g = row b of the table).  Two output words per thread (one 64-bit
-// shared-memory load serves two polynomial bits), the 19937 coefficients split between the two halves of the CTA; the
-// coefficient word is warp-uniform, so a zero bit costs a not-taken branch only.
+// X[0..623] <- the 624 words J = 2^b positions further on (g = row b of the table).  The 19937 coefficients are consumed in four
+// slabs of 4992: each slab needs the raw words X[i0 .. i0 + 5616), which is what the buffer holds after 8 twists; its last 624
+// words then become the front of the next slab's buffer.  Two output words per thread (one 64-bit shared-memory load serves two
+// polynomial bits), the slab's coefficient words split between the two halves of the CTA; the coefficient word is warp-uniform.
 __device__ __forceinline__ void mtj_apply(uint32_t* __restrict__ X, uint32_t* __restrict__ P, const uint32_t* __restrict__ g, int tid) {
   for (int i = tid; i < 624; i += MTJ_THREADS) P[i] = __ldg(g + i);
-  mtj_fill(X, MTJ_BLOCKS, tid);
   const int grp = tid / 320, t = tid - grp * 320;
   uint32_t a0 = 0, a1 = 0;
-  if (t < 312) {
-    for (int iw = grp * 312; iw < (grp + 1) * 312; ++iw) {
-      const uint32_t gw = P[iw];
-      const uint2* xp = reinterpret_cast<const uint2*>(X + iw * 32 + 2 * t);
-      uint2 cur = xp[0];
+  for (int slab = 0; slab < 4; ++slab) {
+    mtj_fill(X, MTJ_BLOCKS, tid);                                        // (its barriers also publish P and the moved front)
+    if (t < 312) {
+      const int w0 = grp * (MTJ_SLABW / 2), w1 = w0 + MTJ_SLABW / 2;
+      for (int iw = w0; iw < w1; ++iw) {
+        const uint32_t gw = P[slab * MTJ_SLABW + iw];
+        const uint2* xp = reinterpret_cast<const uint2*>(X + iw * 32 + 2 * t);
+        uint2 cur = xp[0];
 #pragma unroll
-      for (int b = 0; b < 32; b += 2) {
-        const uint2 nxt = xp[b / 2 + 1];
-        if (gw & (1u << b)) { a0 ^= cur.x; a1 ^= cur.y; }
-        if (gw & (2u << b)) { a0 ^= cur.y; a1 ^= nxt.x; }
-        cur = nxt;
+        for (int b = 0; b < 32; b += 2) {
+          const uint2 nxt = xp[b / 2 + 1];
+          if (gw & (1u << b)) { a0 ^= cur.x; a1 ^= cur.y; }
+          if (gw & (2u << b)) { a0 ^= cur.y; a1 ^= nxt.x; }
+          cur = nxt;
+        }
       }
     }
+    __syncthreads();
+    if (slab < 3) {                                                      // the newest 624 words start the next slab
+      const uint32_t v = tid < 624 ? X[624 * MTJ_BLOCKS + tid] : 0u;
+      __syncthreads();
+      if (tid < 624) X[tid] = v;
+      __syncthreads();
+    }
   }
-  __syncthreads();
   if (grp == 1 && t < 312) { P[2 * t] = a0; P[2 * t + 1] = a1; }
   __syncthreads();
   if (grp == 0 && t < 312) { X[2 * t] = a0 ^ P[2 * t]; X[2 * t + 1] = a1 ^ P[2 * t + 1]; }
@@ -1172,7 +1183,7 @@ __global__ void __launch_bounds__(MTJ_THREADS)
 mt19937_jump_bits_kernel(const uint32_t* __restrict__ state, uint32_t* __restrict__ state_out, uint32_t* __restrict__ backup,
                          const uint32_t* __restrict__ tab, long long skip_before, long long count, long long total,
                          long long chunk, uint8_t* __restrict__ out) {
-  extern __shared__ uint32_t mtj_smem[];
+  __shared__ uint32_t mtj_smem[MTJ_BUF + 624];
   uint32_t* X = mtj_smem;
   uint32_t* P = mtj_smem + MTJ_BUF;
   const int tid = threadIdx.x;

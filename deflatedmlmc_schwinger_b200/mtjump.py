@@ -131,6 +131,69 @@ def make_table(path=TABLE):
     return tab
 
 
+# ---- general jump polynomials (host): t^D mod phi by products of the table entries -----------------------------------------
+_NFFT = 1 << 16
+
+
+def _words_to_bits(w):
+    return np.unpackbits(np.ascontiguousarray(w, dtype=np.uint32).view(np.uint8), bitorder="little")[:DEG].astype(np.float64)
+
+
+def poly_mul(a_words, b_words, phi):
+    """(a * b) mod phi for polynomials packed 32 coefficients per word: the product over GF(2) = the integer convolution of
+    the coefficient vectors mod 2 (FFT in float64: every sum is an integer <= 19937, exact), reduced by the sparse phi"""
+    fa = np.fft.rfft(_words_to_bits(a_words), _NFFT)
+    fb = np.fft.rfft(_words_to_bits(b_words), _NFFT)
+    c = np.rint(np.fft.irfft(fa * fb, _NFFT)).astype(np.int64) & 1
+    prod = int.from_bytes(np.packbits(c[:2 * DEG].astype(np.uint8), bitorder="little").tobytes(), "little")
+    return poly_to_words(_reduce(prod, phi))
+
+
+_PHI = None
+_POLY_CACHE = {}
+
+
+def _phi():
+    global _PHI
+    if _PHI is None:
+        _PHI = char_poly()
+    return _PHI
+
+
+def poly_for_distance(D):
+    """t^D mod phi (uint32[624])"""
+    D = int(D)
+    if D in _POLY_CACHE:
+        return _POLY_CACHE[D]
+    tab = table()
+    out = None
+    b = 0
+    d = D
+    while d:
+        if d & 1:
+            out = tab[b].copy() if out is None else poly_mul(out, tab[b], _phi())
+        d >>= 1
+        b += 1
+    if out is None:
+        out = np.zeros(N, dtype=np.uint32)
+        out[0] = 1
+    if len(_POLY_CACHE) < 4096:
+        _POLY_CACHE[D] = out
+    return out
+
+
+def chunk_polys(skip_before, chunk, nchunks, end_distance):
+    """rows c < nchunks: t^(skip_before + c * chunk) mod phi; last row: t^end_distance mod phi   (uint32 [nchunks + 1][624])"""
+    out = np.zeros((nchunks + 1, N), dtype=np.uint32)
+    if nchunks > 0:
+        out[0] = poly_for_distance(skip_before)
+        step = poly_for_distance(chunk)
+        for c in range(1, nchunks):
+            out[c] = poly_mul(out[c - 1], step, _phi())
+    out[nchunks] = poly_for_distance(end_distance)
+    return out
+
+
 _TAB = None
 
 

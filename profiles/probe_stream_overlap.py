@@ -98,6 +98,12 @@ def host_call_ms():
 res = {"host_side_call_ms": [host_call_ms() for _ in range(3)], "h_tiny_side_stream_kernel_ms": timed(h), "e_generator_call_without_outputs_ms": timed(e),
        "g_generator_then_sync_ms": timed(g), "a_fixed_probes_ms": timed(a), "b_plus_expand_ms": timed(b), "c_plus_generator_ms": timed(c), "d_device_probe_source_ms": timed(d)}
 src.end()
+dev.set_option("mt_prio", 1)
+res["c_high_priority_ms"] = timed(c)
+src.begin()
+res["d_high_priority_ms"] = timed(d)
+src.end()
+dev.set_option("mt_prio", 0)
 mg.set_option("use_graphs", 0)
 res["a_no_graphs_ms"] = timed(a)
 res["c_no_graphs_ms"] = timed(c)

@@ -129,3 +129,36 @@ def test_synthetic_256_matches_oracle(gsynth):
     assert res1.max() <= RES_MAX
     for m in (mg.precond_mg, mg.precond_mg1, mg):
         m.dev.close()
+
+
+def test_geometric_preconditioner_of_the_level2_solve(gsynth):
+    """Synthetic 256^2 with the dense-inverse threshold lowered to 4096, so that level 2 (n = 8192) is solved iteratively as on
+    the 512^2 / 1024^2 lattices: its FGMRES is preconditioned by a geometric hierarchy of its own (MG.precond_mg_coarse[2]; the
+    block map is geometric_blocks_level1 with the t-extent merged up to level 2).  Same solutions as with the estimator's own
+    hierarchy in the V-cycle (params['geometric_coarse_levels'] = 1), true residuals <= 1.3e-12, fewer iterations."""
+    from deflatedmlmc_schwinger_b200 import lattice, multigrid
+    g = gsynth
+    L, mass = int(g["L"]), float(g["mass"])
+    A = lattice.wilson_matrix(lattice.random_u1_links(L, int(g["seed"]), float(g["sigma"])), mass)
+    tvs = [lattice.unpack_bf16_vectors(g["tv%d_bf16" % i]) for i in range(3)]
+    out = {}
+    for deepest in (2, 1):
+        tp = {"use_permuted": False, "latt_dims": [L, L], "x_displacement": 2, "test_vectors_type": "EVs",
+              "function_params": {"tol": 1e-12}, "geometric_coarse_levels": deepest}
+        mg = multigrid.MG(A, smoother_degree=80, geometric_precond=True, dense_coarse_threshold=4096)
+        mg.setup(dof=list(g["dof"]), aggrs=list(g["aggrs"]), max_levels=4, acc_eigvs="low", params=tp, test_vectors=tvs)
+        assert 2 not in mg.dense_levels and mg.precond_mg1 is not None
+        assert (2 in mg.precond_mg_coarse) == (deepest == 2)
+        n2, k = mg.level_shapes[2], 16
+        B = np.random.RandomState(5).choice([-1.0, 1.0], size=(n2, k)).astype(np.complex128)
+        X, iters, relres = mg.solve_batch(2, torch.from_numpy(B).cuda(), 1e-12)
+        x = host(X)
+        A2 = mg.ml.levels[2].A
+        res = np.linalg.norm(B - A2 @ x, axis=0) / np.linalg.norm(B, axis=0)
+        assert res.max() <= RES_MAX
+        out[deepest] = (x, int(iters.max()))
+        for m in [mg.precond_mg, mg.precond_mg1, mg] + list(mg.precond_mg_coarse.values()):
+            m.dev.close()
+    print("level-2 solve: iterations with the geometric hierarchy", out[2][1], ", with the estimator's own", out[1][1])
+    assert np.abs(out[2][0] - out[1][0]).max() < 1e-8 * np.abs(out[1][0]).max()
+    assert out[2][1] < out[1][1]

@@ -338,3 +338,24 @@ def test_geometric_blocks_of_the_coarse_levels_are_local(port128):
             bs, bq, bx = b % 2, (b // 2) % gt, (b // 2) // gt
             assert np.all(s == bs) and np.all(x // 2 == bx) and np.all(t // a_sites == bq), (lvl, r)
         assert np.bincount(cblk).min() == np.bincount(cblk).max() == 16      # 2 groups x 2 halves x 4 vectors per block
+
+
+def test_mt19937_jump_polynomial_for_any_distance():
+    """mtjump.poly_for_distance / chunk_polys: t^D mod phi by FFT products of the table entries -- one application of that
+    polynomial lands on the words np.random produces D draws later (the multi-jump kernel applies one table entry per set bit
+    of D instead; both are the same linear map)."""
+    from deflatedmlmc_schwinger_b200 import mtjump as mj
+    rs = np.random.RandomState(123456)
+    rs.bytes(4 * 77)
+    st = rs.get_state()
+    key, pos = np.asarray(st[1], dtype=np.uint32), st[2]
+    P = mj.chunk_polys(3 * (1 << 16) + 5, 1 << 12, 3, 12345)
+    arr = mj.raw_words(key, mj.N + 1)[1:]                      # the window one word further on (see jump_host)
+    for c, D in enumerate([3 * (1 << 16) + 5, 3 * (1 << 16) + 5 + (1 << 12), 3 * (1 << 16) + 5 + 2 * (1 << 12), 12345]):
+        X = mj.raw_words(mj.apply_poly(arr, P[c]), (pos - 1) + 600)
+        r2 = np.random.RandomState()
+        r2.set_state(st)
+        r2.bytes(4 * D)
+        assert np.array_equal(np.frombuffer(r2.bytes(4 * 600 - 4 * (pos - 1) + 4 * (pos - 1)), dtype=np.uint32)[:600 - (pos - 1)],
+                              mj.temper(X[pos - 1:600]))
+    assert np.array_equal(mj.poly_for_distance(0)[:2], np.array([1, 0], dtype=np.uint32))
