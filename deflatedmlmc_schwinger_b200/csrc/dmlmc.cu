@@ -122,6 +122,7 @@ struct dmlmc_hier {
   uint32_t* mt_tab = nullptr; int mt_tab_rows = 0;    // jump polynomials t^(2^b) mod phi (dmlmc_set_mt_jump_table)
   uint32_t* mt_state_out = nullptr;                   // [625] state written by the jump kernel, copied over the caller's afterwards
   int mt_jump = 1;                                    // option: 0 = the sequential one-CTA generator
+  int gs_x2 = 1;                                      // option: two-column (16-byte) Gram-Schmidt kernels for complex64 vectors
   int mt_prio = 0;                                    // option: 1 = the jump-ahead kernel on the high-priority stream as well
   int hop_tma = 0;                                    // option: the even-odd sweeps with the halo staged in shared memory by TMA bulk copies
                                                       // (OFF: measured 27.8 us per sweep against 18.0 us of the direct kernel, runs r2_9 / r2_10)
@@ -825,6 +826,16 @@ template <typename VT = double, typename WT = double>
 int multi_dot(dmlmc_hier* h, const Cx<VT>* Vbase, size_t vstride, int nv, const Cx<WT>* W, int n, int k, Z* partial, Z* out, int accumulate) {
   const int nchunks = (n + ROWS_PER_CHUNK - 1) / ROWS_PER_CHUNK;
   dim3 blk(DOT_TX, DOT_TY), grd((k + DOT_TX - 1) / DOT_TX, nchunks);
+  if constexpr (std::is_same<VT, float>::value && std::is_same<WT, float>::value) {
+    if ((k % 2) == 0 && (vstride % 2) == 0 && h->gs_x2) {
+      dim3 g2((k / 2 + DOT_TX - 1) / DOT_TX, nchunks);
+      multi_dot_c64x2_kernel<<<g2, blk, 0, h->stream>>>(Vbase, vstride, nv, W, n, k, ROWS_PER_CHUNK, partial);
+      LAUNCH_CHECK(h);
+      sum_partials_kernel<<<nblocks((size_t)nv * k, 32), dim3(32, 8), 0, h->stream>>>(partial, nchunks, nv * k, out, accumulate);
+      LAUNCH_CHECK(h);
+      return 0;
+    }
+  }
   multi_dot_kernel<VT, WT><<<grd, blk, 0, h->stream>>>(Vbase, vstride, nv, W, n, k, ROWS_PER_CHUNK, partial);
   LAUNCH_CHECK(h);
   sum_partials_kernel<<<nblocks((size_t)nv * k, 32), dim3(32, 8), 0, h->stream>>>(partial, nchunks, nv * k, out, accumulate);
@@ -850,6 +861,16 @@ template <typename VT = double>
 int multi_axpy_norm(dmlmc_hier* h, const Cx<VT>* Vbase, size_t vstride, int nv, const Z* hc, Cx<VT>* W, int n, int k, Z* partial, Z* nrm2) {
   const int nchunks = (n + ROWS_PER_CHUNK - 1) / ROWS_PER_CHUNK;
   dim3 blk(DOT_TX, DOT_TY), grd((k + DOT_TX - 1) / DOT_TX, nchunks);
+  if constexpr (std::is_same<VT, float>::value) {
+    if ((k % 2) == 0 && (vstride % 2) == 0 && h->gs_x2) {
+      dim3 g2((k / 2 + DOT_TX - 1) / DOT_TX, nchunks);
+      multi_axpy_norm_c64x2_kernel<<<g2, blk, 0, h->stream>>>(Vbase, vstride, nv, hc, W, n, k, ROWS_PER_CHUNK, partial);
+      LAUNCH_CHECK(h);
+      sum_partials_kernel<<<nblocks((size_t)k, 32), dim3(32, 8), 0, h->stream>>>(partial, nchunks, k, nrm2, 0);
+      LAUNCH_CHECK(h);
+      return 0;
+    }
+  }
   multi_axpy_norm_kernel<VT><<<grd, blk, 0, h->stream>>>(Vbase, vstride, nv, hc, W, n, k, ROWS_PER_CHUNK, partial);
   LAUNCH_CHECK(h);
   sum_partials_kernel<<<nblocks((size_t)k, 32), dim3(32, 8), 0, h->stream>>>(partial, nchunks, k, nrm2, 0);
@@ -1793,8 +1814,11 @@ int dmlmc_apply_perm(dmlmc_hier* h, int level, const void* X, void* RHS, int k) 
 
 size_t dmlmc_workspace_bytes(dmlmc_hier* h, int level, int k, int restart) {
   if (!h || level < 0 || level >= h->n_levels || k < 1 || restart < 1) return 0;
-  // level_sample: fine solve + (sequentially) coarse solve share the FGMRES arena
-  size_t b = fgmres_bytes(h, level, k, restart);
+  // level_sample: fine solve + (sequentially) coarse solve share the FGMRES arena; the coarse level may need MORE than the fine
+  // one now that the fine stencil level solves on half-lattice complex64 vectors
+  size_t b = 0;
+  for (int l = level; l < h->n_levels - 1 && l <= level + 2; ++l)
+    if (h->lv[l].n > 0 && h->lv[l].kind >= 0) b = std::max(b, fgmres_bytes(h, l, k, std::min(restart, std::max(1, h->lv[l].n))));
   const size_t nk = (size_t)h->lv[level].n * k * sizeof(Z);
   b += 8 * align_up(nk) + align_up(partial_count(h->lv[level].n, 64, k) * sizeof(Z));
   b += align_up((size_t)h->lv[level].n * k / 8 + 64);
@@ -1857,6 +1881,7 @@ int dmlmc_set_option(dmlmc_hier* h, const char* name, double value) {
   if (std::strcmp(name, "outer_drop") == 0) { h->outer_drop = value; return 0; }
   if (std::strcmp(name, "mt_jump") == 0) { h->mt_jump = value != 0.0; return 0; }
   if (std::strcmp(name, "mt_prio") == 0) { h->mt_prio = value != 0.0; return 0; }
+  if (std::strcmp(name, "gs_x2") == 0) { h->gs_x2 = value != 0.0; return 0; }
   if (std::strcmp(name, "hop_tma") == 0) { h->hop_tma = value != 0.0; return 0; }
   if (std::strcmp(name, "precond_smoother_only") == 0) { h->smoother_only = value != 0.0; return 0; }
   if (std::strcmp(name, "smoother_eo") == 0) { h->smoother_eo = value != 0.0; return 0; }

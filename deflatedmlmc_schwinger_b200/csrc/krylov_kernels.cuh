@@ -88,6 +88,101 @@ multi_dot_kernel(const Cx<VT>* __restrict__ Vbase, size_t vstride, int nv, const
   }
 }
 
+// ---- the same two kernels for complex64 vectors (the mixed-precision Schur-complement solve), two columns per thread: 16-byte
+// loads put twice the bytes in flight per thread (ncu of the one-column form at k = 512: 2.9 TB/s, latency-bound; nv <= 3 there).
+// Products in FP32, sums in FP64; same row chunks and partial layout as the kernels above (deterministic).  k must be even.
+constexpr int D2_NI = 4;
+__global__ void __launch_bounds__(256)
+multi_dot_c64x2_kernel(const Cx<float>* __restrict__ Vbase, size_t vstride, int nv, const Cx<float>* __restrict__ W,
+                       int n, int k, int rows_per_chunk, Z* __restrict__ partial) {
+  __shared__ Z red[DOT_TY][D2_NI][2 * DOT_TX + 1];
+  typedef Pack<float, 2> P;
+  const int tx = threadIdx.x, ty = threadIdx.y;
+  const int col = (blockIdx.x * DOT_TX + tx) * 2;
+  const int r0 = blockIdx.y * rows_per_chunk;
+  const int r1 = min(n, r0 + rows_per_chunk);
+  const bool ok = col < k;
+  const int kp = k >> 1, cp = col >> 1;
+  const P* Wp = reinterpret_cast<const P*>(W);
+  const int tid = ty * DOT_TX + tx;
+  for (int i0 = 0; i0 < nv; i0 += D2_NI) {
+    double ar[D2_NI][2], ai[D2_NI][2];
+#pragma unroll
+    for (int i = 0; i < D2_NI; ++i) { ar[i][0] = ar[i][1] = ai[i][0] = ai[i][1] = 0.0; }
+    if (ok) {
+#pragma unroll 2
+      for (int r = r0 + ty; r < r1; r += DOT_TY) {
+        const size_t off = (size_t)r * kp + cp;
+        const P w = ldp_ro<float, 2>(Wp, off);
+#pragma unroll
+        for (int i = 0; i < D2_NI; ++i)
+          if (i0 + i < nv) {
+            const P v = ldp_ro<float, 2>(reinterpret_cast<const P*>(Vbase + (size_t)(i0 + i) * vstride), off);
+            ar[i][0] += (double)fmaf(v.d[0], w.d[0], v.d[1] * w.d[1]); ai[i][0] += (double)fmaf(v.d[0], w.d[1], -(v.d[1] * w.d[0]));
+            ar[i][1] += (double)fmaf(v.d[2], w.d[2], v.d[3] * w.d[3]); ai[i][1] += (double)fmaf(v.d[2], w.d[3], -(v.d[3] * w.d[2]));
+          }
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < D2_NI; ++i) { red[ty][i][2 * tx] = cx<double>(ar[i][0], ai[i][0]); red[ty][i][2 * tx + 1] = cx<double>(ar[i][1], ai[i][1]); }
+    __syncthreads();
+    // thread t reduces (vector t / 64, column t % 64) over the 8 row lanes
+    {
+      const int i = tid >> 6, c = tid & 63;
+      Z sacc = cx<double>(0.0, 0.0);
+#pragma unroll
+      for (int y = 0; y < DOT_TY; ++y) sacc = zadd(sacc, red[y][i][c]);
+      const int gcol = blockIdx.x * DOT_TX * 2 + c;
+      if (gcol < k && i0 + i < nv) partial[((size_t)blockIdx.y * nv + (i0 + i)) * k + gcol] = sacc;
+    }
+    __syncthreads();
+  }
+}
+__global__ void __launch_bounds__(256)
+multi_axpy_norm_c64x2_kernel(const Cx<float>* __restrict__ Vbase, size_t vstride, int nv, const Z* __restrict__ h,
+                             Cx<float>* __restrict__ W, int n, int k, int rows_per_chunk, Z* __restrict__ partial) {
+  __shared__ double red[DOT_TY][2 * DOT_TX + 1];
+  typedef Pack<float, 2> P;
+  const int tx = threadIdx.x, ty = threadIdx.y;
+  const int col = (blockIdx.x * DOT_TX + tx) * 2;
+  const int r0 = blockIdx.y * rows_per_chunk;
+  const int r1 = min(n, r0 + rows_per_chunk);
+  const int kp = k >> 1, cp = col >> 1;
+  P* Wp = reinterpret_cast<P*>(W);
+  double sq0 = 0.0, sq1 = 0.0;
+  if (col < k) {
+#pragma unroll 2
+    for (int r = r0 + ty; r < r1; r += DOT_TY) {
+      const size_t off = (size_t)r * kp + cp;
+      float a0r = 0.f, a0i = 0.f, a1r = 0.f, a1i = 0.f;
+      for (int i = 0; i < nv; ++i) {
+        const P v = ldp_ro<float, 2>(reinterpret_cast<const P*>(Vbase + (size_t)i * vstride), off);
+        const Z h0 = ldc_ro<double>(h, (size_t)i * k + col), h1 = ldc_ro<double>(h, (size_t)i * k + col + 1);
+        const float h0r = (float)h0.re, h0i = (float)h0.im, h1r = (float)h1.re, h1i = (float)h1.im;
+        a0r = fmaf(h0r, v.d[0], fmaf(-h0i, v.d[1], a0r)); a0i = fmaf(h0r, v.d[1], fmaf(h0i, v.d[0], a0i));
+        a1r = fmaf(h1r, v.d[2], fmaf(-h1i, v.d[3], a1r)); a1i = fmaf(h1r, v.d[3], fmaf(h1i, v.d[2], a1i));
+      }
+      P w = Wp[off];
+      w.d[0] -= a0r; w.d[1] -= a0i; w.d[2] -= a1r; w.d[3] -= a1i;
+      Wp[off] = w;
+      sq0 += (double)fmaf(w.d[0], w.d[0], w.d[1] * w.d[1]);
+      sq1 += (double)fmaf(w.d[2], w.d[2], w.d[3] * w.d[3]);
+    }
+  }
+  red[ty][2 * tx] = sq0; red[ty][2 * tx + 1] = sq1;
+  __syncthreads();
+  const int tid = ty * DOT_TX + tx;
+  if (tid < 2 * DOT_TX) {
+    const int gcol = blockIdx.x * DOT_TX * 2 + tid;
+    if (gcol < k) {
+      double t = red[0][tid];
+#pragma unroll
+      for (int y = 1; y < DOT_TY; ++y) t += red[y][tid];
+      partial[(size_t)blockIdx.y * k + gcol] = cx<double>(t, 0.0);
+    }
+  }
+}
+
 // out[idx] (+)= sum_chunk partial[chunk*count + idx].  Block (32, 8): 8 lanes share the chunks of an output, then a
 // fixed-order shared-memory reduction (deterministic; the order depends on nchunks only).
 __global__ void __launch_bounds__(256)
