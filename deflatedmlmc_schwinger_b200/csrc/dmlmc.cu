@@ -122,6 +122,7 @@ struct dmlmc_hier {
   uint32_t* mt_tab = nullptr; int mt_tab_rows = 0;    // jump polynomials t^(2^b) mod phi (dmlmc_set_mt_jump_table)
   uint32_t* mt_state_out = nullptr;                   // [625] state written by the jump kernel, copied over the caller's afterwards
   int mt_jump = 1;                                    // option: 0 = the sequential one-CTA generator
+  int fuse_residual = 1;                              // option: true residual of the Schur system + its norms in one kernel per cycle
   int gs_x2 = 1;                                      // option: two-column (16-byte) Gram-Schmidt kernels for complex64 vectors
   int mt_prio = 0;                                    // option: 1 = the jump-ahead kernel on the high-priority stream as well
   int hop_tma = 0;                                    // option: the even-odd sweeps with the halo staged in shared memory by TMA bulk copies
@@ -1097,6 +1098,25 @@ int launch_hop_z(dmlmc_hier* h, const Level& L, int p, const Cx<T>* Inq, const C
   LAUNCH_CHECK(h);
   return 0;
 }
+// r = b^ - S x and ||r||^2 per column in one pass (see wilson_schur_residual_kernel); false if the partial buffer is too small
+bool launch_schur_residual(dmlmc_hier* h, const Level& L, const Z* Wo, const Z* Xe, const Z* Bhat, Z* Rb, double c, int k,
+                           Z* partial, size_t partial_cap, Z* nrm2, int* rc) {
+  StencilDev<double> op; op.LX = L.LX; op.LT = L.LT; op.Ut = L.d.Ut; op.Ux = L.d.Ux; op.diag = L.d.diag;
+  int bx = 1; while (bx < 32 && bx < k) bx *= 2;
+  dim3 blk(bx, 4, 2), grd((k + bx - 1) / bx, (L.LT / 2 + 3) / 4, (L.LX + 1) / 2);
+  const size_t nchunks = (size_t)grd.y * grd.z;
+  if (!h->fuse_residual || nchunks * k > partial_cap) return false;
+  *rc = 0;
+  wilson_schur_residual_kernel<<<grd, blk, 0, h->stream>>>(op, 0, Wo, Xe, Bhat, Rb, cx<double>(c, 0.0), cx<double>(-1.0 / c, 0.0), k, partial);
+  h->launches++;
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) { *rc = fail((int)e, std::string("kernel launch: ") + cudaGetErrorString(e)); return true; }
+  sum_partials_kernel<<<nblocks((size_t)k, 32), dim3(32, 8), 0, h->stream>>>(partial, (int)nchunks, k, nrm2, 0);
+  h->launches++;
+  e = cudaGetLastError();
+  if (e != cudaSuccess) *rc = fail((int)e, std::string("kernel launch: ") + cudaGetErrorString(e));
+  return true;
+}
 bool outer_eo_ok(dmlmc_hier* h, int level, int k) {
   if (!h->outer_eo || !h->fuse_io || h->smoother_only) return false;
   Level& L = h->lv[level];
@@ -1168,8 +1188,11 @@ int fgmres_eo_t(dmlmc_hier* h, int level, const Z* B, Z* X, int k, double tol, i
   const std::vector<int> exp_cyc = have_exp ? h->expect_cyc[level] : std::vector<int>();
   std::vector<int> cyc_len;
   int total_it = 0, nact = 0, mode = 3, cycles = 0;
+  bool have_norm = false;                 // s.nrm2 already holds ||Rsrc||^2 per column (written by the fused residual kernel)
+  const size_t partial_cap = partial_count(n, m + 1, k);
   while (true) {
-    RET(multi_dot(h, Rsrc, 0, 1, Rsrc, nh, k, partial, s.nrm2, 0));
+    if (!have_norm) RET(multi_dot(h, Rsrc, 0, 1, Rsrc, nh, k, partial, s.nrm2, 0));
+    have_norm = false;
     CU(cudaMemsetAsync(s.n_active, 0, sizeof(int), h->stream));
     gmres_init_kernel<<<nblocks(k, 256), 256, 0, h->stream>>>(s, tol, mode, drop); LAUNCH_CHECK(h);
     mode = 2;
@@ -1194,7 +1217,17 @@ int fgmres_eo_t(dmlmc_hier* h, int level, const Z* B, Z* X, int k, double tol, i
         RET((multi_axpy_norm<VT>(h, Vb, nkh, j + 1, s.hsum, W, nh, k, partial, s.nrm2)));
         CU(cudaMemsetAsync(s.n_active, 0, sizeof(int), h->stream));
         gmres_step_kernel<<<gk, 128, 0, h->stream>>>(s, j, tol); LAUNCH_CHECK(h);
-        if (j + 1 < m) { col_scale_eo_kernel<VT, VT><<<nblocks(nkh, 256), 256, 0, h->stream>>>(L.LX, L.LT, W, s.scale, Vb + (size_t)(j + 1) * nkh, k, V32); LAUNCH_CHECK(h); }
+        if (j + 1 < m) {
+          bool done2 = false;
+          if constexpr (MIXED) {
+            if (h->gs_x2 && (k % 2) == 0) {
+              col_scale_eo_c64x2_kernel<<<nblocks(nkh / 2, 256), 256, 0, h->stream>>>(L.LX, L.LT, W, s.scale, Vb + (size_t)(j + 1) * nkh, k, V32);
+              LAUNCH_CHECK(h);
+              done2 = true;
+            }
+          }
+          if (!done2) { col_scale_eo_kernel<VT, VT><<<nblocks(nkh, 256), 256, 0, h->stream>>>(L.LX, L.LT, W, s.scale, Vb + (size_t)(j + 1) * nkh, k, V32); LAUNCH_CHECK(h); }
+        }
         return 0;
       };
       // (the kernel arguments of iteration j are the same in every cycle: one graph per j serves all cycles)
@@ -1210,8 +1243,14 @@ int fgmres_eo_t(dmlmc_hier* h, int level, const Z* B, Z* X, int k, double tol, i
     RET((multi_axpy<VT>(h, Zb, nkh, steps, s.y, Xe, nh, k, +1.0)));
     // true residual of the Schur system (= the residual of the full system, whose odd part is zero by construction)
     RET((launch_hop_z<double, false>(h, L, 1, Xe, nullptr, Wo, ONE, ONE, k)));
-    RET((launch_hop_z<double, true>(h, L, 0, Wo, Xe, Wd, CC, NIC, k)));
-    vec_sub_kernel<<<nblocks(nkh, 256), 256, 0, h->stream>>>(Bhat, Wd, Rb, nkh); LAUNCH_CHECK(h);
+    int rc_res = 0;
+    if (launch_schur_residual(h, L, Wo, Xe, Bhat, Rb, c, k, partial, partial_cap, s.nrm2, &rc_res)) {
+      RET(rc_res);
+      have_norm = true;
+    } else {
+      RET((launch_hop_z<double, true>(h, L, 0, Wo, Xe, Wd, CC, NIC, k)));
+      vec_sub_kernel<<<nblocks(nkh, 256), 256, 0, h->stream>>>(Bhat, Wd, Rb, nkh); LAUNCH_CHECK(h);
+    }
     Rsrc = Rb;
     ++cycles;
   }
@@ -1882,6 +1921,7 @@ int dmlmc_set_option(dmlmc_hier* h, const char* name, double value) {
   if (std::strcmp(name, "mt_jump") == 0) { h->mt_jump = value != 0.0; return 0; }
   if (std::strcmp(name, "mt_prio") == 0) { h->mt_prio = value != 0.0; return 0; }
   if (std::strcmp(name, "gs_x2") == 0) { h->gs_x2 = value != 0.0; return 0; }
+  if (std::strcmp(name, "fuse_residual") == 0) { h->fuse_residual = value != 0.0; return 0; }
   if (std::strcmp(name, "hop_tma") == 0) { h->hop_tma = value != 0.0; return 0; }
   if (std::strcmp(name, "precond_smoother_only") == 0) { h->smoother_only = value != 0.0; return 0; }
   if (std::strcmp(name, "smoother_eo") == 0) { h->smoother_eo = value != 0.0; return 0; }

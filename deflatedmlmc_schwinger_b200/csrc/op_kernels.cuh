@@ -495,6 +495,71 @@ wilson_hop_eo_z_kernel(StencilDev<T> op, int p, const Cx<T>* __restrict__ Inq, c
   O[ic] = o0; O[ic + sp] = o1;
 }
 
+// The true residual of the Schur-complement system at the end of a cycle, in one pass:  R = Bh - (a * X + b * H Wo)  on the
+// even sites (complex128, one column per thread; a = c, b = -1/c gives R = b^ - S x with Wo = H_oe x), and the squared norm of
+// every column of R as per-block partial sums  partial[(blockIdx.z * gridDim.y + blockIdx.y) * k + col]  (fixed order:
+// deterministic, independent of the batch) -- replaces the operator kernel + vec_sub_kernel + multi_dot_kernel of that step.
+__global__ void __launch_bounds__(256)
+wilson_schur_residual_kernel(StencilDev<double> op, int p, const Cx<double>* __restrict__ Inq, const Cx<double>* __restrict__ In2,
+                             const Cx<double>* __restrict__ In3, Cx<double>* __restrict__ Outp, Cx<double> a, Cx<double> b, int k,
+                             Cx<double>* __restrict__ partial) {
+  typedef Pack<double, 1> P;
+  __shared__ double red[8][33];
+  const int col = blockIdx.x * blockDim.x + threadIdx.x;
+  const int th = blockIdx.y * blockDim.y + threadIdx.y;
+  const int x = blockIdx.z * blockDim.z + threadIdx.z;
+  const int LX = op.LX, LT = op.LT, LH = LT >> 1;
+  const bool valid = col < k && th < LH && x < LX;
+  double sq = 0.0;
+  if (valid) {
+    const int off = (x + p) & 1;
+    const int t = 2 * th + off;
+    const int site = x * LT + t;
+    const int tm = (t == 0) ? LT - 1 : t - 1;
+    const int xp = (x + 1 == LX) ? 0 : x + 1, xm = (x == 0) ? LX - 1 : x - 1;
+    const int th_f = off ? ((th + 1 == LH) ? 0 : th + 1) : th;
+    const int th_b = off ? th : ((th == 0) ? LH - 1 : th - 1);
+    const Cx<double> ut = ldc_ro<double>(op.Ut, site), utb = cconj(ldc_ro<double>(op.Ut, x * LT + tm));
+    const Cx<double> ux = ldc_ro<double>(op.Ux, site), uxb = cconj(ldc_ro<double>(op.Ux, xm * LT + t));
+    const size_t kz = (size_t)k, sp = (size_t)(LX * LH) * kz;
+    const P* Q = reinterpret_cast<const P*>(Inq);
+    const size_t i_f = ((size_t)x * LH + th_f) * kz + col, i_b = ((size_t)x * LH + th_b) * kz + col;
+    const size_t i_r = ((size_t)xp * LH + th) * kz + col,  i_l = ((size_t)xm * LH + th) * kz + col;
+    const P f0 = ldp_ro<double, 1>(Q, i_f), f1 = ldp_ro<double, 1>(Q, i_f + sp);
+    const P b0 = ldp_ro<double, 1>(Q, i_b), b1 = ldp_ro<double, 1>(Q, i_b + sp);
+    const P r0 = ldp_ro<double, 1>(Q, i_r), r1 = ldp_ro<double, 1>(Q, i_r + sp);
+    const P l0 = ldp_ro<double, 1>(Q, i_l), l1 = ldp_ro<double, 1>(Q, i_l + sp);
+    const P pa = psub<double, 1>(f0, f1);
+    const P pb = padd<double, 1>(b0, b1);
+    const P pc = padd<double, 1>(r0, pmul_i<double, 1>(r1));
+    const P pd = psub<double, 1>(l0, pmul_i<double, 1>(l1));
+    const P ua = pscale<double, 1>(ut, pa), ub = pscale<double, 1>(utb, pb);
+    const P uc = pscale<double, 1>(ux, pc), ud = pscale<double, 1>(uxb, pd);
+    P h0 = pzero<double, 1>();
+    h0 = psub<double, 1>(h0, padd<double, 1>(padd<double, 1>(ua, ub), padd<double, 1>(uc, ud)));
+    const P h1 = padd<double, 1>(psub<double, 1>(ua, ub), pmul_i<double, 1>(psub<double, 1>(uc, ud)));
+    P o0 = pscale<double, 1>(b, h0), o1 = pscale<double, 1>(b, h1);
+    const size_t ic = ((size_t)x * LH + th) * kz + col;
+    const P* C = reinterpret_cast<const P*>(In2);
+    pfma<double, 1>(o0, a, ldp_ro<double, 1>(C, ic));
+    pfma<double, 1>(o1, a, ldp_ro<double, 1>(C, ic + sp));
+    const P* B3 = reinterpret_cast<const P*>(In3);
+    const P q0 = psub<double, 1>(ldp_ro<double, 1>(B3, ic), o0), q1 = psub<double, 1>(ldp_ro<double, 1>(B3, ic + sp), o1);
+    P* O = reinterpret_cast<P*>(Outp);
+    O[ic] = q0; O[ic + sp] = q1;
+    sq = fma(q0.d[0], q0.d[0], fma(q0.d[1], q0.d[1], fma(q1.d[0], q1.d[0], q1.d[1] * q1.d[1])));
+  }
+  const int lane = threadIdx.z * blockDim.y + threadIdx.y;                // 0 .. 7 (blockDim = (bx, 4, 2))
+  red[lane][threadIdx.x] = sq;
+  __syncthreads();
+  if (lane == 0 && col < k) {
+    double t = red[0][threadIdx.x];
+    const int nl = blockDim.y * blockDim.z;
+    for (int y = 1; y < nl; ++y) t += red[y][threadIdx.x];
+    partial[((size_t)blockIdx.z * gridDim.y + blockIdx.y) * k + col] = cx<double>(t, 0.0);
+  }
+}
+
 // full-lattice X[s][x][t][k]  <->  checkerboard halves E, O [s][x][t/2][k]   (complex128)
 // dir = 0: split X into E and O;  dir = 1: merge E and O into X
 __global__ void __launch_bounds__(256)
@@ -532,6 +597,29 @@ col_scale_eo_kernel(int LX, int LT, const Cx<TI>* __restrict__ In, const double*
   const Cx<TO> o = cx<TO>((TO)((double)v.re * sc), (TO)((double)v.im * sc));
   Out[idx] = o;
   if (Out32 != nullptr) Out32[((size_t)s * (LX * LT) + (size_t)x * LT + t) * k + col] = cx<float>((float)o.re, (float)o.im);
+}
+
+// the complex64 -> complex64 case of col_scale_eo_kernel with two columns per thread (16-byte loads and stores; k even)
+__global__ void __launch_bounds__(256)
+col_scale_eo_c64x2_kernel(int LX, int LT, const Cx<float>* __restrict__ In, const double* __restrict__ scale, Cx<float>* __restrict__ Out,
+                          int k, Cx<float>* __restrict__ Out32) {
+  typedef Pack<float, 2> P;
+  const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;      // pack index
+  const int kp = k >> 1;
+  const size_t npk = (size_t)LX * LT * kp;
+  if (idx >= npk) return;
+  const size_t hrow = idx / kp; const int cp = (int)(idx - hrow * kp);
+  const int VH = (LX * LT) >> 1, LH = LT >> 1;
+  const int s = (int)(hrow / VH); const int r = (int)(hrow - (size_t)s * VH);
+  const int x = r / LH, th = r - x * LH;
+  const int t = 2 * th + (x & 1);
+  const double s0 = __ldg(scale + 2 * cp), s1 = __ldg(scale + 2 * cp + 1);
+  const P v = ldp_ro<float, 2>(reinterpret_cast<const P*>(In), idx);
+  P o;
+  o.d[0] = (float)((double)v.d[0] * s0); o.d[1] = (float)((double)v.d[1] * s0);
+  o.d[2] = (float)((double)v.d[2] * s1); o.d[3] = (float)((double)v.d[3] * s1);
+  reinterpret_cast<P*>(Out)[idx] = o;
+  if (Out32 != nullptr) reinterpret_cast<P*>(Out32)[((size_t)s * (LX * LT) + (size_t)x * LT + t) * kp + cp] = o;
 }
 
 // Shared-memory-tiled variant of the same factor kernel (option "stencil_smem", OFF by default: measured on B200 at
