@@ -36,6 +36,13 @@ _SIGS = {
     "dmlmc_set_dense_inverse_device": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_void_p]),
     "dmlmc_prolongator_values": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int,
                                                ctypes.c_int, ctypes.c_void_p]),
+    "dmlmc_block_orthonormal_values": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_int,
+                                                      ctypes.c_int, ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p]),
+    "dmlmc_galerkin": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p,
+                                      ctypes.POINTER(ctypes.c_int)]),
+    "dmlmc_set_bsr_device": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int,
+                                            ctypes.c_void_p, ctypes.c_void_p]),
+    "dmlmc_dense_inverse": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p]),
     "dmlmc_set_dense_inverse_device_full": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_void_p]),
     "dmlmc_set_smoother": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_void_p,
                                           ctypes.c_double, ctypes.c_double]),
@@ -98,7 +105,7 @@ def load():
         fn = getattr(lib, name)          # AttributeError if the ABI is incomplete
         fn.restype = res
         fn.argtypes = args
-    if lib.dmlmc_abi_version() != 5:
+    if lib.dmlmc_abi_version() != 6:
         raise RuntimeError("libdmlmc_sm100.so ABI version mismatch")
     _lib = lib
     return lib
@@ -206,6 +213,62 @@ class Hierarchy:
         _check(self.lib.dmlmc_prolongator_values(self.h, ctypes.c_void_p(ev.data_ptr()), int(ev.shape[1]), int(ev.shape[0]),
                                                  int(aggr_size), int(dofi), int(nvec), ctypes.c_void_p(pv.data_ptr())))
         return pv
+
+    def block_orthonormal_values(self, vecs, cblk, nvec, passes=2):
+        """the first nvec columns of `vecs` orthonormalised within every coarse block cblk[r] (equal-sized blocks) on the
+        device -> (pvals torch [n, nvec], rows torch int32 [n_blocks, m])"""
+        torch = self.torch
+        ev = vecs if torch.is_tensor(vecs) else torch.from_numpy(np.ascontiguousarray(vecs, dtype=np.complex128))
+        ev = ev.to(self.device).contiguous()
+        cb = cblk if torch.is_tensor(cblk) else torch.from_numpy(np.ascontiguousarray(cblk, dtype=np.int32))
+        cb = cb.to(self.device)
+        n = int(ev.shape[0])
+        nb = int(cb.max().item()) + 1
+        m = n // nb
+        rows = torch.argsort(cb.to(torch.int64), stable=True).to(torch.int32).contiguous()
+        if m * nb != n or not bool((cb[rows.long()].reshape(nb, m) == torch.arange(nb, device=self.device, dtype=cb.dtype)[:, None]).all()):
+            raise DmlmcError("block_orthonormal_values: the coarse blocks must all have the same number of rows")
+        pv = torch.empty((n, nvec), dtype=torch.complex128, device=self.device)
+        _check(self.lib.dmlmc_block_orthonormal_values(self.h, ctypes.c_void_p(ev.data_ptr()), int(ev.shape[1]), n, m, int(nvec),
+                                                       ctypes.c_void_p(rows.data_ptr()), int(passes), ctypes.c_void_p(pv.data_ptr())))
+        return pv, rows.reshape(nb, m)
+
+    def galerkin(self, level, nvec, n_coarse, cap=24):
+        """A_{level+1} = R A P (multigrid.py:276) on the device from this level's operator and transfer; the coarse operator is
+        installed on level + 1 (padded block-sparse rows) and returned as (col torch int32 [nb, bpr], vals torch complex128
+        [nb, bpr, nvec, nvec])."""
+        torch = self.torch
+        nb = n_coarse // nvec
+        while True:
+            col = torch.empty((nb, cap), dtype=torch.int32, device=self.device)
+            vals = torch.empty((nb, cap, nvec, nvec), dtype=torch.complex128, device=self.device)
+            slots = ctypes.c_int(0)
+            _check(self.lib.dmlmc_galerkin(self.h, level, cap, ctypes.c_void_p(col.data_ptr()), ctypes.c_void_p(vals.data_ptr()),
+                                           ctypes.byref(slots)))
+            if slots.value <= cap:
+                break
+            del col, vals
+            cap *= 2
+        bpr = max(int(slots.value), 1)
+        col = col[:, :bpr].contiguous()
+        vals = vals[:, :bpr].contiguous()
+        self.set_bsr_device(level + 1, n_coarse, nvec, col, vals)
+        return col, vals
+
+    def set_bsr_device(self, level, n, bs, col, vals):
+        assert col.is_cuda and col.is_contiguous() and col.dtype == self.torch.int32
+        assert vals.is_cuda and vals.is_contiguous() and vals.dtype == self.torch.complex128
+        _check(self.lib.dmlmc_set_bsr_device(self.h, level, int(n), int(bs), int(col.shape[1]), ctypes.c_void_p(col.data_ptr()),
+                                             ctypes.c_void_p(vals.data_ptr())))
+        self.sizes[level] = int(n)
+
+    def dense_inverse(self, M):
+        """multigrid.py:342-344 on the device: the inverse of a dense complex128 matrix (numpy or torch, n <= 1024) -> torch [n, n]"""
+        torch = self.torch
+        A = M if torch.is_tensor(M) else torch.from_numpy(np.ascontiguousarray(M, dtype=np.complex128))
+        A = A.to(self.device).clone().contiguous()
+        _check(self.lib.dmlmc_dense_inverse(self.h, int(A.shape[0]), ctypes.c_void_p(A.data_ptr())))
+        return A
 
     def set_dense_inverse_device(self, level, minv_dev, full=False):
         """minv_dev: torch complex128 CUDA tensor [n, n] (row-major inverse); full: keep it in all precisions (else only as

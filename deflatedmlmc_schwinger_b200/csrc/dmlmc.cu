@@ -8,6 +8,7 @@
 #include "krylov_kernels.cuh"
 #include "dense_umma.cuh"
 #include "hop_tma.cuh"
+#include "setup_kernels.cuh"
 
 #include <algorithm>
 #include <cstdio>
@@ -1628,8 +1629,87 @@ int dmlmc_prolongator_values(dmlmc_hier* h, const void* eig_vecs_dev, int ld, in
   int wpb = 4; while (wpb > 1 && wpb * per_warp > 48 * 1024) wpb /= 2;
   const long long nitems = 2ll * (n / aggr_size);
   prolongator_values_kernel<<<(unsigned)((nitems + wpb - 1) / wpb), 32 * wpb, wpb * per_warp, h->stream>>>(
-      (const Cx<double>*)eig_vecs_dev, ld, n, aggr_size, dofi, nvec, (Cx<double>*)pvals_dev);
+      (const Cx<double>*)eig_vecs_dev, ld, n, aggr_size, dofi, nvec, (Cx<double>*)pvals_dev, nullptr, 1);
   LAUNCH_CHECK(h);
+  return 0;
+}
+
+int dmlmc_block_orthonormal_values(dmlmc_hier* h, const void* vecs_dev, int ld, int n, int m, int nvec, const int32_t* rows_dev,
+                                   int passes, void* pvals_dev) {
+  CHECK(h != nullptr, "NULL handle"); CU(cudaSetDevice(h->device));
+  CHECK(vecs_dev && pvals_dev && rows_dev && n > 0 && nvec >= 1 && nvec <= 16 && ld >= nvec, "block_orthonormal_values: bad arguments");
+  CHECK(m >= nvec && n % m == 0 && (passes == 1 || passes == 2), "block_orthonormal_values: blocks of m >= nvec rows, n a multiple of m");
+  const size_t per_warp = (size_t)m * nvec * sizeof(double2);
+  CHECK(per_warp <= 48 * 1024, "block_orthonormal_values: block too large for one warp's shared memory");
+  int wpb = 4; while (wpb > 1 && wpb * per_warp > 48 * 1024) wpb /= 2;
+  const long long nitems = n / m;
+  prolongator_values_kernel<<<(unsigned)((nitems + wpb - 1) / wpb), 32 * wpb, wpb * per_warp, h->stream>>>(
+      (const Cx<double>*)vecs_dev, ld, n, 2 * m, 2, nvec, (Cx<double>*)pvals_dev, rows_dev, passes);
+  LAUNCH_CHECK(h);
+  return 0;
+}
+
+int dmlmc_galerkin(dmlmc_hier* h, int level, int cap, int32_t* col_dev, void* vals_dev, int* slots_host) {
+  CHECK(h && level >= 0 && level < h->n_levels - 1, "galerkin: bad handle/level");
+  CU(cudaSetDevice(h->device));
+  Level& L = h->lv[level];
+  CHECK(L.kind >= 0 && L.has_transfer, "galerkin: the level needs its operator and its transfer operator first");
+  CHECK(cap >= 1 && cap <= 1024 && col_dev && vals_dev && slots_host, "galerkin: bad arguments");
+  GalOp A; A.kind = L.kind; A.LX = L.LX; A.LT = L.LT; A.Ut = L.d.Ut; A.Ux = L.d.Ux; A.diag = L.d.diag;
+  A.bs = L.bs; A.bpr = L.bpr; A.col = L.bsr_col; A.vals = L.d.bsr_vals;
+  GalTr T; T.aggr = L.aggr; T.dofi = L.dofi; T.nvec = L.nvec; T.rows = L.tr_rows; T.cblk = L.tr_cblk; T.pv = L.d.pv;
+  T.m = L.tr_rows ? L.tr_m : L.aggr / 2;
+  const int nbc = L.n_c / L.nvec;
+  int* maxw = nullptr;
+  CU(cudaMalloc(&maxw, sizeof(int)));
+  CU(cudaMemsetAsync(maxw, 0, sizeof(int), h->stream));
+  CU(cudaMemsetAsync(vals_dev, 0, (size_t)nbc * cap * L.nvec * L.nvec * sizeof(Cx<double>), h->stream));
+  galerkin_kernel<<<nbc, 256, cap * sizeof(int), h->stream>>>(A, T, cap, col_dev, (Cx<double>*)vals_dev, maxw);
+  h->launches++;
+  cudaError_t e = cudaGetLastError();
+  if (e == cudaSuccess) e = cudaMemcpyAsync(slots_host, maxw, sizeof(int), cudaMemcpyDeviceToHost, h->stream);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
+  cudaFree(maxw);
+  if (e != cudaSuccess) return fail((int)e, std::string("galerkin: ") + cudaGetErrorString(e));
+  return 0;
+}
+
+int dmlmc_set_bsr_device(dmlmc_hier* h, int level, int n, int bs, int bpr, const int32_t* colidx_dev, const void* vals_dev) {
+  if (h) invalidate_graphs(h);
+  CHECK(h && level >= 0 && level < h->n_levels, "set_bsr_device: bad handle/level");
+  CHECK(bs == 1 || bs == 2 || bs == 4 || bs == 8, "set_bsr_device: block size must be 1, 2, 4 or 8");
+  CHECK(n > 0 && n % bs == 0 && bpr >= 1 && colidx_dev && vals_dev, "set_bsr_device: bad arguments");
+  CU(cudaSetDevice(h->device));
+  Level& L = h->lv[level];
+  L.kind = 1; L.n = n; L.bs = bs; L.bpr = bpr; L.nb = n / bs;
+  const size_t nc = (size_t)L.nb * bpr, cnt = nc * bs * bs;
+  int* col = nullptr; Cx<double>* vd = nullptr; Cx<float>* vf = nullptr; float4* v4 = nullptr;
+  CU(cudaMalloc(&col, nc * sizeof(int))); h->owned.push_back(col);
+  CU(cudaMalloc(&vd, cnt * sizeof(Cx<double>))); h->owned.push_back(vd);
+  CU(cudaMalloc(&vf, cnt * sizeof(Cx<float>))); h->owned.push_back(vf);
+  CU(cudaMalloc(&v4, cnt * sizeof(float4))); h->owned.push_back(v4);
+  CU(cudaMemcpyAsync(col, colidx_dev, nc * sizeof(int), cudaMemcpyDeviceToDevice, h->stream));
+  CU(cudaMemcpyAsync(vd, vals_dev, cnt * sizeof(Cx<double>), cudaMemcpyDeviceToDevice, h->stream));
+  dense_formats_kernel<<<nblocks(cnt, 256), 256, 0, h->stream>>>(vd, cnt, vf, v4); LAUNCH_CHECK(h);
+  CU(cudaStreamSynchronize(h->stream));
+  L.bsr_col = col; L.d.bsr_vals = vd; L.f.bsr_vals = vf; L.bsr_vals4 = v4;
+  return 0;
+}
+
+int dmlmc_dense_inverse(dmlmc_hier* h, int n, void* m_dev) {
+  CHECK(h != nullptr, "NULL handle"); CU(cudaSetDevice(h->device));
+  CHECK(m_dev && n >= 1 && n <= GJ_MAX_N, "dense_inverse: n must be in [1, 1024]");
+  int* aux = nullptr;
+  CU(cudaMalloc(&aux, (size_t)(n + 1) * sizeof(int)));
+  dense_inverse_kernel<<<1, 1024, 0, h->stream>>>((Cx<double>*)m_dev, n, aux, aux + n);
+  h->launches++;
+  int info = 0;
+  cudaError_t e = cudaGetLastError();
+  if (e == cudaSuccess) e = cudaMemcpyAsync(&info, aux + n, sizeof(int), cudaMemcpyDeviceToHost, h->stream);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
+  cudaFree(aux);
+  if (e != cudaSuccess) return fail((int)e, std::string("dense_inverse: ") + cudaGetErrorString(e));
+  CHECK(info == 0, "dense_inverse: the matrix is singular (zero pivot)");
   return 0;
 }
 

@@ -1391,7 +1391,7 @@ cvt_cols_kernel(const Cx<Tin>* __restrict__ in, size_t ld_in, Cx<Tout>* __restri
 // ev: [n][ld] row-major (first nvec columns used), pv: [n][nvec].  Dynamic shared memory: warps_per_block * mrows * nvec complex.
 __global__ void __launch_bounds__(128)
 prolongator_values_kernel(const Cx<double>* __restrict__ ev, int ld, int n, int aggr_size, int dofi, int nvec,
-                          Cx<double>* __restrict__ pv) {
+                          Cx<double>* __restrict__ pv, const int* __restrict__ rows, int passes) {
   extern __shared__ double2 pvk_smem[];
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5, wpb = blockDim.x >> 5;
   const long long item = (long long)blockIdx.x * wpb + wib;            // (aggregate, half)
@@ -1401,14 +1401,20 @@ prolongator_values_kernel(const Cx<double>* __restrict__ ev, int ld, int n, int 
   const int half = (int)(item & 1);
   const size_t base = (size_t)(item >> 1) * aggr_size;
   double2* B = pvk_smem + (size_t)wib * mrows * nvec;                  // B[q * nvec + v]
+  // rows != nullptr: the block's rows are rows[item * mrows + q] (indexed aggregates of the geometric hierarchies)
+  auto row_of = [&](int q) -> size_t {
+    return rows != nullptr ? (size_t)rows[(size_t)item * mrows + q] : base + (size_t)(q / hd) * dofi + (q % hd) + half * hd;
+  };
   for (int idx = lane; idx < mrows * nvec; idx += 32) {
     const int q = idx / nvec, v = idx - q * nvec;
-    const size_t row = base + (size_t)(q / hd) * dofi + (q % hd) + half * hd;
-    const Cx<double> e = ev[row * ld + v];
+    const Cx<double> e = ev[row_of(q) * ld + v];
     B[idx] = make_double2(e.re, e.im);
   }
   __syncwarp();
   for (int c = 0; c < nvec; ++c) {
+   // passes = 2: the projections are taken and subtracted a second time before the normalisation (blocks whose test-vector
+   // pieces are nearly dependent; the reference's aggregates use one pass, multigrid.py:232-259)
+   for (int pass = 0; pass < passes; ++pass) {
     // rs[w] = <col_w, col_c> for w < c, from the unmodified column c
     double2 rs[16];
     for (int w = 0; w < c; ++w) {
@@ -1431,6 +1437,7 @@ prolongator_values_kernel(const Cx<double>* __restrict__ ev, int ld, int n, int 
       }
       __syncwarp();
     }
+   }
     double sq = 0.0;
     for (int q = lane; q < mrows; q += 32) { const double2 b = B[q * nvec + c]; sq += b.x * b.x + b.y * b.y; }
     for (int o = 16; o > 0; o >>= 1) sq += __shfl_xor_sync(0xffffffffu, sq, o);
@@ -1440,8 +1447,7 @@ prolongator_values_kernel(const Cx<double>* __restrict__ ev, int ld, int n, int 
   }
   for (int idx = lane; idx < mrows * nvec; idx += 32) {
     const int q = idx / nvec, v = idx - q * nvec;
-    const size_t row = base + (size_t)(q / hd) * dofi + (q % hd) + half * hd;
-    pv[row * nvec + v] = cx<double>(B[idx].x, B[idx].y);
+    pv[row_of(q) * nvec + v] = cx<double>(B[idx].x, B[idx].y);
   }
 }
 

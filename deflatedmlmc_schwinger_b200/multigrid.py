@@ -380,6 +380,19 @@ def bsr_padded(A, bs):
     return col, vals
 
 
+def csr_from_padded_bsr(col, vals):
+    """(colidx[nb][bpr] with -1 padding, vals[nb][bpr][bs][bs]) -> scipy CSR (the inverse of bsr_padded)"""
+    from scipy.sparse import bsr_matrix
+    col = np.asarray(col)
+    vals = np.asarray(vals)
+    nb, bs = col.shape[0], vals.shape[2]
+    mask = col >= 0
+    indptr = np.concatenate([[0], np.cumsum(mask.sum(axis=1))]).astype(np.int64)
+    M = bsr_matrix((vals[mask], col[mask].astype(np.int64), indptr), shape=(nb * bs, nb * bs)).tocsr()
+    M.eliminate_zeros()
+    return M
+
+
 def ell_padded(M):
     """scipy matrix -> (cols[n][w] with -1 padding, vals[n][w])."""
     M = csr_matrix(M)
@@ -488,6 +501,15 @@ class MG:
             # the caller passes the blocks of its rows and the lattice of the resulting coarse blocks
             first = params.get('geometric_first', None)
 
+        # The hierarchy is built ON the device (round 2): the level's operator is uploaded, the transfer operator's values are
+        # orthonormalised there, and the Galerkin product R A P (multigrid.py:276) is formed there straight in the padded
+        # block-sparse layout of the coarse-level kernels (dmlmc_galerkin); params['host_galerkin'] restores scipy's R*A*P.
+        gdev = None
+        self._gdev = None
+        if not params.get('host_galerkin', False):
+            gdev = _lib.Hierarchy(max_levels, self.device)
+            self._set_level0_operator(gdev, Al, params)
+
         for i in range(max_levels - 1):
             dofi = dof[i] if i == 0 else int(dof[i] / 2)
             dofip1 = int(dof[i + 1] / 2)
@@ -543,14 +565,24 @@ class MG:
                     cblk = geometric_blocks_coarse(geo[0], geo[1], n // (2 * geo[0] * geo[1]), bx, bt)
                 if cblk.shape[0] != n:
                     raise Exception("geometric aggregation: level size does not match the lattice")
-                pvals = block_orthonormal_values(eig_vecs, cblk, dofip1)
+                m_rows = n // (int(cblk.max()) + 1)
+                if gdev is None or params.get('host_prolongator', False) or m_rows * dofip1 * 16 > 48 * 1024:
+                    pvals = block_orthonormal_values(eig_vecs, cblk, dofip1)
+                else:           # classical Gram-Schmidt with re-orthogonalisation, all blocks at once on the device
+                    if m_rows < dofip1:
+                        raise Exception("geometric aggregation: aggregates smaller than the number of test vectors")
+                    pvals = gdev.block_orthonormal_values(eig_vecs, cblk, dofip1)[0].cpu().numpy()
                 Pl = prolongator_csr_indexed(pvals, cblk)
                 self._transfer_meta.append(("indexed", cblk, dofip1, pvals))
                 geo = [geo[0] // bx, geo[1] // bt]
                 ml.levels[i].P = Pl
                 Rl = Pl.conjugate().transpose().tocsr()
                 ml.levels[i].R = Rl
-                Al = (Rl * Al * Pl).tocsr()
+                if gdev is not None:
+                    gdev.set_transfer_indexed(i, n, dofip1, pvals, cblk)
+                    Al = self._device_galerkin(gdev, i, dofip1, Pl.shape[1])
+                else:
+                    Al = (Rl * Al * Pl).tocsr()
                 ml.levels.append(LevelML())
                 ml.levels[i + 1].A = Al.copy()
                 continue
@@ -562,15 +594,19 @@ class MG:
                 pvals = build_prolongator_values(eig_vecs, aggr_size, dofi, dofip1)      # bit-identical to the reference
             else:
                 # the same classical Gram-Schmidt, all aggregates at once on the device (values agree to ~1e-15)
-                if getattr(self, "_setup_dev", None) is None:
+                if gdev is None and getattr(self, "_setup_dev", None) is None:
                     self._setup_dev = _lib.Hierarchy(1, self.device)
-                pvals = self._setup_dev.prolongator_values(eig_vecs, aggr_size, dofi, dofip1).cpu().numpy()
+                pvals = (gdev or self._setup_dev).prolongator_values(eig_vecs, aggr_size, dofi, dofip1).cpu().numpy()
             Pl = prolongator_csr(pvals, aggr_size, dofi, dofip1)
             self._transfer_meta.append((aggr_size, dofi, dofip1, pvals))
             ml.levels[i].P = Pl
             Rl = Pl.conjugate().transpose().tocsr()
             ml.levels[i].R = Rl
-            Al = (Rl * Al * Pl).tocsr()
+            if gdev is not None:
+                gdev.set_transfer(i, n, aggr_size, dofi, dofip1, pvals)
+                Al = self._device_galerkin(gdev, i, dofip1, Pl.shape[1])
+            else:
+                Al = (Rl * Al * Pl).tocsr()
             ml.levels.append(LevelML())
             ml.levels[i + 1].A = Al.copy()
 
@@ -588,9 +624,48 @@ class MG:
             self._setup_dev.close()
             self._setup_dev = None
         self.ml = ml
-        self.coarsest_inv = np.linalg.inv(np.asarray(ml.levels[-1].A.todense()))
+        n_last = ml.levels[-1].A.shape[0]
+        if gdev is not None and n_last <= 1024 and not params.get('host_coarsest_inverse', False):
+            # multigrid.py:342-344 on the device (Gauss-Jordan with partial pivoting, dmlmc_dense_inverse)
+            self.coarsest_inv = gdev.dense_inverse(np.asarray(ml.levels[-1].A.todense())).cpu().numpy()
+        else:
+            self.coarsest_inv = np.linalg.inv(np.asarray(ml.levels[-1].A.todense()))
         self.level_shapes = [l.A.shape[0] for l in ml.levels]
+        self._gdev = gdev
         self._upload(params, use_permuted)
+
+    def _device_galerkin(self, gdev, i, nvec, n_coarse):
+        """A_{i+1} = R_i A_i P_i on the device (installed on level i + 1 of gdev); the scipy copy that the host-side consumers
+        of ml.levels[i + 1].A read (the reference's attribute) is assembled from the same numbers."""
+        col, vals = gdev.galerkin(i, nvec, n_coarse)
+        self._bsr_on_device = getattr(self, "_bsr_on_device", {})
+        self._bsr_on_device[i + 1] = (int(col.shape[1]), nvec)
+        return csr_from_padded_bsr(col.cpu().numpy(), vals.cpu().numpy())
+
+    def _set_level0_operator(self, dev, A0, params):
+        """level 0 on the device: link form if A is a Wilson-Dirac stencil, else generic padded rows (block size level0_block)"""
+        n0 = A0.shape[0]
+        dims = params.get('latt_dims', None)
+        if dims is None:
+            L = int(round(np.sqrt(n0 / 2)))
+            dims = [L, L]
+        try:
+            links, diag = lattice.links_from_matrix(A0, dims[1] if len(dims) > 1 else dims[0], dims[0])
+        except lattice.NotAStencil as why:
+            links = None
+            if params.get('geometric_first') is None:
+                # the caller's own matrix: say that the link-form kernels are not in use (orders of magnitude slower)
+                _warn("level 0 is not a Wilson-Dirac stencil on the %s lattice (%s): generic block-sparse kernels are used"
+                              % (dims, why))
+        if links is not None:
+            dev.set_stencil(0, links, diag)
+            self.level0_format = "stencil"
+            self._level0_diag = diag
+        else:
+            col, vals = bsr_padded(A0, self.level0_block)
+            dev.set_bsr(0, n0, self.level0_block, col, vals)
+            self.level0_format = "bsr%d" % self.level0_block
+        return dims
 
     def device_test_vectors(self, Al, nvec, tol, params, level, hint=None):
         """multigrid.py:174 (`eigs(Al, k=nvec, which='LM', sigma=0.0, tol)`) on the device: block Arnoldi on A_l^{-1}
@@ -675,30 +750,22 @@ class MG:
         """Re-lay out the hierarchy for the device kernels and copy it to the GPU once."""
         lv = self.ml.levels
         nl = len(lv)
-        dev = _lib.Hierarchy(nl, self.device)
-        # level 0: link form if A is a Wilson-Dirac stencil, else generic padded rows (bs = 1)
         A0 = lv[0].A
         n0 = A0.shape[0]
-        dims = params.get('latt_dims', None)
-        if dims is None:
-            L = int(round(np.sqrt(n0 / 2)))
-            dims = [L, L]
-        try:
-            links, diag = lattice.links_from_matrix(A0, dims[1] if len(dims) > 1 else dims[0], dims[0])
-        except lattice.NotAStencil as why:
-            links = None
-            if params.get('geometric_first') is None:
-                # the caller's own matrix: say that the link-form kernels are not in use (orders of magnitude slower)
-                _warn("level 0 is not a Wilson-Dirac stencil on the %s lattice (%s): generic block-sparse kernels are used"
-                              % (dims, why))
-        if links is not None:
-            dev.set_stencil(0, links, diag)
-            self.level0_format = "stencil"
+        on_dev = getattr(self, "_gdev", None) is not None          # operators and transfers are already there (setup)
+        if on_dev:
+            dev = self._gdev
+            self._gdev = None
+            dims = params.get('latt_dims', None)
+            if dims is None:
+                L = int(round(np.sqrt(n0 / 2)))
+                dims = [L, L]
+            diag = getattr(self, "_level0_diag", None)
         else:
-            col, vals = bsr_padded(A0, self.level0_block)
-            dev.set_bsr(0, n0, self.level0_block, col, vals)
-            self.level0_format = "bsr%d" % self.level0_block
-        for i in range(nl - 1):
+            dev = _lib.Hierarchy(nl, self.device)
+            dims = self._set_level0_operator(dev, A0, params)
+            diag = getattr(self, "_level0_diag", None)
+        for i in range(0 if not on_dev else nl - 1, nl - 1):
             if self._transfer_meta[i][0] == "indexed":
                 _, cblk, nvec, pvals = self._transfer_meta[i]
                 dev.set_transfer_indexed(i, lv[i].A.shape[0], nvec, pvals, cblk)

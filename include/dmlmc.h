@@ -32,7 +32,7 @@
 extern "C" {
 #endif
 
-#define DMLMC_ABI_VERSION 5
+#define DMLMC_ABI_VERSION 6
 
 enum { DMLMC_C128 = 0, DMLMC_C64 = 1 };
 
@@ -85,6 +85,23 @@ int dmlmc_set_dense_inverse_device(dmlmc_hier* h, int level, int n, const void* 
  * (which is bit-identical to the reference) ~1e-15, the summation order inside an inner product being the only difference. */
 int dmlmc_prolongator_values(dmlmc_hier* h, const void* eig_vecs_dev, int ld, int n, int aggr_size, int dofi, int nvec,
                              void* pvals_dev);
+/* The same orthonormalisation on INDEXED blocks (the geometric aggregates of the preconditioner hierarchies, where the
+ * reference has nothing to compare with): block b owns the m rows rows_dev[b*m .. b*m+m) (n / m blocks, m >= nvec);
+ * passes = 2 repeats the projection step once (classical Gram-Schmidt with re-orthogonalisation). */
+int dmlmc_block_orthonormal_values(dmlmc_hier* h, const void* vecs_dev, int ld, int n, int m, int nvec, const int32_t* rows_dev,
+                                   int passes, void* pvals_dev);
+/* Set-up, multigrid.py:276: the Galerkin product A_{level+1} = R A P on the device, from the operator (dmlmc_set_stencil /
+ * dmlmc_set_bsr[_device]) and the transfer operator (dmlmc_set_transfer[_indexed]) of `level`, written straight in the padded
+ * block-sparse layout of dmlmc_set_bsr with `cap` slots per block row: col_dev[n_c/nvec][cap] int32 (sorted block columns,
+ * -1 = padding), vals_dev[n_c/nvec][cap][nvec][nvec] complex128.  *slots_host = the number of slots the fullest row needs
+ * (the bpr to keep); cap + 1 if a row did not fit (call again with a larger cap).  One thread sums each output number in a
+ * fixed order: identical on every rank and launch; agreement with scipy's R*A*P ~1e-16 relative (summation order). */
+int dmlmc_galerkin(dmlmc_hier* h, int level, int cap, int32_t* col_dev, void* vals_dev, int* slots_host);
+/* dmlmc_set_bsr from DEVICE arrays (the output of dmlmc_galerkin, trimmed to bpr slots); the arrays are copied. */
+int dmlmc_set_bsr_device(dmlmc_hier* h, int level, int n, int bs, int bpr, const int32_t* colidx_dev, const void* vals_dev);
+/* Set-up, multigrid.py:342-344 (np.linalg.inv of the coarsest operator): in-place inverse of the dense complex128 device
+ * matrix m_dev[n][n], n <= 1024, by Gauss-Jordan elimination with partial pivoting (one thread block, matrix in L2). */
+int dmlmc_dense_inverse(dmlmc_hier* h, int n, void* m_dev);
 /* The same hand-over for an inverse kept in ALL precisions (what dmlmc_set_dense_inverse makes from a host array: the
  * complex128 and complex64 copies, the splatted FP32 operand and the tensor-core operands), from a complex128 device
  * array [n][n] -- the inverse never visits the host (multigrid.py:342-344 of the reference inverts on the host). */

@@ -25,7 +25,7 @@ def test_build_and_symbols():
     for name in names:
         assert hasattr(lib, name), "missing export " + name
     assert set(names) == set(_lib.EXPORTED_SYMBOLS)
-    assert _lib.load().dmlmc_abi_version() == 5
+    assert _lib.load().dmlmc_abi_version() == 6
 
 
 def test_header_cites_reference():
