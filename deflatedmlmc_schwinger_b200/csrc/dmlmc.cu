@@ -1698,14 +1698,23 @@ int dmlmc_set_bsr_device(dmlmc_hier* h, int level, int n, int bs, int bpr, const
 
 int dmlmc_dense_inverse(dmlmc_hier* h, int n, void* m_dev) {
   CHECK(h != nullptr, "NULL handle"); CU(cudaSetDevice(h->device));
-  CHECK(m_dev && n >= 1 && n <= GJ_MAX_N, "dense_inverse: n must be in [1, 1024]");
-  int* aux = nullptr;
-  CU(cudaMalloc(&aux, (size_t)(n + 1) * sizeof(int)));
-  dense_inverse_kernel<<<1, 1024, 0, h->stream>>>((Cx<double>*)m_dev, n, aux, aux + n);
-  h->launches++;
+  CHECK(m_dev && n >= 1 && n <= GJ_MAX_N, "dense_inverse: n must be in [1, 4096]");
+  char* aux = nullptr;                                                  // piv[n], info, rowk[n], colk[n]
+  const size_t ints = ((size_t)(n + 1) * sizeof(int) + 15) & ~(size_t)15;
+  CU(cudaMalloc(&aux, ints + 2 * (size_t)n * sizeof(double2)));
+  int* piv = reinterpret_cast<int*>(aux); int* info_d = piv + n;
+  double2* rowk = reinterpret_cast<double2*>(aux + ints); double2* colk = rowk + n;
+  cudaError_t e = cudaMemsetAsync(info_d, 0, sizeof(int), h->stream);
+  Cx<double>* M = (Cx<double>*)m_dev;
+  for (int k = 0; k < n && e == cudaSuccess; ++k) {
+    gj_pivot_kernel<<<1, 1024, 0, h->stream>>>(M, n, k, piv, info_d, rowk, colk);
+    gj_update_kernel<<<dim3((n + 127) / 128, n), 128, 0, h->stream>>>(M, n, k, rowk, colk);
+    h->launches += 2;
+    e = cudaGetLastError();
+  }
+  if (e == cudaSuccess) { gj_unscramble_kernel<<<(n + 127) / 128, 128, 0, h->stream>>>(M, n, piv); h->launches++; e = cudaGetLastError(); }
   int info = 0;
-  cudaError_t e = cudaGetLastError();
-  if (e == cudaSuccess) e = cudaMemcpyAsync(&info, aux + n, sizeof(int), cudaMemcpyDeviceToHost, h->stream);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(&info, info_d, sizeof(int), cudaMemcpyDeviceToHost, h->stream);
   if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
   cudaFree(aux);
   if (e != cudaSuccess) return fail((int)e, std::string("dense_inverse: ") + cudaGetErrorString(e));

@@ -125,90 +125,84 @@ galerkin_kernel(GalOp A, GalTr T, int cap, int* __restrict__ col_out, Cx<double>
   }
 }
 
-// In-place Gauss-Jordan inversion with partial (row) pivoting of a dense complex128 matrix M[n][n], n <= 1024, by ONE thread
-// block (the matrix stays in L2; n steps of a pivot search, a row swap and a rank-one update of the whole matrix), followed by
-// the column swaps that undo the row exchanges.  *info = 0, or k + 1 when the k-th pivot is exactly zero.  Replaces
-// np.linalg.inv (LAPACK getrf / getri, the same pivoting strategy) of multigrid.py:342-344.
-constexpr int GJ_MAX_N = 1024;
+// In-place Gauss-Jordan inversion with partial (row) pivoting of a dense complex128 matrix M[n][n] (the matrix stays in L2):
+// per step one single-block kernel (pivot search over column k, row exchange, scaled pivot row and the eliminated column saved
+// to rowk / colk) and one wide kernel (rank-one update of all other rows); at the end every row undoes the row exchanges on its
+// own entries (column swaps, last exchange first).  *info = k + 1 when the k-th pivot is exactly zero (cleared by the caller).
+// Replaces np.linalg.inv (LAPACK getrf / getri, the same pivoting strategy) of multigrid.py:342-344.
+constexpr int GJ_MAX_N = 4096;
 __global__ void __launch_bounds__(1024)
-dense_inverse_kernel(Cx<double>* __restrict__ M, int n, int* __restrict__ piv, int* __restrict__ info) {
-  __shared__ double2 rowk[GJ_MAX_N];
-  __shared__ double2 colk[GJ_MAX_N];
+gj_pivot_kernel(Cx<double>* __restrict__ M, int n, int k, int* __restrict__ piv, int* __restrict__ info,
+                double2* __restrict__ rowk, double2* __restrict__ colk) {
   __shared__ double red_v[32];
   __shared__ int red_i[32];
   __shared__ int s_p;
+  __shared__ double2 s_piv;
   const int tid = threadIdx.x, nt = blockDim.x, lane = tid & 31, wid = tid >> 5;
-  if (tid == 0) *info = 0;
-  for (int k = 0; k < n; ++k) {
-    // pivot: the largest |M[i][k]|, i >= k (first one on ties)
-    double best = -1.0; int bi = k;
-    for (int i = k + tid; i < n; i += nt) {
-      const Cx<double> v = M[(size_t)i * n + k];
-      const double a = v.re * v.re + v.im * v.im;
-      if (a > best) { best = a; bi = i; }
-    }
-    for (int o = 16; o > 0; o >>= 1) {
-      const double ob = __shfl_xor_sync(0xffffffffu, best, o); const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
-      if (ob > best || (ob == best && oi < bi)) { best = ob; bi = oi; }
-    }
-    if (lane == 0) { red_v[wid] = best; red_i[wid] = bi; }
-    __syncthreads();
-    if (tid == 0) {
-      double b = red_v[0]; int p = red_i[0];
-      for (int w = 1; w < (nt >> 5); ++w) if (red_v[w] > b || (red_v[w] == b && red_i[w] < p)) { b = red_v[w]; p = red_i[w]; }
-      s_p = p; piv[k] = p;
-      if (!(b > 0.0) && *info == 0) *info = k + 1;
-    }
-    __syncthreads();
-    const int p = s_p;
-    // swap rows k and p; keep the (new) row k and column k in shared memory
-    for (int j = tid; j < n; j += nt) {
-      const Cx<double> a = M[(size_t)p * n + j];
-      if (p != k) { M[(size_t)p * n + j] = M[(size_t)k * n + j]; }
-      rowk[j] = make_double2(a.re, a.im);
-    }
-    __syncthreads();
-    for (int i = tid; i < n; i += nt) {
-      Cx<double> f;
-      if (i == k) f = cx<double>(rowk[k].x, rowk[k].y);
-      else f = M[(size_t)i * n + k];
-      colk[i] = make_double2(f.re, f.im);
-    }
-    __syncthreads();
-    // row k <- row k / pivot with a 1 in the pivot position first; other rows: M[i][:] -= f_i * row k with M[i][k] = 0 first
-    const double pr = colk[k].x, pi = colk[k].y, pd = pr * pr + pi * pi;
-    const double qr = pr / pd, qi = -pi / pd;                             // 1 / pivot
-    for (int j = tid; j < n; j += nt) {
-      double2 a = (j == k) ? make_double2(1.0, 0.0) : rowk[j];
-      const double2 s = make_double2(a.x * qr - a.y * qi, a.x * qi + a.y * qr);
-      rowk[j] = s;
-      M[(size_t)k * n + j] = cx<double>(s.x, s.y);
-    }
-    __syncthreads();
-    for (int i = wid; i < n; i += (nt >> 5)) {
-      if (i == k) continue;
-      const double2 f = colk[i];
-      Cx<double>* Mi = M + (size_t)i * n;
-      for (int j = lane; j < n; j += 32) {
-        const double2 rk = rowk[j];
-        Cx<double> a = (j == k) ? cx<double>(0.0, 0.0) : Mi[j];
-        a.re = fma(-f.x, rk.x, fma(f.y, rk.y, a.re));
-        a.im = fma(-f.x, rk.y, fma(-f.y, rk.x, a.im));
-        Mi[j] = a;
-      }
-    }
-    __syncthreads();
+  // pivot: the largest |M[i][k]|, i >= k (first one on ties)
+  double best = -1.0; int bi = k;
+  for (int i = k + tid; i < n; i += nt) {
+    const Cx<double> v = M[(size_t)i * n + k];
+    const double a = v.re * v.re + v.im * v.im;
+    if (a > best) { best = a; bi = i; }
   }
-  // undo the row exchanges: swap columns piv[k] and k, last exchange first
+  for (int o = 16; o > 0; o >>= 1) {
+    const double ob = __shfl_xor_sync(0xffffffffu, best, o); const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+    if (ob > best || (ob == best && oi < bi)) { best = ob; bi = oi; }
+  }
+  if (lane == 0) { red_v[wid] = best; red_i[wid] = bi; }
+  __syncthreads();
+  if (tid == 0) {
+    double b = red_v[0]; int p = red_i[0];
+    for (int w = 1; w < (nt >> 5); ++w) if (red_v[w] > b || (red_v[w] == b && red_i[w] < p)) { b = red_v[w]; p = red_i[w]; }
+    s_p = p; piv[k] = p;
+    if (!(b > 0.0) && *info == 0) *info = k + 1;
+    const Cx<double> pv = M[(size_t)p * n + k];
+    s_piv = make_double2(pv.re, pv.im);
+  }
+  __syncthreads();
+  const int p = s_p;
+  const double pr = s_piv.x, pi = s_piv.y, pd = pr * pr + pi * pi;
+  const double qr = pr / pd, qi = -pi / pd;                               // 1 / pivot
+  // row exchange k <-> p; the new row k is divided by the pivot, with a 1 in the pivot position first
+  for (int j = tid; j < n; j += nt) {
+    const Cx<double> a = M[(size_t)p * n + j];
+    if (p != k) M[(size_t)p * n + j] = M[(size_t)k * n + j];
+    const double ar = (j == k) ? 1.0 : a.re, ai = (j == k) ? 0.0 : a.im;
+    const double2 s = make_double2(ar * qr - ai * qi, ar * qi + ai * qr);
+    rowk[j] = s;
+    M[(size_t)k * n + j] = cx<double>(s.x, s.y);
+  }
+  __syncthreads();
+  // the column that the update eliminates (after the exchange; row k itself is not updated)
+  for (int i = tid; i < n; i += nt) {
+    const Cx<double> f = (i == k) ? cx<double>(0.0, 0.0) : M[(size_t)i * n + k];
+    colk[i] = make_double2(f.re, f.im);
+  }
+}
+
+// M[i][:] -= f_i * row k  (with M[i][k] = 0 first) for every row i != k; grid (ceil(n / 128), n)
+__global__ void __launch_bounds__(128)
+gj_update_kernel(Cx<double>* __restrict__ M, int n, int k, const double2* __restrict__ rowk, const double2* __restrict__ colk) {
+  const int i = blockIdx.y, j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i == k || j >= n) return;
+  const double2 f = colk[i], rk = rowk[j];
+  Cx<double>* Mi = M + (size_t)i * n;
+  Cx<double> a = (j == k) ? cx<double>(0.0, 0.0) : Mi[j];
+  a.re = fma(-f.x, rk.x, fma(f.y, rk.y, a.re));
+  a.im = fma(-f.x, rk.y, fma(-f.y, rk.x, a.im));
+  Mi[j] = a;
+}
+
+// undo the row exchanges: in every row swap the entries of columns piv[k] and k, last exchange first (one thread per row)
+__global__ void __launch_bounds__(128)
+gj_unscramble_kernel(Cx<double>* __restrict__ M, int n, const int* __restrict__ piv) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  Cx<double>* Mi = M + (size_t)i * n;
   for (int k = n - 1; k >= 0; --k) {
-    const int p = piv[k];
-    if (p != k)
-      for (int i = tid; i < n; i += nt) {
-        const Cx<double> a = M[(size_t)i * n + k];
-        M[(size_t)i * n + k] = M[(size_t)i * n + p];
-        M[(size_t)i * n + p] = a;
-      }
-    __syncthreads();
+    const int p = __ldg(piv + k);
+    if (p != k) { const Cx<double> a = Mi[k]; Mi[k] = Mi[p]; Mi[p] = a; }
   }
 }
 

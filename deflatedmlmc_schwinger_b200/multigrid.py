@@ -246,7 +246,7 @@ def harmonic_ritz_inv_roots_device(apply, n, degree, device, seed=7):
     for j in range(degree):
         w = apply(V[j].reshape(n, 1)).reshape(n)
         for _ in range(2):
-            hh = V[:j + 1].conj() @ w
+            hh = torch.mv(V[:j + 1], w.conj_physical()).conj_physical()      # V^* w without a conjugated copy of the basis
             H[:j + 1, j] += hh
             w = w - hh @ V[:j + 1]
         nw = torch.linalg.vector_norm(w)
@@ -625,7 +625,7 @@ class MG:
             self._setup_dev = None
         self.ml = ml
         n_last = ml.levels[-1].A.shape[0]
-        if gdev is not None and n_last <= 1024 and not params.get('host_coarsest_inverse', False):
+        if gdev is not None and n_last <= 2048 and not params.get('host_coarsest_inverse', False):
             # multigrid.py:342-344 on the device (Gauss-Jordan with partial pivoting, dmlmc_dense_inverse)
             self.coarsest_inv = gdev.dense_inverse(np.asarray(ml.levels[-1].A.todense())).cpu().numpy()
         else:
@@ -642,6 +642,22 @@ class MG:
         self._bsr_on_device[i + 1] = (int(col.shape[1]), nvec)
         return csr_from_padded_bsr(col.cpu().numpy(), vals.cpu().numpy())
 
+    def _links_of(self, dims):
+        """lattice.links_from_matrix of the level-0 matrix self.A, once per matrix object (the check rebuilds the matrix from
+        the links on the host; the hierarchies that precondition this one are built on the same object and share the answer)"""
+        cache = getattr(self, "_links_cache", None)
+        if cache is not None and cache[0] is self.A:
+            if isinstance(cache[1], Exception):
+                raise cache[1]
+            return cache[1]
+        try:
+            out = lattice.links_from_matrix(self.A, dims[1] if len(dims) > 1 else dims[0], dims[0])
+        except lattice.NotAStencil as why:
+            self._links_cache = (self.A, why)
+            raise
+        self._links_cache = (self.A, out)
+        return out
+
     def _set_level0_operator(self, dev, A0, params):
         """level 0 on the device: link form if A is a Wilson-Dirac stencil, else generic padded rows (block size level0_block)"""
         n0 = A0.shape[0]
@@ -650,7 +666,7 @@ class MG:
             L = int(round(np.sqrt(n0 / 2)))
             dims = [L, L]
         try:
-            links, diag = lattice.links_from_matrix(A0, dims[1] if len(dims) > 1 else dims[0], dims[0])
+            links, diag = self._links_of(dims)
         except lattice.NotAStencil as why:
             links = None
             if params.get('geometric_first') is None:
@@ -685,7 +701,7 @@ class MG:
                 Ls = int(round(np.sqrt(n / 2)))
                 dims = [Ls, Ls]
             try:
-                links, diag = lattice.links_from_matrix(Al, dims[1] if len(dims) > 1 else dims[0], dims[0])
+                links, diag = self._links_of(dims)
                 dev.set_stencil(0, links, diag)
                 fmt = "stencil"
             except lattice.NotAStencil:
@@ -720,6 +736,31 @@ class MG:
         if hint is not None:
             X0[:, :hint.shape[1]] = torch.from_numpy(np.ascontiguousarray(hint))
         X0 = X0.to(dev.device)
+        # Two-stage bootstrap (large stencil levels): FGMRES preconditioned by a polynomial alone needs ~200 iterations per
+        # solve there.  Stage 1: the start block is smoothed, X <- orth(p(A) X), a few times (approximate inverse iteration
+        # with no solves) and its Ritz vectors of smallest modulus serve as ROUGH test vectors of a geometric hierarchy;
+        # stage 2: the block Arnoldi run below is preconditioned by that hierarchy's V-cycle.  The eigenvectors it returns
+        # meet the same residual test either way.
+        pm0 = None
+        two_stage = fmt == "stencil" and hint is None and self.geometric_precond and \
+            n >= int(params.get('two_stage_min_n', 100000)) and self._geometric_precond_possible(params)
+        if two_stage:
+            X = X0
+            for _ in range(int(params.get('two_stage_smoothing_passes', 4))):
+                X, _ = torch.linalg.qr(dev.smooth(0, X.contiguous()))
+            Hs = (X.conj().T @ dev.spmm(0, X.contiguous())).cpu().numpy()
+            th, S = np.linalg.eig(Hs)
+            keep = np.argsort(np.abs(th), kind='stable')
+            X0 = X @ torch.from_numpy(np.ascontiguousarray(S[:, keep])).to(X.device)
+            X0 = X0 / torch.linalg.vector_norm(X0, dim=0, keepdim=True)
+            rough = X0[:, :nvec].cpu().numpy()
+            p2 = dict(params)
+            p2['two_stage_min_n'] = 1 << 62
+            pm0 = self._make_geometric_hierarchy(p2, rough)
+            if pm0 is not None:
+                dev.set_option("precond_smoother_only", 0)
+                dev.set_inner_precision(_lib.C64 if self.inner_precision == "c64" else _lib.C128)
+                dev.set_preconditioner(0, pm0.dev, 0)
         maxit = n if n < 4000 else 4000
         restart = min(self.restart, maxit)
         solve_tol = min(1e-4, max(1e-12, 1e-2 * tol))      # the Arnoldi relation needs the solves two digits below the target
@@ -738,11 +779,17 @@ class MG:
                                                              min_blocks=3 if hint is not None else 1)
         if not info["converged"]:
             raise Exception("test-vector eigensolver did not converge on level %d (residuals %s)" % (level, res))
-        info.update({"theta": theta, "residuals": res, "fgmres_iters": stats["iters"], "block": p, "bootstrap_degree": deg})
+        info.update({"theta": theta, "residuals": res, "fgmres_iters": stats["iters"], "block": p, "bootstrap_degree": deg,
+                     "two_stage": pm0 is not None})
         self.test_vector_info = getattr(self, "test_vector_info", {})
         self.test_vector_info[level] = info
         out = X.cpu().numpy()
         dev.release_workspace()
+        if pm0 is not None:
+            dev.set_preconditioner(0, None)
+            for sub in [pm0.precond_mg, pm0.precond_mg1] + list(getattr(pm0, "precond_mg_coarse", {}).values()) + [pm0]:
+                if sub is not None and sub.dev is not None:
+                    sub.dev.close()
         dev.close()
         return out
 
@@ -874,7 +921,7 @@ class MG:
 
     def _geometric_precond_possible(self, params):
         dims = params.get('latt_dims', None)
-        n0 = self.ml.levels[0].A.shape[0]
+        n0 = self.A.shape[0]
         if dims is None:
             Ls = int(round(np.sqrt(n0 / 2)))
             dims = [Ls, Ls]
@@ -887,8 +934,22 @@ class MG:
         number of test vectors per level, level-0 test vectors shared with the estimator's hierarchy) whose V-cycle
         preconditions the level-0 FGMRES.  Skipped (the estimator's own hierarchy preconditions) when the lattice does
         not divide into the blocks."""
+        pm = self._make_geometric_hierarchy(params, self.test_vectors[0])
+        if pm is None:
+            return
         dims = params.get('latt_dims', None)
-        n0 = self.ml.levels[0].A.shape[0]
+        if dims is None:
+            Ls = int(round(np.sqrt(self.A.shape[0] / 2)))
+            dims = [Ls, Ls]
+        LX, LT = (dims[1] if len(dims) > 1 else dims[0]), dims[0]
+        self.precond_mg = pm
+        self.dev.set_preconditioner(0, pm.dev, 0)
+        self._build_level1_preconditioner(params, LX, LT)
+
+    def _make_geometric_hierarchy(self, params, tv0):
+        """the geometric hierarchy of level 0 built from the level-0 vectors tv0 (None when the lattice does not divide)"""
+        dims = params.get('latt_dims', None)
+        n0 = self.A.shape[0]
         if dims is None:
             Ls = int(round(np.sqrt(n0 / 2)))
             dims = [Ls, Ls]
@@ -896,7 +957,7 @@ class MG:
         bx, bt = self.precond_blocks
         sa = self._setup_args
         if not self._geometric_precond_possible(params):
-            return
+            return None
         # levels: blocks of bx x bt sites, then 2 x 2, until the level is small enough for a host-side dense inverse
         nv = [int(d // 2) for d in sa['dof'][1:]]
         gx, gt = LX // bx, LT // bt
@@ -912,15 +973,14 @@ class MG:
         pm = MG(self.A, smoother_degree=degs, restart=self.restart, inner_precision=self.inner_precision,
                 device=self.device, dense_coarse_threshold=self.dense_coarse_threshold, pre_smooth=self.pre_smooth,
                 aggregation="geometric", precond_blocks=self.precond_blocks, eo_degree=self.precond_eo_degree)
+        pm._links_cache = getattr(self, "_links_cache", None)
         p2 = dict(params)
         p2['use_permuted'] = False
         p2['latt_dims'] = [LT, LX]
         p2.pop('geometric_first', None)
         pm.setup(dof=dof, aggrs=[bx * bt] + [4] * (levels - 2), max_levels=levels, acc_eigvs=sa['acc_eigvs'],
-                 params=p2, test_vectors=[self.test_vectors[0]])
-        self.precond_mg = pm
-        self.dev.set_preconditioner(0, pm.dev, 0)
-        self._build_level1_preconditioner(params, LX, LT)
+                 params=p2, test_vectors=[tv0])
+        return pm
 
     def _build_level1_preconditioner(self, params, LX, LT):
         """Geometric preconditioner hierarchies for the estimator's COARSE-level solves on lattices whose level l >= 1 is too

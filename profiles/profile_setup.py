@@ -11,6 +11,8 @@ ap.add_argument("--L", type=int, default=0)
 ap.add_argument("--mass", type=float, default=-0.062)
 ap.add_argument("--lines", type=int, default=45)
 ap.add_argument("--uninjected", action="store_true", help="128^2 without the golden test vectors")
+ap.add_argument("--no-two-stage", action="store_true", help="level-0 eigensolve preconditioned by the polynomial only (round-2 run 5)")
+ap.add_argument("--host-galerkin", action="store_true", help="scipy R*A*P, host QR and np.linalg.inv instead of the device set-up")
 args = ap.parse_args()
 import numpy as np
 import torch
@@ -40,6 +42,10 @@ def build():
     nlev = len(sizes)
     params = {"use_permuted": False, "latt_dims": [L, L], "x_displacement": 2, "test_vectors_type": "EVs",
               "function_params": {"tol": 1e-12}}
+    if args.no_two_stage:
+        params["two_stage_min_n"] = 1 << 62
+    if args.host_galerkin:
+        params["host_galerkin"] = True
     mg = multigrid.MG(A, smoother_degree=80, geometric_precond=True, precond_degree=36)
     mg.setup(dof=[2] + [8] * (nlev - 1), aggrs=[16] + [4] * (nlev - 2), max_levels=nlev, acc_eigvs="low", params=params)
     return mg

@@ -90,6 +90,32 @@ def test_device_test_vectors_128_span_the_reference_subspace(g128):
 
 
 @pytest.mark.gpu
+def test_two_stage_bootstrap_128_gives_the_same_test_vectors(g128):
+    """The two-stage bootstrap of large lattices (smoothed start block -> rough geometric hierarchy -> block Arnoldi
+    preconditioned by its V-cycle), forced on at 128^2: the same invariant subspace, the same residual bound, an order of
+    magnitude fewer FGMRES iterations than the polynomial-preconditioned solves of the test above."""
+    from deflatedmlmc_schwinger_b200 import matrix, multigrid, utils
+    p = params128()
+    tp = utils.trace_params_from_params(p, "mlmc")
+    tp["two_stage_min_n"] = 0
+    A = matrix.loadMatrix(p["matrix"], p["matrix_params"])
+    mg = multigrid.MG(A)
+    mg._transfer_meta = []
+    mg._setup_args = dict(dof=list(tp["dof"]), aggrs=list(tp["aggrs"]), max_levels=tp["max_nr_levels"],
+                          acc_eigvs=tp["accuracy_mg_eigvs"])
+    V = mg.device_test_vectors(A.tocsr(), 4, 1e-9, tp, 0)
+    info = mg.test_vector_info[0]
+    print("two-stage level-0 test vectors:", info["theta"], "residuals", info["residuals"], "block solves", info["block_solves"],
+          "FGMRES iterations", info["fgmres_iters"])
+    assert info["two_stage"]
+    assert info["residuals"].max() <= 1e-9
+    assert np.all(np.abs(A @ V - V * info["theta"][None, :]).max(axis=0) < 1e-8)
+    assert info["theta"][3].imag > 0
+    assert _cos_min(V, g128["tv0"]) > 1 - 1e-8
+    assert info["fgmres_iters"] < 200
+
+
+@pytest.mark.gpu
 def test_uninjected_setup_16_reproduces_the_reference_hierarchy(g16):
     """MG.setup without injected test vectors (device eigensolver on every level): the level operators equal those built
     from the reference's own test vectors, because they depend on the test vectors only through their span."""
