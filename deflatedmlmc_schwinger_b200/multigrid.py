@@ -231,18 +231,24 @@ def _harmonic_ritz_from_hessenberg(H, degree):
     return 1.0 / np.array(out, dtype=np.complex128)
 
 
-def harmonic_ritz_inv_roots_device(apply, n, degree, device, seed=7):
+def harmonic_ritz_inv_roots_device(apply, n, degree, device, seed=7, support=None):
     """The same Arnoldi run with the operator applied on the device (`apply`: torch complex128 [n, 1] -> [n, 1], the level's
     SpMM kernel) and the basis kept there; the start vector is the host version's, so both give the same polynomial up to
-    rounding.  The (degree + 1) x degree Hessenberg matrix comes back once at the end."""
+    rounding.  The (degree + 1) x degree Hessenberg matrix comes back once at the end.  support: the operator acts on the
+    rows `support` of the n-vectors only (the even sites of the even-odd Schur complement); the host version's start vector
+    of that length is scattered there."""
     import torch
-    degree = int(min(degree, n - 1))
+    m = n if support is None else int(support.shape[0])
+    degree = int(min(degree, m - 1))
     rs = np.random.RandomState(seed)
-    b = rs.standard_normal(n) + 1j * rs.standard_normal(n)
+    b = rs.standard_normal(m) + 1j * rs.standard_normal(m)
     b /= np.linalg.norm(b)
     V = torch.zeros((degree + 1, n), dtype=torch.complex128, device=device)
     H = torch.zeros((degree + 1, degree), dtype=torch.complex128, device=device)
-    V[0] = torch.from_numpy(b).to(device)
+    if support is None:
+        V[0] = torch.from_numpy(b).to(device)
+    else:
+        V[0, support] = torch.from_numpy(b).to(device)
     for j in range(degree):
         w = apply(V[j].reshape(n, 1)).reshape(n)
         for _ in range(2):
@@ -362,6 +368,54 @@ def smoother_storage_error_device(dev, level, nu, p0, storage):
     if not bool(torch.isfinite(E.real).all()) or not bool(torch.isfinite(E.imag).all()):
         return np.inf
     return float((torch.linalg.vector_norm(E - Eref) / torch.linalg.vector_norm(Eref)).item())
+
+
+def even_odd_schur_device(dev, LX, LT, c):
+    """S = c - H_eo H_oe / c of the stencil on level 0 of `dev` as a callable on FULL-lattice column batches that vanish on
+    the odd sites (two applications of the level's SpMM kernel and two masks), for complex128 and complex64 input.  Returns
+    (apply_S, even_rows): even_rows = the rows of the even sites in increasing order, the ordering of even_odd_schur's S."""
+    import torch
+    s, x, t = np.meshgrid(np.arange(2), np.arange(LX), np.arange(LT), indexing='ij')
+    par = ((x + t) & 1).ravel()
+    pe = torch.from_numpy((par == 0).astype(np.float64).reshape(-1, 1)).to(dev.device)
+    po = 1.0 - pe
+    masks = {torch.complex128: (pe, po), torch.complex64: (pe.to(torch.float32), po.to(torch.float32))}
+    even_rows = torch.from_numpy(np.where(par == 0)[0]).to(dev.device)
+
+    def apply_S(X):
+        me, mo = masks[X.dtype]
+        W = dev.spmm(0, X.contiguous()) * mo                 # H_oe x_e on the odd sites
+        Z = dev.spmm(0, W.contiguous()) * me                 # H_eo H_oe x_e on the even sites
+        return c * X - Z / c
+    return apply_S, even_rows
+
+
+def smoother_storage_error_op(apply, n, support, omega, nu, p0, device):
+    """smoother_storage_error for an operator given as a device callable (complex128 and complex64 column batches [n, 1]
+    supported on the rows `support`): the product form evaluated in complex64 with BF16-stored intermediates against the
+    Richardson form in complex128, same start vector as the host version."""
+    import torch
+    m = int(support.shape[0])
+    rs = np.random.RandomState(11)
+    b = rs.standard_normal(m) + 1j * rs.standard_normal(m)
+    b /= np.linalg.norm(b)
+    B = torch.zeros((n, 1), dtype=torch.complex128, device=device)
+    B[support, 0] = torch.from_numpy(b).to(device)
+    r = B.clone()
+    e = torch.zeros_like(B)
+    for i, wi in enumerate(omega):
+        e = e + complex(wi) * r
+        if i < len(omega) - 1:
+            r = r - complex(wi) * apply(r)
+    y = (64.0 * B).to(torch.complex64)
+    for i, v in enumerate(nu):
+        y = y - complex(np.complex64(v)) * apply(y)
+        if i < len(nu) - 1:
+            y = torch.view_as_complex(torch.view_as_real(y).to(torch.bfloat16).to(torch.float32))
+        if not bool(torch.isfinite(torch.view_as_real(y)).all()):
+            return np.inf
+    y = (complex(p0) / 64.0) * y.to(torch.complex128)
+    return float((torch.linalg.vector_norm(y - e) / torch.linalg.vector_norm(e)).item())
 
 
 def bsr_padded(A, bs):
@@ -731,11 +785,11 @@ class MG:
         dev.set_option("precond_smoother_only", 1)
         p = int(params.get('eigensolver_block', max(4 * nvec, 16)))
         p = max(nvec, min(p, n // 4))
-        gen = torch.Generator().manual_seed(20240531 + level)
-        X0 = torch.complex(torch.randn(n, p, dtype=torch.float64, generator=gen), torch.randn(n, p, dtype=torch.float64, generator=gen))
+        gen = torch.Generator(device=dev.device).manual_seed(20240531 + level)      # (Philox: the same block on every rank)
+        X0 = torch.complex(torch.randn(n, p, dtype=torch.float64, generator=gen, device=dev.device),
+                           torch.randn(n, p, dtype=torch.float64, generator=gen, device=dev.device))
         if hint is not None:
-            X0[:, :hint.shape[1]] = torch.from_numpy(np.ascontiguousarray(hint))
-        X0 = X0.to(dev.device)
+            X0[:, :hint.shape[1]] = torch.from_numpy(np.ascontiguousarray(hint)).to(dev.device)
         # Two-stage bootstrap (large stencil levels): FGMRES preconditioned by a polynomial alone needs ~200 iterations per
         # solve there.  Stage 1: the start block is smoothed, X <- orth(p(A) X), a few times (approximate inverse iteration
         # with no solves) and its Ritz vectors of smallest modulus serve as ROUGH test vectors of a geometric hierarchy;
@@ -865,16 +919,23 @@ class MG:
                 if LXs % 2 or LTs % 2 or abs(complex(diag).imag) > 0:
                     _warn("even-odd smoother not used: odd lattice extent or complex mass")
                 else:
-                    S, _c = even_odd_schur(lv[0].A, LXs, LTs)
+                    eo_on_device = n0 >= 4096 and not params.get('host_smoother_setup', False)
+                    if eo_on_device:    # Arnoldi and storage check of the Schur complement through the device SpMM
+                        apply_S, even_rows = even_odd_schur_device(dev, LXs, LTs, float(complex(diag).real))
+                    else:
+                        S, _c = even_odd_schur(lv[0].A, LXs, LTs)
                     de = int(self.eo_degree)
                     while de >= 2:
-                        om = harmonic_ritz_inv_roots(S, de)
+                        om = harmonic_ritz_inv_roots_device(apply_S, n0, de, dev.device, support=even_rows) if eo_on_device \
+                            else harmonic_ritz_inv_roots(S, de)
                         try:
                             nue, p0e = smoother_product_form(om)
                         except SmootherPolynomialError:
                             de = (3 * de) // 4
                             continue
-                        if smoother_storage_error(S, om, nue, p0e, 'bf16') < 0.15:
+                        err_eo = smoother_storage_error_op(apply_S, n0, even_rows, om, nue, p0e, dev.device) if eo_on_device \
+                            else smoother_storage_error(S, om, nue, p0e, 'bf16')
+                        if err_eo < 0.15:
                             dev.set_smoother_eo(0, nue, p0e)
                             self.eo_poly = (nue, p0e)
                             break
@@ -915,7 +976,9 @@ class MG:
             del Minv
         dev.release_workspace()
         import torch
-        torch.cuda.empty_cache()
+        free_b, total_b = torch.cuda.mem_get_info(dev.device)
+        if free_b < 0.5 * total_b:       # the library allocates its operators with cudaMalloc, outside torch's cache
+            torch.cuda.empty_cache()
         if self.geometric_precond and self.level0_format == "stencil":
             self._build_geometric_preconditioner(params)
 

@@ -119,3 +119,39 @@ def test_setup_16_device_and_host_builds_give_the_same_samples(g16):
         ed, _ = md.dev.level_sample(1, lf, lf + 1, Xl, 1e-12, 40, 1000)
         eh, _ = mh.dev.level_sample(1, lf, lf + 1, Xl, 1e-12, 40, 1000)
         assert np.abs(ed.cpu().numpy() - eh.cpu().numpy()).max() < 1e-9 * np.abs(eh.cpu().numpy()).max()
+
+
+def test_even_odd_smoother_setup_on_the_device_matches_the_host(mg128):
+    """the Schur complement as a device callable against scipy's S; the GMRES polynomial of S from the device Arnoldi run against
+    the host's (same start vector): the same polynomial as a function on the spectrum; the BF16-storage check agrees"""
+    import torch
+    from deflatedmlmc_schwinger_b200 import multigrid as mgm
+    mg, _, A = mg128
+    pm = mg.precond_mg                      # the hierarchy whose level 0 carries the even-odd smoother
+    L = 128
+    c = 4.0 + params128()["matrix_params"]["mass"]
+    S, c_host = mgm.even_odd_schur(A, L, L)
+    assert abs(c - c_host) < 1e-14
+    apply_S, even_rows = mgm.even_odd_schur_device(pm.dev, L, L, c)
+    n0 = A.shape[0]
+    rs = np.random.RandomState(4)
+    xe = rs.standard_normal((n0 // 2, 2)) + 1j * rs.standard_normal((n0 // 2, 2))
+    X = torch.zeros((n0, 2), dtype=torch.complex128, device=pm.dev.device)
+    X[even_rows] = torch.from_numpy(xe).to(X.device)
+    Y = apply_S(X).cpu().numpy()
+    ie = even_rows.cpu().numpy()
+    assert np.abs(Y[ie] - S @ xe).max() < 1e-12
+    assert np.abs(np.delete(Y, ie, axis=0)).max() == 0.0
+    de = 16
+    om_d = mgm.harmonic_ritz_inv_roots_device(apply_S, n0, de, pm.dev.device, support=even_rows)
+    om_h = mgm.harmonic_ritz_inv_roots(S, de)
+    z = np.linspace(0.05, 7.5, 200)
+    res = lambda om: np.prod(1.0 - np.outer(z, om), axis=1)          # the GMRES residual polynomial prod (1 - omega_i z)
+    assert np.abs(res(om_d) - res(om_h)).max() < 1e-6
+    nu, p0 = mgm.smoother_product_form(om_d)
+    e_d = mgm.smoother_storage_error_op(apply_S, n0, even_rows, om_d, nu, p0, pm.dev.device)
+    e_h = mgm.smoother_storage_error(S, om_h, *mgm.smoother_product_form(om_h), 'bf16')
+    assert e_d < 0.15 and e_h < 0.15 and abs(e_d - e_h) < 0.5 * max(e_d, e_h) + 1e-3
+    # and the polynomial the set-up installed is this one
+    assert pm.eo_poly is not None and len(pm.eo_poly[0]) == de - 1
+    assert np.abs(np.sort_complex(pm.eo_poly[0]) - np.sort_complex(nu)).max() < 1e-9 * np.abs(nu).max()
