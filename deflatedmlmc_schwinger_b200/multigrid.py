@@ -465,6 +465,14 @@ def ell_padded(M):
 
 # ------------------------------------------------------------------------------------------
 
+def _close_hierarchies(pm):
+    """free the device side of a (temporary) hierarchy and of the hierarchies that precondition it"""
+    for sub in [pm.precond_mg, pm.precond_mg1] + list(getattr(pm, "precond_mg_coarse", {}).values()) + [pm]:
+        if sub is not None and getattr(sub, "dev", None) is not None:
+            sub.dev.close()
+            sub.dev = None
+
+
 class MG:
     """Same public surface as the reference's MG (multigrid.py:56-557)."""
 
@@ -601,7 +609,7 @@ class MG:
                     # A fine eigenvector lies in range(P), so its restriction is an eigenvector of R A P for the same
                     # eigenvalue: the start block of the coarse eigensolve (which then only has to confirm it)
                     hint = ml.levels[i - 1].R @ self.test_vectors[i - 1][:, :dofip1]
-                eig_vecs = self.device_test_vectors(Al, dofip1, tolx, params, i, hint)
+                eig_vecs = self.device_test_vectors(Al, dofip1, tolx, params, i, hint, gdev=gdev)
                 eig_vecs = _same_on_all_ranks(eig_vecs, self.device)
             self.test_vectors.append(eig_vecs)
 
@@ -737,50 +745,57 @@ class MG:
             self.level0_format = "bsr%d" % self.level0_block
         return dims
 
-    def device_test_vectors(self, Al, nvec, tol, params, level, hint=None):
+    def device_test_vectors(self, Al, nvec, tol, params, level, hint=None, gdev=None):
         """multigrid.py:174 (`eigs(Al, k=nvec, which='LM', sigma=0.0, tol)`) on the device: block Arnoldi on A_l^{-1}
         (eigensolve.smallest_eigenpairs), every block step one batched FGMRES solve of p columns.  No hierarchy exists yet
         when the test vectors of a level are wanted, so the solver is the bootstrap one: FGMRES preconditioned by the
-        level's own smoother polynomial (option precond_smoother_only).  Deterministic: seeded start block, conjugate
-        pairs cut by nvec keep the member with Im > 0 (scipy's eigs starts from a random vector and may return either).
+        level's own smoother polynomial (option precond_smoother_only) -- or, on large levels, by a geometric hierarchy built
+        from rough vectors (two-stage bootstrap, below).  Deterministic: seeded start block, conjugate pairs cut by nvec keep
+        the member with Im > 0 (scipy's eigs starts from a random vector and may return either).  gdev: the hierarchy under
+        construction, whose level `level` already holds A_l (else a temporary one is made from the scipy matrix).
         Returns eig_vecs[n][nvec] (numpy); self.test_vector_info[level] holds eigenvalues, residuals and solve counts."""
         import torch
         from . import eigensolve
         n = Al.shape[0]
         dims = params.get('latt_dims', None)
-        dev = _lib.Hierarchy(2, self.device)
+        if dims is None:
+            Ls = int(round(np.sqrt(self.A.shape[0] / 2)))
+            dims = [Ls, Ls]
+        own = gdev is None
         fmt = None
-        if level == 0 and self.aggregation == "reference":
-            if dims is None:
-                Ls = int(round(np.sqrt(n / 2)))
-                dims = [Ls, Ls]
-            try:
-                links, diag = self._links_of(dims)
-                dev.set_stencil(0, links, diag)
+        if own:
+            dev, lvl = _lib.Hierarchy(2, self.device), 0
+            if level == 0 and self.aggregation == "reference":
+                try:
+                    links, diag = self._links_of(dims)
+                    dev.set_stencil(0, links, diag)
+                    fmt = "stencil"
+                except lattice.NotAStencil:
+                    fmt = None
+            if fmt is None:
+                bs = 1
+                if level > 0 and self._transfer_meta and self._transfer_meta[level - 1][0] != "indexed":
+                    bs = self._transfer_meta[level - 1][2]
+                col, vals = bsr_padded(Al, bs)
+                dev.set_bsr(0, n, bs, col, vals)
+        else:
+            dev, lvl = gdev, level
+            if level == 0 and getattr(self, "level0_format", None) == "stencil":
                 fmt = "stencil"
-            except lattice.NotAStencil:
-                fmt = None
-        if fmt is None:
-            bs = 1
-            if level > 0 and self._transfer_meta and self._transfer_meta[level - 1][0] != "indexed":
-                bs = self._transfer_meta[level - 1][2]
-            col, vals = bsr_padded(Al, bs)
-            dev.set_bsr(0, n, bs, col, vals)
         deg = int(params.get('bootstrap_degree', 80))
-        Ai = csr_matrix(Al)
         while True:
             try:
                 if n >= 4096:
-                    om = harmonic_ritz_inv_roots_device(lambda X: dev.spmm(0, X.contiguous()), n, deg, dev.device)
+                    om = harmonic_ritz_inv_roots_device(lambda X: dev.spmm(lvl, X.contiguous()), n, deg, dev.device)
                 else:
-                    om = harmonic_ritz_inv_roots(Ai, deg)
+                    om = harmonic_ritz_inv_roots(csr_matrix(Al), deg)
                 nu, p0 = smoother_product_form(om)
                 break
             except SmootherPolynomialError:
                 if deg <= 4:
                     raise
                 deg = max(4, (3 * deg) // 4)
-        dev.set_smoother(0, nu, p0, storage16=False)
+        dev.set_smoother(lvl, nu, p0, storage16=False)
         dev.set_inner_precision(_lib.C128)
         dev.set_option("precond_smoother_only", 1)
         p = int(params.get('eigensolver_block', max(4 * nvec, 16)))
@@ -790,19 +805,20 @@ class MG:
                            torch.randn(n, p, dtype=torch.float64, generator=gen, device=dev.device))
         if hint is not None:
             X0[:, :hint.shape[1]] = torch.from_numpy(np.ascontiguousarray(hint)).to(dev.device)
-        # Two-stage bootstrap (large stencil levels): FGMRES preconditioned by a polynomial alone needs ~200 iterations per
-        # solve there.  Stage 1: the start block is smoothed, X <- orth(p(A) X), a few times (approximate inverse iteration
-        # with no solves) and its Ritz vectors of smallest modulus serve as ROUGH test vectors of a geometric hierarchy;
-        # stage 2: the block Arnoldi run below is preconditioned by that hierarchy's V-cycle.  The eigenvectors it returns
-        # meet the same residual test either way.
+        # Two-stage bootstrap (large levels): FGMRES preconditioned by a polynomial alone needs ~200 iterations per solve
+        # there.  Level 0 -- stage 1: the start block is smoothed, X <- orth(p(A) X), a few times (approximate inverse
+        # iteration with no solves) and its Ritz vectors of smallest modulus serve as ROUGH test vectors of a geometric
+        # hierarchy; stage 2: the block Arnoldi run below is preconditioned by that hierarchy's V-cycle.  Coarse levels -- the
+        # restricted fine test vectors (`hint`: eigenvectors of R A P up to the accuracy of the fine ones) give the level's
+        # geometric hierarchy directly; it is kept for the level's solves of the sampling phase (_build_level1_preconditioner).
+        # The eigenvectors returned meet the same residual test either way.
         pm0 = None
-        two_stage = fmt == "stencil" and hint is None and self.geometric_precond and \
-            n >= int(params.get('two_stage_min_n', 100000)) and self._geometric_precond_possible(params)
-        if two_stage:
+        big = n >= int(params.get('two_stage_min_n', 100000)) and self.aggregation == "reference" and self.geometric_precond
+        if big and level == 0 and fmt == "stencil" and hint is None and self._geometric_precond_possible(params):
             X = X0
             for _ in range(int(params.get('two_stage_smoothing_passes', 4))):
-                X, _ = torch.linalg.qr(dev.smooth(0, X.contiguous()))
-            Hs = (X.conj().T @ dev.spmm(0, X.contiguous())).cpu().numpy()
+                X, _ = torch.linalg.qr(dev.smooth(lvl, X.contiguous()))
+            Hs = (X.conj().T @ dev.spmm(lvl, X.contiguous())).cpu().numpy()
             th, S = np.linalg.eig(Hs)
             keep = np.argsort(np.abs(th), kind='stable')
             X0 = X @ torch.from_numpy(np.ascontiguousarray(S[:, keep])).to(X.device)
@@ -811,23 +827,27 @@ class MG:
             p2 = dict(params)
             p2['two_stage_min_n'] = 1 << 62
             pm0 = self._make_geometric_hierarchy(p2, rough)
-            if pm0 is not None:
-                dev.set_option("precond_smoother_only", 0)
-                dev.set_inner_precision(_lib.C64 if self.inner_precision == "c64" else _lib.C128)
-                dev.set_preconditioner(0, pm0.dev, 0)
+        elif big and level >= 1 and hint is not None and hint.shape[1] >= nvec and \
+                getattr(self, "level0_format", None) == "stencil" and level <= int(params.get('geometric_coarse_levels', 2)):
+            LX, LT = (dims[1] if len(dims) > 1 else dims[0]), dims[0]
+            pm0 = self._coarse_geometric_hierarchy(level, Al, np.ascontiguousarray(hint[:, :nvec]), params, LX, LT)
+        if pm0 is not None:
+            dev.set_option("precond_smoother_only", 0)
+            dev.set_inner_precision(_lib.C64 if self.inner_precision == "c64" else _lib.C128)
+            dev.set_preconditioner(lvl, pm0.dev, 0)
         maxit = n if n < 4000 else 4000
         restart = min(self.restart, maxit)
         solve_tol = min(1e-4, max(1e-12, 1e-2 * tol))      # the Arnoldi relation needs the solves two digits below the target
         stats = {"solves": 0, "iters": 0}
 
         def apply_Ainv(V):
-            X, it, rr = dev.fgmres(0, V.contiguous(), solve_tol, restart=restart, maxiter=maxit)
+            X, it, rr = dev.fgmres(lvl, V.contiguous(), solve_tol, restart=restart, maxiter=maxit)
             stats["solves"] += 1
             stats["iters"] += int(it.max())
             return X
 
         def apply_A(V):
-            return dev.spmm(0, V.contiguous())
+            return dev.spmm(lvl, V.contiguous())
         theta, X, res, info = eigensolve.smallest_eigenpairs(apply_A, apply_Ainv, X0, nvec, tol=max(tol, 1e-11),
                                                              max_blocks=int(params.get('eigensolver_blocks', 16)),
                                                              min_blocks=3 if hint is not None else 1)
@@ -839,12 +859,16 @@ class MG:
         self.test_vector_info[level] = info
         out = X.cpu().numpy()
         dev.release_workspace()
+        dev.set_option("precond_smoother_only", 0)
         if pm0 is not None:
-            dev.set_preconditioner(0, None)
-            for sub in [pm0.precond_mg, pm0.precond_mg1] + list(getattr(pm0, "precond_mg_coarse", {}).values()) + [pm0]:
-                if sub is not None and sub.dev is not None:
-                    sub.dev.close()
-        dev.close()
+            dev.set_preconditioner(lvl, None)
+            if level >= 1:
+                self._early_coarse_pm = getattr(self, "_early_coarse_pm", {})
+                self._early_coarse_pm[level] = pm0           # reused by _build_level1_preconditioner
+            else:
+                _close_hierarchies(pm0)
+        if own:
+            dev.close()
         return out
 
     def _upload(self, params, use_permuted):
@@ -1052,58 +1076,85 @@ class MG:
         have merged up to level l (a_1 = aggr_size of level 0, a_{l+1} = a_l times the strips per level-l aggregate).
         Geometric blocks: 2 neighbouring groups in x, both halves, split by the spin s; then 2 x 2.  CPU experiment at 128^2
         (exact two-grid method on A_1): 11 outer iterations at degree 32 against 33 (18 at degree 80) with the estimator's own
-        level-2 aggregates.  Level 1 -> self.precond_mg1, deeper levels -> self.precond_mg_coarse[l]."""
+        level-2 aggregates.  Level 1 -> self.precond_mg1, deeper levels -> self.precond_mg_coarse[l].  A hierarchy that the
+        set-up already built for the level's eigensolve (device_test_vectors, from the restricted fine test vectors) is used
+        as it is."""
         lv = self.ml.levels
-        sa = self._setup_args
         self.precond_mg_coarse = {}
-        if len(lv) < 3 or self._transfer_meta[0][0] == "indexed" or getattr(self, "level1_unused", False) and len(lv) < 4:
-            return
-        aggr0, dofi0, _, _ = self._transfer_meta[0]
-        V = LX * LT
-        if dofi0 != 2 or LX % 2:
-            return
-        a_sites = aggr0                         # rows of one spin component per strip (dofi = 2: rows = sites of one spin)
-        max_level = int(params.get('geometric_coarse_levels', 2))
-        for l in range(1, len(lv) - 1):
-            nv_l = self._transfer_meta[l - 1][2]
-            if l > 1:
-                aggr_prev = self._transfer_meta[l - 1][0]
-                if self._transfer_meta[l - 1][0] == "indexed" or aggr_prev % (2 * self._transfer_meta[l - 2][2]):
+        early = getattr(self, "_early_coarse_pm", {})
+        self._early_coarse_pm = {}
+        try:
+            if len(lv) < 3 or self._transfer_meta[0][0] == "indexed" or getattr(self, "level1_unused", False) and len(lv) < 4:
+                return
+            max_level = int(params.get('geometric_coarse_levels', 2))
+            for l in range(1, len(lv) - 1):
+                if l in self.dense_levels or l > max_level:
                     return
-                a_sites = a_sites * (aggr_prev // (2 * self._transfer_meta[l - 2][2]))
-            if l in self.dense_levels or l > max_level:
-                return
-            if l == 1 and getattr(self, "level1_unused", False):
-                continue
-            n_l = lv[l].A.shape[0]
-            if LT % a_sites or n_l != (2 * V // a_sites) * 2 * nv_l or (LT // a_sites) < 1:
-                return
-            cblk, (gx, gt) = geometric_blocks_level1(LX, LT, a_sites, nv_l, 2)
-            nq = gt
-            nvs = [int(d // 2) for d in sa['dof'][l + 1:]] or [nv_l]
-            levels = 2
-            while True:
-                nvl = nvs[min(levels - 2, len(nvs) - 1)]
-                if 2 * gx * gt * nvl <= 1024 or gx % 2 or gt % 2 or gx < 4 or gt < 4:
-                    break
-                gx, gt = gx // 2, gt // 2
-                levels += 1
-            dof = [2 * nv_l] + [2 * nvs[min(jj, len(nvs) - 1)] for jj in range(levels - 1)]
-            degs = [self.precond_degree] + [self.precond_coarse_degree] * (levels - 1)
-            pm = MG(lv[l].A, smoother_degree=degs, restart=self.restart, inner_precision=self.inner_precision,
-                    device=self.device, dense_coarse_threshold=self.dense_coarse_threshold, pre_smooth=self.pre_smooth,
-                    aggregation="geometric", precond_blocks=(1, 1), level0_block=nv_l)
-            p2 = dict(params)
-            p2['use_permuted'] = False
-            p2['latt_dims'] = [LT, LX]
-            p2['geometric_first'] = {'cblk': cblk, 'coarse_dims': (LX // 2, nq)}
-            pm.setup(dof=dof, aggrs=[4] * (levels - 1), max_levels=levels, acc_eigvs=sa['acc_eigvs'], params=p2,
-                     test_vectors=[self.test_vectors[l]])
-            if l == 1:
-                self.precond_mg1 = pm
-            else:
-                self.precond_mg_coarse[l] = pm
-            self.dev.set_preconditioner(l, pm.dev, 0)
+                if l == 1 and getattr(self, "level1_unused", False):
+                    continue
+                pm = early.pop(l, None)
+                if pm is None:
+                    pm = self._coarse_geometric_hierarchy(l, lv[l].A, self.test_vectors[l], params, LX, LT)
+                if pm is None:
+                    return
+                if l == 1:
+                    self.precond_mg1 = pm
+                else:
+                    self.precond_mg_coarse[l] = pm
+                self.dev.set_preconditioner(l, pm.dev, 0)
+        finally:
+            for pm in early.values():          # built for an eigensolve, not needed by the sampling phase
+                _close_hierarchies(pm)
+
+    def _strip_sites(self, l):
+        """a_l of _build_level1_preconditioner: t-sites per strip group of the rows of level l (None: other structure)"""
+        if self._transfer_meta[0][0] == "indexed":
+            return None
+        aggr0, dofi0, _, _ = self._transfer_meta[0]
+        if dofi0 != 2:
+            return None
+        a = aggr0                               # rows of one spin component per strip (dofi = 2: rows = sites of one spin)
+        for m in range(2, l + 1):
+            meta = self._transfer_meta[m - 1]
+            if meta[0] == "indexed" or meta[0] % (2 * self._transfer_meta[m - 2][2]):
+                return None
+            a = a * (meta[0] // (2 * self._transfer_meta[m - 2][2]))
+        return a
+
+    def _coarse_geometric_hierarchy(self, l, A_l, tv_l, params, LX, LT):
+        """the geometric hierarchy of the estimator's level l >= 1 (operator A_l, its test vectors tv_l); None if the level's
+        rows do not have the strip structure"""
+        sa = self._setup_args
+        a_sites = self._strip_sites(l)
+        if a_sites is None or LX % 2:
+            return None
+        nv_l = self._transfer_meta[l - 1][2]
+        V = LX * LT
+        n_l = A_l.shape[0]
+        if LT % a_sites or n_l != (2 * V // a_sites) * 2 * nv_l or (LT // a_sites) < 1:
+            return None
+        cblk, (gx, gt) = geometric_blocks_level1(LX, LT, a_sites, nv_l, 2)
+        nq = gt
+        nvs = [int(d // 2) for d in sa['dof'][l + 1:]] or [nv_l]
+        levels = 2
+        while True:
+            nvl = nvs[min(levels - 2, len(nvs) - 1)]
+            if 2 * gx * gt * nvl <= 1024 or gx % 2 or gt % 2 or gx < 4 or gt < 4:
+                break
+            gx, gt = gx // 2, gt // 2
+            levels += 1
+        dof = [2 * nv_l] + [2 * nvs[min(jj, len(nvs) - 1)] for jj in range(levels - 1)]
+        degs = [self.precond_degree] + [self.precond_coarse_degree] * (levels - 1)
+        pm = MG(A_l, smoother_degree=degs, restart=self.restart, inner_precision=self.inner_precision,
+                device=self.device, dense_coarse_threshold=self.dense_coarse_threshold, pre_smooth=self.pre_smooth,
+                aggregation="geometric", precond_blocks=(1, 1), level0_block=nv_l)
+        p2 = dict(params)
+        p2['use_permuted'] = False
+        p2['latt_dims'] = [LT, LX]
+        p2['geometric_first'] = {'cblk': cblk, 'coarse_dims': (LX // 2, nq)}
+        pm.setup(dof=dof, aggrs=[4] * (levels - 1), max_levels=levels, acc_eigvs=sa['acc_eigvs'], params=p2,
+                 test_vectors=[tv_l])
+        return pm
 
     def _device_inverse(self, level, tol, batch=1024):
         """A_level^{-1} as a torch complex128 CUDA tensor [n, n], solved in column batches on the device"""
