@@ -148,9 +148,18 @@ struct dmlmc_hier {
 
 namespace {
 
+// Device memory of the operators comes from the device's stream-ordered pool (cudaMallocAsync on the handle's stream; the pool
+// keeps what is freed: dmlmc_hier_create sets its release threshold): set-up builds and discards whole hierarchies (the rough
+// one of the two-stage eigensolve), and cudaFree / cudaMalloc of hundreds of buffers cost seconds there (1.5 s per discarded
+// hierarchy at 1024^2, profiles/r2_run27_*).
+template <typename T> cudaError_t dev_alloc(dmlmc_hier* h, T** p, size_t bytes) {
+  return cudaMallocAsync(reinterpret_cast<void**>(p), std::max<size_t>(bytes, 16), h->stream);
+}
+inline void dev_free(dmlmc_hier* h, void* p) { if (p) cudaFreeAsync(p, h->stream); }
+
 template <typename T> int upload(dmlmc_hier* h, const T* host, size_t count, T** out) {
   T* p = nullptr;
-  CU(cudaMalloc(&p, std::max<size_t>(count, 1) * sizeof(T)));
+  CU(dev_alloc(h, &p, std::max<size_t>(count, 1) * sizeof(T)));
   h->owned.push_back(p);
   if (count) CU(cudaMemcpyAsync(p, host, count * sizeof(T), cudaMemcpyHostToDevice, h->stream));
   CU(cudaStreamSynchronize(h->stream));
@@ -435,7 +444,7 @@ int build_umma_operand(dmlmc_hier* h, int level, const Cx<double>* minv_dev) {
   const size_t n = L.n;
   if (n % 8 != 0) return 0;                       // TMA needs 16-byte row strides; such tiny levels use the SIMT kernel
   __nv_bfloat16* mt = nullptr;
-  CU(cudaMalloc(&mt, 4 * n * n * sizeof(__nv_bfloat16)));
+  CU(dev_alloc(h, &mt, 4 * n * n * sizeof(__nv_bfloat16)));
   h->owned.push_back(mt);
   umma_expand_matrix_kernel<<<nblocks(n * n, 256), 256, 0, h->stream>>>(minv_dev, (int)n, mt); LAUNCH_CHECK(h);
   CU(cudaStreamSynchronize(h->stream));
@@ -449,7 +458,7 @@ int build_umma_split_operand(dmlmc_hier* h, int level, const Cx<double>* minv_de
   const size_t n = L.n;
   if (n % 8 != 0) return 0;
   __nv_bfloat16* mt = nullptr;
-  CU(cudaMalloc(&mt, 12 * n * n * sizeof(__nv_bfloat16)));
+  CU(dev_alloc(h, &mt, 12 * n * n * sizeof(__nv_bfloat16)));
   h->owned.push_back(mt);
   umma_expand_matrix_split_kernel<<<nblocks(n * n, 256), 256, 0, h->stream>>>(minv_dev, (int)n, mt); LAUNCH_CHECK(h);
   CU(cudaStreamSynchronize(h->stream));
@@ -1448,6 +1457,17 @@ int dmlmc_hier_create(int device, void* cuda_stream, int n_levels, dmlmc_hier** 
   dmlmc_hier* h = new dmlmc_hier();
   h->device = device; h->stream = (cudaStream_t)cuda_stream; h->n_levels = n_levels;
   { int sms = 0; if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device) == cudaSuccess && sms > 0) h->n_sms = sms; }
+  {
+    // the stream-ordered pool keeps up to 16 GB of freed operator memory for the next hierarchy instead of returning it to
+    // the driver at every synchronisation (see dev_alloc)
+    cudaMemPool_t pool = nullptr;
+    if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess && pool != nullptr) {
+      uint64_t cur = 0, want = 16ull << 30;
+      if (cudaMemPoolGetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &cur) == cudaSuccess && cur < want)
+        cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &want);
+    }
+    cudaGetLastError();
+  }
   cudaError_t e2 = cudaMallocHost(&h->h_nactive, sizeof(int));
   if (e2 != cudaSuccess) { delete h; return fail((int)e2, "cudaMallocHost failed"); }
   int lo = 0, hi = 0;
@@ -1468,13 +1488,14 @@ int dmlmc_hier_destroy(dmlmc_hier* h) {
   cudaSetDevice(h->device);
   cudaStreamSynchronize(h->stream);
   invalidate_graphs(h);
-  for (void* p : h->owned) cudaFree(p);
+  for (void* p : h->owned) dev_free(h, p);
   if (h->h_nactive) cudaFreeHost(h->h_nactive);
   if (h->rng_stream) { cudaStreamSynchronize(h->rng_stream); cudaStreamDestroy(h->rng_stream); }
   if (h->rng_stream_lo) { cudaStreamSynchronize(h->rng_stream_lo); cudaStreamDestroy(h->rng_stream_lo); }
   if (h->rng_order) cudaEventDestroy(h->rng_order);
-  if (h->mt_tab) cudaFree(h->mt_tab);
-  if (h->mt_state_out) cudaFree(h->mt_state_out);
+  dev_free(h, h->mt_tab);
+  dev_free(h, h->mt_state_out);
+  cudaStreamSynchronize(h->stream);
   if (h->rng_done) cudaEventDestroy(h->rng_done);
   if (h->cap_stream) cudaStreamDestroy(h->cap_stream);
   delete h;
@@ -1661,7 +1682,7 @@ int dmlmc_galerkin(dmlmc_hier* h, int level, int cap, int32_t* col_dev, void* va
   T.m = L.tr_rows ? L.tr_m : L.aggr / 2;
   const int nbc = L.n_c / L.nvec;
   int* maxw = nullptr;
-  CU(cudaMalloc(&maxw, sizeof(int)));
+  CU(dev_alloc(h, &maxw, sizeof(int)));
   CU(cudaMemsetAsync(maxw, 0, sizeof(int), h->stream));
   CU(cudaMemsetAsync(vals_dev, 0, (size_t)nbc * cap * L.nvec * L.nvec * sizeof(Cx<double>), h->stream));
   galerkin_kernel<<<nbc, 256, cap * sizeof(int), h->stream>>>(A, T, cap, col_dev, (Cx<double>*)vals_dev, maxw);
@@ -1669,7 +1690,7 @@ int dmlmc_galerkin(dmlmc_hier* h, int level, int cap, int32_t* col_dev, void* va
   cudaError_t e = cudaGetLastError();
   if (e == cudaSuccess) e = cudaMemcpyAsync(slots_host, maxw, sizeof(int), cudaMemcpyDeviceToHost, h->stream);
   if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
-  cudaFree(maxw);
+  dev_free(h, maxw);
   if (e != cudaSuccess) return fail((int)e, std::string("galerkin: ") + cudaGetErrorString(e));
   return 0;
 }
@@ -1684,10 +1705,10 @@ int dmlmc_set_bsr_device(dmlmc_hier* h, int level, int n, int bs, int bpr, const
   L.kind = 1; L.n = n; L.bs = bs; L.bpr = bpr; L.nb = n / bs;
   const size_t nc = (size_t)L.nb * bpr, cnt = nc * bs * bs;
   int* col = nullptr; Cx<double>* vd = nullptr; Cx<float>* vf = nullptr; float4* v4 = nullptr;
-  CU(cudaMalloc(&col, nc * sizeof(int))); h->owned.push_back(col);
-  CU(cudaMalloc(&vd, cnt * sizeof(Cx<double>))); h->owned.push_back(vd);
-  CU(cudaMalloc(&vf, cnt * sizeof(Cx<float>))); h->owned.push_back(vf);
-  CU(cudaMalloc(&v4, cnt * sizeof(float4))); h->owned.push_back(v4);
+  CU(dev_alloc(h, &col, nc * sizeof(int))); h->owned.push_back(col);
+  CU(dev_alloc(h, &vd, cnt * sizeof(Cx<double>))); h->owned.push_back(vd);
+  CU(dev_alloc(h, &vf, cnt * sizeof(Cx<float>))); h->owned.push_back(vf);
+  CU(dev_alloc(h, &v4, cnt * sizeof(float4))); h->owned.push_back(v4);
   CU(cudaMemcpyAsync(col, colidx_dev, nc * sizeof(int), cudaMemcpyDeviceToDevice, h->stream));
   CU(cudaMemcpyAsync(vd, vals_dev, cnt * sizeof(Cx<double>), cudaMemcpyDeviceToDevice, h->stream));
   dense_formats_kernel<<<nblocks(cnt, 256), 256, 0, h->stream>>>(vd, cnt, vf, v4); LAUNCH_CHECK(h);
@@ -1701,7 +1722,7 @@ int dmlmc_dense_inverse(dmlmc_hier* h, int n, void* m_dev) {
   CHECK(m_dev && n >= 1 && n <= GJ_MAX_N, "dense_inverse: n must be in [1, 4096]");
   char* aux = nullptr;                                                  // piv[n], info, rowk[n], colk[n]
   const size_t ints = ((size_t)(n + 1) * sizeof(int) + 15) & ~(size_t)15;
-  CU(cudaMalloc(&aux, ints + 2 * (size_t)n * sizeof(double2)));
+  CU(dev_alloc(h, &aux, ints + 2 * (size_t)n * sizeof(double2)));
   int* piv = reinterpret_cast<int*>(aux); int* info_d = piv + n;
   double2* rowk = reinterpret_cast<double2*>(aux + ints); double2* colk = rowk + n;
   cudaError_t e = cudaMemsetAsync(info_d, 0, sizeof(int), h->stream);
@@ -1716,7 +1737,7 @@ int dmlmc_dense_inverse(dmlmc_hier* h, int n, void* m_dev) {
   int info = 0;
   if (e == cudaSuccess) e = cudaMemcpyAsync(&info, info_d, sizeof(int), cudaMemcpyDeviceToHost, h->stream);
   if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
-  cudaFree(aux);
+  dev_free(h, aux);
   if (e != cudaSuccess) return fail((int)e, std::string("dense_inverse: ") + cudaGetErrorString(e));
   CHECK(info == 0, "dense_inverse: the matrix is singular (zero pivot)");
   return 0;
@@ -1731,9 +1752,9 @@ int dmlmc_set_dense_inverse_device_full(dmlmc_hier* h, int level, int n, const v
   L.n = n;
   const size_t cnt = (size_t)n * n;
   Cx<double>* md = nullptr; Cx<float>* mf = nullptr; float4* m4 = nullptr;
-  CU(cudaMalloc(&md, cnt * sizeof(Cx<double>))); h->owned.push_back(md);
-  CU(cudaMalloc(&mf, cnt * sizeof(Cx<float>))); h->owned.push_back(mf);
-  CU(cudaMalloc(&m4, cnt * sizeof(float4))); h->owned.push_back(m4);
+  CU(dev_alloc(h, &md, cnt * sizeof(Cx<double>))); h->owned.push_back(md);
+  CU(dev_alloc(h, &mf, cnt * sizeof(Cx<float>))); h->owned.push_back(mf);
+  CU(dev_alloc(h, &m4, cnt * sizeof(float4))); h->owned.push_back(m4);
   CU(cudaMemcpyAsync(md, minv_dev, cnt * sizeof(Cx<double>), cudaMemcpyDeviceToDevice, h->stream));
   dense_formats_kernel<<<nblocks(cnt, 256), 256, 0, h->stream>>>(md, cnt, mf, m4); LAUNCH_CHECK(h);
   L.minv_d = md; L.minv_f = mf; L.minv4 = m4;
@@ -1868,10 +1889,14 @@ int dmlmc_probe_expand(dmlmc_hier* h, const uint8_t* bits_dev, int n, int k, voi
 }
 int dmlmc_set_mt_jump_table(dmlmc_hier* h, const uint32_t* tab_host, int rows) {
   ENTER(h); CHECK(tab_host && rows >= 11 && rows <= 64, "set_mt_jump_table: bad arguments");
-  if (h->mt_tab) { CU(cudaFree(h->mt_tab)); h->mt_tab = nullptr; }
-  CU(cudaMalloc(&h->mt_tab, (size_t)rows * 624 * sizeof(uint32_t)));
+  if (h->mt_tab) {
+    CU(cudaStreamSynchronize(h->rng_stream)); CU(cudaStreamSynchronize(h->rng_stream_lo));      // a generator may still read it
+    dev_free(h, h->mt_tab); h->mt_tab = nullptr;
+  }
+  CU(dev_alloc(h, &h->mt_tab, (size_t)rows * 624 * sizeof(uint32_t)));
+  CU(cudaStreamSynchronize(h->stream));                 // (the copy below and the generator run on other streams)
   CU(cudaMemcpy(h->mt_tab, tab_host, (size_t)rows * 624 * sizeof(uint32_t), cudaMemcpyHostToDevice));
-  if (!h->mt_state_out) CU(cudaMalloc(&h->mt_state_out, 625 * sizeof(uint32_t)));
+  if (!h->mt_state_out) { CU(dev_alloc(h, &h->mt_state_out, 625 * sizeof(uint32_t))); CU(cudaStreamSynchronize(h->stream)); }
   h->mt_tab_rows = rows;
   return 0;
 }

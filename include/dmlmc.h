@@ -17,7 +17,7 @@
  *     `*_host` arguments are host memory.  Everything runs asynchronously on the stream
  *     given at creation; the only host synchronisations are the documented convergence
  *     polls inside dmlmc_fgmres / dmlmc_level_sample* and the *_host entry points.
- *   - the library allocates device memory only for the operators it is handed at setup
+ *   - the library allocates device memory (stream-ordered pool, cudaMallocAsync) only for the operators it is handed at setup
  *     (dmlmc_set_*); solver work space is supplied by the caller (dmlmc_set_workspace).
  *   - one hierarchy handle is single-threaded; different handles are independent.
  *   - there is NO CPU fallback: without a CUDA device every call that touches data fails.
