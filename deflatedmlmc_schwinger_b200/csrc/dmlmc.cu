@@ -34,6 +34,7 @@ static int fail(int code, const std::string& msg) { g_err = msg; return code; }
 namespace {
 
 constexpr int ROWS_PER_CHUNK = 256;
+constexpr int MIN_ROWS_PER_CHUNK = 32;     // smallest row chunk of the complex64 Gram-Schmidt kernels (option "gs_rows")
 constexpr int MAX_LEVELS = 12;
 
 template <typename T> struct LevelT {
@@ -125,6 +126,10 @@ struct dmlmc_hier {
   int mt_jump = 1;                                    // option: 0 = the sequential one-CTA generator
   int fuse_residual = 1;                              // option: true residual of the Schur system + its norms in one kernel per cycle
   int gs_x2 = 1;                                      // option: two-column (16-byte) Gram-Schmidt kernels for complex64 vectors
+  int gs_rows = 0;                                    // option: rows per chunk (= per thread block) of the complex64 Gram-Schmidt kernels;
+                                                      // 0 = the largest power of two <= 256 that gives >= 2 048 blocks (256 gave 512 blocks
+                                                      // of 80 registers for 444 resident slots at k = 512: two waves, the second 15 % full,
+                                                      // ncu r2_run29: 2.6 TB/s)
   int mt_prio = 0;                                    // option: 1 = the jump-ahead kernel on the high-priority stream as well
   int hop_tma = 0;                                    // option: the even-odd sweeps with the halo staged in shared memory by TMA bulk copies
                                                       // (OFF: measured 27.8 us per sweep against 18.0 us of the direct kernel, runs r2_9 / r2_10)
@@ -833,14 +838,24 @@ int vcycle(dmlmc_hier* h, int level0, const void* Bin, void* Xout, int k, const 
 }
 
 // ---- reductions (complex128 accumulation; the vectors complex128, or complex64 in the mixed-precision Schur solve) ---------
+// rows per chunk of the complex64 Gram-Schmidt kernels for n rows and k columns (see dmlmc_hier::gs_rows)
+int gs_rows_c64(const dmlmc_hier* h, int n, int k) {
+  if (h->gs_rows > 0) return h->gs_rows;
+  const long long colblocks = (k / 2 + DOT_TX - 1) / DOT_TX;
+  int rows = ROWS_PER_CHUNK;
+  while (rows > MIN_ROWS_PER_CHUNK && (long long)((n + rows - 1) / rows) * colblocks < 2048) rows >>= 1;
+  return rows;
+}
 template <typename VT = double, typename WT = double>
 int multi_dot(dmlmc_hier* h, const Cx<VT>* Vbase, size_t vstride, int nv, const Cx<WT>* W, int n, int k, Z* partial, Z* out, int accumulate) {
-  const int nchunks = (n + ROWS_PER_CHUNK - 1) / ROWS_PER_CHUNK;
+  int nchunks = (n + ROWS_PER_CHUNK - 1) / ROWS_PER_CHUNK;
   dim3 blk(DOT_TX, DOT_TY), grd((k + DOT_TX - 1) / DOT_TX, nchunks);
   if constexpr (std::is_same<VT, float>::value && std::is_same<WT, float>::value) {
     if ((k % 2) == 0 && (vstride % 2) == 0 && h->gs_x2) {
+      const int rows = gs_rows_c64(h, n, k);
+      nchunks = (n + rows - 1) / rows;
       dim3 g2((k / 2 + DOT_TX - 1) / DOT_TX, nchunks);
-      multi_dot_c64x2_kernel<<<g2, blk, 0, h->stream>>>(Vbase, vstride, nv, W, n, k, ROWS_PER_CHUNK, partial);
+      multi_dot_c64x2_kernel<<<g2, blk, 0, h->stream>>>(Vbase, vstride, nv, W, n, k, rows, partial);
       LAUNCH_CHECK(h);
       sum_partials_kernel<<<nblocks((size_t)nv * k, 32), dim3(32, 8), 0, h->stream>>>(partial, nchunks, nv * k, out, accumulate);
       LAUNCH_CHECK(h);
@@ -857,7 +872,15 @@ int multi_dot(dmlmc_hier* h, const Cx<VT>* Vbase, size_t vstride, int nv, const 
 int multi_dot32(dmlmc_hier* h, const Cx<float>* Vbase, size_t vstride, int nv, const Z* W, int n, int k, Z* partial, Z* out) {
   return multi_dot<float, double>(h, Vbase, vstride, nv, W, n, k, partial, out, 0);
 }
-size_t partial_count(int n, int nv, int k) { return (size_t)((n + ROWS_PER_CHUNK - 1) / ROWS_PER_CHUNK) * nv * k; }
+// complex numbers of the partial-sum buffer of a reduction over n (or, in the Schur-complement solve, n / 2) rows
+size_t partial_count(const dmlmc_hier* h, int n, int nv, int k) {
+  size_t chunks = (size_t)(n + ROWS_PER_CHUNK - 1) / ROWS_PER_CHUNK;
+  for (int rows_n : {n, (n + 1) / 2}) {
+    const int rows = std::min(ROWS_PER_CHUNK, gs_rows_c64(h, rows_n, k));
+    chunks = std::max(chunks, (size_t)(rows_n + rows - 1) / rows);
+  }
+  return chunks * nv * k;
+}
 
 template <typename VT = double>
 int multi_axpy(dmlmc_hier* h, const Cx<VT>* Vbase, size_t vstride, int nv, const Z* hc, Z* W, int n, int k, double sgn) {
@@ -870,12 +893,14 @@ int multi_axpy(dmlmc_hier* h, const Cx<VT>* Vbase, size_t vstride, int nv, const
 // W -= sum_i hc[i] V_i and nrm2[col] = ||W[:, col]||^2 (deterministic chunked reduction)
 template <typename VT = double>
 int multi_axpy_norm(dmlmc_hier* h, const Cx<VT>* Vbase, size_t vstride, int nv, const Z* hc, Cx<VT>* W, int n, int k, Z* partial, Z* nrm2) {
-  const int nchunks = (n + ROWS_PER_CHUNK - 1) / ROWS_PER_CHUNK;
+  int nchunks = (n + ROWS_PER_CHUNK - 1) / ROWS_PER_CHUNK;
   dim3 blk(DOT_TX, DOT_TY), grd((k + DOT_TX - 1) / DOT_TX, nchunks);
   if constexpr (std::is_same<VT, float>::value) {
     if ((k % 2) == 0 && (vstride % 2) == 0 && h->gs_x2) {
+      const int rows = gs_rows_c64(h, n, k);
+      nchunks = (n + rows - 1) / rows;
       dim3 g2((k / 2 + DOT_TX - 1) / DOT_TX, nchunks);
-      multi_axpy_norm_c64x2_kernel<<<g2, blk, 0, h->stream>>>(Vbase, vstride, nv, hc, W, n, k, ROWS_PER_CHUNK, partial);
+      multi_axpy_norm_c64x2_kernel<<<g2, blk, 0, h->stream>>>(Vbase, vstride, nv, hc, W, n, k, rows, partial);
       LAUNCH_CHECK(h);
       sum_partials_kernel<<<nblocks((size_t)k, 32), dim3(32, 8), 0, h->stream>>>(partial, nchunks, k, nrm2, 0);
       LAUNCH_CHECK(h);
@@ -1000,7 +1025,7 @@ int fgmres(dmlmc_hier* h, int level, const Z* B, Z* X, int k, double tol, int re
   RET(ws_get<Z>(h, nk * m, &Zb));
   RET(ws_get<Z>(h, nk, &W));
   RET(ws_get<Z>(h, nk, &Rb));
-  RET(ws_get<Z>(h, partial_count(n, m + 1, k), &partial));
+  RET(ws_get<Z>(h, partial_count(h, n, m + 1, k), &partial));
   RET(ws_get<Z>(h, (size_t)(m + 1) * k, &s.hsum));
   RET(ws_get<Z>(h, (size_t)k, &s.nrm2));
   RET(ws_get<Z>(h, (size_t)m * m * k, &s.Rm));
@@ -1164,7 +1189,7 @@ int fgmres_eo_t(dmlmc_hier* h, int level, const Z* B, Z* X, int k, double tol, i
   RET(ws_get<Z>(h, nkh, &Wo)); RET(ws_get<Z>(h, nkh, &Wd)); RET(ws_get<Z>(h, nkh, &Rb));
   RET(ws_get<Z>(h, nkh, &Be)); RET(ws_get<Z>(h, nkh, &Bo)); RET(ws_get<Z>(h, nkh, &Bhat));
   RET(ws_get<Z>(h, nkh, &Xe)); RET(ws_get<Z>(h, nkh, &Xo));
-  RET(ws_get<Z>(h, partial_count(n, m + 1, k), &partial));
+  RET(ws_get<Z>(h, partial_count(h, n, m + 1, k), &partial));
   RET(ws_get<Z>(h, (size_t)(m + 1) * k, &s.hsum));
   RET(ws_get<Z>(h, (size_t)k, &s.nrm2));
   RET(ws_get<Z>(h, (size_t)m * m * k, &s.Rm));
@@ -1199,7 +1224,7 @@ int fgmres_eo_t(dmlmc_hier* h, int level, const Z* B, Z* X, int k, double tol, i
   std::vector<int> cyc_len;
   int total_it = 0, nact = 0, mode = 3, cycles = 0;
   bool have_norm = false;                 // s.nrm2 already holds ||Rsrc||^2 per column (written by the fused residual kernel)
-  const size_t partial_cap = partial_count(n, m + 1, k);
+  const size_t partial_cap = partial_count(h, n, m + 1, k);
   while (true) {
     if (!have_norm) RET(multi_dot(h, Rsrc, 0, 1, Rsrc, nh, k, partial, s.nrm2, 0));
     have_norm = false;
@@ -1297,7 +1322,7 @@ int deflate(dmlmc_hier* h, int level, Z* X, int k) {
   const int n = L.n, d = L.defl_d;
   WsScope ws_scope(h); const size_t mark = ws_scope.mark;
   Z *partial, *C;
-  RET(ws_get<Z>(h, partial_count(n, d, k), &partial));
+  RET(ws_get<Z>(h, partial_count(h, n, d, k), &partial));
   RET(ws_get<Z>(h, (size_t)d * k, &C));
   const int nchunks = (n + ROWS_PER_CHUNK - 1) / ROWS_PER_CHUNK;
   const size_t nk = (size_t)n * k;
@@ -1347,7 +1372,7 @@ int level_sample(dmlmc_hier* h, int method, int lf, int lc, const Z* X0, int k, 
   RET(ws_get<Z>(h, nkf, &Xdef));
   RET(ws_get<Z>(h, nkf, &RHS));
   RET(ws_get<Z>(h, nkf, &Zs));
-  RET(ws_get<Z>(h, partial_count(nf, 1, k), &partial));
+  RET(ws_get<Z>(h, partial_count(h, nf, 1, k), &partial));
   RET(ws_get<Z>(h, (size_t)k, &e1));
   // x_def = x0 - V (V^H x0)            utils.py:224,266
   const Z* xd = X0;
@@ -1428,7 +1453,7 @@ size_t fgmres_bytes(dmlmc_hier* h, int level, int k, int m) {
   } else {
     b += align_up(nk * (m + 1) * z) + align_up(nk * m * z) + 2 * align_up(nk * z);
   }
-  b += align_up(partial_count((int)n, m + 1, k) * z);
+  b += align_up(partial_count(h, (int)n, m + 1, k) * z);
   b += align_up((size_t)m * m * k * z) + 6 * align_up((size_t)(m + 1) * k * z) + 16 * align_up((size_t)k * 16);
   size_t vb = vcycle_bytes(h, level, k, sizeof(Z));
   if (h->prec_hier[level]) vb = std::max(vb, vcycle_bytes(h->prec_hier[level], h->prec_level[level], k, sizeof(Z)) + (size_t)(1 << 16));
@@ -1871,7 +1896,7 @@ int dmlmc_precondition(dmlmc_hier* h, int level, const void* V, void* Zout, int 
 int dmlmc_dotc(dmlmc_hier* h, const void* X, const void* Y, int n, int k, void* out_dev) {
   ENTER(h); CHECK(X && Y && out_dev && n >= 1 && k >= 1, "dotc: bad arguments");
   WsScope ws_scope(h); const size_t mark = ws_scope.mark;
-  Z* partial; RET(ws_get<Z>(h, partial_count(n, 1, k), &partial));
+  Z* partial; RET(ws_get<Z>(h, partial_count(h, n, 1, k), &partial));
   int rc = multi_dot(h, (const Z*)X, 0, 1, (const Z*)Y, n, k, partial, (Z*)out_dev, 0);
   h->ws_off = mark;
   return rc;
@@ -1973,7 +1998,7 @@ size_t dmlmc_workspace_bytes(dmlmc_hier* h, int level, int k, int restart) {
   for (int l = level; l < h->n_levels - 1 && l <= level + 2; ++l)
     if (h->lv[l].n > 0 && h->lv[l].kind >= 0) b = std::max(b, fgmres_bytes(h, l, k, std::min(restart, std::max(1, h->lv[l].n))));
   const size_t nk = (size_t)h->lv[level].n * k * sizeof(Z);
-  b += 8 * align_up(nk) + align_up(partial_count(h->lv[level].n, 64, k) * sizeof(Z));
+  b += 8 * align_up(nk) + align_up(partial_count(h, h->lv[level].n, 64, k) * sizeof(Z));
   b += align_up((size_t)h->lv[level].n * k / 8 + 64);
   return b + (1 << 20);
 }
@@ -2035,6 +2060,11 @@ int dmlmc_set_option(dmlmc_hier* h, const char* name, double value) {
   if (std::strcmp(name, "mt_jump") == 0) { h->mt_jump = value != 0.0; return 0; }
   if (std::strcmp(name, "mt_prio") == 0) { h->mt_prio = value != 0.0; return 0; }
   if (std::strcmp(name, "gs_x2") == 0) { h->gs_x2 = value != 0.0; return 0; }
+  if (std::strcmp(name, "gs_rows") == 0) {
+    const int v = (int)value;
+    CHECK(v == 0 || (v >= MIN_ROWS_PER_CHUNK && v <= 1024 && v % 8 == 0), "set_option: gs_rows must be 0 (automatic) or a multiple of 8 in [32, 1024]");
+    h->gs_rows = v; return 0;
+  }
   if (std::strcmp(name, "fuse_residual") == 0) { h->fuse_residual = value != 0.0; return 0; }
   if (std::strcmp(name, "hop_tma") == 0) { h->hop_tma = value != 0.0; return 0; }
   if (std::strcmp(name, "precond_smoother_only") == 0) { h->smoother_only = value != 0.0; return 0; }

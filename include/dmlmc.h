@@ -249,7 +249,11 @@ int dmlmc_level_sample_host(dmlmc_hier* h, int method, int level_f, int level_c,
  *                  count the previous solve with the same (level, k, tol) needed, and done every 4th iteration at least
  *   "smoother_eo"  1 (default): use the even-odd post-smoother on a stencil level that has one (dmlmc_set_smoother_eo);
  *                  "eo_packs" 2 (default) | 1: column packs per thread of its kernel; "eo_by", "eo_bz": thread-block tile (2 x 2)
- *   "dot32"        0 (default; 1 measured harmful): Gram-Schmidt coefficients from complex64 copies of the basis */
+ *   "dot32"        0 (default; 1 measured harmful): Gram-Schmidt coefficients from complex64 copies of the basis
+ *   "gs_x2"        1 (default): two-column (16-byte) Gram-Schmidt kernels for complex64 Krylov vectors
+ *   "gs_rows"      rows per thread block of those kernels (fixed-order partial sums per chunk of rows); 0 (default) = the
+ *                  largest power of two <= 256 that gives at least 2 048 thread blocks
+ *   "fuse_residual" 1 (default): true residual of the Schur-complement system, its storage and its column norms in one kernel */
 int dmlmc_set_option(dmlmc_hier* h, const char* name, double value);
 
 /* columns that the solves of the last dmlmc_fgmres / dmlmc_level_sample[_host] call left above the tolerance when
