@@ -2,16 +2,20 @@
 (setup / solve / one_mg_step / diff_op / diff_op_Q / matvec), whose solve path runs on the
 GPU through libdmlmc_sm100.so (batched FGMRES + V-cycle, see csrc/dmlmc.cu).
 
-What stays on the host, once per hierarchy: the test-vector eigensolve (scipy eigs exactly as
-multigrid.py:174; SURVEY.md 8f "next"), the aggregation prolongator (closed-form index maps of
-multigrid.py:192-227, bit-exact; per-aggregate classical Gram-Schmidt of :232-259 done sparse,
-never through the dense n_l x n_{l+1} array of :200), R = P^H, the Galerkin products and the
-dense coarsest inverse (:342-344).  The results are uploaded once and every solve is on device.
+The set-up (multigrid.py:100-344 of the reference) runs on the device as well since round 2: the
+test-vector eigensolve of :174 (block Arnoldi on the batched solver, two-stage bootstrap on large
+lattices), the per-aggregate classical Gram-Schmidt of :232-259 (closed-form index maps of
+:192-227, bit-exact; never the dense n_l x n_{l+1} array of :200), the Galerkin products R A P of
+:276 straight into the padded block-sparse layout of the coarse-level kernels, the dense coarsest
+inverse of :342-344, the smoother polynomials.  The host keeps scipy / numpy copies of P, R, A_l
+and coarsest_inv under the reference's attribute names, assembled from the device's numbers;
+params['host_galerkin' | 'host_prolongator' | 'host_coarsest_inverse' | 'host_eigensolver' |
+'host_smoother_setup'] restore the host computations one by one.
 
 The smoother is NOT the reference's lgmres(maxiter=2) (multigrid.py:393-394): FGMRES is
 flexible and parity is on the converged solution, so the V-cycle uses a
 reduction-free fixed polynomial of A (Leja-ordered harmonic-Ritz roots of a degree-`smoother_degree`
-GMRES polynomial computed at setup), applied as fused operator+update Richardson steps.
+GMRES polynomial computed at setup), applied in product form, one fused operator+update kernel per factor.
 """
 import sys
 

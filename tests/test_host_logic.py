@@ -359,3 +359,27 @@ def test_mt19937_jump_polynomial_for_any_distance():
         assert np.array_equal(np.frombuffer(r2.bytes(4 * 600 - 4 * (pos - 1) + 4 * (pos - 1)), dtype=np.uint32)[:600 - (pos - 1)],
                               mj.temper(X[pos - 1:600]))
     assert np.array_equal(mj.poly_for_distance(0)[:2], np.array([1, 0], dtype=np.uint32))
+
+
+def test_padded_block_rows_round_trip():
+    """bsr_padded (scipy -> the device layout) and csr_from_padded_bsr (the device layout, as dmlmc_galerkin writes it, ->
+    scipy) are inverse to each other, rows with fewer blocks than the widest one included"""
+    import scipy.sparse as sp
+    from deflatedmlmc_schwinger_b200 import multigrid as mgm
+    rs = np.random.RandomState(0)
+    nb, bs = 12, 4
+    mask = rs.rand(nb, nb) < 0.3
+    mask[np.arange(nb), np.arange(nb)] = True
+    mask[3, :] = False
+    mask[3, 5] = True                           # one row with a single block
+    D = np.zeros((nb * bs, nb * bs), dtype=np.complex128)
+    for i, j in zip(*np.nonzero(mask)):
+        D[i * bs:(i + 1) * bs, j * bs:(j + 1) * bs] = rs.standard_normal((bs, bs)) + 1j * rs.standard_normal((bs, bs))
+    A = sp.csr_matrix(D)
+    col, vals = mgm.bsr_padded(A, bs)
+    assert col.shape == (nb, mask.sum(axis=1).max()) and (col[3] >= 0).sum() == 1
+    assert all(np.all(np.diff(r[r >= 0]) > 0) for r in col)
+    B = mgm.csr_from_padded_bsr(col, vals)
+    assert abs(B - A).max() == 0.0
+    col2, vals2 = mgm.bsr_padded(B, bs)
+    assert np.array_equal(col, col2) and np.array_equal(vals, vals2)
