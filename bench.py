@@ -660,10 +660,11 @@ def main():
                     "avg_launch_us": 1e6 * t_pair / 2, "alg_bytes_per_launch": pair_bytes / 2,
                     "timing": "CUDA events around %d consecutive launches through dmlmc_hop_eo (the V-cycle's own launch "
                               "configuration and coefficients)" % (2 * me * 5),
-                    "traffic": {512: 56.96e6, 256: 26.3e6}.get(k),
-                    "traffic_source": ("ncu --set full of this command at k = 512 (profiles/r2_run1_ncu_full_k512.md, 20 launches "
-                                       "each): dram__bytes_read.sum + dram__bytes_write.sum = 68.6 + 8.9 MB (sweep with In2) / 34.6 + "
-                                       "1.8 MB (sweep without), averaged over the two sweeps; k = 256: profiles/r1_run36_hop_eo_ncu.md; "
+                    "traffic": {512: 57.1e6, 256: 26.3e6}.get(k),
+                    "traffic_source": ("ncu --set full of this command at k = 512 (profiles/r2_run29_ncu_full_k512.md, 30 launches "
+                                       "each; the same figures in r2_run1 / r2_run8): dram__bytes_read.sum + dram__bytes_write.sum = "
+                                       "68.6 + 8.6 MB (sweep with In2) / 34.7 + 2.3 MB (sweep without), averaged over the two sweeps; "
+                                       "k = 256: profiles/r1_run36_hop_eo_ncu.md; "
                                        "no capture at other batch sizes (null).  ncu replays each launch cold: the inputs come from "
                                        "DRAM there, most of the output stays in L2"),
                     "limiter": "the five %.1f MB half-lattice vectors of a Schur-complement application %s the 126 MB L2 across the "
