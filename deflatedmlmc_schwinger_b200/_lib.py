@@ -263,7 +263,7 @@ class Hierarchy:
         self.sizes[level] = int(n)
 
     def dense_inverse(self, M):
-        """multigrid.py:342-344 on the device: the inverse of a dense complex128 matrix (numpy or torch, n <= 4096) -> torch [n, n]"""
+        """multigrid.py:342-344 on the device: the inverse of a dense complex128 matrix (numpy or torch, n <= 8192) -> torch [n, n]"""
         torch = self.torch
         A = M if torch.is_tensor(M) else torch.from_numpy(np.ascontiguousarray(M, dtype=np.complex128))
         A = A.to(self.device).clone().contiguous()

@@ -1744,7 +1744,7 @@ int dmlmc_set_bsr_device(dmlmc_hier* h, int level, int n, int bs, int bpr, const
 
 int dmlmc_dense_inverse(dmlmc_hier* h, int n, void* m_dev) {
   CHECK(h != nullptr, "NULL handle"); CU(cudaSetDevice(h->device));
-  CHECK(m_dev && n >= 1 && n <= GJ_MAX_N, "dense_inverse: n must be in [1, 4096]");
+  CHECK(m_dev && n >= 1 && n <= GJ_MAX_N, "dense_inverse: n must be in [1, 8192]");
   char* aux = nullptr;                                                  // piv[n], info, rowk[n], colk[n]
   const size_t ints = ((size_t)(n + 1) * sizeof(int) + 15) & ~(size_t)15;
   CU(dev_alloc(h, &aux, ints + 2 * (size_t)n * sizeof(double2)));

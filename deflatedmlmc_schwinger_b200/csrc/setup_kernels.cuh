@@ -130,7 +130,7 @@ galerkin_kernel(GalOp A, GalTr T, int cap, int* __restrict__ col_out, Cx<double>
 // to rowk / colk) and one wide kernel (rank-one update of all other rows); at the end every row undoes the row exchanges on its
 // own entries (column swaps, last exchange first).  *info = k + 1 when the k-th pivot is exactly zero (cleared by the caller).
 // Replaces np.linalg.inv (LAPACK getrf / getri, the same pivoting strategy) of multigrid.py:342-344.
-constexpr int GJ_MAX_N = 4096;
+constexpr int GJ_MAX_N = 8192;      // (8 192: 8 192 rank-one updates of a 1 GB matrix, ~3.5 s)
 __global__ void __launch_bounds__(1024)
 gj_pivot_kernel(Cx<double>* __restrict__ M, int n, int k, int* __restrict__ piv, int* __restrict__ info,
                 double2* __restrict__ rowk, double2* __restrict__ colk) {

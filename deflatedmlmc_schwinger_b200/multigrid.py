@@ -691,7 +691,7 @@ class MG:
             self._setup_dev = None
         self.ml = ml
         n_last = ml.levels[-1].A.shape[0]
-        if gdev is not None and n_last <= 2048 and not params.get('host_coarsest_inverse', False):
+        if gdev is not None and n_last <= 8192 and not params.get('host_coarsest_inverse', False):
             # multigrid.py:342-344 on the device (Gauss-Jordan with partial pivoting, dmlmc_dense_inverse)
             self.coarsest_inv = gdev.dense_inverse(np.asarray(ml.levels[-1].A.todense())).cpu().numpy()
         else:

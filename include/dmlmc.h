@@ -100,7 +100,7 @@ int dmlmc_galerkin(dmlmc_hier* h, int level, int cap, int32_t* col_dev, void* va
 /* dmlmc_set_bsr from DEVICE arrays (the output of dmlmc_galerkin, trimmed to bpr slots); the arrays are copied. */
 int dmlmc_set_bsr_device(dmlmc_hier* h, int level, int n, int bs, int bpr, const int32_t* colidx_dev, const void* vals_dev);
 /* Set-up, multigrid.py:342-344 (np.linalg.inv of the coarsest operator): in-place inverse of the dense complex128 device
- * matrix m_dev[n][n], n <= 4096, by Gauss-Jordan elimination with partial pivoting (two kernels per pivot, matrix in L2). */
+ * matrix m_dev[n][n], n <= 8192, by Gauss-Jordan elimination with partial pivoting (two kernels per pivot, matrix in L2). */
 int dmlmc_dense_inverse(dmlmc_hier* h, int n, void* m_dev);
 /* The same hand-over for an inverse kept in ALL precisions (what dmlmc_set_dense_inverse makes from a host array: the
  * complex128 and complex64 copies, the splatted FP32 operand and the tensor-core operands), from a complex128 device

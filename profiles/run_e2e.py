@@ -24,6 +24,7 @@ ap.add_argument("--fixed", action="store_true", help="sequential_stop=False: sam
 ap.add_argument("--exact", action="store_true", help="also compute the EXACT level values with unit vectors (stoch_trace.exact_trace)")
 ap.add_argument("--set", default="schwinger128", help="gateway.set_params name: schwinger128 (G202/G102) or synthetic<L> (BASELINE configs[4])")
 ap.add_argument("--coarse-geo", type=int, default=-1, help="params['geometric_coarse_levels']: deepest estimator level that gets a geometric preconditioner hierarchy (default: the package's, 2)")
+ap.add_argument("--trace-tol", type=float, default=0.0, help="params['trace_tol'] (default: the parameter set's 1e-2)")
 ap.add_argument("--deflated", action="store_true",
                 help="the valid deflated-MLMC variant of SURVEY.md 8d cfg-2: not permuted, mlmc_deflat_vctrs=[16,0,16]")
 args = ap.parse_args()
@@ -48,6 +49,8 @@ def run(method):
     p["verbose"] = False
     p["probe_batch"] = args.batch
     p["sequential_stop"] = not args.fixed
+    if args.trace_tol > 0:
+        p["trace_tol"] = args.trace_tol
     if args.deflated:
         p["use_permuted"] = False
         p["mlmc_deflat_vctrs"] = [16, 0, 16]
@@ -72,7 +75,7 @@ def run(method):
            "trace": [float(np.real(res["trace"])), float(np.imag(res["trace"]))],
            "exact": [exact.real, exact.imag],
            "abs_err": float(abs(res["trace"] - exact)),
-           "target_err": float(abs(1e-2 * res["rough_trace"])),
+           "target_err": float(abs(p["trace_tol"] * res["rough_trace"])),
            "rough_trace": [float(np.real(res["rough_trace"])), float(np.imag(res["rough_trace"]))],
            "wall_s": wall, "sampling_s": float(res["sampling_seconds"]), "probes_evaluated": res["probes_evaluated"],
            "sequential_stop": not args.fixed, "probe_batch_per_gpu": args.batch}
