@@ -383,3 +383,21 @@ def test_padded_block_rows_round_trip():
     assert abs(B - A).max() == 0.0
     col2, vals2 = mgm.bsr_padded(B, bs)
     assert np.array_equal(col, col2) and np.array_equal(vals, vals2)
+
+
+def test_strip_sites_of_the_coarse_levels():
+    """a_l of MG._build_level1_preconditioner (t-sites per strip group of the rows of level l): a_1 = the level-0 aggregate,
+    a_{l+1} = a_l times the strips a level-l aggregate merges; other aggregate structures give None"""
+    import scipy.sparse as sp
+    from deflatedmlmc_schwinger_b200 import multigrid as mgm
+    mg = mgm.MG(sp.identity(8, format="csr", dtype=np.complex128))
+    mg._transfer_meta = [(32, 2, 4, None), (32, 8, 4, None), (32, 8, 4, None)]       # (aggr_size, dofi, nvec, values)
+    assert mg._strip_sites(1) == 32
+    assert mg._strip_sites(2) == 32 * (32 // 8)
+    assert mg._strip_sites(3) == 32 * (32 // 8) * (32 // 8)
+    mg._transfer_meta = [(32, 4, 4, None), (32, 8, 4, None)]                         # dofi != 2 on level 0
+    assert mg._strip_sites(1) is None
+    mg._transfer_meta = [("indexed", None, 4, None)]
+    assert mg._strip_sites(1) is None
+    mg._transfer_meta = [(32, 2, 4, None), (36, 8, 4, None)]                         # aggregate not a whole number of strips
+    assert mg._strip_sites(1) == 32 and mg._strip_sites(2) is None
